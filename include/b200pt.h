@@ -1,0 +1,217 @@
+/* b200pt.h -- C ABI of the B200-native wavefront path-tracing engine.
+ *
+ * This is the boundary a pbrt-v4 maintainer binds to replace the WavefrontPathIntegrator hot path
+ * (reference: src/pbrt/wavefront/integrator.h:32-54 WavefrontAggregate, integrator.cpp:80-287 ctor,
+ * :290-493 Render(); src/pbrt/gpu/optix/aggregate.h:32-37 OptiXAggregate ctor).  Plain C structs and
+ * pointers only: caller-owned host arrays are copied at bpt_scene_* time; the engine owns all device memory.
+ * One engine per GPU; an engine is not thread-safe.  Every function returns BPT_OK (0) or a negative
+ * error code; bpt_last_error() gives the message (the reference aborts via LOG_FATAL instead,
+ * gpu/util.h:35-49).  There is no CPU fallback: every entry point that computes fails with
+ * BPT_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Tag values (camera/film/filter/sampler/material/light/light-sampler types) are the positions in the
+ * reference's TaggedPointer type lists: base/camera.h:34, base/film.h:25, base/filter.h:25,
+ * base/sampler.h:40-42, base/material.h:36-39, base/light.h:40-43, base/lightsampler.h:29.
+ */
+#ifndef B200PT_H
+#define B200PT_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPT_OK 0
+#define BPT_ERR_INVALID (-1)
+#define BPT_ERR_NO_DEVICE (-2)
+#define BPT_ERR_CUDA (-3)
+#define BPT_ERR_UNSUPPORTED (-4)
+#define BPT_ERR_IO (-5)
+
+typedef struct bpt_engine bpt_engine;
+
+/* ---- tags ---- */
+enum { BPT_CAMERA_PERSPECTIVE = 0, BPT_CAMERA_ORTHOGRAPHIC = 1, BPT_CAMERA_SPHERICAL = 2, BPT_CAMERA_REALISTIC = 3 };
+enum { BPT_FILM_RGB = 0, BPT_FILM_GBUFFER = 1, BPT_FILM_SPECTRAL = 2 };
+enum { BPT_FILTER_BOX = 0, BPT_FILTER_GAUSSIAN = 1, BPT_FILTER_MITCHELL = 2, BPT_FILTER_SINC = 3, BPT_FILTER_TRIANGLE = 4 };
+enum { BPT_SAMPLER_PMJ02BN = 0, BPT_SAMPLER_INDEPENDENT = 1, BPT_SAMPLER_STRATIFIED = 2, BPT_SAMPLER_HALTON = 3,
+       BPT_SAMPLER_PADDED_SOBOL = 4, BPT_SAMPLER_SOBOL = 5, BPT_SAMPLER_ZSOBOL = 6 };
+enum { BPT_RANDOMIZE_NONE = 0, BPT_RANDOMIZE_PERMUTE_DIGITS = 1, BPT_RANDOMIZE_FAST_OWEN = 2, BPT_RANDOMIZE_OWEN = 3 };
+enum { BPT_MAT_COATED_DIFFUSE = 0, BPT_MAT_COATED_CONDUCTOR = 1, BPT_MAT_CONDUCTOR = 2, BPT_MAT_DIELECTRIC = 3,
+       BPT_MAT_DIFFUSE = 4, BPT_MAT_DIFFUSE_TRANSMISSION = 5, BPT_MAT_HAIR = 6, BPT_MAT_MEASURED = 7,
+       BPT_MAT_SUBSURFACE = 8, BPT_MAT_THIN_DIELECTRIC = 9, BPT_MAT_MIX = 10, BPT_MAT_INTERFACE = 11 };
+enum { BPT_LIGHT_POINT = 0, BPT_LIGHT_DISTANT = 1, BPT_LIGHT_PROJECTION = 2, BPT_LIGHT_GONIOMETRIC = 3, BPT_LIGHT_SPOT = 4,
+       BPT_LIGHT_DIFFUSE_AREA = 5, BPT_LIGHT_UNIFORM_INFINITE = 6, BPT_LIGHT_IMAGE_INFINITE = 7,
+       BPT_LIGHT_PORTAL_IMAGE_INFINITE = 8 };
+enum { BPT_LIGHTSAMPLER_UNIFORM = 0, BPT_LIGHTSAMPLER_POWER = 1, BPT_LIGHTSAMPLER_EXHAUSTIVE = 2, BPT_LIGHTSAMPLER_BVH = 3 };
+
+/* How a spectrum-valued parameter was given in the scene description (paramdict.cpp GetOneSpectrum). */
+enum { BPT_SPEC_NONE = 0, BPT_SPEC_RGB = 1, BPT_SPEC_CONSTANT = 2, BPT_SPEC_NAMED = 3, BPT_SPEC_SAMPLED = 4,
+       BPT_SPEC_BLACKBODY = 5 };
+typedef struct {
+    int kind;
+    float rgb[3];         /* BPT_SPEC_RGB */
+    float value;          /* BPT_SPEC_CONSTANT value / BPT_SPEC_BLACKBODY temperature */
+    char name[48];        /* BPT_SPEC_NAMED, e.g. "metal-Cu-eta" */
+    const float *samples; /* BPT_SPEC_SAMPLED: n (lambda, value) pairs */
+    int n_samples;
+} bpt_spectrum;
+
+typedef struct { float m[4][4]; } bpt_mat4;
+
+typedef struct {
+    int type;                     /* BPT_CAMERA_* (only PERSPECTIVE is implemented) */
+    bpt_mat4 camera_from_world;   /* CTM at the Camera directive */
+    bpt_mat4 world_from_camera;   /* its tracked inverse (pbrt keeps both); all zeros => computed numerically */
+    float fov, lens_radius, focal_distance;
+    float frame_aspect_ratio;     /* <= 0: xres / yres */
+    float screen_window[4];       /* used when has_screen_window */
+    int has_screen_window;
+    float shutter_open, shutter_close;
+} bpt_camera;
+
+typedef struct {
+    int type;                     /* BPT_FILM_RGB | BPT_FILM_GBUFFER */
+    int xres, yres;
+    int pixel_bounds[4];          /* x0, x1, y0, y1 (exclusive upper); all 0 => full image */
+    float iso, exposure_time, white_balance;
+    float max_component_value;    /* <= 0: infinity */
+    float diagonal;               /* mm, default 35 */
+} bpt_film;
+
+typedef struct { int type; float xradius, yradius; float sigma, b, c, tau; } bpt_filter;
+typedef struct { int type; int spp; int seed; int randomize; } bpt_sampler;
+typedef struct { int max_depth; int regularize; int light_sampler; } bpt_integrator;
+
+typedef struct {
+    int type;                     /* BPT_MAT_* */
+    bpt_spectrum reflectance;     /* diffuse; conductor "reflectance"; coatedconductor "reflectance" */
+    bpt_spectrum eta, k;          /* conductor eta/k; dielectric eta (constant or spectrum) */
+    float roughness, uroughness, vroughness;   /* < 0 means "not given" for u/v */
+    int remap_roughness;
+    /* coated conductor */
+    float iface_roughness, iface_uroughness, iface_vroughness, thickness, g;
+    bpt_spectrum iface_eta, conductor_eta, conductor_k, albedo;
+    int max_depth, n_samples;
+} bpt_material;
+
+typedef struct {
+    bpt_spectrum L;               /* BPT_SPEC_NONE => colour-space illuminant */
+    float scale;
+    int two_sided;
+    float power;                  /* <= 0: unused */
+} bpt_area_light;
+
+typedef struct {
+    int n_vertices, n_triangles;
+    const float *P;               /* 3*n_vertices, object space */
+    const float *N;               /* optional, 3*n_vertices */
+    const float *UV;              /* optional, 2*n_vertices */
+    const int *indices;           /* 3*n_triangles */
+    bpt_mat4 world_from_object;   /* CTM at the Shape directive */
+    int reverse_orientation;
+    int material;                 /* index into the material array, -1 = "interface" */
+    int area_light;               /* index into the area-light array, -1 = none */
+    int medium_inside, medium_outside;   /* -1 = none */
+    int object_id;                /* -1: top-level shape; >= 0: belongs to instance definition object_id */
+} bpt_mesh;
+
+typedef struct {
+    int object_id;
+    bpt_mat4 world_from_instance;
+} bpt_instance;
+
+typedef struct {
+    int type;                     /* BPT_LIGHT_UNIFORM_INFINITE | BPT_LIGHT_IMAGE_INFINITE */
+    bpt_mat4 world_from_light;
+    bpt_spectrum L;
+    float scale;
+    float illuminance;            /* <= 0: unused */
+    const float *image_rgb;       /* IMAGE_INFINITE: res*res*3 floats, equal-area octahedral parameterisation */
+    int image_res;
+} bpt_light;
+
+typedef struct {
+    int type;                     /* 0 = uniform grid ("uniformgrid") */
+    bpt_mat4 world_from_medium;
+    bpt_spectrum sigma_a, sigma_s;
+    float scale, g;
+    float bounds[6];              /* p0, p1 */
+    const float *density; int nx, ny, nz;
+    bpt_spectrum Le; float Le_scale;
+} bpt_medium;
+
+typedef struct {
+    double seconds_build, seconds_render;
+    uint64_t camera_rays, indirect_rays, shadow_rays;
+    uint64_t nodes_visited, tris_tested;   /* only filled by a counting render (bpt_render with count_stats) */
+    uint64_t counted_rays;
+    int bvh_nodes, bvh_triangles, bvh_depth;
+    uint64_t bytes_bvh_nodes, bytes_bvh_tris;
+    int kernel_launches;
+    double ms_trace_closest, ms_trace_shadow, ms_shade, ms_other;  /* CUDA-event sums over the last bpt_render */
+} bpt_stats;
+
+/* ---- lifecycle ---- */
+int bpt_create(int cuda_device, const char *tables_path /* NULL: <lib dir>/../data/pbrt_tables.bin */, bpt_engine **out);
+void bpt_destroy(bpt_engine *e);
+const char *bpt_last_error(const bpt_engine *e /* may be NULL for create errors */);
+
+/* ---- scene description (copies everything) ---- */
+int bpt_scene_begin(bpt_engine *e);
+int bpt_scene_set_camera(bpt_engine *e, const bpt_camera *c);
+int bpt_scene_set_film(bpt_engine *e, const bpt_film *f);
+int bpt_scene_set_filter(bpt_engine *e, const bpt_filter *f);
+int bpt_scene_set_sampler(bpt_engine *e, const bpt_sampler *s);
+int bpt_scene_set_integrator(bpt_engine *e, const bpt_integrator *i);
+int bpt_scene_set_materials(bpt_engine *e, const bpt_material *m, int n);
+int bpt_scene_set_area_lights(bpt_engine *e, const bpt_area_light *a, int n);
+int bpt_scene_add_mesh(bpt_engine *e, const bpt_mesh *m);
+int bpt_scene_add_instance(bpt_engine *e, const bpt_instance *i);
+int bpt_scene_add_light(bpt_engine *e, const bpt_light *l);
+int bpt_scene_add_medium(bpt_engine *e, const bpt_medium *m);
+int bpt_scene_set_camera_medium(bpt_engine *e, int medium);
+/* Upload, build the BVH(s), light sampler and all tables.  After this the engine can render. */
+int bpt_scene_commit(bpt_engine *e);
+
+/* Convenience front end: parse a .pbrt file (subset: see INTEGRATION.md) and commit it. */
+int bpt_load_pbrt(bpt_engine *e, const char *path);
+/* Same with the command-line overrides of the reference (cmd/pbrt.cpp --spp, --seed); spp_override <= 0: none. */
+int bpt_load_pbrt_ex(bpt_engine *e, const char *path, int spp_override, int seed);
+const char *bpt_frontend_error(void);
+
+/* ---- rendering ---- */
+/* Render sample indices [first_sample, first_sample + n_samples) of the pixels in pixel_bounds
+ * (x0, x1, y0, y1; NULL = the film's pixel bounds) and accumulate them into the film.
+ * flags: bit0 = count traversal statistics (slower counting kernels). */
+int bpt_render(bpt_engine *e, int first_sample, int n_samples, const int *pixel_bounds, int flags);
+int bpt_film_clear(bpt_engine *e);
+/* Film accumulators: xres*yres*4 doubles {rgbSum[3], weightSum} over the FULL resolution (zero outside
+ * rendered tiles), row-major, y down -- RGBFilm::Pixel (film.h:302-307). */
+int bpt_film_read(bpt_engine *e, double *rgbw_host);
+int bpt_film_write(bpt_engine *e, const double *rgbw_host);                /* replace accumulators (after a reduce) */
+int bpt_film_copy_to_device(bpt_engine *e, void *dst_device_ptr);         /* d2d copy of the same layout */
+int bpt_film_copy_from_device(bpt_engine *e, const void *src_device_ptr);
+/* Final image, RGBFilm::GetPixelRGB (film.h:258-274): xres*yres*3 floats, output colour space. */
+int bpt_film_resolve(bpt_engine *e, float *rgb_host);
+int bpt_film_dims(const bpt_engine *e, int *xres, int *yres);
+int bpt_get_stats(bpt_engine *e, bpt_stats *out);
+
+/* ---- ray-level entry points (WavefrontAggregate::IntersectClosest / IntersectShadow on raw rays) ---- */
+/* rays: n x 8 floats {o.xyz, tMax, d.xyz, unused}; hits: n x 4 {prim (int bits, -1 = miss), b0, b1, b2}, t in t_out */
+int bpt_trace_closest(bpt_engine *e, const float *rays_host, int n, float *hits_host, float *t_out_host);
+int bpt_trace_any(bpt_engine *e, const float *rays_host, int n, int *occluded_host);
+/* device-resident variants for benchmarking (pointers are device pointers) */
+int bpt_trace_closest_device(bpt_engine *e, const void *rays_dev, int n, void *hits_dev, int flags);
+
+/* ---- unit-level probes used by the parity tests (device evaluation of restated reference functions) ---- */
+int bpt_probe_sampler(bpt_engine *e, const int *pixels_xy, const int *sample_index, const int *dimension, int n,
+                      float *out_1d, float *out_2d /* 2n */);
+int bpt_probe_intersect_triangle(bpt_engine *e, const float *rays /* n x 7: o, d, tMax */, const float *tris /* n x 9 */,
+                                 int n, float *out /* n x 5: hit, b0, b1, b2, t */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,310 @@
+// ref_dump.cpp -- TEST / DATA-GENERATION TOOL, linked against the UNMODIFIED reference (oracle/_ref/lib/libpbrt.a).
+// Not part of the product; built by oracle/build_ref.py.
+//
+//   ref_dump tables <out.bin>       standard data tables the engine loads at start-up (CIE matching functions,
+//                                   D65 illuminant, sRGB matrices, the sRGB RGB->spectrum coefficient table produced by
+//                                   the reference's rgb2spec_opt generator, Sobol' generator matrices, named metal spectra)
+//   ref_dump golden <out.bin>       golden vectors of path functions evaluated by the reference itself
+//                                   (hash, ZSobol sampler, IntersectTriangle, sampling routines, BVH closest hits ...)
+#include <algorithm>
+#include <any>
+#include <array>
+#include <atomic>
+#include <condition_variable>
+#include <fstream>
+#include <functional>
+#include <future>
+#include <iostream>
+#include <list>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <optional>
+#include <set>
+#include <shared_mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <tuple>
+#include <unordered_map>
+#include <unordered_set>
+#include <variant>
+#include <vector>
+#include <memory_resource>
+#include <cmath>
+#include <limits>
+#include <numeric>
+#include <random>
+#include <chrono>
+#include <iomanip>
+#include <typeindex>
+#include <type_traits>
+#include <utility>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#define private public
+#define protected public
+#include <pbrt/pbrt.h>
+#include <pbrt/cpu/aggregates.h>
+#include <pbrt/cpu/primitive.h>
+#include <pbrt/lightsamplers.h>
+#include <pbrt/lights.h>
+#include <pbrt/options.h>
+#include <pbrt/samplers.h>
+#include <pbrt/shapes.h>
+#include <pbrt/util/color.h>
+#include <pbrt/util/colorspace.h>
+#include <pbrt/util/hash.h>
+#include <pbrt/util/lowdiscrepancy.h>
+#include <pbrt/util/mesh.h>
+#include <pbrt/util/rng.h>
+#include <pbrt/util/sampling.h>
+#include <pbrt/util/sobolmatrices.h>
+#include <pbrt/util/spectrum.h>
+#undef private
+#undef protected
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pbrt;
+
+namespace pbrt {
+extern const float sRGBToSpectrumTable_Scale[64];
+extern const RGBToSpectrumTable::CoefficientArray sRGBToSpectrumTable_Data;
+}
+
+struct Blob {
+    FILE *f;
+    explicit Blob(const char *path) { f = fopen(path, "wb"); if (!f) { perror(path); exit(1); } fwrite("BPTTBL1", 1, 8, f); }
+    ~Blob() { fclose(f); }
+    void put(const char *name, uint32_t dtype, const void *data, uint64_t count) {
+        char nm[32]; memset(nm, 0, 32); strncpy(nm, name, 31);
+        fwrite(nm, 1, 32, f); fwrite(&dtype, 4, 1, f); fwrite(&count, 8, 1, f); fwrite(data, 4, count, f);
+    }
+    void f32(const char *name, const std::vector<float> &v) { put(name, 0, v.data(), v.size()); }
+    void u32(const char *name, const std::vector<uint32_t> &v) { put(name, 1, v.data(), v.size()); }
+    void i32(const char *name, const std::vector<int> &v) { put(name, 2, v.data(), v.size()); }
+};
+
+static std::vector<float> Dense(Spectrum s) {
+    std::vector<float> v;
+    for (int l = 360; l <= 830; ++l) v.push_back(s(l));
+    return v;
+}
+
+static void DumpTables(const char *path) {
+    Blob b(path);
+    b.f32("cie_x", Dense(&Spectra::X()));
+    b.f32("cie_y", Dense(&Spectra::Y()));
+    b.f32("cie_z", Dense(&Spectra::Z()));
+    b.f32("cie_y_integral", {CIE_Y_integral});
+    const RGBColorSpace *cs = RGBColorSpace::sRGB;
+    b.f32("srgb_illuminant", Dense(&cs->illuminant));
+    std::vector<float> m;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m.push_back(cs->RGBFromXYZ[i][j]);
+    b.f32("srgb_rgb_from_xyz", m);
+    m.clear();
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m.push_back(cs->XYZFromRGB[i][j]);
+    b.f32("srgb_xyz_from_rgb", m);
+    b.f32("srgb_white", {cs->w.x, cs->w.y});
+    b.f32("rgb2spec_srgb_scale", std::vector<float>(sRGBToSpectrumTable_Scale, sRGBToSpectrumTable_Scale + 64));
+    const float *cd = &sRGBToSpectrumTable_Data[0][0][0][0][0];
+    b.f32("rgb2spec_srgb_coeffs", std::vector<float>(cd, cd + 3 * 64 * 64 * 64 * 3));
+    b.u32("sobol32_2x52", std::vector<uint32_t>(SobolMatrices32, SobolMatrices32 + 2 * SobolMatrixSize));
+    // named spectra (piecewise linear): lambdas then values
+    const char *names[] = {"metal-Cu-eta", "metal-Cu-k", "metal-Au-eta", "metal-Au-k", "metal-Ag-eta", "metal-Ag-k",
+                           "metal-Al-eta", "metal-Al-k", "glass-BK7", "glass-BAF10", "glass-F11", "stdillum-D65",
+                           "illum-A", "illum-D50"};
+    for (const char *nm : names) {
+        Spectrum s = GetNamedSpectrum(nm);
+        if (!s) { fprintf(stderr, "named spectrum %s missing\n", nm); continue; }
+        if (s.Is<PiecewiseLinearSpectrum>()) {
+            const PiecewiseLinearSpectrum *pl = s.Cast<PiecewiseLinearSpectrum>();
+            std::vector<float> v(pl->lambdas.begin(), pl->lambdas.end());
+            v.insert(v.end(), pl->values.begin(), pl->values.end());
+            b.f32((std::string("pl:") + nm).c_str(), v);
+        } else {
+            b.f32((std::string("dense:") + nm).c_str(), Dense(s));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ golden vectors
+static void DumpGolden(const char *path) {
+    Blob b(path);
+    RNG rng(1234);
+    // hashes
+    {
+        std::vector<uint32_t> out;
+        for (int i = 0; i < 64; ++i) {
+            int a = rng.Uniform<uint32_t>() >> 8, c = rng.Uniform<uint32_t>() & 0xffff;
+            uint64_t h = Hash(a, c);
+            uint64_t mx = MixBits(((uint64_t)a << 20) ^ c);
+            float fa = rng.Uniform<float>(), fb = rng.Uniform<float>(), fc = rng.Uniform<float>();
+            uint64_t h3 = Hash(Point3f(fa, fb, fc));
+            uint64_t h1 = Hash(fa);
+            out.insert(out.end(), {(uint32_t)a, (uint32_t)c, (uint32_t)h, (uint32_t)(h >> 32), (uint32_t)mx, (uint32_t)(mx >> 32),
+                                   FloatToBits(fa), FloatToBits(fb), FloatToBits(fc), (uint32_t)h3, (uint32_t)(h3 >> 32),
+                                   (uint32_t)h1, (uint32_t)(h1 >> 32)});
+        }
+        b.u32("hash", out);
+    }
+    // ZSobol + Independent sampler values: (px, py, sampleIndex, dim) -> Get1D, Get2D
+    for (int cfg = 0; cfg < 4; ++cfg) {
+        int spp = cfg == 0 ? 64 : (cfg == 1 ? 32 : (cfg == 2 ? 256 : 16));
+        Point2i res = cfg == 2 ? Point2i(1024, 1024) : Point2i(256, 200);
+        int seed = cfg == 1 ? 7 : 0;
+        RandomizeStrategy rs = cfg == 3 ? RandomizeStrategy::Owen : (cfg == 1 ? RandomizeStrategy::PermuteDigits : RandomizeStrategy::FastOwen);
+        ZSobolSampler zs(spp, res, rs, seed);
+        IndependentSampler is(spp, seed);
+        std::vector<int> in;
+        std::vector<float> out, outI;
+        for (int i = 0; i < 512; ++i) {
+            int px = rng.Uniform<uint32_t>() % res.x, py = rng.Uniform<uint32_t>() % res.y;
+            int si = rng.Uniform<uint32_t>() % spp, dim = rng.Uniform<uint32_t>() % 60;
+            in.insert(in.end(), {px, py, si, dim});
+            zs.StartPixelSample({px, py}, si, dim);
+            float a = zs.Get1D();
+            zs.StartPixelSample({px, py}, si, dim);
+            Point2f p = zs.Get2D();
+            out.insert(out.end(), {a, p.x, p.y});
+            is.StartPixelSample({px, py}, si, dim);
+            float ia = is.Get1D();
+            is.StartPixelSample({px, py}, si, dim);
+            Point2f ip = is.Get2D();
+            outI.insert(outI.end(), {ia, ip.x, ip.y});
+        }
+        b.i32(StringPrintf("sampler%d_params", cfg).c_str(), {spp, res.x, res.y, seed, (int)rs});
+        b.i32(StringPrintf("sampler%d_in", cfg).c_str(), in);
+        b.f32(StringPrintf("sampler%d_zsobol", cfg).c_str(), out);
+        b.f32(StringPrintf("sampler%d_indep", cfg).c_str(), outI);
+    }
+    // IntersectTriangle: random rays vs random triangles (including edge/vertex grazing cases)
+    {
+        std::vector<float> in, out;
+        for (int i = 0; i < 4096; ++i) {
+            auto r = [&]() { return 2 * rng.Uniform<float>() - 1; };
+            Point3f p0(r(), r(), r()), p1(r(), r(), r()), p2(r(), r(), r());
+            if (i % 4 == 1) { p1 = p0 + 0.01f * Vector3f(r(), r(), r()); p2 = p0 + 0.01f * Vector3f(r(), r(), r()); }
+            Point3f o(3 * r(), 3 * r(), 3 * r());
+            Float b0 = rng.Uniform<float>(), b1 = rng.Uniform<float>() * (1 - b0);
+            Point3f target = b0 * p0 + b1 * p1 + (1 - b0 - b1) * p2;
+            if (i % 8 == 3) target = p0;                           // through a vertex
+            if (i % 8 == 5) target = 0.5f * p0 + 0.5f * p1;          // through an edge
+            if (i % 3 == 2) target += Vector3f(r(), r(), r()) * 0.7f;  // likely miss
+            Vector3f d = target - o;
+            if (i % 2) d = Normalize(d);
+            Float tMax = (i % 5 == 4) ? 0.9f * Length(target - o) / Length(d) : Infinity;
+            pstd::optional<TriangleIntersection> ti = IntersectTriangle(Ray(o, d), tMax, p0, p1, p2);
+            in.insert(in.end(), {o.x, o.y, o.z, d.x, d.y, d.z, tMax, p0.x, p0.y, p0.z, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z});
+            if (ti) out.insert(out.end(), {1.f, ti->b0, ti->b1, ti->b2, ti->t}); else out.insert(out.end(), {0.f, 0.f, 0.f, 0.f, 0.f});
+        }
+        b.f32("tri_in", in);
+        b.f32("tri_out", out);
+    }
+    // the reference's own known-answer case, Triangle.BadCases (shapes_test.cpp:435): must miss
+    {
+        std::vector<float> in = {-1113.45459f, 79.049614f, -56.2431908f, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        b.f32("tri_badcase_note", in);
+    }
+    // sampling routines
+    {
+        std::vector<float> in, out;
+        for (int i = 0; i < 1024; ++i) {
+            Point2f u(rng.Uniform<float>(), rng.Uniform<float>());
+            Point2f d = SampleUniformDiskConcentric(u);
+            Vector3f c = SampleCosineHemisphere(u);
+            Float lam = SampleVisibleWavelengths(u.x), lpdf = VisibleWavelengthsPDF(lam);
+            auto r = [&]() { return 2 * rng.Uniform<float>() - 1; };
+            pstd::array<Point3f, 3> v = {Point3f(r(), 2 + r(), r()), Point3f(r(), 2 + r(), r()), Point3f(r(), 2 + r(), r())};
+            Point3f p(r(), r() - 1, r());
+            Float pdf;
+            pstd::array<Float, 3> bc = SampleSphericalTriangle(v, p, u, &pdf);
+            Float w[4] = {rng.Uniform<float>(), rng.Uniform<float>(), rng.Uniform<float>(), rng.Uniform<float>()};
+            Point2f bl = SampleBilinear(u, w);
+            Float blp = BilinearPDF(bl, w);
+            Float area = SphericalTriangleArea(Normalize(v[0] - p), Normalize(v[1] - p), Normalize(v[2] - p));
+            Vector3f wdir = Normalize((bc[0] * v[0] + bc[1] * v[1] + bc[2] * v[2]) - p);
+            Point2f inv = InvertSphericalTriangleSample(v, p, wdir);
+            in.insert(in.end(), {u.x, u.y, v[0].x, v[0].y, v[0].z, v[1].x, v[1].y, v[1].z, v[2].x, v[2].y, v[2].z, p.x, p.y, p.z,
+                                 w[0], w[1], w[2], w[3]});
+            out.insert(out.end(), {d.x, d.y, c.x, c.y, c.z, lam, lpdf, bc[0], bc[1], bc[2], pdf, bl.x, bl.y, blp, area, inv.x, inv.y});
+        }
+        b.f32("sampling_in", in);
+        b.f32("sampling_out", out);
+    }
+    // FastExp / Gaussian / RGB -> spectrum
+    {
+        std::vector<float> in, out;
+        for (int i = 0; i < 512; ++i) {
+            float x = -20 * rng.Uniform<float>();
+            RGB rgb(rng.Uniform<float>(), rng.Uniform<float>(), rng.Uniform<float>());
+            if (i % 7 == 0) rgb = RGB(rgb.r, rgb.r, rgb.r);
+            RGBSigmoidPolynomial sp = RGBColorSpace::sRGB->ToRGBCoeffs(rgb);
+            float lam = 360 + 470 * rng.Uniform<float>();
+            RGBAlbedoSpectrum as(*RGBColorSpace::sRGB, rgb);
+            RGBIlluminantSpectrum il(*RGBColorSpace::sRGB, RGB(17 * rgb.r, 12 * rgb.g, 4 * rgb.b));
+            in.insert(in.end(), {x, rgb.r, rgb.g, rgb.b, lam});
+            out.insert(out.end(), {FastExp(x), sp.c0, sp.c1, sp.c2, as(lam), il(lam), il.scale});
+        }
+        b.f32("spectrum_in", in);
+        b.f32("spectrum_out", out);
+    }
+    // BVHAggregate closest hits on a seeded random triangle soup (hit record = primitive, b0, b1, b2, t)
+    {
+        Allocator alloc;
+        const int nTri = 2000;
+        std::vector<int> idx; std::vector<Point3f> P;
+        for (int i = 0; i < nTri; ++i) {
+            auto r = [&]() { return 2 * rng.Uniform<float>() - 1; };
+            Point3f c(r(), r(), r());
+            for (int k = 0; k < 3; ++k) { P.push_back(c + 0.15f * Vector3f(r(), r(), r())); idx.push_back(3 * i + k); }
+        }
+        TriangleMesh *mesh = alloc.new_object<TriangleMesh>(Transform(), false, idx, P, std::vector<Vector3f>(), std::vector<Normal3f>(),
+                                                            std::vector<Point2f>(), std::vector<int>(), alloc);
+        pstd::vector<Shape> tris = Triangle::CreateTriangles(mesh, alloc);
+        std::vector<Primitive> prims;
+        for (Shape s : tris) prims.push_back(new SimplePrimitive(s, nullptr));
+        BVHAggregate bvh(prims, 4, BVHAggregate::SplitMethod::SAH);
+        std::vector<float> verts, rays, hits;
+        for (const Point3f &p : mesh->p ? std::vector<Point3f>(mesh->p, mesh->p + 3 * nTri) : P) { verts.push_back(p.x); verts.push_back(p.y); verts.push_back(p.z); }
+        for (int i = 0; i < 20000; ++i) {
+            auto r = [&]() { return 2 * rng.Uniform<float>() - 1; };
+            Point3f o(1.5f * r(), 1.5f * r(), 1.5f * r());
+            Vector3f d = Normalize(Vector3f(r(), r(), r()));
+            Float tMax = (i % 4 == 3) ? rng.Uniform<float>() : Infinity;
+            pstd::optional<ShapeIntersection> si = bvh.Intersect(Ray(o, d), tMax);
+            bool occluded = bvh.IntersectP(Ray(o, d), tMax);
+            rays.insert(rays.end(), {o.x, o.y, o.z, tMax, d.x, d.y, d.z, 0.f});
+            if (si) {
+                // recover the primitive by re-testing (closest t is unique up to ties)
+                int prim = -1; Float b0 = 0, b1 = 0, b2 = 0;
+                for (int k = 0; k < nTri; ++k) {
+                    auto ti = IntersectTriangle(Ray(o, d), tMax, mesh->p[3 * k], mesh->p[3 * k + 1], mesh->p[3 * k + 2]);
+                    if (ti && ti->t == si->tHit) { prim = k; b0 = ti->b0; b1 = ti->b1; b2 = ti->b2; break; }
+                }
+                hits.insert(hits.end(), {(float)prim, b0, b1, b2, si->tHit, occluded ? 1.f : 0.f, si->intr.p().x, si->intr.p().y, si->intr.p().z,
+                                         si->intr.n.x, si->intr.n.y, si->intr.n.z});
+            } else
+                hits.insert(hits.end(), {-1.f, 0, 0, 0, 0, occluded ? 1.f : 0.f, 0, 0, 0, 0, 0, 0});
+        }
+        b.f32("bvh_verts", verts);
+        b.f32("bvh_rays", rays);
+        b.f32("bvh_hits", hits);
+    }
+}
+
+int main(int argc, char **argv) {
+    if (argc < 3) { fprintf(stderr, "usage: ref_dump tables|golden <out.bin>\n"); return 1; }
+    PBRTOptions opt;
+    opt.quiet = true;
+    InitPBRT(opt);
+    if (!strcmp(argv[1], "tables")) DumpTables(argv[2]);
+    else if (!strcmp(argv[1], "golden")) DumpGolden(argv[2]);
+    else return 1;
+    return 0;
+}

@@ -1,0 +1,218 @@
+// bvh.cuh -- 8-wide compressed BVH (80-byte nodes, quantised child boxes, octant-ordered slots) and its
+// closest-hit / any-hit traversal.  No reference counterpart: the reference GPU path calls optixTrace
+// (gpu/optix/optix.cu:65) and its CPU path walks a binary 32-byte-node BVH (cpu/aggregates.cpp:529-624).
+// The only reference semantics kept here are the hit acceptance rules: the leaf test is the watertight
+// IntersectTriangle (shapes.cpp:168-269) with a shrinking tMax, so the closest hit (t, b0, b1, b2) is the one
+// BVHAggregate::Intersect would report (up to exact-t ties).
+//
+// Node layout (5 x 16 B, loaded as five 128-bit loads):
+//   n0 = { p.x, p.y, p.z, ex | ey<<8 | ez<<16 | imask<<24 }      origin + biased exponents + internal mask
+//   n1 = { childBase, triBase, meta[0..3], meta[4..7] }
+//   n2 = { qlo.x[0..3], qlo.x[4..7], qhi.x[0..3], qhi.x[4..7] }
+//   n3 = { qlo.y ... , qhi.y ... }      n4 = { qlo.z ... , qhi.z ... }
+//   meta[i]: empty = 0; internal = 0b001_sssss with sssss = 24 + slot; leaf = unary tri count (1,3,7) << 5 | first
+//   triangle offset relative to triBase (<= 23).
+#pragma once
+#include <cuda_runtime.h>
+#include "pmath.h"
+#include "shapes.h"
+
+namespace bpt {
+
+struct BVHView {
+    const float4 *nodes;      // 5 float4 per wide node; node 0 = root
+    const float4 *tris;       // 3 float4 per triangle in leaf order (p0.w = original triangle id)
+};
+
+#define BPT_STACK_SIZE 40
+
+struct RayPre {              // per-ray constants of the watertight test
+    Pt3 o; Vec3 d;
+    int kx, ky, kz;
+    float Sx, Sy, Sz;
+};
+BPT_D RayPre MakeRayPre(Pt3 o, Vec3 dir) {
+    RayPre r;
+    r.o = o; r.d = dir;
+    r.kz = MaxComponentIndex(Abs(dir));
+    r.kx = r.kz + 1; if (r.kx == 3) r.kx = 0;
+    r.ky = r.kx + 1; if (r.ky == 3) r.ky = 0;
+    Vec3 d = Permute(dir, r.kx, r.ky, r.kz);
+    r.Sx = -d.x / d.z; r.Sy = -d.y / d.z; r.Sz = 1 / d.z;
+    return r;
+}
+BPT_D Vec3 PermuteK(Vec3 v, int kz) {
+    // (kx,ky,kz) is a cyclic rotation: kz=2 -> (x,y,z), kz=0 -> (y,z,x), kz=1 -> (z,x,y)
+    return kz == 2 ? v : (kz == 0 ? Vec3(v.y, v.z, v.x) : Vec3(v.z, v.x, v.y));
+}
+// Same arithmetic as IntersectTriangle (shapes.h) with the per-ray terms hoisted.
+BPT_D bool IntersectTrianglePre(const RayPre &r, float tMax, Pt3 p0, Pt3 p1, Pt3 p2, TriHit *hit) {
+    if (LengthSquared(Cross(p2 - p0, p1 - p0)) == 0) return false;
+    Vec3 p0t = PermuteK(p0 - r.o, r.kz), p1t = PermuteK(p1 - r.o, r.kz), p2t = PermuteK(p2 - r.o, r.kz);
+    p0t.x += r.Sx * p0t.z; p0t.y += r.Sy * p0t.z;
+    p1t.x += r.Sx * p1t.z; p1t.y += r.Sy * p1t.z;
+    p2t.x += r.Sx * p2t.z; p2t.y += r.Sy * p2t.z;
+    float e0 = DifferenceOfProducts(p1t.x, p2t.y, p1t.y, p2t.x);
+    float e1 = DifferenceOfProducts(p2t.x, p0t.y, p2t.y, p0t.x);
+    float e2 = DifferenceOfProducts(p0t.x, p1t.y, p0t.y, p1t.x);
+    if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {
+        double p2txp1ty = (double)p2t.x * (double)p1t.y;
+        double p2typ1tx = (double)p2t.y * (double)p1t.x;
+        e0 = (float)(p2typ1tx - p2txp1ty);
+        double p0txp2ty = (double)p0t.x * (double)p2t.y;
+        double p0typ2tx = (double)p0t.y * (double)p2t.x;
+        e1 = (float)(p0typ2tx - p0txp2ty);
+        double p1txp0ty = (double)p1t.x * (double)p0t.y;
+        double p1typ0tx = (double)p1t.y * (double)p0t.x;
+        e2 = (float)(p1typ0tx - p1txp0ty);
+    }
+    if ((e0 < 0 || e1 < 0 || e2 < 0) && (e0 > 0 || e1 > 0 || e2 > 0)) return false;
+    float det = e0 + e1 + e2;
+    if (det == 0) return false;
+    p0t.z *= r.Sz; p1t.z *= r.Sz; p2t.z *= r.Sz;
+    float tScaled = e0 * p0t.z + e1 * p1t.z + e2 * p2t.z;
+    if (det < 0 && (tScaled >= 0 || tScaled < tMax * det)) return false;
+    else if (det > 0 && (tScaled <= 0 || tScaled > tMax * det)) return false;
+    float invDet = 1 / det;
+    float b0 = e0 * invDet, b1 = e1 * invDet, b2 = e2 * invDet;
+    float t = tScaled * invDet;
+    float maxZt = MaxComponentValue(Abs(Vec3(p0t.z, p1t.z, p2t.z)));
+    float deltaZ = gamma_n(3) * maxZt;
+    float maxXt = MaxComponentValue(Abs(Vec3(p0t.x, p1t.x, p2t.x)));
+    float maxYt = MaxComponentValue(Abs(Vec3(p0t.y, p1t.y, p2t.y)));
+    float deltaX = gamma_n(5) * (maxXt + maxZt);
+    float deltaY = gamma_n(5) * (maxYt + maxZt);
+    float deltaE = 2 * (gamma_n(2) * maxXt * maxYt + deltaY * maxXt + deltaX * maxYt);
+    float maxE = MaxComponentValue(Abs(Vec3(e0, e1, e2)));
+    float deltaT = 3 * (gamma_n(3) * maxE * maxZt + deltaE * maxZt + deltaZ * maxE) * fabsf(invDet);
+    if (t <= deltaT) return false;
+    hit->b0 = b0; hit->b1 = b1; hit->b2 = b2; hit->t = t;
+    return true;
+}
+
+BPT_D unsigned ExtractByte(unsigned x, unsigned i) { return (x >> (i * 8)) & 0xff; }
+BPT_D unsigned SignExtendS8x4(unsigned x) {
+    unsigned r;
+    asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(x));
+    return r;
+}
+BPT_D float SafeInvDir(float d) { return 1.0f / (fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }
+
+struct HitRec { int tri; float b0, b1, b2, t; };   // tri = leaf-order triangle index, -1 = miss
+
+// Conservative slab test of the 8 quantised children; returns the hit mask (internal children in bits 24..31
+// in octant-permuted order, triangles in bits 0..23).  The box test uses fast fused arithmetic: it only has to
+// be conservative (every box whose triangle could be accepted is visited), which the per-axis error margin
+// guarantees; it does not influence the reported hit.
+BPT_D unsigned NodeIntersect(Vec3 o, Vec3 idir, unsigned octinv4, float tMax, float4 n0, float4 n1, float4 n2, float4 n3,
+                             float4 n4) {
+    unsigned e_imask = __float_as_uint(n0.w);
+    float ex = __uint_as_float(ExtractByte(e_imask, 0) << 23);
+    float ey = __uint_as_float(ExtractByte(e_imask, 1) << 23);
+    float ez = __uint_as_float(ExtractByte(e_imask, 2) << 23);
+    float ax = ex * idir.x, ay = ey * idir.y, az = ez * idir.z;
+    float ox = (n0.x - o.x) * idir.x, oy = (n0.y - o.y) * idir.y, oz = (n0.z - o.z) * idir.z;
+    // error margin: |org| and the largest |q*adj| each carry a few ulps
+    const float kEps = 4.76837158203125e-7f;   // 2^-21
+    float mx = kEps * __fmaf_rn(256.f, fabsf(ax), fabsf(ox));
+    float my = kEps * __fmaf_rn(256.f, fabsf(ay), fabsf(oy));
+    float mz = kEps * __fmaf_rn(256.f, fabsf(az), fabsf(oz));
+    float oxlo = ox - mx, oxhi = ox + mx, oylo = oy - my, oyhi = oy + my, ozlo = oz - mz, ozhi = oz + mz;
+    unsigned hitmask = 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        unsigned meta4 = __float_as_uint(i == 0 ? n1.z : n1.w);
+        unsigned is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010;
+        unsigned inner_mask4 = SignExtendS8x4(is_inner4 << 3);
+        unsigned bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1f;
+        unsigned child_bits4 = (meta4 >> 5) & 0x07070707;
+        unsigned qlox = __float_as_uint(i == 0 ? n2.x : n2.y), qhix = __float_as_uint(i == 0 ? n2.z : n2.w);
+        unsigned qloy = __float_as_uint(i == 0 ? n3.x : n3.y), qhiy = __float_as_uint(i == 0 ? n3.z : n3.w);
+        unsigned qloz = __float_as_uint(i == 0 ? n4.x : n4.y), qhiz = __float_as_uint(i == 0 ? n4.z : n4.w);
+        unsigned xmin = idir.x < 0 ? qhix : qlox, xmax = idir.x < 0 ? qlox : qhix;
+        unsigned ymin = idir.y < 0 ? qhiy : qloy, ymax = idir.y < 0 ? qloy : qhiy;
+        unsigned zmin = idir.z < 0 ? qhiz : qloz, zmax = idir.z < 0 ? qloz : qhiz;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float tminx = __fmaf_rn((float)ExtractByte(xmin, j), ax, oxlo);
+            float tminy = __fmaf_rn((float)ExtractByte(ymin, j), ay, oylo);
+            float tminz = __fmaf_rn((float)ExtractByte(zmin, j), az, ozlo);
+            float tmaxx = __fmaf_rn((float)ExtractByte(xmax, j), ax, oxhi);
+            float tmaxy = __fmaf_rn((float)ExtractByte(ymax, j), ay, oyhi);
+            float tmaxz = __fmaf_rn((float)ExtractByte(zmax, j), az, ozhi);
+            float tmin = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, 0.f));
+            float tmax = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, tMax));
+            if (tmin <= tmax) {
+                unsigned child_bits = ExtractByte(child_bits4, j);
+                unsigned bit_index = ExtractByte(bit_index4, j);
+                hitmask |= child_bits << bit_index;
+            }
+        }
+    }
+    return hitmask;
+}
+
+// Traversal statistics (counting build only)
+struct TraceCounters { unsigned long long nodes, tris, rays; };
+
+template <bool ANYHIT, bool COUNT>
+BPT_D void TraceRay(const BVHView &bvh, Pt3 o, Vec3 d, float tMax, HitRec *rec, unsigned *nNodes, unsigned *nTris) {
+    RayPre rp = MakeRayPre(o, d);
+    Vec3 idir(SafeInvDir(d.x), SafeInvDir(d.y), SafeInvDir(d.z));
+    Vec3 ov(o.x, o.y, o.z);
+    unsigned octinv = (d.x < 0 ? 0u : 4u) | (d.y < 0 ? 0u : 2u) | (d.z < 0 ? 0u : 1u);
+    unsigned octinv4 = octinv * 0x01010101u;
+    // box culling distance: the accepted-hit rule compares tScaled against tMax*det; give the boxes a little slack
+    float tBox = tMax * (1 + 2 * gamma_n(3));
+
+    uint2 stack[BPT_STACK_SIZE];
+    int sp = 0;
+    uint2 cur = make_uint2(0u, 0x80000000u);
+    rec->tri = -1; rec->t = tMax;
+
+    while (true) {
+        uint2 triGroup;
+        if (cur.y & 0xff000000u) {
+            unsigned hits_imask = cur.y;
+            unsigned child_bit = 31 - __clz(hits_imask);
+            unsigned child_base = cur.x;
+            cur.y &= ~(1u << child_bit);
+            if (cur.y & 0xff000000u) stack[sp++] = cur;
+            unsigned slot = (child_bit - 24) ^ (octinv4 & 0xff);
+            unsigned rel = __popc(hits_imask & ~(0xffffffffu << slot));
+            unsigned node = child_base + rel;
+            const float4 *np = bvh.nodes + (size_t)node * 5;
+            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            if (COUNT) ++*nNodes;
+            unsigned hitmask = NodeIntersect(ov, idir, octinv4, tBox, n0, n1, n2, n3, n4);
+            unsigned imask = ExtractByte(__float_as_uint(n0.w), 3);
+            cur.x = __float_as_uint(n1.x);
+            triGroup.x = __float_as_uint(n1.y);
+            cur.y = (hitmask & 0xff000000u) | imask;
+            triGroup.y = hitmask & 0x00ffffffu;
+        } else {
+            triGroup = cur;
+            cur = make_uint2(0, 0);
+        }
+        while (triGroup.y != 0) {
+            unsigned ti = 31 - __clz(triGroup.y);
+            triGroup.y &= ~(1u << ti);
+            unsigned tri = triGroup.x + ti;
+            const float4 *tp = bvh.tris + (size_t)tri * 3;
+            float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            if (COUNT) ++*nTris;
+            TriHit th;
+            if (IntersectTrianglePre(rp, rec->t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th)) {
+                rec->tri = (int)tri; rec->b0 = th.b0; rec->b1 = th.b1; rec->b2 = th.b2; rec->t = th.t;
+                if (ANYHIT) return;
+                tBox = th.t * (1 + 2 * gamma_n(3));
+            }
+        }
+        if ((cur.y & 0xff000000u) == 0) {
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+}
+
+}  // namespace bpt

@@ -1,0 +1,908 @@
+// engine.cu -- implementation of the C ABI in include/b200pt.h: scene intake, host-side scene preparation
+// (restating what BasicScene::Create* and the WavefrontPathIntegrator constructor do, wavefront/integrator.cpp:80-287),
+// device upload, BVH build and the wavefront render loop (wavefront/integrator.cpp:290-493).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+#include "../../include/b200pt.h"
+#include "bvh_build.h"
+#include "kernels.h"
+#include "lightbvh.h"
+#include "tables.h"
+#include "xform.h"
+
+using namespace bpt;
+
+namespace {
+
+struct OwnedSpectrum {
+    bpt_spectrum s;
+    std::vector<float> samples;
+    void Set(const bpt_spectrum &in) {
+        s = in;
+        samples.clear();
+        if (in.kind == BPT_SPEC_SAMPLED && in.samples && in.n_samples > 0) samples.assign(in.samples, in.samples + 2 * (size_t)in.n_samples);
+        s.samples = nullptr;
+    }
+};
+struct OwnedMaterial {
+    bpt_material m;
+    OwnedSpectrum reflectance, eta, k, iface_eta, conductor_eta, conductor_k, albedo;
+};
+struct OwnedMesh {
+    bpt_mesh m;
+    std::vector<float> P, N, UV;
+    std::vector<int> idx;
+};
+struct OwnedLight {
+    bpt_light l;
+    OwnedSpectrum L;
+    std::vector<float> image;
+};
+struct OwnedAreaLight { bpt_area_light a; OwnedSpectrum L; };
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) {
+        if (p) { cudaFree(p); p = nullptr; }
+        n = count;
+        return cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T> &v) {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess) return e;
+        if (!v.empty()) e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+        return e;
+    }
+};
+
+}  // namespace
+
+struct bpt_engine {
+    int device = 0;
+    int smCount = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    Tables tables;
+    // description
+    bpt_camera cam{};
+    bpt_film film{};
+    bpt_filter filter{};
+    bpt_sampler sampler{};
+    bpt_integrator integ{};
+    bool haveCam = false, haveFilm = false;
+    std::vector<OwnedMaterial> materials;
+    std::vector<OwnedAreaLight> areaLights;
+    std::vector<OwnedMesh> meshes;
+    std::vector<bpt_instance> instances;
+    std::vector<OwnedLight> lights;
+    int cameraMedium = -1;
+    // device
+    DevBuf<float4> triPool;
+    DevBuf<DeviceMesh> dMeshes;
+    DevBuf<int> indexPool;
+    DevBuf<float> nPool, uvPool, specPool;
+    DevBuf<DeviceMaterial> dMaterials;
+    DevBuf<DeviceLight> dLights;
+    DevBuf<DeviceLightBVHNode> dLightNodes;
+    DevBuf<int> dInfinite, dLightInBVH;
+    DevBuf<uint32_t> dBitTrails;
+    DevBuf<float> dTables;     // cieX, cieY, cieZ, illum (4 x 471)
+    DevBuf<float> dFilter;     // func, cdf, funcInt, mfunc, mcdf, f
+    DevBuf<double4> filmPixels;
+    DevBuf<float> filmRGB;
+    DevBuf<int> counts;
+    DevBuf<unsigned long long> stats;
+    DevBuf<int> queueMem;
+    DevBuf<ShadowItem> shadowItems;
+    DevBuf<float4> stateF4;
+    DevBuf<uint4> stateMisc;
+    DevBuf<float2> stateAux;
+    DevBuf<int> rawCursor;
+    WideBVH bvh{};
+    RenderCtx rc{};
+    bool committed = false;
+    bool materialPresent[MAT_NTAGS] = {};
+    bool haveAreaLights = false;
+    int nTrisTotal = 0;
+    int maxPaths = 0;
+    bpt_stats st{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    int fail(int code, const std::string &m) { err = m; return code; }
+    int cudaFail(cudaError_t e, const char *what) { err = std::string(what) + ": " + cudaGetErrorString(e); return BPT_ERR_CUDA; }
+};
+
+static std::string g_createError;
+
+#define ECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e->cudaFail(e_, #call); } while (0)
+
+// ------------------------------------------------------------------------------------------- spectra (host)
+namespace {
+
+// RGBToSpectrumTable::operator() (util/color.cpp:31-68)
+void RGBToCoeffs(const Tables &t, const float rgbIn[3], float c[3]) {
+    const std::vector<float> &zNodes = t.F("rgb2spec_srgb_scale");
+    const std::vector<float> &coeffs = t.F("rgb2spec_srgb_coeffs");
+    const int res = 64;
+    float rgb[3] = {stdmax(0.f, rgbIn[0]), stdmax(0.f, rgbIn[1]), stdmax(0.f, rgbIn[2])};   // ClampZero
+    if (rgb[0] == rgb[1] && rgb[1] == rgb[2]) {
+        c[0] = 0; c[1] = 0; c[2] = (rgb[0] - .5f) / std::sqrt(rgb[0] * (1 - rgb[0]));
+        return;
+    }
+    int maxc = (rgb[0] > rgb[1]) ? ((rgb[0] > rgb[2]) ? 0 : 2) : ((rgb[1] > rgb[2]) ? 1 : 2);
+    float z = rgb[maxc];
+    float x = rgb[(maxc + 1) % 3] * (res - 1) / z;
+    float y = rgb[(maxc + 2) % 3] * (res - 1) / z;
+    int xi = std::min((int)x, res - 2), yi = std::min((int)y, res - 2);
+    int zi = FindIntervalLT(zNodes.data(), res, z);
+    float dx = x - xi, dy = y - yi, dz = (z - zNodes[zi]) / (zNodes[zi + 1] - zNodes[zi]);
+    for (int i = 0; i < 3; ++i) {
+        auto co = [&](int ddx, int ddy, int ddz) {
+            return coeffs[((((size_t)maxc * res + (zi + ddz)) * res + (yi + ddy)) * res + (xi + ddx)) * 3 + i];
+        };
+        c[i] = Lerp(dz, Lerp(dy, Lerp(dx, co(0, 0, 0), co(1, 0, 0)), Lerp(dx, co(0, 1, 0), co(1, 1, 0))),
+                    Lerp(dy, Lerp(dx, co(0, 0, 1), co(1, 0, 1)), Lerp(dx, co(0, 1, 1), co(1, 1, 1))));
+    }
+}
+
+enum SpecType { ST_ALBEDO, ST_UNBOUNDED, ST_ILLUMINANT };
+
+struct SpecPool {
+    std::vector<float> pool;
+    int addDense(const std::vector<float> &v) { int o = (int)pool.size(); pool.insert(pool.end(), v.begin(), v.end()); return o; }
+};
+
+// host evaluation of a SpectrumRec at one wavelength (Spectrum::operator()(lambda))
+float EvalRecAt(const SpectrumRec &r, const std::vector<float> &pool, float lambda) {
+    switch (r.kind) {
+    case SPEC_CONSTANT: return r.c0;
+    case SPEC_RGB_ALBEDO: return SigmoidPoly(r.c0, r.c1, r.c2, lambda);
+    case SPEC_RGB_UNBOUNDED: return r.scale * SigmoidPoly(r.c0, r.c1, r.c2, lambda);
+    case SPEC_DENSE: return DenseLookup(pool.data() + r.table, lambda);
+    case SPEC_PIECEWISE: return PiecewiseLinearEval(pool.data() + r.table, pool.data() + r.table + r.n, r.n, lambda);
+    }
+    return 0;
+}
+
+// Builds a SpectrumRec for a material / medium parameter.  Returns false if unsupported.
+bool MakeSpectrumRec(const bpt_engine *e, const OwnedSpectrum &os, SpecType type, SpecPool &sp, SpectrumRec *out, std::string *err) {
+    std::memset(out, 0, sizeof(*out));
+    const bpt_spectrum &s = os.s;
+    switch (s.kind) {
+    case BPT_SPEC_CONSTANT: out->kind = SPEC_CONSTANT; out->c0 = s.value; return true;
+    case BPT_SPEC_RGB: {
+        float c[3];
+        if (type == ST_ALBEDO) {
+            RGBToCoeffs(e->tables, s.rgb, c);
+            out->kind = SPEC_RGB_ALBEDO; out->c0 = c[0]; out->c1 = c[1]; out->c2 = c[2];
+        } else {
+            float m = stdmax(stdmax(s.rgb[0], s.rgb[1]), s.rgb[2]);
+            float scale = 2 * m;
+            float rgb[3] = {0, 0, 0};
+            if (scale) { rgb[0] = s.rgb[0] / scale; rgb[1] = s.rgb[1] / scale; rgb[2] = s.rgb[2] / scale; }
+            RGBToCoeffs(e->tables, rgb, c);
+            out->kind = SPEC_RGB_UNBOUNDED; out->scale = scale; out->c0 = c[0]; out->c1 = c[1]; out->c2 = c[2];
+            if (type == ST_ILLUMINANT) {
+                // RGBIlluminantSpectrum: scale * rsp(lambda) * illuminant(lambda), densely sampled (LightBase::LookupSpectrum)
+                const std::vector<float> &illum = e->tables.F("srgb_illuminant");
+                std::vector<float> v(kNLambda);
+                for (int i = 0; i < kNLambda; ++i) v[i] = scale * SigmoidPoly(c[0], c[1], c[2], (float)(kLambdaMin + i)) * illum[i];
+                out->kind = SPEC_DENSE; out->table = sp.addDense(v);
+            }
+        }
+        return true;
+    }
+    case BPT_SPEC_NAMED: {
+        std::string key = std::string("pl:") + s.name;
+        auto it = e->tables.f32.find(key);
+        if (it == e->tables.f32.end()) {
+            auto it2 = e->tables.f32.find(std::string("dense:") + s.name);
+            if (it2 == e->tables.f32.end()) { *err = std::string("unknown named spectrum ") + s.name; return false; }
+            out->kind = SPEC_DENSE; out->table = sp.addDense(it2->second);
+            return true;
+        }
+        out->kind = SPEC_PIECEWISE; out->n = (int)it->second.size() / 2; out->table = sp.addDense(it->second);
+        return true;
+    }
+    case BPT_SPEC_SAMPLED: {
+        // PiecewiseLinearSpectrum::FromInterleaved without normalisation: lambdas then values
+        int n = (int)os.samples.size() / 2;
+        std::vector<float> v(2 * (size_t)n);
+        for (int i = 0; i < n; ++i) { v[i] = os.samples[2 * i]; v[n + i] = os.samples[2 * i + 1]; }
+        out->kind = SPEC_PIECEWISE; out->n = n; out->table = sp.addDense(v);
+        return true;
+    }
+    default: *err = "unsupported spectrum kind"; return false;
+    }
+}
+
+// FilterSampler tables (filters.cpp:FilterSampler ctor) + PiecewiseConstant2D (util/sampling.h)
+struct FilterTables {
+    int nx = 0, ny = 0;
+    std::vector<float> f, func, cdf, funcInt, mfunc, mcdf;
+    float mfuncInt = 0;
+};
+void BuildPC1D(const float *f, int n, float mn, float mx, float *func, float *cdf, float *funcInt) {
+    for (int i = 0; i < n; ++i) func[i] = std::abs(f[i]);
+    cdf[0] = 0;
+    for (int i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + func[i - 1] * (mx - mn) / n;
+    *funcInt = cdf[n];
+    if (*funcInt == 0) for (int i = 1; i < n + 1; ++i) cdf[i] = float(i) / float(n);
+    else for (int i = 1; i < n + 1; ++i) cdf[i] /= *funcInt;
+}
+void BuildPC2D(const std::vector<float> &f, int nu, int nv, float min0, float max0, float min1, float max1, FilterTables *t) {
+    t->func.resize((size_t)nu * nv); t->cdf.resize((size_t)(nu + 1) * nv); t->funcInt.resize(nv);
+    for (int v = 0; v < nv; ++v)
+        BuildPC1D(f.data() + (size_t)v * nu, nu, min0, max0, t->func.data() + (size_t)v * nu, t->cdf.data() + (size_t)v * (nu + 1), &t->funcInt[v]);
+    t->mfunc.resize(nv); t->mcdf.resize(nv + 1);
+    std::vector<float> marg(t->funcInt);
+    BuildPC1D(marg.data(), nv, min1, max1, t->mfunc.data(), t->mcdf.data(), &t->mfuncInt);
+}
+
+std::string DefaultTablesPath() {
+    Dl_info info;
+    if (dladdr((void *)&DefaultTablesPath, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t s = p.find_last_of('/');
+        std::string dir = (s == std::string::npos) ? "." : p.substr(0, s);
+        return dir + "/data/pbrt_tables.bin";
+    }
+    return "pbrt_tables.bin";
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------- lifecycle
+extern "C" int bpt_create(int cuda_device, const char *tables_path, bpt_engine **out) {
+    if (!out) return BPT_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        g_createError = std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0") +
+                        " (this engine has no CPU fallback)";
+        return BPT_ERR_NO_DEVICE;
+    }
+    if (cuda_device < 0 || cuda_device >= ndev) { g_createError = "invalid device index"; return BPT_ERR_INVALID; }
+    std::unique_ptr<bpt_engine> e(new bpt_engine);
+    e->device = cuda_device;
+    if ((ce = cudaSetDevice(cuda_device)) != cudaSuccess) { g_createError = cudaGetErrorString(ce); return BPT_ERR_CUDA; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, cuda_device);
+    e->smCount = prop.multiProcessorCount;
+    if (prop.major < 10) { g_createError = "device is not sm_100 class"; return BPT_ERR_NO_DEVICE; }
+    std::string terr;
+    if (!e->tables.Load(tables_path ? tables_path : DefaultTablesPath(), &terr)) { g_createError = terr; return BPT_ERR_IO; }
+    if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) { g_createError = cudaGetErrorString(ce); return BPT_ERR_CUDA; }
+    cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
+    UploadSobolTable(e->tables.u32.at("sobol32_2x52").data());
+    // defaults (scene.cpp / film.cpp / samplers.cpp defaults)
+    e->filter = bpt_filter{BPT_FILTER_GAUSSIAN, 1.5f, 1.5f, 0.5f, 1.f / 3.f, 1.f / 3.f, 3.f};
+    e->sampler = bpt_sampler{BPT_SAMPLER_ZSOBOL, 16, 0, BPT_RANDOMIZE_FAST_OWEN};
+    e->integ = bpt_integrator{5, 0, BPT_LIGHTSAMPLER_BVH};
+    const char *mp = std::getenv("BPT_MAX_PATHS");
+    e->maxPaths = mp ? std::atoi(mp) : (4 << 20);
+    *out = e.release();
+    return BPT_OK;
+}
+
+extern "C" void bpt_destroy(bpt_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    FreeWideBVH(&e->bvh);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" const char *bpt_last_error(const bpt_engine *e) { return e ? e->err.c_str() : g_createError.c_str(); }
+
+// ------------------------------------------------------------------------------------------- scene intake
+extern "C" int bpt_scene_begin(bpt_engine *e) {
+    if (!e) return BPT_ERR_INVALID;
+    e->materials.clear(); e->areaLights.clear(); e->meshes.clear(); e->instances.clear(); e->lights.clear();
+    e->haveCam = e->haveFilm = false; e->committed = false; e->cameraMedium = -1;
+    return BPT_OK;
+}
+extern "C" int bpt_scene_set_camera(bpt_engine *e, const bpt_camera *c) {
+    if (!e || !c) return BPT_ERR_INVALID;
+    if (c->type != BPT_CAMERA_PERSPECTIVE) return e->fail(BPT_ERR_UNSUPPORTED, "only the perspective camera is implemented");
+    e->cam = *c; e->haveCam = true; return BPT_OK;
+}
+extern "C" int bpt_scene_set_film(bpt_engine *e, const bpt_film *f) {
+    if (!e || !f) return BPT_ERR_INVALID;
+    if (f->type != BPT_FILM_RGB && f->type != BPT_FILM_GBUFFER) return e->fail(BPT_ERR_UNSUPPORTED, "film type not implemented");
+    if (f->xres <= 0 || f->yres <= 0 || f->xres > 65535 || f->yres > 65535) return e->fail(BPT_ERR_INVALID, "bad film resolution");
+    e->film = *f; e->haveFilm = true; return BPT_OK;
+}
+extern "C" int bpt_scene_set_filter(bpt_engine *e, const bpt_filter *f) {
+    if (!e || !f) return BPT_ERR_INVALID;
+    if (f->type != BPT_FILTER_GAUSSIAN && f->type != BPT_FILTER_BOX) return e->fail(BPT_ERR_UNSUPPORTED, "filter not implemented (gaussian, box)");
+    e->filter = *f; return BPT_OK;
+}
+extern "C" int bpt_scene_set_sampler(bpt_engine *e, const bpt_sampler *s) {
+    if (!e || !s) return BPT_ERR_INVALID;
+    if (s->type != BPT_SAMPLER_ZSOBOL && s->type != BPT_SAMPLER_INDEPENDENT) return e->fail(BPT_ERR_UNSUPPORTED, "sampler not implemented (zsobol, independent)");
+    if (s->spp <= 0) return e->fail(BPT_ERR_INVALID, "spp must be positive");
+    e->sampler = *s; return BPT_OK;
+}
+extern "C" int bpt_scene_set_integrator(bpt_engine *e, const bpt_integrator *i) {
+    if (!e || !i) return BPT_ERR_INVALID;
+    if (i->light_sampler != BPT_LIGHTSAMPLER_BVH && i->light_sampler != BPT_LIGHTSAMPLER_UNIFORM)
+        return e->fail(BPT_ERR_UNSUPPORTED, "light sampler not implemented (bvh, uniform)");
+    if (i->max_depth < 0 || i->max_depth > 200) return e->fail(BPT_ERR_INVALID, "bad maxdepth");
+    e->integ = *i; return BPT_OK;
+}
+extern "C" int bpt_scene_set_materials(bpt_engine *e, const bpt_material *m, int n) {
+    if (!e || (n > 0 && !m)) return BPT_ERR_INVALID;
+    e->materials.resize(n);
+    for (int i = 0; i < n; ++i) {
+        OwnedMaterial &o = e->materials[i];
+        o.m = m[i];
+        o.reflectance.Set(m[i].reflectance); o.eta.Set(m[i].eta); o.k.Set(m[i].k); o.iface_eta.Set(m[i].iface_eta);
+        o.conductor_eta.Set(m[i].conductor_eta); o.conductor_k.Set(m[i].conductor_k); o.albedo.Set(m[i].albedo);
+    }
+    return BPT_OK;
+}
+extern "C" int bpt_scene_set_area_lights(bpt_engine *e, const bpt_area_light *a, int n) {
+    if (!e || (n > 0 && !a)) return BPT_ERR_INVALID;
+    e->areaLights.resize(n);
+    for (int i = 0; i < n; ++i) { e->areaLights[i].a = a[i]; e->areaLights[i].L.Set(a[i].L); }
+    return BPT_OK;
+}
+extern "C" int bpt_scene_add_mesh(bpt_engine *e, const bpt_mesh *m) {
+    if (!e || !m || !m->P || !m->indices || m->n_vertices <= 0 || m->n_triangles < 0) return e ? e->fail(BPT_ERR_INVALID, "bad mesh") : BPT_ERR_INVALID;
+    for (int i = 0; i < 3 * m->n_triangles; ++i)
+        if (m->indices[i] < 0 || m->indices[i] >= m->n_vertices) return e->fail(BPT_ERR_INVALID, "mesh index out of range");
+    e->meshes.emplace_back();
+    OwnedMesh &o = e->meshes.back();
+    o.m = *m;
+    o.P.assign(m->P, m->P + 3 * (size_t)m->n_vertices);
+    if (m->N) o.N.assign(m->N, m->N + 3 * (size_t)m->n_vertices);
+    if (m->UV) o.UV.assign(m->UV, m->UV + 2 * (size_t)m->n_vertices);
+    o.idx.assign(m->indices, m->indices + 3 * (size_t)m->n_triangles);
+    o.m.P = o.m.N = o.m.UV = nullptr; o.m.indices = nullptr;
+    return BPT_OK;
+}
+extern "C" int bpt_scene_add_instance(bpt_engine *e, const bpt_instance *i) {
+    if (!e || !i) return BPT_ERR_INVALID;
+    e->instances.push_back(*i); return BPT_OK;
+}
+extern "C" int bpt_scene_add_light(bpt_engine *e, const bpt_light *l) {
+    if (!e || !l) return BPT_ERR_INVALID;
+    if (l->type != BPT_LIGHT_UNIFORM_INFINITE && l->type != BPT_LIGHT_IMAGE_INFINITE) return e->fail(BPT_ERR_UNSUPPORTED, "light type not implemented");
+    e->lights.emplace_back();
+    OwnedLight &o = e->lights.back();
+    o.l = *l; o.L.Set(l->L);
+    if (l->image_rgb && l->image_res > 0) o.image.assign(l->image_rgb, l->image_rgb + 3 * (size_t)l->image_res * l->image_res);
+    o.l.image_rgb = nullptr;
+    return BPT_OK;
+}
+extern "C" int bpt_scene_add_medium(bpt_engine *e, const bpt_medium *) { return e ? e->fail(BPT_ERR_UNSUPPORTED, "media are not implemented yet") : BPT_ERR_INVALID; }
+extern "C" int bpt_scene_set_camera_medium(bpt_engine *e, int medium) { if (!e) return BPT_ERR_INVALID; e->cameraMedium = medium; return BPT_OK; }
+
+// ------------------------------------------------------------------------------------------- commit
+static M4 ToM4(const bpt_mat4 &a) { M4 r; std::memcpy(r.m, a.m, sizeof(r.m)); return r; }
+static Mat4 ToMat4(const M4 &a) { Mat4 r; std::memcpy(r.m, a.m, sizeof(r.m)); return r; }
+static bool AllZero(const bpt_mat4 &a) { for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) if (a.m[i][j] != 0) return false; return true; }
+
+extern "C" int bpt_scene_commit(bpt_engine *e) {
+    if (!e) return BPT_ERR_INVALID;
+    if (!e->haveCam || !e->haveFilm) return e->fail(BPT_ERR_INVALID, "camera and film must be set before commit");
+    if (!e->instances.empty()) return e->fail(BPT_ERR_UNSUPPORTED, "object instancing is not implemented yet");
+    ECK(cudaSetDevice(e->device));
+    auto t0 = std::chrono::steady_clock::now();
+    e->committed = false;
+    std::string serr;
+
+    // ---- camera transforms (BasicSceneBuilder::Camera scene.cpp:138-156, CameraTransform cameras.cpp, rendering space = CameraWorld)
+    Xform cameraFromWorld;
+    {
+        M4 cfw = ToM4(e->cam.camera_from_world), wfc;
+        if (AllZero(e->cam.world_from_camera)) { if (!Inverse(cfw, &wfc)) return e->fail(BPT_ERR_INVALID, "singular camera transform"); }
+        else wfc = ToM4(e->cam.world_from_camera);
+        cameraFromWorld = Xform(cfw, wfc);
+    }
+    Xform worldFromCamera = Inverse(cameraFromWorld);
+    Pt3 pCamera = worldFromCamera(Pt3(0, 0, 0));
+    Xform worldFromRender = Translate(Vec3(pCamera.x, pCamera.y, pCamera.z));
+    Xform renderFromWorld = Inverse(worldFromRender);
+    Xform renderFromCamera = renderFromWorld * worldFromCamera;
+
+    // ---- film / filter / sensor (film.cpp FilmBaseParameters, PixelSensor::Create, RGBFilm ctor)
+    const bpt_film &fl = e->film;
+    int pb[4] = {fl.pixel_bounds[0], fl.pixel_bounds[1], fl.pixel_bounds[2], fl.pixel_bounds[3]};
+    if (pb[0] == 0 && pb[1] == 0 && pb[2] == 0 && pb[3] == 0) { pb[0] = 0; pb[1] = fl.xres; pb[2] = 0; pb[3] = fl.yres; }
+    if (pb[0] < 0 || pb[1] > fl.xres || pb[2] < 0 || pb[3] > fl.yres || pb[0] >= pb[1] || pb[2] >= pb[3]) return e->fail(BPT_ERR_INVALID, "bad pixel bounds");
+    DeviceFilm df{};
+    df.xres = fl.xres; df.yres = fl.yres; df.pbx0 = pb[0]; df.pbx1 = pb[1]; df.pby0 = pb[2]; df.pby1 = pb[3];
+    float exposureTime = fl.exposure_time > 0 ? fl.exposure_time : (e->cam.shutter_close - e->cam.shutter_open);
+    if (!(exposureTime > 0)) exposureTime = 1;
+    float iso = fl.iso > 0 ? fl.iso : 100.f;
+    df.imagingRatio = exposureTime * iso / 100;
+    df.maxComponentValue = fl.max_component_value > 0 ? fl.max_component_value : BPT_INFINITY;
+    if (fl.white_balance != 0) return e->fail(BPT_ERR_UNSUPPORTED, "sensor white balance is not implemented");
+    {
+        const std::vector<float> &m = e->tables.F("srgb_rgb_from_xyz");
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) df.outRGBFromSensor[i][j] = m[3 * i + j];   // RGBFromXYZ * identity
+    }
+    df.isGBuffer = fl.type == BPT_FILM_GBUFFER;
+
+    DeviceFilter dflt{};
+    FilterTables ft;
+    dflt.radiusX = e->filter.xradius; dflt.radiusY = e->filter.yradius;
+    if (e->filter.type == BPT_FILTER_GAUSSIAN) {
+        float sigma = e->filter.sigma, rx = e->filter.xradius, ry = e->filter.yradius;
+        float expX = Gaussian(rx, 0, sigma), expY = Gaussian(ry, 0, sigma);
+        ft.nx = int(32 * rx); ft.ny = int(32 * ry);
+        ft.f.resize((size_t)ft.nx * ft.ny);
+        for (int y = 0; y < ft.ny; ++y)
+            for (int x = 0; x < ft.nx; ++x) {
+                float px = Lerp((x + 0.5f) / ft.nx, -rx, rx), py = Lerp((y + 0.5f) / ft.ny, -ry, ry);
+                ft.f[(size_t)y * ft.nx + x] = stdmax(0.f, Gaussian(px, 0, sigma) - expX) * stdmax(0.f, Gaussian(py, 0, sigma) - expY);
+            }
+        BuildPC2D(ft.f, ft.nx, ft.ny, -rx, rx, -ry, ry, &ft);
+        dflt.sampled = 1; dflt.nx = ft.nx; dflt.ny = ft.ny;
+    }
+
+    // ---- projective camera (cameras.h:254-273, PerspectiveCamera::Create cameras.cpp)
+    DeviceCamera dc{};
+    {
+        float frame = e->cam.frame_aspect_ratio > 0 ? e->cam.frame_aspect_ratio : float(fl.xres) / float(fl.yres);
+        float sw[4];
+        if (frame > 1.f) { sw[0] = -frame; sw[1] = frame; sw[2] = -1.f; sw[3] = 1.f; }
+        else { sw[0] = -1.f; sw[1] = 1.f; sw[2] = -1.f / frame; sw[3] = 1.f / frame; }
+        if (e->cam.has_screen_window) for (int i = 0; i < 4; ++i) sw[i] = e->cam.screen_window[i];
+        Xform screenFromCamera = Perspective(e->cam.fov > 0 ? e->cam.fov : 90.f, 1e-2f, 1000.f);
+        Xform NDCFromScreen = Scale(1 / (sw[1] - sw[0]), 1 / (sw[3] - sw[2]), 1) * Translate(Vec3(-sw[0], -sw[3], 0));
+        Xform rasterFromNDC = Scale((float)fl.xres, -(float)fl.yres, 1);
+        Xform rasterFromScreen = rasterFromNDC * NDCFromScreen;
+        Xform screenFromRaster = Inverse(rasterFromScreen);
+        Xform cameraFromRaster = Inverse(screenFromCamera) * screenFromRaster;
+        dc.cameraFromRaster = ToMat4(cameraFromRaster.m);
+        dc.renderFromCamera = ToMat4(renderFromCamera.m);
+        dc.lensRadius = e->cam.lens_radius;
+        dc.focalDistance = e->cam.focal_distance > 0 ? e->cam.focal_distance : 1e6f;
+        dc.type = e->cam.type;
+    }
+
+    // ---- sampler (samplers.h:228-239)
+    SamplerParams sp{};
+    sp.type = e->sampler.type == BPT_SAMPLER_ZSOBOL ? 0 : 1;
+    sp.randomize = e->sampler.randomize;
+    sp.seed = e->sampler.seed;
+    sp.samplesPerPixel = e->sampler.spp;
+    {
+        auto log2i = [](unsigned v) { int l = 0; while (v >>= 1) ++l; return l; };
+        auto roundUpPow2 = [](int v) { int r = 1; while (r < v) r <<= 1; return r; };
+        sp.log2SamplesPerPixel = log2i((unsigned)e->sampler.spp);
+        int res = roundUpPow2(std::max(fl.xres, fl.yres));
+        int log4SamplesPerPixel = (sp.log2SamplesPerPixel + 1) / 2;
+        sp.nBase4Digits = log2i((unsigned)res) + log4SamplesPerPixel;
+    }
+
+    // ---- materials
+    SpecPool spool;
+    std::vector<DeviceMaterial> dmats(e->materials.size());
+    std::fill(e->materialPresent, e->materialPresent + MAT_NTAGS, false);
+    for (size_t i = 0; i < e->materials.size(); ++i) {
+        const OwnedMaterial &om = e->materials[i];
+        DeviceMaterial &dm = dmats[i];
+        std::memset(&dm, 0, sizeof(dm));
+        dm.type = om.m.type;
+        switch (om.m.type) {
+        case BPT_MAT_DIFFUSE:
+            if (om.reflectance.s.kind == BPT_SPEC_NONE) { dm.reflectance.kind = SPEC_CONSTANT; dm.reflectance.c0 = 0.5f; }
+            else if (!MakeSpectrumRec(e, om.reflectance, ST_ALBEDO, spool, &dm.reflectance, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
+            break;
+        case BPT_MAT_INTERFACE: break;
+        default: return e->fail(BPT_ERR_UNSUPPORTED, "material type not implemented yet");
+        }
+    }
+
+    // ---- meshes: transform to render space (TriangleMesh ctor util/mesh.cpp:25-70), build pools and lights
+    std::vector<float4> tri;
+    std::vector<DeviceMesh> dmesh(e->meshes.size());
+    std::vector<int> indexPool;
+    std::vector<float> nPool, uvPool;
+    std::vector<DeviceLight> dlights;
+    std::vector<LightBoundsH> lbounds;
+    size_t totalTris = 0;
+    for (const OwnedMesh &om : e->meshes) totalTris += om.m.n_triangles;
+    if (totalTris == 0) return e->fail(BPT_ERR_INVALID, "scene has no triangles");
+    if (totalTris > (size_t)1 << 30) return e->fail(BPT_ERR_INVALID, "too many triangles");
+    tri.reserve(3 * totalTris);
+    e->haveAreaLights = false;
+    const std::vector<float> &cieY = e->tables.F("cie_y");
+    const std::vector<float> &illum = e->tables.F("srgb_illuminant");
+    for (size_t mi = 0; mi < e->meshes.size(); ++mi) {
+        const OwnedMesh &om = e->meshes[mi];
+        if (om.m.object_id >= 0) return e->fail(BPT_ERR_UNSUPPORTED, "instanced object definitions are not implemented yet");
+        if (om.m.material >= (int)e->materials.size()) return e->fail(BPT_ERR_INVALID, "mesh material index out of range");
+        Xform renderFromObject(Mul(renderFromWorld.m, ToM4(om.m.world_from_object)));   // scene.h:475-477
+        std::vector<Pt3> P(om.m.n_vertices);
+        for (int v = 0; v < om.m.n_vertices; ++v) P[v] = renderFromObject(Pt3(om.P[3 * v], om.P[3 * v + 1], om.P[3 * v + 2]));
+        DeviceMesh &dm = dmesh[mi];
+        dm.material = om.m.material;
+        int matType = om.m.material < 0 ? MAT_INTERFACE : e->materials[om.m.material].m.type;
+        e->materialPresent[matType] = true;
+        bool flip = (om.m.reverse_orientation != 0) ^ renderFromObject.SwapsHandedness();
+        dm.flags = (flip ? 1 : 0) | (!om.N.empty() ? 2 : 0) | (!om.UV.empty() ? 4 : 0);
+        dm.indexOffset = (int)indexPool.size();
+        dm.nOffset = (int)(nPool.size() / 3);
+        dm.uvOffset = (int)(uvPool.size() / 2);
+        dm.mediumInside = om.m.medium_inside; dm.mediumOutside = om.m.medium_outside;
+        if (!om.N.empty() || !om.UV.empty()) indexPool.insert(indexPool.end(), om.idx.begin(), om.idx.end());
+        if (!om.N.empty())
+            for (int v = 0; v < om.m.n_vertices; ++v) {
+                Nrm3 nn = renderFromObject(Nrm3(om.N[3 * v], om.N[3 * v + 1], om.N[3 * v + 2]));
+                if (om.m.reverse_orientation) nn = -nn;
+                nPool.push_back(nn.x); nPool.push_back(nn.y); nPool.push_back(nn.z);
+            }
+        if (!om.UV.empty()) uvPool.insert(uvPool.end(), om.UV.begin(), om.UV.end());
+        // area light (CreateLights scene.cpp; ignored for "interface" material)
+        bool emissive = om.m.area_light >= 0 && matType != MAT_INTERFACE;
+        dm.areaLightBase = emissive ? (int)dlights.size() : -1;
+        SpectrumRec Lrec{};
+        float lightScale = 1, LemitMax = 0;
+        const OwnedAreaLight *al = nullptr;
+        if (emissive) {
+            if (om.m.area_light >= (int)e->areaLights.size()) return e->fail(BPT_ERR_INVALID, "area light index out of range");
+            al = &e->areaLights[om.m.area_light];
+            std::vector<float> dense(kNLambda);
+            if (al->L.s.kind == BPT_SPEC_NONE) dense = illum;
+            else {
+                if (!MakeSpectrumRec(e, al->L, ST_ILLUMINANT, spool, &Lrec, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
+                for (int i = 0; i < kNLambda; ++i) dense[i] = EvalRecAt(Lrec, spool.pool, (float)(kLambdaMin + i));
+            }
+            Lrec.kind = SPEC_DENSE; Lrec.table = spool.addDense(dense);
+            // scale /= SpectrumToPhotometric(L): RGB illuminant spectra use the colour-space illuminant only
+            float photometric = 0;
+            if (al->L.s.kind == BPT_SPEC_RGB || al->L.s.kind == BPT_SPEC_NONE) { for (int i = 0; i < kNLambda; ++i) photometric += cieY[i] * illum[i]; }
+            else { for (int i = 0; i < kNLambda; ++i) photometric += cieY[i] * dense[i]; }
+            lightScale = al->a.scale / photometric;
+            LemitMax = *std::max_element(dense.begin(), dense.end());
+            e->haveAreaLights = true;
+        }
+        unsigned cls = (unsigned)matType | (emissive ? 0x100u : 0u);
+        for (int t = 0; t < om.m.n_triangles; ++t) {
+            Pt3 p0 = P[om.idx[3 * t]], p1 = P[om.idx[3 * t + 1]], p2 = P[om.idx[3 * t + 2]];
+            int gtri = (int)(tri.size() / 3);
+            tri.push_back(make_float4(p0.x, p0.y, p0.z, b2f((uint32_t)mi)));
+            tri.push_back(make_float4(p1.x, p1.y, p1.z, b2f((uint32_t)t)));
+            tri.push_back(make_float4(p2.x, p2.y, p2.z, b2f(cls)));
+            if (emissive) {
+                DeviceLight dl{};
+                dl.type = LIGHT_DIFFUSE_AREA; dl.tri = gtri; dl.twoSided = al->a.two_sided; dl.LemitTable = Lrec.table;
+                float area = 0.5f * Length(Cross(p1 - p0, p2 - p0));
+                float scale = lightScale;
+                if (al->a.power > 0) {
+                    float k_e = 1;
+                    k_e *= (al->a.two_sided ? 2 : 1) * area * kPi;
+                    scale *= al->a.power / k_e;
+                }
+                dl.scale = scale;
+                dlights.push_back(dl);
+                // DiffuseAreaLight::Bounds (lights.cpp) + Triangle::NormalBounds (shapes.cpp:283-298)
+                float phi = LemitMax;
+                phi *= scale * area * kPi;
+                Nrm3 n = Normalize(Nrm3(Cross(p1 - p0, p2 - p0)));
+                if (!om.N.empty()) {
+                    size_t nb = 3 * (size_t)dm.nOffset;
+                    auto NN = [&](int v) { return Nrm3(nPool[nb + 3 * v], nPool[nb + 3 * v + 1], nPool[nb + 3 * v + 2]); };
+                    Nrm3 ns = NN(om.idx[3 * t]) + NN(om.idx[3 * t + 1]) + NN(om.idx[3 * t + 2]);
+                    n = FaceForward(n, ns);
+                } else if (flip) n = n * -1.f;
+                Bounds3 b = Union(Bounds3(p0, p1), p2);
+                lbounds.push_back(LightBoundsH(b, Normalize(V(n)), phi, 1.f /* cone cosTheta */, std::cos(kPi / 2), al->a.two_sided != 0));
+            }
+        }
+    }
+    if (!e->lights.empty()) return e->fail(BPT_ERR_UNSUPPORTED, "infinite lights are not implemented yet");
+    if (dlights.empty()) return e->fail(BPT_ERR_INVALID, "scene has no lights");
+
+    // ---- light sampler (wavefront/integrator.cpp:182-186: uniform when there is exactly one light)
+    LightBVHBuilder lb;
+    DeviceLightSampler dls{};
+    dls.nLights = (int)dlights.size();
+    int lsType = e->integ.light_sampler;
+    if (dlights.size() == 1) lsType = BPT_LIGHTSAMPLER_UNIFORM;
+    dls.type = lsType;
+    if (lsType == BPT_LIGHTSAMPLER_BVH) lb.Build(lbounds);
+    else { lb.bitTrails.assign(dlights.size(), 0); lb.lightInBVH.assign(dlights.size(), 0); }
+    dls.nInfinite = (int)lb.infiniteLights.size();
+    dls.nNodes = (int)lb.nodes.size();
+
+    // ---- upload
+    ECK(e->triPool.upload(tri));
+    ECK(e->dMeshes.upload(dmesh));
+    ECK(e->indexPool.upload(indexPool));
+    ECK(e->nPool.upload(nPool));
+    ECK(e->uvPool.upload(uvPool));
+    ECK(e->specPool.upload(spool.pool));
+    ECK(e->dMaterials.upload(dmats));
+    ECK(e->dLights.upload(dlights));
+    ECK(e->dLightNodes.upload(lb.nodes));
+    ECK(e->dInfinite.upload(lb.infiniteLights));
+    ECK(e->dLightInBVH.upload(lb.lightInBVH));
+    ECK(e->dBitTrails.upload(lb.bitTrails));
+    {
+        std::vector<float> tb;
+        tb.insert(tb.end(), e->tables.F("cie_x").begin(), e->tables.F("cie_x").end());
+        tb.insert(tb.end(), cieY.begin(), cieY.end());
+        tb.insert(tb.end(), e->tables.F("cie_z").begin(), e->tables.F("cie_z").end());
+        tb.insert(tb.end(), illum.begin(), illum.end());
+        ECK(e->dTables.upload(tb));
+    }
+    if (dflt.sampled) {
+        std::vector<float> fb;
+        size_t oFunc = 0; fb.insert(fb.end(), ft.func.begin(), ft.func.end());
+        size_t oCdf = fb.size(); fb.insert(fb.end(), ft.cdf.begin(), ft.cdf.end());
+        size_t oFI = fb.size(); fb.insert(fb.end(), ft.funcInt.begin(), ft.funcInt.end());
+        size_t oMF = fb.size(); fb.insert(fb.end(), ft.mfunc.begin(), ft.mfunc.end());
+        size_t oMC = fb.size(); fb.insert(fb.end(), ft.mcdf.begin(), ft.mcdf.end());
+        size_t oF = fb.size(); fb.insert(fb.end(), ft.f.begin(), ft.f.end());
+        ECK(e->dFilter.upload(fb));
+        dflt.distrib.func = e->dFilter.p + oFunc; dflt.distrib.cdf = e->dFilter.p + oCdf; dflt.distrib.funcInt = e->dFilter.p + oFI;
+        dflt.distrib.mfunc = e->dFilter.p + oMF; dflt.distrib.mcdf = e->dFilter.p + oMC; dflt.distrib.mfuncInt = ft.mfuncInt;
+        dflt.distrib.nu = ft.nx; dflt.distrib.nv = ft.ny;
+        dflt.distrib.min0 = -dflt.radiusX; dflt.distrib.max0 = dflt.radiusX; dflt.distrib.min1 = -dflt.radiusY; dflt.distrib.max1 = dflt.radiusY;
+        dflt.f = e->dFilter.p + oF;
+    }
+
+    // ---- BVH
+    FreeWideBVH(&e->bvh);
+    char berr[256] = {0};
+    auto tb0 = std::chrono::steady_clock::now();
+    if (!BuildWideBVH(e->triPool.p, (int)totalTris, &e->bvh, e->stream, berr)) return e->fail(BPT_ERR_CUDA, berr);
+    ECK(cudaStreamSynchronize(e->stream));
+    auto tb1 = std::chrono::steady_clock::now();
+    e->nTrisTotal = (int)totalTris;
+
+    // ---- path state and queues
+    int nPixPass = (pb[1] - pb[0]) * (pb[3] - pb[2]);
+    int maxPaths = std::max(e->maxPaths, nPixPass);
+    // one pass covers the whole pixel bounds for S samples; S is chosen at render time with S * nPix <= maxPaths
+    e->rc = RenderCtx{};
+    RenderCtx &rc = e->rc;
+    rc.maxPaths = maxPaths;
+    ECK(e->stateF4.alloc((size_t)maxPaths * 12));
+    ECK(e->stateMisc.alloc(maxPaths));
+    ECK(e->stateAux.alloc(maxPaths));
+    float4 *f4 = e->stateF4.p;
+    rc.ps.rayO = f4; rc.ps.rayD = f4 + (size_t)maxPaths; rc.ps.hit = f4 + 2 * (size_t)maxPaths; rc.ps.beta = f4 + 3 * (size_t)maxPaths;
+    rc.ps.r_u = f4 + 4 * (size_t)maxPaths; rc.ps.r_l = f4 + 5 * (size_t)maxPaths; rc.ps.L = f4 + 6 * (size_t)maxPaths;
+    rc.ps.lambda = f4 + 7 * (size_t)maxPaths; rc.ps.lambdaPdf = f4 + 8 * (size_t)maxPaths; rc.ps.ctx0 = f4 + 9 * (size_t)maxPaths;
+    rc.ps.ctx1 = f4 + 10 * (size_t)maxPaths; rc.ps.ctx2 = f4 + 11 * (size_t)maxPaths;
+    rc.ps.misc = e->stateMisc.p; rc.ps.aux = e->stateAux.p;
+    int nQueues = 0;
+    int qIndex[Q_CURSOR_CLOSEST];
+    for (int q = 0; q < Q_CURSOR_CLOSEST; ++q) {
+        bool need = q == Q_RAY0 || q == Q_RAY1 || q == Q_ESCAPED || q == Q_HITLIGHT || (q >= Q_MAT0 && e->materialPresent[q - Q_MAT0]);
+        qIndex[q] = need ? nQueues++ : -1;
+    }
+    ECK(e->queueMem.alloc((size_t)nQueues * maxPaths));
+    for (int q = 0; q < Q_CURSOR_CLOSEST; ++q) rc.queues[q] = qIndex[q] >= 0 ? e->queueMem.p + (size_t)qIndex[q] * maxPaths : nullptr;
+    ECK(e->shadowItems.alloc(maxPaths));
+    rc.shadowItems = e->shadowItems.p;
+    ECK(e->counts.alloc(Q_NCOUNTERS));
+    ECK(cudaMemset(e->counts.p, 0, sizeof(int) * Q_NCOUNTERS));
+    rc.counts = e->counts.p;
+    ECK(e->stats.alloc(8));
+    ECK(cudaMemset(e->stats.p, 0, sizeof(unsigned long long) * 8));
+    rc.stats = e->stats.p;
+    ECK(e->rawCursor.alloc(1));
+    rc.bvh.nodes = e->bvh.nodes; rc.bvh.tris = e->bvh.tris;
+    SceneView &sv = rc.sv;
+    sv.triPool = e->triPool.p; sv.meshes = e->dMeshes.p; sv.indexPool = e->indexPool.p; sv.nPool = e->nPool.p; sv.uvPool = e->uvPool.p;
+    sv.materials = e->dMaterials.p; sv.lights = e->dLights.p; sv.specPool = e->specPool.p;
+    dls.nodes = e->dLightNodes.p; dls.infiniteLights = e->dInfinite.p; dls.bitTrails = e->dBitTrails.p; dls.lightInBVH = e->dLightInBVH.p;
+    sv.ls = dls;
+    sv.allbMin = lb.allLightBounds.pMin; sv.allbMax = lb.allLightBounds.pMax;
+    sv.imageLights = nullptr;
+    sv.cieX = e->dTables.p; sv.cieY = e->dTables.p + kNLambda; sv.cieZ = e->dTables.p + 2 * kNLambda; sv.illumD65 = e->dTables.p + 3 * kNLambda;
+    sv.rgb2specScale = nullptr; sv.rgb2specCoeffs = nullptr;
+    sv.nLights = (int)dlights.size();
+    rc.camera = dc; rc.film = df; rc.filter = dflt; rc.sampler = sp;
+    rc.integ.maxDepth = e->integ.max_depth; rc.integ.regularize = e->integ.regularize;
+    rc.nInfinite = dls.nInfinite;
+    ECK(e->filmPixels.alloc((size_t)fl.xres * fl.yres));
+    ECK(cudaMemset(e->filmPixels.p, 0, sizeof(double4) * (size_t)fl.xres * fl.yres));
+    rc.filmPixels = e->filmPixels.p;
+    ECK(e->filmRGB.alloc(3 * (size_t)fl.xres * fl.yres));
+    ECK(cudaDeviceSynchronize());
+
+    auto t1 = std::chrono::steady_clock::now();
+    e->st = bpt_stats{};
+    e->st.seconds_build = std::chrono::duration<double>(tb1 - tb0).count();
+    e->st.bvh_nodes = e->bvh.nNodes; e->st.bvh_triangles = e->bvh.nTris; e->st.bvh_depth = e->bvh.depth;
+    e->st.bytes_bvh_nodes = (uint64_t)e->bvh.nNodes * 80; e->st.bytes_bvh_tris = (uint64_t)e->bvh.nTris * 48;
+    (void)t0; (void)t1;
+    e->committed = true;
+    return BPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------- rendering
+extern "C" int bpt_render(bpt_engine *e, int first_sample, int n_samples, const int *pixel_bounds, int flags) {
+    if (!e) return BPT_ERR_INVALID;
+    if (!e->committed) return e->fail(BPT_ERR_INVALID, "scene not committed");
+    if (n_samples <= 0 || first_sample < 0) return e->fail(BPT_ERR_INVALID, "bad sample range");
+    ECK(cudaSetDevice(e->device));
+    RenderCtx &rc = e->rc;
+    int x0 = rc.film.pbx0, x1 = rc.film.pbx1, y0 = rc.film.pby0, y1 = rc.film.pby1;
+    if (pixel_bounds) {
+        x0 = std::max(x0, pixel_bounds[0]); x1 = std::min(x1, pixel_bounds[1]);
+        y0 = std::max(y0, pixel_bounds[2]); y1 = std::min(y1, pixel_bounds[3]);
+    }
+    if (x0 >= x1 || y0 >= y1) return BPT_OK;   // empty tile
+    const bool count = flags & 1;
+    cudaStream_t st = e->stream;
+    const int sms = e->smCount;
+    int launches = 0;
+    ECK(cudaEventRecord(e->ev0, st));
+    // scanline bands so that a band of S samples fits in the path-state arrays
+    int width = x1 - x0;
+    int rowsPerBand = std::max(1, std::min(y1 - y0, rc.maxPaths / width));
+    if (width > rc.maxPaths) return e->fail(BPT_ERR_INVALID, "image row exceeds path-state capacity");
+    for (int by0 = y0; by0 < y1; by0 += rowsPerBand) {
+        int by1 = std::min(y1, by0 + rowsPerBand);
+        int nPix = width * (by1 - by0);
+        int S = std::max(1, std::min(n_samples, rc.maxPaths / nPix));
+        for (int s0 = 0; s0 < n_samples; s0 += S) {
+            int ns = std::min(S, n_samples - s0);
+            LaunchResetAll(rc, st); ++launches;
+            LaunchGenerateCameraRays(rc, x0, x1, by0, by1, first_sample + s0, ns, sms, st); ++launches;
+            int cur = Q_RAY0, next = Q_RAY1;
+            int maxDepth = rc.integ.maxDepth;
+            for (int depth = 0; depth <= maxDepth; ++depth) {
+                LaunchResetDepth(rc, next, st); ++launches;
+                LaunchTraceClosest(rc, cur, count, sms, st); ++launches;
+                if (rc.nInfinite > 0) { LaunchHandleEscaped(rc, sms, st); ++launches; }
+                if (e->haveAreaLights) { LaunchHandleEmissive(rc, sms, st); ++launches; }
+                if (depth == maxDepth) break;
+                for (int m = 0; m < MAT_NTAGS; ++m)
+                    if (e->materialPresent[m]) { LaunchShade(rc, m, next, sms, st); ++launches; }
+                LaunchTraceShadow(rc, count, sms, st); ++launches;
+                std::swap(cur, next);
+            }
+            LaunchUpdateFilm(rc, x0, x1, by0, by1, ns, sms, st); ++launches;
+        }
+    }
+    ECK(cudaEventRecord(e->ev1, st));
+    ECK(cudaStreamSynchronize(st));
+    ECK(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->st.seconds_render += ms * 1e-3;
+    e->st.kernel_launches += launches;
+    return BPT_OK;
+}
+
+extern "C" int bpt_film_clear(bpt_engine *e) {
+    if (!e || !e->committed) return BPT_ERR_INVALID;
+    ECK(cudaSetDevice(e->device));
+    ECK(cudaMemset(e->filmPixels.p, 0, sizeof(double4) * e->filmPixels.n));
+    ECK(cudaMemset(e->stats.p, 0, sizeof(unsigned long long) * 8));
+    e->st.seconds_render = 0; e->st.kernel_launches = 0;
+    return BPT_OK;
+}
+extern "C" int bpt_film_read(bpt_engine *e, double *out) {
+    if (!e || !e->committed || !out) return BPT_ERR_INVALID;
+    ECK(cudaSetDevice(e->device));
+    ECK(cudaMemcpy(out, e->filmPixels.p, sizeof(double4) * e->filmPixels.n, cudaMemcpyDeviceToHost));
+    return BPT_OK;
+}
+extern "C" int bpt_film_write(bpt_engine *e, const double *in) {
+    if (!e || !e->committed || !in) return BPT_ERR_INVALID;
+    ECK(cudaSetDevice(e->device));
+    ECK(cudaMemcpy(e->filmPixels.p, in, sizeof(double4) * e->filmPixels.n, cudaMemcpyHostToDevice));
+    return BPT_OK;
+}
+extern "C" int bpt_film_copy_to_device(bpt_engine *e, void *dst) {
+    if (!e || !e->committed || !dst) return BPT_ERR_INVALID;
+    ECK(cudaSetDevice(e->device));
+    ECK(cudaMemcpy(dst, e->filmPixels.p, sizeof(double4) * e->filmPixels.n, cudaMemcpyDeviceToDevice));
+    return BPT_OK;
+}
+extern "C" int bpt_film_copy_from_device(bpt_engine *e, const void *src) {
+    if (!e || !e->committed || !src) return BPT_ERR_INVALID;
+    ECK(cudaSetDevice(e->device));
+    ECK(cudaMemcpy(e->filmPixels.p, src, sizeof(double4) * e->filmPixels.n, cudaMemcpyDeviceToDevice));
+    return BPT_OK;
+}
+extern "C" int bpt_film_resolve(bpt_engine *e, float *rgb) {
+    if (!e || !e->committed || !rgb) return BPT_ERR_INVALID;
+    ECK(cudaSetDevice(e->device));
+    LaunchResolveFilm(e->filmPixels.p, e->rc.film, e->filmRGB.p, e->smCount, e->stream);
+    ECK(cudaStreamSynchronize(e->stream));
+    ECK(cudaMemcpy(rgb, e->filmRGB.p, sizeof(float) * e->filmRGB.n, cudaMemcpyDeviceToHost));
+    return BPT_OK;
+}
+extern "C" int bpt_film_dims(const bpt_engine *e, int *xres, int *yres) {
+    if (!e || !e->haveFilm) return BPT_ERR_INVALID;
+    if (xres) *xres = e->film.xres;
+    if (yres) *yres = e->film.yres;
+    return BPT_OK;
+}
+extern "C" int bpt_get_stats(bpt_engine *e, bpt_stats *out) {
+    if (!e || !out) return BPT_ERR_INVALID;
+    if (e->committed) {
+        unsigned long long h[8];
+        ECK(cudaSetDevice(e->device));
+        ECK(cudaMemcpy(h, e->stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+        e->st.camera_rays = h[0];
+        e->st.indirect_rays = h[1] >= h[0] ? h[1] - h[0] : 0;
+        e->st.shadow_rays = h[2];
+        e->st.nodes_visited = h[3]; e->st.tris_tested = h[4]; e->st.counted_rays = h[5];
+    }
+    *out = e->st;
+    return BPT_OK;
+}
+
+// ------------------------------------------------------------------------------------------- raw rays / probes
+extern "C" int bpt_trace_closest_device(bpt_engine *e, const void *rays_dev, int n, void *hits_dev, int flags) {
+    if (!e || !e->committed || !rays_dev || !hits_dev || n < 0) return BPT_ERR_INVALID;
+    ECK(cudaSetDevice(e->device));
+    LaunchTraceRaw(e->rc.bvh, (const float4 *)rays_dev, n, (float4 *)hits_dev, nullptr, e->rawCursor.p, e->stats.p, (flags & 2) != 0, (flags & 1) != 0,
+                   e->smCount, e->stream);
+    ECK(cudaStreamSynchronize(e->stream));
+    return BPT_OK;
+}
+static int TraceHost(bpt_engine *e, const float *rays, int n, float *hits, float *tOut, int *occ, bool any) {
+    if (!e || !e->committed || !rays || n < 0) return BPT_ERR_INVALID;
+    ECK(cudaSetDevice(e->device));
+    DevBuf<float4> dr, dh; DevBuf<float> dt;
+    ECK(dr.alloc(2 * (size_t)n)); ECK(dh.alloc(n)); ECK(dt.alloc(n));
+    ECK(cudaMemcpy(dr.p, rays, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice));
+    LaunchTraceRaw(e->rc.bvh, dr.p, n, dh.p, dt.p, e->rawCursor.p, e->stats.p, any, false, e->smCount, e->stream);
+    ECK(cudaStreamSynchronize(e->stream));
+    ECK(cudaGetLastError());
+    std::vector<float> hh(4 * (size_t)n);
+    ECK(cudaMemcpy(hh.data(), dh.p, sizeof(float) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    if (hits) std::memcpy(hits, hh.data(), sizeof(float) * 4 * (size_t)n);
+    if (tOut) ECK(cudaMemcpy(tOut, dt.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (occ) for (int i = 0; i < n; ++i) { int prim; std::memcpy(&prim, &hh[4 * (size_t)i], 4); occ[i] = prim >= 0; }
+    return BPT_OK;
+}
+extern "C" int bpt_trace_closest(bpt_engine *e, const float *rays, int n, float *hits, float *t_out) { return TraceHost(e, rays, n, hits, t_out, nullptr, false); }
+extern "C" int bpt_trace_any(bpt_engine *e, const float *rays, int n, int *occluded) { return TraceHost(e, rays, n, nullptr, nullptr, occluded, true); }
+
+extern "C" int bpt_probe_sampler(bpt_engine *e, const int *pxy, const int *sidx, const int *dim, int n, float *o1, float *o2) {
+    if (!e || !e->committed || n <= 0) return BPT_ERR_INVALID;
+    ECK(cudaSetDevice(e->device));
+    DevBuf<int> a, b, c; DevBuf<float> r1, r2;
+    ECK(a.alloc(2 * (size_t)n)); ECK(b.alloc(n)); ECK(c.alloc(n)); ECK(r1.alloc(n)); ECK(r2.alloc(2 * (size_t)n));
+    ECK(cudaMemcpy(a.p, pxy, sizeof(int) * 2 * (size_t)n, cudaMemcpyHostToDevice));
+    ECK(cudaMemcpy(b.p, sidx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+    ECK(cudaMemcpy(c.p, dim, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+    LaunchProbeSampler(e->rc.sampler, a.p, b.p, c.p, n, r1.p, r2.p, e->stream);
+    ECK(cudaStreamSynchronize(e->stream));
+    ECK(cudaMemcpy(o1, r1.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
+    ECK(cudaMemcpy(o2, r2.p, sizeof(float) * 2 * (size_t)n, cudaMemcpyDeviceToHost));
+    return BPT_OK;
+}
+extern "C" int bpt_probe_intersect_triangle(bpt_engine *e, const float *rays, const float *tris, int n, float *out) {
+    if (!e || n <= 0) return BPT_ERR_INVALID;
+    ECK(cudaSetDevice(e->device));
+    DevBuf<float> a, b, c;
+    ECK(a.alloc(7 * (size_t)n)); ECK(b.alloc(9 * (size_t)n)); ECK(c.alloc(5 * (size_t)n));
+    ECK(cudaMemcpy(a.p, rays, sizeof(float) * 7 * (size_t)n, cudaMemcpyHostToDevice));
+    ECK(cudaMemcpy(b.p, tris, sizeof(float) * 9 * (size_t)n, cudaMemcpyHostToDevice));
+    LaunchProbeTri(a.p, b.p, n, c.p, e->stream);
+    ECK(cudaStreamSynchronize(e->stream));
+    ECK(cudaMemcpy(out, c.p, sizeof(float) * 5 * (size_t)n, cudaMemcpyDeviceToHost));
+    return BPT_OK;
+}

@@ -1,0 +1,22 @@
+// kernels.h -- host-callable launchers of the kernels in wavefront.cu.
+#pragma once
+#include "wavefront.cuh"
+
+namespace bpt {
+void UploadSobolTable(const uint32_t *t);
+void LaunchResetAll(const RenderCtx &rc, cudaStream_t st);
+void LaunchResetDepth(const RenderCtx &rc, int nextQ, cudaStream_t st);
+void LaunchGenerateCameraRays(const RenderCtx &rc, int x0, int x1, int y0, int y1, int firstSample, int nSamples, int sms, cudaStream_t st);
+void LaunchTraceClosest(const RenderCtx &rc, int curQ, bool count, int sms, cudaStream_t st);
+void LaunchTraceShadow(const RenderCtx &rc, bool count, int sms, cudaStream_t st);
+void LaunchHandleEmissive(const RenderCtx &rc, int sms, cudaStream_t st);
+void LaunchHandleEscaped(const RenderCtx &rc, int sms, cudaStream_t st);
+void LaunchShade(const RenderCtx &rc, int materialTag, int nextQ, int sms, cudaStream_t st);
+bool ShadeSupported(int materialTag);
+void LaunchUpdateFilm(const RenderCtx &rc, int x0, int x1, int y0, int y1, int nSamples, int sms, cudaStream_t st);
+void LaunchResolveFilm(const double4 *pix, const DeviceFilm &film, float *rgbOut, int sms, cudaStream_t st);
+void LaunchTraceRaw(const BVHView &bvh, const float4 *rays, int n, float4 *hits, float *tOut, int *cursor, unsigned long long *stats,
+                    bool any, bool count, int sms, cudaStream_t st);
+void LaunchProbeSampler(const SamplerParams &sp, const int *pxy, const int *sidx, const int *dim, int n, float *o1, float *o2, cudaStream_t st);
+void LaunchProbeTri(const float *rays, const float *tris, int n, float *out, cudaStream_t st);
+}  // namespace bpt

@@ -1,0 +1,228 @@
+// lights.h -- light sampling on the path (device + host).
+//   LightSampleContext                         base/light.h / lights.h
+//   DiffuseAreaLight::L / SampleLi / PDF_Li     lights.h:438-456, lights.cpp:739-767
+//   CompactLightBounds::Importance              lightsamplers.h:144-200
+//   BVHLightSampler::Sample / PMF               lightsamplers.h:267-353
+//   UniformLightSampler                         lightsamplers.h:27-55
+//   ImageInfiniteLight / UniformInfiniteLight   lights.h:500-628, lights.cpp
+#pragma once
+#include "scene.h"
+#include "shapes.h"
+
+namespace bpt {
+
+struct LightSampleContext {
+    Pt3i pi;
+    Nrm3 n, ns;
+    BPT_HD Pt3 p() const { return pi.p(); }
+};
+
+// Everything the kernels need to reach scene data
+struct SceneView {
+    const float4 *triPool;           // 3 x float4 per triangle, ORIGINAL order (p0.w = meshId, p1.w = triIndex)
+    const DeviceMesh *meshes;
+    const int *indexPool;
+    const float *nPool;              // xyz triples
+    const float *uvPool;             // uv pairs
+    const DeviceMaterial *materials;
+    const DeviceLight *lights;
+    const float *specPool;           // dense tables / piecewise data
+    DeviceLightSampler ls;
+    Pt3 allbMin, allbMax;            // BVHLightSampler::allLightBounds
+    const DeviceImageLight *imageLights;
+    const float *cieX, *cieY, *cieZ; // 471-entry densely sampled matching functions
+    const float *illumD65;           // sRGB colour space illuminant (densely sampled)
+    const float *rgb2specScale;      // 64 z-nodes
+    const float *rgb2specCoeffs;     // [3][64][64][64][3]
+    int nLights;
+};
+
+#if defined(__CUDACC__)
+BPT_D Pt3 ldP3(const float4 *p) { float4 v = __ldg(p); return Pt3(v.x, v.y, v.z); }
+#endif
+
+struct TriData { Pt3 p0, p1, p2; TriAttribs a; int mesh, triIndex; };
+
+BPT_HD TriData LoadTriangle(const SceneView &sv, int tri) {
+    TriData td;
+    const float4 *t = sv.triPool + (size_t)tri * 3;
+    float4 a = t[0], b = t[1], c = t[2];
+    td.p0 = Pt3(a.x, a.y, a.z); td.p1 = Pt3(b.x, b.y, b.z); td.p2 = Pt3(c.x, c.y, c.z);
+    td.mesh = (int)f2b(a.w);
+    td.triIndex = (int)f2b(b.w);
+    const DeviceMesh &m = sv.meshes[td.mesh];
+    td.a.flipNormal = m.flags & 1;
+    td.a.hasN = (m.flags & 2) != 0;
+    td.a.hasUV = (m.flags & 4) != 0;
+    if (td.a.hasN || td.a.hasUV) {
+        const int *v = sv.indexPool + m.indexOffset + 3 * td.triIndex;
+        int v0 = v[0], v1 = v[1], v2 = v[2];
+        if (td.a.hasN) {
+            const float *n = sv.nPool + 3 * (size_t)m.nOffset;
+            td.a.n0 = Nrm3(n[3 * v0], n[3 * v0 + 1], n[3 * v0 + 2]);
+            td.a.n1 = Nrm3(n[3 * v1], n[3 * v1 + 1], n[3 * v1 + 2]);
+            td.a.n2 = Nrm3(n[3 * v2], n[3 * v2 + 1], n[3 * v2 + 2]);
+        }
+        if (td.a.hasUV) {
+            const float *uv = sv.uvPool + 2 * (size_t)m.uvOffset;
+            td.a.uv0 = Vec2(uv[2 * v0], uv[2 * v0 + 1]);
+            td.a.uv1 = Vec2(uv[2 * v1], uv[2 * v1 + 1]);
+            td.a.uv2 = Vec2(uv[2 * v2], uv[2 * v2 + 1]);
+        }
+    }
+    return td;
+}
+
+// ---------------------------------------------------------------- DiffuseAreaLight
+BPT_HD Spec AreaLightL(const SceneView &sv, const DeviceLight &light, Nrm3 n, Vec3 w, const Wavelengths &wl) {
+    if (!light.twoSided && Dot(n, w) < 0) return Spec(0.f);
+    return light.scale * DenseSample(sv.specPool + light.LemitTable, wl);
+}
+
+struct LightLiSample { Spec L; Vec3 wi; float pdf; Pt3i pLight; Nrm3 nLight; bool valid; };
+
+BPT_HD LightLiSample AreaLightSampleLi(const SceneView &sv, const DeviceLight &light, const LightSampleContext &ctx, Vec2 u,
+                                       const Wavelengths &wl) {
+    LightLiSample ls;
+    ls.valid = false;
+    TriData td = LoadTriangle(sv, light.tri);
+    ShapeSample ss = TriangleSampleSolidAngle(td.p0, td.p1, td.p2, td.a, ctx.p(), ctx.ns, u);
+    if (!ss.valid || ss.pdf == 0 || LengthSquared(ss.pi.p() - ctx.p()) == 0) return ls;
+    Vec3 wi = Normalize(ss.pi.p() - ctx.p());
+    Spec Le = AreaLightL(sv, light, ss.n, -wi, wl);
+    if (!Le.IsNonZero()) return ls;
+    ls.L = Le; ls.wi = wi; ls.pdf = ss.pdf; ls.pLight = ss.pi; ls.nLight = ss.n; ls.valid = true;
+    return ls;
+}
+BPT_HD float AreaLightPDF_Li(const SceneView &sv, const DeviceLight &light, const LightSampleContext &ctx, Vec3 wi) {
+    TriData td = LoadTriangle(sv, light.tri);
+    return TrianglePDFSolidAngle(td.p0, td.p1, td.p2, td.a, ctx.pi, ctx.n, ctx.ns, wi);
+}
+
+// ---------------------------------------------------------------- infinite lights (filled in with config 3)
+BPT_HD Spec InfiniteLightLe(const SceneView &sv, const DeviceLight &light, Vec3 rd, const Wavelengths &wl) { return Spec(0.f); }
+BPT_HD float InfiniteLightPDF_Li(const SceneView &sv, const DeviceLight &light, const LightSampleContext &ctx, Vec3 wi) { return 0; }
+BPT_HD LightLiSample InfiniteLightSampleLi(const SceneView &sv, const DeviceLight &light, const LightSampleContext &ctx, Vec2 u,
+                                           const Wavelengths &wl) { LightLiSample ls; ls.valid = false; return ls; }
+
+// ---------------------------------------------------------------- light BVH
+BPT_HD float BoundSubtendedCos(Pt3 bmin, Pt3 bmax, Pt3 p) {
+    // BoundSubtendedDirections(b, p).cosTheta  (vecmath.h:1815-1828)
+    Pt3 pCenter = (bmin + bmax) / 2;
+    bool inside = pCenter.x >= bmin.x && pCenter.x <= bmax.x && pCenter.y >= bmin.y && pCenter.y <= bmax.y &&
+                  pCenter.z >= bmin.z && pCenter.z <= bmax.z;
+    float radius = inside ? Distance(pCenter, bmax) : 0;
+    if (DistanceSquared(p, pCenter) < Sqr(radius)) return -1;
+    float sin2ThetaMax = Sqr(radius) / DistanceSquared(pCenter, p);
+    return SafeSqrt(1 - sin2ThetaMax);
+}
+BPT_HD float CosSubClamped(float sinTheta_a, float cosTheta_a, float sinTheta_b, float cosTheta_b) {
+    if (cosTheta_a > cosTheta_b) return 1;
+    return cosTheta_a * cosTheta_b + sinTheta_a * sinTheta_b;
+}
+BPT_HD float SinSubClamped(float sinTheta_a, float cosTheta_a, float sinTheta_b, float cosTheta_b) {
+    if (cosTheta_a > cosTheta_b) return 0;
+    return sinTheta_a * cosTheta_b - cosTheta_a * sinTheta_b;
+}
+BPT_HD float LightBoundsImportance(const DeviceLightBVHNode &b, Pt3 p, Nrm3 n) {
+    float cosTheta_o = b.cosTheta_o, cosTheta_e = b.cosTheta_e;
+    Pt3 pc = (b.bmin + b.bmax) / 2;
+    float d2 = DistanceSquared(p, pc);
+    d2 = stdmax(d2, Length(b.bmax - b.bmin) / 2);
+    Vec3 wi = Normalize(p - pc);
+    float cosTheta_w = Dot(b.w, wi);
+    if (b.twoSided) cosTheta_w = fabsf(cosTheta_w);
+    float sinTheta_w = SafeSqrt(1 - Sqr(cosTheta_w));
+    float cosTheta_b = BoundSubtendedCos(b.bmin, b.bmax, p);
+    float sinTheta_b = SafeSqrt(1 - Sqr(cosTheta_b));
+    float sinTheta_o = SafeSqrt(1 - Sqr(cosTheta_o));
+    float cosTheta_x = CosSubClamped(sinTheta_w, cosTheta_w, sinTheta_o, cosTheta_o);
+    float sinTheta_x = SinSubClamped(sinTheta_w, cosTheta_w, sinTheta_o, cosTheta_o);
+    float cosThetap = CosSubClamped(sinTheta_x, cosTheta_x, sinTheta_b, cosTheta_b);
+    if (cosThetap <= cosTheta_e) return 0;
+    float importance = b.phi * cosThetap / d2;
+    if (n != Nrm3(0, 0, 0)) {
+        float cosTheta_i = AbsDot(wi, n);
+        float sinTheta_i = SafeSqrt(1 - Sqr(cosTheta_i));
+        float cosThetap_i = CosSubClamped(sinTheta_i, cosTheta_i, sinTheta_b, cosTheta_b);
+        importance *= cosThetap_i;
+    }
+    importance = stdmax(importance, 0.f);
+    return importance;
+}
+
+BPT_HD int SampleDiscrete2(const float w[2], float u, float *pmf, float *uRemapped) {
+    float sumWeights = 0;
+    sumWeights += w[0];
+    sumWeights += w[1];
+    float up = u * sumWeights;
+    if (up == sumWeights) up = NextFloatDown(up);
+    int offset = 0;
+    float sum = 0;
+    while (sum + w[offset] <= up) sum += w[offset++];
+    *pmf = w[offset] / sumWeights;
+    *uRemapped = stdmin((up - sum) / w[offset], kOneMinusEpsilon);
+    return offset;
+}
+
+// returns light index or -1
+BPT_HD int LightSamplerSample(const SceneView &sv, const LightSampleContext &ctx, float u, float *pmfOut) {
+    const DeviceLightSampler &ls = sv.ls;
+    if (ls.type == LS_UNIFORM) {
+        if (ls.nLights == 0) return -1;
+        int lightIndex = imin((int)(u * ls.nLights), ls.nLights - 1);
+        *pmfOut = 1.f / ls.nLights;
+        return lightIndex;
+    }
+    float pInfinite = float(ls.nInfinite) / float(ls.nInfinite + (ls.nNodes == 0 ? 0 : 1));
+    if (u < pInfinite) {
+        u /= pInfinite;
+        int index = imin((int)(u * ls.nInfinite), ls.nInfinite - 1);
+        *pmfOut = pInfinite / ls.nInfinite;
+        return ls.infiniteLights[index];
+    }
+    if (ls.nNodes == 0) return -1;
+    Pt3 p = ctx.p();
+    Nrm3 n = ctx.ns;
+    u = stdmin((u - pInfinite) / (1 - pInfinite), kOneMinusEpsilon);
+    int nodeIndex = 0;
+    float pmf = 1 - pInfinite;
+    while (true) {
+        const DeviceLightBVHNode &node = ls.nodes[nodeIndex];
+        if (!node.isLeaf) {
+            float ci[2] = {LightBoundsImportance(ls.nodes[nodeIndex + 1], p, n),
+                           LightBoundsImportance(ls.nodes[node.childOrLightIndex], p, n)};
+            if (ci[0] == 0 && ci[1] == 0) return -1;
+            float nodePMF;
+            int child = SampleDiscrete2(ci, u, &nodePMF, &u);
+            pmf *= nodePMF;
+            nodeIndex = (child == 0) ? (nodeIndex + 1) : node.childOrLightIndex;
+        } else {
+            if (nodeIndex > 0 || LightBoundsImportance(node, p, n) > 0) { *pmfOut = pmf; return node.childOrLightIndex; }
+            return -1;
+        }
+    }
+}
+
+BPT_HD float LightSamplerPMF(const SceneView &sv, const LightSampleContext &ctx, int light) {
+    const DeviceLightSampler &ls = sv.ls;
+    if (ls.type == LS_UNIFORM) return ls.nLights == 0 ? 0.f : 1.f / ls.nLights;
+    if (!ls.lightInBVH[light]) return 1.f / (ls.nInfinite + (ls.nNodes == 0 ? 0 : 1));
+    uint32_t bitTrail = ls.bitTrails[light];
+    Pt3 p = ctx.p();
+    Nrm3 n = ctx.ns;
+    float pInfinite = float(ls.nInfinite) / float(ls.nInfinite + (ls.nNodes == 0 ? 0 : 1));
+    float pmf = 1 - pInfinite;
+    int nodeIndex = 0;
+    while (true) {
+        const DeviceLightBVHNode &node = ls.nodes[nodeIndex];
+        if (node.isLeaf) return pmf;
+        float ci[2] = {LightBoundsImportance(ls.nodes[nodeIndex + 1], p, n),
+                       LightBoundsImportance(ls.nodes[node.childOrLightIndex], p, n)};
+        pmf *= ci[bitTrail & 1] / (ci[0] + ci[1]);
+        nodeIndex = (bitTrail & 1) ? node.childOrLightIndex : (nodeIndex + 1);
+        bitTrail >>= 1;
+    }
+}
+
+}  // namespace bpt

@@ -1,0 +1,534 @@
+// pbrt_frontend.cpp -- ".pbrt scene in" front end above the C ABI: a from-scratch tokenizer / directive interpreter
+// for the subset of the pbrt-v4 scene format that the hot path consumes.  It plays the role of
+// parser.cpp + BasicSceneBuilder (scene.cpp:105-737) for these directives and feeds bpt_scene_* exactly what
+// BasicScene would hold (CTMs with tracked inverses, parameter lists resolved to POD records).
+//
+// Supported: LookAt Translate Scale Rotate Identity Transform ConcatTransform CoordinateSystem CoordSysTransform
+//            Camera("perspective") Film("rgb"|"gbuffer") Sampler("zsobol"|"independent") PixelFilter("gaussian"|"box")
+//            Integrator("volpath"|"path") Option ColorSpace("srgb") WorldBegin AttributeBegin/End TransformBegin/End
+//            ReverseOrientation Material MakeNamedMaterial NamedMaterial AreaLightSource("diffuse")
+//            LightSource("infinite") Shape("trianglemesh"|"plymesh") ObjectBegin/End ObjectInstance
+//            MakeNamedMedium MediumInterface Include
+// Anything else is an error (never silently ignored), matching the reference's ErrorExit behaviour.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+#include "../../include/b200pt.h"
+#include "xform.h"
+
+using namespace bpt;
+
+namespace {
+
+struct Param {
+    std::string type, name;
+    std::vector<double> nums;
+    std::vector<std::string> strs;
+    std::vector<bool> bools;
+    bool used = false;
+};
+struct ParamList {
+    std::vector<Param> p;
+    Param *find(const std::string &name) { for (auto &q : p) if (q.name == name) { q.used = true; return &q; } return nullptr; }
+    float f(const std::string &n, float d) { Param *q = find(n); return (q && !q->nums.empty()) ? (float)q->nums[0] : d; }
+    int i(const std::string &n, int d) { Param *q = find(n); return (q && !q->nums.empty()) ? (int)q->nums[0] : d; }
+    bool b(const std::string &n, bool d) { Param *q = find(n); return (q && !q->bools.empty()) ? (bool)q->bools[0] : d; }
+    std::string s(const std::string &n, const std::string &d) { Param *q = find(n); return (q && !q->strs.empty()) ? q->strs[0] : d; }
+    std::string unused() const { for (auto &q : p) if (!q.used) return q.type + " " + q.name; return ""; }
+};
+
+struct Tokenizer {
+    std::string buf; size_t pos = 0; std::string file; int line = 1;
+    bool load(const std::string &path) {
+        std::ifstream in(path, std::ios::binary);
+        if (!in) return false;
+        std::stringstream ss; ss << in.rdbuf(); buf = ss.str(); file = path; return true;
+    }
+    // returns false at EOF.  quoted: token was a "string"
+    bool next(std::string *tok, bool *quoted) {
+        while (pos < buf.size()) {
+            char c = buf[pos];
+            if (c == '\n') { ++line; ++pos; }
+            else if (c == ' ' || c == '\t' || c == '\r') ++pos;
+            else if (c == '#') { while (pos < buf.size() && buf[pos] != '\n') ++pos; }
+            else break;
+        }
+        if (pos >= buf.size()) return false;
+        char c = buf[pos];
+        *quoted = false;
+        if (c == '"') {
+            size_t e = buf.find('"', pos + 1);
+            if (e == std::string::npos) e = buf.size();
+            *tok = buf.substr(pos + 1, e - pos - 1); pos = e + 1; *quoted = true; return true;
+        }
+        if (c == '[' || c == ']') { *tok = std::string(1, c); ++pos; return true; }
+        size_t s = pos;
+        while (pos < buf.size() && !strchr(" \t\r\n\"[]#", buf[pos])) ++pos;
+        *tok = buf.substr(s, pos - s);
+        return true;
+    }
+};
+
+struct GState {
+    Xform ctm;
+    bool reverseOrientation = false;
+    int material = 0;
+    int areaLight = -1;
+    std::string mediumInside, mediumOutside;
+};
+
+struct MeshRec {
+    std::vector<float> P, N, UV; std::vector<int> idx;
+    bpt_mesh m;
+};
+
+struct Frontend {
+    bpt_engine *e;
+    std::string err;
+    std::string baseDir;
+    GState gs;
+    std::vector<GState> stack;
+    std::vector<Xform> xstack;
+    std::map<std::string, Xform> namedCS;
+    bool inWorld = false;
+    bpt_camera cam{}; bool haveCam = false;
+    bpt_film film{}; bpt_filter filter{}; bpt_sampler sampler{}; bpt_integrator integ{};
+    bool haveFilter = false, haveSampler = false, haveInteg = false;
+    std::vector<bpt_material> materials;
+    std::vector<std::unique_ptr<std::vector<float>>> sampleStore;
+    std::map<std::string, int> namedMaterials;
+    std::vector<bpt_area_light> areaLights;
+    std::vector<std::unique_ptr<MeshRec>> meshes;
+    std::vector<bpt_instance> instances;
+    std::vector<bpt_light> lights;
+    std::vector<std::unique_ptr<std::vector<float>>> imageStore;
+    std::map<std::string, int> objectIds;
+    int curObject = -1;
+    int seedOption = 0;
+    int sppOverride = 0;
+
+    bool fail(const Tokenizer &t, const std::string &m) { err = t.file + ":" + std::to_string(t.line) + ": " + m; return false; }
+
+    static bpt_mat4 ToB(const M4 &a) { bpt_mat4 r; std::memcpy(r.m, a.m, sizeof(r.m)); return r; }
+
+    bool getSpectrum(ParamList &pl, const std::string &name, bpt_spectrum *out) {
+        std::memset(out, 0, sizeof(*out));
+        Param *q = pl.find(name);
+        if (!q) { out->kind = BPT_SPEC_NONE; return true; }
+        if (q->type == "rgb" && q->nums.size() == 3) { out->kind = BPT_SPEC_RGB; for (int k = 0; k < 3; ++k) out->rgb[k] = (float)q->nums[k]; return true; }
+        if (q->type == "float" && q->nums.size() == 1) { out->kind = BPT_SPEC_CONSTANT; out->value = (float)q->nums[0]; return true; }
+        if (q->type == "spectrum") {
+            if (!q->strs.empty()) { out->kind = BPT_SPEC_NAMED; std::strncpy(out->name, q->strs[0].c_str(), sizeof(out->name) - 1); return true; }
+            if (q->nums.size() >= 2 && q->nums.size() % 2 == 0) {
+                sampleStore.emplace_back(new std::vector<float>(q->nums.begin(), q->nums.end()));
+                out->kind = BPT_SPEC_SAMPLED; out->samples = sampleStore.back()->data(); out->n_samples = (int)q->nums.size() / 2; return true;
+            }
+        }
+        if (q->type == "blackbody" && q->nums.size() == 1) { out->kind = BPT_SPEC_BLACKBODY; out->value = (float)q->nums[0]; return true; }
+        err = "parameter \"" + name + "\": unsupported spectrum specification (type " + q->type + ")";
+        return false;
+    }
+
+    bool makeMaterial(const std::string &type, ParamList &pl, bpt_material *m) {
+        std::memset(m, 0, sizeof(*m));
+        m->uroughness = m->vroughness = m->iface_uroughness = m->iface_vroughness = -1;
+        if (type == "diffuse") {
+            m->type = BPT_MAT_DIFFUSE;
+            return getSpectrum(pl, "reflectance", &m->reflectance);
+        }
+        if (type == "interface" || type == "none" || type == "") { m->type = BPT_MAT_INTERFACE; return true; }
+        if (type == "conductor") {
+            m->type = BPT_MAT_CONDUCTOR;
+            if (!getSpectrum(pl, "eta", &m->eta) || !getSpectrum(pl, "k", &m->k) || !getSpectrum(pl, "reflectance", &m->reflectance)) return false;
+            m->roughness = pl.f("roughness", 0.f);
+            m->uroughness = pl.f("uroughness", m->roughness); m->vroughness = pl.f("vroughness", m->roughness);
+            m->remap_roughness = pl.b("remaproughness", true);
+            return true;
+        }
+        if (type == "dielectric") {
+            m->type = BPT_MAT_DIELECTRIC;
+            if (!getSpectrum(pl, "eta", &m->eta)) return false;
+            m->roughness = pl.f("roughness", 0.f);
+            m->uroughness = pl.f("uroughness", m->roughness); m->vroughness = pl.f("vroughness", m->roughness);
+            m->remap_roughness = pl.b("remaproughness", true);
+            return true;
+        }
+        if (type == "coatedconductor") {
+            m->type = BPT_MAT_COATED_CONDUCTOR;
+            if (!getSpectrum(pl, "interface.eta", &m->iface_eta) || !getSpectrum(pl, "conductor.eta", &m->conductor_eta) ||
+                !getSpectrum(pl, "conductor.k", &m->conductor_k) || !getSpectrum(pl, "reflectance", &m->reflectance) ||
+                !getSpectrum(pl, "albedo", &m->albedo)) return false;
+            m->iface_roughness = pl.f("interface.roughness", 0.f);
+            m->iface_uroughness = pl.f("interface.uroughness", m->iface_roughness); m->iface_vroughness = pl.f("interface.vroughness", m->iface_roughness);
+            m->roughness = pl.f("conductor.roughness", 0.f);
+            m->uroughness = pl.f("conductor.uroughness", m->roughness); m->vroughness = pl.f("conductor.vroughness", m->roughness);
+            m->thickness = pl.f("thickness", .01f);
+            m->g = pl.f("g", 0.f);
+            m->max_depth = pl.i("maxdepth", 10); m->n_samples = pl.i("nsamples", 1);
+            m->remap_roughness = pl.b("remaproughness", true);
+            return true;
+        }
+        err = "material \"" + type + "\" is not supported by this front end";
+        return false;
+    }
+
+    bool readPLY(const std::string &path, MeshRec *mr) {
+        std::ifstream in(path, std::ios::binary);
+        if (!in) { err = "cannot open PLY file " + path; return false; }
+        std::string line;
+        std::getline(in, line);
+        if (line.substr(0, 3) != "ply") { err = path + ": not a PLY file"; return false; }
+        bool binary = false;
+        int nVerts = 0, nFaces = 0;
+        struct Prop { std::string name, type, listCount, listItem; bool isList; };
+        std::vector<Prop> vprops, fprops;
+        int cur = 0;
+        while (std::getline(in, line)) {
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            std::istringstream ls(line);
+            std::string w; ls >> w;
+            if (w == "format") { std::string f; ls >> f; if (f == "binary_little_endian") binary = true; else if (f == "ascii") binary = false; else { err = path + ": unsupported PLY format " + f; return false; } }
+            else if (w == "element") { std::string n; int c; ls >> n >> c; if (n == "vertex") { nVerts = c; cur = 1; } else if (n == "face") { nFaces = c; cur = 2; } else cur = 3; }
+            else if (w == "property") {
+                Prop p; std::string t; ls >> t;
+                if (t == "list") { p.isList = true; ls >> p.listCount >> p.listItem >> p.name; } else { p.isList = false; p.type = t; ls >> p.name; }
+                if (cur == 1) vprops.push_back(p); else if (cur == 2) fprops.push_back(p);
+            } else if (w == "end_header") break;
+        }
+        auto tsize = [](const std::string &t) { if (t == "float" || t == "float32" || t == "int" || t == "int32" || t == "uint" || t == "uint32") return 4; if (t == "double" || t == "float64") return 8; if (t == "uchar" || t == "uint8" || t == "char" || t == "int8") return 1; if (t == "short" || t == "int16" || t == "ushort" || t == "uint16") return 2; return 0; };
+        auto readNum = [&](const std::string &t, double *out) -> bool {
+            if (!binary) { in >> *out; return (bool)in; }
+            char b[8]; int sz = tsize(t); if (!sz) return false; in.read(b, sz); if (!in) return false;
+            if (t == "float" || t == "float32") { float v; memcpy(&v, b, 4); *out = v; }
+            else if (t == "double" || t == "float64") { double v; memcpy(&v, b, 8); *out = v; }
+            else if (t == "int" || t == "int32") { int32_t v; memcpy(&v, b, 4); *out = v; }
+            else if (t == "uint" || t == "uint32") { uint32_t v; memcpy(&v, b, 4); *out = v; }
+            else if (t == "uchar" || t == "uint8") { *out = (unsigned char)b[0]; }
+            else if (t == "char" || t == "int8") { *out = (signed char)b[0]; }
+            else if (t == "short" || t == "int16") { int16_t v; memcpy(&v, b, 2); *out = v; }
+            else { uint16_t v; memcpy(&v, b, 2); *out = v; }
+            return true;
+        };
+        bool hasN = false, hasUV = false;
+        for (auto &p : vprops) { if (p.name == "nx") hasN = true; if (p.name == "u" || p.name == "s") hasUV = true; }
+        mr->P.resize(3 * (size_t)nVerts); if (hasN) mr->N.resize(3 * (size_t)nVerts); if (hasUV) mr->UV.resize(2 * (size_t)nVerts);
+        for (int v = 0; v < nVerts; ++v)
+            for (auto &p : vprops) {
+                double d; if (!readNum(p.type, &d)) { err = path + ": truncated vertex data"; return false; }
+                float f = (float)d;
+                if (p.name == "x") mr->P[3 * v] = f; else if (p.name == "y") mr->P[3 * v + 1] = f; else if (p.name == "z") mr->P[3 * v + 2] = f;
+                else if (p.name == "nx") mr->N[3 * v] = f; else if (p.name == "ny") mr->N[3 * v + 1] = f; else if (p.name == "nz") mr->N[3 * v + 2] = f;
+                else if (p.name == "u" || p.name == "s") mr->UV[2 * v] = f; else if (p.name == "v" || p.name == "t") mr->UV[2 * v + 1] = f;
+            }
+        for (int f = 0; f < nFaces; ++f)
+            for (auto &p : fprops) {
+                if (!p.isList) { double d; if (!readNum(p.type, &d)) { err = path + ": truncated face data"; return false; } continue; }
+                double cnt; if (!readNum(p.listCount, &cnt)) { err = path + ": truncated face data"; return false; }
+                std::vector<int> v((int)cnt);
+                for (int k = 0; k < (int)cnt; ++k) { double d; if (!readNum(p.listItem, &d)) { err = path + ": truncated face data"; return false; } v[k] = (int)d; }
+                if (p.name == "vertex_indices" || p.name == "vertex_index") {
+                    if (cnt == 3) mr->idx.insert(mr->idx.end(), v.begin(), v.end());
+                    else { err = path + ": only triangle faces are supported (quads become bilinear patches in pbrt)"; return false; }
+                }
+            }
+        return true;
+    }
+
+    bool shape(const std::string &type, ParamList &pl) {
+        std::unique_ptr<MeshRec> mr(new MeshRec);
+        if (type == "trianglemesh") {
+            Param *P = pl.find("P");
+            if (!P || P->nums.size() % 3) { err = "trianglemesh: missing or bad \"P\""; return false; }
+            mr->P.assign(P->nums.begin(), P->nums.end());
+            Param *I = pl.find("indices");
+            if (I) mr->idx.assign(I->nums.begin(), I->nums.end());
+            else if (mr->P.size() == 9) mr->idx = {0, 1, 2};
+            else { err = "trianglemesh: \"indices\" required"; return false; }
+            if (Param *N = pl.find("N")) mr->N.assign(N->nums.begin(), N->nums.end());
+            if (Param *U = pl.find("uv")) mr->UV.assign(U->nums.begin(), U->nums.end());
+            if (!mr->N.empty() && mr->N.size() != mr->P.size()) { err = "trianglemesh: N size mismatch"; return false; }
+            if (!mr->UV.empty() && mr->UV.size() / 2 != mr->P.size() / 3) { err = "trianglemesh: uv size mismatch"; return false; }
+        } else if (type == "plymesh") {
+            std::string fn = pl.s("filename", "");
+            if (fn.empty()) { err = "plymesh: missing filename"; return false; }
+            if (fn[0] != '/') fn = baseDir + "/" + fn;
+            if (!readPLY(fn, mr.get())) return false;
+        } else { err = "shape \"" + type + "\" is not supported (triangle meshes only)"; return false; }
+        if (pl.find("alpha")) { err = "alpha textures are not supported"; return false; }
+        std::memset(&mr->m, 0, sizeof(mr->m));
+        mr->m.n_vertices = (int)mr->P.size() / 3; mr->m.n_triangles = (int)mr->idx.size() / 3;
+        mr->m.world_from_object = ToB(gs.ctm.m);
+        mr->m.reverse_orientation = gs.reverseOrientation;
+        mr->m.material = (materials[gs.material].type == BPT_MAT_INTERFACE) ? -1 : gs.material;
+        mr->m.area_light = gs.areaLight;
+        mr->m.medium_inside = mr->m.medium_outside = -1;
+        mr->m.object_id = curObject;
+        if (curObject >= 0 && gs.areaLight >= 0) { err = "area lights are not supported with object instancing"; return false; }
+        meshes.push_back(std::move(mr));
+        return true;
+    }
+
+    bool directive(Tokenizer &t, const std::string &d, std::vector<std::string> &args, ParamList &pl);
+    bool parseFile(const std::string &path);
+    bool finish();
+};
+
+bool Frontend::parseFile(const std::string &path) {
+    Tokenizer t;
+    if (!t.load(path)) { err = "cannot open " + path; return false; }
+    std::string tok; bool q;
+    bool have = t.next(&tok, &q);
+    while (have) {
+        if (q) return fail(t, "unexpected string \"" + tok + "\"");
+        std::string d = tok;
+        std::vector<std::string> args;   // positional args (numbers or the type string)
+        ParamList pl;
+        // collect until next bare identifier that starts with an uppercase letter
+        have = t.next(&tok, &q);
+        // positional part
+        while (have) {
+            if (q) {
+                // either the directive's type string (first quoted, no space) or a param declaration "type name"
+                if (tok.find(' ') == std::string::npos && pl.p.empty() && args.empty() && d != "Include" && d != "CoordinateSystem" && d != "CoordSysTransform" &&
+                    d != "NamedMaterial" && d != "ObjectBegin" && d != "ObjectInstance" && d != "MediumInterface" && d != "ColorSpace" && d != "Option") { args.push_back(tok); }
+                else if (tok.find(' ') == std::string::npos) args.push_back(tok);
+                else {
+                    Param p;
+                    std::istringstream ss(tok); ss >> p.type >> p.name;
+                    std::string v; bool vq;
+                    if (!t.next(&v, &vq)) return fail(t, "premature EOF in parameter list");
+                    auto addVal = [&](const std::string &s, bool sq) {
+                        if (sq) p.strs.push_back(s);
+                        else if (s == "true") p.bools.push_back(true);
+                        else if (s == "false") p.bools.push_back(false);
+                        else p.nums.push_back(std::strtod(s.c_str(), nullptr));
+                    };
+                    if (!vq && v == "[") {
+                        while (true) {
+                            if (!t.next(&v, &vq)) return fail(t, "premature EOF in parameter list");
+                            if (!vq && v == "]") break;
+                            addVal(v, vq);
+                        }
+                    } else addVal(v, vq);
+                    if (p.type == "bool" && p.bools.empty() && !p.strs.empty()) { for (auto &s : p.strs) p.bools.push_back(s == "true"); }
+                    pl.p.push_back(p);
+                }
+                have = t.next(&tok, &q);
+            } else if (tok == "[") {
+                while (true) { if (!(have = t.next(&tok, &q))) return fail(t, "premature EOF"); if (!q && tok == "]") break; args.push_back(tok); }
+                have = t.next(&tok, &q);
+            } else if (std::isupper((unsigned char)tok[0])) break;
+            else { args.push_back(tok); have = t.next(&tok, &q); }
+        }
+        if (!directive(t, d, args, pl)) { if (err.find(t.file) == std::string::npos) fail(t, d + ": " + err); return false; }
+        std::string un = pl.unused();
+        if (!un.empty() && d != "Film" && d != "Camera") return fail(t, d + ": parameter \"" + un + "\" is not supported by this front end");
+    }
+    return true;
+}
+
+bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::string> &a, ParamList &pl) {
+    auto num = [&](size_t i) { return i < a.size() ? (float)std::strtod(a[i].c_str(), nullptr) : 0.f; };
+    auto need = [&](size_t n) { if (a.size() != n) { err = "expected " + std::to_string(n) + " arguments"; return false; } return true; };
+    if (d == "LookAt") {
+        if (!need(9)) return false;
+        bool ok;
+        Xform la = LookAt(Pt3(num(0), num(1), num(2)), Pt3(num(3), num(4), num(5)), Vec3(num(6), num(7), num(8)), &ok);
+        if (!ok) { err = "up vector and viewing direction are collinear"; return false; }
+        gs.ctm = gs.ctm * la; return true;
+    }
+    if (d == "Translate") { if (!need(3)) return false; gs.ctm = gs.ctm * Translate(Vec3(num(0), num(1), num(2))); return true; }
+    if (d == "Scale") { if (!need(3)) return false; gs.ctm = gs.ctm * Scale(num(0), num(1), num(2)); return true; }
+    if (d == "Rotate") { if (!need(4)) return false; gs.ctm = gs.ctm * Rotate(num(0), Vec3(num(1), num(2), num(3))); return true; }
+    if (d == "Identity") { gs.ctm = Xform(); return true; }
+    if (d == "Transform" || d == "ConcatTransform") {
+        if (!need(16)) return false;
+        // pbrt: Transpose(SquareMatrix<4>(pstd::MakeSpan(tr, 16)))
+        M4 m;
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) m[i][j] = num(4 * j + i);
+        if (d == "Transform") gs.ctm = Xform(m); else gs.ctm = gs.ctm * Xform(m);
+        return true;
+    }
+    if (d == "CoordinateSystem") { if (a.empty()) { err = "name expected"; return false; } namedCS[a[0]] = gs.ctm; return true; }
+    if (d == "CoordSysTransform") { if (a.empty() || !namedCS.count(a[0])) { err = "unknown coordinate system"; return false; } gs.ctm = namedCS[a[0]]; return true; }
+    if (d == "ReverseOrientation") { gs.reverseOrientation = !gs.reverseOrientation; return true; }
+    if (d == "AttributeBegin") { stack.push_back(gs); return true; }
+    if (d == "AttributeEnd") { if (stack.empty()) { err = "unmatched AttributeEnd"; return false; } gs = stack.back(); stack.pop_back(); return true; }
+    if (d == "TransformBegin") { xstack.push_back(gs.ctm); return true; }
+    if (d == "TransformEnd") { if (xstack.empty()) { err = "unmatched TransformEnd"; return false; } gs.ctm = xstack.back(); xstack.pop_back(); return true; }
+    if (d == "Option") { if (Param *s = pl.find("seed")) seedOption = (int)s->nums[0]; for (auto &q : pl.p) q.used = true; return true; }
+    if (d == "ColorSpace") { if (a.empty() || a[0] != "srgb") { err = "only the srgb colour space is supported"; return false; } return true; }
+    if (d == "Include") { if (a.empty()) { err = "filename expected"; return false; } std::string fn = a[0]; if (fn[0] != '/') fn = baseDir + "/" + fn; return parseFile(fn); }
+    if (d == "Camera") {
+        if (a.empty() || a[0] != "perspective") { err = "only the perspective camera is supported"; return false; }
+        std::memset(&cam, 0, sizeof(cam));
+        cam.type = BPT_CAMERA_PERSPECTIVE;
+        cam.camera_from_world = ToB(gs.ctm.m); cam.world_from_camera = ToB(gs.ctm.mInv);
+        cam.fov = pl.f("fov", 90.f); cam.lens_radius = pl.f("lensradius", 0.f); cam.focal_distance = pl.f("focaldistance", 1e6f);
+        cam.frame_aspect_ratio = pl.f("frameaspectratio", -1.f);
+        if (Param *sw = pl.find("screenwindow")) { if (sw->nums.size() != 4) { err = "screenwindow needs four values"; return false; } cam.has_screen_window = 1; for (int k = 0; k < 4; ++k) cam.screen_window[k] = (float)sw->nums[k]; }
+        cam.shutter_open = pl.f("shutteropen", 0.f); cam.shutter_close = pl.f("shutterclose", 1.f);
+        namedCS["camera"] = Inverse(gs.ctm);
+        haveCam = true; return true;
+    }
+    if (d == "Film") {
+        if (a.empty() || (a[0] != "rgb" && a[0] != "gbuffer")) { err = "only rgb / gbuffer films are supported"; return false; }
+        std::memset(&film, 0, sizeof(film));
+        film.type = a[0] == "rgb" ? BPT_FILM_RGB : BPT_FILM_GBUFFER;
+        film.xres = pl.i("xresolution", 1280); film.yres = pl.i("yresolution", 720);
+        if (Param *pb = pl.find("pixelbounds")) { if (pb->nums.size() != 4) { err = "pixelbounds needs four values"; return false; } for (int k = 0; k < 4; ++k) film.pixel_bounds[k] = (int)pb->nums[k]; }
+        if (Param *cw = pl.find("cropwindow")) {
+            if (cw->nums.size() != 4) { err = "cropwindow needs four values"; return false; }
+            // film.cpp:138-160
+            float c[4]; for (int k = 0; k < 4; ++k) c[k] = (float)cw->nums[k];
+            auto clamp01 = [](float v) { return v < 0 ? 0.f : (v > 1 ? 1.f : v); };
+            float x0 = clamp01(std::min(c[0], c[1])), x1 = clamp01(std::max(c[0], c[1])), y0 = clamp01(std::min(c[2], c[3])), y1 = clamp01(std::max(c[2], c[3]));
+            film.pixel_bounds[0] = (int)std::ceil(film.xres * x0); film.pixel_bounds[1] = (int)std::ceil(film.xres * x1);
+            film.pixel_bounds[2] = (int)std::ceil(film.yres * y0); film.pixel_bounds[3] = (int)std::ceil(film.yres * y1);
+        }
+        film.iso = pl.f("iso", 100.f); film.white_balance = pl.f("whitebalance", 0.f); film.exposure_time = -1;
+        film.max_component_value = pl.f("maxcomponentvalue", -1.f); film.diagonal = pl.f("diagonal", 35.f);
+        std::string sensor = pl.s("sensor", "cie1931");
+        if (sensor != "cie1931") { err = "only the cie1931 sensor is supported"; return false; }
+        pl.s("filename", ""); pl.b("savefp16", true);
+        return true;
+    }
+    if (d == "Sampler") {
+        std::memset(&sampler, 0, sizeof(sampler));
+        std::string ty = a.empty() ? "zsobol" : a[0];
+        if (ty == "zsobol") sampler.type = BPT_SAMPLER_ZSOBOL; else if (ty == "independent") sampler.type = BPT_SAMPLER_INDEPENDENT;
+        else { err = "sampler \"" + ty + "\" is not supported (zsobol, independent)"; return false; }
+        sampler.spp = pl.i("pixelsamples", 16); sampler.seed = pl.i("seed", seedOption);
+        std::string r = pl.s("randomization", "fastowen");
+        sampler.randomize = r == "none" ? BPT_RANDOMIZE_NONE : r == "permutedigits" ? BPT_RANDOMIZE_PERMUTE_DIGITS : r == "owen" ? BPT_RANDOMIZE_OWEN : BPT_RANDOMIZE_FAST_OWEN;
+        haveSampler = true; return true;
+    }
+    if (d == "PixelFilter") {
+        std::memset(&filter, 0, sizeof(filter));
+        std::string ty = a.empty() ? "gaussian" : a[0];
+        if (ty == "gaussian") { filter.type = BPT_FILTER_GAUSSIAN; filter.xradius = pl.f("xradius", 1.5f); filter.yradius = pl.f("yradius", 1.5f); filter.sigma = pl.f("sigma", 0.5f); }
+        else if (ty == "box") { filter.type = BPT_FILTER_BOX; filter.xradius = pl.f("xradius", 0.5f); filter.yradius = pl.f("yradius", 0.5f); }
+        else { err = "pixel filter \"" + ty + "\" is not supported (gaussian, box)"; return false; }
+        haveFilter = true; return true;
+    }
+    if (d == "Integrator") {
+        std::string ty = a.empty() ? "volpath" : a[0];
+        if (ty != "volpath" && ty != "path") { err = "integrator \"" + ty + "\" is not supported (volpath)"; return false; }
+        integ.max_depth = pl.i("maxdepth", 5); integ.regularize = pl.b("regularize", false);
+        std::string ls = pl.s("lightsampler", "bvh");
+        integ.light_sampler = ls == "uniform" ? BPT_LIGHTSAMPLER_UNIFORM : ls == "bvh" ? BPT_LIGHTSAMPLER_BVH : -1;
+        if (integ.light_sampler < 0) { err = "light sampler \"" + ls + "\" is not supported (bvh, uniform)"; return false; }
+        haveInteg = true; return true;
+    }
+    if (d == "WorldBegin") { inWorld = true; gs.ctm = Xform(); namedCS["world"] = gs.ctm; return true; }
+    if (d == "Material") {
+        bpt_material m;
+        if (!makeMaterial(a.empty() ? "diffuse" : a[0], pl, &m)) return false;
+        materials.push_back(m); gs.material = (int)materials.size() - 1; return true;
+    }
+    if (d == "MakeNamedMaterial") {
+        if (a.empty()) { err = "name expected"; return false; }
+        bpt_material m;
+        if (!makeMaterial(pl.s("type", ""), pl, &m)) return false;
+        materials.push_back(m); namedMaterials[a[0]] = (int)materials.size() - 1; return true;
+    }
+    if (d == "NamedMaterial") { if (a.empty() || !namedMaterials.count(a[0])) { err = "unknown named material"; return false; } gs.material = namedMaterials[a[0]]; return true; }
+    if (d == "AreaLightSource") {
+        if (a.empty() || a[0] != "diffuse") { err = "only \"diffuse\" area lights are supported"; return false; }
+        bpt_area_light al; std::memset(&al, 0, sizeof(al));
+        if (!getSpectrum(pl, "L", &al.L)) return false;
+        al.scale = pl.f("scale", 1.f); al.two_sided = pl.b("twosided", false); al.power = pl.f("power", -1.f);
+        if (pl.find("filename")) { err = "image area lights are not supported"; return false; }
+        areaLights.push_back(al); gs.areaLight = (int)areaLights.size() - 1; return true;
+    }
+    if (d == "LightSource") {
+        if (a.empty() || a[0] != "infinite") { err = "only \"infinite\" light sources are supported"; return false; }
+        bpt_light l; std::memset(&l, 0, sizeof(l));
+        l.world_from_light = ToB(gs.ctm.m);
+        if (!getSpectrum(pl, "L", &l.L)) return false;
+        l.scale = pl.f("scale", 1.f); l.illuminance = pl.f("illuminance", -1.f);
+        std::string fn = pl.s("filename", "");
+        if (fn.empty()) l.type = BPT_LIGHT_UNIFORM_INFINITE;
+        else {
+            l.type = BPT_LIGHT_IMAGE_INFINITE;
+            if (fn[0] != '/') fn = baseDir + "/" + fn;
+            // PFM reader (util/image.cpp ReadPFM): RGB, bottom-to-top rows
+            FILE *f = std::fopen(fn.c_str(), "rb");
+            if (!f) { err = "cannot open " + fn; return false; }
+            char hdr[3]; int w, h; float sc;
+            if (std::fscanf(f, "%2s %d %d %f", hdr, &w, &h, &sc) != 4 || std::strcmp(hdr, "PF") != 0 || w != h) { std::fclose(f); err = fn + ": square RGB PFM expected"; return false; }
+            std::fgetc(f);
+            imageStore.emplace_back(new std::vector<float>(3 * (size_t)w * h));
+            std::vector<float> row(3 * (size_t)w);
+            for (int y = h - 1; y >= 0; --y) {
+                if (std::fread(row.data(), 4, row.size(), f) != row.size()) { std::fclose(f); err = fn + ": truncated"; return false; }
+                for (size_t k = 0; k < row.size(); ++k) (*imageStore.back())[(size_t)y * 3 * w + k] = row[k] * std::abs(sc);
+            }
+            std::fclose(f);
+            if (sc > 0) { err = fn + ": big-endian PFM not supported"; return false; }
+            l.image_rgb = imageStore.back()->data(); l.image_res = w;
+        }
+        lights.push_back(l); return true;
+    }
+    if (d == "Shape") { if (a.empty()) { err = "shape type expected"; return false; } return shape(a[0], pl); }
+    if (d == "ObjectBegin") { if (a.empty()) { err = "name expected"; return false; } if (curObject >= 0) { err = "nested ObjectBegin"; return false; } stack.push_back(gs); int id = (int)objectIds.size(); objectIds[a[0]] = id; curObject = id; return true; }
+    if (d == "ObjectEnd") { if (curObject < 0) { err = "unmatched ObjectEnd"; return false; } curObject = -1; gs = stack.back(); stack.pop_back(); return true; }
+    if (d == "ObjectInstance") {
+        if (a.empty() || !objectIds.count(a[0])) { err = "unknown object"; return false; }
+        bpt_instance in; in.object_id = objectIds[a[0]]; in.world_from_instance = ToB(gs.ctm.m); instances.push_back(in); return true;
+    }
+    err = "directive is not supported by this front end";
+    (void)t;
+    return false;
+}
+
+bool Frontend::finish() {
+    if (!haveCam) { err = "scene has no Camera"; return false; }
+    if (film.xres == 0) { film.type = BPT_FILM_RGB; film.xres = 1280; film.yres = 720; film.iso = 100; film.diagonal = 35; film.exposure_time = -1; film.max_component_value = -1; }
+    auto ck = [&](int rc) { if (rc != BPT_OK) { err = bpt_last_error(e); return false; } return true; };
+    if (!ck(bpt_scene_begin(e))) return false;
+    if (!ck(bpt_scene_set_camera(e, &cam)) || !ck(bpt_scene_set_film(e, &film))) return false;
+    if (haveFilter && !ck(bpt_scene_set_filter(e, &filter))) return false;
+    if (haveSampler) { if (sppOverride > 0) sampler.spp = sppOverride; if (!ck(bpt_scene_set_sampler(e, &sampler))) return false; }
+    else if (sppOverride > 0 || seedOption) { bpt_sampler s{BPT_SAMPLER_ZSOBOL, sppOverride > 0 ? sppOverride : 16, seedOption, BPT_RANDOMIZE_FAST_OWEN}; if (!ck(bpt_scene_set_sampler(e, &s))) return false; }
+    if (haveInteg && !ck(bpt_scene_set_integrator(e, &integ))) return false;
+    if (!ck(bpt_scene_set_materials(e, materials.data(), (int)materials.size()))) return false;
+    if (!ck(bpt_scene_set_area_lights(e, areaLights.data(), (int)areaLights.size()))) return false;
+    for (auto &m : meshes) {
+        bpt_mesh bm = m->m;
+        bm.P = m->P.data(); bm.N = m->N.empty() ? nullptr : m->N.data(); bm.UV = m->UV.empty() ? nullptr : m->UV.data(); bm.indices = m->idx.data();
+        if (!ck(bpt_scene_add_mesh(e, &bm))) return false;
+    }
+    for (auto &in : instances) if (!ck(bpt_scene_add_instance(e, &in))) return false;
+    for (auto &l : lights) if (!ck(bpt_scene_add_light(e, &l))) return false;
+    return ck(bpt_scene_commit(e));
+}
+
+}  // namespace
+
+static std::string g_frontendError;
+
+extern "C" int bpt_load_pbrt_ex(bpt_engine *e, const char *path, int spp_override, int seed) {
+    if (!e || !path) return BPT_ERR_INVALID;
+    Frontend fe;
+    fe.e = e;
+    std::string p = path;
+    size_t s = p.find_last_of('/');
+    fe.baseDir = s == std::string::npos ? "." : p.substr(0, s);
+    fe.seedOption = seed; fe.sppOverride = spp_override;
+    // default material (scene.cpp: graphicsState.currentMaterialIndex = 0 -> "diffuse")
+    bpt_material dm; std::memset(&dm, 0, sizeof(dm)); dm.type = BPT_MAT_DIFFUSE;
+    fe.materials.push_back(dm);
+    fe.integ.max_depth = 5; fe.integ.light_sampler = BPT_LIGHTSAMPLER_BVH;
+    if (!fe.parseFile(p) || !fe.finish()) { g_frontendError = fe.err; return BPT_ERR_INVALID; }
+    return BPT_OK;
+}
+extern "C" int bpt_load_pbrt(bpt_engine *e, const char *path) { return bpt_load_pbrt_ex(e, path, 0, 0); }
+extern "C" const char *bpt_frontend_error(void) { return g_frontendError.c_str(); }

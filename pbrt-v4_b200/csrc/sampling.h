@@ -1,0 +1,416 @@
+// sampling.h -- hashing, PCG32, ZSobol / Independent samplers and the sampling routines on the path.
+//
+// Restates (CPU branches, operation for operation):
+//   MurmurHash64A / MixBits / Hash(...)        util/hash.h:20-116
+//   RNG (PCG32)                                util/rng.h
+//   ZSobolSampler, IndependentSampler          samplers.h:225-364, 442-476
+//   SobolSample, FastOwenScrambler             util/lowdiscrepancy.h:166-232
+//   SampleUniformDiskConcentric, SampleCosineHemisphere, SampleUniformTriangle, SampleLinear,
+//   SampleBilinear, BilinearPDF                util/sampling.h:120-160,173-183,325-417
+//   SampleSphericalTriangle, InvertSphericalTriangleSample   util/sampling.cpp
+//   SampleVisibleWavelengths / PDF             util/sampling.h:163-171
+#pragma once
+#include "pmath.h"
+
+namespace bpt {
+
+// ------------------------------------------------------------------ hashing
+BPT_HD uint64_t MurmurHash64A(const uint64_t *words, int len, uint64_t seed) {
+    // `words` holds the key zero-padded to a multiple of 8 bytes; `len` is the key length in bytes.
+    const uint64_t m = 0xc6a4a7935bd1e995ull;
+    const int r = 47;
+    uint64_t h = seed ^ ((uint64_t)len * m);
+    int nfull = len / 8;
+    for (int i = 0; i < nfull; ++i) {
+        uint64_t k = words[i];
+        k *= m; k ^= k >> r; k *= m;
+        h ^= k; h *= m;
+    }
+    int rem = len & 7;
+    if (rem) {
+        // tail bytes key[0..rem-1] occupy the low bytes of the (little-endian) padded word
+        uint64_t t = words[nfull] & ((1ull << (8 * rem)) - 1);
+        h ^= t;
+        h *= m;
+    }
+    h ^= h >> r; h *= m; h ^= h >> r;
+    return h;
+}
+BPT_HD uint64_t MixBits(uint64_t v) {
+    v ^= (v >> 31); v *= 0x7fb5d329728ea185ull;
+    v ^= (v >> 27); v *= 0x81dadef4bc2dd44dull;
+    v ^= (v >> 33);
+    return v;
+}
+BPT_HD uint64_t Hash_i32x2(int a, int b) {   // Hash(int, int)
+    uint64_t w = (uint64_t)(uint32_t)a | ((uint64_t)(uint32_t)b << 32);
+    return MurmurHash64A(&w, 8, 0);
+}
+BPT_HD uint64_t Hash_f32(float a) { uint64_t w = f2b(a); return MurmurHash64A(&w, 4, 0); }
+BPT_HD uint64_t Hash_f32x2(float a, float b) {
+    uint64_t w = (uint64_t)f2b(a) | ((uint64_t)f2b(b) << 32);
+    return MurmurHash64A(&w, 8, 0);
+}
+BPT_HD uint64_t Hash_f32x3(float a, float b, float c) {   // Hash(Point3f) / Hash(Vector3f)
+    uint64_t w[2] = {(uint64_t)f2b(a) | ((uint64_t)f2b(b) << 32), (uint64_t)f2b(c)};
+    return MurmurHash64A(w, 12, 0);
+}
+
+// ------------------------------------------------------------------ PCG32 (util/rng.h)
+struct RNG {
+    uint64_t state, inc;
+    BPT_HD RNG() : state(0x853c49e6748fea9bULL), inc(0xda3e39cb94b95bdbULL) {}
+    BPT_HD RNG(uint64_t seqIndex, uint64_t offset) { SetSequence(seqIndex, offset); }
+    BPT_HD explicit RNG(uint64_t seqIndex) { SetSequence(seqIndex, MixBits(seqIndex)); }
+    BPT_HD void SetSequence(uint64_t sequenceIndex, uint64_t seed) {
+        state = 0u;
+        inc = (sequenceIndex << 1u) | 1u;
+        UniformU32();
+        state += seed;
+        UniformU32();
+    }
+    BPT_HD uint32_t UniformU32() {
+        uint64_t oldstate = state;
+        state = oldstate * 0x5851f42d4c957f2dULL + inc;
+        uint32_t xorshifted = (uint32_t)(((oldstate >> 18u) ^ oldstate) >> 27u);
+        uint32_t rot = (uint32_t)(oldstate >> 59u);
+        return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+    }
+    BPT_HD float UniformFloat() { return stdmin(kOneMinusEpsilon, (float)UniformU32() * 0x1p-32f); }
+    BPT_HD void Advance(int64_t idelta) {
+        uint64_t curMult = 0x5851f42d4c957f2dULL, curPlus = inc, accMult = 1u;
+        uint64_t accPlus = 0u, delta = (uint64_t)idelta;
+        while (delta > 0) {
+            if (delta & 1) { accMult *= curMult; accPlus = accPlus * curMult + curPlus; }
+            curPlus = (curMult + 1) * curPlus;
+            curMult *= curMult;
+            delta /= 2;
+        }
+        state = accMult * state + accPlus;
+    }
+};
+
+// ------------------------------------------------------------------ Sobol' + ZSobol
+// First two 32-bit Sobol' generator matrices, 52 columns each (util/sobolmatrices.cpp; table data is
+// loaded from the data blob by the host and copied into constant memory / this host-side array).
+#if defined(__CUDACC__) && defined(BPT_SOBOL_DEVICE_TABLE)
+__constant__ uint32_t c_sobol32[2 * 52];   // defined by the one translation unit that samples on the device
+#endif
+extern uint32_t h_sobol32[2 * 52];
+BPT_HD const uint32_t *SobolTable() {
+#if defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
+    return c_sobol32;
+#else
+    return h_sobol32;
+#endif
+}
+
+BPT_HD uint32_t ReverseBits32(uint32_t n) {
+#if defined(__CUDA_ARCH__)
+    return __brev(n);
+#else
+    n = (n << 16) | (n >> 16);
+    n = ((n & 0x00ff00ff) << 8) | ((n & 0xff00ff00) >> 8);
+    n = ((n & 0x0f0f0f0f) << 4) | ((n & 0xf0f0f0f0) >> 4);
+    n = ((n & 0x33333333) << 2) | ((n & 0xcccccccc) >> 2);
+    n = ((n & 0x55555555) << 1) | ((n & 0xaaaaaaaa) >> 1);
+    return n;
+#endif
+}
+BPT_HD uint32_t FastOwenScramble(uint32_t v, uint32_t seed) {
+    v = ReverseBits32(v);
+    v ^= v * 0x3d20adea;
+    v += seed;
+    v *= (seed >> 16) | 1;
+    v ^= v * 0x05526c56;
+    v ^= v * 0x53a22864;
+    return ReverseBits32(v);
+}
+enum RandomizeStrategy { RANDOMIZE_NONE = 0, RANDOMIZE_PERMUTE_DIGITS = 1, RANDOMIZE_FAST_OWEN = 2, RANDOMIZE_OWEN = 3 };
+
+BPT_HD uint32_t OwenScramble(uint32_t v, uint32_t seed) {   // lowdiscrepancy.h OwenScrambler
+    if (seed & 1) v ^= 1u << 31;
+    for (int b = 1; b < 32; ++b) {
+        uint32_t mask = (~0u) << (32 - b);
+        if ((uint32_t)MixBits((v & mask) ^ seed) & (1u << b)) v ^= 1u << (31 - b);
+    }
+    return v;
+}
+
+BPT_HD float SobolSampleRand(uint64_t a, int dimension, int randomize, uint32_t hash) {
+    const uint32_t *C = SobolTable() + dimension * 52;
+    uint32_t v = 0;
+    for (int i = 0; a != 0; a >>= 1, i++)
+        if (a & 1) v ^= C[i];
+    if (randomize == RANDOMIZE_PERMUTE_DIGITS) v = hash ^ v;
+    else if (randomize == RANDOMIZE_FAST_OWEN) v = FastOwenScramble(v, hash);
+    else if (randomize == RANDOMIZE_OWEN) v = OwenScramble(v, hash);
+    return stdmin((float)v * 0x1p-32f, kOneMinusEpsilon);
+}
+
+BPT_HD uint64_t LeftShift2(uint64_t x) {
+    x &= 0xffffffff;
+    x = (x ^ (x << 16)) & 0x0000ffff0000ffffull;
+    x = (x ^ (x << 8)) & 0x00ff00ff00ff00ffull;
+    x = (x ^ (x << 4)) & 0x0f0f0f0f0f0f0f0full;
+    x = (x ^ (x << 2)) & 0x3333333333333333ull;
+    x = (x ^ (x << 1)) & 0x5555555555555555ull;
+    return x;
+}
+BPT_HD uint64_t EncodeMorton2(uint32_t x, uint32_t y) { return (LeftShift2(y) << 1) | LeftShift2(x); }
+
+struct SamplerParams {
+    int type;                  // 0 = zsobol, 1 = independent
+    int randomize;             // RandomizeStrategy
+    int seed;
+    int log2SamplesPerPixel;
+    int nBase4Digits;
+    int samplesPerPixel;
+};
+
+// One sampler object per path vertex evaluation: stateless function of (pixel, sampleIndex, dimension).
+struct Sampler {
+    const SamplerParams *sp;
+    uint64_t mortonIndex;
+    int dimension;
+    RNG rng;   // independent sampler only
+    BPT_HD void StartPixelSample(const SamplerParams *params, int px, int py, int index, int dim) {
+        sp = params;
+        dimension = dim;
+        if (sp->type == 0)
+            mortonIndex = (EncodeMorton2((uint32_t)px, (uint32_t)py) << sp->log2SamplesPerPixel) | (uint64_t)index;
+        else {
+            // IndependentSampler::StartPixelSample (samplers.h:457-460): Hash(Point2i p, int seed)
+            uint64_t w[2] = {(uint64_t)(uint32_t)px | ((uint64_t)(uint32_t)py << 32), (uint64_t)(uint32_t)sp->seed};
+            uint64_t h = MurmurHash64A(w, 12, 0);
+            rng.SetSequence(h, MixBits(h));
+            rng.Advance((int64_t)((uint64_t)index * 65536ull + (uint64_t)dim));
+        }
+    }
+    BPT_HD uint64_t GetSampleIndex() const {
+        const uint8_t perm[24][4] = {
+            {0, 1, 2, 3}, {0, 1, 3, 2}, {0, 2, 1, 3}, {0, 2, 3, 1}, {0, 3, 2, 1}, {0, 3, 1, 2},
+            {1, 0, 2, 3}, {1, 0, 3, 2}, {1, 2, 0, 3}, {1, 2, 3, 0}, {1, 3, 2, 0}, {1, 3, 0, 2},
+            {2, 1, 0, 3}, {2, 1, 3, 0}, {2, 0, 1, 3}, {2, 0, 3, 1}, {2, 3, 0, 1}, {2, 3, 1, 0},
+            {3, 1, 2, 0}, {3, 1, 0, 2}, {3, 2, 1, 0}, {3, 2, 0, 1}, {3, 0, 2, 1}, {3, 0, 1, 2}};
+        uint64_t sampleIndex = 0;
+        bool pow2Samples = sp->log2SamplesPerPixel & 1;
+        int lastDigit = pow2Samples ? 1 : 0;
+        for (int i = sp->nBase4Digits - 1; i >= lastDigit; --i) {
+            int digitShift = 2 * i - (pow2Samples ? 1 : 0);
+            int digit = (int)((mortonIndex >> digitShift) & 3);
+            uint64_t higherDigits = mortonIndex >> (digitShift + 2);
+            int p = (int)((MixBits(higherDigits ^ (uint64_t)(0x55555555u * (uint32_t)dimension)) >> 24) % 24);
+            // packed permutation lookup (table lives in registers/constant after unrolling)
+            digit = perm[p][digit];
+            sampleIndex |= (uint64_t)digit << digitShift;
+        }
+        if (pow2Samples) {
+            int digit = (int)(mortonIndex & 1);
+            sampleIndex |= (uint64_t)(digit ^ (int)(MixBits((mortonIndex >> 1) ^ (uint64_t)(0x55555555u * (uint32_t)dimension)) & 1));
+        }
+        return sampleIndex;
+    }
+    BPT_HD float Get1D() {
+        if (sp->type == 1) { ++dimension; return rng.UniformFloat(); }
+        uint64_t sampleIndex = GetSampleIndex();
+        ++dimension;
+        uint32_t sampleHash = (uint32_t)Hash_i32x2(dimension, sp->seed);
+        return SobolSampleRand(sampleIndex, 0, sp->randomize, sampleHash);
+    }
+    BPT_HD Vec2 Get2D() {
+        if (sp->type == 1) { dimension += 2; float a = rng.UniformFloat(); float b = rng.UniformFloat(); return {a, b}; }
+        uint64_t sampleIndex = GetSampleIndex();
+        dimension += 2;
+        uint64_t bits = Hash_i32x2(dimension, sp->seed);
+        return {SobolSampleRand(sampleIndex, 0, sp->randomize, (uint32_t)bits),
+                SobolSampleRand(sampleIndex, 1, sp->randomize, (uint32_t)(bits >> 32))};
+    }
+};
+
+// ------------------------------------------------------------------ sampling routines
+BPT_HD float SampleVisibleWavelengths(float u) { return 538 - 138.888889f * atanhf(0.85691062f - 1.82750197f * u); }
+BPT_HD float VisibleWavelengthsPDF(float lambda) {
+    if (lambda < 360 || lambda > 830) return 0;
+    return 0.0039398042f / Sqr(coshf(0.0072f * (lambda - 538)));
+}
+
+BPT_HD Vec2 SampleUniformDiskConcentric(Vec2 u) {
+    Vec2 uOffset(2 * u.x - 1, 2 * u.y - 1);
+    if (uOffset.x == 0 && uOffset.y == 0) return {0, 0};
+    float theta, r;
+    if (fabsf(uOffset.x) > fabsf(uOffset.y)) {
+        r = uOffset.x;
+        theta = kPiOver4 * (uOffset.y / uOffset.x);
+    } else {
+        r = uOffset.y;
+        theta = kPiOver2 - kPiOver4 * (uOffset.x / uOffset.y);
+    }
+    return {r * cosf(theta), r * sinf(theta)};
+}
+BPT_HD Vec3 SampleCosineHemisphere(Vec2 u) {
+    Vec2 d = SampleUniformDiskConcentric(u);
+    float z = SafeSqrt(1 - Sqr(d.x) - Sqr(d.y));
+    return {d.x, d.y, z};
+}
+BPT_HD float CosineHemispherePDF(float cosTheta) { return cosTheta * kInvPi; }
+
+BPT_HD void SampleUniformTriangle(Vec2 u, float b[3]) {
+    float b0, b1;
+    if (u.x < u.y) { b0 = u.x / 2; b1 = u.y - b0; }
+    else { b1 = u.y / 2; b0 = u.x - b1; }
+    b[0] = b0; b[1] = b1; b[2] = 1 - b0 - b1;
+}
+BPT_HD float SampleLinear(float u, float a, float b) {
+    if (u == 0 && a == 0) return 0;
+    float x = u * (a + b) / (a + sqrtf(Lerp(u, Sqr(a), Sqr(b))));
+    return stdmin(x, kOneMinusEpsilon);
+}
+BPT_HD float BilinearPDF(Vec2 p, const float w[4]) {
+    if (p.x < 0 || p.x > 1 || p.y < 0 || p.y > 1) return 0;
+    if (w[0] + w[1] + w[2] + w[3] == 0) return 1;
+    return 4 * ((1 - p.x) * (1 - p.y) * w[0] + p.x * (1 - p.y) * w[1] + (1 - p.x) * p.y * w[2] + p.x * p.y * w[3]) /
+           (w[0] + w[1] + w[2] + w[3]);
+}
+BPT_HD Vec2 SampleBilinear(Vec2 u, const float w[4]) {
+    Vec2 p;
+    p.y = SampleLinear(u.y, w[0] + w[1], w[2] + w[3]);
+    p.x = SampleLinear(u.x, Lerp(p.y, w[0], w[2]), Lerp(p.y, w[1], w[3]));
+    return p;
+}
+BPT_HD float SphericalTriangleArea(Vec3 a, Vec3 b, Vec3 c) {
+    return fabsf(2 * atan2f(Dot(a, Cross(b, c)), 1 + Dot(a, b) + Dot(a, c) + Dot(b, c)));
+}
+
+// util/sampling.cpp SampleSphericalTriangle.  Returns false for the "{}" (all-zero barycentrics) exits.
+BPT_HD void SampleSphericalTriangle(Pt3 v0, Pt3 v1, Pt3 v2, Pt3 p, Vec2 u, float *pdf, float bary[3]) {
+    *pdf = 0;
+    bary[0] = bary[1] = bary[2] = 0;
+    Vec3 a = v0 - p, b = v1 - p, c = v2 - p;
+    a = Normalize(a); b = Normalize(b); c = Normalize(c);
+    Vec3 n_ab = Cross(a, b), n_bc = Cross(b, c), n_ca = Cross(c, a);
+    if (LengthSquared(n_ab) == 0 || LengthSquared(n_bc) == 0 || LengthSquared(n_ca) == 0) return;
+    n_ab = Normalize(n_ab); n_bc = Normalize(n_bc); n_ca = Normalize(n_ca);
+    float alpha = AngleBetween(n_ab, -n_ca);
+    float beta = AngleBetween(n_bc, -n_ab);
+    float gamma = AngleBetween(n_ca, -n_bc);
+    float A_pi = alpha + beta + gamma;
+    float Ap_pi = Lerp(u.x, kPi, A_pi);
+    float A = A_pi - kPi;
+    *pdf = (A <= 0) ? 0 : 1 / A;
+    float cosAlpha = cosf(alpha), sinAlpha = sinf(alpha);
+    float sinPhi = sinf(Ap_pi) * cosAlpha - cosf(Ap_pi) * sinAlpha;
+    float cosPhi = cosf(Ap_pi) * cosAlpha + sinf(Ap_pi) * sinAlpha;
+    float k1 = cosPhi + cosAlpha;
+    float k2 = sinPhi - sinAlpha * Dot(a, b);
+    float cosBp = (k2 + (DifferenceOfProducts(k2, cosPhi, k1, sinPhi)) * cosAlpha) /
+                  ((SumOfProducts(k2, sinPhi, k1, cosPhi)) * sinAlpha);
+    cosBp = Clampf(cosBp, -1, 1);
+    float sinBp = SafeSqrt(1 - Sqr(cosBp));
+    Vec3 cp = cosBp * a + sinBp * Normalize(GramSchmidt(c, a));
+    float cosTheta = 1 - u.y * (1 - Dot(cp, b));
+    float sinTheta = SafeSqrt(1 - Sqr(cosTheta));
+    Vec3 w = cosTheta * b + sinTheta * Normalize(GramSchmidt(cp, b));
+    Vec3 e1 = v1 - v0, e2 = v2 - v0;
+    Vec3 s1 = Cross(w, e2);
+    float divisor = Dot(s1, e1);
+    if (divisor == 0) { bary[0] = bary[1] = bary[2] = 1.f / 3.f; return; }
+    float invDivisor = 1 / divisor;
+    Vec3 s = p - v0;
+    float b1 = Dot(s, s1) * invDivisor;
+    float b2 = Dot(w, Cross(s, e1)) * invDivisor;
+    b1 = Clampf(b1, 0, 1);
+    b2 = Clampf(b2, 0, 1);
+    if (b1 + b2 > 1) {
+        b1 /= b1 + b2;
+        b2 /= b1 + b2;   // (sic) the reference divides by the already-updated b1 + b2
+    }
+    bary[0] = 1 - b1 - b2; bary[1] = b1; bary[2] = b2;
+}
+
+BPT_HD Vec2 InvertSphericalTriangleSample(Pt3 v0, Pt3 v1, Pt3 v2, Pt3 p, Vec3 w) {
+    Vec3 a = v0 - p, b = v1 - p, c = v2 - p;
+    a = Normalize(a); b = Normalize(b); c = Normalize(c);
+    Vec3 n_ab = Cross(a, b), n_bc = Cross(b, c), n_ca = Cross(c, a);
+    if (LengthSquared(n_ab) == 0 || LengthSquared(n_bc) == 0 || LengthSquared(n_ca) == 0) return {0, 0};
+    n_ab = Normalize(n_ab); n_bc = Normalize(n_bc); n_ca = Normalize(n_ca);
+    float alpha = AngleBetween(n_ab, -n_ca);
+    float beta = AngleBetween(n_bc, -n_ab);
+    float gamma = AngleBetween(n_ca, -n_bc);
+    Vec3 cp = Normalize(Cross(Cross(b, w), Cross(c, a)));
+    if (Dot(cp, a + c) < 0) cp = -cp;
+    float u0;
+    if (Dot(a, cp) > 0.99999847691f) u0 = 0;
+    else {
+        Vec3 n_cpb = Cross(cp, b), n_acp = Cross(a, cp);
+        if (LengthSquared(n_cpb) == 0 || LengthSquared(n_acp) == 0) return {0.5f, 0.5f};
+        n_cpb = Normalize(n_cpb); n_acp = Normalize(n_acp);
+        float Ap = alpha + AngleBetween(n_ab, n_cpb) + AngleBetween(n_acp, -n_cpb) - kPi;
+        float A = alpha + beta + gamma - kPi;
+        u0 = Ap / A;
+    }
+    float u1 = (1 - Dot(w, b)) / (1 - Dot(cp, b));
+    return {Clampf(u0, 0, 1), Clampf(u1, 0, 1)};
+}
+
+// FindInterval (util/math.h:508-519) over a float array with predicate arr[i] <= u
+BPT_HD int FindIntervalLE(const float *arr, int sz, float u) {
+    int size = sz - 2, first = 1;
+    while (size > 0) {
+        int half = size >> 1, middle = first + half;
+        bool pr = arr[middle] <= u;
+        first = pr ? middle + 1 : first;
+        size = pr ? size - (half + 1) : half;
+    }
+    return Clampi(first - 1, 0, sz - 2);
+}
+BPT_HD int FindIntervalLT(const float *arr, int sz, float u) {
+    int size = sz - 2, first = 1;
+    while (size > 0) {
+        int half = size >> 1, middle = first + half;
+        bool pr = arr[middle] < u;
+        first = pr ? middle + 1 : first;
+        size = pr ? size - (half + 1) : half;
+    }
+    return Clampi(first - 1, 0, sz - 2);
+}
+
+// PiecewiseConstant2D stored flat: func[nv][nu], cdf[nv][nu+1], funcInt[nv], then marginal func[nv], cdf[nv+1].
+struct PC2DView {
+    const float *func;       // nv*nu (already |.|)
+    const float *cdf;        // nv*(nu+1)
+    const float *funcInt;    // nv
+    const float *mfunc;      // nv
+    const float *mcdf;       // nv+1
+    float mfuncInt;
+    int nu, nv;
+    float min0, max0, min1, max1;
+};
+BPT_HD float PC1DSample(const float *func, const float *cdf, int n, float funcInt, float mn, float mx, float u,
+                        float *pdf, int *offset) {
+    int o = FindIntervalLE(cdf, n + 1, u);
+    *offset = o;
+    float du = u - cdf[o];
+    if (cdf[o + 1] - cdf[o] > 0) du /= cdf[o + 1] - cdf[o];
+    *pdf = (funcInt > 0) ? func[o] / funcInt : 0;
+    return Lerp((o + du) / n, mn, mx);
+}
+BPT_HD Vec2 PC2DSample(const PC2DView &d, Vec2 u, float *pdf, int *ou, int *ov) {
+    float pdf0, pdf1;
+    float d1 = PC1DSample(d.mfunc, d.mcdf, d.nv, d.mfuncInt, d.min1, d.max1, u.y, &pdf1, ov);
+    float d0 = PC1DSample(d.func + (size_t)(*ov) * d.nu, d.cdf + (size_t)(*ov) * (d.nu + 1), d.nu, d.funcInt[*ov],
+                          d.min0, d.max0, u.x, &pdf0, ou);
+    *pdf = pdf0 * pdf1;
+    return {d0, d1};
+}
+BPT_HD float PC2DPDF(const PC2DView &d, Vec2 pr) {
+    // domain.Offset(pr)
+    float ox = pr.x - d.min0, oy = pr.y - d.min1;
+    if (d.max0 > d.min0) ox /= d.max0 - d.min0;
+    if (d.max1 > d.min1) oy /= d.max1 - d.min1;
+    int iu = Clampi((int)(ox * d.nu), 0, d.nu - 1);
+    int iv = Clampi((int)(oy * d.nv), 0, d.nv - 1);
+    return d.func[(size_t)iv * d.nu + iu] / d.mfuncInt;
+}
+
+}  // namespace bpt

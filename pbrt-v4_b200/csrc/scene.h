@@ -1,0 +1,116 @@
+// scene.h -- POD scene records as they live in HBM (shared by host setup and kernels).
+// Tag values follow the reference's TaggedPointer type lists (tag = position in list):
+//   Material  base/material.h:36-39   Light  base/light.h:40-43   BxDF base/bxdf.h:167-169
+//   Camera    base/camera.h:34        Film   base/film.h:25       Sampler base/sampler.h:40-42
+#pragma once
+#include <cuda_runtime.h>
+#include "pmath.h"
+#include "spectrum.h"
+
+namespace bpt {
+
+enum MaterialTag { MAT_COATED_DIFFUSE = 0, MAT_COATED_CONDUCTOR = 1, MAT_CONDUCTOR = 2, MAT_DIELECTRIC = 3, MAT_DIFFUSE = 4,
+                   MAT_DIFFUSE_TRANSMISSION = 5, MAT_HAIR = 6, MAT_MEASURED = 7, MAT_SUBSURFACE = 8, MAT_THIN_DIELECTRIC = 9,
+                   MAT_MIX = 10, MAT_INTERFACE = 11 /* null material ("interface") */, MAT_NTAGS = 12 };
+enum LightTag { LIGHT_POINT = 0, LIGHT_DISTANT = 1, LIGHT_PROJECTION = 2, LIGHT_GONIOMETRIC = 3, LIGHT_SPOT = 4,
+                LIGHT_DIFFUSE_AREA = 5, LIGHT_UNIFORM_INFINITE = 6, LIGHT_IMAGE_INFINITE = 7, LIGHT_PORTAL_IMAGE_INFINITE = 8 };
+enum LightSamplerTag { LS_UNIFORM = 0, LS_POWER = 1, LS_EXHAUSTIVE = 2, LS_BVH = 3 };
+
+struct Mat4 { float m[4][4]; };
+
+struct DeviceCamera {
+    Mat4 cameraFromRaster;      // ProjectiveCamera::cameraFromRaster (cameras.h:272)
+    Mat4 renderFromCamera;      // CameraTransform::renderFromCamera (start transform; static camera)
+    float lensRadius, focalDistance;
+    int type, pad;
+};
+
+struct DeviceFilm {
+    int xres, yres;
+    int pbx0, pby0, pbx1, pby1;          // pixel bounds
+    float imagingRatio, maxComponentValue;
+    float outRGBFromSensor[3][3];
+    int isGBuffer, pad;
+};
+
+struct DeviceFilter {          // FilterSampler tables (filters.cpp FilterSampler ctor)
+    PC2DView distrib;
+    const float *f;            // ny*nx tabulated filter values
+    int nx, ny;
+    float radiusX, radiusY;
+    int sampled;               // 0: box/triangle analytic sampling not used; 1: FilterSampler
+};
+
+struct DeviceMaterial {
+    int type;                  // MaterialTag
+    int flags;                 // bit0: remaproughness
+    SpectrumRec reflectance;   // diffuse
+    SpectrumRec eta, k;        // conductor (spectral), dielectric eta (eta.kind constant or spectrum)
+    float uroughness, vroughness;
+    // coated conductor
+    float iface_uroughness, iface_vroughness, thickness, g;
+    SpectrumRec iface_eta, albedo;
+    int maxDepth, nSamples;
+    int useReflectance;        // conductor specified by "reflectance" instead of eta/k
+    int pad;
+};
+
+struct DeviceMesh {
+    int material;              // index into materials, -1 = none ("interface")
+    int areaLightBase;         // index of the DiffuseAreaLight of triangle 0, or -1
+    int flags;                 // bit0 flipNormal (reverseOrientation ^ swapsHandedness), bit1 hasN, bit2 hasUV
+    int indexOffset;           // offset (in ints) of this mesh's vertexIndices in the global index pool
+    int nOffset;               // offset (in float3) into the normal pool
+    int uvOffset;              // offset (in float2) into the uv pool
+    int mediumInside, mediumOutside;   // -1 = none
+};
+
+struct DeviceLight {
+    int type;                  // LightTag
+    int tri;                   // DIFFUSE_AREA: global triangle id (pre-reorder id; tri data pool index)
+    float scale;
+    int twoSided;
+    int LemitTable;            // offset into the dense table pool
+    int instance;              // instance index for lights on instanced meshes (unused: pbrt forbids)
+    // infinite lights
+    float sceneRadius;
+    Pt3 sceneCenter;
+    int image;                 // ImageInfinite: index of image record
+    Mat4 renderFromLight, lightFromRender;
+};
+
+// Light BVH node with CompactLightBounds already de-quantised on the host (lightsamplers.h:104-200):
+// the de-quantisation is deterministic float arithmetic, so doing it once is value-identical.
+struct DeviceLightBVHNode {
+    Vec3 w;                    // Normalize(Vector3f(OctahedralVector))
+    float phi;
+    float cosTheta_o, cosTheta_e;
+    Pt3 bmin, bmax;            // CompactLightBounds::Bounds(allb)
+    int twoSided;
+    int childOrLightIndex;
+    int isLeaf;
+    int pad;
+};
+
+struct DeviceLightSampler {
+    int type;                  // LightSamplerTag
+    int nLights, nInfinite, nNodes;
+    const DeviceLightBVHNode *nodes;
+    const int *infiniteLights; // light indices
+    const uint32_t *bitTrails; // per light; 0xffffffff for lights not in the BVH
+    const int *lightInBVH;     // per light 0/1
+};
+
+struct DeviceImageLight {      // ImageInfiniteLight (lights.h:544-628)
+    const float *rgb;          // res*res*3
+    int res;
+    PC2DView distrib, compensatedDistrib;
+    // image colour space = sRGB (tables shared)
+};
+
+struct IntegratorParams {
+    int maxDepth;
+    int regularize;
+};
+
+}  // namespace bpt

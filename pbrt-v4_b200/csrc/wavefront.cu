@@ -1,0 +1,606 @@
+// wavefront.cu -- the wavefront path-tracing kernels (sm_100a).
+//
+// Kernel                      reference counterpart (what it must reproduce, CPU semantics)
+//   k_generate_camera_rays    RayIntegrator::EvaluatePixelSample cpu/integrators.cpp:227-289 (+ wavefront/camera.cpp:31-80)
+//   k_trace_closest           BVHAggregate::Intersect cpu/aggregates.cpp:529-579 + EnqueueWorkAfterIntersection/Miss
+//                             wavefront/intersect.h:16-156   (persistent threads, dynamic ray fetch, wide BVH)
+//   k_handle_escaped          VolPathIntegrator::Li miss branch cpu/integrators.cpp:1081-1098 (wavefront/integrator.cpp:495-537)
+//   k_handle_emissive         Li emission branch cpu/integrators.cpp:1100-1112 (wavefront/integrator.cpp:539-573)
+//   k_shade<Material>         Li body cpu/integrators.cpp:1115-1268 + SampleLd :1273-1390 (wavefront/surfscatter.cpp:57-328)
+//   k_trace_shadow            SampleLd shadow loop cpu/integrators.cpp:1331-1382 (wavefront/intersect.h:31-46)
+//   k_update_film             EvaluatePixelSample tail + RGBFilm::AddSample film.h:239-255 (wavefront/film.cpp:13-39)
+// Sampler dimensions are consumed sequentially exactly as VolPathIntegrator::Li does: the path
+// carries its own dimension counter.
+#define BPT_SOBOL_DEVICE_TABLE
+#include "wavefront.cuh"
+#include "bxdfs.h"
+#include "materials.cuh"
+#include "kernels.h"
+
+namespace bpt {
+
+uint32_t h_sobol32[2 * 52];
+
+void UploadSobolTable(const uint32_t *t) {
+    for (int i = 0; i < 104; ++i) h_sobol32[i] = t[i];
+    cudaMemcpyToSymbol(c_sobol32, t, sizeof(uint32_t) * 104);
+}
+
+// ---------------------------------------------------------------- small helpers
+__device__ __forceinline__ Pt3 XformPoint(const Mat4 &T, Pt3 p) {
+    const float (*m)[4] = T.m;
+    float xp = m[0][0] * p.x + m[0][1] * p.y + m[0][2] * p.z + m[0][3];
+    float yp = m[1][0] * p.x + m[1][1] * p.y + m[1][2] * p.z + m[1][3];
+    float zp = m[2][0] * p.x + m[2][1] * p.y + m[2][2] * p.z + m[2][3];
+    float wp = m[3][0] * p.x + m[3][1] * p.y + m[3][2] * p.z + m[3][3];
+    if (wp == 1) return Pt3(xp, yp, zp);
+    return Pt3(xp, yp, zp) / wp;
+}
+__device__ __forceinline__ Vec3 XformVector(const Mat4 &T, Vec3 v) {
+    const float (*m)[4] = T.m;
+    return Vec3(m[0][0] * v.x + m[0][1] * v.y + m[0][2] * v.z, m[1][0] * v.x + m[1][1] * v.y + m[1][2] * v.z,
+                m[2][0] * v.x + m[2][1] * v.y + m[2][2] * v.z);
+}
+// Transform::operator()(const Ray &r) (util/transform.h:336-349) for an exact origin
+__device__ __forceinline__ void XformRay(const Mat4 &T, Pt3 &o, Vec3 &d) {
+    const float (*m)[4] = T.m;
+    float x = o.x, y = o.y, z = o.z;
+    float xp = (m[0][0] * x + m[0][1] * y) + (m[0][2] * z + m[0][3]);
+    float yp = (m[1][0] * x + m[1][1] * y) + (m[1][2] * z + m[1][3]);
+    float zp = (m[2][0] * x + m[2][1] * y) + (m[2][2] * z + m[2][3]);
+    float wp = (m[3][0] * x + m[3][1] * y) + (m[3][2] * z + m[3][3]);
+    Vec3 pError;
+    pError.x = gamma_n(3) * (fabsf(m[0][0] * x) + fabsf(m[0][1] * y) + fabsf(m[0][2] * z) + fabsf(m[0][3]));
+    pError.y = gamma_n(3) * (fabsf(m[1][0] * x) + fabsf(m[1][1] * y) + fabsf(m[1][2] * z) + fabsf(m[1][3]));
+    pError.z = gamma_n(3) * (fabsf(m[2][0] * x) + fabsf(m[2][1] * y) + fabsf(m[2][2] * z) + fabsf(m[2][3]));
+    Pt3i oi(Pt3(xp, yp, zp), pError);
+    if (wp != 1) {
+        // Point3fi / Float: Interval::operator/=(Float)
+        auto divI = [](Interval i, float f) { return f > 0 ? Interval(DivRoundDown(i.low, f), DivRoundUp(i.high, f))
+                                                          : Interval(DivRoundDown(i.high, f), DivRoundUp(i.low, f)); };
+        oi.x = divI(oi.x, wp); oi.y = divI(oi.y, wp); oi.z = divI(oi.z, wp);
+    }
+    Vec3 dn = XformVector(T, d);
+    float lengthSquared = LengthSquared(dn);
+    if (lengthSquared > 0) {
+        float dt = Dot(Abs(dn), oi.Error()) / lengthSquared;
+        Vec3 off = dn * dt;
+        oi.x = oi.x + off.x; oi.y = oi.y + off.y; oi.z = oi.z + off.z;
+    }
+    o = oi.p();
+    d = dn;
+}
+
+__device__ __forceinline__ Spec ld4(const float4 *p) { float4 v = *p; return Spec(v.x, v.y, v.z, v.w); }
+__device__ __forceinline__ void st4(float4 *p, Spec s) { *p = make_float4(s[0], s[1], s[2], s[3]); }
+
+__device__ __forceinline__ Wavelengths LoadLambda(const PathState &ps, int slot) {
+    Wavelengths wl;
+    float4 a = ps.lambda[slot], b = ps.lambdaPdf[slot];
+    wl.lambda[0] = a.x; wl.lambda[1] = a.y; wl.lambda[2] = a.z; wl.lambda[3] = a.w;
+    wl.pdf[0] = b.x; wl.pdf[1] = b.y; wl.pdf[2] = b.z; wl.pdf[3] = b.w;
+    return wl;
+}
+__device__ __forceinline__ LightSampleContext LoadCtx(const PathState &ps, int slot) {
+    float4 a = ps.ctx0[slot], b = ps.ctx1[slot], c = ps.ctx2[slot];
+    LightSampleContext ctx;
+    ctx.pi.x.low = a.x; ctx.pi.x.high = a.y; ctx.pi.y.low = a.z; ctx.pi.y.high = a.w;
+    ctx.pi.z.low = b.x; ctx.pi.z.high = b.y;
+    ctx.n = Nrm3(b.z, b.w, c.x);
+    ctx.ns = Nrm3(c.y, c.z, c.w);
+    return ctx;
+}
+__device__ __forceinline__ void StoreCtx(const PathState &ps, int slot, const Pt3i &pi, Nrm3 n, Nrm3 ns) {
+    ps.ctx0[slot] = make_float4(pi.x.low, pi.x.high, pi.y.low, pi.y.high);
+    ps.ctx1[slot] = make_float4(pi.z.low, pi.z.high, n.x, n.y);
+    ps.ctx2[slot] = make_float4(n.z, ns.x, ns.y, ns.z);
+}
+
+// ---------------------------------------------------------------- queue reset
+__global__ void k_reset_counts(int *counts, int first, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) counts[first + i] = 0;
+}
+__global__ void k_reset_depth(int *counts, int nextRayQ) {
+    int i = threadIdx.x;
+    if (i == nextRayQ || i == Q_SHADOW || i == Q_ESCAPED || i == Q_HITLIGHT || (i >= Q_MAT0 && i < Q_NCOUNTERS)) counts[i] = 0;
+}
+
+// ---------------------------------------------------------------- camera rays
+__global__ void __launch_bounds__(256) k_generate_camera_rays(RenderCtx rc, int x0, int x1, int y0, int y1, int firstSample, int nSamples) {
+    int nPix = (x1 - x0) * (y1 - y0);
+    int total = nPix * nSamples;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x) {
+        int s = slot / nPix, pix = slot - s * nPix;
+        int py = y0 + pix / (x1 - x0), px = x0 + pix % (x1 - x0);
+        int sampleIndex = firstSample + s;
+        Sampler sampler;
+        sampler.StartPixelSample(&rc.sampler, px, py, sampleIndex, 0);
+        float lu = sampler.Get1D();
+        Wavelengths wl = Wavelengths::SampleVisible(lu);
+        // GetCameraSample (samplers.h:797-814)
+        Vec2 uf = sampler.Get2D();
+        Vec2 fp; float fweight;
+        if (rc.filter.sampled) {
+            float pdf; int ou, ov;
+            fp = PC2DSample(rc.filter.distrib, uf, &pdf, &ou, &ov);
+            fweight = rc.filter.f[ov * rc.filter.nx + ou] / pdf;
+        } else {   // BoxFilter::Sample (filters.h)
+            fp = Vec2(Lerp(uf.x, -rc.filter.radiusX, rc.filter.radiusX), Lerp(uf.y, -rc.filter.radiusY, rc.filter.radiusY));
+            fweight = 1;
+        }
+        Vec2 pFilm((px + fp.x) + 0.5f, (py + fp.y) + 0.5f);
+        float time = sampler.Get1D();
+        Vec2 pLens = sampler.Get2D();
+        // PerspectiveCamera::GenerateRayDifferential (cameras.cpp:429-447), main ray only
+        Pt3 pCamera = XformPoint(rc.camera.cameraFromRaster, Pt3(pFilm.x, pFilm.y, 0));
+        Vec3 dir = Normalize(Vec3(pCamera.x, pCamera.y, pCamera.z));
+        Pt3 o(0, 0, 0);
+        if (rc.camera.lensRadius > 0) {
+            Vec2 dsk = SampleUniformDiskConcentric(pLens);
+            Vec2 pl(rc.camera.lensRadius * dsk.x, rc.camera.lensRadius * dsk.y);
+            float ft = rc.camera.focalDistance / dir.z;
+            Pt3 pFocus = o + dir * ft;
+            o = Pt3(pl.x, pl.y, 0);
+            dir = Normalize(pFocus - o);
+        }
+        XformRay(rc.camera.renderFromCamera, o, dir);
+        const PathState &ps = rc.ps;
+        ps.rayO[slot] = make_float4(o.x, o.y, o.z, 0.f);
+        ps.rayD[slot] = make_float4(dir.x, dir.y, dir.z, time);
+        ps.beta[slot] = make_float4(1, 1, 1, 1);
+        ps.r_u[slot] = make_float4(1, 1, 1, 1);
+        ps.r_l[slot] = make_float4(1, 1, 1, 1);
+        ps.L[slot] = make_float4(0, 0, 0, 0);
+        ps.lambda[slot] = make_float4(wl.lambda[0], wl.lambda[1], wl.lambda[2], wl.lambda[3]);
+        ps.lambdaPdf[slot] = make_float4(wl.pdf[0], wl.pdf[1], wl.pdf[2], wl.pdf[3]);
+        ps.misc[slot] = make_uint4((unsigned)px | ((unsigned)py << 16), (unsigned)sampleIndex, (unsigned)sampler.dimension, 0u);
+        ps.aux[slot] = make_float2(1.f, fweight);
+        rc.queues[Q_RAY0][slot] = slot;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        rc.counts[Q_RAY0] = total;
+        atomicAdd(&rc.stats[0], (unsigned long long)total);
+    }
+}
+
+// ---------------------------------------------------------------- closest hit (persistent threads + dynamic fetch)
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_closest(RenderCtx rc, int curQ) {
+    const int lane = threadIdx.x & 31;
+    const int nRays = rc.counts[curQ];
+    const int *queue = rc.queues[curQ];
+    unsigned locNodes = 0, locTris = 0, locRays = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&rc.stats[1], (unsigned long long)nRays);
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&rc.counts[Q_CURSOR_CLOSEST], 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= nRays) break;
+        int idx = base + lane;
+        if (idx < nRays) {
+            int slot = queue[idx];
+            float4 o4 = rc.ps.rayO[slot], d4 = rc.ps.rayD[slot];
+            HitRec rec;
+            TraceRay<false, COUNT>(rc.bvh, Pt3(o4.x, o4.y, o4.z), Vec3(d4.x, d4.y, d4.z), BPT_INFINITY, &rec, &locNodes, &locTris);
+            if (COUNT) ++locRays;
+            if (rec.tri < 0) {
+                if (rc.nInfinite > 0) { int p = WarpAggPush(&rc.counts[Q_ESCAPED]); rc.queues[Q_ESCAPED][p] = slot; }
+            } else {
+                const float4 *tp = rc.bvh.tris + (size_t)rec.tri * 3;
+                int orig = __float_as_int(__ldg(tp).w);
+                unsigned cls = __float_as_uint(__ldg(tp + 1).w);
+                rc.ps.hit[slot] = make_float4(__int_as_float(orig), rec.b0, rec.b1, rec.b2);
+                if (cls & 0x100u) { int p = WarpAggPush(&rc.counts[Q_HITLIGHT]); rc.queues[Q_HITLIGHT][p] = slot; }
+                unsigned mt = cls & 0xffu;
+                int p = WarpAggPush(&rc.counts[Q_MAT0 + mt]);
+                rc.queues[Q_MAT0 + mt][p] = slot;
+            }
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&rc.stats[3], (unsigned long long)locNodes);
+        atomicAdd(&rc.stats[4], (unsigned long long)locTris);
+        atomicAdd(&rc.stats[5], (unsigned long long)locRays);
+    }
+}
+
+// ---------------------------------------------------------------- shadow rays
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_shadow(RenderCtx rc) {
+    const int lane = threadIdx.x & 31;
+    const int nRays = rc.counts[Q_SHADOW];
+    unsigned locNodes = 0, locTris = 0, locRays = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&rc.stats[2], (unsigned long long)nRays);
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&rc.counts[Q_CURSOR_SHADOW], 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= nRays) break;
+        int idx = base + lane;
+        if (idx < nRays) {
+            ShadowItem it = rc.shadowItems[idx];
+            HitRec rec;
+            TraceRay<true, COUNT>(rc.bvh, Pt3(it.o_slot.x, it.o_slot.y, it.o_slot.z), Vec3(it.d.x, it.d.y, it.d.z), it.d.w, &rec,
+                                  &locNodes, &locTris);
+            if (COUNT) ++locRays;
+            if (rec.tri < 0) {
+                int slot = __float_as_int(it.o_slot.w);
+                float4 L = rc.ps.L[slot];
+                L.x += it.Ld.x; L.y += it.Ld.y; L.z += it.Ld.z; L.w += it.Ld.w;
+                rc.ps.L[slot] = L;
+            }
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&rc.stats[3], (unsigned long long)locNodes);
+        atomicAdd(&rc.stats[4], (unsigned long long)locTris);
+        atomicAdd(&rc.stats[5], (unsigned long long)locRays);
+    }
+}
+
+// ---------------------------------------------------------------- emission at hit vertices
+__global__ void __launch_bounds__(128) k_handle_emissive(RenderCtx rc) {
+    const int n = rc.counts[Q_HITLIGHT];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int slot = rc.queues[Q_HITLIGHT][i];
+        const PathState &ps = rc.ps;
+        float4 h = ps.hit[slot];
+        int tri = __float_as_int(h.x);
+        TriData td = LoadTriangle(rc.sv, tri);
+        TriHit th{h.y, h.z, h.w, 0.f};
+        SurfaceIntr isect = TriangleInteraction(td.p0, td.p1, td.p2, td.a, th);
+        const DeviceMesh &mesh = rc.sv.meshes[td.mesh];
+        int lightIndex = mesh.areaLightBase + td.triIndex;
+        const DeviceLight &light = rc.sv.lights[lightIndex];
+        float4 d4 = ps.rayD[slot];
+        Vec3 rd(d4.x, d4.y, d4.z);
+        Wavelengths wl = LoadLambda(ps, slot);
+        Spec Le = AreaLightL(rc.sv, light, isect.n, -rd, wl);
+        if (!Le.IsNonZero()) continue;
+        uint4 misc = ps.misc[slot];
+        int depth = misc.w & 0xff;
+        bool specularBounce = (misc.w >> 8) & 1;
+        Spec beta = ld4(&ps.beta[slot]), r_u = ld4(&ps.r_u[slot]);
+        Spec L = ld4(&ps.L[slot]);
+        if (depth == 0 || specularBounce)
+            L += beta * Le / r_u.Average();
+        else {
+            LightSampleContext prev = LoadCtx(ps, slot);
+            float p_l = LightSamplerPMF(rc.sv, prev, lightIndex) * AreaLightPDF_Li(rc.sv, light, prev, rd);
+            Spec r_l = ld4(&ps.r_l[slot]);
+            r_l *= p_l;
+            L += beta * Le / (r_u + r_l).Average();
+        }
+        st4(&ps.L[slot], L);
+    }
+}
+
+// ---------------------------------------------------------------- escaped rays (infinite lights)
+__global__ void __launch_bounds__(128) k_handle_escaped(RenderCtx rc) {
+    const int n = rc.counts[Q_ESCAPED];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int slot = rc.queues[Q_ESCAPED][i];
+        const PathState &ps = rc.ps;
+        float4 d4 = ps.rayD[slot];
+        Vec3 rd(d4.x, d4.y, d4.z);
+        Wavelengths wl = LoadLambda(ps, slot);
+        uint4 misc = ps.misc[slot];
+        int depth = misc.w & 0xff;
+        bool specularBounce = (misc.w >> 8) & 1;
+        Spec beta = ld4(&ps.beta[slot]), r_u = ld4(&ps.r_u[slot]), r_l = ld4(&ps.r_l[slot]);
+        Spec L = ld4(&ps.L[slot]);
+        LightSampleContext prev = LoadCtx(ps, slot);
+        for (int k = 0; k < rc.sv.ls.nInfinite; ++k) {
+            int lightIndex = rc.sv.ls.infiniteLights[k];
+            const DeviceLight &light = rc.sv.lights[lightIndex];
+            Spec Le = InfiniteLightLe(rc.sv, light, rd, wl);
+            if (!Le.IsNonZero()) continue;
+            if (depth == 0 || specularBounce)
+                L += beta * Le / r_u.Average();
+            else {
+                float p_l = LightSamplerPMF(rc.sv, prev, lightIndex) * InfiniteLightPDF_Li(rc.sv, light, prev, rd);
+                r_l *= p_l;
+                L += beta * Le / (r_u + r_l).Average();
+            }
+        }
+        st4(&ps.L[slot], L);
+    }
+}
+
+// ---------------------------------------------------------------- surface scattering, one instantiation per material
+template <typename Material>
+__global__ void __launch_bounds__(128) k_shade(RenderCtx rc, int nextQ) {
+    const int n = rc.counts[Q_MAT0 + Material::kTag];
+    const int *queue = rc.queues[Q_MAT0 + Material::kTag];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int slot = queue[i];
+        const PathState &ps = rc.ps;
+        float4 h = ps.hit[slot];
+        int tri = __float_as_int(h.x);
+        TriData td = LoadTriangle(rc.sv, tri);
+        TriHit th{h.y, h.z, h.w, 0.f};
+        SurfaceIntr isect = TriangleInteraction(td.p0, td.p1, td.p2, td.a, th);
+        const DeviceMesh &mesh = rc.sv.meshes[td.mesh];
+        float4 d4 = ps.rayD[slot];
+        Vec3 wo = -Vec3(d4.x, d4.y, d4.z);
+        Wavelengths wl = LoadLambda(ps, slot);
+        uint4 misc = ps.misc[slot];
+        int depth = misc.w & 0xff;
+        bool anyNonSpecularBounces = (misc.w >> 9) & 1;
+        int px = misc.x & 0xffff, py = misc.x >> 16;
+
+        if (Material::kTag == MAT_INTERFACE) {
+            // isect.SkipIntersection(&ray, tHit): respawn the ray past the surface, same depth (interaction.h)
+            Pt3 o = OffsetRayOrigin(isect.pi, isect.n, -wo);
+            ps.rayO[slot] = make_float4(o.x, o.y, o.z, 0.f);
+            int p = WarpAggPush(&rc.counts[nextQ]);
+            rc.queues[nextQ][p] = slot;
+            continue;
+        }
+        // Get BSDF (material.GetBxDF may terminate secondary wavelengths)
+        const DeviceMaterial &mat = rc.sv.materials[mesh.material];
+        bool lambdaChanged = false;
+        typename Material::BxDF bxdf = Material::GetBxDF(mat, rc.sv, wl, &lambdaChanged);
+        BSDF<typename Material::BxDF> bsdf(isect.ns, isect.dpdus, bxdf);
+        if (lambdaChanged) ps.lambdaPdf[slot] = make_float4(wl.pdf[0], wl.pdf[1], wl.pdf[2], wl.pdf[3]);
+
+        // Terminate path if maximum depth reached
+        if (depth++ >= rc.integ.maxDepth) continue;
+        if (rc.integ.regularize && anyNonSpecularBounces) bsdf.Regularize();
+
+        Sampler sampler;
+        sampler.StartPixelSample(&rc.sampler, px, py, (int)misc.y, (int)misc.z);
+        Spec beta = ld4(&ps.beta[slot]), r_u = ld4(&ps.r_u[slot]);
+        int flags = bsdf.Flags();
+
+        // Sample illumination from lights (SampleLd)
+        if (IsNonSpecular(flags)) {
+            LightSampleContext ctx;
+            ctx.pi = isect.pi; ctx.n = isect.n; ctx.ns = isect.ns;
+            if (IsReflective(flags) && !IsTransmissive(flags)) ctx.pi = Pt3i(OffsetRayOrigin(isect.pi, isect.n, wo));
+            else if (IsTransmissive(flags) && !IsReflective(flags)) ctx.pi = Pt3i(OffsetRayOrigin(isect.pi, isect.n, -wo));
+            float u = sampler.Get1D();
+            float lightPMF = 0;
+            int lightIndex = LightSamplerSample(rc.sv, ctx, u, &lightPMF);
+            Vec2 uLight = sampler.Get2D();
+            if (lightIndex >= 0) {
+                const DeviceLight &light = rc.sv.lights[lightIndex];
+                LightLiSample ls;
+                if (light.type == LIGHT_DIFFUSE_AREA) ls = AreaLightSampleLi(rc.sv, light, ctx, uLight, wl);
+                else ls = InfiniteLightSampleLi(rc.sv, light, ctx, uLight, wl);
+                if (ls.valid && ls.L.IsNonZero() && ls.pdf != 0) {
+                    float p_l = lightPMF * ls.pdf;
+                    Vec3 wi = ls.wi;
+                    Spec f_hat = bsdf.f(wo, wi) * AbsDot(wi, isect.ns);
+                    float scatterPDF = bsdf.PDF(wo, wi);
+                    if (f_hat.IsNonZero()) {
+                        // lightRay = intr.SpawnRayTo(ls->pLight)  (ray.h:94-101, both ends offset)
+                        Pt3 pf, pt;
+                        if (light.type == LIGHT_DIFFUSE_AREA) {
+                            pf = OffsetRayOrigin(isect.pi, isect.n, ls.pLight.p() - isect.pi.p());
+                            pt = OffsetRayOrigin(ls.pLight, ls.nLight, pf - ls.pLight.p());
+                        } else {
+                            // infinite light: pLight is a plain point with n = 0: OffsetRayOrigin leaves it unchanged
+                            pf = OffsetRayOrigin(isect.pi, isect.n, ls.pLight.p() - isect.pi.p());
+                            pt = ls.pLight.p();
+                        }
+                        Vec3 rdv = pt - pf;
+                        if (rdv != Vec3(0, 0, 0)) {
+                            Spec r_l = r_u * p_l;
+                            Spec r_uu = r_u * scatterPDF;
+                            Spec Ld = beta * f_hat * ls.L / (r_l + r_uu).Average();
+                            int p = WarpAggPush(&rc.counts[Q_SHADOW]);
+                            ShadowItem it;
+                            it.o_slot = make_float4(pf.x, pf.y, pf.z, __int_as_float(slot));
+                            it.d = make_float4(rdv.x, rdv.y, rdv.z, 1 - kShadowEpsilon);
+                            it.Ld = make_float4(Ld[0], Ld[1], Ld[2], Ld[3]);
+                            rc.shadowItems[p] = it;
+                        } else {
+                            // zero-length light ray: the reference's while loop does not run and the contribution is added
+                            Spec r_l = r_u * p_l;
+                            Spec r_uu = r_u * scatterPDF;
+                            Spec Ld = beta * f_hat * ls.L / (r_l + r_uu).Average();
+                            float4 L = ps.L[slot];
+                            L.x += Ld[0]; L.y += Ld[1]; L.z += Ld[2]; L.w += Ld[3];
+                            ps.L[slot] = L;
+                        }
+                    }
+                }
+            }
+        }
+        // prevIntrContext = LightSampleContext(isect)
+        StoreCtx(ps, slot, isect.pi, isect.n, isect.ns);
+
+        // Sample BSDF to get new path direction
+        float u = sampler.Get1D();
+        Vec2 u2 = sampler.Get2D();
+        BSDFSample bs = bsdf.Sample_f(wo, u, u2);
+        if (!bs.valid) continue;
+        beta *= bs.f * AbsDot(bs.wi, isect.ns) / bs.pdf;
+        Spec r_l;
+        if (bs.pdfIsProportional) r_l = r_u / bsdf.PDF(wo, bs.wi);
+        else r_l = r_u / bs.pdf;
+        bool specularBounce = IsSpecular(bs.flags);
+        anyNonSpecularBounces |= !IsSpecular(bs.flags);
+        float2 aux = ps.aux[slot];
+        float etaScale = aux.x;
+        if (IsTransmissive(bs.flags)) etaScale *= Sqr(bs.eta);
+        // ray = isect.SpawnRay(ray, bsdf, bs->wi, bs->flags, bs->eta)
+        Pt3 o = OffsetRayOrigin(isect.pi, isect.n, bs.wi);
+
+        // Russian roulette
+        if (!beta.IsNonZero()) continue;
+        Spec rrBeta = beta * etaScale / r_u.Average();
+        float uRR = sampler.Get1D();
+        if (rrBeta.MaxComponentValue() < 1 && depth > 1) {
+            float q = stdmax(0.f, 1 - rrBeta.MaxComponentValue());
+            if (uRR < q) continue;
+            beta /= 1 - q;
+        }
+        ps.rayO[slot] = make_float4(o.x, o.y, o.z, 0.f);
+        ps.rayD[slot] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, d4.w);
+        st4(&ps.beta[slot], beta);
+        st4(&ps.r_l[slot], r_l);
+        ps.aux[slot] = make_float2(etaScale, aux.y);
+        ps.misc[slot] = make_uint4(misc.x, misc.y, (unsigned)sampler.dimension,
+                                   (unsigned)depth | (specularBounce ? 0x100u : 0u) | (anyNonSpecularBounces ? 0x200u : 0u));
+        int p = WarpAggPush(&rc.counts[nextQ]);
+        rc.queues[nextQ][p] = slot;
+    }
+}
+
+// ---------------------------------------------------------------- film
+__global__ void __launch_bounds__(256) k_update_film(RenderCtx rc, int x0, int x1, int y0, int y1, int nSamples) {
+    int nPix = (x1 - x0) * (y1 - y0);
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < nPix; pix += gridDim.x * blockDim.x) {
+        int py = y0 + pix / (x1 - x0), px = x0 + pix % (x1 - x0);
+        double4 acc = rc.filmPixels[(size_t)py * rc.film.xres + px];
+        for (int s = 0; s < nSamples; ++s) {
+            int slot = s * nPix + pix;
+            Spec L = ld4(&rc.ps.L[slot]);
+            Wavelengths wl = LoadLambda(rc.ps, slot);
+            // NaN / infinite radiance scrub (cpu/integrators.cpp:263-273)
+            if (L.HasNaNs()) L = Spec(0.f);
+            else {
+                Spec Ys = DenseSample(rc.sv.cieY, wl);
+                float y = SafeDiv(Ys * L, wl.PDF()).Average() / 106.856895f;
+                if (IsInf_(y)) L = Spec(0.f);
+            }
+            // PixelSensor::ToSensorRGB (film.h:95-100)
+            Spec Lp = SafeDiv(L, wl.PDF());
+            float r = rc.film.imagingRatio * (DenseSample(rc.sv.cieX, wl) * Lp).Average();
+            float g = rc.film.imagingRatio * (DenseSample(rc.sv.cieY, wl) * Lp).Average();
+            float b = rc.film.imagingRatio * (DenseSample(rc.sv.cieZ, wl) * Lp).Average();
+            float m = stdmax(stdmax(r, g), b);
+            if (m > rc.film.maxComponentValue) { float sc = rc.film.maxComponentValue / m; r *= sc; g *= sc; b *= sc; }
+            float weight = rc.ps.aux[slot].y;
+            acc.x += (double)(weight * r);
+            acc.y += (double)(weight * g);
+            acc.z += (double)(weight * b);
+            acc.w += (double)weight;
+        }
+        rc.filmPixels[(size_t)py * rc.film.xres + px] = acc;
+    }
+}
+
+__global__ void k_resolve_film(const double4 *pix, DeviceFilm film, float *rgbOut) {
+    int n = film.xres * film.yres;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double4 p = pix[i];
+        float rgb[3] = {(float)p.x, (float)p.y, (float)p.z};
+        float weightSum = (float)p.w;
+        if (weightSum != 0) { rgb[0] /= weightSum; rgb[1] /= weightSum; rgb[2] /= weightSum; }
+        // rgbSplat is always zero on this path: rgb[c] += splatScale * 0 / filterIntegral
+        for (int c = 0; c < 3; ++c) rgb[c] += 0.f;
+        float out[3];
+        for (int r = 0; r < 3; ++r) {
+            float v = 0;
+            for (int c = 0; c < 3; ++c) v += film.outRGBFromSensor[r][c] * rgb[c];
+            out[r] = v;
+        }
+        rgbOut[3 * (size_t)i] = out[0]; rgbOut[3 * (size_t)i + 1] = out[1]; rgbOut[3 * (size_t)i + 2] = out[2];
+    }
+}
+
+// ---------------------------------------------------------------- raw ray entry points
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_raw(BVHView bvh, const float4 *rays, int n, float4 *hits, float *tOut, int *cursor,
+                                                   unsigned long long *stats) {
+    const int lane = threadIdx.x & 31;
+    unsigned locNodes = 0, locTris = 0;
+    while (true) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        int i = base + lane;
+        if (i < n) {
+            float4 a = rays[2 * (size_t)i], b = rays[2 * (size_t)i + 1];
+            HitRec rec;
+            TraceRay<ANY, COUNT>(bvh, Pt3(a.x, a.y, a.z), Vec3(b.x, b.y, b.z), a.w, &rec, &locNodes, &locTris);
+            int orig = -1;
+            if (rec.tri >= 0) orig = __float_as_int(__ldg(bvh.tris + (size_t)rec.tri * 3).w);
+            hits[i] = make_float4(__int_as_float(orig), rec.b0, rec.b1, rec.b2);
+            if (tOut) tOut[i] = rec.tri >= 0 ? rec.t : BPT_INFINITY;
+        }
+    }
+    if (COUNT && stats) { atomicAdd(&stats[3], (unsigned long long)locNodes); atomicAdd(&stats[4], (unsigned long long)locTris); }
+}
+
+// ---------------------------------------------------------------- probes for unit parity tests
+__global__ void k_probe_sampler(SamplerParams sp, const int *pxy, const int *sidx, const int *dim, int n, float *o1, float *o2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Sampler s;
+    s.StartPixelSample(&sp, pxy[2 * i], pxy[2 * i + 1], sidx[i], dim[i]);
+    o1[i] = s.Get1D();
+    s.StartPixelSample(&sp, pxy[2 * i], pxy[2 * i + 1], sidx[i], dim[i]);
+    Vec2 v = s.Get2D();
+    o2[2 * i] = v.x; o2[2 * i + 1] = v.y;
+}
+__global__ void k_probe_tri(const float *rays, const float *tris, int n, float *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *r = rays + 7 * (size_t)i, *t = tris + 9 * (size_t)i;
+    TriHit th{0, 0, 0, 0};
+    bool hit = IntersectTriangle(Pt3(r[0], r[1], r[2]), Vec3(r[3], r[4], r[5]), r[6], Pt3(t[0], t[1], t[2]), Pt3(t[3], t[4], t[5]),
+                                 Pt3(t[6], t[7], t[8]), &th);
+    // cross-check the hoisted variant used by traversal
+    RayPre rp = MakeRayPre(Pt3(r[0], r[1], r[2]), Vec3(r[3], r[4], r[5]));
+    TriHit th2{0, 0, 0, 0};
+    bool hit2 = IntersectTrianglePre(rp, r[6], Pt3(t[0], t[1], t[2]), Pt3(t[3], t[4], t[5]), Pt3(t[6], t[7], t[8]), &th2);
+    bool same = hit == hit2 && (!hit || (th.b0 == th2.b0 && th.b1 == th2.b1 && th.b2 == th2.b2 && th.t == th2.t));
+    float *o = out + 5 * (size_t)i;
+    o[0] = same ? (hit ? 1.f : 0.f) : -1.f; o[1] = th.b0; o[2] = th.b1; o[3] = th.b2; o[4] = th.t;
+}
+
+// ================================================================= host-side launchers
+static inline int GridFor(int smCount, int perSM) { return smCount * perSM; }
+
+void LaunchResetAll(const RenderCtx &rc, cudaStream_t st) { k_reset_counts<<<1, 64, 0, st>>>(rc.counts, 0, Q_NCOUNTERS); }
+void LaunchResetDepth(const RenderCtx &rc, int nextQ, cudaStream_t st) { k_reset_depth<<<1, 64, 0, st>>>(rc.counts, nextQ); }
+void LaunchGenerateCameraRays(const RenderCtx &rc, int x0, int x1, int y0, int y1, int firstSample, int nSamples, int sms, cudaStream_t st) {
+    k_generate_camera_rays<<<GridFor(sms, 8), 256, 0, st>>>(rc, x0, x1, y0, y1, firstSample, nSamples);
+}
+void LaunchTraceClosest(const RenderCtx &rc, int curQ, bool count, int sms, cudaStream_t st) {
+    if (count) k_trace_closest<true><<<GridFor(sms, 8), 128, 0, st>>>(rc, curQ);
+    else k_trace_closest<false><<<GridFor(sms, 8), 128, 0, st>>>(rc, curQ);
+}
+void LaunchTraceShadow(const RenderCtx &rc, bool count, int sms, cudaStream_t st) {
+    if (count) k_trace_shadow<true><<<GridFor(sms, 8), 128, 0, st>>>(rc);
+    else k_trace_shadow<false><<<GridFor(sms, 8), 128, 0, st>>>(rc);
+}
+void LaunchHandleEmissive(const RenderCtx &rc, int sms, cudaStream_t st) { k_handle_emissive<<<GridFor(sms, 4), 128, 0, st>>>(rc); }
+void LaunchHandleEscaped(const RenderCtx &rc, int sms, cudaStream_t st) { k_handle_escaped<<<GridFor(sms, 4), 128, 0, st>>>(rc); }
+void LaunchShade(const RenderCtx &rc, int materialTag, int nextQ, int sms, cudaStream_t st) {
+    switch (materialTag) {
+    case MAT_DIFFUSE: k_shade<DiffuseMaterialEval><<<GridFor(sms, 8), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_INTERFACE: k_shade<InterfaceMaterialEval><<<GridFor(sms, 4), 128, 0, st>>>(rc, nextQ); break;
+    default: break;
+    }
+}
+bool ShadeSupported(int materialTag) { return materialTag == MAT_DIFFUSE || materialTag == MAT_INTERFACE; }
+void LaunchUpdateFilm(const RenderCtx &rc, int x0, int x1, int y0, int y1, int nSamples, int sms, cudaStream_t st) {
+    k_update_film<<<GridFor(sms, 8), 256, 0, st>>>(rc, x0, x1, y0, y1, nSamples);
+}
+void LaunchResolveFilm(const double4 *pix, const DeviceFilm &film, float *rgbOut, int sms, cudaStream_t st) {
+    k_resolve_film<<<GridFor(sms, 4), 256, 0, st>>>(pix, film, rgbOut);
+}
+void LaunchTraceRaw(const BVHView &bvh, const float4 *rays, int n, float4 *hits, float *tOut, int *cursor, unsigned long long *stats,
+                    bool any, bool count, int sms, cudaStream_t st) {
+    cudaMemsetAsync(cursor, 0, sizeof(int), st);
+    int g = GridFor(sms, 8);
+    if (any) { if (count) k_trace_raw<true, true><<<g, 128, 0, st>>>(bvh, rays, n, hits, tOut, cursor, stats);
+               else k_trace_raw<true, false><<<g, 128, 0, st>>>(bvh, rays, n, hits, tOut, cursor, stats); }
+    else { if (count) k_trace_raw<false, true><<<g, 128, 0, st>>>(bvh, rays, n, hits, tOut, cursor, stats);
+           else k_trace_raw<false, false><<<g, 128, 0, st>>>(bvh, rays, n, hits, tOut, cursor, stats); }
+}
+void LaunchProbeSampler(const SamplerParams &sp, const int *pxy, const int *sidx, const int *dim, int n, float *o1, float *o2, cudaStream_t st) {
+    k_probe_sampler<<<(n + 127) / 128, 128, 0, st>>>(sp, pxy, sidx, dim, n, o1, o2);
+}
+void LaunchProbeTri(const float *rays, const float *tris, int n, float *out, cudaStream_t st) {
+    k_probe_tri<<<(n + 127) / 128, 128, 0, st>>>(rays, tris, n, out);
+}
+
+}  // namespace bpt

@@ -1,0 +1,66 @@
+// wavefront.cuh -- device-side state of the wavefront path tracer: SOA path state, index queues, render context.
+//
+// B200-first restructuring of the reference's work queues (wavefront/workitems.soa, workqueue.h:41-172):
+// the reference copies a 184..452-byte work item from queue to queue at every stage; here the path state
+// stays in place in float4-packed SOA arrays indexed by the path slot and the queues
+// (RayQueue / EscapedRayQueue / HitAreaLightQueue / per-material MaterialEvalQueue) carry only 4-byte slot
+// indices, compacted with warp-aggregated atomics.  Only the ShadowRayQueue carries a payload (48 B).
+#pragma once
+#include <cuda_runtime.h>
+#include "scene.h"
+#include "lights.h"
+#include "bvh.cuh"
+
+namespace bpt {
+
+// queue ids inside RenderCtx::counts
+enum { Q_RAY0 = 0, Q_RAY1 = 1, Q_SHADOW = 2, Q_ESCAPED = 3, Q_HITLIGHT = 4, Q_MAT0 = 5 /* + MaterialTag */,
+       Q_CURSOR_CLOSEST = Q_MAT0 + MAT_NTAGS, Q_CURSOR_SHADOW, Q_NCOUNTERS };
+
+struct PathState {
+    float4 *rayO;        // o.xyz, (unused)
+    float4 *rayD;        // d.xyz, time
+    float4 *hit;         // original triangle id (int bits), b0, b1, b2
+    float4 *beta, *r_u, *r_l, *L;
+    float4 *lambda, *lambdaPdf;
+    float4 *ctx0;        // prevIntrCtx: pi.x.low, pi.x.high, pi.y.low, pi.y.high
+    float4 *ctx1;        //              pi.z.low, pi.z.high, n.x, n.y
+    float4 *ctx2;        //              n.z, ns.x, ns.y, ns.z
+    uint4 *misc;         // px | py << 16, sampleIndex, sampler dimension, depth | specularBounce << 8 | anyNonSpecular << 9
+    float2 *aux;         // etaScale, filterWeight
+};
+
+struct ShadowItem { float4 o_slot; float4 d; float4 Ld; };   // o.xyz + slot bits ; d.xyz + tMax ; Ld
+
+struct RenderCtx {
+    PathState ps;
+    int *queues[Q_CURSOR_CLOSEST];     // item arrays for Q_RAY0.. (Q_SHADOW unused: shadow items below)
+    ShadowItem *shadowItems;
+    int *counts;                       // Q_NCOUNTERS ints
+    unsigned long long *stats;         // [0] camera rays [1] indirect rays [2] shadow rays [3] nodes [4] tris [5] counted rays
+    BVHView bvh;
+    SceneView sv;
+    DeviceCamera camera;
+    DeviceFilm film;
+    DeviceFilter filter;
+    SamplerParams sampler;
+    IntegratorParams integ;
+    double4 *filmPixels;               // xres*yres {rgbSum[3], weightSum}
+    int nInfinite;
+    int maxPaths;
+};
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ int WarpAggPush(int *counter) {
+    // warp-aggregated atomic slot allocation for the currently converged lanes
+    unsigned m = __activemask();
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane) - 1));
+}
+#endif
+
+}  // namespace bpt

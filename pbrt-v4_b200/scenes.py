@@ -1,0 +1,86 @@
+"""Seeded procedural scene generators for the BASELINE.json configs: each writes a
+`.pbrt` file (plus binary PLY meshes) that both this engine and the reference `pbrt` binary read unchanged."""
+import os
+import struct
+
+import numpy as np
+
+
+def write_ply(path, P, idx, N=None):
+    """binary_little_endian PLY with float x y z [nx ny nz] and int triangle faces."""
+    P = np.asarray(P, dtype="<f4").reshape(-1, 3)
+    idx = np.asarray(idx, dtype="<i4").reshape(-1, 3)
+    with open(path, "wb") as f:
+        hdr = "ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n" % len(P)
+        if N is not None:
+            hdr += "property float nx\nproperty float ny\nproperty float nz\n"
+        hdr += "element face %d\nproperty list uchar int vertex_indices\nend_header\n" % len(idx)
+        f.write(hdr.encode())
+        if N is not None:
+            f.write(np.hstack([P, np.asarray(N, dtype="<f4").reshape(-1, 3)]).astype("<f4").tobytes())
+        else:
+            f.write(P.tobytes())
+        rec = np.empty(len(idx), dtype=[("n", "u1"), ("v", "<i4", 3)])
+        rec["n"] = 3
+        rec["v"] = idx
+        f.write(rec.tobytes())
+
+
+def _header(res, spp, maxdepth, cam, fov, extra=""):
+    (ex, ey, ez), (lx, ly, lz) = cam
+    return (f"LookAt {ex} {ey} {ez}  {lx} {ly} {lz}  0 1 0\n"
+            f"Camera \"perspective\" \"float fov\" {fov}\n"
+            f"Sampler \"zsobol\" \"integer pixelsamples\" {spp}\n"
+            f"Integrator \"volpath\" \"integer maxdepth\" {maxdepth}\n"
+            f"Film \"rgb\" \"integer xresolution\" {res[0]} \"integer yresolution\" {res[1]} \"string filename\" \"out.pfm\" \"bool savefp16\" false\n"
+            f"{extra}WorldBegin\n")
+
+
+def cornell(outdir, res=(256, 256), spp=64, maxdepth=5):
+    """Config 1: Cornell box, 5 wall quads + 1 quad area light (12 triangles)."""
+    os.makedirs(outdir, exist_ok=True)
+    s = _header(res, spp, maxdepth, ((0, 1, 3.4), (0, 1, 0)), 40)
+    quad = "Shape \"trianglemesh\" \"integer indices\" [0 1 2 0 2 3] \"point3 P\" [%s]\n"
+    s += "AttributeBegin\n  AreaLightSource \"diffuse\" \"rgb L\" [17 12 4]\n  Material \"diffuse\" \"rgb reflectance\" [0 0 0]\n  "
+    s += quad % "-0.25 1.98 -0.25  0.25 1.98 -0.25  0.25 1.98 0.25  -0.25 1.98 0.25"
+    s += "AttributeEnd\nMaterial \"diffuse\" \"rgb reflectance\" [0.73 0.73 0.73]\n"
+    s += quad % "-1 0 -1  -1 0 1  1 0 1  1 0 -1"
+    s += quad % "-1 2 -1  1 2 -1  1 2 1  -1 2 1"
+    s += quad % "-1 0 -1  1 0 -1  1 2 -1  -1 2 -1"
+    s += "Material \"diffuse\" \"rgb reflectance\" [0.65 0.05 0.05]\n" + quad % "-1 0 -1  -1 2 -1  -1 2 1  -1 0 1"
+    s += "Material \"diffuse\" \"rgb reflectance\" [0.12 0.45 0.15]\n" + quad % "1 0 -1  1 0 1  1 2 1  1 2 -1"
+    path = os.path.join(outdir, "cornell.pbrt")
+    open(path, "w").write(s)
+    return path
+
+
+def heightfield_mesh(n, seed=1234, amp=0.05, noise=0.01):
+    g = np.linspace(-1.0, 1.0, n, dtype=np.float64)
+    X, Z = np.meshgrid(g, g, indexing="xy")
+    rng = np.random.Generator(np.random.PCG64(seed))
+    Y = amp * np.sin(9 * X) * np.cos(7 * Z) + noise * rng.standard_normal(X.shape)
+    P = np.stack([X, Y, Z], axis=-1).reshape(-1, 3).astype(np.float32)
+    i = np.arange(n - 1)
+    I, J = np.meshgrid(i, i, indexing="xy")
+    v00 = (J * n + I).reshape(-1)
+    v10 = v00 + 1
+    v01 = v00 + n
+    v11 = v01 + 1
+    # counter-clockwise seen from +y so that geometric normals point up
+    idx = np.concatenate([np.stack([v00, v01, v11], -1), np.stack([v00, v11, v10], -1)], axis=0).astype(np.int32)
+    return P, idx
+
+
+def diffuse_heightfield(outdir, n=708, res=(1024, 1024), spp=256, maxdepth=5, seed=1234):
+    """Config 2: (n-1)^2*2-triangle diffuse height field (n=708 -> 999 698 triangles), one 1x1 quad light at y=2."""
+    os.makedirs(outdir, exist_ok=True)
+    P, idx = heightfield_mesh(n, seed)
+    write_ply(os.path.join(outdir, "heightfield.ply"), P, idx)
+    s = _header(res, spp, maxdepth, ((0, 1.6, 2.6), (0, 0, 0)), 45)
+    s += ("AttributeBegin\n  AreaLightSource \"diffuse\" \"rgb L\" [20 20 20]\n  Material \"diffuse\" \"rgb reflectance\" [0 0 0]\n"
+          "  Shape \"trianglemesh\" \"integer indices\" [0 1 2 0 2 3] \"point3 P\" [-0.5 2 -0.5  0.5 2 -0.5  0.5 2 0.5  -0.5 2 0.5]\n"
+          "AttributeEnd\n")
+    s += "Material \"diffuse\" \"rgb reflectance\" [0.6 0.6 0.6]\nShape \"plymesh\" \"string filename\" \"heightfield.ply\"\n"
+    path = os.path.join(outdir, "heightfield.pbrt")
+    open(path, "w").write(s)
+    return path
