@@ -1,0 +1,310 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native wavefront path tracer (BASELINE.json metric: Mrays/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (one process per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path (oracle/_ref/bin/pbrt)
+
+A "step" is one full render of the workload (BASELINE configs[1]: procedural ~1M-triangle diffuse height field, one
+quad area light, 1024x1024, 256 spp, maxdepth 5, zsobol) -- all wavefront depths, shadow rays and the film update.
+`value` = rays traced (camera + indirect + shadow, counted on the device) per second over all GPUs, scene resident in
+HBM, timed with CUDA events inside the engine; `e2e` = the same metric through the public scene-file API with host
+inputs: parse + host->device upload + BVH build + render + film read-back every step.
+Multi-GPU: scanline bands of the film are split over the ranks (weak in rays per band is not fixed: total work is
+fixed, so scaling is "strong"); one NCCL reduce of the per-rank film accumulators per step (frame end).
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (generator, kwargs, description)
+    "heightfield1m": dict(n=708, res=(1024, 1024), spp=256, desc="procedural 999698-triangle diffuse height field, 1 quad area light, 1024x1024, 256 spp, maxdepth 5, zsobol"),
+    "heightfield_small": dict(n=128, res=(256, 256), spp=16, desc="procedural 32258-triangle diffuse height field, 256x256, 16 spp (smoke size)"),
+}
+
+
+def scene_dir():
+    d = os.environ.get("BPT_BENCH_DIR", os.path.join(tempfile.gettempdir(), "bpt_bench"))
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def make_scene(name, spp=None, res=None):
+    from pbrt_v4_b200 import scenes
+    w = WORKLOADS[name]
+    spp = spp or w["spp"]
+    res = res or w["res"]
+    d = os.path.join(scene_dir(), f"{name}_{res[0]}x{res[1]}_{spp}")
+    path = os.path.join(d, "heightfield.pbrt")
+    if not os.path.exists(path):
+        path = scenes.diffuse_heightfield(d, n=w["n"], res=res, spp=spp)
+    return path
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for k, nm in enumerate(names):
+                if len(s) > 2 + k and s[2 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_reference_cpu(scene_path, spp_lo, spp_hi, threads=None):
+    """Times the reference's CPU VolPathIntegrator (oracle/_ref/bin/pbrt) on the host cores: two runs at different spp so
+    that parse + BVH-build time cancels; rays = its own 'Regular ray intersection tests' statistic."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "bin", "pbrt")
+    if not os.path.exists(exe):
+        return None
+    threads = threads or os.cpu_count()
+    res = []
+    for spp in (spp_lo, spp_hi):
+        out_pfm = os.path.join(scene_dir(), f"ref_{os.getpid()}.pfm")
+        t0 = time.time()
+        p = subprocess.run([exe, "--quiet", "--stats", "--seed", "0", "--nthreads", str(threads), "--spp", str(spp), "--outfile", out_pfm,
+                            scene_path], capture_output=True, text=True)
+        dt = time.time() - t0
+        m = re.search(r"Regular ray intersection tests\s+(\d+)", p.stdout + p.stderr)
+        rays = int(m.group(1)) if m else 0
+        res.append((dt, rays))
+    d_t = res[1][0] - res[0][0]
+    d_r = res[1][1] - res[0][1]
+    mrays = d_r / d_t / 1e6 if d_t > 0 else 0.0
+    return {"value": mrays, "unit": "Mrays/s", "cores": threads, "kind": "reference",
+            "sample": f"oracle/_ref/bin/pbrt (reference CPU VolPathIntegrator) on the bench scene at reduced film settings, "
+                      f"delta between --spp {spp_lo} ({res[0][0]:.1f}s) and --spp {spp_hi} ({res[1][0]:.1f}s) runs, {d_r} rays"}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample of the same workload: same scene, 256x256 film region, low spp
+    path = make_scene(args.workload, spp=4, res=(256, 256))
+    vals = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = run_reference_cpu(path, 4, 16)
+        if base is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin/pbrt is not built (python oracle/build_ref.py)"}))
+            return
+        if i >= args.warmup:
+            vals.append(base["value"])
+    v = sum(vals) / len(vals)
+    base["value"] = v
+    line = {"metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference", "config": {"workload": WORKLOADS[args.workload]["desc"], "sample": "256x256 film, spp 4 -> 16 delta"},
+            "cpu_baseline": base, "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default=os.environ.get("BPT_WORKLOAD", "heightfield1m"))
+    ap.add_argument("--spp", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    from pbrt_v4_b200 import engine as E
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w = WORKLOADS[args.workload]
+    spp = args.spp or w["spp"]
+    path = make_scene(args.workload, spp=spp) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+        path = make_scene(args.workload, spp=spp)
+    xres, yres = w["res"]
+
+    eng = E.Engine(local_rank)
+    eng.load_pbrt(path, seed=0)
+    st0 = eng.stats()
+    # scanline bands, interleaved in blocks of 16 rows for load balance
+    band = 16
+    my_bands = [(y, min(y + band, yres)) for i, y in enumerate(range(0, yres, band)) if i % world == rank]
+    film_t = torch.zeros((yres, xres, 4), dtype=torch.float64, device="cuda")
+
+    def step():
+        eng.film_clear()
+        if world == 1:
+            eng.render(0, spp)
+        else:
+            for (ya, yb) in my_bands:
+                eng.render(0, spp, (0, xres, ya, yb))
+            # frame end: one NCCL reduce of the per-rank film accumulators (zero outside the rank's bands)
+            eng.film_to_device_ptr(film_t.data_ptr())
+            dist.reduce(film_t, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                eng.film_from_device_ptr(film_t.data_ptr())
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    eng.stats_reset()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    clocks.stop_flag = True
+    s_after = eng.stats()
+    rays_rank_total = sum(s_after[k] for k in ("camera_rays", "indirect_rays", "shadow_rays"))   # over all K steps
+    dev_seconds = s_after["seconds_render"]                                                     # engine CUDA events, K steps
+    tvals = torch.tensor([wall, float(rays_rank_total), dev_seconds], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = tvals.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tvals.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        wall_max = float(tmax[0]); total_rays = float(tsum[1])
+    else:
+        wall_max = wall; total_rays = float(rays_rank_total)
+    # N = 1: device time of the K steps from the engine's CUDA events on its launch stream;
+    # N > 1: max over ranks of the barrier-bracketed region (includes the NCCL film reduce)
+    step_seconds = (dev_seconds if world == 1 else wall_max) / args.steps
+    value = total_rays / args.steps / step_seconds / 1e6
+    msamples = xres * yres * spp / step_seconds / 1e6
+
+    line = None
+    if rank == 0:
+        # ---- roofline: counting pass (nodes / triangles per ray) + per-kernel CUDA-event timing of a full step
+        tile = None if world == 1 else (0, xres, my_bands[0][0], my_bands[0][1])
+        eng.stats_reset(); eng.film_clear()
+        eng.render(0, min(spp, 16), tile, count_stats=True)
+        sc = eng.stats()
+        nc, tc = sc["nodes_visited"] / max(1, sc["counted_rays"]), sc["tris_tested"] / max(1, sc["counted_rays"])
+        ns, ts = sc["nodes_visited_shadow"] / max(1, sc["counted_rays_shadow"]), sc["tris_tested_shadow"] / max(1, sc["counted_rays_shadow"])
+        eng.stats_reset(); eng.film_clear()
+        eng.render(0, spp, tile, profile=True)
+        sp = eng.stats()
+        peak, peak_src = measured_peak_gbs()
+        rays_c = sp["camera_rays"] + sp["indirect_rays"]
+        rays_s = sp["shadow_rays"]
+        # algorithmic bytes per ray of each kernel: queue index 4 + ray 32 + result (hit record 16 + queue push 4 | L RMW 32)
+        bytes_c = rays_c * (4 + 32 + 20 + nc * 80.0 + tc * 48.0)
+        bytes_s = rays_s * (48 + 16 + ns * 80.0 + ts * 48.0)
+        kern = {"k_trace_closest": {"ms_total": sp["ms_trace_closest"], "launches": sp["launches_trace_closest"], "rays": rays_c,
+                                    "nodes_per_ray": nc, "tris_per_ray": tc, "gbs": bytes_c / max(1e-9, sp["ms_trace_closest"] * 1e-3) / 1e9},
+                "k_trace_shadow": {"ms_total": sp["ms_trace_shadow"], "launches": sp["launches_trace_shadow"], "rays": rays_s,
+                                   "nodes_per_ray": ns, "tris_per_ray": ts, "gbs": bytes_s / max(1e-9, sp["ms_trace_shadow"] * 1e-3) / 1e9},
+                "k_shade": {"ms_total": sp["ms_shade"]}, "step_ms_profiled": sp["seconds_render"] * 1e3}
+        dom = "k_trace_closest" if sp["ms_trace_closest"] >= sp["ms_trace_shadow"] else "k_trace_shadow"
+        achieved = kern[dom]["gbs"]
+        all_rays = rays_c + rays_s
+        n_bar = (sc["nodes_visited"] + sc["nodes_visited_shadow"]) / max(1, sc["counted_rays"] + sc["counted_rays_shadow"])
+        t_bar = (sc["tris_tested"] + sc["tris_tested_shadow"]) / max(1, sc["counted_rays"] + sc["counted_rays_shadow"])
+        b_ray = 300.0 + n_bar * 80.0 + t_bar * 48.0
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "kernel": dom, "peak_source": peak_src, "kernels": kern,
+                    "launch_avg_ms": kern[dom]["ms_total"] / max(1, kern[dom]["launches"]),
+                    "bytes_per_launch_avg": (bytes_c if dom == "k_trace_closest" else bytes_s) / max(1, kern[dom]["launches"]),
+                    # whole-step figure of SURVEY 8(d): B_ray = 300 + N*80 + T*48 over all rays of the step
+                    "step": {"bytes_per_ray": b_ray, "nodes_per_ray": n_bar, "tris_per_ray": t_bar,
+                             "achieved_gbs": value * 1e6 / world * b_ray / 1e9, "frac": value * 1e6 / world * b_ray / 1e9 / peak,
+                             "roofline_mrays_per_gpu": peak * 1e9 / b_ray / 1e6}}
+        # ---- e2e: scene file -> parse -> H2D upload -> BVH build -> render -> film read-back, every step
+        mesh_bytes = os.path.getsize(os.path.join(os.path.dirname(path), "heightfield.ply"))
+        e2e_steps = max(1, min(args.steps, 3))
+        te = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2 = E.Engine(local_rank)
+            e2.load_pbrt(path, seed=0)
+            e2.render(0, spp)
+            img = e2.image()
+            st2 = e2.stats()
+            e2.close()
+        te = (time.perf_counter() - te) / e2e_steps
+        rays_full = sum(st2[k] for k in ("camera_rays", "indirect_rays", "shadow_rays"))
+        e2e = {"value": rays_full / te / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(mesh_bytes), "d2h_bytes_per_step": int(img.nbytes),
+               "seconds_per_step": te, "seconds_bvh_build": st2["seconds_build"], "n_gpus": 1}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu = run_reference_cpu(make_scene(args.workload, spp=4, res=(256, 256)), 4, 16)
+        line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": step_seconds * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "msamples_per_s": msamples,
+                "config": {"workload": w["desc"], "spp": spp, "rays_per_step": total_rays / args.steps, "tiling": f"{band}-row bands round-robin over ranks",
+                           "l2": "inputs larger than L2: BVH+triangles %.0f MB + path state %.0f MB per pass" % ((st0["bytes_bvh_nodes"] + st0["bytes_bvh_tris"]) / 1e6, 4194304 * 240 / 1e6),
+                           "bvh": {"nodes": st0["bvh_nodes"], "depth": st0["bvh_depth"], "build_seconds": st0["seconds_build"]}},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(s_after["kernel_launches"]) * args.steps,
+                "clocks": clocks.summary(), "wall_seconds_timed_region": wall_max}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

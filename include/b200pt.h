@@ -145,12 +145,15 @@ typedef struct {
 typedef struct {
     double seconds_build, seconds_render;
     uint64_t camera_rays, indirect_rays, shadow_rays;
-    uint64_t nodes_visited, tris_tested;   /* only filled by a counting render (bpt_render with count_stats) */
-    uint64_t counted_rays;
+    /* traversal counters, filled only by a counting render (bpt_render flags bit0): closest-hit and shadow kernels */
+    uint64_t nodes_visited, tris_tested, counted_rays;            /* closest-hit rays */
+    uint64_t nodes_visited_shadow, tris_tested_shadow, counted_rays_shadow;
     int bvh_nodes, bvh_triangles, bvh_depth;
     uint64_t bytes_bvh_nodes, bytes_bvh_tris;
     int kernel_launches;
-    double ms_trace_closest, ms_trace_shadow, ms_shade, ms_other;  /* CUDA-event sums over the last bpt_render */
+    /* per-kernel-class CUDA-event sums, filled only by a profiling render (bpt_render flags bit1) */
+    double ms_trace_closest, ms_trace_shadow, ms_shade, ms_other;
+    int launches_trace_closest, launches_trace_shadow;
 } bpt_stats;
 
 /* ---- lifecycle ---- */
@@ -184,9 +187,10 @@ const char *bpt_frontend_error(void);
 /* ---- rendering ---- */
 /* Render sample indices [first_sample, first_sample + n_samples) of the pixels in pixel_bounds
  * (x0, x1, y0, y1; NULL = the film's pixel bounds) and accumulate them into the film.
- * flags: bit0 = count traversal statistics (slower counting kernels). */
+ * flags: bit0 = count traversal statistics (slower counting kernels); bit1 = time every kernel class with CUDA events. */
 int bpt_render(bpt_engine *e, int first_sample, int n_samples, const int *pixel_bounds, int flags);
 int bpt_film_clear(bpt_engine *e);
+int bpt_stats_reset(bpt_engine *e);
 /* Film accumulators: xres*yres*4 doubles {rgbSum[3], weightSum} over the FULL resolution (zero outside
  * rendered tiles), row-major, y down -- RGBFilm::Pixel (film.h:302-307). */
 int bpt_film_read(bpt_engine *e, double *rgbw_host);

@@ -701,8 +701,8 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     ECK(e->counts.alloc(Q_NCOUNTERS));
     ECK(cudaMemset(e->counts.p, 0, sizeof(int) * Q_NCOUNTERS));
     rc.counts = e->counts.p;
-    ECK(e->stats.alloc(8));
-    ECK(cudaMemset(e->stats.p, 0, sizeof(unsigned long long) * 8));
+    ECK(e->stats.alloc(16));
+    ECK(cudaMemset(e->stats.p, 0, sizeof(unsigned long long) * 16));
     rc.stats = e->stats.p;
     ECK(e->rawCursor.alloc(1));
     rc.bvh.nodes = e->bvh.nodes; rc.bvh.tris = e->bvh.tris;
@@ -749,7 +749,15 @@ extern "C" int bpt_render(bpt_engine *e, int first_sample, int n_samples, const 
     }
     if (x0 >= x1 || y0 >= y1) return BPT_OK;   // empty tile
     const bool count = flags & 1;
+    const bool profile = flags & 2;
     cudaStream_t st = e->stream;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof;   // (class, (start, stop))
+    auto profBegin = [&](int cls) {
+        if (!profile) return;
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, st); prof.push_back({cls, {a, b}});
+    };
+    auto profEnd = [&]() { if (profile) cudaEventRecord(prof.back().second.second, st); };
     const int sms = e->smCount;
     int launches = 0;
     ECK(cudaEventRecord(e->ev0, st));
@@ -769,13 +777,15 @@ extern "C" int bpt_render(bpt_engine *e, int first_sample, int n_samples, const 
             int maxDepth = rc.integ.maxDepth;
             for (int depth = 0; depth <= maxDepth; ++depth) {
                 LaunchResetDepth(rc, next, st); ++launches;
-                LaunchTraceClosest(rc, cur, count, sms, st); ++launches;
+                profBegin(0); LaunchTraceClosest(rc, cur, count, sms, st); ++launches; profEnd();
                 if (rc.nInfinite > 0) { LaunchHandleEscaped(rc, sms, st); ++launches; }
                 if (e->haveAreaLights) { LaunchHandleEmissive(rc, sms, st); ++launches; }
                 if (depth == maxDepth) break;
+                profBegin(2);
                 for (int m = 0; m < MAT_NTAGS; ++m)
                     if (e->materialPresent[m]) { LaunchShade(rc, m, next, sms, st); ++launches; }
-                LaunchTraceShadow(rc, count, sms, st); ++launches;
+                profEnd();
+                profBegin(1); LaunchTraceShadow(rc, count, sms, st); ++launches; profEnd();
                 std::swap(cur, next);
             }
             LaunchUpdateFilm(rc, x0, x1, by0, by1, ns, sms, st); ++launches;
@@ -788,6 +798,14 @@ extern "C" int bpt_render(bpt_engine *e, int first_sample, int n_samples, const 
     cudaEventElapsedTime(&ms, e->ev0, e->ev1);
     e->st.seconds_render += ms * 1e-3;
     e->st.kernel_launches += launches;
+    for (auto &pe : prof) {
+        float pm = 0;
+        cudaEventElapsedTime(&pm, pe.second.first, pe.second.second);
+        if (pe.first == 0) { e->st.ms_trace_closest += pm; e->st.launches_trace_closest++; }
+        else if (pe.first == 1) { e->st.ms_trace_shadow += pm; e->st.launches_trace_shadow++; }
+        else e->st.ms_shade += pm;
+        cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second);
+    }
     return BPT_OK;
 }
 
@@ -795,8 +813,15 @@ extern "C" int bpt_film_clear(bpt_engine *e) {
     if (!e || !e->committed) return BPT_ERR_INVALID;
     ECK(cudaSetDevice(e->device));
     ECK(cudaMemset(e->filmPixels.p, 0, sizeof(double4) * e->filmPixels.n));
-    ECK(cudaMemset(e->stats.p, 0, sizeof(unsigned long long) * 8));
+    return BPT_OK;
+}
+extern "C" int bpt_stats_reset(bpt_engine *e) {
+    if (!e || !e->committed) return BPT_ERR_INVALID;
+    ECK(cudaSetDevice(e->device));
+    ECK(cudaMemset(e->stats.p, 0, sizeof(unsigned long long) * 16));
     e->st.seconds_render = 0; e->st.kernel_launches = 0;
+    e->st.ms_trace_closest = e->st.ms_trace_shadow = e->st.ms_shade = e->st.ms_other = 0;
+    e->st.launches_trace_closest = e->st.launches_trace_shadow = 0;
     return BPT_OK;
 }
 extern "C" int bpt_film_read(bpt_engine *e, double *out) {
@@ -840,13 +865,14 @@ extern "C" int bpt_film_dims(const bpt_engine *e, int *xres, int *yres) {
 extern "C" int bpt_get_stats(bpt_engine *e, bpt_stats *out) {
     if (!e || !out) return BPT_ERR_INVALID;
     if (e->committed) {
-        unsigned long long h[8];
+        unsigned long long h[16];
         ECK(cudaSetDevice(e->device));
         ECK(cudaMemcpy(h, e->stats.p, sizeof(h), cudaMemcpyDeviceToHost));
         e->st.camera_rays = h[0];
         e->st.indirect_rays = h[1] >= h[0] ? h[1] - h[0] : 0;
         e->st.shadow_rays = h[2];
         e->st.nodes_visited = h[3]; e->st.tris_tested = h[4]; e->st.counted_rays = h[5];
+        e->st.nodes_visited_shadow = h[6]; e->st.tris_tested_shadow = h[7]; e->st.counted_rays_shadow = h[8];
     }
     *out = e->st;
     return BPT_OK;

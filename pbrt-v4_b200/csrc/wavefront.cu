@@ -233,9 +233,9 @@ __global__ void __launch_bounds__(128) k_trace_shadow(RenderCtx rc) {
         }
     }
     if (COUNT) {
-        atomicAdd(&rc.stats[3], (unsigned long long)locNodes);
-        atomicAdd(&rc.stats[4], (unsigned long long)locTris);
-        atomicAdd(&rc.stats[5], (unsigned long long)locRays);
+        atomicAdd(&rc.stats[6], (unsigned long long)locNodes);
+        atomicAdd(&rc.stats[7], (unsigned long long)locTris);
+        atomicAdd(&rc.stats[8], (unsigned long long)locRays);
     }
 }
 

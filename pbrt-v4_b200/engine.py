@@ -18,16 +18,17 @@ class BptStats(C.Structure):
     _fields_ = [("seconds_build", C.c_double), ("seconds_render", C.c_double),
                 ("camera_rays", C.c_uint64), ("indirect_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("counted_rays", C.c_uint64),
+                ("nodes_visited_shadow", C.c_uint64), ("tris_tested_shadow", C.c_uint64), ("counted_rays_shadow", C.c_uint64),
                 ("bvh_nodes", C.c_int), ("bvh_triangles", C.c_int), ("bvh_depth", C.c_int),
                 ("bytes_bvh_nodes", C.c_uint64), ("bytes_bvh_tris", C.c_uint64), ("kernel_launches", C.c_int),
                 ("ms_trace_closest", C.c_double), ("ms_trace_shadow", C.c_double), ("ms_shade", C.c_double),
-                ("ms_other", C.c_double)]
+                ("ms_other", C.c_double), ("launches_trace_closest", C.c_int), ("launches_trace_shadow", C.c_int)]
 
 
 EXPORTS = """bpt_create bpt_destroy bpt_last_error bpt_scene_begin bpt_scene_set_camera bpt_scene_set_film
 bpt_scene_set_filter bpt_scene_set_sampler bpt_scene_set_integrator bpt_scene_set_materials bpt_scene_set_area_lights
 bpt_scene_add_mesh bpt_scene_add_instance bpt_scene_add_light bpt_scene_add_medium bpt_scene_set_camera_medium
-bpt_scene_commit bpt_load_pbrt bpt_load_pbrt_ex bpt_frontend_error bpt_render bpt_film_clear bpt_film_read bpt_film_write
+bpt_scene_commit bpt_load_pbrt bpt_load_pbrt_ex bpt_frontend_error bpt_render bpt_film_clear bpt_stats_reset bpt_film_read bpt_film_write
 bpt_film_copy_to_device bpt_film_copy_from_device bpt_film_resolve bpt_film_dims bpt_get_stats bpt_trace_closest
 bpt_trace_any bpt_trace_closest_device bpt_probe_sampler bpt_probe_intersect_triangle""".split()
 
@@ -50,6 +51,7 @@ def load_library():
     lib.bpt_load_pbrt_ex.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
     lib.bpt_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
     lib.bpt_film_clear.argtypes = [C.c_void_p]
+    lib.bpt_stats_reset.argtypes = [C.c_void_p]
     lib.bpt_film_read.argtypes = [C.c_void_p, C.c_void_p]
     lib.bpt_film_write.argtypes = [C.c_void_p, C.c_void_p]
     lib.bpt_film_copy_to_device.argtypes = [C.c_void_p, C.c_void_p]
@@ -106,14 +108,17 @@ class Engine:
                            f"{self.lib.bpt_last_error(self.h).decode()}")
 
     # ---- render
-    def render(self, first_sample, n_samples, pixel_bounds=None, count_stats=False):
+    def render(self, first_sample, n_samples, pixel_bounds=None, count_stats=False, profile=False):
         pb = None
         if pixel_bounds is not None:
             pb = (C.c_int * 4)(*[int(v) for v in pixel_bounds])
-        self._ck(self.lib.bpt_render(self.h, int(first_sample), int(n_samples), pb, 1 if count_stats else 0), "bpt_render")
+        self._ck(self.lib.bpt_render(self.h, int(first_sample), int(n_samples), pb, (1 if count_stats else 0) | (2 if profile else 0)), "bpt_render")
 
     def film_clear(self):
         self._ck(self.lib.bpt_film_clear(self.h), "bpt_film_clear")
+
+    def stats_reset(self):
+        self._ck(self.lib.bpt_stats_reset(self.h), "bpt_stats_reset")
 
     def dims(self):
         x, y = C.c_int(), C.c_int()
