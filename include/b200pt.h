@@ -215,6 +215,9 @@ int bpt_probe_sampler(bpt_engine *e, const int *pixels_xy, const int *sample_ind
 int bpt_probe_intersect_triangle(bpt_engine *e, const float *rays /* n x 7: o, d, tMax */, const float *tris /* n x 9 */,
                                  int n, float *out /* n x 5: hit, b0, b1, b2, t */);
 
+/* device evaluation of libdevice / double-rounded transcendental candidates (fn: see wavefront.cu k_probe_math) */
+int bpt_probe_math(bpt_engine *e, int fn, const float *x, const float *y, int n, float *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,8 +46,9 @@ BPT_D Vec3 PermuteK(Vec3 v, int kz) {
     return kz == 2 ? v : (kz == 0 ? Vec3(v.y, v.z, v.x) : Vec3(v.z, v.x, v.y));
 }
 // Same arithmetic as IntersectTriangle (shapes.h) with the per-ray terms hoisted.
+// The degenerate-triangle early-out of the reference (LengthSquared(Cross(p2 - p0, p1 - p0)) == 0) depends only on the
+// triangle; the builder evaluates it once and stores the verdict in bit 31 of the leaf record's class word.
 BPT_D bool IntersectTrianglePre(const RayPre &r, float tMax, Pt3 p0, Pt3 p1, Pt3 p2, TriHit *hit) {
-    if (LengthSquared(Cross(p2 - p0, p1 - p0)) == 0) return false;
     Vec3 p0t = PermuteK(p0 - r.o, r.kz), p1t = PermuteK(p1 - r.o, r.kz), p2t = PermuteK(p2 - r.o, r.kz);
     p0t.x += r.Sx * p0t.z; p0t.y += r.Sy * p0t.z;
     p1t.x += r.Sx * p1t.z; p1t.y += r.Sy * p1t.z;
@@ -202,7 +203,8 @@ BPT_D void TraceRay(const BVHView &bvh, Pt3 o, Vec3 d, float tMax, HitRec *rec, 
             float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
             if (COUNT) ++*nTris;
             TriHit th;
-            if (IntersectTrianglePre(rp, rec->t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th)) {
+            if (!(__float_as_uint(b.w) & 0x80000000u) &&
+                IntersectTrianglePre(rp, rec->t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th)) {
                 rec->tri = (int)tri; rec->b0 = th.b0; rec->b1 = th.b1; rec->b2 = th.b2; rec->t = th.t;
                 if (ANYHIT) return;
                 tBox = th.t * (1 + 2 * gamma_n(3));
@@ -211,6 +213,133 @@ BPT_D void TraceRay(const BVHView &bvh, Pt3 o, Vec3 d, float tMax, HitRec *rec, 
         if ((cur.y & 0xff000000u) == 0) {
             if (sp == 0) break;
             cur = stack[--sp];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Warp-synchronous persistent traversal (the production path).
+//
+// ncu on the first per-lane formulation (profiles/r01_*) showed 4.0 active threads per issued instruction: with
+// independent thread scheduling the lanes of a warp drifted apart and every triangle test ran with one lane.
+// Here the warp advances in explicit lock-step phases -- [fetch] [one node step] [triangle tests] [pop / commit] --
+// separated by warp votes, so lanes doing the same kind of work execute together, and finished lanes are refilled
+// from the ray queue (dynamic fetch) once enough of them are idle.
+//
+//   Load(i, &o, &d, &tMax)      reads ray i of the queue
+//   Commit(i, rec)              stores the result of ray i (called exactly once per ray, by the lane that owns it)
+constexpr int kFetchThreshold = 8;     // refill when at least this many lanes are idle
+constexpr int kTriCap = 8;             // per-lane ring of deferred leaf groups (triBase, hit mask); one entry per node step
+constexpr int kTriBlock = 5;           // a lane stops taking node steps while it holds more than this many groups
+constexpr int kFlushLanes = 16;        // start triangle rounds when this many lanes have candidates
+constexpr int kRoundLanes = 8;         // keep going while this many lanes still have candidates
+
+template <bool ANYHIT, bool COUNT, typename LoadF, typename CommitF>
+BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF Load, CommitF Commit, unsigned *nNodes,
+                              unsigned *nTris, unsigned *nRaysDone) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    __shared__ uint2 s_tri[kTriCap][128];
+    uint2 (*triRing)[128] = s_tri;
+    const int tid = threadIdx.x;
+    int rayIdx = -1;
+    bool exhausted = false;
+    RayPre rp; Vec3 idir, ov; unsigned octinv4 = 0; float tBox = 0;
+    uint2 stack[BPT_STACK_SIZE];
+    int sp = 0;
+    unsigned head = 0, tail = 0;   // deferred triangle ring [head, tail)
+    uint2 cur = make_uint2(0, 0);
+    HitRec rec; rec.tri = -1; rec.t = 0; rec.b0 = rec.b1 = rec.b2 = 0;
+    while (true) {
+        // ---- fetch
+        unsigned idle = __ballot_sync(FULL, rayIdx < 0);
+        if (idle != 0 && !exhausted && (__popc(idle) >= kFetchThreshold || idle == FULL)) {
+            int nNeed = __popc(idle);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(cursor, nNeed);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + nNeed >= nRays) exhausted = true;
+            if (rayIdx < 0) {
+                int i = base + __popc(idle & ((1u << lane) - 1));
+                if (i < nRays) {
+                    rayIdx = i;
+                    Pt3 o; Vec3 d; float tMax;
+                    Load(i, &o, &d, &tMax);
+                    rp = MakeRayPre(o, d);
+                    idir = Vec3(SafeInvDir(d.x), SafeInvDir(d.y), SafeInvDir(d.z));
+                    ov = Vec3(o.x, o.y, o.z);
+                    unsigned octinv = (d.x < 0 ? 0u : 4u) | (d.y < 0 ? 0u : 2u) | (d.z < 0 ? 0u : 1u);
+                    octinv4 = octinv * 0x01010101u;
+                    tBox = tMax * (1 + 2 * gamma_n(3));
+                    sp = 0; head = tail = 0;
+                    cur = make_uint2(0u, 0x80000000u);
+                    rec.tri = -1; rec.t = tMax;
+                }
+            }
+        }
+        bool act = rayIdx >= 0;
+        if (!__any_sync(FULL, act)) break;
+        // ---- one node step for every lane that has node work and room for its triangle candidates
+        bool canNode = act && (cur.y & 0xff000000u) != 0 && (tail - head) <= (unsigned)kTriBlock;
+        if (canNode) {
+            unsigned hits_imask = cur.y;
+            unsigned child_bit = 31 - __clz(hits_imask);
+            unsigned child_base = cur.x;
+            cur.y &= ~(1u << child_bit);
+            if (cur.y & 0xff000000u) stack[sp++] = cur;
+            unsigned slot = (child_bit - 24) ^ (octinv4 & 0xff);
+            unsigned rel = __popc(hits_imask & ~(0xffffffffu << slot));
+            const float4 *np = bvh.nodes + (size_t)(child_base + rel) * 5;
+            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            if (COUNT) ++*nNodes;
+            unsigned hitmask = NodeIntersect(ov, idir, octinv4, tBox, n0, n1, n2, n3, n4);
+            cur.x = __float_as_uint(n1.x);
+            cur.y = (hitmask & 0xff000000u) | ExtractByte(__float_as_uint(n0.w), 3);
+            unsigned triBase = __float_as_uint(n1.y);
+            unsigned tmask = hitmask & 0x00ffffffu;
+            if (tmask) { triRing[tail & (kTriCap - 1)][tid] = make_uint2(triBase, tmask); ++tail; }
+            if ((cur.y & 0xff000000u) == 0 && sp > 0) cur = stack[--sp];
+        }
+        // ---- triangle rounds (deferred so that many lanes test together)
+        bool hasNode = act && (cur.y & 0xff000000u) != 0;
+        bool hasTri = act && tail != head;
+        unsigned triLanes = __ballot_sync(FULL, hasTri);
+        bool anyNodeRunnable = __any_sync(FULL, hasNode && (tail - head) <= (unsigned)kTriBlock);
+        bool finished = false;
+        if (triLanes != 0 && (__popc(triLanes) >= kFlushLanes || !anyNodeRunnable)) {
+            while (true) {
+                if (hasTri) {
+                    uint2 g = triRing[head & (kTriCap - 1)][tid];
+                    unsigned ti = 31 - __clz(g.y);
+                    g.y &= ~(1u << ti);
+                    if (g.y == 0) ++head; else triRing[head & (kTriCap - 1)][tid].y = g.y;
+                    unsigned tri = g.x + ti;
+                    const float4 *tp = bvh.tris + (size_t)tri * 3;
+                    float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                    if (COUNT) ++*nTris;
+                    TriHit th;
+                    if (!(__float_as_uint(b.w) & 0x80000000u) &&
+                        IntersectTrianglePre(rp, rec.t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th)) {
+                        rec.tri = (int)tri; rec.b0 = th.b0; rec.b1 = th.b1; rec.b2 = th.b2; rec.t = th.t;
+                        if (ANYHIT) { finished = true; head = tail; }
+                        else tBox = th.t * (1 + 2 * gamma_n(3));
+                    }
+                    hasTri = tail != head;
+                }
+                unsigned m = __ballot_sync(FULL, hasTri);
+                if (m == 0) break;
+                if (__popc(m) < kRoundLanes && anyNodeRunnable) break;
+            }
+        }
+        // ---- commit finished rays
+        if (act) {
+            if (!finished && (cur.y & 0xff000000u) == 0 && sp == 0 && tail == head) finished = true;
+            if (finished) {
+                Commit(rayIdx, rec);
+                if (COUNT) ++*nRaysDone;
+                rayIdx = -1;
+                cur = make_uint2(0, 0); sp = 0; head = tail = 0;
+            }
         }
     }
 }

@@ -260,7 +260,13 @@ __global__ void collapse_kernel(const CollapseItem *__restrict__ items, int nIte
                 // p2.w = mesh id  (input pool: p0.w = mesh id, p1.w = triangle index in mesh, p2.w = class bits)
                 float meshId = a.w;
                 a.w = __int_as_float(orig);
-                b.w = c.w;
+                // degenerate test of IntersectTriangle (shapes.cpp:172), same float expression, evaluated once per triangle
+                unsigned cls = __float_as_uint(c.w);
+                {
+                    Vec3 e20(c.x - a.x, c.y - a.y, c.z - a.z), e10(b.x - a.x, b.y - a.y, b.z - a.z);
+                    if (LengthSquared(Cross(e20, e10)) == 0) cls |= 0x80000000u;
+                }
+                b.w = __uint_as_float(cls);
                 c.w = meshId;
                 size_t o = 3 * (size_t)(triBase + triOff + t);
                 trisOut[o] = a; trisOut[o + 1] = b; trisOut[o + 2] = c;

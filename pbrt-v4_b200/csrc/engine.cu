@@ -932,3 +932,16 @@ extern "C" int bpt_probe_intersect_triangle(bpt_engine *e, const float *rays, co
     ECK(cudaMemcpy(out, c.p, sizeof(float) * 5 * (size_t)n, cudaMemcpyDeviceToHost));
     return BPT_OK;
 }
+
+extern "C" int bpt_probe_math(bpt_engine *e, int fn, const float *x, const float *y, int n, float *out) {
+    if (!e || n <= 0) return BPT_ERR_INVALID;
+    ECK(cudaSetDevice(e->device));
+    DevBuf<float> a, b, c;
+    ECK(a.alloc(n)); ECK(b.alloc(n)); ECK(c.alloc(n));
+    ECK(cudaMemcpy(a.p, x, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice));
+    ECK(cudaMemcpy(b.p, y, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice));
+    LaunchProbeMath(fn, a.p, b.p, n, c.p, e->stream);
+    ECK(cudaStreamSynchronize(e->stream));
+    ECK(cudaMemcpy(out, c.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
+    return BPT_OK;
+}

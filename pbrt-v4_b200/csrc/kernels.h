@@ -18,5 +18,6 @@ void LaunchResolveFilm(const double4 *pix, const DeviceFilm &film, float *rgbOut
 void LaunchTraceRaw(const BVHView &bvh, const float4 *rays, int n, float4 *hits, float *tOut, int *cursor, unsigned long long *stats,
                     bool any, bool count, int sms, cudaStream_t st);
 void LaunchProbeSampler(const SamplerParams &sp, const int *pxy, const int *sidx, const int *dim, int n, float *o1, float *o2, cudaStream_t st);
+void LaunchProbeMath(int fn, const float *x, const float *y, int n, float *out, cudaStream_t st);
 void LaunchProbeTri(const float *rays, const float *tris, int n, float *out, cudaStream_t st);
 }  // namespace bpt

@@ -96,6 +96,39 @@ BPT_HD float Radians(float deg) { return (kPi / 180) * deg; }
 BPT_HD bool IsNaN_(float v) { return v != v; }
 BPT_HD bool IsInf_(float v) { return fabsf(v) == BPT_INFINITY; }
 
+// Transcendentals.  The reference runs on glibc's float libm.  libdevice's float versions differ from glibc in
+// 15-33 % of arguments (measured on the B200 box, scripts/probe_math.py); evaluating in double and rounding once
+// differs in 0.06-1.3 % (sin, cos, exp, log, pow, tan) to 7-20 % (asin, acos, atan2, atanh, cosh) -- always by 1 ulp.
+// Host code uses libm itself.
+#if defined(__CUDA_ARCH__)
+#define BPT_DEF_T1(name, dfn, hfn) BPT_HD float name(float x) { return (float)dfn((double)x); }
+#else
+#define BPT_DEF_T1(name, dfn, hfn) BPT_HD float name(float x) { return hfn(x); }
+#endif
+BPT_DEF_T1(SinF, sin, sinf)
+BPT_DEF_T1(CosF, cos, cosf)
+BPT_DEF_T1(TanF, tan, tanf)
+BPT_DEF_T1(ASinF, asin, asinf)
+BPT_DEF_T1(ACosF, acos, acosf)
+BPT_DEF_T1(ATanhF, atanh, atanhf)
+BPT_DEF_T1(CoshF, cosh, coshf)
+BPT_DEF_T1(ExpF, exp, expf)
+BPT_DEF_T1(LogF, log, logf)
+BPT_HD float ATan2F(float y, float x) {
+#if defined(__CUDA_ARCH__)
+    return (float)atan2((double)y, (double)x);
+#else
+    return atan2f(y, x);
+#endif
+}
+BPT_HD float PowF(float x, float y) {
+#if defined(__CUDA_ARCH__)
+    return (float)pow((double)x, (double)y);
+#else
+    return powf(x, y);
+#endif
+}
+
 BPT_HD float DifferenceOfProducts(float a, float b, float c, float d) {
     float cd = c * d;
     float dop = FMA(a, b, -cd);
@@ -287,8 +320,8 @@ BPT_HD void CoordinateSystem(Vec3 v1, Vec3 *v2, Vec3 *v3) {
     *v3 = Vec3(b, sign + Sqr(v1.y) * a, -v1.y);
 }
 BPT_HD Vec3 GramSchmidt(Vec3 v, Vec3 w) { return v - Dot(v, w) * w; }
-BPT_HD float SafeASin(float x) { return asinf(Clampf(x, -1, 1)); }
-BPT_HD float SafeACos(float x) { return acosf(Clampf(x, -1, 1)); }
+BPT_HD float SafeASin(float x) { return ASinF(Clampf(x, -1, 1)); }
+BPT_HD float SafeACos(float x) { return ACosF(Clampf(x, -1, 1)); }
 BPT_HD float AngleBetween(Vec3 v1, Vec3 v2) {
     if (Dot(v1, v2) < 0) return kPi - 2 * SafeASin(Length(v1 + v2) / 2);
     else return 2 * SafeASin(Length(v2 - v1) / 2);

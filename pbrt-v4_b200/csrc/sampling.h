@@ -229,10 +229,10 @@ struct Sampler {
 };
 
 // ------------------------------------------------------------------ sampling routines
-BPT_HD float SampleVisibleWavelengths(float u) { return 538 - 138.888889f * atanhf(0.85691062f - 1.82750197f * u); }
+BPT_HD float SampleVisibleWavelengths(float u) { return 538 - 138.888889f * ATanhF(0.85691062f - 1.82750197f * u); }
 BPT_HD float VisibleWavelengthsPDF(float lambda) {
     if (lambda < 360 || lambda > 830) return 0;
-    return 0.0039398042f / Sqr(coshf(0.0072f * (lambda - 538)));
+    return 0.0039398042f / Sqr(CoshF(0.0072f * (lambda - 538)));
 }
 
 BPT_HD Vec2 SampleUniformDiskConcentric(Vec2 u) {
@@ -246,7 +246,7 @@ BPT_HD Vec2 SampleUniformDiskConcentric(Vec2 u) {
         r = uOffset.y;
         theta = kPiOver2 - kPiOver4 * (uOffset.x / uOffset.y);
     }
-    return {r * cosf(theta), r * sinf(theta)};
+    return {r * CosF(theta), r * SinF(theta)};
 }
 BPT_HD Vec3 SampleCosineHemisphere(Vec2 u) {
     Vec2 d = SampleUniformDiskConcentric(u);
@@ -279,7 +279,7 @@ BPT_HD Vec2 SampleBilinear(Vec2 u, const float w[4]) {
     return p;
 }
 BPT_HD float SphericalTriangleArea(Vec3 a, Vec3 b, Vec3 c) {
-    return fabsf(2 * atan2f(Dot(a, Cross(b, c)), 1 + Dot(a, b) + Dot(a, c) + Dot(b, c)));
+    return fabsf(2 * ATan2F(Dot(a, Cross(b, c)), 1 + Dot(a, b) + Dot(a, c) + Dot(b, c)));
 }
 
 // util/sampling.cpp SampleSphericalTriangle.  Returns false for the "{}" (all-zero barycentrics) exits.
@@ -298,9 +298,9 @@ BPT_HD void SampleSphericalTriangle(Pt3 v0, Pt3 v1, Pt3 v2, Pt3 p, Vec2 u, float
     float Ap_pi = Lerp(u.x, kPi, A_pi);
     float A = A_pi - kPi;
     *pdf = (A <= 0) ? 0 : 1 / A;
-    float cosAlpha = cosf(alpha), sinAlpha = sinf(alpha);
-    float sinPhi = sinf(Ap_pi) * cosAlpha - cosf(Ap_pi) * sinAlpha;
-    float cosPhi = cosf(Ap_pi) * cosAlpha + sinf(Ap_pi) * sinAlpha;
+    float cosAlpha = CosF(alpha), sinAlpha = SinF(alpha);
+    float sinPhi = SinF(Ap_pi) * cosAlpha - CosF(Ap_pi) * sinAlpha;
+    float cosPhi = CosF(Ap_pi) * cosAlpha + SinF(Ap_pi) * sinAlpha;
     float k1 = cosPhi + cosAlpha;
     float k2 = sinPhi - sinAlpha * Dot(a, b);
     float cosBp = (k2 + (DifferenceOfProducts(k2, cosPhi, k1, sinPhi)) * cosAlpha) /

@@ -167,37 +167,31 @@ __global__ void __launch_bounds__(256) k_generate_camera_rays(RenderCtx rc, int 
 // ---------------------------------------------------------------- closest hit (persistent threads + dynamic fetch)
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_closest(RenderCtx rc, int curQ) {
-    const int lane = threadIdx.x & 31;
     const int nRays = rc.counts[curQ];
     const int *queue = rc.queues[curQ];
     unsigned locNodes = 0, locTris = 0, locRays = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&rc.stats[1], (unsigned long long)nRays);
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&rc.counts[Q_CURSOR_CLOSEST], 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= nRays) break;
-        int idx = base + lane;
-        if (idx < nRays) {
-            int slot = queue[idx];
-            float4 o4 = rc.ps.rayO[slot], d4 = rc.ps.rayD[slot];
-            HitRec rec;
-            TraceRay<false, COUNT>(rc.bvh, Pt3(o4.x, o4.y, o4.z), Vec3(d4.x, d4.y, d4.z), BPT_INFINITY, &rec, &locNodes, &locTris);
-            if (COUNT) ++locRays;
-            if (rec.tri < 0) {
-                if (rc.nInfinite > 0) { int p = WarpAggPush(&rc.counts[Q_ESCAPED]); rc.queues[Q_ESCAPED][p] = slot; }
-            } else {
-                const float4 *tp = rc.bvh.tris + (size_t)rec.tri * 3;
-                int orig = __float_as_int(__ldg(tp).w);
-                unsigned cls = __float_as_uint(__ldg(tp + 1).w);
-                rc.ps.hit[slot] = make_float4(__int_as_float(orig), rec.b0, rec.b1, rec.b2);
-                if (cls & 0x100u) { int p = WarpAggPush(&rc.counts[Q_HITLIGHT]); rc.queues[Q_HITLIGHT][p] = slot; }
-                unsigned mt = cls & 0xffu;
-                int p = WarpAggPush(&rc.counts[Q_MAT0 + mt]);
-                rc.queues[Q_MAT0 + mt][p] = slot;
-            }
+    auto load = [&](int i, Pt3 *o, Vec3 *d, float *tMax) {
+        int slot = queue[i];
+        float4 o4 = rc.ps.rayO[slot], d4 = rc.ps.rayD[slot];
+        *o = Pt3(o4.x, o4.y, o4.z); *d = Vec3(d4.x, d4.y, d4.z); *tMax = BPT_INFINITY;
+    };
+    auto commit = [&](int i, const HitRec &rec) {
+        int slot = queue[i];
+        if (rec.tri < 0) {
+            if (rc.nInfinite > 0) { int p = WarpAggPush(&rc.counts[Q_ESCAPED]); rc.queues[Q_ESCAPED][p] = slot; }
+        } else {
+            const float4 *tp = rc.bvh.tris + (size_t)rec.tri * 3;
+            int orig = __float_as_int(__ldg(tp).w);
+            unsigned cls = __float_as_uint(__ldg(tp + 1).w);
+            rc.ps.hit[slot] = make_float4(__int_as_float(orig), rec.b0, rec.b1, rec.b2);
+            if (cls & 0x100u) { int p = WarpAggPush(&rc.counts[Q_HITLIGHT]); rc.queues[Q_HITLIGHT][p] = slot; }
+            unsigned mt = cls & 0xffu;
+            int p = WarpAggPush(&rc.counts[Q_MAT0 + mt]);
+            rc.queues[Q_MAT0 + mt][p] = slot;
         }
-    }
+    };
+    TraversePersistent<false, COUNT>(rc.bvh, nRays, &rc.counts[Q_CURSOR_CLOSEST], load, commit, &locNodes, &locTris, &locRays);
     if (COUNT) {
         atomicAdd(&rc.stats[3], (unsigned long long)locNodes);
         atomicAdd(&rc.stats[4], (unsigned long long)locTris);
@@ -208,30 +202,23 @@ __global__ void __launch_bounds__(128) k_trace_closest(RenderCtx rc, int curQ) {
 // ---------------------------------------------------------------- shadow rays
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_shadow(RenderCtx rc) {
-    const int lane = threadIdx.x & 31;
     const int nRays = rc.counts[Q_SHADOW];
     unsigned locNodes = 0, locTris = 0, locRays = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&rc.stats[2], (unsigned long long)nRays);
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&rc.counts[Q_CURSOR_SHADOW], 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= nRays) break;
-        int idx = base + lane;
-        if (idx < nRays) {
-            ShadowItem it = rc.shadowItems[idx];
-            HitRec rec;
-            TraceRay<true, COUNT>(rc.bvh, Pt3(it.o_slot.x, it.o_slot.y, it.o_slot.z), Vec3(it.d.x, it.d.y, it.d.z), it.d.w, &rec,
-                                  &locNodes, &locTris);
-            if (COUNT) ++locRays;
-            if (rec.tri < 0) {
-                int slot = __float_as_int(it.o_slot.w);
-                float4 L = rc.ps.L[slot];
-                L.x += it.Ld.x; L.y += it.Ld.y; L.z += it.Ld.z; L.w += it.Ld.w;
-                rc.ps.L[slot] = L;
-            }
+    auto load = [&](int i, Pt3 *o, Vec3 *d, float *tMax) {
+        float4 a = rc.shadowItems[i].o_slot, b = rc.shadowItems[i].d;
+        *o = Pt3(a.x, a.y, a.z); *d = Vec3(b.x, b.y, b.z); *tMax = b.w;
+    };
+    auto commit = [&](int i, const HitRec &rec) {
+        if (rec.tri < 0) {
+            int slot = __float_as_int(rc.shadowItems[i].o_slot.w);
+            float4 Ld = rc.shadowItems[i].Ld;
+            float4 L = rc.ps.L[slot];
+            L.x += Ld.x; L.y += Ld.y; L.z += Ld.z; L.w += Ld.w;
+            rc.ps.L[slot] = L;
         }
-    }
+    };
+    TraversePersistent<true, COUNT>(rc.bvh, nRays, &rc.counts[Q_CURSOR_SHADOW], load, commit, &locNodes, &locTris, &locRays);
     if (COUNT) {
         atomicAdd(&rc.stats[6], (unsigned long long)locNodes);
         atomicAdd(&rc.stats[7], (unsigned long long)locTris);
@@ -507,24 +494,18 @@ __global__ void k_resolve_film(const double4 *pix, DeviceFilm film, float *rgbOu
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_raw(BVHView bvh, const float4 *rays, int n, float4 *hits, float *tOut, int *cursor,
                                                    unsigned long long *stats) {
-    const int lane = threadIdx.x & 31;
-    unsigned locNodes = 0, locTris = 0;
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(cursor, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        int i = base + lane;
-        if (i < n) {
-            float4 a = rays[2 * (size_t)i], b = rays[2 * (size_t)i + 1];
-            HitRec rec;
-            TraceRay<ANY, COUNT>(bvh, Pt3(a.x, a.y, a.z), Vec3(b.x, b.y, b.z), a.w, &rec, &locNodes, &locTris);
-            int orig = -1;
-            if (rec.tri >= 0) orig = __float_as_int(__ldg(bvh.tris + (size_t)rec.tri * 3).w);
-            hits[i] = make_float4(__int_as_float(orig), rec.b0, rec.b1, rec.b2);
-            if (tOut) tOut[i] = rec.tri >= 0 ? rec.t : BPT_INFINITY;
-        }
-    }
+    unsigned locNodes = 0, locTris = 0, locRays = 0;
+    auto load = [&](int i, Pt3 *o, Vec3 *d, float *tMax) {
+        float4 a = rays[2 * (size_t)i], b = rays[2 * (size_t)i + 1];
+        *o = Pt3(a.x, a.y, a.z); *d = Vec3(b.x, b.y, b.z); *tMax = a.w;
+    };
+    auto commit = [&](int i, const HitRec &rec) {
+        int orig = -1;
+        if (rec.tri >= 0) orig = __float_as_int(__ldg(bvh.tris + (size_t)rec.tri * 3).w);
+        hits[i] = make_float4(__int_as_float(orig), rec.b0, rec.b1, rec.b2);
+        if (tOut) tOut[i] = rec.tri >= 0 ? rec.t : BPT_INFINITY;
+    };
+    TraversePersistent<ANY, COUNT>(bvh, n, cursor, load, commit, &locNodes, &locTris, &locRays);
     if (COUNT && stats) { atomicAdd(&stats[3], (unsigned long long)locNodes); atomicAdd(&stats[4], (unsigned long long)locTris); }
 }
 
@@ -549,10 +530,47 @@ __global__ void k_probe_tri(const float *rays, const float *tris, int n, float *
     // cross-check the hoisted variant used by traversal
     RayPre rp = MakeRayPre(Pt3(r[0], r[1], r[2]), Vec3(r[3], r[4], r[5]));
     TriHit th2{0, 0, 0, 0};
-    bool hit2 = IntersectTrianglePre(rp, r[6], Pt3(t[0], t[1], t[2]), Pt3(t[3], t[4], t[5]), Pt3(t[6], t[7], t[8]), &th2);
+    bool degenerate = LengthSquared(Cross(Pt3(t[6], t[7], t[8]) - Pt3(t[0], t[1], t[2]), Pt3(t[3], t[4], t[5]) - Pt3(t[0], t[1], t[2]))) == 0;
+    bool hit2 = !degenerate && IntersectTrianglePre(rp, r[6], Pt3(t[0], t[1], t[2]), Pt3(t[3], t[4], t[5]), Pt3(t[6], t[7], t[8]), &th2);
     bool same = hit == hit2 && (!hit || (th.b0 == th2.b0 && th.b1 == th2.b1 && th.b2 == th2.b2 && th.t == th2.t));
     float *o = out + 5 * (size_t)i;
     o[0] = same ? (hit ? 1.f : 0.f) : -1.f; o[1] = th.b0; o[2] = th.b1; o[3] = th.b2; o[4] = th.t;
+}
+
+__global__ void k_probe_math(int fn, const float *x, const float *y, int n, float *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a = x[i], b = y[i], r = 0;
+    switch (fn) {
+    case 0: r = sinf(a); break;
+    case 1: r = cosf(a); break;
+    case 2: r = asinf(a); break;
+    case 3: r = acosf(a); break;
+    case 4: r = atan2f(a, b); break;
+    case 5: r = atanhf(a); break;
+    case 6: r = coshf(a); break;
+    case 7: r = expf(a); break;
+    case 8: r = logf(a); break;
+    case 9: r = tanf(a); break;
+    case 10: r = (float)sin((double)a); break;
+    case 11: r = (float)cos((double)a); break;
+    case 12: r = (float)asin((double)a); break;
+    case 13: r = (float)acos((double)a); break;
+    case 14: r = (float)atan2((double)a, (double)b); break;
+    case 15: r = (float)atanh((double)a); break;
+    case 16: r = (float)cosh((double)a); break;
+    case 17: r = (float)exp((double)a); break;
+    case 18: r = (float)log((double)a); break;
+    case 19: r = powf(a, b); break;
+    case 20: r = (float)pow((double)a, (double)b); break;
+    case 21: r = sqrtf(a); break;
+    case 22: r = a / b; break;
+    case 23: r = (float)tan((double)a); break;
+    }
+    out[i] = r;
+}
+void LaunchProbeMath(int fn, const float *x, const float *y, int n, float *out, cudaStream_t st) {
+    k_probe_math<<<(n + 127) / 128, 128, 0, st>>>(fn, x, y, n, out);
 }
 
 // ================================================================= host-side launchers
