@@ -612,7 +612,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         }
     }
     if (!e->lights.empty()) return e->fail(BPT_ERR_UNSUPPORTED, "infinite lights are not implemented yet");
-    if (dlights.empty()) return e->fail(BPT_ERR_INVALID, "scene has no lights");
+    // a scene without lights is legal (it renders black; the raw ray entry points still work)
 
     // ---- light sampler (wavefront/integrator.cpp:182-186: uniform when there is exactly one light)
     LightBVHBuilder lb;

@@ -1,0 +1,43 @@
+"""Multi-GPU film tiling: one process per GPU, disjoint scanline bands, one reduce of the film accumulators at frame end.
+
+The sampler is a stateless function of (pixel, sample index, dimension) and the filter is importance-sampled into its own
+pixel (samplers.h:252-356, film.h:239-255), so bands are independent; the only exchange is the frame-end sum of the
+zero-padded per-rank accumulators {rgbSum[3], weightSum} (float64, order-independent because each pixel is non-zero on
+exactly one rank).  Works with any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests)."""
+
+
+def partition_bands(yres, world, rank, band=16, y0=0):
+    """Rows [y0, yres) in blocks of `band` rows dealt round-robin to the ranks -> list of (ya, yb) for this rank."""
+    out = []
+    for i, y in enumerate(range(y0, yres, band)):
+        if i % world == rank:
+            out.append((y, min(y + band, yres)))
+    return out
+
+
+def reduce_film(film, dist=None, dst=0):
+    """Sum the per-rank film accumulator tensors onto rank `dst` (in place).  `film`: [yres, xres, 4] float64."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return film
+    dist.reduce(film, dst=dst, op=dist.ReduceOp.SUM)
+    return film
+
+
+def render_tiled(engine, spp, dist=None, band=16, first_sample=0):
+    """Render this rank's bands and reduce; returns the film tensor (valid on rank 0)."""
+    import torch
+    x, y = engine.dims()
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    engine.film_clear()
+    if world == 1:
+        engine.render(first_sample, spp)
+    else:
+        for ya, yb in partition_bands(y, world, rank, band):
+            engine.render(first_sample, spp, (0, x, ya, yb))
+    film = torch.zeros((y, x, 4), dtype=torch.float64, device="cuda")
+    engine.film_to_device_ptr(film.data_ptr())
+    reduce_film(film, dist)
+    if rank == 0 and world > 1:
+        engine.film_from_device_ptr(film.data_ptr())
+    return film

@@ -1,0 +1,104 @@
+"""CPU tests of the host-side logic: C-ABI library loads and exports every declared symbol, the engine refuses to run
+without a GPU (no fallback), scene generators / PFM io, band partition, and the world_size=2 film reduce over gloo."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(engine_module):
+    hdr = open(os.path.join(ROOT, "include", "b200pt.h")).read()
+    declared = set(re.findall(r"\b(bpt_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = engine_module.load_library()
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    out = subprocess.run(["nm", "-D", "--defined-only", engine_module.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (bpt_[a-z0-9_]+)", out))
+    assert declared <= exported
+
+
+def test_no_cpu_fallback(engine_module):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(engine_module.BptError) as ei:
+        engine_module.Engine(0)
+    assert "no CUDA device" in str(ei.value) or "-2" in str(ei.value)
+
+
+def test_pfm_roundtrip(tmp_path):
+    from pbrt_v4_b200 import imageio
+    img = np.random.default_rng(0).random((5, 7, 3)).astype(np.float32)
+    p = str(tmp_path / "a.pfm")
+    imageio.write_pfm(p, img)
+    assert (imageio.read_pfm(p) == img).all()
+    assert imageio.rmse(img, img) == 0
+
+
+def test_scene_generators(tmp_path):
+    from pbrt_v4_b200 import scenes
+    p = scenes.cornell(str(tmp_path / "c"), res=(32, 32), spp=4)
+    txt = open(p).read()
+    assert txt.count("Shape \"trianglemesh\"") == 6 and "AreaLightSource" in txt
+    P, idx = scenes.heightfield_mesh(708)
+    assert len(idx) == 999698 and P.shape == (708 * 708, 3)
+    n = np.cross(P[idx[:, 1]] - P[idx[:, 0]], P[idx[:, 2]] - P[idx[:, 0]])
+    assert (n[:, 1] > 0).all()          # geometric normals point up
+    p = scenes.diffuse_heightfield(str(tmp_path / "h"), n=16, res=(32, 32), spp=4)
+    hdr = open(os.path.join(os.path.dirname(p), "heightfield.ply"), "rb").read(200)
+    assert b"element vertex 256" in hdr and b"element face 450" in hdr
+
+
+def test_partition_bands_is_a_partition():
+    from pbrt_v4_b200.parallel import partition_bands
+    for yres, world, band in ((1024, 8, 16), (1080, 4, 16), (77, 3, 5), (16, 8, 16)):
+        rows = np.zeros(yres, int)
+        for r in range(world):
+            for a, b in partition_bands(yres, world, r, band):
+                rows[a:b] += 1
+        assert (rows == 1).all()
+
+
+GLOO_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from pbrt_v4_b200.parallel import partition_bands, reduce_film
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+yres, xres = 40, 24
+full = torch.from_numpy(np.random.default_rng(5).random((yres, xres, 4)))       # the film a single rank would produce
+film = torch.zeros_like(full)
+for a, b in partition_bands(yres, world, rank, band=4):
+    film[a:b] = full[a:b]                                                          # this rank's tiles, zero elsewhere
+reduce_film(film, dist)
+if rank == 0:
+    assert torch.equal(film, full), "reduced film differs from the single-rank film"
+    print("GLOO_REDUCE_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_world_size_2_film_reduce_gloo(tmp_path):
+    w = tmp_path / "worker.py"
+    w.write_text(GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", str(w), ROOT], capture_output=True, text=True, env=env, timeout=300)
+    assert "GLOO_REDUCE_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def test_bench_reference_arm_is_wired():
+    # --impl reference must always print one JSON line (the reference binary exists in this container)
+    exe = os.path.join(ROOT, "oracle", "_ref", "bin", "pbrt")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built")
+    import bench
+    path = bench.make_scene("heightfield_small", spp=4, res=(64, 64))
+    r = bench.run_reference_cpu(path, 1, 4, threads=2)
+    assert r["kind"] == "reference" and r["value"] > 0
