@@ -254,6 +254,47 @@ static void DumpGolden(const char *path) {
         b.f32("spectrum_in", in);
         b.f32("spectrum_out", out);
     }
+    // ImageInfiniteLight: Le / SampleLi / PDF_Li on a seeded procedural 32x32 equal-area environment map
+    {
+        Allocator alloc;
+        const int res = 32;
+        Image img(PixelFormat::Float, {res, res}, {"R", "G", "B"}, nullptr, alloc);
+        std::vector<float> pix;
+        for (int y = 0; y < res; ++y)
+            for (int x = 0; x < res; ++x)
+                for (int c = 0; c < 3; ++c) {
+                    float v = (rng.Uniform<float>() < 0.02f ? 200.f : 1.f) * rng.Uniform<float>() * (c + 1);
+                    img.SetChannel({x, y}, c, v);
+                    pix.push_back(v);
+                }
+        Transform rfl = RotateX(-90) * RotateZ(25);
+        ImageInfiniteLight light(rfl, img, RGBColorSpace::sRGB, 0.37f, "golden", alloc);
+        light.Preprocess(Bounds3f(Point3f(-1, -2, -3), Point3f(2, 3, 5)));
+        std::vector<float> in, out;
+        for (int i = 0; i < 512; ++i) {
+            auto r = [&]() { return 2 * rng.Uniform<float>() - 1; };
+            Vector3f d = Normalize(Vector3f(r(), r(), r()));
+            Point2f u(rng.Uniform<float>(), rng.Uniform<float>());
+            SampledWavelengths lambda = SampledWavelengths::SampleVisible(rng.Uniform<float>());
+            SampledSpectrum Le = light.Le(Ray(Point3f(0, 0, 0), d), lambda);
+            LightSampleContext ctx(Interaction(Point3f(r(), r(), r()), 0.f, Medium()));
+            Float pdf = light.PDF_Li(ctx, d, true);
+            pstd::optional<LightLiSample> ls = light.SampleLi(ctx, u, lambda, true);
+            Point2f sq = EqualAreaSphereToSquare(d);
+            Vector3f back = EqualAreaSquareToSphere(u);
+            in.insert(in.end(), {d.x, d.y, d.z, u.x, u.y, lambda[0], lambda[1], lambda[2], lambda[3], ctx.p().x, ctx.p().y, ctx.p().z});
+            out.insert(out.end(), {Le[0], Le[1], Le[2], Le[3], pdf, sq.x, sq.y, back.x, back.y, back.z});
+            if (ls) out.insert(out.end(), {1.f, ls->L[0], ls->L[1], ls->L[2], ls->L[3], ls->wi.x, ls->wi.y, ls->wi.z, ls->pdf, ls->pLight.p().x, ls->pLight.p().y, ls->pLight.p().z});
+            else out.insert(out.end(), {0.f, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0});
+        }
+        std::vector<float> xf;
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) xf.push_back(rfl.GetMatrix()[i][j]);
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) xf.push_back(rfl.GetInverseMatrix()[i][j]);
+        b.f32("env_pixels", pix);
+        b.f32("env_xform", xf);
+        b.f32("env_in", in);
+        b.f32("env_out", out);
+    }
     // BVHAggregate closest hits on a seeded random triangle soup (hit record = primitive, b0, b1, b2, t)
     {
         Allocator alloc;

@@ -65,6 +65,262 @@ struct DiffuseBxDF {
     BPT_HD void Regularize() {}
 };
 
+// ---------------------------------------------------------------- scattering helpers (util/scattering.h)
+BPT_HD Vec3 Reflect(Vec3 wo, Vec3 n) { return -wo + 2 * Dot(wo, n) * n; }
+BPT_HD bool Refract(Vec3 wi, Nrm3 n, float eta, float *etap, Vec3 *wt) {
+    float cosTheta_i = Dot(n, wi);
+    if (cosTheta_i < 0) { eta = 1 / eta; cosTheta_i = -cosTheta_i; n = -n; }
+    float sin2Theta_i = stdmax(0.f, 1 - Sqr(cosTheta_i));
+    float sin2Theta_t = sin2Theta_i / Sqr(eta);
+    if (sin2Theta_t >= 1) return false;
+    float cosTheta_t = sqrtf(1 - sin2Theta_t);
+    *wt = -wi / eta + (cosTheta_i / eta - cosTheta_t) * V(n);
+    if (etap) *etap = eta;
+    return true;
+}
+BPT_HD float FrDielectric(float cosTheta_i, float eta) {
+    cosTheta_i = Clampf(cosTheta_i, -1, 1);
+    if (cosTheta_i < 0) { eta = 1 / eta; cosTheta_i = -cosTheta_i; }
+    float sin2Theta_i = 1 - Sqr(cosTheta_i);
+    float sin2Theta_t = sin2Theta_i / Sqr(eta);
+    if (sin2Theta_t >= 1) return 1.f;
+    float cosTheta_t = SafeSqrt(1 - sin2Theta_t);
+    float r_parl = (eta * cosTheta_i - cosTheta_t) / (eta * cosTheta_i + cosTheta_t);
+    float r_perp = (cosTheta_i - eta * cosTheta_t) / (cosTheta_i + eta * cosTheta_t);
+    return (Sqr(r_parl) + Sqr(r_perp)) / 2;
+}
+// pstd::complex<float> (util/pstd.h:1066-1229), including its implicit float -> complex promotions
+struct Cplx {
+    float re, im;
+    BPT_HD Cplx(float r) : re(r), im(0) {}
+    BPT_HD Cplx(float r, float i) : re(r), im(i) {}
+    BPT_HD Cplx operator+(Cplx z) const { return {re + z.re, im + z.im}; }
+    BPT_HD Cplx operator-(Cplx z) const { return {re - z.re, im - z.im}; }
+    BPT_HD Cplx operator*(Cplx z) const { return {re * z.re - im * z.im, re * z.im + im * z.re}; }
+    BPT_HD Cplx operator/(Cplx z) const {
+        float scale = 1 / (z.re * z.re + z.im * z.im);
+        return {scale * (re * z.re + im * z.im), scale * (im * z.re - re * z.im)};
+    }
+};
+BPT_HD float CNorm(Cplx z) { return z.re * z.re + z.im * z.im; }
+BPT_HD Cplx CSqrt(Cplx z) {
+    float n = sqrtf(CNorm(z)), t1 = sqrtf(.5f * (n + fabsf(z.re))), t2 = .5f * z.im / t1;
+    if (n == 0) return Cplx(0);
+    if (z.re >= 0) return {t1, t2};
+    return {fabsf(t2), copysignf(t1, z.im)};
+}
+BPT_HD float FrComplex(float cosTheta_i, Cplx eta) {
+    cosTheta_i = Clampf(cosTheta_i, 0, 1);
+    float sin2Theta_i = 1 - Sqr(cosTheta_i);
+    Cplx sin2Theta_t = Cplx(sin2Theta_i) / (eta * eta);
+    Cplx cosTheta_t = CSqrt(Cplx(1) - sin2Theta_t);
+    Cplx r_parl = (eta * Cplx(cosTheta_i) - cosTheta_t) / (eta * Cplx(cosTheta_i) + cosTheta_t);
+    Cplx r_perp = (Cplx(cosTheta_i) - eta * cosTheta_t) / (Cplx(cosTheta_i) + eta * cosTheta_t);
+    return (CNorm(r_parl) + CNorm(r_perp)) / 2;
+}
+BPT_HD Spec FrComplexSpec(float cosTheta_i, Spec eta, Spec k) {
+    Spec r;
+    for (int i = 0; i < 4; ++i) r[i] = FrComplex(cosTheta_i, Cplx(eta[i], k[i]));
+    return r;
+}
+BPT_HD Vec2 SampleUniformDiskPolar(Vec2 u) {
+    float r = sqrtf(u.x);
+    float theta = 2 * kPi * u.y;
+    return {r * CosF(theta), r * SinF(theta)};
+}
+
+// TrowbridgeReitzDistribution (util/scattering.h:109-214)
+struct TRDist {
+    float alpha_x, alpha_y;
+    BPT_HD TRDist() : alpha_x(0), alpha_y(0) {}
+    BPT_HD TRDist(float ax, float ay) : alpha_x(ax), alpha_y(ay) {
+        if (!EffectivelySmooth()) { alpha_x = stdmax(alpha_x, 1e-4f); alpha_y = stdmax(alpha_y, 1e-4f); }
+    }
+    BPT_HD bool EffectivelySmooth() const { return stdmax(alpha_x, alpha_y) < 1e-3f; }
+    BPT_HD float D(Vec3 wm) const {
+        float tan2Theta = Tan2Theta(wm);
+        if (IsInf_(tan2Theta)) return 0;
+        float cos4Theta = Sqr(Cos2Theta(wm));
+        if (cos4Theta < 1e-16f) return 0;
+        float e = tan2Theta * (Sqr(CosPhi(wm) / alpha_x) + Sqr(SinPhi(wm) / alpha_y));
+        return 1 / (kPi * alpha_x * alpha_y * cos4Theta * Sqr(1 + e));
+    }
+    BPT_HD float Lambda(Vec3 w) const {
+        float tan2Theta = Tan2Theta(w);
+        if (IsInf_(tan2Theta)) return 0;
+        float alpha2 = Sqr(CosPhi(w) * alpha_x) + Sqr(SinPhi(w) * alpha_y);
+        return (sqrtf(1 + alpha2 * tan2Theta) - 1) / 2;
+    }
+    BPT_HD float G1(Vec3 w) const { return 1 / (1 + Lambda(w)); }
+    BPT_HD float G(Vec3 wo, Vec3 wi) const { return 1 / (1 + Lambda(wo) + Lambda(wi)); }
+    BPT_HD float D(Vec3 w, Vec3 wm) const { return G1(w) / AbsCosTheta(w) * D(wm) * AbsDot(w, wm); }
+    BPT_HD float PDF(Vec3 w, Vec3 wm) const { return D(w, wm); }
+    BPT_HD Vec3 Sample_wm(Vec3 w, Vec2 u) const {
+        Vec3 wh = Normalize(Vec3(alpha_x * w.x, alpha_y * w.y, w.z));
+        if (wh.z < 0) wh = -wh;
+        Vec3 T1 = (wh.z < 0.99999f) ? Normalize(Cross(Vec3(0, 0, 1), wh)) : Vec3(1, 0, 0);
+        Vec3 T2 = Cross(wh, T1);
+        Vec2 p = SampleUniformDiskPolar(u);
+        float h = sqrtf(1 - Sqr(p.x));
+        p.y = Lerp((1 + wh.z) / 2, h, p.y);
+        float pz = sqrtf(stdmax(0.f, 1 - (Sqr(p.x) + Sqr(p.y))));
+        Vec3 nh = p.x * T1 + p.y * T2 + pz * wh;
+        return Normalize(Vec3(alpha_x * nh.x, alpha_y * nh.y, stdmax(1e-6f, nh.z)));
+    }
+    BPT_HD static float RoughnessToAlpha(float roughness) { return sqrtf(roughness); }
+    BPT_HD void Regularize() {
+        if (alpha_x < 0.3f) alpha_x = Clampf(2 * alpha_x, 0.1f, 0.3f);
+        if (alpha_y < 0.3f) alpha_y = Clampf(2 * alpha_y, 0.1f, 0.3f);
+    }
+};
+
+// ---------------------------------------------------------------- ConductorBxDF (bxdfs.h:280-383)
+struct ConductorBxDF {
+    TRDist mfDistrib;
+    Spec eta, k;
+    BPT_HD int Flags() const { return mfDistrib.EffectivelySmooth() ? BXDF_SPECULAR_REFLECTION : BXDF_GLOSSY_REFLECTION; }
+    BPT_HD BSDFSample Sample_f(Vec3 wo, float uc, Vec2 u, int mode, int sampleFlags = REFLTRANS_ALL) const {
+        if (!(sampleFlags & REFLTRANS_REFLECTION)) return {};
+        if (mfDistrib.EffectivelySmooth()) {
+            Vec3 wi(-wo.x, -wo.y, wo.z);
+            Spec f = FrComplexSpec(AbsCosTheta(wi), eta, k) / AbsCosTheta(wi);
+            return BSDFSample(f, wi, 1, BXDF_SPECULAR_REFLECTION);
+        }
+        if (wo.z == 0) return {};
+        Vec3 wm = mfDistrib.Sample_wm(wo, u);
+        Vec3 wi = Reflect(wo, wm);
+        if (!SameHemisphere(wo, wi)) return {};
+        float pdf = mfDistrib.PDF(wo, wm) / (4 * AbsDot(wo, wm));
+        float cosTheta_o = AbsCosTheta(wo), cosTheta_i = AbsCosTheta(wi);
+        if (cosTheta_i == 0 || cosTheta_o == 0) return {};
+        Spec F = FrComplexSpec(AbsDot(wo, wm), eta, k);
+        Spec f = mfDistrib.D(wm) * F * mfDistrib.G(wo, wi) / (4 * cosTheta_i * cosTheta_o);
+        return BSDFSample(f, wi, pdf, BXDF_GLOSSY_REFLECTION);
+    }
+    BPT_HD Spec f(Vec3 wo, Vec3 wi, int mode) const {
+        if (!SameHemisphere(wo, wi)) return Spec(0.f);
+        if (mfDistrib.EffectivelySmooth()) return Spec(0.f);
+        float cosTheta_o = AbsCosTheta(wo), cosTheta_i = AbsCosTheta(wi);
+        if (cosTheta_i == 0 || cosTheta_o == 0) return Spec(0.f);
+        Vec3 wm = wi + wo;
+        if (LengthSquared(wm) == 0) return Spec(0.f);
+        wm = Normalize(wm);
+        Spec F = FrComplexSpec(AbsDot(wo, wm), eta, k);
+        return mfDistrib.D(wm) * F * mfDistrib.G(wo, wi) / (4 * cosTheta_i * cosTheta_o);
+    }
+    BPT_HD float PDF(Vec3 wo, Vec3 wi, int mode, int sampleFlags = REFLTRANS_ALL) const {
+        if (!(sampleFlags & REFLTRANS_REFLECTION)) return 0;
+        if (!SameHemisphere(wo, wi)) return 0;
+        if (mfDistrib.EffectivelySmooth()) return 0;
+        Vec3 wm = wo + wi;
+        if (LengthSquared(wm) == 0) return 0;
+        wm = FaceForward(Normalize(wm), Nrm3(0, 0, 1));
+        return mfDistrib.PDF(wo, wm) / (4 * AbsDot(wo, wm));
+    }
+    BPT_HD void Regularize() { mfDistrib.Regularize(); }
+};
+
+// ---------------------------------------------------------------- DielectricBxDF (bxdfs.cpp:77-258)
+struct DielectricBxDF {
+    float eta;
+    TRDist mfDistrib;
+    BPT_HD int Flags() const {
+        int flags = (eta == 1) ? BXDF_TRANSMISSION : (BXDF_REFLECTION | BXDF_TRANSMISSION);
+        return flags | (mfDistrib.EffectivelySmooth() ? BXDF_SPECULAR : BXDF_GLOSSY);
+    }
+    BPT_HD BSDFSample Sample_f(Vec3 wo, float uc, Vec2 u, int mode, int sampleFlags = REFLTRANS_ALL) const {
+        if (eta == 1 || mfDistrib.EffectivelySmooth()) {
+            float R = FrDielectric(CosTheta(wo), eta), T = 1 - R;
+            float pr = R, pt = T;
+            if (!(sampleFlags & REFLTRANS_REFLECTION)) pr = 0;
+            if (!(sampleFlags & REFLTRANS_TRANSMISSION)) pt = 0;
+            if (pr == 0 && pt == 0) return {};
+            if (uc < pr / (pr + pt)) {
+                Vec3 wi(-wo.x, -wo.y, wo.z);
+                Spec fr(R / AbsCosTheta(wi));
+                return BSDFSample(fr, wi, pr / (pr + pt), BXDF_SPECULAR_REFLECTION);
+            } else {
+                Vec3 wi; float etap;
+                bool valid = Refract(wo, Nrm3(0, 0, 1), eta, &etap, &wi);
+                if (!valid) return {};
+                Spec ft(T / AbsCosTheta(wi));
+                if (mode == MODE_RADIANCE) ft /= Sqr(etap);
+                return BSDFSample(ft, wi, pt / (pr + pt), BXDF_SPECULAR_TRANSMISSION, etap);
+            }
+        } else {
+            Vec3 wm = mfDistrib.Sample_wm(wo, u);
+            float R = FrDielectric(Dot(wo, wm), eta);
+            float T = 1 - R;
+            float pr = R, pt = T;
+            if (!(sampleFlags & REFLTRANS_REFLECTION)) pr = 0;
+            if (!(sampleFlags & REFLTRANS_TRANSMISSION)) pt = 0;
+            if (pr == 0 && pt == 0) return {};
+            float pdf;
+            if (uc < pr / (pr + pt)) {
+                Vec3 wi = Reflect(wo, wm);
+                if (!SameHemisphere(wo, wi)) return {};
+                pdf = mfDistrib.PDF(wo, wm) / (4 * AbsDot(wo, wm)) * pr / (pr + pt);
+                Spec f(mfDistrib.D(wm) * mfDistrib.G(wo, wi) * R / (4 * CosTheta(wi) * CosTheta(wo)));
+                return BSDFSample(f, wi, pdf, BXDF_GLOSSY_REFLECTION);
+            } else {
+                float etap; Vec3 wi;
+                bool tir = !Refract(wo, Nrm3(wm), eta, &etap, &wi);
+                if (tir) return {};   // (wi is uninitialised in the reference when tir; the test order there still returns {})
+                if (SameHemisphere(wo, wi) || wi.z == 0) return {};
+                float denom = Sqr(Dot(wi, wm) + Dot(wo, wm) / etap);
+                float dwm_dwi = AbsDot(wi, wm) / denom;
+                pdf = mfDistrib.PDF(wo, wm) * dwm_dwi * pt / (pr + pt);
+                Spec ft(T * mfDistrib.D(wm) * mfDistrib.G(wo, wi) * fabsf(Dot(wi, wm) * Dot(wo, wm) / (CosTheta(wi) * CosTheta(wo) * denom)));
+                if (mode == MODE_RADIANCE) ft /= Sqr(etap);
+                return BSDFSample(ft, wi, pdf, BXDF_GLOSSY_TRANSMISSION, etap);
+            }
+        }
+    }
+    BPT_HD Spec f(Vec3 wo, Vec3 wi, int mode) const {
+        if (eta == 1 || mfDistrib.EffectivelySmooth()) return Spec(0.f);
+        float cosTheta_o = CosTheta(wo), cosTheta_i = CosTheta(wi);
+        bool reflect = cosTheta_i * cosTheta_o > 0;
+        float etap = 1;
+        if (!reflect) etap = cosTheta_o > 0 ? eta : (1 / eta);
+        Vec3 wm = wi * etap + wo;
+        if (cosTheta_i == 0 || cosTheta_o == 0 || LengthSquared(wm) == 0) return Spec(0.f);
+        wm = FaceForward(Normalize(wm), Nrm3(0, 0, 1));
+        if (Dot(wm, wi) * cosTheta_i < 0 || Dot(wm, wo) * cosTheta_o < 0) return Spec(0.f);
+        float F = FrDielectric(Dot(wo, wm), eta);
+        if (reflect) return Spec(mfDistrib.D(wm) * mfDistrib.G(wo, wi) * F / fabsf(4 * cosTheta_i * cosTheta_o));
+        float denom = Sqr(Dot(wi, wm) + Dot(wo, wm) / etap) * cosTheta_i * cosTheta_o;
+        float ft = mfDistrib.D(wm) * (1 - F) * mfDistrib.G(wo, wi) * fabsf(Dot(wi, wm) * Dot(wo, wm) / denom);
+        if (mode == MODE_RADIANCE) ft /= Sqr(etap);
+        return Spec(ft);
+    }
+    BPT_HD float PDF(Vec3 wo, Vec3 wi, int mode, int sampleFlags = REFLTRANS_ALL) const {
+        if (eta == 1 || mfDistrib.EffectivelySmooth()) return 0;
+        float cosTheta_o = CosTheta(wo), cosTheta_i = CosTheta(wi);
+        bool reflect = cosTheta_i * cosTheta_o > 0;
+        float etap = 1;
+        if (!reflect) etap = cosTheta_o > 0 ? eta : (1 / eta);
+        Vec3 wm = wi * etap + wo;
+        if (cosTheta_i == 0 || cosTheta_o == 0 || LengthSquared(wm) == 0) return 0;
+        wm = FaceForward(Normalize(wm), Nrm3(0, 0, 1));
+        if (Dot(wm, wi) * cosTheta_i < 0 || Dot(wm, wo) * cosTheta_o < 0) return 0;
+        float R = FrDielectric(Dot(wo, wm), eta);
+        float T = 1 - R;
+        float pr = R, pt = T;
+        if (!(sampleFlags & REFLTRANS_REFLECTION)) pr = 0;
+        if (!(sampleFlags & REFLTRANS_TRANSMISSION)) pt = 0;
+        if (pr == 0 && pt == 0) return 0;
+        float pdf;
+        if (reflect) pdf = mfDistrib.PDF(wo, wm) / (4 * AbsDot(wo, wm)) * pr / (pr + pt);
+        else {
+            float denom = Sqr(Dot(wi, wm) + Dot(wo, wm) / etap);
+            float dwm_dwi = AbsDot(wi, wm) / denom;
+            pdf = mfDistrib.PDF(wo, wm) * dwm_dwi * pt / (pr + pt);
+        }
+        return pdf;
+    }
+    BPT_HD void Regularize() { mfDistrib.Regularize(); }
+};
+
 // ---------------------------------------------------------------- BSDF frame wrapper (bsdf.h)
 template <typename BxDF>
 struct BSDF {

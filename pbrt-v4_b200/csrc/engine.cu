@@ -18,6 +18,7 @@
 #include "lightbvh.h"
 #include "tables.h"
 #include "xform.h"
+#include "lights.h"
 
 using namespace bpt;
 
@@ -110,6 +111,9 @@ struct bpt_engine {
     DevBuf<uint4> stateMisc;
     DevBuf<float2> stateAux;
     DevBuf<int> rawCursor;
+    DevBuf<DeviceImageLight> dImageLights;
+    DevBuf<float> dRgb2spec;
+    std::vector<std::unique_ptr<DevBuf<float>>> imgBufs;
     WideBVH bvh{};
     RenderCtx rc{};
     bool committed = false;
@@ -509,6 +513,33 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             else if (!MakeSpectrumRec(e, om.reflectance, ST_ALBEDO, spool, &dm.reflectance, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
             break;
         case BPT_MAT_INTERFACE: break;
+        case BPT_MAT_CONDUCTOR: {   // ConductorMaterial::Create (materials.cpp): eta/k default to Cu unless "reflectance" is given
+            bool haveRefl = om.reflectance.s.kind != BPT_SPEC_NONE;
+            if (haveRefl && (om.eta.s.kind != BPT_SPEC_NONE || om.k.s.kind != BPT_SPEC_NONE))
+                return e->fail(BPT_ERR_INVALID, "conductor: both reflectance and eta/k given");
+            if (haveRefl) {
+                dm.useReflectance = 1;
+                if (!MakeSpectrumRec(e, om.reflectance, ST_ALBEDO, spool, &dm.reflectance, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
+            } else {
+                OwnedSpectrum eta = om.eta, k = om.k;
+                if (eta.s.kind == BPT_SPEC_NONE) { eta.s.kind = BPT_SPEC_NAMED; std::strcpy(eta.s.name, "metal-Cu-eta"); }
+                if (k.s.kind == BPT_SPEC_NONE) { k.s.kind = BPT_SPEC_NAMED; std::strcpy(k.s.name, "metal-Cu-k"); }
+                if (!MakeSpectrumRec(e, eta, ST_UNBOUNDED, spool, &dm.eta, &serr) || !MakeSpectrumRec(e, k, ST_UNBOUNDED, spool, &dm.k, &serr))
+                    return e->fail(BPT_ERR_UNSUPPORTED, serr);
+            }
+            dm.uroughness = om.m.uroughness >= 0 ? om.m.uroughness : om.m.roughness;
+            dm.vroughness = om.m.vroughness >= 0 ? om.m.vroughness : om.m.roughness;
+            dm.flags = om.m.remap_roughness ? 1 : 0;
+            break;
+        }
+        case BPT_MAT_DIELECTRIC: {  // DielectricMaterial::Create: "eta" float or spectrum, default 1.5
+            if (om.eta.s.kind == BPT_SPEC_NONE) { dm.eta.kind = SPEC_CONSTANT; dm.eta.c0 = 1.5f; }
+            else if (!MakeSpectrumRec(e, om.eta, ST_UNBOUNDED, spool, &dm.eta, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
+            dm.uroughness = om.m.uroughness >= 0 ? om.m.uroughness : om.m.roughness;
+            dm.vroughness = om.m.vroughness >= 0 ? om.m.vroughness : om.m.roughness;
+            dm.flags = om.m.remap_roughness ? 1 : 0;
+            break;
+        }
         default: return e->fail(BPT_ERR_UNSUPPORTED, "material type not implemented yet");
         }
     }
@@ -611,7 +642,71 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             }
         }
     }
-    if (!e->lights.empty()) return e->fail(BPT_ERR_UNSUPPORTED, "infinite lights are not implemented yet");
+    // non-area lights follow the area lights (BasicScene::CreateLights, scene.cpp)
+    std::vector<DeviceImageLight> dimg;
+    struct ImgTables { std::vector<float> rgb; FilterTables dist, comp; int res; };
+    std::vector<ImgTables> imgTables;
+    for (const OwnedLight &ol : e->lights) {
+        DeviceLight dl{};
+        Xform renderFromLight(Mul(renderFromWorld.m, ToM4(ol.l.world_from_light)));
+        dl.renderFromLight = ToMat4(renderFromLight.m); dl.lightFromRender = ToMat4(renderFromLight.mInv);
+        float photometric = 0;
+        for (int i = 0; i < kNLambda; ++i) photometric += cieY[i] * illum[i];
+        float scale = ol.l.scale;
+        if (ol.l.type == BPT_LIGHT_UNIFORM_INFINITE) {
+            dl.type = LIGHT_UNIFORM_INFINITE;
+            std::vector<float> dense(kNLambda);
+            if (ol.L.s.kind == BPT_SPEC_NONE) { dense = illum; scale /= photometric; }
+            else {
+                SpectrumRec Lr{};
+                if (!MakeSpectrumRec(e, ol.L, ST_ILLUMINANT, spool, &Lr, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
+                for (int i = 0; i < kNLambda; ++i) dense[i] = EvalRecAt(Lr, spool.pool, (float)(kLambdaMin + i));
+                float ph = 0;
+                if (ol.L.s.kind == BPT_SPEC_RGB) ph = photometric; else for (int i = 0; i < kNLambda; ++i) ph += cieY[i] * dense[i];
+                scale /= ph;
+            }
+            if (ol.l.illuminance > 0) { float k_e = kPi; scale *= ol.l.illuminance / k_e; }
+            dl.LemitTable = spool.addDense(dense);
+        } else {
+            dl.type = LIGHT_IMAGE_INFINITE;
+            int res = ol.l.image_res;
+            if (res <= 0 || ol.image.size() != 3 * (size_t)res * res) return e->fail(BPT_ERR_INVALID, "infinite light image missing");
+            scale /= photometric;
+            if (ol.l.illuminance > 0) {   // lights.cpp:1620-1647
+                float illuminance = 0;
+                const std::vector<float> &Mx = e->tables.F("srgb_xyz_from_rgb");
+                float lum[3] = {Mx[3], Mx[4], Mx[5]};
+                for (int y = 0; y < res; ++y) {
+                    float v = (float(y) + 0.5f) / float(res);
+                    for (int x = 0; x < res; ++x) {
+                        float u = (x + 0.5f) / res;
+                        Vec3 w = EqualAreaSquareToSphere(Vec2(u, v));
+                        if (w.z <= 0) continue;
+                        for (int c = 0; c < 3; ++c) illuminance += ol.image[3 * ((size_t)y * res + x) + c] * lum[c] * w.z;
+                    }
+                }
+                illuminance *= 2 * kPi / (res * res);
+                scale *= ol.l.illuminance / illuminance;
+            }
+            imgTables.emplace_back();
+            ImgTables &it = imgTables.back();
+            it.res = res; it.rgb = ol.image;
+            // Image::GetSamplingDistribution (util/image.h:449-470) with dxdA = 1 over [0,1]^2, then the compensated copy
+            std::vector<float> d((size_t)res * res);
+            for (size_t i = 0; i < d.size(); ++i) { float sum = 0; sum += ol.image[3 * i]; sum += ol.image[3 * i + 1]; sum += ol.image[3 * i + 2]; d[i] = (sum / 3) * 1.f; }
+            BuildPC2D(d, res, res, 0, 1, 0, 1, &it.dist);
+            double acc = 0; for (float v : d) acc += v;
+            float average = (float)(acc / d.size());
+            bool allZero = true;
+            for (float &v : d) { v = stdmax(v - average, 0.f); if (v != 0) allZero = false; }
+            if (allZero) std::fill(d.begin(), d.end(), 1.f);
+            BuildPC2D(d, res, res, 0, 1, 0, 1, &it.comp);
+            dl.image = (int)imgTables.size() - 1;
+        }
+        dl.scale = scale;
+        dlights.push_back(dl);
+        lbounds.push_back(LightBoundsH());   // no bounds: infinite light
+    }
     // a scene without lights is legal (it renders black; the raw ray entry points still work)
 
     // ---- light sampler (wavefront/integrator.cpp:182-186: uniform when there is exactly one light)
@@ -622,7 +717,11 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     if (dlights.size() == 1) lsType = BPT_LIGHTSAMPLER_UNIFORM;
     dls.type = lsType;
     if (lsType == BPT_LIGHTSAMPLER_BVH) lb.Build(lbounds);
-    else { lb.bitTrails.assign(dlights.size(), 0); lb.lightInBVH.assign(dlights.size(), 0); }
+    else {
+        lb.bitTrails.assign(dlights.size(), 0); lb.lightInBVH.assign(dlights.size(), 0);
+        // the integrator's own list of infinite lights (cpu/integrators.cpp: infiniteLights) does not depend on the sampler
+        for (size_t i = 0; i < lbounds.size(); ++i) if (!lbounds[i].valid) lb.infiniteLights.push_back((int)i);
+    }
     dls.nInfinite = (int)lb.infiniteLights.size();
     dls.nNodes = (int)lb.nodes.size();
 
@@ -671,6 +770,44 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     ECK(cudaStreamSynchronize(e->stream));
     auto tb1 = std::chrono::steady_clock::now();
     e->nTrisTotal = (int)totalTris;
+    // infinite lights: Preprocess(sceneBounds) -> bounding sphere of the aggregate bounds (lights.h: UniformInfiniteLight::Preprocess)
+    {
+        Pt3 bmn(e->bvh.bmin[0], e->bvh.bmin[1], e->bvh.bmin[2]), bmx(e->bvh.bmax[0], e->bvh.bmax[1], e->bvh.bmax[2]);
+        Pt3 center = (bmn + bmx) / 2;
+        bool inside = center.x >= bmn.x && center.x <= bmx.x && center.y >= bmn.y && center.y <= bmx.y && center.z >= bmn.z && center.z <= bmx.z;
+        float radius = inside ? Distance(center, bmx) : 0;
+        bool any = false;
+        for (DeviceLight &dl : dlights) if (dl.type != LIGHT_DIFFUSE_AREA) { dl.sceneCenter = center; dl.sceneRadius = radius; any = true; }
+        if (any) ECK(e->dLights.upload(dlights));
+    }
+    e->imgBufs.clear();
+    for (auto &it : imgTables) {
+        std::vector<float> fb;
+        size_t oRGB = 0; fb.insert(fb.end(), it.rgb.begin(), it.rgb.end());
+        auto put = [&](const std::vector<float> &v) { size_t o = fb.size(); fb.insert(fb.end(), v.begin(), v.end()); return o; };
+        size_t o1 = put(it.dist.func), o2 = put(it.dist.cdf), o3 = put(it.dist.funcInt), o4 = put(it.dist.mfunc), o5 = put(it.dist.mcdf);
+        size_t c1 = put(it.comp.func), c2 = put(it.comp.cdf), c3 = put(it.comp.funcInt), c4 = put(it.comp.mfunc), c5 = put(it.comp.mcdf);
+        e->imgBufs.emplace_back(new DevBuf<float>());
+        ECK(e->imgBufs.back()->upload(fb));
+        const float *b = e->imgBufs.back()->p;
+        DeviceImageLight di{};
+        di.rgb = b + oRGB; di.res = it.res;
+        auto view = [&](const FilterTables &t, size_t a1, size_t a2, size_t a3, size_t a4, size_t a5) {
+            PC2DView v{};
+            v.func = b + a1; v.cdf = b + a2; v.funcInt = b + a3; v.mfunc = b + a4; v.mcdf = b + a5; v.mfuncInt = t.mfuncInt;
+            v.nu = it.res; v.nv = it.res; v.min0 = 0; v.max0 = 1; v.min1 = 0; v.max1 = 1;
+            return v;
+        };
+        di.distrib = view(it.dist, o1, o2, o3, o4, o5);
+        di.compensatedDistrib = view(it.comp, c1, c2, c3, c4, c5);
+        dimg.push_back(di);
+    }
+    ECK(e->dImageLights.upload(dimg));
+    if (!dimg.empty() && e->dRgb2spec.n == 0) {
+        std::vector<float> t(e->tables.F("rgb2spec_srgb_scale"));
+        t.insert(t.end(), e->tables.F("rgb2spec_srgb_coeffs").begin(), e->tables.F("rgb2spec_srgb_coeffs").end());
+        ECK(e->dRgb2spec.upload(t));
+    }
 
     // ---- path state and queues
     int nPixPass = (pb[1] - pb[0]) * (pb[3] - pb[2]);
@@ -712,9 +849,9 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     dls.nodes = e->dLightNodes.p; dls.infiniteLights = e->dInfinite.p; dls.bitTrails = e->dBitTrails.p; dls.lightInBVH = e->dLightInBVH.p;
     sv.ls = dls;
     sv.allbMin = lb.allLightBounds.pMin; sv.allbMax = lb.allLightBounds.pMax;
-    sv.imageLights = nullptr;
+    sv.imageLights = e->dImageLights.p;
     sv.cieX = e->dTables.p; sv.cieY = e->dTables.p + kNLambda; sv.cieZ = e->dTables.p + 2 * kNLambda; sv.illumD65 = e->dTables.p + 3 * kNLambda;
-    sv.rgb2specScale = nullptr; sv.rgb2specCoeffs = nullptr;
+    sv.rgb2specScale = e->dRgb2spec.n ? e->dRgb2spec.p : nullptr; sv.rgb2specCoeffs = e->dRgb2spec.n ? e->dRgb2spec.p + 64 : nullptr;
     sv.nLights = (int)dlights.size();
     rc.camera = dc; rc.film = df; rc.filter = dflt; rc.sampler = sp;
     rc.integ.maxDepth = e->integ.max_depth; rc.integ.regularize = e->integ.regularize;

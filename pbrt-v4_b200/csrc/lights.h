@@ -99,11 +99,113 @@ BPT_HD float AreaLightPDF_Li(const SceneView &sv, const DeviceLight &light, cons
     return TrianglePDFSolidAngle(td.p0, td.p1, td.p2, td.a, ctx.pi, ctx.n, ctx.ns, wi);
 }
 
-// ---------------------------------------------------------------- infinite lights (filled in with config 3)
-BPT_HD Spec InfiniteLightLe(const SceneView &sv, const DeviceLight &light, Vec3 rd, const Wavelengths &wl) { return Spec(0.f); }
-BPT_HD float InfiniteLightPDF_Li(const SceneView &sv, const DeviceLight &light, const LightSampleContext &ctx, Vec3 wi) { return 0; }
+// ---------------------------------------------------------------- infinite lights
+// Equal-area octahedral mapping (util/math.cpp:292-383)
+BPT_HD Vec3 EqualAreaSquareToSphere(Vec2 p) {
+    float u = 2 * p.x - 1, v = 2 * p.y - 1;
+    float up = fabsf(u), vp = fabsf(v);
+    float signedDistance = 1 - (up + vp);
+    float d = fabsf(signedDistance);
+    float r = 1 - d;
+    float phi = (r == 0 ? 1 : (vp - up) / r + 1) * kPi / 4;
+    float z = copysignf(1 - Sqr(r), signedDistance);
+    float cosPhi = copysignf(CosF(phi), u);
+    float sinPhi = copysignf(SinF(phi), v);
+    return Vec3(cosPhi * r * SafeSqrt(2 - Sqr(r)), sinPhi * r * SafeSqrt(2 - Sqr(r)), z);
+}
+BPT_HD Vec2 EqualAreaSphereToSquare(Vec3 d) {
+    float x = fabsf(d.x), y = fabsf(d.y), z = fabsf(d.z);
+    float r = SafeSqrt(1 - z);
+    float a = stdmax(x, y), b = stdmin(x, y);
+    b = a == 0 ? 0 : b / a;
+    const float t1 = 0.406758566246788489601959989e-5f, t2 = 0.636226545274016134946890922156f, t3 = 0.61572017898280213493197203466e-2f,
+                t4 = -0.247333733281268944196501420480f, t5 = 0.881770664775316294736387951347e-1f,
+                t6 = 0.419038818029165735901852432784e-1f, t7 = -0.251390972343483509333252996350e-1f;
+    float phi = EvalPoly(b, t1, t2, t3, t4, t5, t6, t7);
+    if (x < y) phi = 1 - phi;
+    float v = phi * r;
+    float u = r - v;
+    if (d.z < 0) { float t = u; u = v; v = t; u = 1 - u; v = 1 - v; }
+    u = copysignf(u, d.x);
+    v = copysignf(v, d.y);
+    return Vec2(0.5f * (u + 1), 0.5f * (v + 1));
+}
+// RGBToSpectrumTable::operator() on the device (util/color.cpp:31-68)
+BPT_HD void RGBToCoeffsDev(const SceneView &sv, const float rgb[3], float c[3]) {
+    const int res = 64;
+    if (rgb[0] == rgb[1] && rgb[1] == rgb[2]) { c[0] = 0; c[1] = 0; c[2] = (rgb[0] - .5f) / sqrtf(rgb[0] * (1 - rgb[0])); return; }
+    int maxc = (rgb[0] > rgb[1]) ? ((rgb[0] > rgb[2]) ? 0 : 2) : ((rgb[1] > rgb[2]) ? 1 : 2);
+    float z = rgb[maxc];
+    float x = rgb[(maxc + 1) % 3] * (res - 1) / z;
+    float y = rgb[(maxc + 2) % 3] * (res - 1) / z;
+    int xi = imin((int)x, res - 2), yi = imin((int)y, res - 2);
+    int zi = FindIntervalLT(sv.rgb2specScale, res, z);
+    float dx = x - xi, dy = y - yi, dz = (z - sv.rgb2specScale[zi]) / (sv.rgb2specScale[zi + 1] - sv.rgb2specScale[zi]);
+    const float *co = sv.rgb2specCoeffs;
+    for (int i = 0; i < 3; ++i) {
+#define BPT_CO(ddx, ddy, ddz) co[((((size_t)maxc * res + (zi + ddz)) * res + (yi + ddy)) * res + (xi + ddx)) * 3 + i]
+        c[i] = Lerp(dz, Lerp(dy, Lerp(dx, BPT_CO(0, 0, 0), BPT_CO(1, 0, 0)), Lerp(dx, BPT_CO(0, 1, 0), BPT_CO(1, 1, 0))),
+                    Lerp(dy, Lerp(dx, BPT_CO(0, 0, 1), BPT_CO(1, 0, 1)), Lerp(dx, BPT_CO(0, 1, 1), BPT_CO(1, 1, 1))));
+#undef BPT_CO
+    }
+}
+BPT_HD Vec3 ApplyM3(const Mat4 &T, Vec3 v) {
+    const float (*m)[4] = T.m;
+    return Vec3(m[0][0] * v.x + m[0][1] * v.y + m[0][2] * v.z, m[1][0] * v.x + m[1][1] * v.y + m[1][2] * v.z,
+                m[2][0] * v.x + m[2][1] * v.y + m[2][2] * v.z);
+}
+// ImageInfiniteLight::ImageLe (lights.h:612-618)
+BPT_HD Spec ImageLe(const SceneView &sv, const DeviceLight &light, Vec2 uv, const Wavelengths &wl) {
+    const DeviceImageLight &im = sv.imageLights[light.image];
+    int res = im.res;
+    int px = (int)(uv.x * res), py = (int)(uv.y * res);
+    // RemapPixelCoords, WrapMode::OctahedralSphere (util/image.h:100-125)
+    if (px < 0) { px = -px; py = res - 1 - py; } else if (px >= res) { px = 2 * res - 1 - px; py = res - 1 - py; }
+    if (py < 0) { px = res - 1 - px; py = -py; } else if (py >= res) { px = res - 1 - px; py = 2 * res - 1 - py; }
+    if (res == 1) { px = 0; py = 0; }
+    const float *pix = im.rgb + 3 * ((size_t)py * res + px);
+    float rgb[3] = {stdmax(0.f, pix[0]), stdmax(0.f, pix[1]), stdmax(0.f, pix[2])};
+    // RGBIlluminantSpectrum(cs, rgb).Sample(lambda)
+    float m = stdmax(stdmax(rgb[0], rgb[1]), rgb[2]);
+    float scale = 2 * m;
+    float q[3] = {0, 0, 0};
+    if (scale) { q[0] = rgb[0] / scale; q[1] = rgb[1] / scale; q[2] = rgb[2] / scale; }
+    float c[3];
+    RGBToCoeffsDev(sv, q, c);
+    Spec s;
+    for (int i = 0; i < 4; ++i) s[i] = scale * SigmoidPoly(c[0], c[1], c[2], wl.lambda[i]);
+    return light.scale * (s * DenseSample(sv.illumD65, wl));
+}
+BPT_HD Spec InfiniteLightLe(const SceneView &sv, const DeviceLight &light, Vec3 rd, const Wavelengths &wl) {
+    if (light.type == LIGHT_UNIFORM_INFINITE) return light.scale * DenseSample(sv.specPool + light.LemitTable, wl);
+    Vec3 wLight = Normalize(ApplyM3(light.lightFromRender, rd));
+    return ImageLe(sv, light, EqualAreaSphereToSquare(wLight), wl);
+}
+// allowIncompletePDF is true at both call sites on this path (cpu/integrators.cpp:1092, 1303)
+BPT_HD float InfiniteLightPDF_Li(const SceneView &sv, const DeviceLight &light, const LightSampleContext &ctx, Vec3 w) {
+    if (light.type == LIGHT_UNIFORM_INFINITE) return 0;
+    Vec3 wLight = ApplyM3(light.lightFromRender, w);
+    Vec2 uv = EqualAreaSphereToSquare(wLight);
+    return PC2DPDF(sv.imageLights[light.image].compensatedDistrib, uv) / (4 * kPi);
+}
 BPT_HD LightLiSample InfiniteLightSampleLi(const SceneView &sv, const DeviceLight &light, const LightSampleContext &ctx, Vec2 u,
-                                           const Wavelengths &wl) { LightLiSample ls; ls.valid = false; return ls; }
+                                           const Wavelengths &wl) {
+    LightLiSample ls;
+    ls.valid = false;
+    if (light.type == LIGHT_UNIFORM_INFINITE) return ls;
+    float mapPDF = 0; int ou, ov;
+    Vec2 uv = PC2DSample(sv.imageLights[light.image].compensatedDistrib, u, &mapPDF, &ou, &ov);
+    if (mapPDF == 0) return ls;
+    Vec3 wLight = EqualAreaSquareToSphere(uv);
+    Vec3 wi = ApplyM3(light.renderFromLight, wLight);
+    ls.pdf = mapPDF / (4 * kPi);
+    ls.L = ImageLe(sv, light, uv, wl);
+    ls.wi = wi;
+    ls.pLight = Pt3i(ctx.p() + wi * (2 * light.sceneRadius));
+    ls.nLight = Nrm3(0, 0, 0);
+    ls.valid = true;
+    return ls;
+}
 
 // ---------------------------------------------------------------- light BVH
 BPT_HD float BoundSubtendedCos(Pt3 bmin, Pt3 bmax, Pt3 p) {

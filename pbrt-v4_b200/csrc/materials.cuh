@@ -22,6 +22,53 @@ struct DiffuseMaterialEval {
     }
 };
 
+BPT_HD float EvalSpectrumAt(const SpectrumRec &s, const float *pool, float lambda) {
+    switch (s.kind) {
+    case SPEC_CONSTANT: return s.c0;
+    case SPEC_RGB_ALBEDO: return SigmoidPoly(s.c0, s.c1, s.c2, lambda);
+    case SPEC_RGB_UNBOUNDED: return s.scale * SigmoidPoly(s.c0, s.c1, s.c2, lambda);
+    case SPEC_DENSE: return DenseLookup(pool + s.table, lambda);
+    case SPEC_PIECEWISE: return PiecewiseLinearEval(pool + s.table, pool + s.table + s.n, s.n, lambda);
+    }
+    return 0;
+}
+
+struct ConductorMaterialEval {
+    static constexpr int kTag = MAT_CONDUCTOR;
+    typedef ConductorBxDF BxDF;
+    BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged) {
+        float uRough = m.uroughness, vRough = m.vroughness;
+        if (m.flags & 1) { uRough = TRDist::RoughnessToAlpha(uRough); vRough = TRDist::RoughnessToAlpha(vRough); }
+        Spec etas, ks;
+        if (!m.useReflectance) {
+            etas = EvalSpectrum(m.eta, sv.specPool, wl);
+            ks = EvalSpectrum(m.k, sv.specPool, wl);
+        } else {
+            Spec r = ClampSpec(EvalSpectrum(m.reflectance, sv.specPool, wl), 0, .9999f);
+            etas = Spec(1.f);
+            ks = 2 * SqrtSpec(r) / SqrtSpec(ClampZero(Spec(1) - r));
+        }
+        ConductorBxDF b;
+        b.mfDistrib = TRDist(uRough, vRough); b.eta = etas; b.k = ks;
+        return b;
+    }
+};
+
+struct DielectricMaterialEval {
+    static constexpr int kTag = MAT_DIELECTRIC;
+    typedef DielectricBxDF BxDF;
+    BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged) {
+        float sampledEta = EvalSpectrumAt(m.eta, sv.specPool, wl.lambda[0]);
+        if (m.eta.kind != SPEC_CONSTANT) { wl.TerminateSecondary(); *lambdaChanged = true; }
+        if (sampledEta == 0) sampledEta = 1;
+        float urough = m.uroughness, vrough = m.vroughness;
+        if (m.flags & 1) { urough = TRDist::RoughnessToAlpha(urough); vrough = TRDist::RoughnessToAlpha(vrough); }
+        DielectricBxDF b;
+        b.eta = sampledEta; b.mfDistrib = TRDist(urough, vrough);
+        return b;
+    }
+};
+
 struct InterfaceMaterialEval {
     static constexpr int kTag = MAT_INTERFACE;
     typedef DiffuseBxDF BxDF;

@@ -52,14 +52,17 @@ struct RenderCtx {
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ int WarpAggPush(int *counter) {
-    // warp-aggregated atomic slot allocation for the currently converged lanes
+    // Warp-aggregated atomic slot allocation.  Lanes are grouped by the counter they push to (__match_any_sync), not
+    // just by __activemask(): the compiler may merge the bodies of `if (a) push(&x); else push(&y);` into one converged
+    // call, in which case lanes with different counters execute this together (seen as lost queue entries on B200).
     unsigned m = __activemask();
+    unsigned peers = __match_any_sync(m, (unsigned long long)counter);
     int lane = threadIdx.x & 31;
-    int leader = __ffs(m) - 1;
+    int leader = __ffs(peers) - 1;
     int base = 0;
-    if (lane == leader) base = atomicAdd(counter, __popc(m));
-    base = __shfl_sync(m, base, leader);
-    return base + __popc(m & ((1u << lane) - 1));
+    if (lane == leader) base = atomicAdd(counter, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1));
 }
 #endif
 

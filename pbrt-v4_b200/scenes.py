@@ -84,3 +84,56 @@ def diffuse_heightfield(outdir, n=708, res=(1024, 1024), spp=256, maxdepth=5, se
     path = os.path.join(outdir, "heightfield.pbrt")
     open(path, "w").write(s)
     return path
+
+
+def write_envmap_pfm(path, res=256, seed=11):
+    """Procedural HDR environment map in pbrt's equal-area octahedral parameterisation: sky gradient + 3 Gaussian 'suns'."""
+    from .imageio import write_pfm
+    g = (np.arange(res, dtype=np.float64) + 0.5) / res
+    U, V = np.meshgrid(g, g, indexing="xy")
+    # equal-area square -> sphere (Clarberg), vectorised; only used to author the picture (the renderers do their own mapping)
+    u, v = 2 * U - 1, 2 * V - 1
+    up, vp = np.abs(u), np.abs(v)
+    sd = 1 - (up + vp)
+    r = 1 - np.abs(sd)
+    phi = np.where(r == 0, 1.0, (vp - up) / np.where(r == 0, 1, r) + 1) * np.pi / 4
+    z = np.copysign(1 - r * r, sd)
+    c, s = np.copysign(np.cos(phi), u), np.copysign(np.sin(phi), v)
+    x, y = c * r * np.sqrt(np.maximum(0, 2 - r * r)), s * r * np.sqrt(np.maximum(0, 2 - r * r))
+    img = np.zeros((res, res, 3))
+    t = 0.5 * (z + 1)
+    img += (0.15 + 0.85 * t)[..., None] * np.array([0.35, 0.55, 1.0])
+    rng = np.random.Generator(np.random.PCG64(seed))
+    for k in range(3):
+        d = rng.normal(size=3); d[2] = abs(d[2]) + 0.3; d /= np.linalg.norm(d)
+        cosang = x * d[0] + y * d[1] + z * d[2]
+        img += (5e4 if k == 0 else 5e2) * np.exp((cosang - 1) / (2e-4 if k == 0 else 4e-3))[..., None] * np.array([1.0, 0.9, 0.7])
+    write_pfm(path, img.astype(np.float32))
+
+
+def mixed_envmap(outdir, n=2236, res=(1920, 1080), spp=1024, maxdepth=5, envres=2048, nmesh=64, seed=1234):
+    """Config 3: height field split into `nmesh` strips alternating dielectric (eta 1.5, smooth) / conductor (Cu, roughness
+    0.05 and 0.3), lit by a procedural HDR environment map."""
+    os.makedirs(outdir, exist_ok=True)
+    P, idx = heightfield_mesh(n, seed)
+    write_envmap_pfm(os.path.join(outdir, "env.pfm"), envres)
+    s = _header(res, spp, maxdepth, ((0, 1.6, 2.6), (0, 0, 0)), 45)
+    s += "AttributeBegin\n  Rotate -90 1 0 0\n  LightSource \"infinite\" \"string filename\" \"env.pfm\"\nAttributeEnd\n"
+    tri_per = (len(idx) + nmesh - 1) // nmesh
+    mats = ["Material \"dielectric\" \"float eta\" 1.5 \"float roughness\" 0\n",
+            "Material \"conductor\" \"spectrum eta\" \"metal-Cu-eta\" \"spectrum k\" \"metal-Cu-k\" \"float roughness\" 0.05\n",
+            "Material \"dielectric\" \"float eta\" 1.5 \"float roughness\" 0\n",
+            "Material \"conductor\" \"spectrum eta\" \"metal-Cu-eta\" \"spectrum k\" \"metal-Cu-k\" \"float roughness\" 0.3\n"]
+    for m in range(nmesh):
+        sub = idx[m * tri_per:(m + 1) * tri_per]
+        if len(sub) == 0:
+            continue
+        used, inv = np.unique(sub.reshape(-1), return_inverse=True)
+        write_ply(os.path.join(outdir, f"strip{m:03d}.ply"), P[used], inv.reshape(-1, 3))
+        s += mats[m % 4] + f"Shape \"plymesh\" \"string filename\" \"strip{m:03d}.ply\"\n"
+    # a diffuse ground plane below so that refracted paths terminate on something
+    s += ("Material \"diffuse\" \"rgb reflectance\" [0.4 0.4 0.4]\n"
+          "Shape \"trianglemesh\" \"integer indices\" [0 1 2 0 2 3] \"point3 P\" [-3 -0.5 -3  -3 -0.5 3  3 -0.5 3  3 -0.5 -3]\n")
+    path = os.path.join(outdir, "mixed.pbrt")
+    open(path, "w").write(s)
+    return path

@@ -12,6 +12,8 @@ if which == "heightfield":
     path = scenes.diffuse_heightfield(out, n=n, res=(res, res), spp=spp)
 elif which == "cornell":
     path = scenes.cornell(out, res=(res, res), spp=spp)
+elif which == "mixed":
+    path = scenes.mixed_envmap(out, n=n, res=(res, res), spp=spp, envres=int(os.environ.get("ENVRES", "128")), nmesh=int(os.environ.get("NMESH", "8")))
 else:
     path = getattr(scenes, which)(out, res=(res, res), spp=spp)
 t0 = time.time()
@@ -32,4 +34,5 @@ print("mean ref", ref.mean(axis=(0, 1)), "mean gpu", img.mean(axis=(0, 1)))
 print("RMSE per channel", imageio.channel_rmse(img, ref), "max abs", float(d.max()), "frac identical", float((img == ref).all(axis=-1).mean()))
 ys, xs = np.nonzero(d.max(axis=-1) > 1e-3)
 print("pixels with |diff| > 1e-3:", len(ys), [(int(x), int(y), img[y, x].tolist(), ref[y, x].tolist()) for x, y in list(zip(xs, ys))[:5]])
-os.remove(os.path.join(out, "heightfield.ply")) if os.path.exists(os.path.join(out, "heightfield.ply")) else None
+import glob
+for f in glob.glob(os.path.join(out, "*.ply")): os.remove(f)
