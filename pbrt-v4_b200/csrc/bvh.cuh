@@ -19,9 +19,11 @@
 
 namespace bpt {
 
+struct DeviceInstance;
 struct BVHView {
-    const float4 *nodes;      // 5 float4 per wide node; node 0 = root
-    const float4 *tris;       // 3 float4 per triangle in leaf order (p0.w = original triangle id)
+    const float4 *nodes;      // 5 float4 per wide node; node 0 = root (instanced scenes: the top-level BVH over instances)
+    const float4 *tris;       // 3 float4 per triangle in leaf order (p0.w = original triangle id; top level: instance id)
+    const DeviceInstance *instances;   // non-null: two-level scene
 };
 
 #define BPT_STACK_SIZE 40
@@ -99,7 +101,7 @@ BPT_D unsigned SignExtendS8x4(unsigned x) {
 }
 BPT_D float SafeInvDir(float d) { return 1.0f / (fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }
 
-struct HitRec { int tri; float b0, b1, b2, t; };   // tri = leaf-order triangle index, -1 = miss
+struct HitRec { int tri; float b0, b1, b2, t; int inst; };   // tri = leaf-order triangle index (of instance `inst`), -1 = miss
 
 // Conservative slab test of the 8 quantised children; returns the hit mask (internal children in bits 24..31
 // in octant-permuted order, triangles in bits 0..23).  The box test uses fast fused arithmetic: it only has to
@@ -340,6 +342,204 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
                 rayIdx = -1;
                 cur = make_uint2(0, 0); sp = 0; head = tail = 0;
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Two-level variant (object instancing): the top-level BVH's leaf records are instances; entering one restates
+// TransformedPrimitive::Intersect (cpu/primitive.cpp:112-124): the ray is taken to instance space with
+// Transform::ApplyInverse(Ray, &tMax) (util/transform.h:416-430, origin error offset included), the instance's BVH is
+// traversed with the shifted tMax, and -- like the reference -- the reported tHit stays in the instance-space
+// parameterisation.  Stack protocol: [saved top-level node group][sentinel] are pushed on entry; the sentinel is popped
+// only after the lane's deferred triangle groups (which belong to the instance) are drained.
+struct InstRay { Pt3 o; Vec3 d; float dt; };
+BPT_D InstRay ApplyInverseRay(const Mat4 &Minv, Pt3 o, Vec3 d) {
+    const float (*m)[4] = Minv.m;
+    float x = o.x, y = o.y, z = o.z;
+    float xp = (m[0][0] * x + m[0][1] * y) + (m[0][2] * z + m[0][3]);
+    float yp = (m[1][0] * x + m[1][1] * y) + (m[1][2] * z + m[1][3]);
+    float zp = (m[2][0] * x + m[2][1] * y) + (m[2][2] * z + m[2][3]);
+    float wp = (m[3][0] * x + m[3][1] * y) + (m[3][2] * z + m[3][3]);
+    Vec3 e;   // exact input point: util/transform.cpp:263-276 (no |m[i][3]| term)
+    e.x = gamma_n(3) * (fabsf(m[0][0] * x) + fabsf(m[0][1] * y) + fabsf(m[0][2] * z));
+    e.y = gamma_n(3) * (fabsf(m[1][0] * x) + fabsf(m[1][1] * y) + fabsf(m[1][2] * z));
+    e.z = gamma_n(3) * (fabsf(m[2][0] * x) + fabsf(m[2][1] * y) + fabsf(m[2][2] * z));
+    Pt3i oi(Pt3(xp, yp, zp), e);
+    if (wp != 1) {
+        auto divI = [](Interval i, float f) { return f > 0 ? Interval(DivRoundDown(i.low, f), DivRoundUp(i.high, f))
+                                                          : Interval(DivRoundDown(i.high, f), DivRoundUp(i.low, f)); };
+        oi.x = divI(oi.x, wp); oi.y = divI(oi.y, wp); oi.z = divI(oi.z, wp);
+    }
+    Vec3 dn(m[0][0] * d.x + m[0][1] * d.y + m[0][2] * d.z, m[1][0] * d.x + m[1][1] * d.y + m[1][2] * d.z,
+            m[2][0] * d.x + m[2][1] * d.y + m[2][2] * d.z);
+    InstRay r; r.dt = 0;
+    float lengthSquared = LengthSquared(dn);
+    if (lengthSquared > 0) {
+        Vec3 oError(oi.x.Width() / 2, oi.y.Width() / 2, oi.z.Width() / 2);
+        float dt = Dot(Abs(dn), oError) / lengthSquared;
+        Vec3 off = dn * dt;
+        oi.x = oi.x + off.x; oi.y = oi.y + off.y; oi.z = oi.z + off.z;
+        r.dt = dt;
+    }
+    r.o = oi.p(); r.d = dn;
+    return r;
+}
+
+template <bool ANYHIT, bool COUNT, typename LoadF, typename CommitF>
+BPT_D void TraversePersistentInst(const BVHView &bvh, const DeviceInstance *instances, int nRays, int *cursor, LoadF Load,
+                                  CommitF Commit, unsigned *nNodes, unsigned *nTris, unsigned *nRaysDone) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned SENT = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    __shared__ uint2 s_tri[kTriCap][128];
+    uint2 (*triRing)[128] = s_tri;
+    const int tid = threadIdx.x;
+    int rayIdx = -1;
+    bool exhausted = false;
+    RayPre rp; Vec3 idir, ov; unsigned octinv4 = 0; float tBox = 0;
+    uint2 stack[BPT_STACK_SIZE];
+    int sp = 0;
+    unsigned head = 0, tail = 0;
+    uint2 cur = make_uint2(0, 0), instGroup = make_uint2(0, 0);
+    int inst = -1;
+    float tSaved = 0; bool hitHere = false;
+    const float4 *curNodes = bvh.nodes, *curTris = bvh.tris;
+    HitRec rec; rec.tri = -1; rec.t = 0; rec.b0 = rec.b1 = rec.b2 = 0; rec.inst = -1;
+    auto setRay = [&](Pt3 o, Vec3 d) {
+        rp = MakeRayPre(o, d);
+        idir = Vec3(SafeInvDir(d.x), SafeInvDir(d.y), SafeInvDir(d.z));
+        ov = Vec3(o.x, o.y, o.z);
+        unsigned octinv = (d.x < 0 ? 0u : 4u) | (d.y < 0 ? 0u : 2u) | (d.z < 0 ? 0u : 1u);
+        octinv4 = octinv * 0x01010101u;
+    };
+    while (true) {
+        unsigned idle = __ballot_sync(FULL, rayIdx < 0);
+        if (idle != 0 && !exhausted && (__popc(idle) >= kFetchThreshold || idle == FULL)) {
+            int nNeed = __popc(idle);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(cursor, nNeed);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + nNeed >= nRays) exhausted = true;
+            if (rayIdx < 0) {
+                int i = base + __popc(idle & ((1u << lane) - 1));
+                if (i < nRays) {
+                    rayIdx = i;
+                    Pt3 o; Vec3 d; float tMax;
+                    Load(i, &o, &d, &tMax);
+                    setRay(o, d);
+                    tBox = tMax * (1 + 1e-5f);
+                    sp = 0; head = tail = 0; inst = -1; instGroup = make_uint2(0, 0);
+                    curNodes = bvh.nodes; curTris = bvh.tris;
+                    cur = make_uint2(0u, 0x80000000u);
+                    rec.tri = -1; rec.t = tMax; rec.inst = -1;
+                }
+            }
+        }
+        bool act = rayIdx >= 0;
+        if (!__any_sync(FULL, act)) break;
+        // ---- enter the next instance of the pending top-level leaf group
+        if (act && inst < 0 && instGroup.y != 0) {
+            unsigned ti = 31 - __clz(instGroup.y);
+            instGroup.y &= ~(1u << ti);
+            int id = __float_as_int(__ldg(bvh.tris + (size_t)(instGroup.x + ti) * 3).w);
+            const DeviceInstance &I = instances[id];
+            stack[sp++] = cur;
+            stack[sp++] = make_uint2(SENT, 0);
+            inst = id; tSaved = rec.t; hitHere = false;
+            curNodes = I.nodes; curTris = I.tris;
+            if (!I.identity) {
+                Pt3 o; Vec3 d; float tm;
+                Load(rayIdx, &o, &d, &tm);
+                InstRay r = ApplyInverseRay(I.mInv, o, d);
+                setRay(r.o, r.d);
+                rec.t = rec.t - r.dt;
+            }
+            tBox = rec.t * (1 + 1e-5f);
+            cur = make_uint2(0u, 0x80000000u);
+        }
+        // ---- one node step
+        bool canNode = act && (cur.y & 0xff000000u) != 0 && (tail - head) <= (unsigned)kTriBlock && (inst >= 0 || instGroup.y == 0);
+        if (canNode) {
+            unsigned hits_imask = cur.y;
+            unsigned child_bit = 31 - __clz(hits_imask);
+            unsigned child_base = cur.x;
+            cur.y &= ~(1u << child_bit);
+            if (cur.y & 0xff000000u) stack[sp++] = cur;
+            unsigned slot = (child_bit - 24) ^ (octinv4 & 0xff);
+            unsigned rel = __popc(hits_imask & ~(0xffffffffu << slot));
+            const float4 *np = curNodes + (size_t)(child_base + rel) * 5;
+            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            if (COUNT) ++*nNodes;
+            unsigned hitmask = NodeIntersect(ov, idir, octinv4, tBox, n0, n1, n2, n3, n4);
+            cur.x = __float_as_uint(n1.x);
+            cur.y = (hitmask & 0xff000000u) | ExtractByte(__float_as_uint(n0.w), 3);
+            unsigned triBase = __float_as_uint(n1.y);
+            unsigned tmask = hitmask & 0x00ffffffu;
+            if (tmask) {
+                if (inst < 0) instGroup = make_uint2(triBase, tmask);
+                else { triRing[tail & (kTriCap - 1)][tid] = make_uint2(triBase, tmask); ++tail; }
+            }
+            if ((cur.y & 0xff000000u) == 0 && sp > 0 && stack[sp - 1].x != SENT) cur = stack[--sp];
+        } else if (act && (cur.y & 0xff000000u) == 0 && sp > 0 && stack[sp - 1].x != SENT && (inst >= 0 || instGroup.y == 0)) {
+            cur = stack[--sp];
+        }
+        // ---- triangle rounds
+        bool hasNode = act && (cur.y & 0xff000000u) != 0;
+        bool hasTri = act && tail != head;
+        unsigned triLanes = __ballot_sync(FULL, hasTri);
+        bool anyNodeRunnable = __any_sync(FULL, (hasNode && (tail - head) <= (unsigned)kTriBlock) || (act && inst < 0 && instGroup.y != 0));
+        bool finished = false;
+        if (triLanes != 0 && (__popc(triLanes) >= kFlushLanes || !anyNodeRunnable)) {
+            while (true) {
+                if (hasTri) {
+                    uint2 g = triRing[head & (kTriCap - 1)][tid];
+                    unsigned ti = 31 - __clz(g.y);
+                    g.y &= ~(1u << ti);
+                    if (g.y == 0) ++head; else triRing[head & (kTriCap - 1)][tid].y = g.y;
+                    unsigned tri = g.x + ti;
+                    const float4 *tp = curTris + (size_t)tri * 3;
+                    float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                    if (COUNT) ++*nTris;
+                    TriHit th;
+                    if (!(__float_as_uint(b.w) & 0x80000000u) &&
+                        IntersectTrianglePre(rp, rec.t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th)) {
+                        rec.tri = (int)tri; rec.b0 = th.b0; rec.b1 = th.b1; rec.b2 = th.b2; rec.t = th.t; rec.inst = inst;
+                        hitHere = true;
+                        if (ANYHIT) { finished = true; head = tail; }
+                        else tBox = th.t * (1 + 1e-5f);
+                    }
+                    hasTri = tail != head;
+                }
+                unsigned m = __ballot_sync(FULL, hasTri);
+                if (m == 0) break;
+                if (__popc(m) < kRoundLanes && anyNodeRunnable) break;
+            }
+        }
+        // ---- leave the instance / commit
+        if (act && !finished) {
+            bool nodeEmpty = (cur.y & 0xff000000u) == 0;
+            if (inst >= 0 && nodeEmpty && tail == head && sp > 0 && stack[sp - 1].x == SENT) {
+                --sp;                      // sentinel
+                cur = stack[--sp];         // saved top-level node group
+                if (!instances[inst].identity) {
+                    Pt3 o; Vec3 d; float tm;
+                    Load(rayIdx, &o, &d, &tm);
+                    setRay(o, d);
+                }
+                if (!hitHere) rec.t = tSaved;
+                inst = -1;
+                curNodes = bvh.nodes; curTris = bvh.tris;
+                tBox = rec.t * (1 + 1e-5f);
+                nodeEmpty = (cur.y & 0xff000000u) == 0;
+            }
+            if (inst < 0 && nodeEmpty && sp == 0 && instGroup.y == 0 && tail == head) finished = true;
+        }
+        if (act && finished) {
+            Commit(rayIdx, rec);
+            if (COUNT) ++*nRaysDone;
+            rayIdx = -1;
+            cur = make_uint2(0, 0); sp = 0; head = tail = 0; inst = -1; instGroup = make_uint2(0, 0);
         }
     }
 }

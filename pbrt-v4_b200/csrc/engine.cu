@@ -112,6 +112,10 @@ struct bpt_engine {
     DevBuf<float2> stateAux;
     DevBuf<int> rawCursor;
     DevBuf<DeviceImageLight> dImageLights;
+    DevBuf<DeviceInstance> dInstances;
+    DevBuf<float4> dTlasPrims;
+    DevBuf<int> hitInst;
+    std::vector<WideBVH> blas;
     DevBuf<float> dRgb2spec;
     std::vector<std::unique_ptr<DevBuf<float>>> imgBufs;
     WideBVH bvh{};
@@ -306,6 +310,7 @@ extern "C" void bpt_destroy(bpt_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     FreeWideBVH(&e->bvh);
+    for (WideBVH &b : e->blas) FreeWideBVH(&b);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -406,7 +411,6 @@ static bool AllZero(const bpt_mat4 &a) { for (int i = 0; i < 4; ++i) for (int j 
 extern "C" int bpt_scene_commit(bpt_engine *e) {
     if (!e) return BPT_ERR_INVALID;
     if (!e->haveCam || !e->haveFilm) return e->fail(BPT_ERR_INVALID, "camera and film must be set before commit");
-    if (!e->instances.empty()) return e->fail(BPT_ERR_UNSUPPORTED, "object instancing is not implemented yet");
     ECK(cudaSetDevice(e->device));
     auto t0 = std::chrono::steady_clock::now();
     e->committed = false;
@@ -559,9 +563,29 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     e->haveAreaLights = false;
     const std::vector<float> &cieY = e->tables.F("cie_y");
     const std::vector<float> &illum = e->tables.F("srgb_illuminant");
-    for (size_t mi = 0; mi < e->meshes.size(); ++mi) {
+    // triangle groups: group 0 = top-level shapes (scene order), then one group per object definition
+    int nObjects = 0;
+    for (const OwnedMesh &om : e->meshes) nObjects = std::max(nObjects, om.m.object_id + 1);
+    for (const bpt_instance &in : e->instances) if (in.object_id < 0 || in.object_id >= nObjects) return e->fail(BPT_ERR_INVALID, "instance of an undefined object");
+    std::vector<size_t> meshOrder;
+    std::vector<int> groupStart(nObjects + 2, 0);
+    for (int g = -1; g < nObjects; ++g) {
+        groupStart[g + 1] = (int)tri.size();
+        for (size_t mi = 0; mi < e->meshes.size(); ++mi) if (e->meshes[mi].m.object_id == g) { meshOrder.push_back(mi); }
+        // (group extents are fixed up after the loop below, once triangle counts are known)
+    }
+    {
+        int acc = 0; size_t k = 0;
+        for (int g = -1; g < nObjects; ++g) {
+            groupStart[g + 1] = acc;
+            for (; k < meshOrder.size() && e->meshes[meshOrder[k]].m.object_id == g; ++k) acc += e->meshes[meshOrder[k]].m.n_triangles;
+        }
+        groupStart[nObjects + 1] = acc;
+    }
+    for (size_t oi = 0; oi < meshOrder.size(); ++oi) {
+        size_t mi = meshOrder[oi];
         const OwnedMesh &om = e->meshes[mi];
-        if (om.m.object_id >= 0) return e->fail(BPT_ERR_UNSUPPORTED, "instanced object definitions are not implemented yet");
+        if (om.m.object_id >= 0 && om.m.area_light >= 0) return e->fail(BPT_ERR_UNSUPPORTED, "area lights are not supported with object instancing");
         if (om.m.material >= (int)e->materials.size()) return e->fail(BPT_ERR_INVALID, "mesh material index out of range");
         Xform renderFromObject(Mul(renderFromWorld.m, ToM4(om.m.world_from_object)));   // scene.h:475-477
         std::vector<Pt3> P(om.m.n_vertices);
@@ -762,11 +786,58 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         dflt.f = e->dFilter.p + oF;
     }
 
-    // ---- BVH
+    // ---- BVH (single level, or per-definition BVHs + a top-level BVH over instances)
     FreeWideBVH(&e->bvh);
+    for (WideBVH &b : e->blas) FreeWideBVH(&b);
+    e->blas.clear();
     char berr[256] = {0};
     auto tb0 = std::chrono::steady_clock::now();
-    if (!BuildWideBVH(e->triPool.p, (int)totalTris, &e->bvh, e->stream, berr)) return e->fail(BPT_ERR_CUDA, berr);
+    std::vector<DeviceInstance> dinst;
+    const bool instanced = !e->instances.empty();
+    if (!instanced) {
+        if (nObjects > 0) return e->fail(BPT_ERR_INVALID, "object definitions without instances");
+        if (!BuildWideBVH(e->triPool.p, (int)totalTris, &e->bvh, e->stream, berr)) return e->fail(BPT_ERR_CUDA, berr);
+    } else {
+        e->blas.resize(nObjects + 1);
+        std::vector<float4> tlasPrims;
+        auto addInst = [&](int group, const Xform *T) {
+            const WideBVH &b = e->blas[group];
+            DeviceInstance di{};
+            di.nodes = b.nodes; di.tris = b.tris; di.triBase = groupStart[group]; di.identity = T ? 0 : 1;
+            Bounds3 bb(Pt3(b.bmin[0], b.bmin[1], b.bmin[2]), Pt3(b.bmax[0], b.bmax[1], b.bmax[2]));
+            if (T) {
+                di.m = ToMat4(T->m); di.mInv = ToMat4(T->mInv);
+                Bounds3 bt;   // Transform::operator()(const Bounds3f &) (util/transform.cpp:134-139)
+                for (int c = 0; c < 8; ++c)
+                    bt = Union(bt, (*T)(Pt3((c & 1) ? bb.pMax.x : bb.pMin.x, (c & 2) ? bb.pMax.y : bb.pMin.y, (c & 4) ? bb.pMax.z : bb.pMin.z)));
+                bb = bt;
+            } else { M4 I; di.m = ToMat4(I); di.mInv = ToMat4(I); }
+            int id = (int)dinst.size();
+            dinst.push_back(di);
+            // top-level "primitive": a degenerate triangle whose bounds are the instance bounds; p0.w carries the instance id
+            tlasPrims.push_back(make_float4(bb.pMin.x, bb.pMin.y, bb.pMin.z, b2f((uint32_t)id)));
+            tlasPrims.push_back(make_float4(bb.pMax.x, bb.pMax.y, bb.pMax.z, 0.f));
+            tlasPrims.push_back(make_float4(bb.pMin.x, bb.pMin.y, bb.pMin.z, 0.f));
+        };
+        for (int g = 0; g <= nObjects; ++g) {
+            int n = groupStart[g + 1] - groupStart[g];
+            if (n == 0) continue;
+            if (!BuildWideBVH(e->triPool.p + 3 * (size_t)groupStart[g], n, &e->blas[g], e->stream, berr)) return e->fail(BPT_ERR_CUDA, berr);
+        }
+        if (groupStart[1] > groupStart[0]) addInst(0, nullptr);
+        Xform worldFromRenderX = Inverse(renderFromWorld);
+        for (const bpt_instance &in : e->instances) {
+            if (!e->blas[in.object_id + 1].nodes) continue;   // empty definition
+            // scene.cpp:375-393: renderFromInstance = RenderFromObject(0) * worldFromRender
+            Xform rfo(Mul(renderFromWorld.m, ToM4(in.world_from_instance)));
+            Xform renderFromInstance = rfo * worldFromRenderX;
+            addInst(in.object_id + 1, &renderFromInstance);
+        }
+        if (dinst.empty()) return e->fail(BPT_ERR_INVALID, "scene has no geometry");
+        ECK(e->dTlasPrims.upload(tlasPrims));
+        if (!BuildWideBVH(e->dTlasPrims.p, (int)dinst.size(), &e->bvh, e->stream, berr)) return e->fail(BPT_ERR_CUDA, berr);
+        ECK(e->dInstances.upload(dinst));
+    }
     ECK(cudaStreamSynchronize(e->stream));
     auto tb1 = std::chrono::steady_clock::now();
     e->nTrisTotal = (int)totalTris;
@@ -843,6 +914,9 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     rc.stats = e->stats.p;
     ECK(e->rawCursor.alloc(1));
     rc.bvh.nodes = e->bvh.nodes; rc.bvh.tris = e->bvh.tris;
+    rc.bvh.instances = instanced ? e->dInstances.p : nullptr;
+    ECK(e->hitInst.alloc(instanced ? maxPaths : 1));
+    rc.ps.hitInst = e->hitInst.p;
     SceneView &sv = rc.sv;
     sv.triPool = e->triPool.p; sv.meshes = e->dMeshes.p; sv.indexPool = e->indexPool.p; sv.nPool = e->nPool.p; sv.uvPool = e->uvPool.p;
     sv.materials = e->dMaterials.p; sv.lights = e->dLights.p; sv.specPool = e->specPool.p;
@@ -850,6 +924,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     sv.ls = dls;
     sv.allbMin = lb.allLightBounds.pMin; sv.allbMax = lb.allLightBounds.pMax;
     sv.imageLights = e->dImageLights.p;
+    sv.instances = instanced ? e->dInstances.p : nullptr;
     sv.cieX = e->dTables.p; sv.cieY = e->dTables.p + kNLambda; sv.cieZ = e->dTables.p + 2 * kNLambda; sv.illumD65 = e->dTables.p + 3 * kNLambda;
     sv.rgb2specScale = e->dRgb2spec.n ? e->dRgb2spec.p : nullptr; sv.rgb2specCoeffs = e->dRgb2spec.n ? e->dRgb2spec.p + 64 : nullptr;
     sv.nLights = (int)dlights.size();

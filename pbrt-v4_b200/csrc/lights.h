@@ -30,6 +30,7 @@ struct SceneView {
     DeviceLightSampler ls;
     Pt3 allbMin, allbMax;            // BVHLightSampler::allLightBounds
     const DeviceImageLight *imageLights;
+    const DeviceInstance *instances;  // null: single-level scene
     const float *cieX, *cieY, *cieZ; // 471-entry densely sampled matching functions
     const float *illumD65;           // sRGB colour space illuminant (densely sampled)
     const float *rgb2specScale;      // 64 z-nodes
@@ -40,6 +41,63 @@ struct SceneView {
 #if defined(__CUDACC__)
 BPT_D Pt3 ldP3(const float4 *p) { float4 v = __ldg(p); return Pt3(v.x, v.y, v.z); }
 #endif
+
+// Transform::operator()(const SurfaceInteraction &) (util/transform.cpp:207-245) for the members the path uses, and the
+// wo the reference ends up with for an instanced hit: Normalize(M * (-(Minv * d)))  (cpu/primitive.cpp:114-123).
+BPT_HD Pt3i XformPt3i(const Mat4 &T, const Pt3i &p) {
+    const float (*m)[4] = T.m;
+    float x = p.x.Midpoint(), y = p.y.Midpoint(), z = p.z.Midpoint();
+    float xp = (m[0][0] * x + m[0][1] * y) + (m[0][2] * z + m[0][3]);
+    float yp = (m[1][0] * x + m[1][1] * y) + (m[1][2] * z + m[1][3]);
+    float zp = (m[2][0] * x + m[2][1] * y) + (m[2][2] * z + m[2][3]);
+    float wp = (m[3][0] * x + m[3][1] * y) + (m[3][2] * z + m[3][3]);
+    Vec3 pError;
+    if (p.IsExact()) {
+        pError.x = gamma_n(3) * (fabsf(m[0][0] * x) + fabsf(m[0][1] * y) + fabsf(m[0][2] * z) + fabsf(m[0][3]));
+        pError.y = gamma_n(3) * (fabsf(m[1][0] * x) + fabsf(m[1][1] * y) + fabsf(m[1][2] * z) + fabsf(m[1][3]));
+        pError.z = gamma_n(3) * (fabsf(m[2][0] * x) + fabsf(m[2][1] * y) + fabsf(m[2][2] * z) + fabsf(m[2][3]));
+    } else {
+        Vec3 pInError = p.Error();
+        pError.x = (gamma_n(3) + 1) * (fabsf(m[0][0]) * pInError.x + fabsf(m[0][1]) * pInError.y + fabsf(m[0][2]) * pInError.z) +
+                   gamma_n(3) * (fabsf(m[0][0] * x) + fabsf(m[0][1] * y) + fabsf(m[0][2] * z) + fabsf(m[0][3]));
+        pError.y = (gamma_n(3) + 1) * (fabsf(m[1][0]) * pInError.x + fabsf(m[1][1]) * pInError.y + fabsf(m[1][2]) * pInError.z) +
+                   gamma_n(3) * (fabsf(m[1][0] * x) + fabsf(m[1][1] * y) + fabsf(m[1][2] * z) + fabsf(m[1][3]));
+        pError.z = (gamma_n(3) + 1) * (fabsf(m[2][0]) * pInError.x + fabsf(m[2][1]) * pInError.y + fabsf(m[2][2]) * pInError.z) +
+                   gamma_n(3) * (fabsf(m[2][0] * x) + fabsf(m[2][1] * y) + fabsf(m[2][2] * z) + fabsf(m[2][3]));
+    }
+    Pt3i r(Pt3(xp, yp, zp), pError);
+    if (wp != 1) {
+        auto divI = [](Interval i, float f) { return f > 0 ? Interval(DivRoundDown(i.low, f), DivRoundUp(i.high, f))
+                                                          : Interval(DivRoundDown(i.high, f), DivRoundUp(i.low, f)); };
+        r.x = divI(r.x, wp); r.y = divI(r.y, wp); r.z = divI(r.z, wp);
+    }
+    return r;
+}
+BPT_HD Vec3 XformVec(const Mat4 &T, Vec3 v) {
+    const float (*m)[4] = T.m;
+    return Vec3(m[0][0] * v.x + m[0][1] * v.y + m[0][2] * v.z, m[1][0] * v.x + m[1][1] * v.y + m[1][2] * v.z,
+                m[2][0] * v.x + m[2][1] * v.y + m[2][2] * v.z);
+}
+BPT_HD Nrm3 XformNrm(const Mat4 &Tinv, Nrm3 n) {   // Transform::operator()(Normal3f): transpose of the inverse
+    const float (*mi)[4] = Tinv.m;
+    float x = n.x, y = n.y, z = n.z;
+    return Nrm3(mi[0][0] * x + mi[1][0] * y + mi[2][0] * z, mi[0][1] * x + mi[1][1] * y + mi[2][1] * z,
+                mi[0][2] * x + mi[1][2] * y + mi[2][2] * z);
+}
+BPT_HD SurfaceIntr XformInteraction(const DeviceInstance &I, const SurfaceIntr &si) {
+    SurfaceIntr r;
+    r.pi = XformPt3i(I.m, si.pi);
+    r.n = Normalize(XformNrm(I.mInv, si.n));
+    r.uv = si.uv;
+    r.ns = Normalize(XformNrm(I.mInv, si.ns));
+    r.dpdus = XformVec(I.m, si.dpdus);
+    r.ns = FaceForward(r.ns, r.n);
+    return r;
+}
+BPT_HD Vec3 InstancedWo(const DeviceInstance &I, Vec3 rayD) {
+    Vec3 dInst = XformVec(I.mInv, rayD);       // Transform::ApplyInverse(Vector3f)
+    return Normalize(XformVec(I.m, -dInst));   // ret.wo = Normalize(t(si.wo)), si.wo = -ray.d in instance space
+}
 
 struct TriData { Pt3 p0, p1, p2; TriAttribs a; int mesh, triIndex; };
 

@@ -108,6 +108,18 @@ struct DeviceImageLight {      // ImageInfiniteLight (lights.h:544-628)
     // image colour space = sRGB (tables shared)
 };
 
+// One object instance (TransformedPrimitive, cpu/primitive.cpp:112-130): renderFromInstance with its tracked inverse,
+// the 8-wide BVH of its object definition, and the global id of the definition's first triangle.
+// Instance 0 of an instanced scene is the identity pseudo-instance that holds all top-level (non-instanced) triangles.
+struct DeviceInstance {
+    Mat4 m, mInv;
+    const float4 *nodes;
+    const float4 *tris;
+    int triBase;
+    int identity;
+    int pad0, pad1;
+};
+
 struct IntegratorParams {
     int maxDepth;
     int regularize;

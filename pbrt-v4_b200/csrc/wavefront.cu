@@ -191,7 +191,27 @@ __global__ void __launch_bounds__(128) k_trace_closest(RenderCtx rc, int curQ) {
             rc.queues[Q_MAT0 + mt][p] = slot;
         }
     };
-    TraversePersistent<false, COUNT>(rc.bvh, nRays, &rc.counts[Q_CURSOR_CLOSEST], load, commit, &locNodes, &locTris, &locRays);
+    auto commitInst = [&](int i, const HitRec &rec) {
+        int slot = queue[i];
+        if (rec.tri < 0) {
+            if (rc.nInfinite > 0) { int p = WarpAggPush(&rc.counts[Q_ESCAPED]); rc.queues[Q_ESCAPED][p] = slot; }
+        } else {
+            const DeviceInstance &I = rc.bvh.instances[rec.inst];
+            const float4 *tp = I.tris + (size_t)rec.tri * 3;
+            int orig = __float_as_int(__ldg(tp).w) + I.triBase;
+            unsigned cls = __float_as_uint(__ldg(tp + 1).w);
+            rc.ps.hit[slot] = make_float4(__int_as_float(orig), rec.b0, rec.b1, rec.b2);
+            rc.ps.hitInst[slot] = rec.inst;
+            if (cls & 0x100u) { int p = WarpAggPush(&rc.counts[Q_HITLIGHT]); rc.queues[Q_HITLIGHT][p] = slot; }
+            unsigned mt = cls & 0xffu;
+            int p = WarpAggPush(&rc.counts[Q_MAT0 + mt]);
+            rc.queues[Q_MAT0 + mt][p] = slot;
+        }
+    };
+    if (rc.bvh.instances)
+        TraversePersistentInst<false, COUNT>(rc.bvh, rc.bvh.instances, nRays, &rc.counts[Q_CURSOR_CLOSEST], load, commitInst, &locNodes, &locTris, &locRays);
+    else
+        TraversePersistent<false, COUNT>(rc.bvh, nRays, &rc.counts[Q_CURSOR_CLOSEST], load, commit, &locNodes, &locTris, &locRays);
     if (COUNT) {
         atomicAdd(&rc.stats[3], (unsigned long long)locNodes);
         atomicAdd(&rc.stats[4], (unsigned long long)locTris);
@@ -218,7 +238,10 @@ __global__ void __launch_bounds__(128) k_trace_shadow(RenderCtx rc) {
             rc.ps.L[slot] = L;
         }
     };
-    TraversePersistent<true, COUNT>(rc.bvh, nRays, &rc.counts[Q_CURSOR_SHADOW], load, commit, &locNodes, &locTris, &locRays);
+    if (rc.bvh.instances)
+        TraversePersistentInst<true, COUNT>(rc.bvh, rc.bvh.instances, nRays, &rc.counts[Q_CURSOR_SHADOW], load, commit, &locNodes, &locTris, &locRays);
+    else
+        TraversePersistent<true, COUNT>(rc.bvh, nRays, &rc.counts[Q_CURSOR_SHADOW], load, commit, &locNodes, &locTris, &locRays);
     if (COUNT) {
         atomicAdd(&rc.stats[6], (unsigned long long)locNodes);
         atomicAdd(&rc.stats[7], (unsigned long long)locTris);
@@ -242,6 +265,7 @@ __global__ void __launch_bounds__(128) k_handle_emissive(RenderCtx rc) {
         const DeviceLight &light = rc.sv.lights[lightIndex];
         float4 d4 = ps.rayD[slot];
         Vec3 rd(d4.x, d4.y, d4.z);
+        // (area lights are not allowed on instanced shapes -- scene.cpp -- so emissive hits are always in the identity instance)
         Wavelengths wl = LoadLambda(ps, slot);
         Spec Le = AreaLightL(rc.sv, light, isect.n, -rd, wl);
         if (!Le.IsNonZero()) continue;
@@ -311,6 +335,10 @@ __global__ void __launch_bounds__(128) k_shade(RenderCtx rc, int nextQ) {
         const DeviceMesh &mesh = rc.sv.meshes[td.mesh];
         float4 d4 = ps.rayD[slot];
         Vec3 wo = -Vec3(d4.x, d4.y, d4.z);
+        if (rc.sv.instances) {
+            const DeviceInstance &I = rc.sv.instances[ps.hitInst[slot]];
+            if (!I.identity) { isect = XformInteraction(I, isect); wo = InstancedWo(I, Vec3(d4.x, d4.y, d4.z)); }
+        }
         Wavelengths wl = LoadLambda(ps, slot);
         uint4 misc = ps.misc[slot];
         int depth = misc.w & 0xff;
@@ -505,7 +533,14 @@ __global__ void __launch_bounds__(128) k_trace_raw(BVHView bvh, const float4 *ra
         hits[i] = make_float4(__int_as_float(orig), rec.b0, rec.b1, rec.b2);
         if (tOut) tOut[i] = rec.tri >= 0 ? rec.t : BPT_INFINITY;
     };
-    TraversePersistent<ANY, COUNT>(bvh, n, cursor, load, commit, &locNodes, &locTris, &locRays);
+    auto commitInst = [&](int i, const HitRec &rec) {
+        int orig = -1;
+        if (rec.tri >= 0) orig = __float_as_int(__ldg(bvh.instances[rec.inst].tris + (size_t)rec.tri * 3).w) + bvh.instances[rec.inst].triBase;
+        hits[i] = make_float4(__int_as_float(orig), rec.b0, rec.b1, rec.b2);
+        if (tOut) tOut[i] = rec.tri >= 0 ? rec.t : BPT_INFINITY;
+    };
+    if (bvh.instances) TraversePersistentInst<ANY, COUNT>(bvh, bvh.instances, n, cursor, load, commitInst, &locNodes, &locTris, &locRays);
+    else TraversePersistent<ANY, COUNT>(bvh, n, cursor, load, commit, &locNodes, &locTris, &locRays);
     if (COUNT && stats) { atomicAdd(&stats[3], (unsigned long long)locNodes); atomicAdd(&stats[4], (unsigned long long)locTris); }
 }
 

@@ -21,6 +21,7 @@ struct PathState {
     float4 *rayO;        // o.xyz, (unused)
     float4 *rayD;        // d.xyz, time
     float4 *hit;         // original triangle id (int bits), b0, b1, b2
+    int *hitInst;        // instance id of the hit (two-level scenes only)
     float4 *beta, *r_u, *r_l, *L;
     float4 *lambda, *lambdaPdf;
     float4 *ctx0;        // prevIntrCtx: pi.x.low, pi.x.high, pi.y.low, pi.y.high

@@ -137,3 +137,57 @@ def mixed_envmap(outdir, n=2236, res=(1920, 1080), spp=1024, maxdepth=5, envres=
     path = os.path.join(outdir, "mixed.pbrt")
     open(path, "w").write(s)
     return path
+
+
+def icosphere(subdiv):
+    t = (1.0 + 5 ** 0.5) / 2
+    V = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    F = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+         (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    V = [np.array(v, dtype=np.float64) / np.linalg.norm(v) for v in V]
+    for _ in range(subdiv):
+        cache, F2 = {}, []
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = V[a] + V[b]
+                V.append(m / np.linalg.norm(m))
+                cache[key] = len(V) - 1
+            return cache[key]
+        for a, b, c in F:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            F2 += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        F = F2
+    return np.array(V, dtype=np.float32), np.array(F, dtype=np.int32)
+
+
+def instanced(outdir, n_inst=100000, subdiv=3, res=(2048, 2048), spp=512, maxdepth=5, seed=99, material="coatedconductor"):
+    """Config 4: one icosphere mesh (20*4^subdiv triangles; subdiv=3 -> 1280) as an object definition, `n_inst` instances with
+    seeded random translate / rotate / scale in a 100 x 10 x 100 slab (scaled with n_inst), one quad light above."""
+    os.makedirs(outdir, exist_ok=True)
+    V, F = icosphere(subdiv)
+    write_ply(os.path.join(outdir, "ico.ply"), V, F)
+    ext = 50.0 * (n_inst / 100000.0) ** (1 / 3)
+    s = _header(res, spp, maxdepth, ((0, 0.9 * ext, 1.6 * ext), (0, 0, 0)), 45)
+    L = 40.0
+    s += ("AttributeBegin\n  AreaLightSource \"diffuse\" \"rgb L\" [%g %g %g]\n  Material \"diffuse\" \"rgb reflectance\" [0 0 0]\n"
+          "  Shape \"trianglemesh\" \"integer indices\" [0 1 2 0 2 3] \"point3 P\" [%g %g %g  %g %g %g  %g %g %g  %g %g %g]\nAttributeEnd\n" %
+          (L, L, L, -ext, ext, -ext, ext, ext, -ext, ext, ext, ext, -ext, ext, ext))
+    s += ("Material \"diffuse\" \"rgb reflectance\" [0.5 0.5 0.5]\nShape \"trianglemesh\" \"integer indices\" [0 1 2 0 2 3] \"point3 P\" "
+          "[%g %g %g  %g %g %g  %g %g %g  %g %g %g]\n" % (-2 * ext, -0.12 * ext, -2 * ext, -2 * ext, -0.12 * ext, 2 * ext, 2 * ext, -0.12 * ext, 2 * ext, 2 * ext, -0.12 * ext, -2 * ext))
+    mat = {"coatedconductor": "Material \"coatedconductor\"\n", "diffuse": "Material \"diffuse\" \"rgb reflectance\" [0.7 0.4 0.3]\n",
+           "conductor": "Material \"conductor\" \"float roughness\" 0.2\n"}[material]
+    s += "AttributeBegin\n" + mat + "ObjectBegin \"ico\"\n  Shape \"plymesh\" \"string filename\" \"ico.ply\"\nObjectEnd\nAttributeEnd\n"
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lines = []
+    for i in range(n_inst):
+        tx, ty, tz = rng.uniform(-ext, ext), rng.uniform(-0.1 * ext, 0.1 * ext), rng.uniform(-ext, ext)
+        ang = rng.uniform(0, 360); ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+        sc = rng.uniform(0.35, 0.7) * (ext / 50.0) * 50.0 / (n_inst ** (1 / 3)) * 0.9
+        lines.append("AttributeBegin\n  Translate %.6f %.6f %.6f\n  Rotate %.5f %.6f %.6f %.6f\n  Scale %.6f %.6f %.6f\n  ObjectInstance \"ico\"\nAttributeEnd\n" %
+                     (tx, ty, tz, ang, ax[0], ax[1], ax[2], sc, sc, sc))
+    s += "".join(lines)
+    path = os.path.join(outdir, "instanced.pbrt")
+    open(path, "w").write(s)
+    return path

@@ -12,6 +12,8 @@ if which == "heightfield":
     path = scenes.diffuse_heightfield(out, n=n, res=(res, res), spp=spp)
 elif which == "cornell":
     path = scenes.cornell(out, res=(res, res), spp=spp)
+elif which == "instanced":
+    path = scenes.instanced(out, n_inst=int(os.environ.get("NINST", "200")), subdiv=int(os.environ.get("SUBDIV", "2")), res=(res, res), spp=spp, material=os.environ.get("MAT", "diffuse"))
 elif which == "mixed":
     path = scenes.mixed_envmap(out, n=n, res=(res, res), spp=spp, envres=int(os.environ.get("ENVRES", "128")), nmesh=int(os.environ.get("NMESH", "8")))
 else:
