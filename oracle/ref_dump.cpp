@@ -48,6 +48,7 @@
 #include <pbrt/pbrt.h>
 #include <pbrt/cpu/aggregates.h>
 #include <pbrt/cpu/primitive.h>
+#include <pbrt/bxdfs.h>
 #include <pbrt/lightsamplers.h>
 #include <pbrt/lights.h>
 #include <pbrt/options.h>
@@ -253,6 +254,38 @@ static void DumpGolden(const char *path) {
         }
         b.f32("spectrum_in", in);
         b.f32("spectrum_out", out);
+    }
+    // BxDFs in the local frame: conductor, dielectric, coated conductor (LayeredBxDF) -- f, Sample_f, PDF
+    {
+        struct Cfg { float ia, ca, thick, g, albedo; int maxDepth, nSamples; };
+        Cfg cfgs[4] = {{0.f, 0.f, 0.01f, 0.f, 0.f, 10, 1}, {0.3f, 0.2f, 0.01f, 0.f, 0.f, 10, 1}, {0.25f, 0.3f, 0.05f, 0.3f, 0.6f, 10, 2}, {0.f, 0.4f, 0.02f, -0.2f, 0.f, 6, 1}};
+        std::vector<float> in, out;
+        for (int c = 0; c < 4; ++c) {
+            SampledSpectrum eta(0.2f + 0.1f * c), k(3.f + 0.3f * c), alb(cfgs[c].albedo);
+            eta[1] = 0.9f; k[2] = 2.2f;
+            DielectricBxDF top(1.5f, TrowbridgeReitzDistribution(cfgs[c].ia, cfgs[c].ia));
+            ConductorBxDF bottom(TrowbridgeReitzDistribution(cfgs[c].ca, cfgs[c].ca * 0.5f), eta, k);
+            CoatedConductorBxDF layered(top, bottom, cfgs[c].thick, alb, cfgs[c].g, cfgs[c].maxDepth, cfgs[c].nSamples);
+            for (int i = 0; i < 256; ++i) {
+                auto r = [&]() { return 2 * rng.Uniform<float>() - 1; };
+                Vector3f wo = Normalize(Vector3f(r(), r(), r())), wi = Normalize(Vector3f(r(), r(), r()));
+                if (i % 3 == 0) wi.z = std::abs(wi.z) * (wo.z > 0 ? 1 : -1);
+                Float uc = rng.Uniform<float>(); Point2f u(rng.Uniform<float>(), rng.Uniform<float>());
+                in.insert(in.end(), {(float)c, wo.x, wo.y, wo.z, wi.x, wi.y, wi.z, uc, u.x, u.y});
+                auto put = [&](SampledSpectrum f, Float pdf, pstd::optional<BSDFSample> bs, int flags) {
+                    out.insert(out.end(), {f[0], f[1], f[2], f[3], pdf, (float)flags});
+                    if (bs) out.insert(out.end(), {1.f, bs->f[0], bs->f[1], bs->f[2], bs->f[3], bs->wi.x, bs->wi.y, bs->wi.z, bs->pdf, (float)bs->flags, bs->eta, bs->pdfIsProportional ? 1.f : 0.f});
+                    else out.insert(out.end(), {0.f, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0});
+                };
+                put(bottom.f(wo, wi, TransportMode::Radiance), bottom.PDF(wo, wi, TransportMode::Radiance, BxDFReflTransFlags::All),
+                    bottom.Sample_f(wo, uc, u, TransportMode::Radiance), (int)bottom.Flags());
+                DielectricBxDF rough(1.3f + 0.1f * c, TrowbridgeReitzDistribution(cfgs[c].ca, cfgs[c].ca));
+                put(rough.f(wo, wi, TransportMode::Radiance), rough.PDF(wo, wi, TransportMode::Radiance), rough.Sample_f(wo, uc, u, TransportMode::Radiance), (int)rough.Flags());
+                put(layered.f(wo, wi, TransportMode::Radiance), layered.PDF(wo, wi, TransportMode::Radiance), layered.Sample_f(wo, uc, u, TransportMode::Radiance), (int)layered.Flags());
+            }
+        }
+        b.f32("bxdf_in", in);
+        b.f32("bxdf_out", out);
     }
     // ImageInfiniteLight: Le / SampleLi / PDF_Li on a seeded procedural 32x32 equal-area environment map
     {

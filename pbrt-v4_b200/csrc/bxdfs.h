@@ -321,6 +321,291 @@ struct DielectricBxDF {
     BPT_HD void Regularize() { mfDistrib.Regularize(); }
 };
 
+// ---------------------------------------------------------------- Henyey-Greenstein (media.h:43-71, util/scattering.h, util/sampling.cpp)
+BPT_HD float HenyeyGreenstein(float cosTheta, float g) {
+    g = Clampf(g, -.99f, .99f);
+    float denom = 1 + Sqr(g) + 2 * g * cosTheta;
+    return kInv4Pi * (1 - Sqr(g)) / (denom * SafeSqrt(denom));
+}
+BPT_HD Vec3 SampleHenyeyGreenstein(Vec3 wo, float g, Vec2 u, float *pdf) {
+    g = Clampf(g, -.99f, .99f);
+    float cosTheta;
+    if (fabsf(g) < 1e-3f) cosTheta = 1 - 2 * u.x;
+    else cosTheta = -1 / (2 * g) * (1 + Sqr(g) - Sqr((1 - Sqr(g)) / (1 + g - 2 * g * u.x)));
+    float sinTheta = SafeSqrt(1 - Sqr(cosTheta));
+    float phi = 2 * kPi * u.y;
+    Frame wFrame = Frame::FromZ(wo);
+    Vec3 local(Clampf(sinTheta, -1, 1) * CosF(phi), Clampf(sinTheta, -1, 1) * SinF(phi), Clampf(cosTheta, -1, 1));
+    Vec3 wi = wFrame.FromLocal(local);
+    *pdf = HenyeyGreenstein(cosTheta, g);
+    return wi;
+}
+BPT_HD float PowerHeuristic(int nf, float fPdf, int ng, float gPdf) {
+    float f = nf * fPdf, g = ng * gPdf;
+    if (IsInf_(Sqr(f))) return 1;
+    return Sqr(f) / (Sqr(f) + Sqr(g));
+}
+BPT_HD float SampleExponential(float u, float a) { return -LogF(1 - u) / a; }
+BPT_HD uint64_t Hash_i32_f32x3(int s, Vec3 v) {   // Hash(int seed, Vector3f)
+    uint64_t w[2] = {(uint64_t)(uint32_t)s | ((uint64_t)f2b(v.x) << 32), (uint64_t)f2b(v.y) | ((uint64_t)f2b(v.z) << 32)};
+    return MurmurHash64A(w, 16, 0);
+}
+
+// ---------------------------------------------------------------- LayeredBxDF (bxdfs.h:431-900), twoSided = true instantiation
+// Argument evaluation order: the reference writes e.g. `Sample_f(wo, uc, Point2f(r(), r()), ...)`; the order in which
+// the two r() calls run is unspecified in C++ and fixed by the compiler that built the reference (gcc evaluates the
+// arguments of a call right to left).  BPT_R2(a, b) draws in that order: b first, then a.
+#define BPT_R2(a, b) float b = r(); float a = r();
+template <typename TopBxDF, typename BottomBxDF>
+struct LayeredBxDF {
+    TopBxDF top;
+    BottomBxDF bottom;
+    float thickness, g;
+    Spec albedo;
+    int maxDepth, nSamples;
+    int seed;   // Options->seed
+
+    BPT_HD static float Tr(float dz, Vec3 w) {
+        if (fabsf(dz) <= FLT_MIN) return 1;
+        return FastExp(-fabsf(dz / w.z));
+    }
+    BPT_HD void Regularize() { top.Regularize(); bottom.Regularize(); }
+    BPT_HD int Flags() const {
+        int topFlags = top.Flags(), bottomFlags = bottom.Flags();
+        int flags = BXDF_REFLECTION;
+        if (IsSpecular(topFlags)) flags |= BXDF_SPECULAR;
+        if ((topFlags & BXDF_DIFFUSE) || (bottomFlags & BXDF_DIFFUSE) || albedo.IsNonZero()) flags |= BXDF_DIFFUSE;
+        else if ((topFlags & BXDF_GLOSSY) || (bottomFlags & BXDF_GLOSSY)) flags |= BXDF_GLOSSY;
+        if (IsTransmissive(topFlags) && IsTransmissive(bottomFlags)) flags |= BXDF_TRANSMISSION;
+        return flags;
+    }
+    // interface selectors (TopOrBottomBxDF): which = 0 top, 1 bottom
+    BPT_HD Spec If(int which, Vec3 wo, Vec3 wi, int mode) const { return which == 0 ? top.f(wo, wi, mode) : bottom.f(wo, wi, mode); }
+    BPT_HD BSDFSample ISample(int which, Vec3 wo, float uc, Vec2 u, int mode, int sf = REFLTRANS_ALL) const {
+        return which == 0 ? top.Sample_f(wo, uc, u, mode, sf) : bottom.Sample_f(wo, uc, u, mode, sf);
+    }
+    BPT_HD float IPDF(int which, Vec3 wo, Vec3 wi, int mode, int sf = REFLTRANS_ALL) const {
+        return which == 0 ? top.PDF(wo, wi, mode, sf) : bottom.PDF(wo, wi, mode, sf);
+    }
+    BPT_HD int IFlags(int which) const { return which == 0 ? top.Flags() : bottom.Flags(); }
+    BPT_HD static bool Bad(const BSDFSample &b) { return !b.valid || !b.f.IsNonZero() || b.pdf == 0 || b.wi.z == 0; }
+
+    BPT_HD Spec f(Vec3 wo, Vec3 wi, int mode) const {
+        Spec fsum(0.f);
+        if (wo.z < 0) { wo = -wo; wi = -wi; }
+        const bool enteredTop = true;
+        int enterI = 0;
+        int exitI, nonExitI;
+        if (SameHemisphere(wo, wi) ^ enteredTop) { exitI = 1; nonExitI = 0; } else { exitI = 0; nonExitI = 1; }
+        float exitZ = (SameHemisphere(wo, wi) ^ enteredTop) ? 0 : thickness;
+        if (SameHemisphere(wo, wi)) fsum = nSamples * If(enterI, wo, wi, mode);
+        RNG rng(Hash_i32_f32x3(seed, wo), Hash_f32x3(wi.x, wi.y, wi.z));
+        auto r = [&rng]() { return stdmin(rng.UniformFloat(), kOneMinusEpsilon); };
+        for (int s = 0; s < nSamples; ++s) {
+            float uc = r();
+            BPT_R2(ua, ub)
+            BSDFSample wos = ISample(enterI, wo, uc, Vec2(ua, ub), mode, REFLTRANS_TRANSMISSION);
+            if (Bad(wos)) continue;
+            uc = r();
+            BPT_R2(uc2, ud2)
+            BSDFSample wis = ISample(exitI, wi, uc, Vec2(uc2, ud2), !mode, REFLTRANS_TRANSMISSION);
+            if (Bad(wis)) continue;
+            Spec beta = wos.f * AbsCosTheta(wos.wi) / wos.pdf;
+            float z = enteredTop ? thickness : 0;
+            Vec3 w = wos.wi;
+            for (int depth = 0; depth < maxDepth; ++depth) {
+                if (depth > 3 && beta.MaxComponentValue() < 0.25f) {
+                    float q = stdmax(0.f, 1 - beta.MaxComponentValue());
+                    if (r() < q) break;
+                    beta /= 1 - q;
+                }
+                if (!albedo.IsNonZero()) {
+                    z = (z == thickness) ? 0 : thickness;
+                    beta *= Tr(thickness, w);
+                } else {
+                    float sigma_t = 1;
+                    float dz = SampleExponential(r(), sigma_t / fabsf(w.z));
+                    float zp = w.z > 0 ? (z + dz) : (z - dz);
+                    if (z == zp) continue;
+                    if (0 < zp && zp < thickness) {
+                        float wt = 1;
+                        if (!IsSpecular(IFlags(exitI))) wt = PowerHeuristic(1, wis.pdf, 1, HenyeyGreenstein(Dot(-w, -wis.wi), g));
+                        fsum += beta * albedo * HenyeyGreenstein(Dot(-w, -wis.wi), g) * wt * Tr(zp - exitZ, wis.wi) * wis.f / wis.pdf;
+                        float u0 = r(); float u1 = r();   // Point2f u{r(), r()}: braced list, left to right
+                        float ppdf;
+                        Vec3 pwi = SampleHenyeyGreenstein(-w, g, Vec2(u0, u1), &ppdf);
+                        if (ppdf == 0 || pwi.z == 0) continue;
+                        beta *= albedo * ppdf / ppdf;
+                        w = pwi;
+                        z = zp;
+                        if (((z < exitZ && w.z > 0) || (z > exitZ && w.z < 0)) && !IsSpecular(IFlags(exitI))) {
+                            Spec fExit = If(exitI, -w, wi, mode);
+                            if (fExit.IsNonZero()) {
+                                float exitPDF = IPDF(exitI, -w, wi, mode, REFLTRANS_TRANSMISSION);
+                                float wt2 = PowerHeuristic(1, ppdf, 1, exitPDF);
+                                fsum += beta * Tr(zp - exitZ, pwi) * fExit * wt2;
+                            }
+                        }
+                        continue;
+                    }
+                    z = Clampf(zp, 0, thickness);
+                }
+                if (z == exitZ) {
+                    float uc3 = r();
+                    BPT_R2(ue, uf)
+                    BSDFSample bs = ISample(exitI, -w, uc3, Vec2(ue, uf), mode, REFLTRANS_REFLECTION);
+                    if (Bad(bs)) break;
+                    beta *= bs.f * AbsCosTheta(bs.wi) / bs.pdf;
+                    w = bs.wi;
+                } else {
+                    if (!IsSpecular(IFlags(nonExitI))) {
+                        float wt = 1;
+                        if (!IsSpecular(IFlags(exitI))) wt = PowerHeuristic(1, wis.pdf, 1, IPDF(nonExitI, -w, -wis.wi, mode));
+                        fsum += beta * If(nonExitI, -w, -wis.wi, mode) * AbsCosTheta(wis.wi) * wt * Tr(thickness, wis.wi) * wis.f / wis.pdf;
+                    }
+                    float uc4 = r();
+                    BPT_R2(ug, uh)   // Point2f u(r(), r())
+                    BSDFSample bs = ISample(nonExitI, -w, uc4, Vec2(ug, uh), mode, REFLTRANS_REFLECTION);
+                    if (Bad(bs)) break;
+                    beta *= bs.f * AbsCosTheta(bs.wi) / bs.pdf;
+                    w = bs.wi;
+                    if (!IsSpecular(IFlags(exitI))) {
+                        Spec fExit = If(exitI, -w, wi, mode);
+                        if (fExit.IsNonZero()) {
+                            float wt = 1;
+                            if (!IsSpecular(IFlags(nonExitI))) {
+                                float exitPDF = IPDF(exitI, -w, wi, mode, REFLTRANS_TRANSMISSION);
+                                wt = PowerHeuristic(1, bs.pdf, 1, exitPDF);
+                            }
+                            fsum += beta * Tr(thickness, bs.wi) * fExit * wt;
+                        }
+                    }
+                }
+            }
+        }
+        return fsum / nSamples;
+    }
+
+    BPT_HD BSDFSample Sample_f(Vec3 wo, float uc, Vec2 u, int mode, int sampleFlags = REFLTRANS_ALL) const {
+        bool flipWi = false;
+        if (wo.z < 0) { wo = -wo; flipWi = true; }
+        BSDFSample bs = top.Sample_f(wo, uc, u, mode);
+        if (Bad(bs)) return {};
+        if (IsReflective(bs.flags)) {
+            if (flipWi) bs.wi = -bs.wi;
+            bs.pdfIsProportional = true;
+            return bs;
+        }
+        Vec3 w = bs.wi;
+        bool specularPath = IsSpecular(bs.flags);
+        uint64_t wu[2] = {(uint64_t)f2b(uc) | ((uint64_t)f2b(u.x) << 32), (uint64_t)f2b(u.y)};
+        RNG rng(Hash_i32_f32x3(seed, wo), MurmurHash64A(wu, 12, 0));   // Hash(uc, u)
+        auto r = [&rng]() { return stdmin(rng.UniformFloat(), kOneMinusEpsilon); };
+        Spec f = bs.f * AbsCosTheta(bs.wi);
+        float pdf = bs.pdf;
+        float z = thickness;
+        for (int depth = 0; depth < maxDepth; ++depth) {
+            float rrBeta = f.MaxComponentValue() / pdf;
+            if (depth > 3 && rrBeta < 0.25f) {
+                float q = stdmax(0.f, 1 - rrBeta);
+                if (r() < q) return {};
+                pdf *= 1 - q;
+            }
+            if (w.z == 0) return {};
+            if (albedo.IsNonZero()) {
+                float sigma_t = 1;
+                float dz = SampleExponential(r(), sigma_t / AbsCosTheta(w));
+                float zp = w.z > 0 ? (z + dz) : (z - dz);
+                if (zp == z) return {};
+                if (0 < zp && zp < thickness) {
+                    BPT_R2(up0, up1)   // phase.Sample_p(-w, Point2f(r(), r()))
+                    float ppdf;
+                    Vec3 pwi = SampleHenyeyGreenstein(-w, g, Vec2(up0, up1), &ppdf);
+                    if (ppdf == 0 || pwi.z == 0) return {};
+                    f *= albedo * ppdf;
+                    pdf *= ppdf;
+                    specularPath = false;
+                    w = pwi;
+                    z = zp;
+                    continue;
+                }
+                z = Clampf(zp, 0, thickness);
+            } else {
+                z = (z == thickness) ? 0 : thickness;
+                f *= Tr(thickness, w);
+            }
+            int iface = (z == 0) ? 1 : 0;
+            float uc2 = r();
+            BPT_R2(ux, uy)   // Point2f u(r(), r())
+            BSDFSample b2 = ISample(iface, -w, uc2, Vec2(ux, uy), mode);
+            if (Bad(b2)) return {};
+            f *= b2.f;
+            pdf *= b2.pdf;
+            specularPath &= IsSpecular(b2.flags);
+            w = b2.wi;
+            if (IsTransmissive(b2.flags)) {
+                int flags = SameHemisphere(wo, w) ? BXDF_REFLECTION : BXDF_TRANSMISSION;
+                flags |= specularPath ? BXDF_SPECULAR : BXDF_GLOSSY;
+                if (flipWi) w = -w;
+                return BSDFSample(f, w, pdf, flags, 1.f, true);
+            }
+            f *= AbsCosTheta(b2.wi);
+        }
+        return {};
+    }
+
+    BPT_HD float PDF(Vec3 wo, Vec3 wi, int mode, int sampleFlags = REFLTRANS_ALL) const {
+        if (wo.z < 0) { wo = -wo; wi = -wi; }
+        RNG rng(Hash_i32_f32x3(seed, wi), Hash_f32x3(wo.x, wo.y, wo.z));
+        auto r = [&rng]() { return stdmin(rng.UniformFloat(), kOneMinusEpsilon); };
+        float pdfSum = 0;
+        if (SameHemisphere(wo, wi)) pdfSum += nSamples * top.PDF(wo, wi, mode, REFLTRANS_REFLECTION);
+        for (int s = 0; s < nSamples; ++s) {
+            if (SameHemisphere(wo, wi)) {
+                const int rI = 1, tI = 0;
+                // tInterface.Sample_f(wo, r(), {r(), r()}, mode, trans): arguments right to left -> the braced pair first
+                float a0 = r(); float a1 = r(); float auc = r();
+                BSDFSample wos = ISample(tI, wo, auc, Vec2(a0, a1), mode, REFLTRANS_TRANSMISSION);
+                float b0 = r(); float b1 = r(); float buc = r();
+                BSDFSample wis = ISample(tI, wi, buc, Vec2(b0, b1), !mode, REFLTRANS_TRANSMISSION);
+                if (wos.valid && wos.f.IsNonZero() && wos.pdf > 0 && wis.valid && wis.f.IsNonZero() && wis.pdf > 0) {
+                    if (!IsNonSpecular(IFlags(tI))) pdfSum += IPDF(rI, -wos.wi, -wis.wi, mode);
+                    else {
+                        float c0 = r(); float c1 = r(); float cuc = r();
+                        BSDFSample rs = ISample(rI, -wos.wi, cuc, Vec2(c0, c1), mode);
+                        if (rs.valid && rs.f.IsNonZero() && rs.pdf > 0) {
+                            if (!IsNonSpecular(IFlags(rI))) pdfSum += IPDF(tI, -rs.wi, wi, mode);
+                            else {
+                                float rPDF = IPDF(rI, -wos.wi, -wis.wi, mode);
+                                float wt = PowerHeuristic(1, wis.pdf, 1, rPDF);
+                                pdfSum += wt * rPDF;
+                                float tPDF = IPDF(tI, -rs.wi, wi, mode);
+                                wt = PowerHeuristic(1, rs.pdf, 1, tPDF);
+                                pdfSum += wt * tPDF;
+                            }
+                        }
+                    }
+                }
+            } else {
+                const int toI = 0, tiI = 1;
+                float uc = r();
+                BPT_R2(d0, d1)
+                BSDFSample wos = ISample(toI, wo, uc, Vec2(d0, d1), mode);
+                if (Bad(wos) || IsReflective(wos.flags)) continue;
+                uc = r();
+                BPT_R2(e0, e1)
+                BSDFSample wis = ISample(tiI, wi, uc, Vec2(e0, e1), !mode);
+                if (Bad(wis) || IsReflective(wis.flags)) continue;
+                if (IsSpecular(IFlags(toI))) pdfSum += IPDF(tiI, -wos.wi, wi, mode);
+                else if (IsSpecular(IFlags(tiI))) pdfSum += IPDF(toI, wo, -wis.wi, mode);
+                else pdfSum += (IPDF(toI, wo, -wis.wi, mode) + IPDF(tiI, -wos.wi, wi, mode)) / 2;
+            }
+        }
+        return Lerp(0.9f, 1 / (4 * kPi), pdfSum / nSamples);
+    }
+};
+typedef LayeredBxDF<DielectricBxDF, ConductorBxDF> CoatedConductorBxDF;
+
 // ---------------------------------------------------------------- BSDF frame wrapper (bsdf.h)
 template <typename BxDF>
 struct BSDF {

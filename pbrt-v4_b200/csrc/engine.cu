@@ -544,6 +544,36 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             dm.flags = om.m.remap_roughness ? 1 : 0;
             break;
         }
+        case BPT_MAT_COATED_CONDUCTOR: {   // CoatedConductorMaterial::Create (materials.cpp)
+            dm.iface_uroughness = om.m.iface_uroughness >= 0 ? om.m.iface_uroughness : om.m.iface_roughness;
+            dm.iface_vroughness = om.m.iface_vroughness >= 0 ? om.m.iface_vroughness : om.m.iface_roughness;
+            dm.thickness = om.m.thickness > 0 ? om.m.thickness : .01f;
+            if (om.iface_eta.s.kind == BPT_SPEC_NONE) { dm.iface_eta.kind = SPEC_CONSTANT; dm.iface_eta.c0 = 1.5f; }
+            else if (!MakeSpectrumRec(e, om.iface_eta, ST_UNBOUNDED, spool, &dm.iface_eta, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
+            dm.uroughness = om.m.uroughness >= 0 ? om.m.uroughness : om.m.roughness;
+            dm.vroughness = om.m.vroughness >= 0 ? om.m.vroughness : om.m.roughness;
+            bool haveRefl = om.reflectance.s.kind != BPT_SPEC_NONE;
+            if (haveRefl && (om.conductor_eta.s.kind != BPT_SPEC_NONE || om.conductor_k.s.kind != BPT_SPEC_NONE))
+                return e->fail(BPT_ERR_INVALID, "coatedconductor: both reflectance and conductor.eta/k given");
+            if (haveRefl) {
+                dm.useReflectance = 1;
+                if (!MakeSpectrumRec(e, om.reflectance, ST_ALBEDO, spool, &dm.reflectance, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
+            } else {
+                OwnedSpectrum eta = om.conductor_eta, k = om.conductor_k;
+                if (eta.s.kind == BPT_SPEC_NONE) { eta.s.kind = BPT_SPEC_NAMED; std::strcpy(eta.s.name, "metal-Cu-eta"); }
+                if (k.s.kind == BPT_SPEC_NONE) { k.s.kind = BPT_SPEC_NAMED; std::strcpy(k.s.name, "metal-Cu-k"); }
+                if (!MakeSpectrumRec(e, eta, ST_UNBOUNDED, spool, &dm.eta, &serr) || !MakeSpectrumRec(e, k, ST_UNBOUNDED, spool, &dm.k, &serr))
+                    return e->fail(BPT_ERR_UNSUPPORTED, serr);
+            }
+            dm.maxDepth = om.m.max_depth > 0 ? om.m.max_depth : 10;
+            dm.nSamples = om.m.n_samples > 0 ? om.m.n_samples : 1;
+            dm.g = om.m.g;
+            if (om.albedo.s.kind == BPT_SPEC_NONE) { dm.albedo.kind = SPEC_CONSTANT; dm.albedo.c0 = 0.f; }
+            else if (!MakeSpectrumRec(e, om.albedo, ST_ALBEDO, spool, &dm.albedo, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
+            dm.flags = om.m.remap_roughness ? 1 : 0;
+            dm.optionsSeed = e->sampler.seed;
+            break;
+        }
         default: return e->fail(BPT_ERR_UNSUPPORTED, "material type not implemented yet");
         }
     }

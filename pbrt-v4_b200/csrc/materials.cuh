@@ -69,6 +69,42 @@ struct DielectricMaterialEval {
     }
 };
 
+struct CoatedConductorMaterialEval {
+    static constexpr int kTag = MAT_COATED_CONDUCTOR;
+    typedef CoatedConductorBxDF BxDF;
+    BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged) {
+        float iurough = m.iface_uroughness, ivrough = m.iface_vroughness;
+        if (m.flags & 1) { iurough = TRDist::RoughnessToAlpha(iurough); ivrough = TRDist::RoughnessToAlpha(ivrough); }
+        TRDist interfaceDistrib(iurough, ivrough);
+        float thick = m.thickness;
+        float ieta = EvalSpectrumAt(m.iface_eta, sv.specPool, wl.lambda[0]);
+        if (m.iface_eta.kind != SPEC_CONSTANT) { wl.TerminateSecondary(); *lambdaChanged = true; }
+        if (ieta == 0) ieta = 1;
+        Spec ce, ck;
+        if (!m.useReflectance) {
+            ce = EvalSpectrum(m.eta, sv.specPool, wl);
+            ck = EvalSpectrum(m.k, sv.specPool, wl);
+        } else {
+            Spec r = ClampSpec(EvalSpectrum(m.reflectance, sv.specPool, wl), 0, .9999f);
+            ce = Spec(1.f);
+            ck = 2 * SqrtSpec(r) / SqrtSpec(ClampZero(Spec(1) - r));
+        }
+        ce /= ieta;
+        ck /= ieta;
+        float curough = m.uroughness, cvrough = m.vroughness;
+        if (m.flags & 1) { curough = TRDist::RoughnessToAlpha(curough); cvrough = TRDist::RoughnessToAlpha(cvrough); }
+        TRDist conductorDistrib(curough, cvrough);
+        Spec a = ClampSpec(EvalSpectrum(m.albedo, sv.specPool, wl), 0, 1);
+        float gg = Clampf(m.g, -1, 1);
+        CoatedConductorBxDF b;
+        b.top.eta = ieta; b.top.mfDistrib = interfaceDistrib;
+        b.bottom.mfDistrib = conductorDistrib; b.bottom.eta = ce; b.bottom.k = ck;
+        b.thickness = stdmax(thick, FLT_MIN); b.albedo = a; b.g = gg; b.maxDepth = m.maxDepth; b.nSamples = m.nSamples;
+        b.seed = m.optionsSeed;
+        return b;
+    }
+};
+
 struct InterfaceMaterialEval {
     static constexpr int kTag = MAT_INTERFACE;
     typedef DiffuseBxDF BxDF;

@@ -52,7 +52,7 @@ struct DeviceMaterial {
     SpectrumRec iface_eta, albedo;
     int maxDepth, nSamples;
     int useReflectance;        // conductor specified by "reflectance" instead of eta/k
-    int pad;
+    int optionsSeed;           // Options->seed (LayeredBxDF seeds its RNG with it, bxdfs.h:510)
 };
 
 struct DeviceMesh {

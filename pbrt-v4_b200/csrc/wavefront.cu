@@ -631,11 +631,12 @@ void LaunchShade(const RenderCtx &rc, int materialTag, int nextQ, int sms, cudaS
     case MAT_DIFFUSE: k_shade<DiffuseMaterialEval><<<GridFor(sms, 8), 128, 0, st>>>(rc, nextQ); break;
     case MAT_CONDUCTOR: k_shade<ConductorMaterialEval><<<GridFor(sms, 8), 128, 0, st>>>(rc, nextQ); break;
     case MAT_DIELECTRIC: k_shade<DielectricMaterialEval><<<GridFor(sms, 8), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_COATED_CONDUCTOR: k_shade<CoatedConductorMaterialEval><<<GridFor(sms, 8), 128, 0, st>>>(rc, nextQ); break;
     case MAT_INTERFACE: k_shade<InterfaceMaterialEval><<<GridFor(sms, 4), 128, 0, st>>>(rc, nextQ); break;
     default: break;
     }
 }
-bool ShadeSupported(int materialTag) { return materialTag == MAT_DIFFUSE || materialTag == MAT_INTERFACE || materialTag == MAT_CONDUCTOR || materialTag == MAT_DIELECTRIC; }
+bool ShadeSupported(int materialTag) { return materialTag == MAT_DIFFUSE || materialTag == MAT_INTERFACE || materialTag == MAT_CONDUCTOR || materialTag == MAT_DIELECTRIC || materialTag == MAT_COATED_CONDUCTOR; }
 void LaunchUpdateFilm(const RenderCtx &rc, int x0, int x1, int y0, int y1, int nSamples, int sms, cudaStream_t st) {
     k_update_film<<<GridFor(sms, 8), 256, 0, st>>>(rc, x0, x1, y0, y1, nSamples);
 }
