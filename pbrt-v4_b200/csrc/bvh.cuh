@@ -145,11 +145,8 @@ BPT_D unsigned NodeIntersect(Vec3 o, Vec3 idir, unsigned octinv4, float tMax, fl
             float tmaxz = __fmaf_rn((float)ExtractByte(zmax, j), az, ozhi);
             float tmin = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, 0.f));
             float tmax = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, tMax));
-            if (tmin <= tmax) {
-                unsigned child_bits = ExtractByte(child_bits4, j);
-                unsigned bit_index = ExtractByte(bit_index4, j);
-                hitmask |= child_bits << bit_index;
-            }
+            unsigned hb = ExtractByte(child_bits4, j) << ExtractByte(bit_index4, j);
+            hitmask |= (tmin <= tmax) ? hb : 0u;   // branch-free: a branch here runs its body with ~3 lanes (ncu r01b)
         }
     }
     return hitmask;
@@ -230,11 +227,28 @@ BPT_D void TraceRay(const BVHView &bvh, Pt3 o, Vec3 d, float tMax, HitRec *rec, 
 //
 //   Load(i, &o, &d, &tMax)      reads ray i of the queue
 //   Commit(i, rec)              stores the result of ray i (called exactly once per ray, by the lane that owns it)
-constexpr int kFetchThreshold = 8;     // refill when at least this many lanes are idle
+// (tuning knobs are macros so that scripts/build_variants.py can sweep them on the GPU box)
+#ifndef BPT_FETCH_THRESHOLD
+#define BPT_FETCH_THRESHOLD 8
+#endif
+#ifndef BPT_FLUSH_LANES
+#define BPT_FLUSH_LANES 16
+#endif
+#ifndef BPT_ROUND_LANES
+#define BPT_ROUND_LANES 8
+#endif
+#ifndef BPT_TRI_BLOCK
+#define BPT_TRI_BLOCK 5
+#endif
+#ifndef BPT_DEFER_COMMIT
+#define BPT_DEFER_COMMIT 1
+#endif
+constexpr int kFetchThreshold = BPT_FETCH_THRESHOLD;   // refill when at least this many lanes are idle
 constexpr int kTriCap = 8;             // per-lane ring of deferred leaf groups (triBase, hit mask); one entry per node step
-constexpr int kTriBlock = 5;           // a lane stops taking node steps while it holds more than this many groups
-constexpr int kFlushLanes = 16;        // start triangle rounds when this many lanes have candidates
-constexpr int kRoundLanes = 8;         // keep going while this many lanes still have candidates
+constexpr int kTriBlock = BPT_TRI_BLOCK;       // a lane stops taking node steps while it holds more than this many groups
+constexpr int kFlushLanes = BPT_FLUSH_LANES;   // start triangle rounds when this many lanes have candidates
+constexpr int kRoundLanes = BPT_ROUND_LANES;   // keep going while this many lanes still have candidates
+constexpr bool kDeferCommit = BPT_DEFER_COMMIT != 0;   // finished lanes wait and commit together with the next refill
 
 template <bool ANYHIT, bool COUNT, typename LoadF, typename CommitF>
 BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF Load, CommitF Commit, unsigned *nNodes,
@@ -252,9 +266,21 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
     unsigned head = 0, tail = 0;   // deferred triangle ring [head, tail)
     uint2 cur = make_uint2(0, 0);
     HitRec rec; rec.tri = -1; rec.t = 0; rec.b0 = rec.b1 = rec.b2 = 0;
+    bool done = false;             // traversal of rayIdx finished, result not yet committed
     while (true) {
+        // ---- commit (batched: finished lanes wait until enough of them can commit and refill together)
+        unsigned doneMask = __ballot_sync(FULL, done);
+        unsigned idle = __ballot_sync(FULL, rayIdx < 0) | doneMask;
+        if (doneMask != 0 && (!kDeferCommit || __popc(idle) >= kFetchThreshold || idle == FULL || exhausted)) {
+            if (done) {
+                Commit(rayIdx, rec);
+                if (COUNT) ++*nRaysDone;
+                rayIdx = -1; done = false;
+            }
+        } else {
+            idle &= ~doneMask;
+        }
         // ---- fetch
-        unsigned idle = __ballot_sync(FULL, rayIdx < 0);
         if (idle != 0 && !exhausted && (__popc(idle) >= kFetchThreshold || idle == FULL)) {
             int nNeed = __popc(idle);
             int base = 0;
@@ -279,8 +305,8 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
                 }
             }
         }
-        bool act = rayIdx >= 0;
-        if (!__any_sync(FULL, act)) break;
+        bool act = rayIdx >= 0 && !done;
+        if (!__any_sync(FULL, rayIdx >= 0)) break;
         // ---- one node step for every lane that has node work and room for its triangle candidates
         bool canNode = act && (cur.y & 0xff000000u) != 0 && (tail - head) <= (unsigned)kTriBlock;
         if (canNode) {
@@ -333,15 +359,10 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
                 if (__popc(m) < kRoundLanes && anyNodeRunnable) break;
             }
         }
-        // ---- commit finished rays
+        // ---- mark finished rays (committed at the top of the loop)
         if (act) {
             if (!finished && (cur.y & 0xff000000u) == 0 && sp == 0 && tail == head) finished = true;
-            if (finished) {
-                Commit(rayIdx, rec);
-                if (COUNT) ++*nRaysDone;
-                rayIdx = -1;
-                cur = make_uint2(0, 0); sp = 0; head = tail = 0;
-            }
+            if (finished) { done = true; cur = make_uint2(0, 0); sp = 0; head = tail = 0; }
         }
     }
 }
@@ -353,39 +374,6 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
 // traversed with the shifted tMax, and -- like the reference -- the reported tHit stays in the instance-space
 // parameterisation.  Stack protocol: [saved top-level node group][sentinel] are pushed on entry; the sentinel is popped
 // only after the lane's deferred triangle groups (which belong to the instance) are drained.
-struct InstRay { Pt3 o; Vec3 d; float dt; };
-BPT_D InstRay ApplyInverseRay(const Mat4 &Minv, Pt3 o, Vec3 d) {
-    const float (*m)[4] = Minv.m;
-    float x = o.x, y = o.y, z = o.z;
-    float xp = (m[0][0] * x + m[0][1] * y) + (m[0][2] * z + m[0][3]);
-    float yp = (m[1][0] * x + m[1][1] * y) + (m[1][2] * z + m[1][3]);
-    float zp = (m[2][0] * x + m[2][1] * y) + (m[2][2] * z + m[2][3]);
-    float wp = (m[3][0] * x + m[3][1] * y) + (m[3][2] * z + m[3][3]);
-    Vec3 e;   // exact input point: util/transform.cpp:263-276 (no |m[i][3]| term)
-    e.x = gamma_n(3) * (fabsf(m[0][0] * x) + fabsf(m[0][1] * y) + fabsf(m[0][2] * z));
-    e.y = gamma_n(3) * (fabsf(m[1][0] * x) + fabsf(m[1][1] * y) + fabsf(m[1][2] * z));
-    e.z = gamma_n(3) * (fabsf(m[2][0] * x) + fabsf(m[2][1] * y) + fabsf(m[2][2] * z));
-    Pt3i oi(Pt3(xp, yp, zp), e);
-    if (wp != 1) {
-        auto divI = [](Interval i, float f) { return f > 0 ? Interval(DivRoundDown(i.low, f), DivRoundUp(i.high, f))
-                                                          : Interval(DivRoundDown(i.high, f), DivRoundUp(i.low, f)); };
-        oi.x = divI(oi.x, wp); oi.y = divI(oi.y, wp); oi.z = divI(oi.z, wp);
-    }
-    Vec3 dn(m[0][0] * d.x + m[0][1] * d.y + m[0][2] * d.z, m[1][0] * d.x + m[1][1] * d.y + m[1][2] * d.z,
-            m[2][0] * d.x + m[2][1] * d.y + m[2][2] * d.z);
-    InstRay r; r.dt = 0;
-    float lengthSquared = LengthSquared(dn);
-    if (lengthSquared > 0) {
-        Vec3 oError(oi.x.Width() / 2, oi.y.Width() / 2, oi.z.Width() / 2);
-        float dt = Dot(Abs(dn), oError) / lengthSquared;
-        Vec3 off = dn * dt;
-        oi.x = oi.x + off.x; oi.y = oi.y + off.y; oi.z = oi.z + off.z;
-        r.dt = dt;
-    }
-    r.o = oi.p(); r.d = dn;
-    return r;
-}
-
 template <bool ANYHIT, bool COUNT, typename LoadF, typename CommitF>
 BPT_D void TraversePersistentInst(const BVHView &bvh, const DeviceInstance *instances, int nRays, int *cursor, LoadF Load,
                                   CommitF Commit, unsigned *nNodes, unsigned *nTris, unsigned *nRaysDone) {
@@ -413,8 +401,19 @@ BPT_D void TraversePersistentInst(const BVHView &bvh, const DeviceInstance *inst
         unsigned octinv = (d.x < 0 ? 0u : 4u) | (d.y < 0 ? 0u : 2u) | (d.z < 0 ? 0u : 1u);
         octinv4 = octinv * 0x01010101u;
     };
+    bool done = false;
     while (true) {
-        unsigned idle = __ballot_sync(FULL, rayIdx < 0);
+        unsigned doneMask = __ballot_sync(FULL, done);
+        unsigned idle = __ballot_sync(FULL, rayIdx < 0) | doneMask;
+        if (doneMask != 0 && (!kDeferCommit || __popc(idle) >= kFetchThreshold || idle == FULL || exhausted)) {
+            if (done) {
+                Commit(rayIdx, rec);
+                if (COUNT) ++*nRaysDone;
+                rayIdx = -1; done = false;
+            }
+        } else {
+            idle &= ~doneMask;
+        }
         if (idle != 0 && !exhausted && (__popc(idle) >= kFetchThreshold || idle == FULL)) {
             int nNeed = __popc(idle);
             int base = 0;
@@ -436,8 +435,8 @@ BPT_D void TraversePersistentInst(const BVHView &bvh, const DeviceInstance *inst
                 }
             }
         }
-        bool act = rayIdx >= 0;
-        if (!__any_sync(FULL, act)) break;
+        bool act = rayIdx >= 0 && !done;
+        if (!__any_sync(FULL, rayIdx >= 0)) break;
         // ---- enter the next instance of the pending top-level leaf group
         if (act && inst < 0 && instGroup.y != 0) {
             unsigned ti = 31 - __clz(instGroup.y);
@@ -536,9 +535,7 @@ BPT_D void TraversePersistentInst(const BVHView &bvh, const DeviceInstance *inst
             if (inst < 0 && nodeEmpty && sp == 0 && instGroup.y == 0 && tail == head) finished = true;
         }
         if (act && finished) {
-            Commit(rayIdx, rec);
-            if (COUNT) ++*nRaysDone;
-            rayIdx = -1;
+            done = true;
             cur = make_uint2(0, 0); sp = 0; head = tail = 0; inst = -1; instGroup = make_uint2(0, 0);
         }
     }

@@ -1,0 +1,250 @@
+// media.h -- participating media on the path, float-exact restatement of the reference's CPU semantics:
+//   HGPhaseFunction / HenyeyGreenstein / SampleHenyeyGreenstein   media.h:43-71, util/scattering.h:49-58, util/sampling.cpp:348-372
+//   HomogeneousMajorantIterator, DDAMajorantIterator              media.h:80-102, 136-214
+//   HomogeneousMedium / GridMedium ::SamplePoint / ::SampleRay    media.h:217-262, 265-352 (no emission: Le is rejected at intake)
+//   SampledGrid<Float>::Lookup (trilinear, zero outside)          util/containers.h:803-835
+//   Bounds3f::IntersectP(o, d, tMax, &t0, &t1), Bounds3f::Offset  util/vecmath.h:1547-1571, 1323-1332
+//   SampleT_maj                                                   media.h:736-800
+// Host + device so that tests/tools can pin it against vectors produced by the reference itself.
+#pragma once
+#include "pmath.h"
+#include "sampling.h"
+#include "spectrum.h"
+#include "scene.h"
+#include "bxdfs.h"   // SampleExponential
+
+namespace bpt {
+
+enum { MEDIUM_HOMOGENEOUS = 0, MEDIUM_GRID = 1 };
+
+struct DeviceMedium {
+    int type;
+    int sigmaA, sigmaS;          // offsets (floats) of the 471-entry DenselySampledSpectrum tables, already multiplied by "scale"
+    float g;
+    Mat4 mInv;                   // renderFromMedium.mInv (GridMedium)
+    float bmin[3], bmax[3];      // GridMedium::bounds (medium space)
+    const float *density;        // nx*ny*nz, x fastest
+    int nx, ny, nz;
+    const float *majorant;       // mres^3 maximum densities (MajorantGrid::voxels)
+    int mres[3];
+};
+
+// ------------------------------------------------------------------ phase function
+// (HenyeyGreenstein / SampleHenyeyGreenstein live in bxdfs.h, shared with LayeredBxDF)
+BPT_HD float PhaseHG_p(float g, Vec3 wo, Vec3 wi) { return HenyeyGreenstein(Dot(wo, wi), g); }
+
+// SampleDiscrete over three weights (util/sampling.h:79-113), offset only
+BPT_HD int SampleDiscrete3(float w0, float w1, float w2, float u) {
+    float w[3] = {w0, w1, w2};
+    float sumWeights = 0;
+    for (int i = 0; i < 3; ++i) sumWeights += w[i];
+    float up = u * sumWeights;
+    if (up == sumWeights) up = NextFloatDown(up);
+    int offset = 0;
+    float sum = 0;
+    while (offset < 2 && sum + w[offset] <= up) sum += w[offset++];   // (the reference DCHECKs offset < size)
+    return offset;
+}
+
+// ------------------------------------------------------------------ transforms (medium space)
+BPT_HD Pt3 ApplyInversePoint(const Mat4 &Minv, Pt3 p) {   // Transform::ApplyInverse(Point3f) (util/transform.h:387-398)
+    const float (*m)[4] = Minv.m;
+    float x = p.x, y = p.y, z = p.z;
+    float xp = (m[0][0] * x + m[0][1] * y) + (m[0][2] * z + m[0][3]);
+    float yp = (m[1][0] * x + m[1][1] * y) + (m[1][2] * z + m[1][3]);
+    float zp = (m[2][0] * x + m[2][1] * y) + (m[2][2] * z + m[2][3]);
+    float wp = (m[3][0] * x + m[3][1] * y) + (m[3][2] * z + m[3][3]);
+    if (wp == 1) return Pt3(xp, yp, zp);
+    return Pt3(xp, yp, zp) / wp;
+}
+BPT_HD Vec3 BoundsOffset(const float bmin[3], const float bmax[3], Pt3 p) {
+    Vec3 o(p.x - bmin[0], p.y - bmin[1], p.z - bmin[2]);
+    if (bmax[0] > bmin[0]) o.x /= bmax[0] - bmin[0];
+    if (bmax[1] > bmin[1]) o.y /= bmax[1] - bmin[1];
+    if (bmax[2] > bmin[2]) o.z /= bmax[2] - bmin[2];
+    return o;
+}
+BPT_HD bool BoundsIntersectP(const float bmin[3], const float bmax[3], Pt3 o, Vec3 d, float tMax, float *hitt0, float *hitt1) {
+    float t0 = 0, t1 = tMax;
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    for (int i = 0; i < 3; ++i) {
+        float invRayDir = 1 / dd[i];
+        float tNear = (bmin[i] - oo[i]) * invRayDir;
+        float tFar = (bmax[i] - oo[i]) * invRayDir;
+        if (tNear > tFar) { float t = tNear; tNear = tFar; tFar = t; }
+        tFar *= 1 + 2 * gamma_n(3);
+        t0 = tNear > t0 ? tNear : t0;
+        t1 = tFar < t1 ? tFar : t1;
+        if (t0 > t1) return false;
+    }
+    *hitt0 = t0; *hitt1 = t1;
+    return true;
+}
+
+// ------------------------------------------------------------------ density grid
+BPT_HD float GridFetch(const DeviceMedium &m, int x, int y, int z) {
+    if (x < 0 || y < 0 || z < 0 || x >= m.nx || y >= m.ny || z >= m.nz) return 0.f;
+    size_t i = ((size_t)z * m.ny + y) * m.nx + x;
+#if defined(__CUDA_ARCH__)
+    return __ldg(m.density + i);
+#else
+    return m.density[i];
+#endif
+}
+BPT_HD float GridLookup(const DeviceMedium &m, Vec3 p) {
+    float sx = p.x * m.nx - .5f, sy = p.y * m.ny - .5f, sz = p.z * m.nz - .5f;
+    float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
+    int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    float dx = sx - (float)ix, dy = sy - (float)iy, dz = sz - (float)iz;
+    float d00 = Lerp(dx, GridFetch(m, ix, iy, iz), GridFetch(m, ix + 1, iy, iz));
+    float d10 = Lerp(dx, GridFetch(m, ix, iy + 1, iz), GridFetch(m, ix + 1, iy + 1, iz));
+    float d01 = Lerp(dx, GridFetch(m, ix, iy, iz + 1), GridFetch(m, ix + 1, iy, iz + 1));
+    float d11 = Lerp(dx, GridFetch(m, ix, iy + 1, iz + 1), GridFetch(m, ix + 1, iy + 1, iz + 1));
+    return Lerp(dz, Lerp(dy, d00, d10), Lerp(dy, d01, d11));
+}
+
+// ------------------------------------------------------------------ majorant iterators
+struct MajorantSegment { float tMin, tMax; Spec sigma_maj; };
+
+struct MajorantIter {
+    int kind;                 // 0: exhausted / empty, 1: homogeneous (one segment), 2: DDA over the majorant grid
+    Spec sigma;               // homogeneous: sigma_maj; DDA: sigma_t
+    float tMin, tMax;
+    const float *grid; int res[3];
+    float nextCrossingT[3], deltaT[3];
+    int step[3], voxelLimit[3], voxel[3];
+
+    BPT_HD bool Next(MajorantSegment *seg) {
+        if (kind == 1) {
+            kind = 0;
+            seg->tMin = tMin; seg->tMax = tMax; seg->sigma_maj = sigma;
+            return true;
+        }
+        if (kind != 2) return false;
+        if (tMin >= tMax) return false;
+        int bits = ((nextCrossingT[0] < nextCrossingT[1]) << 2) + ((nextCrossingT[0] < nextCrossingT[2]) << 1) +
+                   ((nextCrossingT[1] < nextCrossingT[2]));
+        // cmpToAxis[8] = {2, 1, 2, 1, 2, 2, 0, 0}, packed 2 bits per entry
+        int stepAxis = (int)((0x0A66u >> (2 * bits)) & 3u);
+        float nct = stepAxis == 0 ? nextCrossingT[0] : (stepAxis == 1 ? nextCrossingT[1] : nextCrossingT[2]);
+        float tVoxelExit = stdmin(tMax, nct);
+        size_t vi = (size_t)voxel[0] + (size_t)res[0] * ((size_t)voxel[1] + (size_t)res[1] * (size_t)voxel[2]);
+#if defined(__CUDA_ARCH__)
+        float maxDensity = __ldg(grid + vi);
+#else
+        float maxDensity = grid[vi];
+#endif
+        seg->sigma_maj = sigma * maxDensity;
+        seg->tMin = tMin; seg->tMax = tVoxelExit;
+        tMin = tVoxelExit;
+        if (nct > tMax) tMin = tMax;
+        // (component updates written without dynamic indexing so that the arrays stay in registers)
+        if (stepAxis == 0) { voxel[0] += step[0]; if (voxel[0] == voxelLimit[0]) tMin = tMax; nextCrossingT[0] += deltaT[0]; }
+        else if (stepAxis == 1) { voxel[1] += step[1]; if (voxel[1] == voxelLimit[1]) tMin = tMax; nextCrossingT[1] += deltaT[1]; }
+        else { voxel[2] += step[2]; if (voxel[2] == voxelLimit[2]) tMin = tMax; nextCrossingT[2] += deltaT[2]; }
+        return true;
+    }
+};
+
+// InstRay ApplyInverseRay(Minv, o, d) is Transform::ApplyInverse(Ray, &tMax) (scene.h)
+BPT_HD MajorantIter MediumSampleRay(const DeviceMedium &m, const float *specPool, Pt3 o, Vec3 d, float raytMax, const Wavelengths &wl) {
+    MajorantIter it;
+    it.kind = 0;
+    Spec sigma_a = DenseSample(specPool + m.sigmaA, wl), sigma_s = DenseSample(specPool + m.sigmaS, wl);
+    if (m.type == MEDIUM_HOMOGENEOUS) {
+        it.kind = 1; it.tMin = 0; it.tMax = raytMax; it.sigma = sigma_a + sigma_s;
+        return it;
+    }
+    InstRay r = ApplyInverseRay(m.mInv, o, d);
+    raytMax -= r.dt;
+    float tMin, tMax;
+    if (!BoundsIntersectP(m.bmin, m.bmax, r.o, r.d, raytMax, &tMin, &tMax)) return it;
+    it.kind = 2;
+    it.sigma = sigma_a + sigma_s;
+    it.tMin = tMin; it.tMax = tMax;
+    it.grid = m.majorant;
+    // DDAMajorantIterator constructor
+    Vec3 diag(m.bmax[0] - m.bmin[0], m.bmax[1] - m.bmin[1], m.bmax[2] - m.bmin[2]);
+    Vec3 og = BoundsOffset(m.bmin, m.bmax, r.o);
+    float rd[3] = {r.d.x / diag.x, r.d.y / diag.y, r.d.z / diag.z};
+    float gi[3] = {og.x + rd[0] * tMin, og.y + rd[1] * tMin, og.z + rd[2] * tMin};
+    for (int axis = 0; axis < 3; ++axis) {
+        int res = m.mres[axis];
+        it.res[axis] = res;
+        float v = gi[axis] * res;
+        float lo = 0, hi = (float)(res - 1);
+        v = v < lo ? lo : (v > hi ? hi : v);
+        it.voxel[axis] = (int)v;
+        it.deltaT[axis] = 1 / (fabsf(rd[axis]) * res);
+        if (rd[axis] == -0.f) rd[axis] = 0.f;
+        if (rd[axis] >= 0) {
+            float nextVoxelPos = (float)(it.voxel[axis] + 1) / res;
+            it.nextCrossingT[axis] = tMin + (nextVoxelPos - gi[axis]) / rd[axis];
+            it.step[axis] = 1;
+            it.voxelLimit[axis] = res;
+        } else {
+            float nextVoxelPos = (float)(it.voxel[axis]) / res;
+            it.nextCrossingT[axis] = tMin + (nextVoxelPos - gi[axis]) / rd[axis];
+            it.step[axis] = -1;
+            it.voxelLimit[axis] = -1;
+        }
+    }
+    return it;
+}
+
+struct MediumProps { Spec sigma_a, sigma_s; };
+BPT_HD MediumProps MediumSamplePoint(const DeviceMedium &m, const float *specPool, Pt3 p, const Wavelengths &wl) {
+    MediumProps mp;
+    mp.sigma_a = DenseSample(specPool + m.sigmaA, wl);
+    mp.sigma_s = DenseSample(specPool + m.sigmaS, wl);
+    if (m.type == MEDIUM_GRID) {
+        Pt3 pm = ApplyInversePoint(m.mInv, p);
+        Vec3 po = BoundsOffset(m.bmin, m.bmax, pm);
+        float d = GridLookup(m, po);
+        mp.sigma_a *= d;
+        mp.sigma_s *= d;
+    }
+    return mp;
+}
+
+// SampleT_maj (media.h:736-800).  callback(p, mp, sigma_maj, T_maj) -> bool (false stops the tracking)
+template <typename F>
+BPT_HD Spec SampleT_maj(const DeviceMedium &m, const float *specPool, Pt3 o, Vec3 d, float tMax, float u, RNG &rng,
+                        const Wavelengths &wl, F callback) {
+    tMax *= Length(d);
+    d = Normalize(d);
+    MajorantIter iter = MediumSampleRay(m, specPool, o, d, tMax, wl);
+    Spec T_maj(1.f);
+    bool done = false;
+    while (!done) {
+        MajorantSegment seg;
+        if (!iter.Next(&seg)) return T_maj;
+        if (seg.sigma_maj[0] == 0) {
+            float dt = seg.tMax - seg.tMin;
+            if (IsInf_(dt)) dt = 3.402823466e+38f;
+            T_maj *= FastExpSpec(seg.sigma_maj * (-dt));
+            continue;
+        }
+        float tMin = seg.tMin;
+        while (true) {
+            float t = tMin + SampleExponential(u, seg.sigma_maj[0]);
+            u = rng.UniformFloat();
+            if (t < seg.tMax) {
+                T_maj *= FastExpSpec(seg.sigma_maj * (-(t - tMin)));
+                Pt3 p = o + d * t;
+                MediumProps mp = MediumSamplePoint(m, specPool, p, wl);
+                if (!callback(p, mp, seg.sigma_maj, T_maj)) { done = true; break; }
+                T_maj = Spec(1.f);
+                tMin = t;
+            } else {
+                float dt = seg.tMax - tMin;
+                if (IsInf_(dt)) dt = 3.402823466e+38f;
+                T_maj *= FastExpSpec(seg.sigma_maj * (-dt));
+                break;
+            }
+        }
+    }
+    return Spec(1.f);
+}
+
+}  // namespace bpt

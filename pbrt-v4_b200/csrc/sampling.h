@@ -95,6 +95,7 @@ struct RNG {
 // loaded from the data blob by the host and copied into constant memory / this host-side array).
 #if defined(__CUDACC__) && defined(BPT_SOBOL_DEVICE_TABLE)
 __constant__ uint32_t c_sobol32[2 * 52];   // defined by the one translation unit that samples on the device
+__device__ uint32_t g_sobolByteLUT[2 * 4 * 256];   // [dimension][byte position][byte value] partial products
 #endif
 extern uint32_t h_sobol32[2 * 52];
 BPT_HD const uint32_t *SobolTable() {
@@ -140,8 +141,19 @@ BPT_HD uint32_t OwenScramble(uint32_t v, uint32_t seed) {   // lowdiscrepancy.h 
 BPT_HD float SobolSampleRand(uint64_t a, int dimension, int randomize, uint32_t hash) {
     const uint32_t *C = SobolTable() + dimension * 52;
     uint32_t v = 0;
+#if defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
+    // the generator-matrix product is linear over GF(2): XOR of four per-byte partial products from a 4 KB table
+    // (same value as the bit loop below; the loop only runs for indices >= 2^32)
+    const uint32_t *T = g_sobolByteLUT + dimension * 1024;
+    uint32_t lo = (uint32_t)a;
+    v = __ldg(T + (lo & 255u)) ^ __ldg(T + 256 + ((lo >> 8) & 255u)) ^ __ldg(T + 512 + ((lo >> 16) & 255u)) ^ __ldg(T + 768 + (lo >> 24));
+    a >>= 32;
+    for (int i = 32; a != 0; a >>= 1, i++)
+        if (a & 1) v ^= C[i];
+#else
     for (int i = 0; a != 0; a >>= 1, i++)
         if (a & 1) v ^= C[i];
+#endif
     if (randomize == RANDOMIZE_PERMUTE_DIGITS) v = hash ^ v;
     else if (randomize == RANDOMIZE_FAST_OWEN) v = FastOwenScramble(v, hash);
     else if (randomize == RANDOMIZE_OWEN) v = OwenScramble(v, hash);
@@ -188,11 +200,9 @@ struct Sampler {
         }
     }
     BPT_HD uint64_t GetSampleIndex() const {
-        const uint8_t perm[24][4] = {
-            {0, 1, 2, 3}, {0, 1, 3, 2}, {0, 2, 1, 3}, {0, 2, 3, 1}, {0, 3, 2, 1}, {0, 3, 1, 2},
-            {1, 0, 2, 3}, {1, 0, 3, 2}, {1, 2, 0, 3}, {1, 2, 3, 0}, {1, 3, 2, 0}, {1, 3, 0, 2},
-            {2, 1, 0, 3}, {2, 1, 3, 0}, {2, 0, 1, 3}, {2, 0, 3, 1}, {2, 3, 0, 1}, {2, 3, 1, 0},
-            {3, 1, 2, 0}, {3, 1, 0, 2}, {3, 2, 1, 0}, {3, 2, 0, 1}, {3, 0, 2, 1}, {3, 0, 1, 2}};
+        // the 24 permutations of {0,1,2,3} (lowdiscrepancy.h:354-382), packed 2 bits per entry and keyed by the digit:
+        // kPerm[d] >> 2p & 3 == permutations[p][d]
+        const uint64_t kPerm0 = 0xfffaaa555000ull, kPerm1 = 0x0a5f05fa0fa5ull, kPerm2 = 0x6124dc2ce6deull, kPerm3 = 0x94817383b97bull;
         uint64_t sampleIndex = 0;
         bool pow2Samples = sp->log2SamplesPerPixel & 1;
         int lastDigit = pow2Samples ? 1 : 0;
@@ -200,9 +210,11 @@ struct Sampler {
             int digitShift = 2 * i - (pow2Samples ? 1 : 0);
             int digit = (int)((mortonIndex >> digitShift) & 3);
             uint64_t higherDigits = mortonIndex >> (digitShift + 2);
-            int p = (int)((MixBits(higherDigits ^ (uint64_t)(0x55555555u * (uint32_t)dimension)) >> 24) % 24);
-            // packed permutation lookup (table lives in registers/constant after unrolling)
-            digit = perm[p][digit];
+            uint64_t mix = MixBits(higherDigits ^ (uint64_t)(0x55555555u * (uint32_t)dimension)) >> 24;
+            // mix % 24 in 32-bit arithmetic: mix < 2^40, 2^32 % 24 == 16
+            uint32_t p = (((uint32_t)(mix >> 32) % 24u) * 16u + (uint32_t)mix % 24u) % 24u;
+            uint64_t pk = digit == 0 ? kPerm0 : digit == 1 ? kPerm1 : digit == 2 ? kPerm2 : kPerm3;
+            digit = (int)((pk >> (2 * p)) & 3);
             sampleIndex |= (uint64_t)digit << digitShift;
         }
         if (pow2Samples) {

@@ -125,4 +125,39 @@ struct IntegratorParams {
     int regularize;
 };
 
+// Transform::ApplyInverse(const Ray &, Float *tMax) (util/transform.h:416-429): dt is what the caller subtracts from tMax
+struct InstRay { Pt3 o; Vec3 d; float dt; };
+BPT_HD InstRay ApplyInverseRay(const Mat4 &Minv, Pt3 o, Vec3 d) {
+    const float (*m)[4] = Minv.m;
+    float x = o.x, y = o.y, z = o.z;
+    float xp = (m[0][0] * x + m[0][1] * y) + (m[0][2] * z + m[0][3]);
+    float yp = (m[1][0] * x + m[1][1] * y) + (m[1][2] * z + m[1][3]);
+    float zp = (m[2][0] * x + m[2][1] * y) + (m[2][2] * z + m[2][3]);
+    float wp = (m[3][0] * x + m[3][1] * y) + (m[3][2] * z + m[3][3]);
+    Vec3 e;   // exact input point: util/transform.cpp:263-276 (no |m[i][3]| term)
+    e.x = gamma_n(3) * (fabsf(m[0][0] * x) + fabsf(m[0][1] * y) + fabsf(m[0][2] * z));
+    e.y = gamma_n(3) * (fabsf(m[1][0] * x) + fabsf(m[1][1] * y) + fabsf(m[1][2] * z));
+    e.z = gamma_n(3) * (fabsf(m[2][0] * x) + fabsf(m[2][1] * y) + fabsf(m[2][2] * z));
+    Pt3i oi(Pt3(xp, yp, zp), e);
+    if (wp != 1) {
+        auto divI = [](Interval i, float f) { return f > 0 ? Interval(DivRoundDown(i.low, f), DivRoundUp(i.high, f))
+                                                          : Interval(DivRoundDown(i.high, f), DivRoundUp(i.low, f)); };
+        oi.x = divI(oi.x, wp); oi.y = divI(oi.y, wp); oi.z = divI(oi.z, wp);
+    }
+    Vec3 dn(m[0][0] * d.x + m[0][1] * d.y + m[0][2] * d.z, m[1][0] * d.x + m[1][1] * d.y + m[1][2] * d.z,
+            m[2][0] * d.x + m[2][1] * d.y + m[2][2] * d.z);
+    InstRay r; r.dt = 0;
+    float lengthSquared = LengthSquared(dn);
+    if (lengthSquared > 0) {
+        Vec3 oError(oi.x.Width() / 2, oi.y.Width() / 2, oi.z.Width() / 2);
+        float dt = Dot(Abs(dn), oError) / lengthSquared;
+        Vec3 off = dn * dt;
+        oi.x = oi.x + off.x; oi.y = oi.y + off.y; oi.z = oi.z + off.z;
+        r.dt = dt;
+    }
+    r.o = oi.p(); r.d = dn;
+    return r;
+}
+
+
 }  // namespace bpt

@@ -24,6 +24,15 @@ uint32_t h_sobol32[2 * 52];
 void UploadSobolTable(const uint32_t *t) {
     for (int i = 0; i < 104; ++i) h_sobol32[i] = t[i];
     cudaMemcpyToSymbol(c_sobol32, t, sizeof(uint32_t) * 104);
+    static uint32_t lut[2 * 4 * 256];
+    for (int d = 0; d < 2; ++d)
+        for (int b = 0; b < 4; ++b)
+            for (int x = 0; x < 256; ++x) {
+                uint32_t v = 0;
+                for (int i = 0; i < 8; ++i) if (x >> i & 1) v ^= t[d * 52 + b * 8 + i];
+                lut[(d * 4 + b) * 256 + x] = v;
+            }
+    cudaMemcpyToSymbol(g_sobolByteLUT, lut, sizeof(lut));
 }
 
 // ---------------------------------------------------------------- small helpers
@@ -103,7 +112,7 @@ __global__ void k_reset_counts(int *counts, int first, int n) {
 }
 __global__ void k_reset_depth(int *counts, int nextRayQ) {
     int i = threadIdx.x;
-    if (i == nextRayQ || i == Q_SHADOW || i == Q_ESCAPED || i == Q_HITLIGHT || (i >= Q_MAT0 && i < Q_NCOUNTERS)) counts[i] = 0;
+    if (i == nextRayQ || i == Q_SHADOW || i == Q_ESCAPED || i == Q_HITLIGHT || i == Q_MEDIUM || (i >= Q_MAT0 && i < Q_NCOUNTERS)) counts[i] = 0;
 }
 
 // ---------------------------------------------------------------- camera rays
@@ -156,6 +165,7 @@ __global__ void __launch_bounds__(256) k_generate_camera_rays(RenderCtx rc, int 
         ps.lambdaPdf[slot] = make_float4(wl.pdf[0], wl.pdf[1], wl.pdf[2], wl.pdf[3]);
         ps.misc[slot] = make_uint4((unsigned)px | ((unsigned)py << 16), (unsigned)sampleIndex, (unsigned)sampler.dimension, 0u);
         ps.aux[slot] = make_float2(1.f, fweight);
+        if (rc.nMedia > 0) ps.medium[slot] = rc.cameraMedium;   // CameraBase::medium (cameras.h)
         rc.queues[Q_RAY0][slot] = slot;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -165,8 +175,11 @@ __global__ void __launch_bounds__(256) k_generate_camera_rays(RenderCtx rc, int 
 }
 
 // ---------------------------------------------------------------- closest hit (persistent threads + dynamic fetch)
+#ifndef BPT_TRACE_CTAS
+#define BPT_TRACE_CTAS 8      // resident CTAs per SM the persistent traversal kernels are sized (and register-limited) for
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_closest(RenderCtx rc, int curQ) {
+__global__ void __launch_bounds__(128, BPT_TRACE_CTAS) k_trace_closest(RenderCtx rc, int curQ) {
     const int nRays = rc.counts[curQ];
     const int *queue = rc.queues[curQ];
     unsigned locNodes = 0, locTris = 0, locRays = 0;
@@ -178,6 +191,17 @@ __global__ void __launch_bounds__(128) k_trace_closest(RenderCtx rc, int curQ) {
     };
     auto commit = [&](int i, const HitRec &rec) {
         int slot = queue[i];
+        if (rc.nMedia > 0 && rc.ps.medium[slot] >= 0) {
+            // ray.medium set: the segment goes through SampleMediumInteraction first (EnqueueWorkAfterMiss/AfterIntersection,
+            // wavefront/intersect.h:16-29,48-70); the medium kernel forwards unscattered paths to the surface queues
+            int orig = -1;
+            if (rec.tri >= 0) orig = __float_as_int(__ldg(rc.bvh.tris + (size_t)rec.tri * 3).w);
+            rc.ps.hit[slot] = make_float4(__int_as_float(orig), rec.b0, rec.b1, rec.b2);
+            rc.ps.hitT[slot] = rec.tri >= 0 ? rec.t : BPT_INFINITY;
+            int p = WarpAggPush(&rc.counts[Q_MEDIUM]);
+            rc.queues[Q_MEDIUM][p] = slot;
+            return;
+        }
         if (rec.tri < 0) {
             if (rc.nInfinite > 0) { int p = WarpAggPush(&rc.counts[Q_ESCAPED]); rc.queues[Q_ESCAPED][p] = slot; }
         } else {
@@ -221,7 +245,7 @@ __global__ void __launch_bounds__(128) k_trace_closest(RenderCtx rc, int curQ) {
 
 // ---------------------------------------------------------------- shadow rays
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_shadow(RenderCtx rc) {
+__global__ void __launch_bounds__(128, BPT_TRACE_CTAS) k_trace_shadow(RenderCtx rc) {
     const int nRays = rc.counts[Q_SHADOW];
     unsigned locNodes = 0, locTris = 0, locRays = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&rc.stats[2], (unsigned long long)nRays);
@@ -319,6 +343,29 @@ __global__ void __launch_bounds__(128) k_handle_escaped(RenderCtx rc) {
     }
 }
 
+// Interaction::GetMedium(w) for a surface hit (interaction.h:117-121): the primitive's MediumInterface when it is a
+// transition, the ray's medium otherwise (SurfaceInteraction::SetIntersectionProperties, interaction.h:218-229)
+__device__ __forceinline__ int SurfaceGetMedium(const DeviceMesh &mesh, Vec3 w, Nrm3 n, int rayMedium) {
+    if (mesh.mediumInside != mesh.mediumOutside) return Dot(w, n) > 0 ? mesh.mediumOutside : mesh.mediumInside;
+    return rayMedium;
+}
+
+__device__ __forceinline__ void PushShadowTr(const RenderCtx &rc, int slot, Pt3 pf, Vec3 d, int medium, Spec bf, Spec Ls, Spec rl,
+                                             Spec ru, const Pt3i &pLight, Nrm3 nLight) {
+    int p = WarpAggPush(&rc.counts[Q_SHADOW]);
+    ShadowTrItem it;
+    it.o_slot = make_float4(pf.x, pf.y, pf.z, __int_as_float(slot));
+    it.d_med = make_float4(d.x, d.y, d.z, __int_as_float(medium));
+    it.bf = make_float4(bf[0], bf[1], bf[2], bf[3]);
+    it.Ls = make_float4(Ls[0], Ls[1], Ls[2], Ls[3]);
+    it.rl = make_float4(rl[0], rl[1], rl[2], rl[3]);
+    it.ru = make_float4(ru[0], ru[1], ru[2], ru[3]);
+    it.pl0 = make_float4(pLight.x.low, pLight.x.high, pLight.y.low, pLight.y.high);
+    it.pl1 = make_float4(pLight.z.low, pLight.z.high, nLight.x, nLight.y);
+    it.pl2 = make_float4(nLight.z, 0.f, 0.f, 0.f);
+    rc.shadowTr[p] = it;
+}
+
 // ---------------------------------------------------------------- surface scattering, one instantiation per material
 template <typename Material>
 __global__ void __launch_bounds__(128) k_shade(RenderCtx rc, int nextQ) {
@@ -345,10 +392,12 @@ __global__ void __launch_bounds__(128) k_shade(RenderCtx rc, int nextQ) {
         bool anyNonSpecularBounces = (misc.w >> 9) & 1;
         int px = misc.x & 0xffff, py = misc.x >> 16;
 
+        const int rayMedium = rc.nMedia > 0 ? ps.medium[slot] : -1;
         if (Material::kTag == MAT_INTERFACE) {
             // isect.SkipIntersection(&ray, tHit): respawn the ray past the surface, same depth (interaction.h)
             Pt3 o = OffsetRayOrigin(isect.pi, isect.n, -wo);
             ps.rayO[slot] = make_float4(o.x, o.y, o.z, 0.f);
+            if (rc.nMedia > 0) ps.medium[slot] = SurfaceGetMedium(mesh, -wo, isect.n, rayMedium);
             int p = WarpAggPush(&rc.counts[nextQ]);
             rc.queues[nextQ][p] = slot;
             continue;
@@ -401,7 +450,11 @@ __global__ void __launch_bounds__(128) k_shade(RenderCtx rc, int nextQ) {
                             pt = ls.pLight.p();
                         }
                         Vec3 rdv = pt - pf;
-                        if (rdv != Vec3(0, 0, 0)) {
+                        if (rc.useTr) {
+                            Nrm3 nL = light.type == LIGHT_DIFFUSE_AREA ? ls.nLight : Nrm3(0, 0, 0);
+                            PushShadowTr(rc, slot, pf, rdv, SurfaceGetMedium(mesh, rdv, isect.n, rayMedium), beta * f_hat, ls.L,
+                                         r_u * p_l, r_u * scatterPDF, ls.pLight, nL);
+                        } else if (rdv != Vec3(0, 0, 0)) {
                             Spec r_l = r_u * p_l;
                             Spec r_uu = r_u * scatterPDF;
                             Spec Ld = beta * f_hat * ls.L / (r_l + r_uu).Average();
@@ -455,6 +508,7 @@ __global__ void __launch_bounds__(128) k_shade(RenderCtx rc, int nextQ) {
         }
         ps.rayO[slot] = make_float4(o.x, o.y, o.z, 0.f);
         ps.rayD[slot] = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, d4.w);
+        if (rc.nMedia > 0) ps.medium[slot] = SurfaceGetMedium(mesh, bs.wi, isect.n, rayMedium);   // SpawnRay: GetMedium(wi)
         st4(&ps.beta[slot], beta);
         st4(&ps.r_l[slot], r_l);
         ps.aux[slot] = make_float2(etaScale, aux.y);
@@ -462,6 +516,210 @@ __global__ void __launch_bounds__(128) k_shade(RenderCtx rc, int nextQ) {
                                    (unsigned)depth | (specularBounce ? 0x100u : 0u) | (anyNonSpecularBounces ? 0x200u : 0u));
         int p = WarpAggPush(&rc.counts[nextQ]);
         rc.queues[nextQ][p] = slot;
+    }
+}
+
+// ---------------------------------------------------------------- participating media
+// VolPathIntegrator::Li, "Sample the participating medium" (cpu/integrators.cpp:970-1078) == wavefront SampleMediumInteraction +
+// SampleMediumScattering (wavefront/media.cpp:22-352) with VolPath's sampler consumption (3 x Get1D, then SampleLd's 1D + 2D and the
+// phase function's 2D at a real scattering event).
+__global__ void __launch_bounds__(128) k_sample_medium(RenderCtx rc, int nextQ) {
+    const int n = rc.counts[Q_MEDIUM];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int slot = rc.queues[Q_MEDIUM][i];
+        const PathState &ps = rc.ps;
+        float4 o4 = ps.rayO[slot], d4 = ps.rayD[slot];
+        Pt3 ro(o4.x, o4.y, o4.z); Vec3 rd(d4.x, d4.y, d4.z);
+        const int mediumId = ps.medium[slot];
+        const DeviceMedium &med = rc.media[mediumId];
+        float4 h = ps.hit[slot];
+        int tri = __float_as_int(h.x);
+        float tMax = ps.hitT[slot];
+        Wavelengths wl = LoadLambda(ps, slot);
+        uint4 misc = ps.misc[slot];
+        int depth = misc.w & 0xff;
+        bool specularBounce = (misc.w >> 8) & 1;
+        bool anyNonSpecularBounces = (misc.w >> 9) & 1;
+        int px = misc.x & 0xffff, py = misc.x >> 16;
+        Sampler sampler;
+        sampler.StartPixelSample(&rc.sampler, px, py, (int)misc.y, (int)misc.z);
+        Spec beta = ld4(&ps.beta[slot]), r_u = ld4(&ps.r_u[slot]), r_l = ld4(&ps.r_l[slot]);
+        bool scattered = false, terminated = false;
+        uint64_t hash0 = Hash_f32(sampler.Get1D());
+        uint64_t hash1 = Hash_f32(sampler.Get1D());
+        RNG rng(hash0, hash1);
+        float uT = sampler.Get1D();
+        Pt3 newO = ro; Vec3 newD = rd;
+        const int maxDepth = rc.integ.maxDepth;
+        Spec T_maj = SampleT_maj(med, rc.sv.specPool, ro, rd, tMax, uT, rng, wl,
+            [&](Pt3 p, const MediumProps &mp, Spec sigma_maj, Spec T_maj) -> bool {
+                if (!beta.IsNonZero()) { terminated = true; return false; }
+                // (no emission: media with Le are rejected at scene intake)
+                float pAbsorb = mp.sigma_a[0] / sigma_maj[0];
+                float pScatter = mp.sigma_s[0] / sigma_maj[0];
+                float pNull = stdmax(0.f, 1 - pAbsorb - pScatter);
+                float um = rng.UniformFloat();
+                int mode = SampleDiscrete3(pAbsorb, pScatter, pNull, um);
+                if (mode == 0) { terminated = true; return false; }
+                if (mode == 1) {
+                    if (depth++ >= maxDepth) { terminated = true; return false; }
+                    float pdf = T_maj[0] * mp.sigma_s[0];
+                    beta *= T_maj * mp.sigma_s / pdf;
+                    r_u *= T_maj * mp.sigma_s / pdf;
+                    if (beta.IsNonZero() && r_u.IsNonZero()) {
+                        // SampleLd(intr, nullptr, ...) at a MediumInteraction(p, -ray.d): LightSampleContext(intr) has n = ns = 0
+                        Vec3 wo = -rd;
+                        LightSampleContext ctx;
+                        ctx.pi = Pt3i(p); ctx.n = Nrm3(0, 0, 0); ctx.ns = Nrm3(0, 0, 0);
+                        float u = sampler.Get1D();
+                        float lightPMF = 0;
+                        int lightIndex = LightSamplerSample(rc.sv, ctx, u, &lightPMF);
+                        Vec2 uLight = sampler.Get2D();
+                        if (lightIndex >= 0) {
+                            const DeviceLight &light = rc.sv.lights[lightIndex];
+                            LightLiSample ls;
+                            if (light.type == LIGHT_DIFFUSE_AREA) ls = AreaLightSampleLi(rc.sv, light, ctx, uLight, wl);
+                            else ls = InfiniteLightSampleLi(rc.sv, light, ctx, uLight, wl);
+                            if (ls.valid && ls.L.IsNonZero() && ls.pdf != 0) {
+                                float p_l = lightPMF * ls.pdf;
+                                float ph = PhaseHG_p(med.g, wo, ls.wi);
+                                Spec f_hat(ph);
+                                float scatterPDF = ph;
+                                if (f_hat.IsNonZero()) {
+                                    Nrm3 nL = light.type == LIGHT_DIFFUSE_AREA ? ls.nLight : Nrm3(0, 0, 0);
+                                    Pt3 pf = OffsetRayOrigin(ctx.pi, ctx.n, ls.pLight.p() - ctx.pi.p());
+                                    Pt3 pt = OffsetRayOrigin(ls.pLight, nL, pf - ls.pLight.p());
+                                    PushShadowTr(rc, slot, pf, pt - pf, mediumId, beta * f_hat, ls.L, r_u * p_l, r_u * scatterPDF,
+                                                 ls.pLight, nL);
+                                }
+                            }
+                        }
+                        // Sample new direction at real-scattering event
+                        Vec2 u2 = sampler.Get2D();
+                        float ppdf;
+                        Vec3 wi = SampleHenyeyGreenstein(wo, med.g, u2, &ppdf);
+                        if (ppdf == 0) terminated = true;
+                        else {
+                            // beta *= ps->p / ps->pdf with p == pdf
+                            beta *= ppdf / ppdf;
+                            r_l = r_u / ppdf;
+                            StoreCtx(ps, slot, ctx.pi, ctx.n, ctx.ns);
+                            scattered = true;
+                            newO = p; newD = wi;
+                            specularBounce = false;
+                            anyNonSpecularBounces = true;
+                        }
+                    }
+                    return false;
+                }
+                // null scattering
+                Spec sigma_n = ClampZero(sigma_maj - mp.sigma_a - mp.sigma_s);
+                float pdf = T_maj[0] * sigma_n[0];
+                beta *= T_maj * sigma_n / pdf;
+                if (pdf == 0) beta = Spec(0.f);
+                r_u *= T_maj * sigma_n / pdf;
+                r_l *= T_maj * sigma_maj / pdf;
+                return beta.IsNonZero() && r_u.IsNonZero();
+            });
+        if (terminated || !beta.IsNonZero() || !r_u.IsNonZero()) continue;
+        unsigned flagsW = (unsigned)depth | (specularBounce ? 0x100u : 0u) | (anyNonSpecularBounces ? 0x200u : 0u);
+        if (scattered) {
+            ps.rayO[slot] = make_float4(newO.x, newO.y, newO.z, 0.f);
+            ps.rayD[slot] = make_float4(newD.x, newD.y, newD.z, d4.w);
+            st4(&ps.beta[slot], beta); st4(&ps.r_u[slot], r_u); st4(&ps.r_l[slot], r_l);
+            ps.misc[slot] = make_uint4(misc.x, misc.y, (unsigned)sampler.dimension, flagsW);
+            int p = WarpAggPush(&rc.counts[nextQ]);
+            rc.queues[nextQ][p] = slot;
+            continue;
+        }
+        beta *= T_maj / T_maj[0];
+        r_u *= T_maj / T_maj[0];
+        r_l *= T_maj / T_maj[0];
+        st4(&ps.beta[slot], beta); st4(&ps.r_u[slot], r_u); st4(&ps.r_l[slot], r_l);
+        ps.misc[slot] = make_uint4(misc.x, misc.y, (unsigned)sampler.dimension, flagsW);
+        // surviving unscattered ray: hand over to the surface queues (what the closest-hit commit does for vacuum rays)
+        if (tri < 0) {
+            if (rc.nInfinite > 0) { int p = WarpAggPush(&rc.counts[Q_ESCAPED]); rc.queues[Q_ESCAPED][p] = slot; }
+        } else {
+            unsigned cls = __float_as_uint(__ldg(rc.sv.triPool + (size_t)tri * 3 + 2).w);
+            if (cls & 0x100u) { int p = WarpAggPush(&rc.counts[Q_HITLIGHT]); rc.queues[Q_HITLIGHT][p] = slot; }
+            unsigned mt = cls & 0xffu;
+            int p = WarpAggPush(&rc.counts[Q_MAT0 + mt]);
+            rc.queues[Q_MAT0 + mt][p] = slot;
+        }
+    }
+}
+
+// Shadow rays through media / interface surfaces: the loop of VolPathIntegrator::SampleLd (cpu/integrators.cpp:1331-1389), i.e.
+// the wavefront TraceTransmittance (wavefront/intersect.h:164-274): closest hit, stop at the first surface with a material,
+// ratio-track the transmittance through the current medium, continue behind interface surfaces.
+__global__ void __launch_bounds__(128) k_trace_shadow_tr(RenderCtx rc) {
+    const int n = rc.counts[Q_SHADOW];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&rc.stats[2], (unsigned long long)n);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const ShadowTrItem &it = rc.shadowTr[i];
+        float4 a = it.o_slot, b = it.d_med;
+        int slot = __float_as_int(a.w);
+        Pt3 o(a.x, a.y, a.z); Vec3 d(b.x, b.y, b.z);
+        int medium = __float_as_int(b.w);
+        float4 q0 = it.pl0, q1 = it.pl1, q2 = it.pl2;
+        Pt3i pLight; pLight.x = Interval(q0.x, q0.y); pLight.y = Interval(q0.z, q0.w); pLight.z = Interval(q1.x, q1.y);
+        Nrm3 nLight(q1.z, q1.w, q2.x);
+        Wavelengths wl = LoadLambda(rc.ps, slot);
+        Spec T_ray(1.f), r_l(1.f), r_u(1.f);
+        RNG rng(Hash_f32x3(o.x, o.y, o.z), Hash_f32x3(d.x, d.y, d.z));
+        bool blocked = false;
+        while (d != Vec3(0, 0, 0)) {
+            HitRec rec;
+            unsigned nn = 0, nt = 0;
+            TraceRay<false, false>(rc.bvh, o, d, 1 - kShadowEpsilon, &rec, &nn, &nt);
+            int tri = -1; unsigned cls = 0;
+            if (rec.tri >= 0) {
+                const float4 *tp = rc.bvh.tris + (size_t)rec.tri * 3;
+                tri = __float_as_int(__ldg(tp).w);
+                cls = __float_as_uint(__ldg(tp + 1).w);
+                if ((cls & 0xffu) != MAT_INTERFACE) { blocked = true; break; }
+            }
+            if (medium >= 0) {
+                float tMax = rec.tri >= 0 ? rec.t : (1 - kShadowEpsilon);
+                float u = rng.UniformFloat();
+                Spec T_maj = SampleT_maj(rc.media[medium], rc.sv.specPool, o, d, tMax, u, rng, wl,
+                    [&](Pt3 p, const MediumProps &mp, Spec sigma_maj, Spec T_maj) -> bool {
+                        Spec sigma_n = ClampZero(sigma_maj - mp.sigma_a - mp.sigma_s);
+                        float pdf = T_maj[0] * sigma_maj[0];
+                        T_ray *= T_maj * sigma_n / pdf;
+                        r_l *= T_maj * sigma_maj / pdf;
+                        r_u *= T_maj * sigma_n / pdf;
+                        Spec Tr = T_ray / (r_l + r_u).Average();
+                        if (Tr.MaxComponentValue() < 0.05f) {
+                            float q = 0.75f;
+                            if (rng.UniformFloat() < q) T_ray = Spec(0.f);
+                            else T_ray /= 1 - q;
+                        }
+                        return T_ray.IsNonZero();
+                    });
+                T_ray *= T_maj / T_maj[0];
+                r_l *= T_maj / T_maj[0];
+                r_u *= T_maj / T_maj[0];
+            }
+            if (!T_ray.IsNonZero()) { blocked = true; break; }
+            if (rec.tri < 0) break;
+            // lightRay = si->intr.SpawnRayTo(ls->pLight)
+            TriData td = LoadTriangle(rc.sv, tri);
+            TriHit th{rec.b0, rec.b1, rec.b2, rec.t};
+            SurfaceIntr isect = TriangleInteraction(td.p0, td.p1, td.p2, td.a, th);
+            Pt3 pf = OffsetRayOrigin(isect.pi, isect.n, pLight.p() - isect.pi.p());
+            Pt3 pt = OffsetRayOrigin(pLight, nLight, pf - pLight.p());
+            o = pf; d = pt - pf;
+            medium = SurfaceGetMedium(rc.sv.meshes[td.mesh], d, isect.n, medium);
+        }
+        if (blocked) continue;
+        r_l *= ld4(&it.rl);
+        r_u *= ld4(&it.ru);
+        Spec Ld = ld4(&it.bf) * T_ray * ld4(&it.Ls) / (r_l + r_u).Average();
+        float4 L = rc.ps.L[slot];
+        L.x += Ld[0]; L.y += Ld[1]; L.z += Ld[2]; L.w += Ld[3];
+        rc.ps.L[slot] = L;
     }
 }
 
@@ -611,18 +869,20 @@ void LaunchProbeMath(int fn, const float *x, const float *y, int n, float *out, 
 // ================================================================= host-side launchers
 static inline int GridFor(int smCount, int perSM) { return smCount * perSM; }
 
+void LaunchSampleMedium(const RenderCtx &rc, int nextQ, int sms, cudaStream_t st) { k_sample_medium<<<GridFor(sms, 8), 128, 0, st>>>(rc, nextQ); }
+void LaunchTraceShadowTr(const RenderCtx &rc, int sms, cudaStream_t st) { k_trace_shadow_tr<<<GridFor(sms, 8), 128, 0, st>>>(rc); }
 void LaunchResetAll(const RenderCtx &rc, cudaStream_t st) { k_reset_counts<<<1, 64, 0, st>>>(rc.counts, 0, Q_NCOUNTERS); }
 void LaunchResetDepth(const RenderCtx &rc, int nextQ, cudaStream_t st) { k_reset_depth<<<1, 64, 0, st>>>(rc.counts, nextQ); }
 void LaunchGenerateCameraRays(const RenderCtx &rc, int x0, int x1, int y0, int y1, int firstSample, int nSamples, int sms, cudaStream_t st) {
     k_generate_camera_rays<<<GridFor(sms, 8), 256, 0, st>>>(rc, x0, x1, y0, y1, firstSample, nSamples);
 }
 void LaunchTraceClosest(const RenderCtx &rc, int curQ, bool count, int sms, cudaStream_t st) {
-    if (count) k_trace_closest<true><<<GridFor(sms, 8), 128, 0, st>>>(rc, curQ);
-    else k_trace_closest<false><<<GridFor(sms, 8), 128, 0, st>>>(rc, curQ);
+    if (count) k_trace_closest<true><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc, curQ);
+    else k_trace_closest<false><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc, curQ);
 }
 void LaunchTraceShadow(const RenderCtx &rc, bool count, int sms, cudaStream_t st) {
-    if (count) k_trace_shadow<true><<<GridFor(sms, 8), 128, 0, st>>>(rc);
-    else k_trace_shadow<false><<<GridFor(sms, 8), 128, 0, st>>>(rc);
+    if (count) k_trace_shadow<true><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc);
+    else k_trace_shadow<false><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc);
 }
 void LaunchHandleEmissive(const RenderCtx &rc, int sms, cudaStream_t st) { k_handle_emissive<<<GridFor(sms, 4), 128, 0, st>>>(rc); }
 void LaunchHandleEscaped(const RenderCtx &rc, int sms, cudaStream_t st) { k_handle_escaped<<<GridFor(sms, 4), 128, 0, st>>>(rc); }

@@ -10,11 +10,13 @@
 #include "scene.h"
 #include "lights.h"
 #include "bvh.cuh"
+#include "media.h"
 
 namespace bpt {
 
 // queue ids inside RenderCtx::counts
-enum { Q_RAY0 = 0, Q_RAY1 = 1, Q_SHADOW = 2, Q_ESCAPED = 3, Q_HITLIGHT = 4, Q_MAT0 = 5 /* + MaterialTag */,
+enum { Q_RAY0 = 0, Q_RAY1 = 1, Q_SHADOW = 2, Q_ESCAPED = 3, Q_HITLIGHT = 4, Q_MEDIUM = 5 /* MediumSampleQueue */,
+       Q_MAT0 = 6 /* + MaterialTag */,
        Q_CURSOR_CLOSEST = Q_MAT0 + MAT_NTAGS, Q_CURSOR_SHADOW, Q_NCOUNTERS };
 
 struct PathState {
@@ -22,6 +24,8 @@ struct PathState {
     float4 *rayD;        // d.xyz, time
     float4 *hit;         // original triangle id (int bits), b0, b1, b2
     int *hitInst;        // instance id of the hit (two-level scenes only)
+    float *hitT;         // tHit of the closest hit (scenes with media only; +inf on a miss)
+    int *medium;         // Ray::medium of the current segment, -1 = vacuum (scenes with media only)
     float4 *beta, *r_u, *r_l, *L;
     float4 *lambda, *lambdaPdf;
     float4 *ctx0;        // prevIntrCtx: pi.x.low, pi.x.high, pi.y.low, pi.y.high
@@ -32,11 +36,28 @@ struct PathState {
 };
 
 struct ShadowItem { float4 o_slot; float4 d; float4 Ld; };   // o.xyz + slot bits ; d.xyz + tMax ; Ld
+// Shadow ray of a scene with media or "interface" surfaces (VolPathIntegrator::SampleLd's transmittance loop,
+// cpu/integrators.cpp:1331-1389 / wavefront TraceTransmittance): the ray may cross several interface surfaces, so the item
+// carries the light-side end point (interval + normal) for SpawnRayTo and the factors of the final estimator separately.
+struct ShadowTrItem {
+    float4 o_slot;     // o.xyz, slot
+    float4 d_med;      // d.xyz, medium id (int bits)
+    float4 bf;         // beta * f_hat
+    float4 Ls;         // ls->L
+    float4 rl, ru;     // r_p * p_l, r_p * scatterPDF
+    float4 pl0, pl1;   // pLight: x.low x.high y.low y.high | z.low z.high n.x n.y
+    float4 pl2;        // n.z, -, -, -
+};
 
 struct RenderCtx {
     PathState ps;
     int *queues[Q_CURSOR_CLOSEST];     // item arrays for Q_RAY0.. (Q_SHADOW unused: shadow items below)
     ShadowItem *shadowItems;
+    ShadowTrItem *shadowTr;            // used instead of shadowItems when useTr
+    const DeviceMedium *media;
+    int nMedia;
+    int cameraMedium;
+    int useTr;                         // scene has media or interface surfaces: shadow rays run the transmittance loop
     int *counts;                       // Q_NCOUNTERS ints
     unsigned long long *stats;         // [0] camera rays [1] indirect rays [2] shadow rays [3] nodes [4] tris [5] counted rays
     BVHView bvh;

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200pt.so")
+LIB_PATH = os.environ.get("BPT_LIB") or os.path.join(_HERE, "libb200pt.so")   # BPT_LIB: tuning-variant builds (scripts/sweep.py)
 _lib = None
 
 

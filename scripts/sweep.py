@@ -1,0 +1,20 @@
+"""Times every library variant in pbrt-v4_b200/variants/ on the bench scene (one subprocess per variant)."""
+import glob, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHILD = r'''
+import os, sys, json
+sys.path.insert(0, %r)
+import bench
+from pbrt_v4_b200 import engine as E
+path = bench.make_scene(os.environ.get("BPT_WORKLOAD", "heightfield1m"), spp=256)
+e = E.Engine(0); e.load_pbrt(path, seed=0)
+spp = int(os.environ.get("SPP", "32"))
+e.render(0, spp)
+e.stats_reset(); e.render(0, spp, profile=True)
+s = e.stats()
+print(json.dumps({k: s[k] for k in ("seconds_render", "ms_trace_closest", "ms_trace_shadow", "ms_shade", "ms_other")}))
+''' % ROOT
+for so in sorted(glob.glob(os.path.join(ROOT, "pbrt-v4_b200", "libb200pt_*.so"))):
+    env = dict(os.environ, BPT_LIB=so)
+    r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
+    print(os.path.basename(so), r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:], flush=True)
