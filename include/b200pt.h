@@ -132,9 +132,13 @@ typedef struct {
     int image_res;
 } bpt_light;
 
+enum { BPT_MEDIUM_UNIFORMGRID = 0, BPT_MEDIUM_HOMOGENEOUS = 1 };
+/* Medium (media.h:217-352: HomogeneousMedium, GridMedium; created in media.cpp:165-201,249-330).  Emission is not supported:
+ * Le must be BPT_SPEC_NONE. */
 typedef struct {
-    int type;                     /* 0 = uniform grid ("uniformgrid") */
-    bpt_mat4 world_from_medium;
+    int type;                     /* BPT_MEDIUM_* */
+    bpt_mat4 world_from_medium;   /* CTM at MakeNamedMedium */
+    bpt_mat4 medium_from_world;   /* its tracked inverse; all zeros => computed numerically */
     bpt_spectrum sigma_a, sigma_s;
     float scale, g;
     float bounds[6];              /* p0, p1 */

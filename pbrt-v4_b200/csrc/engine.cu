@@ -49,6 +49,7 @@ struct OwnedLight {
     std::vector<float> image;
 };
 struct OwnedAreaLight { bpt_area_light a; OwnedSpectrum L; };
+struct OwnedMedium { bpt_medium m; OwnedSpectrum sigma_a, sigma_s; std::vector<float> density; };
 
 template <typename T>
 struct DevBuf {
@@ -88,6 +89,7 @@ struct bpt_engine {
     std::vector<OwnedMesh> meshes;
     std::vector<bpt_instance> instances;
     std::vector<OwnedLight> lights;
+    std::vector<OwnedMedium> media;
     int cameraMedium = -1;
     // device
     DevBuf<float4> triPool;
@@ -115,6 +117,12 @@ struct bpt_engine {
     DevBuf<DeviceInstance> dInstances;
     DevBuf<float4> dTlasPrims;
     DevBuf<int> hitInst;
+    DevBuf<float> hitT;
+    DevBuf<int> pathMedium;
+    DevBuf<ShadowTrItem> shadowTr;
+    DevBuf<DeviceMedium> dMedia;
+    std::vector<std::unique_ptr<DevBuf<float>>> mediumBufs;
+    bool haveInterface = false;
     std::vector<WideBVH> blas;
     DevBuf<float> dRgb2spec;
     std::vector<std::unique_ptr<DevBuf<float>>> imgBufs;
@@ -322,7 +330,7 @@ extern "C" const char *bpt_last_error(const bpt_engine *e) { return e ? e->err.c
 // ------------------------------------------------------------------------------------------- scene intake
 extern "C" int bpt_scene_begin(bpt_engine *e) {
     if (!e) return BPT_ERR_INVALID;
-    e->materials.clear(); e->areaLights.clear(); e->meshes.clear(); e->instances.clear(); e->lights.clear();
+    e->materials.clear(); e->areaLights.clear(); e->meshes.clear(); e->instances.clear(); e->lights.clear(); e->media.clear();
     e->haveCam = e->haveFilm = false; e->committed = false; e->cameraMedium = -1;
     return BPT_OK;
 }
@@ -400,7 +408,18 @@ extern "C" int bpt_scene_add_light(bpt_engine *e, const bpt_light *l) {
     o.l.image_rgb = nullptr;
     return BPT_OK;
 }
-extern "C" int bpt_scene_add_medium(bpt_engine *e, const bpt_medium *) { return e ? e->fail(BPT_ERR_UNSUPPORTED, "media are not implemented yet") : BPT_ERR_INVALID; }
+extern "C" int bpt_scene_add_medium(bpt_engine *e, const bpt_medium *m) {
+    if (!e || !m) return BPT_ERR_INVALID;
+    if (m->type != BPT_MEDIUM_UNIFORMGRID && m->type != BPT_MEDIUM_HOMOGENEOUS) return e->fail(BPT_ERR_UNSUPPORTED, "medium type not implemented (homogeneous, uniformgrid)");
+    if (m->Le.kind != BPT_SPEC_NONE) return e->fail(BPT_ERR_UNSUPPORTED, "emissive media are not implemented");
+    if (m->type == BPT_MEDIUM_UNIFORMGRID && (!m->density || m->nx <= 0 || m->ny <= 0 || m->nz <= 0)) return e->fail(BPT_ERR_INVALID, "uniformgrid medium needs a density grid");
+    e->media.emplace_back();
+    OwnedMedium &o = e->media.back();
+    o.m = *m; o.sigma_a.Set(m->sigma_a); o.sigma_s.Set(m->sigma_s);
+    if (m->type == BPT_MEDIUM_UNIFORMGRID) o.density.assign(m->density, m->density + (size_t)m->nx * m->ny * m->nz);
+    o.m.density = nullptr;
+    return BPT_OK;
+}
 extern "C" int bpt_scene_set_camera_medium(bpt_engine *e, int medium) { if (!e) return BPT_ERR_INVALID; e->cameraMedium = medium; return BPT_OK; }
 
 // ------------------------------------------------------------------------------------------- commit
@@ -779,6 +798,74 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     dls.nInfinite = (int)lb.infiniteLights.size();
     dls.nNodes = (int)lb.nodes.size();
 
+    // ---- media (HomogeneousMedium / GridMedium constructors, media.h:222-232, media.cpp:212-247)
+    std::vector<DeviceMedium> dmedia(e->media.size());
+    e->mediumBufs.clear();
+    for (size_t i = 0; i < e->media.size(); ++i) {
+        const OwnedMedium &om = e->media[i];
+        DeviceMedium &dm = dmedia[i];
+        std::memset(&dm, 0, sizeof(dm));
+        dm.type = om.m.type == BPT_MEDIUM_HOMOGENEOUS ? MEDIUM_HOMOGENEOUS : MEDIUM_GRID;
+        dm.g = om.m.g;
+        for (int k = 0; k < 2; ++k) {
+            // DenselySampledSpectrum(spec) at integer wavelengths, then Scale(sigmaScale)
+            const OwnedSpectrum &os = k == 0 ? om.sigma_a : om.sigma_s;
+            std::vector<float> v(kNLambda, 1.f);   // no parameter: ConstantSpectrum(1)
+            if (os.s.kind != BPT_SPEC_NONE) {
+                SpectrumRec r; std::string serr;
+                if (!MakeSpectrumRec(e, os, ST_UNBOUNDED, spool, &r, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, "medium spectrum: " + serr);
+                for (int l = 0; l < kNLambda; ++l) v[l] = EvalRecAt(r, spool.pool, (float)(kLambdaMin + l));
+            }
+            for (float &x : v) x *= om.m.scale;
+            (k == 0 ? dm.sigmaA : dm.sigmaS) = spool.addDense(v);
+        }
+        if (dm.type == MEDIUM_GRID) {
+            M4 wfm = ToM4(om.m.world_from_medium), mfw = ToM4(om.m.medium_from_world);
+            bool haveInv = false;
+            for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) if (mfw[a][b] != 0) haveInv = true;
+            Xform worldFromMedium = haveInv ? Xform(wfm, mfw) : Xform(wfm);
+            Xform renderFromMedium = renderFromWorld * worldFromMedium;   // RenderFromObject() (scene.h:475-477)
+            dm.mInv = ToMat4(renderFromMedium.mInv);
+            for (int k = 0; k < 3; ++k) { dm.bmin[k] = om.m.bounds[k]; dm.bmax[k] = om.m.bounds[3 + k]; }
+            const int nx = om.m.nx, ny = om.m.ny, nz = om.m.nz;
+            dm.nx = nx; dm.ny = ny; dm.nz = nz;
+            const int R = 16;
+            dm.mres[0] = dm.mres[1] = dm.mres[2] = R;
+            // majorantGrid.Set(x, y, z, densityGrid.MaxValue(majorantGrid.VoxelBounds(x, y, z)))  (util/containers.h:837-858)
+            std::vector<float> maj((size_t)R * R * R);
+            auto look = [&](int x, int y, int z) -> float {
+                if (x < 0 || y < 0 || z < 0 || x >= nx || y >= ny || z >= nz) return 0.f;
+                return om.density[((size_t)z * ny + y) * nx + x];
+            };
+            for (int z = 0; z < R; ++z) for (int y = 0; y < R; ++y) for (int x = 0; x < R; ++x) {
+                float p0[3] = {float(x) / R, float(y) / R, float(z) / R}, p1[3] = {float(x + 1) / R, float(y + 1) / R, float(z + 1) / R};
+                int n3[3] = {nx, ny, nz}, lo[3], hi[3];
+                for (int k = 0; k < 3; ++k) {
+                    float a = p0[k] * n3[k] - .5f, b = p1[k] * n3[k] - .5f;
+                    lo[k] = std::max((int)std::floor(a), 0);
+                    hi[k] = std::min((int)std::floor(b) + 1, n3[k] - 1);
+                }
+                float mv = look(lo[0], lo[1], lo[2]);
+                for (int zz = lo[2]; zz <= hi[2]; ++zz) for (int yy = lo[1]; yy <= hi[1]; ++yy) for (int xx = lo[0]; xx <= hi[0]; ++xx)
+                    mv = std::max(mv, look(xx, yy, zz));
+                maj[(size_t)x + R * ((size_t)y + R * (size_t)z)] = mv;
+            }
+            e->mediumBufs.emplace_back(new DevBuf<float>());
+            ECK(e->mediumBufs.back()->upload(om.density));
+            dm.density = e->mediumBufs.back()->p;
+            e->mediumBufs.emplace_back(new DevBuf<float>());
+            ECK(e->mediumBufs.back()->upload(maj));
+            dm.majorant = e->mediumBufs.back()->p;
+        }
+    }
+    ECK(e->dMedia.upload(dmedia));
+    e->haveInterface = e->materialPresent[MAT_INTERFACE];
+    for (const OwnedMesh &om : e->meshes)
+        if (om.m.medium_inside >= (int)e->media.size() || om.m.medium_outside >= (int)e->media.size()) return e->fail(BPT_ERR_INVALID, "mesh medium index out of range");
+    if (e->cameraMedium >= (int)e->media.size()) return e->fail(BPT_ERR_INVALID, "camera medium index out of range");
+    if ((e->haveInterface || !e->media.empty()) && !e->instances.empty())
+        return e->fail(BPT_ERR_UNSUPPORTED, "media / interface surfaces are not supported together with object instancing");
+
     // ---- upload
     ECK(e->triPool.upload(tri));
     ECK(e->dMeshes.upload(dmesh));
@@ -929,13 +1016,23 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     int nQueues = 0;
     int qIndex[Q_CURSOR_CLOSEST];
     for (int q = 0; q < Q_CURSOR_CLOSEST; ++q) {
-        bool need = q == Q_RAY0 || q == Q_RAY1 || q == Q_ESCAPED || q == Q_HITLIGHT || (q >= Q_MAT0 && e->materialPresent[q - Q_MAT0]);
+        bool need = q == Q_RAY0 || q == Q_RAY1 || q == Q_ESCAPED || q == Q_HITLIGHT || (q == Q_MEDIUM && !e->media.empty()) ||
+                    (q >= Q_MAT0 && e->materialPresent[q - Q_MAT0]);
         qIndex[q] = need ? nQueues++ : -1;
     }
     ECK(e->queueMem.alloc((size_t)nQueues * maxPaths));
     for (int q = 0; q < Q_CURSOR_CLOSEST; ++q) rc.queues[q] = qIndex[q] >= 0 ? e->queueMem.p + (size_t)qIndex[q] * maxPaths : nullptr;
-    ECK(e->shadowItems.alloc(maxPaths));
+    rc.nMedia = (int)e->media.size();
+    rc.media = e->dMedia.p;
+    rc.cameraMedium = e->cameraMedium;
+    rc.useTr = (rc.nMedia > 0 || e->haveInterface) ? 1 : 0;
+    ECK(e->shadowItems.alloc(rc.useTr ? 1 : maxPaths));
+    ECK(e->shadowTr.alloc(rc.useTr ? maxPaths : 1));
     rc.shadowItems = e->shadowItems.p;
+    rc.shadowTr = e->shadowTr.p;
+    ECK(e->hitT.alloc(rc.nMedia > 0 ? maxPaths : 1));
+    ECK(e->pathMedium.alloc(rc.nMedia > 0 ? maxPaths : 1));
+    rc.ps.hitT = e->hitT.p; rc.ps.medium = e->pathMedium.p;
     ECK(e->counts.alloc(Q_NCOUNTERS));
     ECK(cudaMemset(e->counts.p, 0, sizeof(int) * Q_NCOUNTERS));
     rc.counts = e->counts.p;
@@ -1017,18 +1114,30 @@ extern "C" int bpt_render(bpt_engine *e, int first_sample, int n_samples, const 
             LaunchGenerateCameraRays(rc, x0, x1, by0, by1, first_sample + s0, ns, sms, st); ++launches;
             int cur = Q_RAY0, next = Q_RAY1;
             int maxDepth = rc.integ.maxDepth;
-            for (int depth = 0; depth <= maxDepth; ++depth) {
+            // Scenes with media or interface surfaces need one wavefront iteration per path *segment* (null collisions and
+            // interface crossings do not advance depth): iterate until the ray queue is empty.  Otherwise depth == iteration.
+            const bool dynamic = rc.useTr != 0;
+            for (int depth = 0; dynamic ? depth < 100000 : depth <= maxDepth; ++depth) {
                 LaunchResetDepth(rc, next, st); ++launches;
                 profBegin(0); LaunchTraceClosest(rc, cur, count, sms, st); ++launches; profEnd();
+                if (rc.nMedia > 0) { profBegin(2); LaunchSampleMedium(rc, next, sms, st); ++launches; profEnd(); }
                 if (rc.nInfinite > 0) { LaunchHandleEscaped(rc, sms, st); ++launches; }
                 if (e->haveAreaLights) { LaunchHandleEmissive(rc, sms, st); ++launches; }
-                if (depth == maxDepth) break;
+                if (!dynamic && depth == maxDepth) break;
                 profBegin(2);
                 for (int m = 0; m < MAT_NTAGS; ++m)
                     if (e->materialPresent[m]) { LaunchShade(rc, m, next, sms, st); ++launches; }
                 profEnd();
-                profBegin(1); LaunchTraceShadow(rc, count, sms, st); ++launches; profEnd();
+                profBegin(1);
+                if (rc.useTr) LaunchTraceShadowTr(rc, sms, st); else LaunchTraceShadow(rc, count, sms, st);
+                ++launches; profEnd();
                 std::swap(cur, next);
+                if (dynamic) {
+                    int live = 0;
+                    ECK(cudaMemcpyAsync(&live, rc.counts + cur, sizeof(int), cudaMemcpyDeviceToHost, st));
+                    ECK(cudaStreamSynchronize(st));
+                    if (live == 0) break;
+                }
             }
             LaunchUpdateFilm(rc, x0, x1, by0, by1, ns, sms, st); ++launches;
         }

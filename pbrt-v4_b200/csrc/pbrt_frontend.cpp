@@ -111,6 +111,10 @@ struct Frontend {
     std::vector<std::unique_ptr<std::vector<float>>> imageStore;
     std::map<std::string, int> objectIds;
     int curObject = -1;
+    std::vector<bpt_medium> media;
+    std::vector<std::unique_ptr<std::vector<float>>> densityStore;
+    std::map<std::string, int> namedMedia;
+    std::string cameraMediumName;
     int seedOption = 0;
     int sppOverride = 0;
 
@@ -269,6 +273,9 @@ struct Frontend {
         mr->m.material = (materials[gs.material].type == BPT_MAT_INTERFACE) ? -1 : gs.material;
         mr->m.area_light = gs.areaLight;
         mr->m.medium_inside = mr->m.medium_outside = -1;
+        if (!gs.mediumInside.empty()) { if (!namedMedia.count(gs.mediumInside)) { err = "unknown medium \"" + gs.mediumInside + "\""; return false; } mr->m.medium_inside = namedMedia[gs.mediumInside]; }
+        if (!gs.mediumOutside.empty()) { if (!namedMedia.count(gs.mediumOutside)) { err = "unknown medium \"" + gs.mediumOutside + "\""; return false; } mr->m.medium_outside = namedMedia[gs.mediumOutside]; }
+        if (curObject >= 0 && (mr->m.medium_inside >= 0 || mr->m.medium_outside >= 0)) { err = "media are not supported with object instancing"; return false; }
         mr->m.object_id = curObject;
         if (curObject >= 0 && gs.areaLight >= 0) { err = "area lights are not supported with object instancing"; return false; }
         meshes.push_back(std::move(mr));
@@ -376,6 +383,7 @@ bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::st
         if (Param *sw = pl.find("screenwindow")) { if (sw->nums.size() != 4) { err = "screenwindow needs four values"; return false; } cam.has_screen_window = 1; for (int k = 0; k < 4; ++k) cam.screen_window[k] = (float)sw->nums[k]; }
         cam.shutter_open = pl.f("shutteropen", 0.f); cam.shutter_close = pl.f("shutterclose", 1.f);
         namedCS["camera"] = Inverse(gs.ctm);
+        cameraMediumName = gs.mediumOutside;   // BasicSceneBuilder::Camera: camera.medium = graphicsState.currentOutsideMedium
         haveCam = true; return true;
     }
     if (d == "Film") {
@@ -439,6 +447,37 @@ bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::st
         if (!makeMaterial(pl.s("type", ""), pl, &m)) return false;
         materials.push_back(m); namedMaterials[a[0]] = (int)materials.size() - 1; return true;
     }
+    if (d == "MediumInterface") {
+        // MediumInterface "inside" ["outside"]: one name sets both (parser.cpp)
+        if (a.empty()) { err = "medium name expected"; return false; }
+        gs.mediumInside = a[0]; gs.mediumOutside = a.size() > 1 ? a[1] : a[0];
+        return true;
+    }
+    if (d == "MakeNamedMedium") {
+        if (a.empty()) { err = "name expected"; return false; }
+        bpt_medium m; std::memset(&m, 0, sizeof(m));
+        std::string type = pl.s("type", "");
+        if (type == "uniformgrid") m.type = BPT_MEDIUM_UNIFORMGRID;
+        else if (type == "homogeneous") m.type = BPT_MEDIUM_HOMOGENEOUS;
+        else { err = "medium type \"" + type + "\" is not supported (homogeneous, uniformgrid)"; return false; }
+        if (pl.find("preset")) { err = "medium presets are not supported"; return false; }
+        if (!getSpectrum(pl, "sigma_a", &m.sigma_a) || !getSpectrum(pl, "sigma_s", &m.sigma_s) || !getSpectrum(pl, "Le", &m.Le)) return false;
+        m.scale = pl.f("scale", 1.f); m.g = pl.f("g", 0.f); m.Le_scale = pl.f("Lescale", 1.f);
+        m.world_from_medium = ToB(gs.ctm.m); m.medium_from_world = ToB(gs.ctm.mInv);
+        m.bounds[0] = m.bounds[1] = m.bounds[2] = 0; m.bounds[3] = m.bounds[4] = m.bounds[5] = 1;
+        if (m.type == BPT_MEDIUM_UNIFORMGRID) {
+            Param *dn = pl.find("density");
+            if (!dn || dn->nums.empty()) { err = "uniformgrid medium: no \"density\" values"; return false; }
+            if (pl.find("temperature")) { err = "emissive grid media are not supported"; return false; }
+            m.nx = pl.i("nx", 1); m.ny = pl.i("ny", 1); m.nz = pl.i("nz", 1);
+            if ((size_t)m.nx * m.ny * m.nz != dn->nums.size()) { err = "uniformgrid medium: density count != nx*ny*nz"; return false; }
+            densityStore.emplace_back(new std::vector<float>(dn->nums.begin(), dn->nums.end()));
+            m.density = densityStore.back()->data();
+            if (Param *q = pl.find("p0")) { if (q->nums.size() != 3) { err = "p0 needs three values"; return false; } for (int k = 0; k < 3; ++k) m.bounds[k] = (float)q->nums[k]; }
+            if (Param *q = pl.find("p1")) { if (q->nums.size() != 3) { err = "p1 needs three values"; return false; } for (int k = 0; k < 3; ++k) m.bounds[3 + k] = (float)q->nums[k]; }
+        }
+        media.push_back(m); namedMedia[a[0]] = (int)media.size() - 1; return true;
+    }
     if (d == "NamedMaterial") { if (a.empty() || !namedMaterials.count(a[0])) { err = "unknown named material"; return false; } gs.material = namedMaterials[a[0]]; return true; }
     if (d == "AreaLightSource") {
         if (a.empty() || a[0] != "diffuse") { err = "only \"diffuse\" area lights are supported"; return false; }
@@ -501,6 +540,11 @@ bool Frontend::finish() {
     if (haveInteg && !ck(bpt_scene_set_integrator(e, &integ))) return false;
     if (!ck(bpt_scene_set_materials(e, materials.data(), (int)materials.size()))) return false;
     if (!ck(bpt_scene_set_area_lights(e, areaLights.data(), (int)areaLights.size()))) return false;
+    for (auto &m : media) if (!ck(bpt_scene_add_medium(e, &m))) return false;
+    if (!cameraMediumName.empty()) {
+        if (!namedMedia.count(cameraMediumName)) { err = "unknown camera medium"; return false; }
+        if (!ck(bpt_scene_set_camera_medium(e, namedMedia[cameraMediumName]))) return false;
+    }
     for (auto &m : meshes) {
         bpt_mesh bm = m->m;
         bm.P = m->P.data(); bm.N = m->N.empty() ? nullptr : m->N.data(); bm.UV = m->UV.empty() ? nullptr : m->UV.data(); bm.indices = m->idx.data();

@@ -191,3 +191,59 @@ def instanced(outdir, n_inst=100000, subdiv=3, res=(2048, 2048), spp=512, maxdep
     path = os.path.join(outdir, "instanced.pbrt")
     open(path, "w").write(s)
     return path
+
+
+def smoke_density(grid=256, seed=7):
+    """fBm-thresholded sphere: value noise in 5 octaves (seeded), kept inside a sphere of radius 0.45 around the centre."""
+    rng = np.random.default_rng(seed)
+    d = np.zeros((grid, grid, grid), np.float32)
+    amp, tot = 1.0, 0.0
+    for octave in range(5):
+        n = min(grid, 4 << octave)
+        coarse = rng.random((n + 1, n + 1, n + 1), dtype=np.float32)
+        # trilinear upsampling of the coarse lattice to the grid
+        t = (np.arange(grid, dtype=np.float32) + 0.5) / grid * n
+        i0 = np.minimum(t.astype(np.int32), n - 1); f = (t - i0).astype(np.float32)
+        def ax(a, axis):
+            lo = np.take(a, i0, axis=axis); hi = np.take(a, i0 + 1, axis=axis)
+            shape = [1, 1, 1]; shape[axis] = grid
+            w = f.reshape(shape)
+            return lo * (1 - w) + hi * w
+        c = ax(ax(ax(coarse, 0), 1), 2)
+        d += amp * c; tot += amp; amp *= 0.5
+    d /= tot
+    z, y, x = np.meshgrid(*[(np.arange(grid, dtype=np.float32) + 0.5) / grid - 0.5] * 3, indexing="ij")
+    r = np.sqrt(x * x + y * y + z * z)
+    d = np.clip((d - 0.42) * 6.0, 0, 1) * np.clip((0.45 - r) * 12.0, 0, 1)
+    return d.astype(np.float32)   # indexed [z][y][x]: x fastest, as GridMedium expects
+
+
+def smoke(outdir, grid=256, res=(1024, 1024), spp=2048, maxdepth=5, seed=7, homogeneous=False):
+    """Config 5: grid-density smoke (sigma_a = 2, sigma_s = 8, g = 0.3) inside a unit box with the "interface" material,
+    diffuse floor, quad light; null-scattering VolPath."""
+    os.makedirs(outdir, exist_ok=True)
+    s = _header(res, spp, maxdepth, ((0, 1.1, 3.0), (0, 0.55, 0)), 38)
+    quad = "Shape \"trianglemesh\" \"integer indices\" [0 1 2 0 2 3] \"point3 P\" [%s]\n"
+    s += "AttributeBegin\n  Translate -0.5 0.05 -0.5\n"
+    if homogeneous:
+        s += "  MakeNamedMedium \"smoke\" \"string type\" \"homogeneous\" \"rgb sigma_a\" [2 2 2] \"rgb sigma_s\" [8 8 8] \"float g\" 0.3 \"float scale\" 0.25\n"
+    else:
+        d = smoke_density(grid, seed)
+        s += (f"  MakeNamedMedium \"smoke\" \"string type\" \"uniformgrid\" \"rgb sigma_a\" [2 2 2] \"rgb sigma_s\" [8 8 8] \"float g\" 0.3\n"
+              f"    \"integer nx\" {grid} \"integer ny\" {grid} \"integer nz\" {grid} \"point3 p0\" [0 0 0] \"point3 p1\" [1 1 1]\n    \"float density\" [\n")
+        flat = d.reshape(-1)
+        s += "\n".join(" ".join(repr(float(v)) for v in flat[i:i + 16]) for i in range(0, flat.size, 16))
+        s += "\n    ]\n"
+    s += "AttributeEnd\n"
+    s += "AttributeBegin\n  AreaLightSource \"diffuse\" \"rgb L\" [30 28 24]\n  Material \"diffuse\" \"rgb reflectance\" [0 0 0]\n  "
+    s += quad % "-0.4 2.2 -0.4  0.4 2.2 -0.4  0.4 2.2 0.4  -0.4 2.2 0.4"
+    s += "AttributeEnd\nMaterial \"diffuse\" \"rgb reflectance\" [0.6 0.6 0.6]\n"
+    s += quad % "-3 0 -3  -3 0 3  3 0 3  3 0 -3"
+    # unit box with outward-facing triangles, "interface" material, smoke inside / vacuum outside
+    s += "AttributeBegin\n  MediumInterface \"smoke\" \"\"\n  Material \"interface\"\n  Translate -0.5 0.05 -0.5\n"
+    s += ("  Shape \"trianglemesh\" \"point3 P\" [0 0 0  1 0 0  1 1 0  0 1 0  0 0 1  1 0 1  1 1 1  0 1 1]\n"
+          "    \"integer indices\" [0 2 1 0 3 2  4 5 6 4 6 7  0 1 5 0 5 4  3 6 2 3 7 6  0 4 7 0 7 3  1 2 6 1 6 5]\n")
+    s += "AttributeEnd\n"
+    path = os.path.join(outdir, "smoke.pbrt")
+    open(path, "w").write(s)
+    return path

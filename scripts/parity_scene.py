@@ -16,6 +16,8 @@ elif which == "instanced":
     path = scenes.instanced(out, n_inst=int(os.environ.get("NINST", "200")), subdiv=int(os.environ.get("SUBDIV", "2")), res=(res, res), spp=spp, material=os.environ.get("MAT", "diffuse"))
 elif which == "mixed":
     path = scenes.mixed_envmap(out, n=n, res=(res, res), spp=spp, envres=int(os.environ.get("ENVRES", "128")), nmesh=int(os.environ.get("NMESH", "8")))
+elif which == "smoke":
+    path = scenes.smoke(out, grid=int(os.environ.get("GRID", "32")), res=(res, res), spp=spp, homogeneous=bool(int(os.environ.get("HOMOG", "0"))))
 else:
     path = getattr(scenes, which)(out, res=(res, res), spp=spp)
 t0 = time.time()
