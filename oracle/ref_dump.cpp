@@ -51,6 +51,7 @@
 #include <pbrt/bxdfs.h>
 #include <pbrt/lightsamplers.h>
 #include <pbrt/lights.h>
+#include <pbrt/media.h>
 #include <pbrt/options.h>
 #include <pbrt/samplers.h>
 #include <pbrt/shapes.h>
@@ -369,6 +370,77 @@ static void DumpGolden(const char *path) {
         b.f32("bvh_verts", verts);
         b.f32("bvh_rays", rays);
         b.f32("bvh_hits", hits);
+    }
+    // Media: GridMedium / HomogeneousMedium majorant tracking (SampleT_maj) and Henyey-Greenstein sampling.
+    // (appended last so that the vectors above keep their values)
+    {
+        Allocator alloc;
+        const int nx = 12, ny = 10, nz = 8;
+        std::vector<Float> density(nx * ny * nz);
+        for (Float &v : density) { Float r = rng.Uniform<float>(); v = r < 0.3f ? 0.f : 2.5f * rng.Uniform<float>(); }
+        Transform rfm = Translate(Vector3f(0.3f, -0.2f, 0.5f)) * RotateY(30) * Scale(1.1f, 0.9f, 1.3f);
+        RGBUnboundedSpectrum sa(*RGBColorSpace::sRGB, RGB(0.5f, 1.0f, 2.0f)), ss(*RGBColorSpace::sRGB, RGB(3.f, 2.f, 1.f));
+        ConstantSpectrum zero(0.f);
+        Bounds3f bounds(Point3f(-1, -0.5f, 0), Point3f(1, 1.5f, 2));
+        GridMedium grid(bounds, rfm, &sa, &ss, 1.7f, 0.35f, SampledGrid<Float>(density, nx, ny, nz, alloc), {}, 1.f, 0.f, &zero,
+                        SampledGrid<Float>({1.f}, 1, 1, 1, alloc), alloc);
+        HomogeneousMedium homog(&sa, &ss, 0.6f, &zero, 1.f, -0.2f, alloc);
+        std::vector<float> params = {(float)nx, (float)ny, (float)nz, bounds.pMin.x, bounds.pMin.y, bounds.pMin.z, bounds.pMax.x, bounds.pMax.y, bounds.pMax.z};
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) params.push_back(rfm.GetMatrix()[i][j]);
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) params.push_back(rfm.GetInverseMatrix()[i][j]);
+        b.f32("medium_params", params);
+        b.f32("medium_density", std::vector<float>(density.begin(), density.end()));
+        b.f32("medium_sigma_a", std::vector<float>(grid.sigma_a_spec.values.begin(), grid.sigma_a_spec.values.end()));
+        b.f32("medium_sigma_s", std::vector<float>(grid.sigma_s_spec.values.begin(), grid.sigma_s_spec.values.end()));
+        b.f32("medium_majorant", std::vector<float>(grid.majorantGrid.voxels.begin(), grid.majorantGrid.voxels.end()));
+        b.f32("medium_h_sigma_a", std::vector<float>(homog.sigma_a_spec.values.begin(), homog.sigma_a_spec.values.end()));
+        b.f32("medium_h_sigma_s", std::vector<float>(homog.sigma_s_spec.values.begin(), homog.sigma_s_spec.values.end()));
+        const int kEvents = 6;
+        for (int which = 0; which < 2; ++which) {
+            std::vector<float> in, out;
+            for (int i = 0; i < 768; ++i) {
+                auto r = [&]() { return 2 * rng.Uniform<float>() - 1; };
+                Point3f o(2 * r(), 2 * r(), 2 * r());
+                if (i % 3 == 0) o = rfm(Point3f(bounds.Lerp(Point3f(rng.Uniform<float>(), rng.Uniform<float>(), rng.Uniform<float>()))));   // start inside
+                Vector3f d = Normalize(Vector3f(r(), r(), r())) * (0.5f + 1.5f * rng.Uniform<float>());
+                if (i % 17 == 0) d.y = 0;
+                Float tMax = (i % 4 == 3) ? Infinity : 4 * rng.Uniform<float>();
+                Float u = rng.Uniform<float>();
+                uint64_t s0 = rng.Uniform<uint32_t>() >> 8, s1 = rng.Uniform<uint32_t>() >> 8;   // 24 bits: exactly representable as float
+                SampledWavelengths lambda = SampledWavelengths::SampleVisible(rng.Uniform<float>());
+                RNG trng(s0, s1);
+                std::vector<float> ev;
+                int nEv = 0;
+                auto cb = [&](Point3f p, MediumProperties mp, SampledSpectrum sigma_maj, SampledSpectrum T_maj) {
+                    ev.insert(ev.end(), {p.x, p.y, p.z, mp.sigma_a[0], mp.sigma_a[3], mp.sigma_s[0], mp.sigma_s[2], sigma_maj[0], sigma_maj[1],
+                                         T_maj[0], T_maj[1], T_maj[3]});
+                    return ++nEv < kEvents;
+                };
+                Ray ray(o, d, 0.f, which == 0 ? Medium(&grid) : Medium(&homog));
+                SampledSpectrum T = which == 0 ? SampleT_maj<GridMedium>(ray, tMax, u, trng, lambda, cb)
+                                               : SampleT_maj<HomogeneousMedium>(ray, tMax, u, trng, lambda, cb);
+                ev.resize(12 * kEvents, 0.f);
+                in.insert(in.end(), {o.x, o.y, o.z, d.x, d.y, d.z, tMax, u, (float)s0, (float)s1, lambda[0], lambda[1], lambda[2], lambda[3]});
+                out.push_back((float)nEv);
+                out.insert(out.end(), ev.begin(), ev.end());
+                out.insert(out.end(), {T[0], T[1], T[2], T[3], trng.Uniform<float>()});
+            }
+            b.f32(which == 0 ? "medium_grid_in" : "medium_homog_in", in);
+            b.f32(which == 0 ? "medium_grid_out" : "medium_homog_out", out);
+        }
+        std::vector<float> hin, hout;
+        const float gs[4] = {-0.7f, 0.f, 0.3f, 0.9f};
+        for (int i = 0; i < 512; ++i) {
+            auto r = [&]() { return 2 * rng.Uniform<float>() - 1; };
+            Vector3f wo = Normalize(Vector3f(r(), r(), r())), w2 = Normalize(Vector3f(r(), r(), r()));
+            Point2f u(rng.Uniform<float>(), rng.Uniform<float>());
+            HGPhaseFunction hg(gs[i % 4]);
+            auto ps = hg.Sample_p(wo, u);
+            hin.insert(hin.end(), {wo.x, wo.y, wo.z, w2.x, w2.y, w2.z, u.x, u.y, gs[i % 4]});
+            hout.insert(hout.end(), {ps->wi.x, ps->wi.y, ps->wi.z, ps->pdf, ps->p, hg.p(wo, w2)});
+        }
+        b.f32("hg_in", hin);
+        b.f32("hg_out", hout);
     }
 }
 

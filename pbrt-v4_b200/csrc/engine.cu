@@ -831,25 +831,8 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             dm.nx = nx; dm.ny = ny; dm.nz = nz;
             const int R = 16;
             dm.mres[0] = dm.mres[1] = dm.mres[2] = R;
-            // majorantGrid.Set(x, y, z, densityGrid.MaxValue(majorantGrid.VoxelBounds(x, y, z)))  (util/containers.h:837-858)
             std::vector<float> maj((size_t)R * R * R);
-            auto look = [&](int x, int y, int z) -> float {
-                if (x < 0 || y < 0 || z < 0 || x >= nx || y >= ny || z >= nz) return 0.f;
-                return om.density[((size_t)z * ny + y) * nx + x];
-            };
-            for (int z = 0; z < R; ++z) for (int y = 0; y < R; ++y) for (int x = 0; x < R; ++x) {
-                float p0[3] = {float(x) / R, float(y) / R, float(z) / R}, p1[3] = {float(x + 1) / R, float(y + 1) / R, float(z + 1) / R};
-                int n3[3] = {nx, ny, nz}, lo[3], hi[3];
-                for (int k = 0; k < 3; ++k) {
-                    float a = p0[k] * n3[k] - .5f, b = p1[k] * n3[k] - .5f;
-                    lo[k] = std::max((int)std::floor(a), 0);
-                    hi[k] = std::min((int)std::floor(b) + 1, n3[k] - 1);
-                }
-                float mv = look(lo[0], lo[1], lo[2]);
-                for (int zz = lo[2]; zz <= hi[2]; ++zz) for (int yy = lo[1]; yy <= hi[1]; ++yy) for (int xx = lo[0]; xx <= hi[0]; ++xx)
-                    mv = std::max(mv, look(xx, yy, zz));
-                maj[(size_t)x + R * ((size_t)y + R * (size_t)z)] = mv;
-            }
+            ComputeMajorantGrid(om.density.data(), nx, ny, nz, R, maj.data());
             e->mediumBufs.emplace_back(new DevBuf<float>());
             ECK(e->mediumBufs.back()->upload(om.density));
             dm.density = e->mediumBufs.back()->p;

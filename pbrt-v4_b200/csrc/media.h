@@ -103,6 +103,31 @@ BPT_HD float GridLookup(const DeviceMedium &m, Vec3 p) {
     return Lerp(dz, Lerp(dy, d00, d10), Lerp(dy, d01, d11));
 }
 
+// MajorantGrid of a GridMedium: majorantGrid.Set(x, y, z, densityGrid.MaxValue(majorantGrid.VoxelBounds(x, y, z)))
+// (media.cpp:240-246, media.h:125-129, util/containers.h:837-858).  Host only (scene preparation).
+inline void ComputeMajorantGrid(const float *density, int nx, int ny, int nz, int R, float *maj) {
+    auto look = [&](int x, int y, int z) -> float {
+        if (x < 0 || y < 0 || z < 0 || x >= nx || y >= ny || z >= nz) return 0.f;
+        return density[((size_t)z * ny + y) * nx + x];
+    };
+    for (int z = 0; z < R; ++z) for (int y = 0; y < R; ++y) for (int x = 0; x < R; ++x) {
+        float p0[3] = {float(x) / R, float(y) / R, float(z) / R}, p1[3] = {float(x + 1) / R, float(y + 1) / R, float(z + 1) / R};
+        int n3[3] = {nx, ny, nz}, lo[3], hi[3];
+        for (int k = 0; k < 3; ++k) {
+            float a = p0[k] * n3[k] - .5f, b = p1[k] * n3[k] - .5f;
+            int fa = (int)floorf(a), fb = (int)floorf(b);
+            lo[k] = fa > 0 ? fa : 0;
+            hi[k] = fb + 1 < n3[k] - 1 ? fb + 1 : n3[k] - 1;
+        }
+        float mv = look(lo[0], lo[1], lo[2]);
+        for (int zz = lo[2]; zz <= hi[2]; ++zz) for (int yy = lo[1]; yy <= hi[1]; ++yy) for (int xx = lo[0]; xx <= hi[0]; ++xx) {
+            float v = look(xx, yy, zz);
+            mv = mv < v ? v : mv;
+        }
+        maj[(size_t)x + R * ((size_t)y + R * (size_t)z)] = mv;
+    }
+}
+
 // ------------------------------------------------------------------ majorant iterators
 struct MajorantSegment { float tMin, tMax; Spec sigma_maj; };
 
