@@ -16,6 +16,9 @@
 #include <cuda_runtime.h>
 #include "pmath.h"
 #include "shapes.h"
+#ifndef BPT_FOLD_I2F
+#define BPT_FOLD_I2F 0   // measured neutral (XU relief, but +2 % node visits): profiles/r01d_fold_prefetch_sweep.log
+#endif
 
 namespace bpt {
 
@@ -101,6 +104,11 @@ BPT_D unsigned SignExtendS8x4(unsigned x) {
 }
 BPT_D float SafeInvDir(float d) { return 1.0f / (fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }
 
+BPT_D void PrefetchL1(const void *p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
 struct HitRec { int tri; float b0, b1, b2, t; int inst; };   // tri = leaf-order triangle index (of instance `inst`), -1 = miss
 
 // Conservative slab test of the 8 quantised children; returns the hit mask (internal children in bits 24..31
@@ -120,7 +128,19 @@ BPT_D unsigned NodeIntersect(Vec3 o, Vec3 idir, unsigned octinv4, float tMax, fl
     float mx = kEps * __fmaf_rn(256.f, fabsf(ax), fabsf(ox));
     float my = kEps * __fmaf_rn(256.f, fabsf(ay), fabsf(oy));
     float mz = kEps * __fmaf_rn(256.f, fabsf(az), fabsf(oz));
+#if BPT_FOLD_I2F
+    // byte -> float without the XU pipe (ncu r01b: I2F is 7.5 % of the instructions but keeps the quarter-rate XU pipe 53 % busy):
+    // PRMT builds 2^23 + q, and the 2^23 is folded into the plane offset, o' = o - 2^23 a.  o' carries an absolute rounding
+    // error of at most |a| / 2 (half a quantisation cell), which the margin absorbs -- the test stays conservative.
+    mx = __fmaf_rn(0.51f, fabsf(ax), mx); my = __fmaf_rn(0.51f, fabsf(ay), my); mz = __fmaf_rn(0.51f, fabsf(az), mz);
+    float oxlo = __fmaf_rn(-8388608.f, ax, ox - mx), oxhi = __fmaf_rn(-8388608.f, ax, ox + mx);
+    float oylo = __fmaf_rn(-8388608.f, ay, oy - my), oyhi = __fmaf_rn(-8388608.f, ay, oy + my);
+    float ozlo = __fmaf_rn(-8388608.f, az, oz - mz), ozhi = __fmaf_rn(-8388608.f, az, oz + mz);
+#define BPT_Q2F(word, j) __uint_as_float(__byte_perm((word), 0x4B000000u, 0x7650u + (j)))
+#else
     float oxlo = ox - mx, oxhi = ox + mx, oylo = oy - my, oyhi = oy + my, ozlo = oz - mz, ozhi = oz + mz;
+#define BPT_Q2F(word, j) ((float)ExtractByte((word), (j)))
+#endif
     unsigned hitmask = 0;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -137,18 +157,19 @@ BPT_D unsigned NodeIntersect(Vec3 o, Vec3 idir, unsigned octinv4, float tMax, fl
         unsigned zmin = idir.z < 0 ? qhiz : qloz, zmax = idir.z < 0 ? qloz : qhiz;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float tminx = __fmaf_rn((float)ExtractByte(xmin, j), ax, oxlo);
-            float tminy = __fmaf_rn((float)ExtractByte(ymin, j), ay, oylo);
-            float tminz = __fmaf_rn((float)ExtractByte(zmin, j), az, ozlo);
-            float tmaxx = __fmaf_rn((float)ExtractByte(xmax, j), ax, oxhi);
-            float tmaxy = __fmaf_rn((float)ExtractByte(ymax, j), ay, oyhi);
-            float tmaxz = __fmaf_rn((float)ExtractByte(zmax, j), az, ozhi);
+            float tminx = __fmaf_rn(BPT_Q2F(xmin, j), ax, oxlo);
+            float tminy = __fmaf_rn(BPT_Q2F(ymin, j), ay, oylo);
+            float tminz = __fmaf_rn(BPT_Q2F(zmin, j), az, ozlo);
+            float tmaxx = __fmaf_rn(BPT_Q2F(xmax, j), ax, oxhi);
+            float tmaxy = __fmaf_rn(BPT_Q2F(ymax, j), ay, oyhi);
+            float tmaxz = __fmaf_rn(BPT_Q2F(zmax, j), az, ozhi);
             float tmin = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, 0.f));
             float tmax = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, tMax));
             unsigned hb = ExtractByte(child_bits4, j) << ExtractByte(bit_index4, j);
             hitmask |= (tmin <= tmax) ? hb : 0u;   // branch-free: a branch here runs its body with ~3 lanes (ncu r01b)
         }
     }
+#undef BPT_Q2F
     return hitmask;
 }
 
@@ -243,6 +264,9 @@ BPT_D void TraceRay(const BVHView &bvh, Pt3 o, Vec3 d, float tMax, HitRec *rec, 
 #ifndef BPT_DEFER_COMMIT
 #define BPT_DEFER_COMMIT 1
 #endif
+#ifndef BPT_PREFETCH
+#define BPT_PREFETCH 0      // (measured: +8 % slower, profiles/r01d_fold_prefetch_sweep.log) L1 prefetch of the next node / the first deferred triangle as soon as their addresses are known
+#endif
 constexpr int kFetchThreshold = BPT_FETCH_THRESHOLD;   // refill when at least this many lanes are idle
 constexpr int kTriCap = 8;             // per-lane ring of deferred leaf groups (triBase, hit mask); one entry per node step
 constexpr int kTriBlock = BPT_TRI_BLOCK;       // a lane stops taking node steps while it holds more than this many groups
@@ -325,8 +349,18 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
             cur.y = (hitmask & 0xff000000u) | ExtractByte(__float_as_uint(n0.w), 3);
             unsigned triBase = __float_as_uint(n1.y);
             unsigned tmask = hitmask & 0x00ffffffu;
-            if (tmask) { triRing[tail & (kTriCap - 1)][tid] = make_uint2(triBase, tmask); ++tail; }
+            if (tmask) {
+                triRing[tail & (kTriCap - 1)][tid] = make_uint2(triBase, tmask); ++tail;
+                if (BPT_PREFETCH) PrefetchL1(bvh.tris + (size_t)(triBase + (31 - __clz(tmask))) * 3);
+            }
             if ((cur.y & 0xff000000u) == 0 && sp > 0) cur = stack[--sp];
+            if (BPT_PREFETCH && (cur.y & 0xff000000u)) {
+                // the node the next step will visit (same arithmetic as at the top of the step)
+                unsigned nb = 31 - __clz(cur.y);
+                unsigned ns = (nb - 24) ^ (octinv4 & 0xff);
+                const float4 *nx = bvh.nodes + (size_t)(cur.x + __popc(cur.y & ~(0xffffffffu << ns))) * 5;
+                PrefetchL1(nx); PrefetchL1(nx + 4);
+            }
         }
         // ---- triangle rounds (deferred so that many lanes test together)
         bool hasNode = act && (cur.y & 0xff000000u) != 0;

@@ -12,7 +12,12 @@ spp = int(os.environ.get("SPP", "32"))
 e.render(0, spp)
 e.stats_reset(); e.render(0, spp, profile=True)
 s = e.stats()
-print(json.dumps({k: s[k] for k in ("seconds_render", "ms_trace_closest", "ms_trace_shadow", "ms_shade", "ms_other")}))
+out = {k: round(s[k], 3) for k in ("seconds_render", "ms_trace_closest", "ms_trace_shadow", "ms_shade")}
+e.stats_reset(); e.render(0, 2, count_stats=True)
+c = e.stats()
+out["nodes_per_ray"] = round(c["nodes_visited"] / max(c["counted_rays"], 1), 3)
+out["tris_per_ray"] = round(c["tris_tested"] / max(c["counted_rays"], 1), 3)
+print(json.dumps(out))
 ''' % ROOT
 for so in sorted(glob.glob(os.path.join(ROOT, "pbrt-v4_b200", "libb200pt_*.so"))):
     env = dict(os.environ, BPT_LIB=so)
