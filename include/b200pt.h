@@ -193,6 +193,10 @@ const char *bpt_frontend_error(void);
  * (x0, x1, y0, y1; NULL = the film's pixel bounds) and accumulate them into the film.
  * flags: bit0 = count traversal statistics (slower counting kernels); bit1 = time every kernel class with CUDA events. */
 int bpt_render(bpt_engine *e, int first_sample, int n_samples, const int *pixel_bounds, int flags);
+/* Multi-GPU tiling inside one call: renders the rows y of the film's pixel bounds with ((y - y_min) / band_rows) % n_parts == part
+ * (the scanline-band partition of SURVEY 8(e)); all of a rank's bands share the wavefront passes, which keeps the ray queues as
+ * long as in a single-GPU render. */
+int bpt_render_bands(bpt_engine *e, int first_sample, int n_samples, int band_rows, int n_parts, int part, int flags);
 int bpt_film_clear(bpt_engine *e);
 int bpt_stats_reset(bpt_engine *e);
 /* Film accumulators: xres*yres*4 doubles {rgbSum[3], weightSum} over the FULL resolution (zero outside

@@ -264,6 +264,9 @@ BPT_D void TraceRay(const BVHView &bvh, Pt3 o, Vec3 d, float tMax, HitRec *rec, 
 #ifndef BPT_DEFER_COMMIT
 #define BPT_DEFER_COMMIT 1
 #endif
+#ifndef BPT_FETCH_CHUNK
+#define BPT_FETCH_CHUNK 0   // > 0: rays reserved from the queue cursor per atomic (single-level traversal)
+#endif
 #ifndef BPT_PREFETCH
 #define BPT_PREFETCH 0      // (measured: +8 % slower, profiles/r01d_fold_prefetch_sweep.log) L1 prefetch of the next node / the first deferred triangle as soon as their addresses are known
 #endif
@@ -284,6 +287,8 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
     const int tid = threadIdx.x;
     int rayIdx = -1;
     bool exhausted = false;
+    int wNext = 0, wEnd = 0; bool noMoreGlobal = false;   // (BPT_FETCH_CHUNK) warp-uniform
+    (void)wNext; (void)wEnd; (void)noMoreGlobal;
     RayPre rp; Vec3 idir, ov; unsigned octinv4 = 0; float tBox = 0;
     uint2 stack[BPT_STACK_SIZE];
     int sp = 0;
@@ -308,12 +313,29 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
         if (idle != 0 && !exhausted && (__popc(idle) >= kFetchThreshold || idle == FULL)) {
             int nNeed = __popc(idle);
             int base = 0;
+#if BPT_FETCH_CHUNK > 0
+            // warp-private range [wNext, wEnd) of the queue, refilled BPT_FETCH_CHUNK rays at a time: one atomic on the
+            // (single, contended) queue cursor per chunk instead of one per refill
+            if (wNext >= wEnd) {
+                if (lane == 0) base = atomicAdd(cursor, BPT_FETCH_CHUNK);
+                base = __shfl_sync(FULL, base, 0);
+                wNext = base; wEnd = min(base + BPT_FETCH_CHUNK, nRays);
+                if (base + BPT_FETCH_CHUNK >= nRays) noMoreGlobal = true;
+            }
+            base = wNext;
+            int take = min(nNeed, max(wEnd - wNext, 0));
+            wNext += take;
+            if (noMoreGlobal && wNext >= wEnd) exhausted = true;
+            const int limit = base + take;
+#else
             if (lane == 0) base = atomicAdd(cursor, nNeed);
             base = __shfl_sync(FULL, base, 0);
             if (base + nNeed >= nRays) exhausted = true;
+            const int limit = nRays;
+#endif
             if (rayIdx < 0) {
                 int i = base + __popc(idle & ((1u << lane) - 1));
-                if (i < nRays) {
+                if (i < limit) {
                     rayIdx = i;
                     Pt3 o; Vec3 d; float tMax;
                     Load(i, &o, &d, &tMax);

@@ -17,6 +17,9 @@
 #include "radix_sort.cuh"
 #include "pmath.h"
 
+#ifndef BPT_LEAF_MAX
+#define BPT_LEAF_MAX 3   // subtrees of at most this many triangles become one leaf child (<= 3: unary count in 3 meta bits)
+#endif
 namespace bpt {
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { snprintf(err, 256, "%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); return false; } } while (0)
@@ -220,7 +223,7 @@ __global__ void collapse_kernel(const CollapseItem *__restrict__ items, int nIte
         scale[a] = ldexpf(1.f, e);
     }
     int nInternal = 0, nTris = 0;
-    for (int k = 0; k < ne; ++k) { if (cnt[k] > 3) ++nInternal; else nTris += cnt[k]; }
+    for (int k = 0; k < ne; ++k) { if (cnt[k] > BPT_LEAF_MAX) ++nInternal; else nTris += cnt[k]; }
     int childBase = nInternal ? atomicAdd(nodeCounter, nInternal) : 0;
     int triBase = nTris ? atomicAdd(triCounter, nTris) : 0;
     unsigned imask = 0;
@@ -243,7 +246,7 @@ __global__ void collapse_kernel(const CollapseItem *__restrict__ items, int nIte
             while (qh < 255.f && org[a] + qh * scale[a] < hi3[a]) qh += 1.f;
             qlo[a][s] = (unsigned char)ql; qhi[a][s] = (unsigned char)qh;
         }
-        if (cnt[k] > 3) {
+        if (cnt[k] > BPT_LEAF_MAX) {
             imask |= 1u << s;
             meta[s] = (unsigned char)((1u << 5) | (24 + s));
             int pos = atomicAdd(nextCount, 1);

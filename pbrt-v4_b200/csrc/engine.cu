@@ -57,6 +57,7 @@ struct DevBuf {
     size_t n = 0;
     ~DevBuf() { if (p) cudaFree(p); }
     cudaError_t alloc(size_t count) {
+        if (p && n == count) return cudaSuccess;   // re-commit of a same-sized scene keeps its allocations (cudaMalloc of ~1 GB is not free)
         if (p) { cudaFree(p); p = nullptr; }
         n = count;
         return cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T));
@@ -123,6 +124,9 @@ struct bpt_engine {
     DevBuf<DeviceMedium> dMedia;
     std::vector<std::unique_ptr<DevBuf<float>>> mediumBufs;
     bool haveInterface = false;
+    bool raySort = false;            // BPT_RAY_SORT=1: sort the extension-ray queue by direction/origin key before each trace
+    DevBuf<unsigned> sortKeys, sortKeysTmp, sortHist;
+    DevBuf<int> sortQueueTmp;
     std::vector<WideBVH> blas;
     DevBuf<float> dRgb2spec;
     std::vector<std::unique_ptr<DevBuf<float>>> imgBufs;
@@ -309,7 +313,7 @@ extern "C" int bpt_create(int cuda_device, const char *tables_path, bpt_engine *
     e->sampler = bpt_sampler{BPT_SAMPLER_ZSOBOL, 16, 0, BPT_RANDOMIZE_FAST_OWEN};
     e->integ = bpt_integrator{5, 0, BPT_LIGHTSAMPLER_BVH};
     const char *mp = std::getenv("BPT_MAX_PATHS");
-    e->maxPaths = mp ? std::atoi(mp) : (4 << 20);
+    e->maxPaths = mp ? std::atoi(mp) : (32 << 20);   // profiles/r01g: 4M -> 32M paths per wavefront pass is -20 % step time (launch tails)
     *out = e.release();
     return BPT_OK;
 }
@@ -982,7 +986,9 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
 
     // ---- path state and queues
     int nPixPass = (pb[1] - pb[0]) * (pb[3] - pb[2]);
-    int maxPaths = std::max(e->maxPaths, nPixPass);
+    // pool size: enough for every sample of the frame in one pass, capped by BPT_MAX_PATHS (default 32 Mi paths, ~9 GB)
+    long long wantPaths = (long long)nPixPass * std::max(1, e->sampler.spp);
+    int maxPaths = (int)std::max<long long>(nPixPass, std::min<long long>(e->maxPaths, wantPaths));
     // one pass covers the whole pixel bounds for S samples; S is chosen at render time with S * nPix <= maxPaths
     e->rc = RenderCtx{};
     RenderCtx &rc = e->rc;
@@ -1023,6 +1029,14 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     ECK(cudaMemset(e->stats.p, 0, sizeof(unsigned long long) * 16));
     rc.stats = e->stats.p;
     ECK(e->rawCursor.alloc(1));
+    {
+        const char *rs = std::getenv("BPT_RAY_SORT");
+        e->raySort = rs && std::atoi(rs) != 0;
+        if (e->raySort) {
+            ECK(e->sortKeys.alloc(maxPaths)); ECK(e->sortKeysTmp.alloc(maxPaths)); ECK(e->sortQueueTmp.alloc(maxPaths));
+            ECK(e->sortHist.alloc(256 * (size_t)((maxPaths + 4095) / 4096)));
+        }
+    }
     rc.bvh.nodes = e->bvh.nodes; rc.bvh.tris = e->bvh.tris;
     rc.bvh.instances = instanced ? e->dInstances.p : nullptr;
     ECK(e->hitInst.alloc(instanced ? maxPaths : 1));
@@ -1058,7 +1072,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
 }
 
 // ------------------------------------------------------------------------------------------- rendering
-extern "C" int bpt_render(bpt_engine *e, int first_sample, int n_samples, const int *pixel_bounds, int flags) {
+static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int *pixel_bounds, int flags, int band_rows, int n_parts, int part) {
     if (!e) return BPT_ERR_INVALID;
     if (!e->committed) return e->fail(BPT_ERR_INVALID, "scene not committed");
     if (n_samples <= 0 || first_sample < 0) return e->fail(BPT_ERR_INVALID, "bad sample range");
@@ -1068,6 +1082,15 @@ extern "C" int bpt_render(bpt_engine *e, int first_sample, int n_samples, const 
     if (pixel_bounds) {
         x0 = std::max(x0, pixel_bounds[0]); x1 = std::min(x1, pixel_bounds[1]);
         y0 = std::max(y0, pixel_bounds[2]); y1 = std::min(y1, pixel_bounds[3]);
+    }
+    rc.bandRows = 0; rc.bandParts = 1; rc.bandPart = 0; rc.bandY0 = 0;
+    if (band_rows > 0) {
+        // interleaved bands of the film's pixel bounds: this call covers the local rows [0, nMine) of part `part`
+        if (n_parts <= 0 || part < 0 || part >= n_parts) return e->fail(BPT_ERR_INVALID, "bad band partition");
+        int nMine = 0;
+        for (int k = 0, y = y0; y < y1; ++k, y += band_rows) if (k % n_parts == part) nMine += std::min(band_rows, y1 - y);
+        rc.bandRows = band_rows; rc.bandParts = n_parts; rc.bandPart = part; rc.bandY0 = y0;
+        y0 = 0; y1 = nMine;   // local rows from here on
     }
     if (x0 >= x1 || y0 >= y1) return BPT_OK;   // empty tile
     const bool count = flags & 1;
@@ -1115,11 +1138,19 @@ extern "C" int bpt_render(bpt_engine *e, int first_sample, int n_samples, const 
                 if (rc.useTr) LaunchTraceShadowTr(rc, sms, st); else LaunchTraceShadow(rc, count, sms, st);
                 ++launches; profEnd();
                 std::swap(cur, next);
-                if (dynamic) {
+                if (dynamic || e->raySort) {
                     int live = 0;
                     ECK(cudaMemcpyAsync(&live, rc.counts + cur, sizeof(int), cudaMemcpyDeviceToHost, st));
                     ECK(cudaStreamSynchronize(st));
                     if (live == 0) break;
+                    if (e->raySort && !(!dynamic && depth + 1 > maxDepth)) {
+                        profBegin(3);
+                        bool flipped = LaunchRaySort(rc, cur, live, e->bvh.bmin, e->bvh.bmax, e->sortKeys.p, e->sortKeysTmp.p, e->sortQueueTmp.p,
+                                                     e->sortHist.p, st);
+                        launches += 4;
+                        if (flipped) ECK(cudaMemcpyAsync(rc.queues[cur], e->sortQueueTmp.p, sizeof(int) * (size_t)live, cudaMemcpyDeviceToDevice, st));
+                        profEnd();
+                    }
                 }
             }
             LaunchUpdateFilm(rc, x0, x1, by0, by1, ns, sms, st); ++launches;
@@ -1137,10 +1168,19 @@ extern "C" int bpt_render(bpt_engine *e, int first_sample, int n_samples, const 
         cudaEventElapsedTime(&pm, pe.second.first, pe.second.second);
         if (pe.first == 0) { e->st.ms_trace_closest += pm; e->st.launches_trace_closest++; }
         else if (pe.first == 1) { e->st.ms_trace_shadow += pm; e->st.launches_trace_shadow++; }
+        else if (pe.first == 3) e->st.ms_other += pm;
         else e->st.ms_shade += pm;
         cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second);
     }
     return BPT_OK;
+}
+
+extern "C" int bpt_render(bpt_engine *e, int first_sample, int n_samples, const int *pixel_bounds, int flags) {
+    return RenderImpl(e, first_sample, n_samples, pixel_bounds, flags, 0, 1, 0);
+}
+extern "C" int bpt_render_bands(bpt_engine *e, int first_sample, int n_samples, int band_rows, int n_parts, int part, int flags) {
+    if (band_rows <= 0) return e ? e->fail(BPT_ERR_INVALID, "band_rows must be positive") : BPT_ERR_INVALID;
+    return RenderImpl(e, first_sample, n_samples, nullptr, flags, band_rows, n_parts, part);
 }
 
 extern "C" int bpt_film_clear(bpt_engine *e) {

@@ -9,6 +9,8 @@ void LaunchResetDepth(const RenderCtx &rc, int nextQ, cudaStream_t st);
 void LaunchGenerateCameraRays(const RenderCtx &rc, int x0, int x1, int y0, int y1, int firstSample, int nSamples, int sms, cudaStream_t st);
 void LaunchTraceClosest(const RenderCtx &rc, int curQ, bool count, int sms, cudaStream_t st);
 void LaunchTraceShadow(const RenderCtx &rc, bool count, int sms, cudaStream_t st);
+bool LaunchRaySort(const RenderCtx &rc, int q, int n, const float bmin[3], const float bmax[3], unsigned *keys, unsigned *keysTmp,
+                   int *queueTmp, unsigned *hist, cudaStream_t st);
 void LaunchSampleMedium(const RenderCtx &rc, int nextQ, int sms, cudaStream_t st);
 void LaunchTraceShadowTr(const RenderCtx &rc, int sms, cudaStream_t st);
 void LaunchHandleEmissive(const RenderCtx &rc, int sms, cudaStream_t st);

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_histogram(const KeyT *__restric
 }
 
 // single-block exclusive scan over `len` entries
-__global__ void __launch_bounds__(1024) rs_scan(unsigned *__restrict__ data, int len) {
+static __global__ void __launch_bounds__(1024) rs_scan(unsigned *__restrict__ data, int len) {
     __shared__ unsigned warpSums[32];
     __shared__ unsigned carry;
     if (threadIdx.x == 0) carry = 0;

@@ -13,6 +13,7 @@
 // carries its own dimension counter.
 #define BPT_SOBOL_DEVICE_TABLE
 #include "wavefront.cuh"
+#include "radix_sort.cuh"
 #include "bxdfs.h"
 #include "materials.cuh"
 #include "kernels.h"
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(256) k_generate_camera_rays(RenderCtx rc, int 
     int total = nPix * nSamples;
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x) {
         int s = slot / nPix, pix = slot - s * nPix;
-        int py = y0 + pix / (x1 - x0), px = x0 + pix % (x1 - x0);
+        int py = MapRow(rc, y0 + pix / (x1 - x0)), px = x0 + pix % (x1 - x0);
         int sampleIndex = firstSample + s;
         Sampler sampler;
         sampler.StartPixelSample(&rc.sampler, px, py, sampleIndex, 0);
@@ -367,8 +368,11 @@ __device__ __forceinline__ void PushShadowTr(const RenderCtx &rc, int slot, Pt3 
 }
 
 // ---------------------------------------------------------------- surface scattering, one instantiation per material
+#ifndef BPT_SHADE_CTAS
+#define BPT_SHADE_CTAS 5      // resident 128-thread CTAs per SM the shading kernels are register-limited for
+#endif
 template <typename Material>
-__global__ void __launch_bounds__(128) k_shade(RenderCtx rc, int nextQ) {
+__global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int nextQ) {
     const int n = rc.counts[Q_MAT0 + Material::kTag];
     const int *queue = rc.queues[Q_MAT0 + Material::kTag];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -723,11 +727,27 @@ __global__ void __launch_bounds__(128) k_trace_shadow_tr(RenderCtx rc) {
     }
 }
 
+// ---------------------------------------------------------------- ray sort (no reference counterpart)
+// 8-bit key per queued ray: direction octant (3 bits) and a coarse cell of the origin inside the scene bounds (2 + 1 + 2 bits).
+// One stable LSD pass (radix_sort.cuh) over the slot indices groups rays that take the same child order and start in the same
+// region, while the pixel order inside a bucket is preserved.
+__global__ void k_ray_sort_keys(RenderCtx rc, int q, int n, float3 bmin, float3 binv, unsigned *keys) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int slot = rc.queues[q][i];
+    float4 o = rc.ps.rayO[slot], d = rc.ps.rayD[slot];
+    unsigned oct = (d.x < 0 ? 4u : 0u) | (d.y < 0 ? 2u : 0u) | (d.z < 0 ? 1u : 0u);
+    int cx = min(3, max(0, (int)((o.x - bmin.x) * binv.x * 4.f)));
+    int cy = min(1, max(0, (int)((o.y - bmin.y) * binv.y * 2.f)));
+    int cz = min(3, max(0, (int)((o.z - bmin.z) * binv.z * 4.f)));
+    keys[i] = (oct << 5) | ((unsigned)cz << 3) | ((unsigned)cy << 2) | (unsigned)cx;
+}
+
 // ---------------------------------------------------------------- film
 __global__ void __launch_bounds__(256) k_update_film(RenderCtx rc, int x0, int x1, int y0, int y1, int nSamples) {
     int nPix = (x1 - x0) * (y1 - y0);
     for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < nPix; pix += gridDim.x * blockDim.x) {
-        int py = y0 + pix / (x1 - x0), px = x0 + pix % (x1 - x0);
+        int py = MapRow(rc, y0 + pix / (x1 - x0)), px = x0 + pix % (x1 - x0);
         double4 acc = rc.filmPixels[(size_t)py * rc.film.xres + px];
         for (int s = 0; s < nSamples; ++s) {
             int slot = s * nPix + pix;
@@ -871,6 +891,15 @@ static inline int GridFor(int smCount, int perSM) { return smCount * perSM; }
 
 void LaunchSampleMedium(const RenderCtx &rc, int nextQ, int sms, cudaStream_t st) { k_sample_medium<<<GridFor(sms, 8), 128, 0, st>>>(rc, nextQ); }
 void LaunchTraceShadowTr(const RenderCtx &rc, int sms, cudaStream_t st) { k_trace_shadow_tr<<<GridFor(sms, 8), 128, 0, st>>>(rc); }
+// Sorts queue `q` (n entries, n known on the host) by the ray key; returns true if the sorted indices ended up in queueTmp.
+bool LaunchRaySort(const RenderCtx &rc, int q, int n, const float bmin[3], const float bmax[3], unsigned *keys, unsigned *keysTmp,
+                   int *queueTmp, unsigned *hist, cudaStream_t st) {
+    if (n <= 1) return false;
+    float3 lo = make_float3(bmin[0], bmin[1], bmin[2]);
+    float3 inv = make_float3(1.f / fmaxf(bmax[0] - bmin[0], 1e-20f), 1.f / fmaxf(bmax[1] - bmin[1], 1e-20f), 1.f / fmaxf(bmax[2] - bmin[2], 1e-20f));
+    k_ray_sort_keys<<<(n + 255) / 256, 256, 0, st>>>(rc, q, n, lo, inv, keys);
+    return RadixSortPairs<unsigned, int>(keys, keysTmp, rc.queues[q], queueTmp, n, 0, 8, hist, st);
+}
 void LaunchResetAll(const RenderCtx &rc, cudaStream_t st) { k_reset_counts<<<1, 64, 0, st>>>(rc.counts, 0, Q_NCOUNTERS); }
 void LaunchResetDepth(const RenderCtx &rc, int nextQ, cudaStream_t st) { k_reset_depth<<<1, 64, 0, st>>>(rc.counts, nextQ); }
 void LaunchGenerateCameraRays(const RenderCtx &rc, int x0, int x1, int y0, int y1, int firstSample, int nSamples, int sms, cudaStream_t st) {
@@ -888,10 +917,10 @@ void LaunchHandleEmissive(const RenderCtx &rc, int sms, cudaStream_t st) { k_han
 void LaunchHandleEscaped(const RenderCtx &rc, int sms, cudaStream_t st) { k_handle_escaped<<<GridFor(sms, 4), 128, 0, st>>>(rc); }
 void LaunchShade(const RenderCtx &rc, int materialTag, int nextQ, int sms, cudaStream_t st) {
     switch (materialTag) {
-    case MAT_DIFFUSE: k_shade<DiffuseMaterialEval><<<GridFor(sms, 8), 128, 0, st>>>(rc, nextQ); break;
-    case MAT_CONDUCTOR: k_shade<ConductorMaterialEval><<<GridFor(sms, 8), 128, 0, st>>>(rc, nextQ); break;
-    case MAT_DIELECTRIC: k_shade<DielectricMaterialEval><<<GridFor(sms, 8), 128, 0, st>>>(rc, nextQ); break;
-    case MAT_COATED_CONDUCTOR: k_shade<CoatedConductorMaterialEval><<<GridFor(sms, 8), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_DIFFUSE: k_shade<DiffuseMaterialEval><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_CONDUCTOR: k_shade<ConductorMaterialEval><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_DIELECTRIC: k_shade<DielectricMaterialEval><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_COATED_CONDUCTOR: k_shade<CoatedConductorMaterialEval><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
     case MAT_INTERFACE: k_shade<InterfaceMaterialEval><<<GridFor(sms, 4), 128, 0, st>>>(rc, nextQ); break;
     default: break;
     }

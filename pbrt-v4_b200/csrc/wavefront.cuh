@@ -70,9 +70,17 @@ struct RenderCtx {
     double4 *filmPixels;               // xres*yres {rgbSum[3], weightSum}
     int nInfinite;
     int maxPaths;
+    // interleaved row bands (multi-GPU tiling inside one render call): local row lr of this part maps to film row
+    // bandY0 + ((lr / bandRows) * bandParts + bandPart) * bandRows + lr % bandRows; bandRows == 0: identity
+    int bandRows, bandParts, bandPart, bandY0;
 };
 
 #if defined(__CUDACC__)
+__device__ __forceinline__ int MapRow(const RenderCtx &rc, int lr) {
+    if (rc.bandRows == 0) return lr;
+    int b = lr / rc.bandRows;
+    return rc.bandY0 + (b * rc.bandParts + rc.bandPart) * rc.bandRows + (lr - b * rc.bandRows);
+}
 __device__ __forceinline__ int WarpAggPush(int *counter) {
     // Warp-aggregated atomic slot allocation.  Lanes are grouped by the counter they push to (__match_any_sync), not
     // just by __activemask(): the compiler may merge the bodies of `if (a) push(&x); else push(&y);` into one converged

@@ -28,7 +28,7 @@ class BptStats(C.Structure):
 EXPORTS = """bpt_create bpt_destroy bpt_last_error bpt_scene_begin bpt_scene_set_camera bpt_scene_set_film
 bpt_scene_set_filter bpt_scene_set_sampler bpt_scene_set_integrator bpt_scene_set_materials bpt_scene_set_area_lights
 bpt_scene_add_mesh bpt_scene_add_instance bpt_scene_add_light bpt_scene_add_medium bpt_scene_set_camera_medium
-bpt_scene_commit bpt_load_pbrt bpt_load_pbrt_ex bpt_frontend_error bpt_render bpt_film_clear bpt_stats_reset bpt_film_read bpt_film_write
+bpt_scene_commit bpt_load_pbrt bpt_load_pbrt_ex bpt_frontend_error bpt_render bpt_render_bands bpt_film_clear bpt_stats_reset bpt_film_read bpt_film_write
 bpt_film_copy_to_device bpt_film_copy_from_device bpt_film_resolve bpt_film_dims bpt_get_stats bpt_trace_closest
 bpt_trace_any bpt_trace_closest_device bpt_probe_sampler bpt_probe_intersect_triangle""".split()
 
@@ -50,6 +50,7 @@ def load_library():
     lib.bpt_frontend_error.restype = C.c_char_p
     lib.bpt_load_pbrt_ex.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
     lib.bpt_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
+    lib.bpt_render_bands.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.bpt_film_clear.argtypes = [C.c_void_p]
     lib.bpt_stats_reset.argtypes = [C.c_void_p]
     lib.bpt_film_read.argtypes = [C.c_void_p, C.c_void_p]
@@ -141,6 +142,11 @@ class Engine:
 
     def film_from_device_ptr(self, ptr):
         self._ck(self.lib.bpt_film_copy_from_device(self.h, C.c_void_p(ptr)), "bpt_film_copy_from_device")
+
+    def render_bands(self, first_sample, n_samples, band_rows, n_parts, part, count_stats=False, profile=False):
+        """Render the interleaved scanline bands of part `part` of `n_parts` in one call (multi-GPU tiling)."""
+        self._ck(self.lib.bpt_render_bands(self.h, int(first_sample), int(n_samples), int(band_rows), int(n_parts), int(part),
+                                           (1 if count_stats else 0) | (2 if profile else 0)), "bpt_render_bands")
 
     def image(self):
         """Final RGB image [yres, xres, 3] float32 (RGBFilm::GetPixelRGB)."""

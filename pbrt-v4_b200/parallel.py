@@ -33,8 +33,8 @@ def render_tiled(engine, spp, dist=None, band=16, first_sample=0):
     if world == 1:
         engine.render(first_sample, spp)
     else:
-        for ya, yb in partition_bands(y, world, rank, band):
-            engine.render(first_sample, spp, (0, x, ya, yb))
+        # all of this rank's bands in one call: they share the wavefront passes (long ray queues, as on one GPU)
+        engine.render_bands(first_sample, spp, band, world, rank)
     film = torch.zeros((y, x, 4), dtype=torch.float64, device="cuda")
     engine.film_to_device_ptr(film.data_ptr())
     reduce_film(film, dist)

@@ -14,15 +14,17 @@ def main():
     procs = []
     for spec in sys.argv[1:]:
         name, _, defs = spec.partition(":")
+        name, _, src = name.partition("@")          # name@source.cu:-D... (default source: wavefront.cu)
+        src = src or "wavefront.cu"
         defs = [d for d in defs.split(",") if d]
-        o = os.path.join(objdir, f"wavefront_{name}.o")
-        cmd = [B.NVCC] + B.FLAGS + defs + ["-c", os.path.join(B.CSRC, "wavefront.cu"), "-o", o]
-        procs.append((name, o, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
-    for name, o, p in procs:
+        o = os.path.join(objdir, f"variant_{name}.o")
+        cmd = [B.NVCC] + B.FLAGS + defs + ["-c", os.path.join(B.CSRC, src), "-o", o]
+        procs.append((name, o, src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    for name, o, src, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:
             sys.stderr.write(out.decode()); raise SystemExit(1)
-        objs = [o] + [os.path.join(objdir, s + ".o") for s in B.SOURCES if s != "wavefront.cu"]
+        objs = [o] + [os.path.join(objdir, s + ".o") for s in B.SOURCES if s != src]
         so = os.path.join(vdir, f"libb200pt_{name}.so")
         subprocess.check_call([B.NVCC, "-shared", "-o", so] + objs + ["-ldl"])
         print(so)

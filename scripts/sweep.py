@@ -23,3 +23,12 @@ for so in sorted(glob.glob(os.path.join(ROOT, "pbrt-v4_b200", "libb200pt_*.so"))
     env = dict(os.environ, BPT_LIB=so)
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
     print(os.path.basename(so), r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:], flush=True)
+# the in-tree library itself, plain and with each runtime knob in SWEEP_ENVS ("BPT_RAY_SORT=1,OTHER=2")
+for spec in [""] + [v for v in os.environ.get("SWEEP_ENVS", "").split(",") if v]:
+    env = dict(os.environ)
+    env.pop("BPT_LIB", None)
+    if spec:
+        k, _, v = spec.partition("=")
+        env[k] = v
+    r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
+    print("libb200pt.so", spec or "(default)", r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:], flush=True)

@@ -235,6 +235,10 @@ def test_full_size_properties_1m_triangles(E, tmp_path):
         for a, b in partition_bands(1024, 3, r, band=16):
             e.render(0, 4, (0, 1024, a, b))
     assert (e.film() == full).all(), "band-partitioned render differs from the full render"
+    e.film_clear()
+    for r in range(3):
+        e.render_bands(0, 4, 16, 3, r)   # the multi-GPU path: all bands of a part in one call
+    assert (e.film() == full).all(), "interleaved-band render differs from the full render"
     e.film_clear(); e.render(0, 2); e.render(2, 2)
     assert (e.film() == full).all(), "sample-range split differs from the full render"
     e.close()
