@@ -295,9 +295,11 @@ __global__ void collapse_kernel(const CollapseItem *__restrict__ items, int nIte
 }
 
 template <typename T>
-static bool dalloc(T **p, size_t n, char *err) {
-    cudaError_t e = cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T));
-    if (e != cudaSuccess) { snprintf(err, 256, "cudaMalloc(%zu): %s", n * sizeof(T), cudaGetErrorString(e)); return false; }
+static bool dalloc(T **p, size_t n, char *err, cudaStream_t st = nullptr) {
+    // stream-ordered allocation: the device pool (release threshold raised in bpt_create) recycles the builder's scratch and
+    // output buffers across re-commits instead of paying cudaMalloc / cudaFree (device-wide syncs) every time
+    cudaError_t e = cudaMallocAsync((void **)p, std::max<size_t>(n, 1) * sizeof(T), st);
+    if (e != cudaSuccess) { snprintf(err, 256, "cudaMallocAsync(%zu): %s", n * sizeof(T), cudaGetErrorString(e)); return false; }
     return true;
 }
 
@@ -314,16 +316,15 @@ bool BuildWideBVH(const float4 *trisDev, int n, WideBVH *out, cudaStream_t strea
     CollapseItem *q0 = nullptr, *q1 = nullptr;
     int *counters = nullptr;   // [0]=nodeCounter [1]=triCounter [2]=nextCount
     int nTiles = (n + RS_TILE - 1) / RS_TILE;
-    bool ok = dalloc(&cb, 6, err) && dalloc(&keys, n, err) && dalloc(&keysTmp, n, err) && dalloc(&vals, n, err) &&
-              dalloc(&valsTmp, n, err) && dalloc(&hist, 256 * (size_t)nTiles, err) && dalloc(&left, n, err) &&
-              dalloc(&right, n, err) && dalloc(&parent, 2 * (size_t)n, err) && dalloc(&first, n, err) && dalloc(&last, n, err) &&
-              dalloc(&flags, n, err) && dalloc(&nmin, 2 * (size_t)n, err) && dalloc(&nmax, 2 * (size_t)n, err) &&
-              dalloc(&q0, n, err) && dalloc(&q1, n, err) && dalloc(&counters, 4, err) &&
-              dalloc(&out->nodes, 5 * (size_t)n, err) && dalloc(&out->tris, 3 * (size_t)n, err);
+    bool ok = dalloc(&cb, 6, err, stream) && dalloc(&keys, n, err, stream) && dalloc(&keysTmp, n, err, stream) && dalloc(&vals, n, err, stream) &&
+              dalloc(&valsTmp, n, err, stream) && dalloc(&hist, 256 * (size_t)nTiles, err, stream) && dalloc(&left, n, err, stream) &&
+              dalloc(&right, n, err, stream) && dalloc(&parent, 2 * (size_t)n, err, stream) && dalloc(&first, n, err, stream) && dalloc(&last, n, err, stream) &&
+              dalloc(&flags, n, err, stream) && dalloc(&nmin, 2 * (size_t)n, err, stream) && dalloc(&nmax, 2 * (size_t)n, err, stream) &&
+              dalloc(&q0, n, err, stream) && dalloc(&q1, n, err, stream) && dalloc(&counters, 4, err, stream) &&
+              dalloc(&out->nodes, 5 * (size_t)n, err, stream) && dalloc(&out->tris, 3 * (size_t)n, err, stream);
     auto cleanup = [&]() {
-        cudaFree(cb); cudaFree(keys); cudaFree(keysTmp); cudaFree(vals); cudaFree(valsTmp); cudaFree(hist); cudaFree(left);
-        cudaFree(right); cudaFree(parent); cudaFree(first); cudaFree(last); cudaFree(flags); cudaFree(nmin); cudaFree(nmax);
-        cudaFree(q0); cudaFree(q1); cudaFree(counters);
+        void *scratch[] = {cb, keys, keysTmp, vals, valsTmp, hist, left, right, parent, first, last, flags, nmin, nmax, q0, q1, counters};
+        for (void *q : scratch) if (q) cudaFreeAsync(q, stream);
     };
     if (!ok) { cleanup(); return false; }
     float cbInit[6] = {3.4e38f, 3.4e38f, 3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f};
@@ -373,8 +374,8 @@ bool BuildWideBVH(const float4 *trisDev, int n, WideBVH *out, cudaStream_t strea
 }
 
 void FreeWideBVH(WideBVH *b) {
-    if (b->nodes) cudaFree(b->nodes);
-    if (b->tris) cudaFree(b->tris);
+    if (b->nodes) cudaFreeAsync(b->nodes, nullptr);
+    if (b->tris) cudaFreeAsync(b->tris, nullptr);
     b->nodes = nullptr; b->tris = nullptr;
 }
 

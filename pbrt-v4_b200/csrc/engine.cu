@@ -122,6 +122,7 @@ struct bpt_engine {
     DevBuf<int> pathMedium;
     DevBuf<ShadowTrItem> shadowTr;
     DevBuf<DeviceMedium> dMedia;
+    DevBuf<uint32_t> zsPrefix;
     std::vector<std::unique_ptr<DevBuf<float>>> mediumBufs;
     bool haveInterface = false;
     bool raySort = false;            // BPT_RAY_SORT=1: sort the extension-ray queue by direction/origin key before each trace
@@ -307,6 +308,13 @@ extern "C" int bpt_create(int cuda_device, const char *tables_path, bpt_engine *
     if (!e->tables.Load(tables_path ? tables_path : DefaultTablesPath(), &terr)) { g_createError = terr; return BPT_ERR_IO; }
     if ((ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) { g_createError = cudaGetErrorString(ce); return BPT_ERR_CUDA; }
     cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
+    {   // keep freed stream-ordered allocations (BVH builder scratch / outputs) in the device pool across re-commits
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, e->device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     UploadSobolTable(e->tables.u32.at("sobol32_2x52").data());
     // defaults (scene.cpp / film.cpp / samplers.cpp defaults)
     e->filter = bpt_filter{BPT_FILTER_GAUSSIAN, 1.5f, 1.5f, 0.5f, 1.f / 3.f, 1.f / 3.f, 3.f};
@@ -432,6 +440,16 @@ static Mat4 ToMat4(const M4 &a) { Mat4 r; std::memcpy(r.m, a.m, sizeof(r.m)); re
 static bool AllZero(const bpt_mat4 &a) { for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) if (a.m[i][j] != 0) return false; return true; }
 
 extern "C" int bpt_scene_commit(bpt_engine *e) {
+    const bool timing = std::getenv("BPT_TIMING") != nullptr;
+    auto tc0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        cudaDeviceSynchronize();
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bpt commit] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - tc0).count());
+        tc0 = t;
+    };
+
     if (!e) return BPT_ERR_INVALID;
     if (!e->haveCam || !e->haveFilm) return e->fail(BPT_ERR_INVALID, "camera and film must be set before commit");
     ECK(cudaSetDevice(e->device));
@@ -802,6 +820,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     dls.nInfinite = (int)lb.infiniteLights.size();
     dls.nNodes = (int)lb.nodes.size();
 
+    lap("host scene preparation");
     // ---- media (HomogeneousMedium / GridMedium constructors, media.h:222-232, media.cpp:212-247)
     std::vector<DeviceMedium> dmedia(e->media.size());
     e->mediumBufs.clear();
@@ -895,6 +914,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     for (WideBVH &b : e->blas) FreeWideBVH(&b);
     e->blas.clear();
     char berr[256] = {0};
+    lap("uploads");
     auto tb0 = std::chrono::steady_clock::now();
     std::vector<DeviceInstance> dinst;
     const bool instanced = !e->instances.empty();
@@ -984,6 +1004,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         ECK(e->dRgb2spec.upload(t));
     }
 
+    lap("BVH build");
     // ---- path state and queues
     int nPixPass = (pb[1] - pb[0]) * (pb[3] - pb[2]);
     // pool size: enough for every sample of the frame in one pass, capped by BPT_MAX_PATHS (default 32 Mi paths, ~9 GB)
@@ -1052,6 +1073,21 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     sv.cieX = e->dTables.p; sv.cieY = e->dTables.p + kNLambda; sv.cieZ = e->dTables.p + 2 * kNLambda; sv.illumD65 = e->dTables.p + 3 * kNLambda;
     sv.rgb2specScale = e->dRgb2spec.n ? e->dRgb2spec.p : nullptr; sv.rgb2specCoeffs = e->dRgb2spec.n ? e->dRgb2spec.p + 64 : nullptr;
     sv.nLights = (int)dlights.size();
+    // ZSobol digit-prefix table: [dimension][pixel] uint32 (only when the permuted index fits in 32 bits)
+    sp.prefix = nullptr; sp.prefixDims = 0; sp.prefixW = fl.xres; sp.prefixH = fl.yres;
+    sp.nLowDigits = (sp.log2SamplesPerPixel + 1) / 2;
+    {
+        const char *pd = std::getenv("BPT_ZSOBOL_PREFIX");
+        bool enable = !(pd && std::atoi(pd) == 0);
+        int dims = std::min(6 + 7 * (e->integ.max_depth + 1), 64);
+        size_t entries = (size_t)dims * fl.xres * fl.yres;
+        if (enable && sp.type == 0 && 2 * sp.nBase4Digits <= 32 && sp.nBase4Digits > sp.nLowDigits && entries * 4 <= (size_t)2 << 30) {
+            ECK(e->zsPrefix.alloc(entries));
+            sp.prefixDims = dims;
+            LaunchZSobolPrefix(sp, e->zsPrefix.p, e->smCount, e->stream);
+            sp.prefix = e->zsPrefix.p;
+        }
+    }
     rc.camera = dc; rc.film = df; rc.filter = dflt; rc.sampler = sp;
     rc.integ.maxDepth = e->integ.max_depth; rc.integ.regularize = e->integ.regularize;
     rc.nInfinite = dls.nInfinite;
@@ -1061,6 +1097,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     ECK(e->filmRGB.alloc(3 * (size_t)fl.xres * fl.yres));
     ECK(cudaDeviceSynchronize());
 
+    lap("path state / film allocation");
     auto t1 = std::chrono::steady_clock::now();
     e->st = bpt_stats{};
     e->st.seconds_build = std::chrono::duration<double>(tb1 - tb0).count();

@@ -11,6 +11,7 @@ void LaunchTraceClosest(const RenderCtx &rc, int curQ, bool count, int sms, cuda
 void LaunchTraceShadow(const RenderCtx &rc, bool count, int sms, cudaStream_t st);
 bool LaunchRaySort(const RenderCtx &rc, int q, int n, const float bmin[3], const float bmax[3], unsigned *keys, unsigned *keysTmp,
                    int *queueTmp, unsigned *hist, cudaStream_t st);
+void LaunchZSobolPrefix(const SamplerParams &sp, uint32_t *table, int sms, cudaStream_t st);
 void LaunchSampleMedium(const RenderCtx &rc, int nextQ, int sms, cudaStream_t st);
 void LaunchTraceShadowTr(const RenderCtx &rc, int sms, cudaStream_t st);
 void LaunchHandleEmissive(const RenderCtx &rc, int sms, cudaStream_t st);

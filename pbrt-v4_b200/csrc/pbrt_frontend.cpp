@@ -11,6 +11,7 @@
 //            MakeNamedMedium MediumInterface Include
 // Anything else is an error (never silently ignored), matching the reference's ErrorExit behaviour.
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -641,7 +642,13 @@ extern "C" int bpt_load_pbrt_ex(bpt_engine *e, const char *path, int spp_overrid
     bpt_material dm; std::memset(&dm, 0, sizeof(dm)); dm.type = BPT_MAT_DIFFUSE;
     fe.materials.push_back(dm);
     fe.integ.max_depth = 5; fe.integ.light_sampler = BPT_LIGHTSAMPLER_BVH;
-    if (!fe.parseFile(p) || !fe.finish()) { g_frontendError = fe.err; return BPT_ERR_INVALID; }
+    const bool timing = std::getenv("BPT_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    if (!fe.parseFile(p)) { g_frontendError = fe.err; return BPT_ERR_INVALID; }
+    auto t1 = std::chrono::steady_clock::now();
+    if (!fe.finish()) { g_frontendError = fe.err; return BPT_ERR_INVALID; }
+    if (timing) fprintf(stderr, "[bpt load] parse %.2f ms, scene intake + commit %.2f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     return BPT_OK;
 }
 extern "C" int bpt_load_pbrt(bpt_engine *e, const char *path) { return bpt_load_pbrt_ex(e, path, 0, 0); }

@@ -178,6 +178,11 @@ struct SamplerParams {
     int log2SamplesPerPixel;
     int nBase4Digits;
     int samplesPerPixel;
+    // Optional device table (ZSobol): for every (dimension < prefixDims, pixel of the film) the permuted base-4 digits of the
+    // sample index that depend on the pixel only (digits >= nLowDigits).  The hashes that choose their permutations are the same
+    // for every sample of the pixel, so they are computed once per frame (k_zsobol_prefix) instead of once per Get1D/Get2D call.
+    const uint32_t *prefix;
+    int prefixDims, prefixW, prefixH, nLowDigits;
 };
 
 // One sampler object per path vertex evaluation: stateless function of (pixel, sampleIndex, dimension).
@@ -185,13 +190,16 @@ struct Sampler {
     const SamplerParams *sp;
     uint64_t mortonIndex;
     int dimension;
+    int pixel;   // index into SamplerParams::prefix, -1: no table / pixel outside the film
     RNG rng;   // independent sampler only
     BPT_HD void StartPixelSample(const SamplerParams *params, int px, int py, int index, int dim) {
         sp = params;
         dimension = dim;
-        if (sp->type == 0)
+        pixel = -1;
+        if (sp->type == 0) {
             mortonIndex = (EncodeMorton2((uint32_t)px, (uint32_t)py) << sp->log2SamplesPerPixel) | (uint64_t)index;
-        else {
+            if (sp->prefix && px >= 0 && py >= 0 && px < sp->prefixW && py < sp->prefixH) pixel = py * sp->prefixW + px;
+        } else {
             // IndependentSampler::StartPixelSample (samplers.h:457-460): Hash(Point2i p, int seed)
             uint64_t w[2] = {(uint64_t)(uint32_t)px | ((uint64_t)(uint32_t)py << 32), (uint64_t)(uint32_t)sp->seed};
             uint64_t h = MurmurHash64A(w, 12, 0);
@@ -200,13 +208,24 @@ struct Sampler {
         }
     }
     BPT_HD uint64_t GetSampleIndex() const {
-        // the 24 permutations of {0,1,2,3} (lowdiscrepancy.h:354-382), packed 2 bits per entry and keyed by the digit:
-        // kPerm[d] >> 2p & 3 == permutations[p][d]
-        const uint64_t kPerm0 = 0xfffaaa555000ull, kPerm1 = 0x0a5f05fa0fa5ull, kPerm2 = 0x6124dc2ce6deull, kPerm3 = 0x94817383b97bull;
         uint64_t sampleIndex = 0;
         bool pow2Samples = sp->log2SamplesPerPixel & 1;
         int lastDigit = pow2Samples ? 1 : 0;
-        for (int i = sp->nBase4Digits - 1; i >= lastDigit; --i) {
+        int top = sp->nBase4Digits - 1;
+#if defined(__CUDA_ARCH__)
+        if (pixel >= 0 && dimension < sp->prefixDims) {
+            sampleIndex = __ldg(sp->prefix + (size_t)dimension * ((size_t)sp->prefixW * sp->prefixH) + pixel);
+            top = sp->nLowDigits - 1;
+        }
+#endif
+        return FinishSampleIndex(sampleIndex, top, lastDigit, pow2Samples);
+    }
+    // digits [lastDigit, top] of the permuted sample index (ZSobolSampler::GetSampleIndex, samplers.h:300-356), ORed into `sampleIndex`
+    BPT_HD uint64_t FinishSampleIndex(uint64_t sampleIndex, int top, int lastDigit, bool pow2Samples, bool tail = true) const {
+        // the 24 permutations of {0,1,2,3} (lowdiscrepancy.h:354-382), packed 2 bits per entry and keyed by the digit:
+        // kPerm[d] >> 2p & 3 == permutations[p][d]
+        const uint64_t kPerm0 = 0xfffaaa555000ull, kPerm1 = 0x0a5f05fa0fa5ull, kPerm2 = 0x6124dc2ce6deull, kPerm3 = 0x94817383b97bull;
+        for (int i = top; i >= lastDigit; --i) {
             int digitShift = 2 * i - (pow2Samples ? 1 : 0);
             int digit = (int)((mortonIndex >> digitShift) & 3);
             uint64_t higherDigits = mortonIndex >> (digitShift + 2);
@@ -217,7 +236,7 @@ struct Sampler {
             digit = (int)((pk >> (2 * p)) & 3);
             sampleIndex |= (uint64_t)digit << digitShift;
         }
-        if (pow2Samples) {
+        if (pow2Samples && tail) {
             int digit = (int)(mortonIndex & 1);
             sampleIndex |= (uint64_t)(digit ^ (int)(MixBits((mortonIndex >> 1) ^ (uint64_t)(0x55555555u * (uint32_t)dimension)) & 1));
         }

@@ -116,6 +116,25 @@ __global__ void k_reset_depth(int *counts, int nextRayQ) {
     if (i == nextRayQ || i == Q_SHADOW || i == Q_ESCAPED || i == Q_HITLIGHT || i == Q_MEDIUM || (i >= Q_MAT0 && i < Q_NCOUNTERS)) counts[i] = 0;
 }
 
+// ---------------------------------------------------------------- ZSobol per-pixel digit prefix (see SamplerParams::prefix)
+__global__ void k_zsobol_prefix(SamplerParams sp, uint32_t *table) {
+    const size_t nPix = (size_t)sp.prefixW * sp.prefixH;
+    const size_t total = nPix * sp.prefixDims;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int dim = (int)(i / nPix);
+        int pix = (int)(i - (size_t)dim * nPix);
+        SamplerParams plain = sp;
+        plain.prefix = nullptr;
+        Sampler s;
+        s.StartPixelSample(&plain, pix % sp.prefixW, pix / sp.prefixW, 0, dim);
+        bool pow2Samples = sp.log2SamplesPerPixel & 1;
+        table[i] = (uint32_t)s.FinishSampleIndex(0, sp.nBase4Digits - 1, sp.nLowDigits, pow2Samples, false);
+    }
+}
+void LaunchZSobolPrefix(const SamplerParams &sp, uint32_t *table, int sms, cudaStream_t st) {
+    k_zsobol_prefix<<<sms * 8, 256, 0, st>>>(sp, table);
+}
+
 // ---------------------------------------------------------------- camera rays
 __global__ void __launch_bounds__(256) k_generate_camera_rays(RenderCtx rc, int x0, int x1, int y0, int y1, int firstSample, int nSamples) {
     int nPix = (x1 - x0) * (y1 - y0);
