@@ -36,6 +36,7 @@ WORKLOADS = {
                      desc="configs[2]: 10.0M-triangle height field in 64 meshes, dielectric / rough conductor, 2048^2 HDR image light, 1920x1080, 1024 spp"),
     "instanced100k": dict(gen="instanced", kw=dict(n_inst=100000, subdiv=3, material="coatedconductor"), res=(2048, 2048), spp=512,
                           desc="configs[3]: 100k instances of a 1280-triangle icosphere (two-level BVH), coated conductor, 2048x2048, 512 spp"),
+    "smoke64": dict(gen="smoke", kw=dict(grid=64), res=(512, 512), spp=256, desc="64^3 smoke (tuning size)"),
     "smoke256": dict(gen="smoke", kw=dict(grid=256), res=(1024, 1024), spp=2048,
                      desc="configs[4]: 256^3 grid-density smoke in a unit interface box, null-scattering VolPath, 1024x1024, 2048 spp"),
 }
@@ -184,7 +185,19 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL announces its version on stdout when the first communicator is created; the contract is ONE JSON line on
+        # stdout, so route fd 1 to stderr until the communicator exists
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     w = WORKLOADS[args.workload]
     spp = args.spp or w["spp"]
@@ -334,7 +347,7 @@ def main():
                 "ms_per_step": step_seconds * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "msamples_per_s": msamples,
                 "config": {"workload": w["desc"], "spp": spp, "rays_per_step": total_rays / args.steps, "tiling": f"{band}-row bands round-robin over ranks",
-                           "l2": "inputs larger than L2: BVH+triangles %.0f MB + path state %.0f MB per pass" % ((st0["bytes_bvh_nodes"] + st0["bytes_bvh_tris"]) / 1e6, 4194304 * 240 / 1e6),
+                           "l2": "inputs larger than L2: BVH+triangles %.0f MB + path state %.0f MB per pass" % ((st0["bytes_bvh_nodes"] + st0["bytes_bvh_tris"]) / 1e6, min(32 << 20, xres * yres * spp) * 240 / 1e6),
                            "bvh": {"nodes": st0["bvh_nodes"], "depth": st0["bvh_depth"], "build_seconds": st0["seconds_build"]}},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(s_after["kernel_launches"]) * args.steps,
                 "clocks": clocks.summary(), "wall_seconds_timed_region": wall_max}

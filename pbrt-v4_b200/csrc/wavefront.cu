@@ -546,7 +546,10 @@ __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int
 // VolPathIntegrator::Li, "Sample the participating medium" (cpu/integrators.cpp:970-1078) == wavefront SampleMediumInteraction +
 // SampleMediumScattering (wavefront/media.cpp:22-352) with VolPath's sampler consumption (3 x Get1D, then SampleLd's 1D + 2D and the
 // phase function's 2D at a real scattering event).
-__global__ void __launch_bounds__(128) k_sample_medium(RenderCtx rc, int nextQ) {
+#ifndef BPT_MEDIUM_CTAS
+#define BPT_MEDIUM_CTAS 8     // resident 128-thread CTAs per SM the medium kernels are register-limited for
+#endif
+__global__ void __launch_bounds__(128, BPT_MEDIUM_CTAS) k_sample_medium(RenderCtx rc, int nextQ) {
     const int n = rc.counts[Q_MEDIUM];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         int slot = rc.queues[Q_MEDIUM][i];
@@ -676,7 +679,7 @@ __global__ void __launch_bounds__(128) k_sample_medium(RenderCtx rc, int nextQ) 
 // Shadow rays through media / interface surfaces: the loop of VolPathIntegrator::SampleLd (cpu/integrators.cpp:1331-1389), i.e.
 // the wavefront TraceTransmittance (wavefront/intersect.h:164-274): closest hit, stop at the first surface with a material,
 // ratio-track the transmittance through the current medium, continue behind interface surfaces.
-__global__ void __launch_bounds__(128) k_trace_shadow_tr(RenderCtx rc) {
+__global__ void __launch_bounds__(128, BPT_MEDIUM_CTAS) k_trace_shadow_tr(RenderCtx rc) {
     const int n = rc.counts[Q_SHADOW];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&rc.stats[2], (unsigned long long)n);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -908,8 +911,8 @@ void LaunchProbeMath(int fn, const float *x, const float *y, int n, float *out, 
 // ================================================================= host-side launchers
 static inline int GridFor(int smCount, int perSM) { return smCount * perSM; }
 
-void LaunchSampleMedium(const RenderCtx &rc, int nextQ, int sms, cudaStream_t st) { k_sample_medium<<<GridFor(sms, 8), 128, 0, st>>>(rc, nextQ); }
-void LaunchTraceShadowTr(const RenderCtx &rc, int sms, cudaStream_t st) { k_trace_shadow_tr<<<GridFor(sms, 8), 128, 0, st>>>(rc); }
+void LaunchSampleMedium(const RenderCtx &rc, int nextQ, int sms, cudaStream_t st) { k_sample_medium<<<GridFor(sms, 2 * BPT_MEDIUM_CTAS), 128, 0, st>>>(rc, nextQ); }
+void LaunchTraceShadowTr(const RenderCtx &rc, int sms, cudaStream_t st) { k_trace_shadow_tr<<<GridFor(sms, 2 * BPT_MEDIUM_CTAS), 128, 0, st>>>(rc); }
 // Sorts queue `q` (n entries, n known on the host) by the ray key; returns true if the sorted indices ended up in queueTmp.
 bool LaunchRaySort(const RenderCtx &rc, int q, int n, const float bmin[3], const float bmax[3], unsigned *keys, unsigned *keysTmp,
                    int *queueTmp, unsigned *hist, cudaStream_t st) {

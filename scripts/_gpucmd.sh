@@ -1,17 +1,14 @@
-set -x
 mkdir -p gpurun_out
-BPT_TIMING=1 python - <<'PY' 2>&1 | tail -24
-import sys, time
-sys.path.insert(0, '.')
-import bench
-from pbrt_v4_b200 import engine as E
-path = bench.make_scene("heightfield1m", spp=256)
-e = E.Engine(0)
-for i in range(3):
-    t = time.time(); e.load_pbrt(path, seed=0); print("load_pbrt wall", time.time() - t, flush=True)
-t = time.time(); e.render(0, 32); print("render 32spp", time.time() - t)
-t = time.time(); img = e.image(); print("image()", time.time() - t)
+SECONDS=0
+for w in instanced100k mixed10m smoke256; do
+  timeout 700 python bench.py --workload $w --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
+  echo "== $w rc=$?"; tail -2 gpurun_out/bench_$w.err | cut -c1-300
+  python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/bench_$w.json"))
+    print({k:d[k] for k in ("value","ms_per_step","msamples_per_s")}, d["e2e"]["seconds_per_step"], d["roofline"]["frac"], d["roofline"]["step"]["frac"], {k:(v.get("ms_total"),v.get("nodes_per_ray"),v.get("tris_per_ray")) for k,v in d["roofline"]["kernels"].items() if isinstance(v,dict)}, d["config"]["bvh"])
+except Exception as e: print("no json", e)
 PY
-SPP=32 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r01h_launches.csv python scripts/ncu_target.py > gpurun_out/ncu_l.log 2>&1; tail -2 gpurun_out/ncu_l.log
-SPP=32 ncu --set full --import-source on --clock-control none -k regex:"k_trace_closest|k_shade|k_generate_camera" -c 3 -o gpurun_out/r01h_closest_shade_camera -f python scripts/ncu_target.py > gpurun_out/ncu_f.log 2>&1; tail -2 gpurun_out/ncu_f.log
-cp pbrt-v4_b200/libb200pt.so gpurun_out/r01h_libb200pt.so
+  echo "elapsed $SECONDS s"
+done

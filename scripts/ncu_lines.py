@@ -1,14 +1,14 @@
 """Joins an ncu report's per-SASS-instruction counters with nvdisasm's line info (inline chains) of the in-tree library and
 prints executed warp-instructions / samples aggregated by source location.
 
-usage: python scripts/ncu_lines.py report.ncu-rep kernel_regex [launch_index] [--top N] [--by inner|outer|func] [--mangled RE]
+usage: python scripts/ncu_lines.py report.ncu-rep kernel_regex [launch_index] [--top N] [--by inner|outer|func] [--mangled RE] [--lib path/to/the/libb200pt.so/the/report/was/taken/with]
 The library must be the build the report was taken with (instruction counts are checked).
 """
 import collections, csv, os, re, subprocess, sys, tempfile
 
-def disasm(kernel_re):
+def disasm(kernel_re, so=None):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    so = os.path.join(root, "pbrt-v4_b200", "libb200pt.so")
+    so = so or os.path.join(root, "pbrt-v4_b200", "libb200pt.so")
     d = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=d, capture_output=True)
     txt = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(d, "wavefront.sm_100a.cubin")], capture_output=True, text=True).stdout
@@ -40,7 +40,8 @@ def main():
     launch = int(args[0]) if args and not args[0].startswith("--") else 0
     top = int(args[args.index("--top") + 1]) if "--top" in args else 40
     by = args[args.index("--by") + 1] if "--by" in args else "inner"
-    name, ins = disasm(args[args.index("--mangled") + 1] if "--mangled" in args else kre)
+    name, ins = disasm(args[args.index("--mangled") + 1] if "--mangled" in args else kre,
+                       os.path.abspath(args[args.index("--lib") + 1]) if "--lib" in args else None)
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     secs = []; cur = None; hdr = None

@@ -6,7 +6,7 @@ import os, sys, json
 sys.path.insert(0, %r)
 import bench
 from pbrt_v4_b200 import engine as E
-path = bench.make_scene(os.environ.get("BPT_WORKLOAD", "heightfield1m"), spp=256)
+path = bench.make_scene(os.environ.get("BPT_WORKLOAD", "heightfield1m"), spp=int(os.environ.get("SCENE_SPP", "256")), res=tuple(int(v) for v in os.environ["SCENE_RES"].split("x")) if "SCENE_RES" in os.environ else None)
 e = E.Engine(0); e.load_pbrt(path, seed=0)
 spp = int(os.environ.get("SPP", "32"))
 e.render(0, spp)
