@@ -50,6 +50,33 @@ BPT_D Vec3 PermuteK(Vec3 v, int kz) {
     // (kx,ky,kz) is a cyclic rotation: kz=2 -> (x,y,z), kz=0 -> (y,z,x), kz=1 -> (z,x,y)
     return kz == 2 ? v : (kz == 0 ? Vec3(v.y, v.z, v.x) : Vec3(v.z, v.x, v.y));
 }
+// First stage of the watertight test (translate, permute, shear, edge functions incl. the FP64 fallback, sign and det tests):
+// identical arithmetic to the opening of IntersectTrianglePre below, so `false` here means the full test returns false.
+// ~85 % of the candidates end here; the survivors are parked (one per lane) and finished together with the full test, because
+// running the long tail of the test (range checks, division, error bounds) right away would execute it with ~2 active lanes.
+BPT_D bool IntersectTriangleHead(const RayPre &r, Pt3 p0, Pt3 p1, Pt3 p2) {
+    Vec3 p0t = PermuteK(p0 - r.o, r.kz), p1t = PermuteK(p1 - r.o, r.kz), p2t = PermuteK(p2 - r.o, r.kz);
+    p0t.x += r.Sx * p0t.z; p0t.y += r.Sy * p0t.z;
+    p1t.x += r.Sx * p1t.z; p1t.y += r.Sy * p1t.z;
+    p2t.x += r.Sx * p2t.z; p2t.y += r.Sy * p2t.z;
+    float e0 = DifferenceOfProducts(p1t.x, p2t.y, p1t.y, p2t.x);
+    float e1 = DifferenceOfProducts(p2t.x, p0t.y, p2t.y, p0t.x);
+    float e2 = DifferenceOfProducts(p0t.x, p1t.y, p0t.y, p1t.x);
+    if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {
+        double p2txp1ty = (double)p2t.x * (double)p1t.y;
+        double p2typ1tx = (double)p2t.y * (double)p1t.x;
+        e0 = (float)(p2typ1tx - p2txp1ty);
+        double p0txp2ty = (double)p0t.x * (double)p2t.y;
+        double p0typ2tx = (double)p0t.y * (double)p2t.x;
+        e1 = (float)(p0typ2tx - p0txp2ty);
+        double p1txp0ty = (double)p1t.x * (double)p0t.y;
+        double p1typ0tx = (double)p1t.y * (double)p0t.x;
+        e2 = (float)(p1typ0tx - p1txp0ty);
+    }
+    if ((e0 < 0 || e1 < 0 || e2 < 0) && (e0 > 0 || e1 > 0 || e2 > 0)) return false;
+    float det = e0 + e1 + e2;
+    return det != 0;
+}
 // Same arithmetic as IntersectTriangle (shapes.h) with the per-ray terms hoisted.
 // The degenerate-triangle early-out of the reference (LengthSquared(Cross(p2 - p0, p1 - p0)) == 0) depends only on the
 // triangle; the builder evaluates it once and stores the verdict in bit 31 of the leaf record's class word.
@@ -264,6 +291,9 @@ BPT_D void TraceRay(const BVHView &bvh, Pt3 o, Vec3 d, float tMax, HitRec *rec, 
 #ifndef BPT_DEFER_COMMIT
 #define BPT_DEFER_COMMIT 1
 #endif
+#ifndef BPT_DEFER_TAIL
+#define BPT_DEFER_TAIL 0    // (measured +12 % slower, profiles/r01l_two_stage_triangle_test.log) two-stage triangle test: edge-function stage per round, full test batched at the end of the rounds
+#endif
 #ifndef BPT_FETCH_CHUNK
 #define BPT_FETCH_CHUNK 0   // > 0: rays reserved from the queue cursor per atomic (single-level traversal)
 #endif
@@ -296,6 +326,20 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
     uint2 cur = make_uint2(0, 0);
     HitRec rec; rec.tri = -1; rec.t = 0; rec.b0 = rec.b1 = rec.b2 = 0;
     bool done = false;             // traversal of rayIdx finished, result not yet committed
+    int pend = -1;                 // (BPT_DEFER_TAIL) triangle that passed the edge-function stage, full test outstanding
+    bool anyHitFound = false;
+    auto finishPending = [&]() {
+        const float4 *tp = bvh.tris + (size_t)pend * 3;
+        float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        TriHit th;
+        if (IntersectTrianglePre(rp, rec.t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th)) {
+            rec.tri = pend; rec.b0 = th.b0; rec.b1 = th.b1; rec.b2 = th.b2; rec.t = th.t;
+            if (ANYHIT) anyHitFound = true;
+            else tBox = th.t * (1 + 2 * gamma_n(3));
+        }
+        pend = -1;
+    };
+    (void)anyHitFound;
     while (true) {
         // ---- commit (batched: finished lanes wait until enough of them can commit and refill together)
         unsigned doneMask = __ballot_sync(FULL, done);
@@ -347,7 +391,7 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
                     tBox = tMax * (1 + 2 * gamma_n(3));
                     sp = 0; head = tail = 0;
                     cur = make_uint2(0u, 0x80000000u);
-                    rec.tri = -1; rec.t = tMax;
+                    rec.tri = -1; rec.t = tMax; anyHitFound = false;
                 }
             }
         }
@@ -401,6 +445,13 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
                     const float4 *tp = bvh.tris + (size_t)tri * 3;
                     float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                     if (COUNT) ++*nTris;
+#if BPT_DEFER_TAIL
+                    if (!(__float_as_uint(b.w) & 0x80000000u) &&
+                        IntersectTriangleHead(rp, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z))) {
+                        if (pend >= 0) finishPending();   // second survivor of this lane in one batch (rare): resolve the first now
+                        pend = (int)tri;
+                    }
+#else
                     TriHit th;
                     if (!(__float_as_uint(b.w) & 0x80000000u) &&
                         IntersectTrianglePre(rp, rec.t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th)) {
@@ -408,12 +459,18 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
                         if (ANYHIT) { finished = true; head = tail; }
                         else tBox = th.t * (1 + 2 * gamma_n(3));
                     }
+#endif
                     hasTri = tail != head;
                 }
                 unsigned m = __ballot_sync(FULL, hasTri);
                 if (m == 0) break;
                 if (__popc(m) < kRoundLanes && anyNodeRunnable) break;
             }
+#if BPT_DEFER_TAIL
+            // second stage for every lane that parked a survivor during this batch of rounds
+            if (pend >= 0) finishPending();
+            if (ANYHIT && anyHitFound) { finished = true; head = tail; }
+#endif
         }
         // ---- mark finished rays (committed at the top of the loop)
         if (act) {
