@@ -316,6 +316,7 @@ extern "C" int bpt_create(int cuda_device, const char *tables_path, bpt_engine *
         }
     }
     UploadSobolTable(e->tables.u32.at("sobol32_2x52").data());
+    ConfigureKernels();
     // defaults (scene.cpp / film.cpp / samplers.cpp defaults)
     e->filter = bpt_filter{BPT_FILTER_GAUSSIAN, 1.5f, 1.5f, 0.5f, 1.f / 3.f, 1.f / 3.f, 3.f};
     e->sampler = bpt_sampler{BPT_SAMPLER_ZSOBOL, 16, 0, BPT_RANDOMIZE_FAST_OWEN};

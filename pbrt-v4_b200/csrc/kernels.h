@@ -4,6 +4,7 @@
 
 namespace bpt {
 void UploadSobolTable(const uint32_t *t);
+void ConfigureKernels();
 void LaunchResetAll(const RenderCtx &rc, cudaStream_t st);
 void LaunchResetDepth(const RenderCtx &rc, int nextQ, cudaStream_t st);
 void LaunchGenerateCameraRays(const RenderCtx &rc, int x0, int x1, int y0, int y1, int firstSample, int nSamples, int sms, cudaStream_t st);

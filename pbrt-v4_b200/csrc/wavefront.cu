@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(256) k_generate_camera_rays(RenderCtx rc, int 
 #ifndef BPT_TRACE_CTAS
 #define BPT_TRACE_CTAS 8      // resident CTAs per SM the persistent traversal kernels are sized (and register-limited) for
 #endif
-template <bool COUNT>
+// INST selects the two-level traversal at compile time: one traversal body (and one triangle ring in shared memory) per kernel
+template <bool COUNT, bool INST>
 __global__ void __launch_bounds__(128, BPT_TRACE_CTAS) k_trace_closest(RenderCtx rc, int curQ) {
     const int nRays = rc.counts[curQ];
     const int *queue = rc.queues[curQ];
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(128, BPT_TRACE_CTAS) k_trace_closest(RenderCtx
             rc.queues[Q_MAT0 + mt][p] = slot;
         }
     };
-    if (rc.bvh.instances)
+    if (INST)
         TraversePersistentInst<false, COUNT>(rc.bvh, rc.bvh.instances, nRays, &rc.counts[Q_CURSOR_CLOSEST], load, commitInst, &locNodes, &locTris, &locRays);
     else
         TraversePersistent<false, COUNT>(rc.bvh, nRays, &rc.counts[Q_CURSOR_CLOSEST], load, commit, &locNodes, &locTris, &locRays);
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(128, BPT_TRACE_CTAS) k_trace_closest(RenderCtx
 }
 
 // ---------------------------------------------------------------- shadow rays
-template <bool COUNT>
+template <bool COUNT, bool INST>
 __global__ void __launch_bounds__(128, BPT_TRACE_CTAS) k_trace_shadow(RenderCtx rc) {
     const int nRays = rc.counts[Q_SHADOW];
     unsigned locNodes = 0, locTris = 0, locRays = 0;
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(128, BPT_TRACE_CTAS) k_trace_shadow(RenderCtx 
             rc.ps.L[slot] = L;
         }
     };
-    if (rc.bvh.instances)
+    if (INST)
         TraversePersistentInst<true, COUNT>(rc.bvh, rc.bvh.instances, nRays, &rc.counts[Q_CURSOR_SHADOW], load, commit, &locNodes, &locTris, &locRays);
     else
         TraversePersistent<true, COUNT>(rc.bvh, nRays, &rc.counts[Q_CURSOR_SHADOW], load, commit, &locNodes, &locTris, &locRays);
@@ -922,18 +923,33 @@ bool LaunchRaySort(const RenderCtx &rc, int q, int n, const float bmin[3], const
     k_ray_sort_keys<<<(n + 255) / 256, 256, 0, st>>>(rc, q, n, lo, inv, keys);
     return RadixSortPairs<unsigned, int>(keys, keysTmp, rc.queues[q], queueTmp, n, 0, 8, hist, st);
 }
+// Shared-memory carve-out of the persistent traversal kernels: they need BPT_TRACE_CTAS x 9 KB; everything else should be L1
+// (node / triangle fetches hit L1 in ~40 % of the sectors, ncu r01h)
+void ConfigureKernels() {
+    const int pct = 36;   // of 228 KB: >= 8 x 9 KB
+    cudaFuncSetAttribute(k_trace_closest<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_trace_closest<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_trace_closest<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_trace_closest<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_trace_shadow<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_trace_shadow<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_trace_shadow<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_trace_shadow<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
 void LaunchResetAll(const RenderCtx &rc, cudaStream_t st) { k_reset_counts<<<1, 64, 0, st>>>(rc.counts, 0, Q_NCOUNTERS); }
 void LaunchResetDepth(const RenderCtx &rc, int nextQ, cudaStream_t st) { k_reset_depth<<<1, 64, 0, st>>>(rc.counts, nextQ); }
 void LaunchGenerateCameraRays(const RenderCtx &rc, int x0, int x1, int y0, int y1, int firstSample, int nSamples, int sms, cudaStream_t st) {
     k_generate_camera_rays<<<GridFor(sms, 8), 256, 0, st>>>(rc, x0, x1, y0, y1, firstSample, nSamples);
 }
 void LaunchTraceClosest(const RenderCtx &rc, int curQ, bool count, int sms, cudaStream_t st) {
-    if (count) k_trace_closest<true><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc, curQ);
-    else k_trace_closest<false><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc, curQ);
+    const bool inst = rc.bvh.instances != nullptr;
+    if (count) { if (inst) k_trace_closest<true, true><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc, curQ); else k_trace_closest<true, false><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc, curQ); }
+    else { if (inst) k_trace_closest<false, true><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc, curQ); else k_trace_closest<false, false><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc, curQ); }
 }
 void LaunchTraceShadow(const RenderCtx &rc, bool count, int sms, cudaStream_t st) {
-    if (count) k_trace_shadow<true><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc);
-    else k_trace_shadow<false><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc);
+    const bool inst = rc.bvh.instances != nullptr;
+    if (count) { if (inst) k_trace_shadow<true, true><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc); else k_trace_shadow<true, false><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc); }
+    else { if (inst) k_trace_shadow<false, true><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc); else k_trace_shadow<false, false><<<GridFor(sms, BPT_TRACE_CTAS), 128, 0, st>>>(rc); }
 }
 void LaunchHandleEmissive(const RenderCtx &rc, int sms, cudaStream_t st) { k_handle_emissive<<<GridFor(sms, 4), 128, 0, st>>>(rc); }
 void LaunchHandleEscaped(const RenderCtx &rc, int sms, cudaStream_t st) { k_handle_escaped<<<GridFor(sms, 4), 128, 0, st>>>(rc); }
