@@ -78,6 +78,7 @@ typedef struct {
     float iso, exposure_time, white_balance;
     float max_component_value;    /* <= 0: infinity */
     float diagonal;               /* mm, default 35 */
+    int coordinate_system;        /* BPT_FILM_GBUFFER: 0 = "camera" (default), 1 = "world"  (film.cpp GBufferFilm::Create) */
 } bpt_film;
 
 typedef struct { int type; float xradius, yradius; float sigma, b, c, tau; } bpt_filter;
@@ -197,6 +198,10 @@ int bpt_render(bpt_engine *e, int first_sample, int n_samples, const int *pixel_
  * (the scanline-band partition of SURVEY 8(e)); all of a rank's bands share the wavefront passes, which keeps the ray queues as
  * long as in a single-GPU render. */
 int bpt_render_bands(bpt_engine *e, int first_sample, int n_samples, int band_rows, int n_parts, int part, int flags);
+/* GBufferFilm::GetImage (film.cpp:690-790): 25 floats per pixel of the full film, in the reference's channel order
+ * R G B Albedo.{R,G,B} P.{X,Y,Z} dzdx dzdy N.{X,Y,Z} Ns.{X,Y,Z} u v Variance.{R,G,B} RelativeVariance.{R,G,B}.
+ * Only valid when the film type is BPT_FILM_GBUFFER. */
+int bpt_film_resolve_gbuffer(bpt_engine *e, float *out25);
 int bpt_film_clear(bpt_engine *e);
 int bpt_stats_reset(bpt_engine *e);
 /* Film accumulators: xres*yres*4 doubles {rgbSum[3], weightSum} over the FULL resolution (zero outside

@@ -73,9 +73,19 @@ static ImageAndMetadata ReadEXR(const std::string &name, Allocator alloc) {
     ErrorExit("%s: EXR unsupported in this build", name);
     return {};
 }
+// No OpenEXR here: "*.exr" outputs are written as a raw dump instead (the only multi-channel writer the oracle needs,
+// for GBufferFilm): text header "BPTRAW1 <width> <height> <nchannels>\\n" + one channel name per line, then float32
+// pixels, row-major, channels interleaved.
 bool Image::WriteEXR(const std::string &name, const ImageMetadata &metadata) const {
-    Error("%s: EXR unsupported in this build", name.c_str());
-    return false;
+    FILE *f = fopen(name.c_str(), "wb");
+    if (!f) { Error("%s: cannot open for writing", name.c_str()); return false; }
+    fprintf(f, "BPTRAW1 %d %d %d\\n", resolution.x, resolution.y, NChannels());
+    for (int c = 0; c < NChannels(); ++c) fprintf(f, "%s\\n", channelNames[c].c_str());
+    for (int y = 0; y < resolution.y; ++y)
+        for (int x = 0; x < resolution.x; ++x)
+            for (int c = 0; c < NChannels(); ++c) { float v = GetChannel({x, y}, c); fwrite(&v, 4, 1, f); }
+    fclose(f);
+    return true;
 }
 
 '''

@@ -123,6 +123,9 @@ struct bpt_engine {
     DevBuf<ShadowTrItem> shadowTr;
     DevBuf<DeviceMedium> dMedia;
     DevBuf<uint32_t> zsPrefix;
+    DevBuf<float4> visSurf;
+    DevBuf<GBufferPixel> gbuf;
+    DevBuf<float> gbufOut;
     std::vector<std::unique_ptr<DevBuf<float>>> mediumBufs;
     bool haveInterface = false;
     bool raySort = false;            // BPT_RAY_SORT=1: sort the extension-ray queue by direction/origin key before each trace
@@ -490,6 +493,14 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) df.outRGBFromSensor[i][j] = m[3 * i + j];   // RGBFromXYZ * identity
     }
     df.isGBuffer = fl.type == BPT_FILM_GBUFFER;
+    {
+        const std::vector<float> &m = e->tables.F("srgb_rgb_from_xyz");
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) df.rgbFromXYZ[i][j] = m[3 * i + j];
+        // outputFromRender: "camera" -> cameraTransform.RenderFromCamera() applied inverted, "world" -> WorldFromRender forward
+        Xform out = fl.coordinate_system == 1 ? worldFromRender : renderFromCamera;
+        df.applyInverse = fl.coordinate_system == 1 ? 0 : 1;
+        df.outM = ToMat4(out.m); df.outMInv = ToMat4(out.mInv);
+    }
 
     DeviceFilter dflt{};
     FilterTables ft;
@@ -527,6 +538,10 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         dc.lensRadius = e->cam.lens_radius;
         dc.focalDistance = e->cam.focal_distance > 0 ? e->cam.focal_distance : 1e6f;
         dc.type = e->cam.type;
+        // dxCamera = cameraFromRaster(Point3f(1,0,0)) - cameraFromRaster(Point3f(0,0,0))  (cameras.h:347-351)
+        Pt3 c0 = cameraFromRaster(Pt3(0, 0, 0)), cx = cameraFromRaster(Pt3(1, 0, 0)), cy = cameraFromRaster(Pt3(0, 1, 0));
+        dc.dxCamera = cx - c0; dc.dyCamera = cy - c0;
+        dc.rayDiffScale = std::max(.125f, 1 / std::sqrt((float)std::max(1, e->sampler.spp)));
     }
 
     // ---- sampler (samplers.h:228-239)
@@ -1024,6 +1039,15 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     rc.ps.lambda = f4 + 7 * (size_t)maxPaths; rc.ps.lambdaPdf = f4 + 8 * (size_t)maxPaths; rc.ps.ctx0 = f4 + 9 * (size_t)maxPaths;
     rc.ps.ctx1 = f4 + 10 * (size_t)maxPaths; rc.ps.ctx2 = f4 + 11 * (size_t)maxPaths;
     rc.ps.misc = e->stateMisc.p; rc.ps.aux = e->stateAux.p;
+    if (df.isGBuffer) {
+        if (!e->media.empty() || e->materialPresent[MAT_INTERFACE]) return e->fail(BPT_ERR_UNSUPPORTED, "GBufferFilm with media / interface surfaces is not implemented");
+        ECK(e->visSurf.alloc((size_t)maxPaths * 6));
+        ECK(e->gbuf.alloc((size_t)fl.xres * fl.yres));
+        ECK(cudaMemset(e->gbuf.p, 0, sizeof(GBufferPixel) * (size_t)fl.xres * fl.yres));
+        ECK(e->gbufOut.alloc(25 * (size_t)fl.xres * fl.yres));
+    }
+    rc.ps.vs = df.isGBuffer ? e->visSurf.p : nullptr;
+    rc.gbuf = df.isGBuffer ? e->gbuf.p : nullptr;
     int nQueues = 0;
     int qIndex[Q_CURSOR_CLOSEST];
     for (int q = 0; q < Q_CURSOR_CLOSEST; ++q) {
@@ -1225,6 +1249,16 @@ extern "C" int bpt_film_clear(bpt_engine *e) {
     if (!e || !e->committed) return BPT_ERR_INVALID;
     ECK(cudaSetDevice(e->device));
     ECK(cudaMemset(e->filmPixels.p, 0, sizeof(double4) * e->filmPixels.n));
+    if (e->rc.gbuf) ECK(cudaMemset(e->gbuf.p, 0, sizeof(GBufferPixel) * e->gbuf.n));
+    return BPT_OK;
+}
+extern "C" int bpt_film_resolve_gbuffer(bpt_engine *e, float *out25) {
+    if (!e || !e->committed || !out25) return BPT_ERR_INVALID;
+    if (!e->rc.gbuf) return e->fail(BPT_ERR_INVALID, "the film is not a GBufferFilm");
+    ECK(cudaSetDevice(e->device));
+    LaunchResolveGBuffer(e->filmPixels.p, e->gbuf.p, e->rc.film, e->gbufOut.p, e->smCount, e->stream);
+    ECK(cudaMemcpyAsync(out25, e->gbufOut.p, sizeof(float) * e->gbufOut.n, cudaMemcpyDeviceToHost, e->stream));
+    ECK(cudaStreamSynchronize(e->stream));
     return BPT_OK;
 }
 extern "C" int bpt_stats_reset(bpt_engine *e) {

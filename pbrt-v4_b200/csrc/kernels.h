@@ -20,6 +20,7 @@ void LaunchHandleEscaped(const RenderCtx &rc, int sms, cudaStream_t st);
 void LaunchShade(const RenderCtx &rc, int materialTag, int nextQ, int sms, cudaStream_t st);
 bool ShadeSupported(int materialTag);
 void LaunchUpdateFilm(const RenderCtx &rc, int x0, int x1, int y0, int y1, int nSamples, int sms, cudaStream_t st);
+void LaunchResolveGBuffer(const double4 *pix, const GBufferPixel *gb, const DeviceFilm &film, float *out, int sms, cudaStream_t st);
 void LaunchResolveFilm(const double4 *pix, const DeviceFilm &film, float *rgbOut, int sms, cudaStream_t st);
 void LaunchTraceRaw(const BVHView &bvh, const float4 *rays, int n, float4 *hits, float *tOut, int *cursor, unsigned long long *stats,
                     bool any, bool count, int sms, cudaStream_t st);

@@ -472,6 +472,11 @@ bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::st
             film.pixel_bounds[0] = (int)std::ceil(film.xres * x0); film.pixel_bounds[1] = (int)std::ceil(film.xres * x1);
             film.pixel_bounds[2] = (int)std::ceil(film.yres * y0); film.pixel_bounds[3] = (int)std::ceil(film.yres * y1);
         }
+        {
+            std::string csys = pl.s("coordinatesystem", "camera");
+            if (csys != "camera" && csys != "world") { err = "gbuffer coordinatesystem must be \"camera\" or \"world\""; return false; }
+            film.coordinate_system = csys == "world" ? 1 : 0;
+        }
         film.iso = pl.f("iso", 100.f); film.white_balance = pl.f("whitebalance", 0.f); film.exposure_time = -1;
         film.max_component_value = pl.f("maxcomponentvalue", -1.f); film.diagonal = pl.f("diagonal", 35.f);
         std::string sensor = pl.s("sensor", "cie1931");

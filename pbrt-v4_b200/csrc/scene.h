@@ -23,6 +23,8 @@ struct DeviceCamera {
     Mat4 renderFromCamera;      // CameraTransform::renderFromCamera (start transform; static camera)
     float lensRadius, focalDistance;
     int type, pad;
+    Vec3 dxCamera, dyCamera;    // PerspectiveCamera::dxCamera / dyCamera (cameras.h:347-351), used for GBufferFilm ray differentials
+    float rayDiffScale;         // max(.125, 1 / sqrt(spp))  (cpu/integrators.cpp:251-254)
 };
 
 struct DeviceFilm {
@@ -31,6 +33,20 @@ struct DeviceFilm {
     float imagingRatio, maxComponentValue;
     float outRGBFromSensor[3][3];
     int isGBuffer, pad;
+    // GBufferFilm (film.cpp:588-641): outputFromRender and whether it is applied inverted ("camera": RenderFromCamera inverted,
+    // "world": WorldFromRender forward), plus the colour space's RGBFromXYZ for the albedo channel
+    Mat4 outM, outMInv;
+    int applyInverse, pad2;
+    float rgbFromXYZ[3][3];
+};
+
+// GBufferFilm::Pixel members beyond {rgbSum, weightSum} (film.h:432-444); float / double exactly as the reference declares them
+struct GBufferPixel {
+    float pSum[3], dzdxSum, dzdySum, nSum[3], nsSum[3], uvSum[2];
+    float varMean[3], varS[3];
+    long long varN[3];
+    double gBufferWeightSum;
+    double rgbAlbedoSum[3];
 };
 
 struct DeviceFilter {          // FilterSampler tables (filters.cpp FilterSampler ctor)

@@ -51,6 +51,12 @@ __device__ __forceinline__ Vec3 XformVector(const Mat4 &T, Vec3 v) {
     return Vec3(m[0][0] * v.x + m[0][1] * v.y + m[0][2] * v.z, m[1][0] * v.x + m[1][1] * v.y + m[1][2] * v.z,
                 m[2][0] * v.x + m[2][1] * v.y + m[2][2] * v.z);
 }
+// Normal3f transformed by the transpose of `A` (Transform::operator()(Normal3f): A = mInv; Transform::ApplyInverse(Normal3f): A = m)
+__device__ __forceinline__ Nrm3 XformNormalByTranspose(const Mat4 &A, Nrm3 n) {
+    const float (*m)[4] = A.m;
+    float x = n.x, y = n.y, z = n.z;
+    return Nrm3(m[0][0] * x + m[1][0] * y + m[2][0] * z, m[0][1] * x + m[1][1] * y + m[2][1] * z, m[0][2] * x + m[1][2] * y + m[2][2] * z);
+}
 // Transform::operator()(const Ray &r) (util/transform.h:336-349) for an exact origin
 __device__ __forceinline__ void XformRay(const Mat4 &T, Pt3 &o, Vec3 &d) {
     const float (*m)[4] = T.m;
@@ -136,6 +142,62 @@ void LaunchZSobolPrefix(const SamplerParams &sp, uint32_t *table, int sms, cudaS
 }
 
 // ---------------------------------------------------------------- camera rays
+// wavelength sample + GetCameraSample (samplers.h:797-814): dimensions 0..5 of the pixel sample
+struct CamSample { float lu; Vec2 pFilm; float fweight; float time; Vec2 pLens; };
+__device__ __forceinline__ CamSample GetCameraSample(const RenderCtx &rc, Sampler &sampler, int px, int py, int sampleIndex) {
+    CamSample cs;
+    sampler.StartPixelSample(&rc.sampler, px, py, sampleIndex, 0);
+    cs.lu = sampler.Get1D();
+    Vec2 uf = sampler.Get2D();
+    Vec2 fp;
+    if (rc.filter.sampled) {
+        float pdf; int ou, ov;
+        fp = PC2DSample(rc.filter.distrib, uf, &pdf, &ou, &ov);
+        cs.fweight = rc.filter.f[ov * rc.filter.nx + ou] / pdf;
+    } else {   // BoxFilter::Sample (filters.h)
+        fp = Vec2(Lerp(uf.x, -rc.filter.radiusX, rc.filter.radiusX), Lerp(uf.y, -rc.filter.radiusY, rc.filter.radiusY));
+        cs.fweight = 1;
+    }
+    cs.pFilm = Vec2((px + fp.x) + 0.5f, (py + fp.y) + 0.5f);
+    cs.time = sampler.Get1D();
+    cs.pLens = sampler.Get2D();
+    return cs;
+}
+
+// GBufferFilm: the camera ray differentials of a pixel sample in render space, scaled as the integrator does
+// (PerspectiveCamera::GenerateRayDifferential cameras.cpp:450-477, Transform::operator()(RayDifferential) util/transform.h,
+// RayDifferential::ScaleDifferentials ray.h:53-58).  o, d: the main ray in render space.
+struct RayDiffs { Pt3 rxO, ryO; Vec3 rxD, ryD; };
+__device__ __forceinline__ RayDiffs CameraRayDifferentials(const RenderCtx &rc, const CamSample &cs, Pt3 o, Vec3 d) {
+    const DeviceCamera &cam = rc.camera;
+    Pt3 pCamera = XformPoint(cam.cameraFromRaster, Pt3(cs.pFilm.x, cs.pFilm.y, 0));
+    RayDiffs r;
+    if (cam.lensRadius > 0) {
+        Vec2 dsk = SampleUniformDiskConcentric(cs.pLens);
+        Vec2 pl(cam.lensRadius * dsk.x, cam.lensRadius * dsk.y);
+        Vec3 dx = Normalize(Vec3(pCamera.x + cam.dxCamera.x, pCamera.y + cam.dxCamera.y, pCamera.z + cam.dxCamera.z));
+        float ft = cam.focalDistance / dx.z;
+        Pt3 pFocus = Pt3(0, 0, 0) + (dx * ft);
+        r.rxO = Pt3(pl.x, pl.y, 0);
+        r.rxD = Normalize(pFocus - r.rxO);
+        Vec3 dy = Normalize(Vec3(pCamera.x + cam.dyCamera.x, pCamera.y + cam.dyCamera.y, pCamera.z + cam.dyCamera.z));
+        ft = cam.focalDistance / dy.z;
+        pFocus = Pt3(0, 0, 0) + (dy * ft);
+        r.ryO = Pt3(pl.x, pl.y, 0);
+        r.ryD = Normalize(pFocus - r.ryO);
+    } else {
+        r.rxO = r.ryO = Pt3(0, 0, 0);
+        r.rxD = Normalize(Vec3(pCamera.x, pCamera.y, pCamera.z) + cam.dxCamera);
+        r.ryD = Normalize(Vec3(pCamera.x, pCamera.y, pCamera.z) + cam.dyCamera);
+    }
+    r.rxO = XformPoint(cam.renderFromCamera, r.rxO); r.ryO = XformPoint(cam.renderFromCamera, r.ryO);
+    r.rxD = XformVector(cam.renderFromCamera, r.rxD); r.ryD = XformVector(cam.renderFromCamera, r.ryD);
+    float s = cam.rayDiffScale;
+    r.rxO = o + (r.rxO - o) * s; r.ryO = o + (r.ryO - o) * s;
+    r.rxD = d + (r.rxD - d) * s; r.ryD = d + (r.ryD - d) * s;
+    return r;
+}
+
 __global__ void __launch_bounds__(256) k_generate_camera_rays(RenderCtx rc, int x0, int x1, int y0, int y1, int firstSample, int nSamples) {
     int nPix = (x1 - x0) * (y1 - y0);
     int total = nPix * nSamples;
@@ -144,23 +206,10 @@ __global__ void __launch_bounds__(256) k_generate_camera_rays(RenderCtx rc, int 
         int py = MapRow(rc, y0 + pix / (x1 - x0)), px = x0 + pix % (x1 - x0);
         int sampleIndex = firstSample + s;
         Sampler sampler;
-        sampler.StartPixelSample(&rc.sampler, px, py, sampleIndex, 0);
-        float lu = sampler.Get1D();
-        Wavelengths wl = Wavelengths::SampleVisible(lu);
-        // GetCameraSample (samplers.h:797-814)
-        Vec2 uf = sampler.Get2D();
-        Vec2 fp; float fweight;
-        if (rc.filter.sampled) {
-            float pdf; int ou, ov;
-            fp = PC2DSample(rc.filter.distrib, uf, &pdf, &ou, &ov);
-            fweight = rc.filter.f[ov * rc.filter.nx + ou] / pdf;
-        } else {   // BoxFilter::Sample (filters.h)
-            fp = Vec2(Lerp(uf.x, -rc.filter.radiusX, rc.filter.radiusX), Lerp(uf.y, -rc.filter.radiusY, rc.filter.radiusY));
-            fweight = 1;
-        }
-        Vec2 pFilm((px + fp.x) + 0.5f, (py + fp.y) + 0.5f);
-        float time = sampler.Get1D();
-        Vec2 pLens = sampler.Get2D();
+        CamSample cs = GetCameraSample(rc, sampler, px, py, sampleIndex);
+        Wavelengths wl = Wavelengths::SampleVisible(cs.lu);
+        Vec2 pFilm = cs.pFilm, pLens = cs.pLens;
+        float fweight = cs.fweight, time = cs.time;
         // PerspectiveCamera::GenerateRayDifferential (cameras.cpp:429-447), main ray only
         Pt3 pCamera = XformPoint(rc.camera.cameraFromRaster, Pt3(pFilm.x, pFilm.y, 0));
         Vec3 dir = Normalize(Vec3(pCamera.x, pCamera.y, pCamera.z));
@@ -186,6 +235,7 @@ __global__ void __launch_bounds__(256) k_generate_camera_rays(RenderCtx rc, int 
         ps.misc[slot] = make_uint4((unsigned)px | ((unsigned)py << 16), (unsigned)sampleIndex, (unsigned)sampler.dimension, 0u);
         ps.aux[slot] = make_float2(1.f, fweight);
         if (rc.nMedia > 0) ps.medium[slot] = rc.cameraMedium;   // CameraBase::medium (cameras.h)
+        if (rc.film.isGBuffer) ps.vs[slot] = make_float4(0, 0, 0, 0);   // VisibleSurface::set = false
         rc.queues[Q_RAY0][slot] = slot;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -433,6 +483,50 @@ __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int
         BSDF<typename Material::BxDF> bsdf(isect.ns, isect.dpdus, bxdf);
         if (lambdaChanged) ps.lambdaPdf[slot] = make_float4(wl.pdf[0], wl.pdf[1], wl.pdf[2], wl.pdf[3]);
 
+        // Initialize visibleSurf at first intersection (cpu/integrators.cpp:1118-1145): GBufferFilm only
+        if (rc.film.isGBuffer && depth == 0) {
+            Sampler camSampler;
+            CamSample cs = GetCameraSample(rc, camSampler, px, py, (int)misc.y);
+            float4 o4 = ps.rayO[slot];
+            Vec3 rd(d4.x, d4.y, d4.z);
+            RayDiffs rdif = CameraRayDifferentials(rc, cs, Pt3(o4.x, o4.y, o4.z), rd);
+            // SurfaceInteraction::ComputeDifferentials (interaction.cpp:42-60), the dpdx / dpdy part
+            Vec3 dpdx(0, 0, 0), dpdy(0, 0, 0);
+            Pt3 P = isect.p();
+            if (Dot(isect.n, rdif.rxD) != 0 && Dot(isect.n, rdif.ryD) != 0) {
+                float dd = -Dot(isect.n, Vec3(P.x, P.y, P.z));
+                float tx = (-Dot(isect.n, Vec3(rdif.rxO.x, rdif.rxO.y, rdif.rxO.z)) - dd) / Dot(isect.n, rdif.rxD);
+                Pt3 pxp = rdif.rxO + rdif.rxD * tx;
+                float ty = (-Dot(isect.n, Vec3(rdif.ryO.x, rdif.ryO.y, rdif.ryO.z)) - dd) / Dot(isect.n, rdif.ryD);
+                Pt3 pyp = rdif.ryO + rdif.ryD * ty;
+                dpdx = pxp - P; dpdy = pyp - P;
+            }   // (else: Camera::Approximate_dp_dxy -- a measure-zero case, left at zero)
+            // albedo: bsdf.rho(wo, ucRho, uRho) with the 16 fixed samples (BxDF::rho bxdfs.cpp:1131-1144)
+            const float ucRho[16] = {0.75741637f, 0.37870818f, 0.7083487f, 0.18935409f, 0.9149363f, 0.35417435f, 0.5990858f, 0.09467703f,
+                                     0.8578725f, 0.45746812f, 0.686759f, 0.17708716f, 0.9674518f, 0.2995429f, 0.5083201f, 0.047338516f};
+            const float uRho[16][2] = {{0.855985f, 0.570367f}, {0.381823f, 0.851844f}, {0.285328f, 0.764262f}, {0.733380f, 0.114073f},
+                                       {0.542663f, 0.344465f}, {0.127274f, 0.414848f}, {0.964700f, 0.947162f}, {0.594089f, 0.643463f},
+                                       {0.095109f, 0.170369f}, {0.825444f, 0.263359f}, {0.429467f, 0.454469f}, {0.244460f, 0.816459f},
+                                       {0.756135f, 0.731258f}, {0.516165f, 0.152852f}, {0.180888f, 0.214174f}, {0.898579f, 0.503897f}};
+            Spec albedo(0.f);
+            Vec3 woL = bsdf.RenderToLocal(wo);
+            if (woL.z != 0) {
+                Spec r(0.f);
+                for (int k = 0; k < 16; ++k) {
+                    BSDFSample bs = bsdf.bxdf.Sample_f(woL, ucRho[k], Vec2(uRho[k][0], uRho[k][1]), MODE_RADIANCE);
+                    if (bs.valid && bs.pdf > 0) r += bs.f * AbsCosTheta(bs.wi) / bs.pdf;
+                }
+                albedo = r / 16.f;
+            }
+            Nrm3 vn = FaceForward(isect.n, wo), vns = FaceForward(isect.ns, wo);
+            const size_t M = (size_t)rc.maxPaths;
+            ps.vs[slot] = make_float4(P.x, P.y, P.z, 1.f);
+            ps.vs[M + slot] = make_float4(vn.x, vn.y, vn.z, isect.uv.x);
+            ps.vs[2 * M + slot] = make_float4(vns.x, vns.y, vns.z, isect.uv.y);
+            ps.vs[3 * M + slot] = make_float4(dpdx.x, dpdx.y, dpdx.z, 0.f);
+            ps.vs[4 * M + slot] = make_float4(dpdy.x, dpdy.y, dpdy.z, 0.f);
+            ps.vs[5 * M + slot] = make_float4(albedo[0], albedo[1], albedo[2], albedo[3]);
+        }
         // Terminate path if maximum depth reached
         if (depth++ >= rc.integ.maxDepth) continue;
         if (rc.integ.regularize && anyNonSpecularBounces) bsdf.Regularize();
@@ -791,6 +885,49 @@ __global__ void __launch_bounds__(256) k_update_film(RenderCtx rc, int x0, int x
             float m = stdmax(stdmax(r, g), b);
             if (m > rc.film.maxComponentValue) { float sc = rc.film.maxComponentValue / m; r *= sc; g *= sc; b *= sc; }
             float weight = rc.ps.aux[slot].y;
+            if (rc.film.isGBuffer) {
+                const size_t M = (size_t)rc.maxPaths;
+                float4 v0 = rc.ps.vs[slot];
+                if (v0.w != 0) {   // visibleSurface && *visibleSurface  (GBufferFilm::AddSample film.cpp:588-641)
+                    GBufferPixel &gp = rc.gbuf[(size_t)py * rc.film.xres + px];
+                    float4 v1 = rc.ps.vs[M + slot], v2 = rc.ps.vs[2 * M + slot], v3 = rc.ps.vs[3 * M + slot], v4 = rc.ps.vs[4 * M + slot];
+                    gp.gBufferWeightSum += (double)weight;
+                    const float rgbc[3] = {r, g, b};
+                    for (int c = 0; c < 3; ++c) {   // VarianceEstimator<Float>::Add (util/math.h)
+                        ++gp.varN[c];
+                        float delta = rgbc[c] - gp.varMean[c];
+                        gp.varMean[c] += delta / gp.varN[c];
+                        float delta2 = rgbc[c] - gp.varMean[c];
+                        gp.varS[c] += delta * delta2;
+                    }
+                    Pt3 P(v0.x, v0.y, v0.z); Nrm3 N(v1.x, v1.y, v1.z), NS(v2.x, v2.y, v2.z); Vec3 DX(v3.x, v3.y, v3.z), DY(v4.x, v4.y, v4.z);
+                    Pt3 po; Nrm3 no, nso; float dzx, dzy;
+                    if (rc.film.applyInverse) {
+                        po = ApplyInversePoint(rc.film.outMInv, P);
+                        no = XformNormalByTranspose(rc.film.outM, N); nso = XformNormalByTranspose(rc.film.outM, NS);
+                        dzx = XformVector(rc.film.outMInv, DX).z; dzy = XformVector(rc.film.outMInv, DY).z;
+                    } else {
+                        po = XformPoint(rc.film.outM, P);
+                        no = XformNormalByTranspose(rc.film.outMInv, N); nso = XformNormalByTranspose(rc.film.outMInv, NS);
+                        dzx = XformVector(rc.film.outM, DX).z; dzy = XformVector(rc.film.outM, DY).z;
+                    }
+                    gp.pSum[0] += weight * po.x; gp.pSum[1] += weight * po.y; gp.pSum[2] += weight * po.z;
+                    gp.nSum[0] += weight * no.x; gp.nSum[1] += weight * no.y; gp.nSum[2] += weight * no.z;
+                    gp.nsSum[0] += weight * nso.x; gp.nsSum[1] += weight * nso.y; gp.nsSum[2] += weight * nso.z;
+                    gp.dzdxSum += weight * dzx; gp.dzdySum += weight * dzy;
+                    gp.uvSum[0] += weight * v1.w; gp.uvSum[1] += weight * v2.w;
+                    // albedo * colorSpace->illuminant.Sample(lambda) -> ToRGB(lambda, colorSpace)
+                    Spec alb = ld4(&rc.ps.vs[5 * M + slot]) * DenseSample(rc.sv.illumD65, wl);
+                    Spec pdfS = wl.PDF();
+                    float X = SafeDiv(DenseSample(rc.sv.cieX, wl) * alb, pdfS).Average() / 106.856895f;
+                    float Y = SafeDiv(DenseSample(rc.sv.cieY, wl) * alb, pdfS).Average() / 106.856895f;
+                    float Z = SafeDiv(DenseSample(rc.sv.cieZ, wl) * alb, pdfS).Average() / 106.856895f;
+                    for (int c = 0; c < 3; ++c) {
+                        float v = rc.film.rgbFromXYZ[c][0] * X + rc.film.rgbFromXYZ[c][1] * Y + rc.film.rgbFromXYZ[c][2] * Z;
+                        gp.rgbAlbedoSum[c] += (double)(weight * v);
+                    }
+                }
+            }
             acc.x += (double)(weight * r);
             acc.y += (double)(weight * g);
             acc.z += (double)(weight * b);
@@ -798,6 +935,44 @@ __global__ void __launch_bounds__(256) k_update_film(RenderCtx rc, int x0, int x
         }
         rc.filmPixels[(size_t)py * rc.film.xres + px] = acc;
     }
+}
+
+// GBufferFilm::GetImage (film.cpp:690-790): 25 channels per pixel in the reference's order
+// R G B | Albedo.RGB | P.XYZ | dzdx dzdy | N.XYZ | Ns.XYZ | u v | Variance.RGB | RelativeVariance.RGB
+__global__ void k_resolve_gbuffer(const double4 *pix, const GBufferPixel *gb, DeviceFilm film, float *out) {
+    int n = film.xres * film.yres;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double4 p = pix[i];
+        const GBufferPixel &g = gb[i];
+        float rgb[3] = {(float)p.x, (float)p.y, (float)p.z};
+        float alb[3] = {(float)g.rgbAlbedoSum[0], (float)g.rgbAlbedoSum[1], (float)g.rgbAlbedoSum[2]};
+        float weightSum = (float)p.w, gws = (float)g.gBufferWeightSum;
+        float pt[3] = {g.pSum[0], g.pSum[1], g.pSum[2]}, uv[2] = {g.uvSum[0], g.uvSum[1]};
+        float dzdx = g.dzdxSum, dzdy = g.dzdySum;
+        if (weightSum != 0) { for (int c = 0; c < 3; ++c) { rgb[c] /= weightSum; alb[c] /= weightSum; } }
+        if (gws != 0) { for (int c = 0; c < 3; ++c) pt[c] /= gws; uv[0] /= gws; uv[1] /= gws; dzdx /= gws; dzdy /= gws; }
+        for (int c = 0; c < 3; ++c) rgb[c] += 0.f;   // splats: none on this path
+        float o3[3];
+        for (int r = 0; r < 3; ++r) { float v = 0; for (int c = 0; c < 3; ++c) v += film.outRGBFromSensor[r][c] * rgb[c]; o3[r] = v; }
+        float *o = out + 25 * (size_t)i;
+        o[0] = o3[0]; o[1] = o3[1]; o[2] = o3[2];
+        o[3] = alb[0]; o[4] = alb[1]; o[5] = alb[2];
+        o[6] = pt[0]; o[7] = pt[1]; o[8] = pt[2];
+        o[9] = fabsf(dzdx); o[10] = fabsf(dzdy);
+        Nrm3 nn(g.nSum[0], g.nSum[1], g.nSum[2]), ns(g.nsSum[0], g.nsSum[1], g.nsSum[2]);
+        nn = LengthSquared(nn) > 0 ? Normalize(nn) : Nrm3(0, 0, 0);
+        ns = LengthSquared(ns) > 0 ? Normalize(ns) : Nrm3(0, 0, 0);
+        o[11] = nn.x; o[12] = nn.y; o[13] = nn.z; o[14] = ns.x; o[15] = ns.y; o[16] = ns.z;
+        o[17] = uv[0]; o[18] = uv[1];
+        for (int c = 0; c < 3; ++c) {
+            float var = g.varN[c] > 1 ? g.varS[c] / (g.varN[c] - 1) : 0.f;
+            o[19 + c] = var;
+            o[22 + c] = (g.varN[c] < 1 || g.varMean[c] == 0) ? 0.f : var / g.varMean[c];
+        }
+    }
+}
+void LaunchResolveGBuffer(const double4 *pix, const GBufferPixel *gb, const DeviceFilm &film, float *out, int sms, cudaStream_t st) {
+    k_resolve_gbuffer<<<sms * 4, 256, 0, st>>>(pix, gb, film, out);
 }
 
 __global__ void k_resolve_film(const double4 *pix, DeviceFilm film, float *rgbOut) {

@@ -31,6 +31,8 @@ struct PathState {
     float4 *ctx0;        // prevIntrCtx: pi.x.low, pi.x.high, pi.y.low, pi.y.high
     float4 *ctx1;        //              pi.z.low, pi.z.high, n.x, n.y
     float4 *ctx2;        //              n.z, ns.x, ns.y, ns.z
+    float4 *vs;          // GBufferFilm only: VisibleSurface of the path, 6 float4 per slot in arrays of maxPaths:
+                         //   [0] p.xyz | set  [1] n.xyz | u  [2] ns.xyz | v  [3] dpdx  [4] dpdy  [5] albedo
     uint4 *misc;         // px | py << 16, sampleIndex, sampler dimension, depth | specularBounce << 8 | anyNonSpecular << 9
     float2 *aux;         // etaScale, filterWeight
 };
@@ -68,6 +70,7 @@ struct RenderCtx {
     SamplerParams sampler;
     IntegratorParams integ;
     double4 *filmPixels;               // xres*yres {rgbSum[3], weightSum}
+    GBufferPixel *gbuf;                // xres*yres, GBufferFilm only
     int nInfinite;
     int maxPaths;
     // interleaved row bands (multi-GPU tiling inside one render call): local row lr of this part maps to film row

@@ -28,7 +28,7 @@ class BptStats(C.Structure):
 EXPORTS = """bpt_create bpt_destroy bpt_last_error bpt_scene_begin bpt_scene_set_camera bpt_scene_set_film
 bpt_scene_set_filter bpt_scene_set_sampler bpt_scene_set_integrator bpt_scene_set_materials bpt_scene_set_area_lights
 bpt_scene_add_mesh bpt_scene_add_instance bpt_scene_add_light bpt_scene_add_medium bpt_scene_set_camera_medium
-bpt_scene_commit bpt_load_pbrt bpt_load_pbrt_ex bpt_frontend_error bpt_render bpt_render_bands bpt_film_clear bpt_stats_reset bpt_film_read bpt_film_write
+bpt_scene_commit bpt_load_pbrt bpt_load_pbrt_ex bpt_frontend_error bpt_render bpt_render_bands bpt_film_resolve_gbuffer bpt_film_clear bpt_stats_reset bpt_film_read bpt_film_write
 bpt_film_copy_to_device bpt_film_copy_from_device bpt_film_resolve bpt_film_dims bpt_get_stats bpt_trace_closest
 bpt_trace_any bpt_trace_closest_device bpt_probe_sampler bpt_probe_intersect_triangle""".split()
 
@@ -58,6 +58,7 @@ def load_library():
     lib.bpt_film_copy_to_device.argtypes = [C.c_void_p, C.c_void_p]
     lib.bpt_film_copy_from_device.argtypes = [C.c_void_p, C.c_void_p]
     lib.bpt_film_resolve.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bpt_film_resolve_gbuffer.argtypes = [C.c_void_p, C.c_void_p]
     lib.bpt_film_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.bpt_get_stats.argtypes = [C.c_void_p, C.POINTER(BptStats)]
     lib.bpt_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -153,6 +154,17 @@ class Engine:
         x, y = self.dims()
         out = np.empty((y, x, 3), dtype=np.float32)
         self._ck(self.lib.bpt_film_resolve(self.h, out.ctypes.data), "bpt_film_resolve")
+        return out
+
+    GBUFFER_CHANNELS = ["R", "G", "B", "Albedo.R", "Albedo.G", "Albedo.B", "P.X", "P.Y", "P.Z", "dzdx", "dzdy", "N.X", "N.Y", "N.Z",
+                        "Ns.X", "Ns.Y", "Ns.Z", "u", "v", "Variance.R", "Variance.G", "Variance.B",
+                        "RelativeVariance.R", "RelativeVariance.G", "RelativeVariance.B"]
+
+    def gbuffer(self):
+        """GBufferFilm image [yres, xres, 25] float32 in the reference's channel order (GBufferFilm::GetImage)."""
+        x, y = self.dims()
+        out = np.empty((y, x, 25), dtype=np.float32)
+        self._ck(self.lib.bpt_film_resolve_gbuffer(self.h, out.ctypes.data), "bpt_film_resolve_gbuffer")
         return out
 
     def stats(self):

@@ -35,3 +35,15 @@ def channel_rmse(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return [float(np.sqrt(np.mean((a[..., c] - b[..., c]) ** 2))) for c in range(a.shape[-1])]
+
+
+def read_raw_channels(path):
+    """Multi-channel dump written by the oracle build of the reference for "*.exr" outputs (oracle/build_ref.py):
+    header "BPTRAW1 w h nc", nc channel names, float32 pixels.  Returns (names, array [h, w, nc])."""
+    with open(path, "rb") as f:
+        hdr = f.readline().split()
+        assert hdr[0] == b"BPTRAW1", hdr
+        w, h, nc = int(hdr[1]), int(hdr[2]), int(hdr[3])
+        names = [f.readline().decode().strip() for _ in range(nc)]
+        data = np.frombuffer(f.read(), np.float32).reshape(h, w, nc)
+    return names, data

@@ -247,3 +247,11 @@ def smoke(outdir, grid=256, res=(1024, 1024), spp=2048, maxdepth=5, seed=7, homo
     path = os.path.join(outdir, "smoke.pbrt")
     open(path, "w").write(s)
     return path
+
+
+def as_gbuffer(path, coordinate_system="camera"):
+    """Rewrites a generated scene to use Film "gbuffer" (output name *.exr); returns the new path."""
+    s = open(path).read().replace('Film "rgb"', f'Film "gbuffer" "string coordinatesystem" "{coordinate_system}"').replace('"out.pfm"', '"out.exr"')
+    out = os.path.join(os.path.dirname(path), "gbuffer_" + os.path.basename(path))
+    open(out, "w").write(s)
+    return out

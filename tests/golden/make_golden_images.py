@@ -25,4 +25,11 @@ for name, path in jobs.items():
     if name in second_seed:
         subprocess.check_call([exe, "--quiet", "--seed", "1", "--outfile", os.path.join(out, name + "_seed1.pfm"), path])
     print(name, "done")
+# GBufferFilm: the oracle build writes "*.exr" outputs as a raw 25-channel dump (oracle/build_ref.py)
+gb = {"gbuffer_cornell_64x64_4spp_camera": (scenes.cornell(os.path.join(tmp, "g1"), res=(64, 64), spp=4), "camera"),
+      "gbuffer_heightfield64_64x64_4spp_world": (scenes.diffuse_heightfield(os.path.join(tmp, "g2"), n=64, res=(64, 64), spp=4), "world")}
+for name, (path, csys) in gb.items():
+    subprocess.check_call([exe, "--quiet", "--seed", "0", "--outfile", os.path.join(out, name + ".raw.exr"), scenes.as_gbuffer(path, csys)])
+    os.replace(os.path.join(out, name + ".raw.exr"), os.path.join(out, name + ".raw"))
+    print(name, "done")
 shutil.rmtree(tmp)

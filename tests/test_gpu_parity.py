@@ -202,6 +202,27 @@ def test_chaotic_configs_match_reference_statistically(E, tmp_path, name, gen, k
     assert float((img == ref0).all(axis=-1).mean()) > 0.02
 
 
+@pytest.mark.parametrize("name,gen,kw,csys", [("gbuffer_cornell_64x64_4spp_camera", "cornell", dict(res=(64, 64)), "camera"),
+                                              ("gbuffer_heightfield64_64x64_4spp_world", "diffuse_heightfield", dict(n=64, res=(64, 64)), "world")])
+def test_gbuffer_film_matches_reference_golden(E, tmp_path, name, gen, kw, csys):
+    """GBufferFilm (film.cpp:588-790): all 25 channels against the reference's own output.  Geometry channels (P, dzdx/dzdy from
+    the camera ray differentials, N, Ns, u, v) must be bit-identical; colour, albedo and variance within 1e-4."""
+    from pbrt_v4_b200 import scenes, imageio
+    path = scenes.as_gbuffer(getattr(scenes, gen)(str(tmp_path), spp=4, **kw), csys)
+    e = E.Engine(0)
+    e.load_pbrt(path, seed=0)
+    e.render(0, 4)
+    g = e.gbuffer()
+    e.close()
+    names, ref = imageio.read_raw_channels(os.path.join(ROOT, "tests", "golden", name + ".raw"))
+    assert names == E.Engine.GBUFFER_CHANNELS
+    for c, nm in enumerate(names):
+        if nm.split(".")[0] in ("P", "dzdx", "dzdy", "N", "Ns", "u", "v"):
+            assert (bits(g[..., c]) == bits(ref[..., c])).all(), nm
+        else:
+            assert np.sqrt(((g[..., c] - ref[..., c]) ** 2).mean()) < RMSE_TOL, nm
+
+
 @pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/bin/pbrt not on this box")
 def test_image_matches_live_reference_on_32k_triangle_heightfield(E, tmp_path):
     from pbrt_v4_b200 import scenes, imageio
