@@ -1051,7 +1051,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     int nQueues = 0;
     int qIndex[Q_CURSOR_CLOSEST];
     for (int q = 0; q < Q_CURSOR_CLOSEST; ++q) {
-        bool need = q == Q_RAY0 || q == Q_RAY1 || q == Q_ESCAPED || q == Q_HITLIGHT || (q == Q_MEDIUM && !e->media.empty()) ||
+        bool need = q == Q_RAY0 || q == Q_RAY1 || q == Q_ESCAPED || q == Q_HITLIGHT || ((q == Q_MEDIUM || q == Q_MSCATTER) && !e->media.empty()) ||
                     (q >= Q_MAT0 && e->materialPresent[q - Q_MAT0]);
         qIndex[q] = need ? nQueues++ : -1;
     }
@@ -1188,7 +1188,7 @@ static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int 
             for (int depth = 0; dynamic ? depth < 100000 : depth <= maxDepth; ++depth) {
                 LaunchResetDepth(rc, next, st); ++launches;
                 profBegin(0); LaunchTraceClosest(rc, cur, count, sms, st); ++launches; profEnd();
-                if (rc.nMedia > 0) { profBegin(2); LaunchSampleMedium(rc, next, sms, st); ++launches; profEnd(); }
+                if (rc.nMedia > 0) { profBegin(2); LaunchSampleMedium(rc, next, sms, st); launches += 2; profEnd(); }
                 if (rc.nInfinite > 0) { LaunchHandleEscaped(rc, sms, st); ++launches; }
                 if (e->haveAreaLights) { LaunchHandleEmissive(rc, sms, st); ++launches; }
                 if (!dynamic && depth == maxDepth) break;

@@ -232,44 +232,76 @@ BPT_HD MediumProps MediumSamplePoint(const DeviceMedium &m, const float *specPoo
     return mp;
 }
 
-// SampleT_maj (media.h:736-800).  callback(p, mp, sigma_maj, T_maj) -> bool (false stops the tracking)
+// SampleT_maj (media.h:736-800) as a resumable tracker: each Step() either fetches the next majorant segment or makes one
+// tentative collision, so that a warp can advance 32 independent rays in lock-step and refill the lanes that finish
+// (k_sample_medium).  Same operations in the same order as the reference's doubly nested loop.
+struct TMajTracker {
+    enum { CONTINUE = 0, EVENT = 1, DONE = 2 };
+    MajorantIter iter;
+    MajorantSegment seg;
+    Spec T_maj;
+    Pt3 o; Vec3 d;          // ray with normalised direction
+    float u, tMin, tEvent;
+    bool haveSeg;
+    BPT_HD void Init(const DeviceMedium &m, const float *specPool, Pt3 o_, Vec3 d_, float tMax, float u_, const Wavelengths &wl) {
+        tMax *= Length(d_);
+        d = Normalize(d_);
+        o = o_;
+        iter = MediumSampleRay(m, specPool, o, d, tMax, wl);
+        T_maj = Spec(1.f);
+        u = u_;
+        haveSeg = false;
+        tMin = tEvent = 0;
+    }
+    // EVENT: a tentative collision at *p (= ray(t)); T_maj holds the majorant transmittance since the previous event and
+    // seg.sigma_maj the majorant.  The caller evaluates the medium there and then calls AfterEvent() to go on, or stops.
+    // DONE: no more segments; T_maj is SampleT_maj's return value.
+    BPT_HD int Step(RNG &rng, Pt3 *p) {
+        if (!haveSeg) {
+            if (!iter.Next(&seg)) return DONE;
+            if (seg.sigma_maj[0] == 0) {
+                float dt = seg.tMax - seg.tMin;
+                if (IsInf_(dt)) dt = 3.402823466e+38f;
+                T_maj *= FastExpSpec(seg.sigma_maj * (-dt));
+                return CONTINUE;
+            }
+            tMin = seg.tMin;
+            haveSeg = true;
+            return CONTINUE;
+        }
+        float t = tMin + SampleExponential(u, seg.sigma_maj[0]);
+        u = rng.UniformFloat();
+        if (t < seg.tMax) {
+            T_maj *= FastExpSpec(seg.sigma_maj * (-(t - tMin)));
+            tEvent = t;
+            *p = o + d * t;
+            return EVENT;
+        }
+        float dt = seg.tMax - tMin;
+        if (IsInf_(dt)) dt = 3.402823466e+38f;
+        T_maj *= FastExpSpec(seg.sigma_maj * (-dt));
+        haveSeg = false;
+        return CONTINUE;
+    }
+    BPT_HD void AfterEvent() { T_maj = Spec(1.f); tMin = tEvent; }
+};
+
+// SampleT_maj (media.h:736-800).  callback(p, mp, sigma_maj, T_maj) -> bool (false stops the tracking and makes it return 1)
 template <typename F>
 BPT_HD Spec SampleT_maj(const DeviceMedium &m, const float *specPool, Pt3 o, Vec3 d, float tMax, float u, RNG &rng,
                         const Wavelengths &wl, F callback) {
-    tMax *= Length(d);
-    d = Normalize(d);
-    MajorantIter iter = MediumSampleRay(m, specPool, o, d, tMax, wl);
-    Spec T_maj(1.f);
-    bool done = false;
-    while (!done) {
-        MajorantSegment seg;
-        if (!iter.Next(&seg)) return T_maj;
-        if (seg.sigma_maj[0] == 0) {
-            float dt = seg.tMax - seg.tMin;
-            if (IsInf_(dt)) dt = 3.402823466e+38f;
-            T_maj *= FastExpSpec(seg.sigma_maj * (-dt));
-            continue;
-        }
-        float tMin = seg.tMin;
-        while (true) {
-            float t = tMin + SampleExponential(u, seg.sigma_maj[0]);
-            u = rng.UniformFloat();
-            if (t < seg.tMax) {
-                T_maj *= FastExpSpec(seg.sigma_maj * (-(t - tMin)));
-                Pt3 p = o + d * t;
-                MediumProps mp = MediumSamplePoint(m, specPool, p, wl);
-                if (!callback(p, mp, seg.sigma_maj, T_maj)) { done = true; break; }
-                T_maj = Spec(1.f);
-                tMin = t;
-            } else {
-                float dt = seg.tMax - tMin;
-                if (IsInf_(dt)) dt = 3.402823466e+38f;
-                T_maj *= FastExpSpec(seg.sigma_maj * (-dt));
-                break;
-            }
+    TMajTracker trk;
+    trk.Init(m, specPool, o, d, tMax, u, wl);
+    while (true) {
+        Pt3 p;
+        int st = trk.Step(rng, &p);
+        if (st == TMajTracker::DONE) return trk.T_maj;
+        if (st == TMajTracker::EVENT) {
+            MediumProps mp = MediumSamplePoint(m, specPool, p, wl);
+            if (!callback(p, mp, trk.seg.sigma_maj, trk.T_maj)) return Spec(1.f);
+            trk.AfterEvent();
         }
     }
-    return Spec(1.f);
 }
 
 }  // namespace bpt

@@ -16,8 +16,8 @@ namespace bpt {
 
 // queue ids inside RenderCtx::counts
 enum { Q_RAY0 = 0, Q_RAY1 = 1, Q_SHADOW = 2, Q_ESCAPED = 3, Q_HITLIGHT = 4, Q_MEDIUM = 5 /* MediumSampleQueue */,
-       Q_MAT0 = 6 /* + MaterialTag */,
-       Q_CURSOR_CLOSEST = Q_MAT0 + MAT_NTAGS, Q_CURSOR_SHADOW, Q_NCOUNTERS };
+       Q_MSCATTER = 6 /* MediumScatterQueue */, Q_MAT0 = 7 /* + MaterialTag */,
+       Q_CURSOR_CLOSEST = Q_MAT0 + MAT_NTAGS, Q_CURSOR_SHADOW, Q_CURSOR_MEDIUM, Q_NCOUNTERS };
 
 struct PathState {
     float4 *rayO;        // o.xyz, (unused)
