@@ -34,6 +34,7 @@ WORKLOADS = {
     # the other BASELINE.json configs (parity-test cases; runnable here for measured numbers)
     "mixed10m": dict(gen="mixed_envmap", kw=dict(n=2236, envres=2048, nmesh=64), res=(1920, 1080), spp=1024,
                      desc="configs[2]: 10.0M-triangle height field in 64 meshes, dielectric / rough conductor, 2048^2 HDR image light, 1920x1080, 1024 spp"),
+    "instanced20k": dict(gen="instanced", kw=dict(n_inst=20000, subdiv=3, material="coatedconductor"), res=(512, 512), spp=64, desc="20k instances (tuning size)"),
     "instanced100k": dict(gen="instanced", kw=dict(n_inst=100000, subdiv=3, material="coatedconductor"), res=(2048, 2048), spp=512,
                           desc="configs[3]: 100k instances of a 1280-triangle icosphere (two-level BVH), coated conductor, 2048x2048, 512 spp"),
     "smoke64": dict(gen="smoke", kw=dict(grid=64), res=(512, 512), spp=256, desc="64^3 smoke (tuning size)"),

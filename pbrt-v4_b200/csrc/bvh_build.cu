@@ -157,7 +157,7 @@ __global__ void collapse_kernel(const CollapseItem *__restrict__ items, int nIte
                                 const int *__restrict__ right, const int *__restrict__ first, const int *__restrict__ last,
                                 const float4 *__restrict__ nmin, const float4 *__restrict__ nmax, const int *__restrict__ sortedVals,
                                 const float4 *__restrict__ trisIn, float4 *nodesOut, float4 *trisOut, int *nodeCounter,
-                                int *triCounter, CollapseItem *nextItems, int *nextCount) {
+                                int *triCounter, CollapseItem *nextItems, int *nextCount, int leafMax) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nItems) return;
     CollapseItem it = items[idx];
@@ -223,7 +223,7 @@ __global__ void collapse_kernel(const CollapseItem *__restrict__ items, int nIte
         scale[a] = ldexpf(1.f, e);
     }
     int nInternal = 0, nTris = 0;
-    for (int k = 0; k < ne; ++k) { if (cnt[k] > BPT_LEAF_MAX) ++nInternal; else nTris += cnt[k]; }
+    for (int k = 0; k < ne; ++k) { if (cnt[k] > leafMax) ++nInternal; else nTris += cnt[k]; }
     int childBase = nInternal ? atomicAdd(nodeCounter, nInternal) : 0;
     int triBase = nTris ? atomicAdd(triCounter, nTris) : 0;
     unsigned imask = 0;
@@ -246,7 +246,7 @@ __global__ void collapse_kernel(const CollapseItem *__restrict__ items, int nIte
             while (qh < 255.f && org[a] + qh * scale[a] < hi3[a]) qh += 1.f;
             qlo[a][s] = (unsigned char)ql; qhi[a][s] = (unsigned char)qh;
         }
-        if (cnt[k] > BPT_LEAF_MAX) {
+        if (cnt[k] > leafMax) {
             imask |= 1u << s;
             meta[s] = (unsigned char)((1u << 5) | (24 + s));
             int pos = atomicAdd(nextCount, 1);
@@ -303,7 +303,8 @@ static bool dalloc(T **p, size_t n, char *err, cudaStream_t st = nullptr) {
     return true;
 }
 
-bool BuildWideBVH(const float4 *trisDev, int n, WideBVH *out, cudaStream_t stream, char *err) {
+bool BuildWideBVH(const float4 *trisDev, int n, WideBVH *out, cudaStream_t stream, char *err, int leafMax) {
+    if (leafMax <= 0 || leafMax > 3) leafMax = BPT_LEAF_MAX;
     out->nodes = nullptr; out->tris = nullptr; out->nNodes = 0; out->nTris = n; out->depth = 0;
     if (n <= 0) { snprintf(err, 256, "BuildWideBVH: empty triangle set"); return false; }
     const int B = 256;
@@ -348,7 +349,7 @@ bool BuildWideBVH(const float4 *trisDev, int n, WideBVH *out, cudaStream_t strea
         ++depth;
         CK(cudaMemsetAsync(counters + 2, 0, sizeof(int), stream));
         collapse_kernel<<<(nItems + 63) / 64, 64, 0, stream>>>(cur, nItems, n, left, right, first, last, nmin, nmax, svals, trisDev,
-                                                               out->nodes, out->tris, counters, counters + 1, nxt, counters + 2);
+                                                               out->nodes, out->tris, counters, counters + 1, nxt, counters + 2, leafMax);
         CK(cudaMemcpyAsync(hostCounters, counters, sizeof(hostCounters), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         nItems = hostCounters[2];

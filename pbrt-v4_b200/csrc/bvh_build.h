@@ -14,7 +14,10 @@ struct WideBVH {
 };
 
 // trisDev: 3 float4 per triangle in original order.  Returns false and fills err (256 bytes) on failure.
-bool BuildWideBVH(const float4 *trisDev, int n, WideBVH *out, cudaStream_t stream, char *err);
+// leafMax: subtrees of at most this many primitives become one leaf child (1..3; 0 = default 3).  The top-level BVH of an
+// instanced scene uses 1: entering an instance (ray transform + a second traversal) is far costlier than a triangle test, so
+// every instance gets its own child box.
+bool BuildWideBVH(const float4 *trisDev, int n, WideBVH *out, cudaStream_t stream, char *err, int leafMax = 0);
 void FreeWideBVH(WideBVH *b);
 
 }  // namespace bpt

@@ -975,7 +975,10 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         }
         if (dinst.empty()) return e->fail(BPT_ERR_INVALID, "scene has no geometry");
         ECK(e->dTlasPrims.upload(tlasPrims));
-        if (!BuildWideBVH(e->dTlasPrims.p, (int)dinst.size(), &e->bvh, e->stream, berr)) return e->fail(BPT_ERR_CUDA, berr);
+        {
+            const char *tl = std::getenv("BPT_TLAS_LEAF");
+            if (!BuildWideBVH(e->dTlasPrims.p, (int)dinst.size(), &e->bvh, e->stream, berr, tl ? std::atoi(tl) : 1)) return e->fail(BPT_ERR_CUDA, berr);
+        }
         ECK(e->dInstances.upload(dinst));
     }
     ECK(cudaStreamSynchronize(e->stream));
