@@ -102,3 +102,21 @@ def test_bench_reference_arm_is_wired():
     path = bench.make_scene("heightfield_small", spp=4, res=(64, 64))
     r = bench.run_reference_cpu(path, 1, 4, threads=2)
     assert r["kind"] == "reference" and r["value"] > 0
+
+
+def test_interleaved_band_row_map_is_a_partition():
+    """bpt_render_bands maps local row lr of part p to film row y0 + ((lr // band) * parts + p) * band + lr % band
+    (MapRow in csrc/wavefront.cuh, row count in RenderImpl): every film row must be produced exactly once, by the part
+    parallel.partition_bands assigns it to -- including a ragged last band."""
+    from pbrt_v4_b200.parallel import partition_bands
+    for (y0, y1, band, parts) in [(0, 1024, 16, 8), (0, 1080, 16, 8), (3, 77, 16, 3), (0, 10, 16, 4), (5, 6, 1, 2)]:
+        seen = {}
+        for p in range(parts):
+            n_mine = sum(min(band, y1 - y) for k, y in enumerate(range(y0, y1, band)) if k % parts == p)
+            rows = [y0 + ((lr // band) * parts + p) * band + lr % band for lr in range(n_mine)]
+            expect = [y for (a, b) in partition_bands(y1, parts, p, band=band, y0=y0) for y in range(a, b)]
+            assert rows == expect, (y0, y1, band, parts, p)
+            for y in rows:
+                assert y not in seen
+                seen[y] = p
+        assert sorted(seen) == list(range(y0, y1))
