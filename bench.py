@@ -118,19 +118,29 @@ def run_reference_cpu(scene_path, spp_lo, spp_hi, threads=None):
     if not os.path.exists(exe):
         return None
     threads = threads or os.cpu_count()
-    res = []
-    for spp in (spp_lo, spp_hi):
+
+    def run(spp):
         out_pfm = os.path.join(scene_dir(), f"ref_{os.getpid()}.pfm")
         t0 = time.time()
         p = subprocess.run([exe, "--quiet", "--stats", "--seed", "0", "--nthreads", str(threads), "--spp", str(spp), "--outfile", out_pfm,
                             scene_path], capture_output=True, text=True)
         dt = time.time() - t0
         m = re.search(r"Regular ray intersection tests\s+(\d+)", p.stdout + p.stderr)
-        rays = int(m.group(1)) if m else 0
-        res.append((dt, rays))
+        return dt, (int(m.group(1)) if m else 0)
+
+    # the delta of two runs cancels parse + BVH build; on a noisy host the small run can come out slower than the large one,
+    # so retry the pair, and as a last resort fall back to the large run's whole-run rate (a lower bound: it includes the build)
+    res = None
+    for _ in range(3):
+        res = [run(spp_lo), run(spp_hi)]
+        if res[1][0] - res[0][0] > 0.02 and res[1][1] > res[0][1]:
+            break
     d_t = res[1][0] - res[0][0]
     d_r = res[1][1] - res[0][1]
-    mrays = d_r / d_t / 1e6 if d_t > 0 else 0.0
+    if d_t > 0.02 and d_r > 0:
+        mrays = d_r / d_t / 1e6
+    else:
+        mrays = res[1][1] / max(res[1][0], 1e-9) / 1e6
     return {"value": mrays, "unit": "Mrays/s", "cores": threads, "kind": "reference",
             "sample": f"oracle/_ref/bin/pbrt (reference CPU VolPathIntegrator) on the bench scene at reduced film settings, "
                       f"delta between --spp {spp_lo} ({res[0][0]:.1f}s) and --spp {spp_hi} ({res[1][0]:.1f}s) runs, {d_r} rays"}
@@ -145,7 +155,7 @@ def reference_arm(args):
     vals = []
     base = None
     for i in range(args.warmup + args.steps):
-        base = run_reference_cpu(path, 4, 16)
+        base = run_reference_cpu(path, 16, 64)
         if base is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin/pbrt is not built (python oracle/build_ref.py)"}))
             return
@@ -155,7 +165,7 @@ def reference_arm(args):
     base["value"] = v
     line = {"metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "impl": "reference", "config": {"workload": WORKLOADS[args.workload]["desc"], "sample": "256x256 film, spp 4 -> 16 delta"},
+            "impl": "reference", "config": {"workload": WORKLOADS[args.workload]["desc"], "sample": "256x256 film, spp 16 -> 64 delta"},
             "cpu_baseline": base, "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -358,7 +368,7 @@ def main():
                              "roofline_mrays_per_gpu": peak * 1e9 / b_ray / 1e6}}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            cpu = run_reference_cpu(make_scene(args.workload, spp=4, res=(256, 256)), 4, 16)
+            cpu = run_reference_cpu(make_scene(args.workload, spp=4, res=(256, 256)), 16, 64)
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_seconds * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "msamples_per_s": msamples,
