@@ -297,6 +297,9 @@ BPT_D void TraceRay(const BVHView &bvh, Pt3 o, Vec3 d, float tMax, HitRec *rec, 
 #ifndef BPT_FETCH_CHUNK
 #define BPT_FETCH_CHUNK 0   // > 0: rays reserved from the queue cursor per atomic (single-level traversal)
 #endif
+#ifndef BPT_INST_GATE
+#define BPT_INST_GATE 1     // > 1: gate instance entry / exit on a warp vote (experiment, see TraversePersistentInst)
+#endif
 #ifndef BPT_PREFETCH
 #define BPT_PREFETCH 0      // (measured: +8 % slower, profiles/r01d_fold_prefetch_sweep.log) L1 prefetch of the next node / the first deferred triangle as soon as their addresses are known
 #endif
@@ -551,7 +554,22 @@ BPT_D void TraversePersistentInst(const BVHView &bvh, const DeviceInstance *inst
         bool act = rayIdx >= 0 && !done;
         if (!__any_sync(FULL, rayIdx >= 0)) break;
         // ---- enter the next instance of the pending top-level leaf group
-        if (act && inst < 0 && instGroup.y != 0) {
+#if BPT_INST_GATE > 1
+        // EXPERIMENT, off by default and not yet validated on the GPU (DESIGN.md "Known gaps"): entering / leaving an instance is
+        // ~150 instructions that ncu (profiles/r01o) shows running with 4.5 active lanes, so lanes wait at these two points until
+        // BPT_INST_GATE of them are there -- or until no lane of the warp can take a node step.  Only node-runnable lanes count as
+        // busy: they always make progress, so a waiting lane cannot wait forever (the first attempt also counted lanes that only
+        // held deferred triangles, whose flush in turn waited for the lanes waiting here: a deadlock).
+        const bool wantEnter = act && inst < 0 && instGroup.y != 0;
+        const bool wantLeave = act && inst >= 0 && (cur.y & 0xff000000u) == 0 && tail == head && sp > 0 && stack[sp - 1].x == SENT;
+        const bool nodeRunnable = act && !wantEnter && !wantLeave && (cur.y & 0xff000000u) != 0 && (tail - head) <= (unsigned)kTriBlock;
+        const bool anyBusy = __any_sync(FULL, nodeRunnable);
+        const bool enterNow = __popc(__ballot_sync(FULL, wantEnter)) >= BPT_INST_GATE || !anyBusy;
+        const bool leaveNow = __popc(__ballot_sync(FULL, wantLeave)) >= BPT_INST_GATE || !anyBusy;
+#else
+        const bool enterNow = true, leaveNow = true;
+#endif
+        if (act && inst < 0 && instGroup.y != 0 && enterNow) {
             unsigned ti = 31 - __clz(instGroup.y);
             instGroup.y &= ~(1u << ti);
             int id = __float_as_int(__ldg(bvh.tris + (size_t)(instGroup.x + ti) * 3).w);
@@ -631,7 +649,7 @@ BPT_D void TraversePersistentInst(const BVHView &bvh, const DeviceInstance *inst
         // ---- leave the instance / commit
         if (act && !finished) {
             bool nodeEmpty = (cur.y & 0xff000000u) == 0;
-            if (inst >= 0 && nodeEmpty && tail == head && sp > 0 && stack[sp - 1].x == SENT) {
+            if (leaveNow && inst >= 0 && nodeEmpty && tail == head && sp > 0 && stack[sp - 1].x == SENT) {
                 --sp;                      // sentinel
                 cur = stack[--sp];         // saved top-level node group
                 if (!instances[inst].identity) {
