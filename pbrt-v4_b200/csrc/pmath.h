@@ -10,6 +10,7 @@
 // The translation unit is compiled with -fmad=false (device) and -ffp-contract=off (host); every fused
 // multiply-add below is explicit.
 #pragma once
+#include "libm_exact.h"
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -105,15 +106,29 @@ BPT_HD bool IsInf_(float v) { return fabsf(v) == BPT_INFINITY; }
 #else
 #define BPT_DEF_T1(name, dfn, hfn) BPT_HD float name(float x) { return hfn(x); }
 #endif
+// BPT_EXACT_LIBM: use glibc's own float algorithms for sin / cos / log on the device (libm_exact.h, exhaustively equal to the
+// host libm; tests/tools/libm_exact_check.c).  Off until validated on a GPU (scripts/probe_math.py candidates 30-32).
+#ifndef BPT_EXACT_LIBM
+#define BPT_EXACT_LIBM 0
+#endif
+#if BPT_EXACT_LIBM && defined(__CUDA_ARCH__)
+BPT_HD float SinF(float x) { return bpt_exact_sinf(x); }
+BPT_HD float CosF(float x) { return bpt_exact_cosf(x); }
+#else
 BPT_DEF_T1(SinF, sin, sinf)
 BPT_DEF_T1(CosF, cos, cosf)
+#endif
 BPT_DEF_T1(TanF, tan, tanf)
 BPT_DEF_T1(ASinF, asin, asinf)
 BPT_DEF_T1(ACosF, acos, acosf)
 BPT_DEF_T1(ATanhF, atanh, atanhf)
 BPT_DEF_T1(CoshF, cosh, coshf)
 BPT_DEF_T1(ExpF, exp, expf)
+#if BPT_EXACT_LIBM && defined(__CUDA_ARCH__)
+BPT_HD float LogF(float x) { return bpt_exact_logf(x); }
+#else
 BPT_DEF_T1(LogF, log, logf)
+#endif
 BPT_HD float ATan2F(float y, float x) {
 #if defined(__CUDA_ARCH__)
     return (float)atan2((double)y, (double)x);

@@ -1121,6 +1121,10 @@ __global__ void k_probe_math(int fn, const float *x, const float *y, int n, floa
     case 21: r = sqrtf(a); break;
     case 22: r = a / b; break;
     case 23: r = (float)tan((double)a); break;
+    // glibc's own float algorithms restated in double arithmetic (libm_exact.h; exhaustively equal to the host libm on the CPU)
+    case 30: r = bpt_exact_sinf(a); break;
+    case 31: r = bpt_exact_cosf(a); break;
+    case 32: r = bpt_exact_logf(a); break;
     }
     out[i] = r;
 }

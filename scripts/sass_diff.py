@@ -14,7 +14,7 @@ def kernels(so):
             cur = m.group(1); out[cur] = []; continue
         m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?);", line)
         if cur and m:
-            out[cur].append(re.sub(r"\s+", " ", m.group(1)))
+            out[cur].append(re.sub(r"\.L_x_\d+", ".L", re.sub(r"\s+", " ", m.group(1))))   # label numbers are module-wide counters
     return out
 
 
