@@ -106,29 +106,31 @@ BPT_HD bool IsInf_(float v) { return fabsf(v) == BPT_INFINITY; }
 #else
 #define BPT_DEF_T1(name, dfn, hfn) BPT_HD float name(float x) { return hfn(x); }
 #endif
-// BPT_EXACT_LIBM: use glibc's own float algorithms for sin / cos / log on the device (libm_exact.h, exhaustively equal to the
-// host libm; tests/tools/libm_exact_check.c).  Off until validated on a GPU (scripts/probe_math.py candidates 30-32).
+// BPT_EXACT_LIBM: use glibc's own float algorithms on the device (libm_exact.h: sin, cos, log, exp, asin, acos, atan2, atanh, cosh
+// restated and exhaustively equal to the host libm, tests/tools/libm_exact_check.c).  Off until validated on a GPU
+// (scripts/probe_math.py candidates 30-38): with it every transcendental on the render path reproduces the reference's bits.
 #ifndef BPT_EXACT_LIBM
 #define BPT_EXACT_LIBM 0
 #endif
 #if BPT_EXACT_LIBM && defined(__CUDA_ARCH__)
 BPT_HD float SinF(float x) { return bpt_exact_sinf(x); }
 BPT_HD float CosF(float x) { return bpt_exact_cosf(x); }
+BPT_HD float ASinF(float x) { return bpt_exact_asinf(x); }
+BPT_HD float ACosF(float x) { return bpt_exact_acosf(x); }
+BPT_HD float ATanhF(float x) { return bpt_exact_atanhf(x); }
+BPT_HD float CoshF(float x) { return bpt_exact_coshf(x); }
+BPT_HD float ExpF(float x) { return bpt_exact_expf(x); }
+BPT_HD float LogF(float x) { return bpt_exact_logf(x); }
+BPT_HD float ATan2F(float y, float x) { return bpt_exact_atan2f(y, x); }
 #else
 BPT_DEF_T1(SinF, sin, sinf)
 BPT_DEF_T1(CosF, cos, cosf)
-#endif
-BPT_DEF_T1(TanF, tan, tanf)
 BPT_DEF_T1(ASinF, asin, asinf)
 BPT_DEF_T1(ACosF, acos, acosf)
 BPT_DEF_T1(ATanhF, atanh, atanhf)
 BPT_DEF_T1(CoshF, cosh, coshf)
 BPT_DEF_T1(ExpF, exp, expf)
-#if BPT_EXACT_LIBM && defined(__CUDA_ARCH__)
-BPT_HD float LogF(float x) { return bpt_exact_logf(x); }
-#else
 BPT_DEF_T1(LogF, log, logf)
-#endif
 BPT_HD float ATan2F(float y, float x) {
 #if defined(__CUDA_ARCH__)
     return (float)atan2((double)y, (double)x);
@@ -136,6 +138,8 @@ BPT_HD float ATan2F(float y, float x) {
     return atan2f(y, x);
 #endif
 }
+#endif
+BPT_DEF_T1(TanF, tan, tanf)
 BPT_HD float PowF(float x, float y) {
 #if defined(__CUDA_ARCH__)
     return (float)pow((double)x, (double)y);

@@ -1125,6 +1125,12 @@ __global__ void k_probe_math(int fn, const float *x, const float *y, int n, floa
     case 30: r = bpt_exact_sinf(a); break;
     case 31: r = bpt_exact_cosf(a); break;
     case 32: r = bpt_exact_logf(a); break;
+    case 33: r = bpt_exact_asinf(a); break;
+    case 34: r = bpt_exact_acosf(a); break;
+    case 35: r = bpt_exact_atan2f(a, b); break;
+    case 36: r = bpt_exact_atanhf(a); break;
+    case 37: r = bpt_exact_coshf(a); break;
+    case 38: r = bpt_exact_expf(a); break;
     }
     out[i] = r;
 }
