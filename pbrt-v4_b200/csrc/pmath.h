@@ -106,11 +106,12 @@ BPT_HD bool IsInf_(float v) { return fabsf(v) == BPT_INFINITY; }
 #else
 #define BPT_DEF_T1(name, dfn, hfn) BPT_HD float name(float x) { return hfn(x); }
 #endif
-// BPT_EXACT_LIBM: use glibc's own float algorithms on the device (libm_exact.h: sin, cos, log, exp, asin, acos, atan2, atanh, cosh
-// restated and exhaustively equal to the host libm, tests/tools/libm_exact_check.c).  Off until validated on a GPU
-// (scripts/probe_math.py candidates 30-38): with it every transcendental on the render path reproduces the reference's bits.
+// BPT_EXACT_LIBM (default on): glibc's own float algorithms on the device (libm_exact.h: sin, cos, log, exp, asin, acos, atan2,
+// atanh, cosh restated; exhaustively equal to the host libm on the CPU, tests/tools/libm_exact_check.c; 0 mismatches on the B200,
+// profiles/r01p; the GPU parity suite is green with it).  Every transcendental on the render path then reproduces the reference's
+// bits; BPT_EXACT_LIBM=0 restores "evaluate in FP64, round once" (0.06 - 20 % of arguments off by 1 ulp).
 #ifndef BPT_EXACT_LIBM
-#define BPT_EXACT_LIBM 0
+#define BPT_EXACT_LIBM 1
 #endif
 #if BPT_EXACT_LIBM && defined(__CUDA_ARCH__)
 BPT_HD float SinF(float x) { return bpt_exact_sinf(x); }
