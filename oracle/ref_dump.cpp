@@ -442,6 +442,68 @@ static void DumpGolden(const char *path) {
         b.f32("hg_in", hin);
         b.f32("hg_out", hout);
     }
+    // Many-light next-event estimation: BVHLightSampler over 200 one-triangle DiffuseAreaLights (Sample / PMF with surface and
+    // medium-like contexts) and DiffuseAreaLight::SampleLi / PDF_Li.  (appended last so that the vectors above keep their values)
+    {
+        Allocator alloc;
+        const int nL = 200;
+        std::vector<int> idx; std::vector<Point3f> P;
+        std::vector<float> verts, lparams;
+        for (int i = 0; i < nL; ++i) {
+            auto r = [&]() { return 2 * rng.Uniform<float>() - 1; };
+            Point3f c(2 * r(), 2 * r(), 2 * r());
+            for (int k = 0; k < 3; ++k) { P.push_back(c + 0.3f * Vector3f(r(), r(), r())); idx.push_back(3 * i + k); }
+        }
+        TriangleMesh *mesh = alloc.new_object<TriangleMesh>(Transform(), false, idx, P, std::vector<Vector3f>(), std::vector<Normal3f>(),
+                                                            std::vector<Point2f>(), std::vector<int>(), alloc);
+        for (int i = 0; i < 3 * nL; ++i) { verts.push_back(mesh->p[i].x); verts.push_back(mesh->p[i].y); verts.push_back(mesh->p[i].z); }
+        pstd::vector<Shape> tris = Triangle::CreateTriangles(mesh, alloc);
+        Spectrum Le = &RGBColorSpace::sRGB->illuminant;
+        std::vector<Light> lights;
+        std::map<const void *, int> lightIndex;
+        for (int i = 0; i < nL; ++i) {
+            float scale = 0.5f + 3 * rng.Uniform<float>();
+            bool twoSided = (i % 3) == 0;
+            lparams.push_back(scale); lparams.push_back(twoSided ? 1.f : 0.f);
+            Light l = alloc.new_object<DiffuseAreaLight>(Transform(), MediumInterface(), Le, scale, tris[i], nullptr, Image(alloc), nullptr, twoSided);
+            lightIndex[l.ptr()] = i;
+            lights.push_back(l);
+        }
+        BVHLightSampler sampler(lights, alloc);
+        std::vector<float> in, out;
+        for (int q = 0; q < 2000; ++q) {
+            auto r = [&]() { return 2 * rng.Uniform<float>() - 1; };
+            Point3f p(3 * r(), 3 * r(), 3 * r());
+            Normal3f n(0, 0, 0);
+            if (q % 4 != 0) n = Normal3f(Normalize(Vector3f(r(), r(), r())));
+            LightSampleContext ctx(Point3fi(p), n, n);
+            Float u = rng.Uniform<float>();
+            Point2f u2(rng.Uniform<float>(), rng.Uniform<float>());
+            SampledWavelengths lambda = SampledWavelengths::SampleVisible(rng.Uniform<float>());
+            int other = std::min(nL - 1, int(rng.Uniform<float>() * nL));
+            pstd::optional<SampledLight> sl = sampler.Sample(ctx, u);
+            in.insert(in.end(), {p.x, p.y, p.z, n.x, n.y, n.z, u, u2.x, u2.y, lambda[0], lambda[1], lambda[2], lambda[3], (float)other});
+            float rec[20] = {0};
+            rec[0] = -1;
+            if (sl) {
+                int li = lightIndex[sl->light.ptr()];
+                rec[0] = (float)li; rec[1] = sl->p; rec[2] = sampler.PMF(ctx, lights[li]);
+                pstd::optional<LightLiSample> ls = lights[li].SampleLi(ctx, u2, lambda, true);
+                if (ls) {
+                    rec[4] = 1; rec[5] = ls->L[0]; rec[6] = ls->L[1]; rec[7] = ls->L[3]; rec[8] = ls->wi.x; rec[9] = ls->wi.y; rec[10] = ls->wi.z;
+                    rec[11] = ls->pdf; rec[12] = ls->pLight.p().x; rec[13] = ls->pLight.p().y; rec[14] = ls->pLight.p().z;
+                    rec[15] = ls->pLight.n.x; rec[16] = ls->pLight.n.y; rec[17] = ls->pLight.n.z;
+                    rec[18] = lights[li].PDF_Li(ctx, ls->wi, true);
+                }
+            }
+            rec[3] = sampler.PMF(ctx, lights[other]);
+            out.insert(out.end(), rec, rec + 20);
+        }
+        b.f32("nee_verts", verts);
+        b.f32("nee_lights", lparams);
+        b.f32("nee_in", in);
+        b.f32("nee_out", out);
+    }
 }
 
 int main(int argc, char **argv) {
