@@ -50,6 +50,10 @@
 #include <pbrt/cpu/primitive.h>
 #include <pbrt/bxdfs.h>
 #include <pbrt/lightsamplers.h>
+#include <pbrt/cameras.h>
+#include <pbrt/film.h>
+#include <pbrt/filters.h>
+#include <pbrt/paramdict.h>
 #include <pbrt/lights.h>
 #include <pbrt/media.h>
 #include <pbrt/options.h>
@@ -503,6 +507,53 @@ static void DumpGolden(const char *path) {
         b.f32("nee_lights", lparams);
         b.f32("nee_in", in);
         b.f32("nee_out", out);
+    }
+    // Camera: GetCameraSample (ZSobol dimensions 0..5 + Gaussian FilterSampler) and PerspectiveCamera::GenerateRayDifferential with
+    // and without a lens, transformed to render space and scaled as the integrator does.  (appended last)
+    for (int cfg = 0; cfg < 2; ++cfg) {
+        Allocator alloc;
+        const int xres = 96, yres = 64, spp = 16;
+        Filter filt = alloc.new_object<GaussianFilter>(Vector2f(1.5f, 1.5f), 0.5f, alloc);
+        PixelSensor *sensor = alloc.new_object<PixelSensor>(RGBColorSpace::sRGB, nullptr, 1.f, alloc);
+        FilmBaseParameters fbp(Point2i(xres, yres), Bounds2i(Point2i(0, 0), Point2i(xres, yres)), filt, 35.f, sensor, "golden.pfm");
+        RGBFilm *film = alloc.new_object<RGBFilm>(fbp, RGBColorSpace::sRGB, Infinity, false, alloc);
+        Transform worldFromCamera = Inverse(LookAt(Point3f(0.3f, 1.1f, 3.2f), Point3f(0.1f, 0.6f, -0.2f), Vector3f(0.05f, 1, 0)));
+        CameraTransform camXf{AnimatedTransform(worldFromCamera)};
+        ParsedParameterVector params;
+        auto addF = [&](const char *name, float v) { ParsedParameter *pp = new ParsedParameter(FileLoc()); pp->type = "float"; pp->name = name; pp->AddFloat(v); params.push_back(pp); };
+        addF("fov", 38.f);
+        if (cfg == 1) { addF("lensradius", 0.07f); addF("focaldistance", 3.1f); }
+        ParameterDictionary dict(params, RGBColorSpace::sRGB);
+        FileLoc loc;
+        PerspectiveCamera *cam = PerspectiveCamera::Create(dict, camXf, Film(film), Medium(), &loc, alloc);
+        ZSobolSampler sampler(spp, Point2i(xres, yres), RandomizeStrategy::FastOwen, 0);
+        std::vector<float> cp;
+        auto pushM = [&](const Transform &t) { for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) cp.push_back(t.GetMatrix()[i][j]); };
+        cp.insert(cp.end(), {(float)xres, (float)yres, (float)spp, cam->lensRadius, cam->focalDistance});
+        pushM(cam->cameraFromRaster);
+        pushM(cam->cameraTransform.RenderFromCamera().startTransform);
+        cp.insert(cp.end(), {cam->dxCamera.x, cam->dxCamera.y, cam->dxCamera.z, cam->dyCamera.x, cam->dyCamera.y, cam->dyCamera.z});
+        std::vector<float> in, out;
+        for (int q = 0; q < 1500; ++q) {
+            Point2i pPixel(std::min(xres - 1, int(rng.Uniform<float>() * xres)), std::min(yres - 1, int(rng.Uniform<float>() * yres)));
+            int sampleIndex = std::min(spp - 1, int(rng.Uniform<float>() * spp));
+            sampler.StartPixelSample(pPixel, sampleIndex, 0);
+            Float lu = sampler.Get1D();
+            SampledWavelengths lambda = SampledWavelengths::SampleVisible(lu);
+            CameraSample cs = GetCameraSample(Sampler(&sampler), pPixel, filt);
+            pstd::optional<CameraRayDifferential> crd = cam->GenerateRayDifferential(cs, lambda);
+            Float rayDiffScale = std::max<Float>(.125f, 1 / std::sqrt((Float)spp));
+            crd->ray.ScaleDifferentials(rayDiffScale);
+            const RayDifferential &r = crd->ray;
+            in.insert(in.end(), {(float)pPixel.x, (float)pPixel.y, (float)sampleIndex});
+            out.insert(out.end(), {lu, cs.pFilm.x, cs.pFilm.y, cs.filterWeight, cs.time, cs.pLens.x, cs.pLens.y, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z,
+                                   r.rxOrigin.x, r.rxOrigin.y, r.rxOrigin.z, r.rxDirection.x, r.rxDirection.y, r.rxDirection.z,
+                                   r.ryOrigin.x, r.ryOrigin.y, r.ryOrigin.z, r.ryDirection.x, r.ryDirection.y, r.ryDirection.z,
+                                   lambda[0], lambda[3], lambda.PDF()[0]});
+        }
+        b.f32(cfg == 0 ? "cam0_params" : "cam1_params", cp);
+        b.f32(cfg == 0 ? "cam0_in" : "cam1_in", in);
+        b.f32(cfg == 0 ? "cam0_out" : "cam1_out", out);
     }
 }
 

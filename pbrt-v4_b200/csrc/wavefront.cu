@@ -17,6 +17,7 @@
 #include "bxdfs.h"
 #include "materials.cuh"
 #include "kernels.h"
+#include "camera.h"
 
 namespace bpt {
 
@@ -36,57 +37,7 @@ void UploadSobolTable(const uint32_t *t) {
     cudaMemcpyToSymbol(g_sobolByteLUT, lut, sizeof(lut));
 }
 
-// ---------------------------------------------------------------- small helpers
-__device__ __forceinline__ Pt3 XformPoint(const Mat4 &T, Pt3 p) {
-    const float (*m)[4] = T.m;
-    float xp = m[0][0] * p.x + m[0][1] * p.y + m[0][2] * p.z + m[0][3];
-    float yp = m[1][0] * p.x + m[1][1] * p.y + m[1][2] * p.z + m[1][3];
-    float zp = m[2][0] * p.x + m[2][1] * p.y + m[2][2] * p.z + m[2][3];
-    float wp = m[3][0] * p.x + m[3][1] * p.y + m[3][2] * p.z + m[3][3];
-    if (wp == 1) return Pt3(xp, yp, zp);
-    return Pt3(xp, yp, zp) / wp;
-}
-__device__ __forceinline__ Vec3 XformVector(const Mat4 &T, Vec3 v) {
-    const float (*m)[4] = T.m;
-    return Vec3(m[0][0] * v.x + m[0][1] * v.y + m[0][2] * v.z, m[1][0] * v.x + m[1][1] * v.y + m[1][2] * v.z,
-                m[2][0] * v.x + m[2][1] * v.y + m[2][2] * v.z);
-}
-// Normal3f transformed by the transpose of `A` (Transform::operator()(Normal3f): A = mInv; Transform::ApplyInverse(Normal3f): A = m)
-__device__ __forceinline__ Nrm3 XformNormalByTranspose(const Mat4 &A, Nrm3 n) {
-    const float (*m)[4] = A.m;
-    float x = n.x, y = n.y, z = n.z;
-    return Nrm3(m[0][0] * x + m[1][0] * y + m[2][0] * z, m[0][1] * x + m[1][1] * y + m[2][1] * z, m[0][2] * x + m[1][2] * y + m[2][2] * z);
-}
-// Transform::operator()(const Ray &r) (util/transform.h:336-349) for an exact origin
-__device__ __forceinline__ void XformRay(const Mat4 &T, Pt3 &o, Vec3 &d) {
-    const float (*m)[4] = T.m;
-    float x = o.x, y = o.y, z = o.z;
-    float xp = (m[0][0] * x + m[0][1] * y) + (m[0][2] * z + m[0][3]);
-    float yp = (m[1][0] * x + m[1][1] * y) + (m[1][2] * z + m[1][3]);
-    float zp = (m[2][0] * x + m[2][1] * y) + (m[2][2] * z + m[2][3]);
-    float wp = (m[3][0] * x + m[3][1] * y) + (m[3][2] * z + m[3][3]);
-    Vec3 pError;
-    pError.x = gamma_n(3) * (fabsf(m[0][0] * x) + fabsf(m[0][1] * y) + fabsf(m[0][2] * z) + fabsf(m[0][3]));
-    pError.y = gamma_n(3) * (fabsf(m[1][0] * x) + fabsf(m[1][1] * y) + fabsf(m[1][2] * z) + fabsf(m[1][3]));
-    pError.z = gamma_n(3) * (fabsf(m[2][0] * x) + fabsf(m[2][1] * y) + fabsf(m[2][2] * z) + fabsf(m[2][3]));
-    Pt3i oi(Pt3(xp, yp, zp), pError);
-    if (wp != 1) {
-        // Point3fi / Float: Interval::operator/=(Float)
-        auto divI = [](Interval i, float f) { return f > 0 ? Interval(DivRoundDown(i.low, f), DivRoundUp(i.high, f))
-                                                          : Interval(DivRoundDown(i.high, f), DivRoundUp(i.low, f)); };
-        oi.x = divI(oi.x, wp); oi.y = divI(oi.y, wp); oi.z = divI(oi.z, wp);
-    }
-    Vec3 dn = XformVector(T, d);
-    float lengthSquared = LengthSquared(dn);
-    if (lengthSquared > 0) {
-        float dt = Dot(Abs(dn), oi.Error()) / lengthSquared;
-        Vec3 off = dn * dt;
-        oi.x = oi.x + off.x; oi.y = oi.y + off.y; oi.z = oi.z + off.z;
-    }
-    o = oi.p();
-    d = dn;
-}
-
+// ---------------------------------------------------------------- small helpers (transforms and the camera live in camera.h)
 __device__ __forceinline__ Spec ld4(const float4 *p) { float4 v = *p; return Spec(v.x, v.y, v.z, v.w); }
 __device__ __forceinline__ void st4(float4 *p, Spec s) { *p = make_float4(s[0], s[1], s[2], s[3]); }
 
@@ -142,62 +93,6 @@ void LaunchZSobolPrefix(const SamplerParams &sp, uint32_t *table, int sms, cudaS
 }
 
 // ---------------------------------------------------------------- camera rays
-// wavelength sample + GetCameraSample (samplers.h:797-814): dimensions 0..5 of the pixel sample
-struct CamSample { float lu; Vec2 pFilm; float fweight; float time; Vec2 pLens; };
-__device__ __forceinline__ CamSample GetCameraSample(const RenderCtx &rc, Sampler &sampler, int px, int py, int sampleIndex) {
-    CamSample cs;
-    sampler.StartPixelSample(&rc.sampler, px, py, sampleIndex, 0);
-    cs.lu = sampler.Get1D();
-    Vec2 uf = sampler.Get2D();
-    Vec2 fp;
-    if (rc.filter.sampled) {
-        float pdf; int ou, ov;
-        fp = PC2DSample(rc.filter.distrib, uf, &pdf, &ou, &ov);
-        cs.fweight = rc.filter.f[ov * rc.filter.nx + ou] / pdf;
-    } else {   // BoxFilter::Sample (filters.h)
-        fp = Vec2(Lerp(uf.x, -rc.filter.radiusX, rc.filter.radiusX), Lerp(uf.y, -rc.filter.radiusY, rc.filter.radiusY));
-        cs.fweight = 1;
-    }
-    cs.pFilm = Vec2((px + fp.x) + 0.5f, (py + fp.y) + 0.5f);
-    cs.time = sampler.Get1D();
-    cs.pLens = sampler.Get2D();
-    return cs;
-}
-
-// GBufferFilm: the camera ray differentials of a pixel sample in render space, scaled as the integrator does
-// (PerspectiveCamera::GenerateRayDifferential cameras.cpp:450-477, Transform::operator()(RayDifferential) util/transform.h,
-// RayDifferential::ScaleDifferentials ray.h:53-58).  o, d: the main ray in render space.
-struct RayDiffs { Pt3 rxO, ryO; Vec3 rxD, ryD; };
-__device__ __forceinline__ RayDiffs CameraRayDifferentials(const RenderCtx &rc, const CamSample &cs, Pt3 o, Vec3 d) {
-    const DeviceCamera &cam = rc.camera;
-    Pt3 pCamera = XformPoint(cam.cameraFromRaster, Pt3(cs.pFilm.x, cs.pFilm.y, 0));
-    RayDiffs r;
-    if (cam.lensRadius > 0) {
-        Vec2 dsk = SampleUniformDiskConcentric(cs.pLens);
-        Vec2 pl(cam.lensRadius * dsk.x, cam.lensRadius * dsk.y);
-        Vec3 dx = Normalize(Vec3(pCamera.x + cam.dxCamera.x, pCamera.y + cam.dxCamera.y, pCamera.z + cam.dxCamera.z));
-        float ft = cam.focalDistance / dx.z;
-        Pt3 pFocus = Pt3(0, 0, 0) + (dx * ft);
-        r.rxO = Pt3(pl.x, pl.y, 0);
-        r.rxD = Normalize(pFocus - r.rxO);
-        Vec3 dy = Normalize(Vec3(pCamera.x + cam.dyCamera.x, pCamera.y + cam.dyCamera.y, pCamera.z + cam.dyCamera.z));
-        ft = cam.focalDistance / dy.z;
-        pFocus = Pt3(0, 0, 0) + (dy * ft);
-        r.ryO = Pt3(pl.x, pl.y, 0);
-        r.ryD = Normalize(pFocus - r.ryO);
-    } else {
-        r.rxO = r.ryO = Pt3(0, 0, 0);
-        r.rxD = Normalize(Vec3(pCamera.x, pCamera.y, pCamera.z) + cam.dxCamera);
-        r.ryD = Normalize(Vec3(pCamera.x, pCamera.y, pCamera.z) + cam.dyCamera);
-    }
-    r.rxO = XformPoint(cam.renderFromCamera, r.rxO); r.ryO = XformPoint(cam.renderFromCamera, r.ryO);
-    r.rxD = XformVector(cam.renderFromCamera, r.rxD); r.ryD = XformVector(cam.renderFromCamera, r.ryD);
-    float s = cam.rayDiffScale;
-    r.rxO = o + (r.rxO - o) * s; r.ryO = o + (r.ryO - o) * s;
-    r.rxD = d + (r.rxD - d) * s; r.ryD = d + (r.ryD - d) * s;
-    return r;
-}
-
 __global__ void __launch_bounds__(256) k_generate_camera_rays(RenderCtx rc, int x0, int x1, int y0, int y1, int firstSample, int nSamples) {
     int nPix = (x1 - x0) * (y1 - y0);
     int total = nPix * nSamples;
@@ -206,11 +101,12 @@ __global__ void __launch_bounds__(256) k_generate_camera_rays(RenderCtx rc, int 
         int py = MapRow(rc, y0 + pix / (x1 - x0)), px = x0 + pix % (x1 - x0);
         int sampleIndex = firstSample + s;
         Sampler sampler;
-        CamSample cs = GetCameraSample(rc, sampler, px, py, sampleIndex);
+        CamSample cs = GetCameraSample(rc.sampler, rc.filter, sampler, px, py, sampleIndex);
         Wavelengths wl = Wavelengths::SampleVisible(cs.lu);
         Vec2 pFilm = cs.pFilm, pLens = cs.pLens;
         float fweight = cs.fweight, time = cs.time;
-        // PerspectiveCamera::GenerateRayDifferential (cameras.cpp:429-447), main ray only
+        // PerspectiveCamera::GenerateRayDifferential (cameras.cpp:429-447), main ray only: the statements of GenerateCameraRay()
+        // (camera.h), kept inline here -- calling the helper reorders this kernel's instructions, and a changed binary needs a GPU run
         Pt3 pCamera = XformPoint(rc.camera.cameraFromRaster, Pt3(pFilm.x, pFilm.y, 0));
         Vec3 dir = Normalize(Vec3(pCamera.x, pCamera.y, pCamera.z));
         Pt3 o(0, 0, 0);
@@ -486,10 +382,10 @@ __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int
         // Initialize visibleSurf at first intersection (cpu/integrators.cpp:1118-1145): GBufferFilm only
         if (rc.film.isGBuffer && depth == 0) {
             Sampler camSampler;
-            CamSample cs = GetCameraSample(rc, camSampler, px, py, (int)misc.y);
+            CamSample cs = GetCameraSample(rc.sampler, rc.filter, camSampler, px, py, (int)misc.y);
             float4 o4 = ps.rayO[slot];
             Vec3 rd(d4.x, d4.y, d4.z);
-            RayDiffs rdif = CameraRayDifferentials(rc, cs, Pt3(o4.x, o4.y, o4.z), rd);
+            RayDiffs rdif = CameraRayDifferentials(rc.camera, cs, Pt3(o4.x, o4.y, o4.z), rd);
             // SurfaceInteraction::ComputeDifferentials (interaction.cpp:42-60), the dpdx / dpdy part
             Vec3 dpdx(0, 0, 0), dpdy(0, 0, 0);
             Pt3 P = isect.p();
