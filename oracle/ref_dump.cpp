@@ -555,6 +555,49 @@ static void DumpGolden(const char *path) {
         b.f32(cfg == 0 ? "cam0_in" : "cam1_in", in);
         b.f32(cfg == 0 ? "cam0_out" : "cam1_out", out);
     }
+    // Triangle::InteractionFromIntersection with per-vertex normals / uv (shading frame, error bounds, degenerate uv),
+    // four mesh configurations: (normals, uv, reverse orientation) = (1,1,0) (1,0,1) (0,1,0) (0,0,1).  (appended last)
+    for (int cfg = 0; cfg < 4; ++cfg) {
+        Allocator alloc;
+        const bool hasN = cfg < 2, hasUV = (cfg % 2) == 0, rev = (cfg % 2) == 1;
+        const int nTri = 64;
+        std::vector<int> idx; std::vector<Point3f> P; std::vector<Normal3f> N; std::vector<Point2f> UV;
+        for (int i = 0; i < nTri; ++i) {
+            auto r = [&]() { return 2 * rng.Uniform<float>() - 1; };
+            Point3f c(3 * r(), 3 * r(), 3 * r());
+            Point3f q[3];
+            for (int k = 0; k < 3; ++k) { q[k] = c + 0.8f * Vector3f(r(), r(), r()); P.push_back(q[k]); idx.push_back(3 * i + k); }
+            Normal3f ng = Normal3f(Normalize(Cross(q[0] - q[2], q[1] - q[2])));
+            for (int k = 0; k < 3; ++k) {
+                Normal3f nv = (i % 5 == 4) ? Normal3f(Normalize(Vector3f(r(), r(), r()))) : Normal3f(Normalize(Vector3f(ng) + 0.4f * Vector3f(r(), r(), r())));
+                N.push_back(nv);
+                UV.push_back((i % 7 == 6) ? Point2f(0.25f, 0.5f) : Point2f(rng.Uniform<float>(), rng.Uniform<float>()));   // every 7th triangle: degenerate uv
+            }
+        }
+        TriangleMesh *mesh = alloc.new_object<TriangleMesh>(Transform(), rev, idx, P, std::vector<Vector3f>(), hasN ? N : std::vector<Normal3f>(),
+                                                            hasUV ? UV : std::vector<Point2f>(), std::vector<int>(), alloc);
+        std::vector<float> md, in, out;
+        md.insert(md.end(), {(float)nTri, hasN ? 1.f : 0.f, hasUV ? 1.f : 0.f, (rev ^ mesh->transformSwapsHandedness) ? 1.f : 0.f});
+        for (int i = 0; i < 3 * nTri; ++i) {
+            md.insert(md.end(), {mesh->p[i].x, mesh->p[i].y, mesh->p[i].z});
+            if (hasN) md.insert(md.end(), {mesh->n[i].x, mesh->n[i].y, mesh->n[i].z}); else md.insert(md.end(), {0.f, 0.f, 0.f});
+            if (hasUV) md.insert(md.end(), {mesh->uv[i].x, mesh->uv[i].y}); else md.insert(md.end(), {0.f, 0.f});
+        }
+        for (int q = 0; q < 256; ++q) {
+            int tri = std::min(nTri - 1, int(rng.Uniform<float>() * nTri));
+            float b0 = rng.Uniform<float>(), b1 = rng.Uniform<float>() * (1 - b0), b2 = 1 - b0 - b1;
+            auto r = [&]() { return 2 * rng.Uniform<float>() - 1; };
+            Vector3f wo = Normalize(Vector3f(r(), r(), r()));
+            SurfaceInteraction si = Triangle::InteractionFromIntersection(mesh, tri, TriangleIntersection{b0, b1, b2, 1.f}, 0.f, wo);
+            in.insert(in.end(), {(float)tri, b0, b1, b2});
+            out.insert(out.end(), {si.pi.x.LowerBound(), si.pi.x.UpperBound(), si.pi.y.LowerBound(), si.pi.y.UpperBound(), si.pi.z.LowerBound(), si.pi.z.UpperBound(),
+                                   si.n.x, si.n.y, si.n.z, si.shading.n.x, si.shading.n.y, si.shading.n.z, si.uv.x, si.uv.y,
+                                   si.shading.dpdu.x, si.shading.dpdu.y, si.shading.dpdu.z});
+        }
+        b.f32(StringPrintf("triintr%d_mesh", cfg).c_str(), md);
+        b.f32(StringPrintf("triintr%d_in", cfg).c_str(), in);
+        b.f32(StringPrintf("triintr%d_out", cfg).c_str(), out);
+    }
 }
 
 int main(int argc, char **argv) {
