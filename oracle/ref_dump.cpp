@@ -55,6 +55,8 @@
 #include <pbrt/filters.h>
 #include <pbrt/paramdict.h>
 #include <pbrt/lights.h>
+#include <pbrt/materials.h>
+#include <pbrt/textures.h>
 #include <pbrt/media.h>
 #include <pbrt/options.h>
 #include <pbrt/samplers.h>
@@ -597,6 +599,46 @@ static void DumpGolden(const char *path) {
         b.f32(StringPrintf("triintr%d_mesh", cfg).c_str(), md);
         b.f32(StringPrintf("triintr%d_in", cfg).c_str(), in);
         b.f32(StringPrintf("triintr%d_out", cfg).c_str(), out);
+    }
+    // Material::GetBxDF parameter mapping (roughness remap, spectral eta / k sampling, reflectance -> k, termination of the
+    // secondary wavelengths by a dispersive interface): the BxDF members the reference ends up with.  (appended last)
+    {
+        Allocator alloc;
+        auto F = [&](float v) { return FloatTexture(alloc.new_object<FloatConstantTexture>(v)); };
+        auto S = [&](Spectrum sp) { return SpectrumTexture(alloc.new_object<SpectrumConstantTexture>(sp)); };
+        Spectrum cuEta = GetNamedSpectrum("metal-Cu-eta"), cuK = GetNamedSpectrum("metal-Cu-k"), bk7 = GetNamedSpectrum("glass-BK7");
+        Spectrum c15 = alloc.new_object<ConstantSpectrum>(1.5f), c07 = alloc.new_object<ConstantSpectrum>(0.7f), c0 = alloc.new_object<ConstantSpectrum>(0.f);
+        ConductorMaterial condSpectral(S(cuEta), S(cuK), nullptr, F(0.3f), F(0.05f), nullptr, nullptr, true);
+        ConductorMaterial condRefl(nullptr, nullptr, S(c07), F(0.2f), F(0.2f), nullptr, nullptr, false);
+        DielectricMaterial dielConst(F(0.f), F(0.f), c15, nullptr, nullptr, true);
+        DielectricMaterial dielDisp(F(0.1f), F(0.25f), bk7, nullptr, nullptr, true);
+        CoatedConductorMaterial coated(F(0.f), F(0.f), F(0.01f), c15, F(0.f), S(c0), F(0.f), F(0.f), S(cuEta), S(cuK), nullptr, nullptr, nullptr, true, 10, 1);
+        CoatedConductorMaterial coated2(F(0.2f), F(0.1f), F(0.05f), bk7, F(0.3f), S(c07), F(0.3f), F(0.15f), nullptr, nullptr, S(c07), nullptr, nullptr, false, 6, 2);
+        std::vector<float> in, out;
+        for (int q = 0; q < 64; ++q) {
+            Float u = rng.Uniform<float>();
+            in.push_back(u);
+            SurfaceInteraction si;
+            MaterialEvalContext ctx(si);
+            UniversalTextureEvaluator te;
+            auto lam = [&]() { return SampledWavelengths::SampleVisible(u); };
+            { SampledWavelengths l = lam(); ConductorBxDF bx = condSpectral.GetBxDF(te, ctx, l);
+              out.insert(out.end(), {bx.mfDistrib.alpha_x, bx.mfDistrib.alpha_y, bx.eta[0], bx.eta[3], bx.k[0], bx.k[3], l.PDF()[0], l.PDF()[3]}); }
+            { SampledWavelengths l = lam(); ConductorBxDF bx = condRefl.GetBxDF(te, ctx, l);
+              out.insert(out.end(), {bx.mfDistrib.alpha_x, bx.mfDistrib.alpha_y, bx.eta[0], bx.eta[3], bx.k[0], bx.k[3], l.PDF()[0], l.PDF()[3]}); }
+            { SampledWavelengths l = lam(); DielectricBxDF bx = dielConst.GetBxDF(te, ctx, l);
+              out.insert(out.end(), {bx.mfDistrib.alpha_x, bx.mfDistrib.alpha_y, bx.eta, l.PDF()[0], l.PDF()[3]}); }
+            { SampledWavelengths l = lam(); DielectricBxDF bx = dielDisp.GetBxDF(te, ctx, l);
+              out.insert(out.end(), {bx.mfDistrib.alpha_x, bx.mfDistrib.alpha_y, bx.eta, l.PDF()[0], l.PDF()[3]}); }
+            for (int c = 0; c < 2; ++c) {
+                SampledWavelengths l = lam(); CoatedConductorBxDF bx = (c ? coated2 : coated).GetBxDF(te, ctx, l);
+                out.insert(out.end(), {bx.top.mfDistrib.alpha_x, bx.top.mfDistrib.alpha_y, bx.top.eta, bx.bottom.mfDistrib.alpha_x, bx.bottom.mfDistrib.alpha_y,
+                                       bx.bottom.eta[0], bx.bottom.eta[3], bx.bottom.k[0], bx.bottom.k[3], bx.thickness, bx.g, bx.albedo[0], (float)bx.maxDepth,
+                                       (float)bx.nSamples, l.PDF()[0], l.PDF()[3]});
+            }
+        }
+        b.f32("mat_in", in);
+        b.f32("mat_out", out);
     }
 }
 
