@@ -111,6 +111,7 @@ typedef struct {
     const float *UV;              /* optional, 2*n_vertices */
     const int *indices;           /* 3*n_triangles */
     bpt_mat4 world_from_object;   /* CTM at the Shape directive */
+    bpt_mat4 object_from_world;   /* its tracked inverse (pbrt composes inverses analytically, util/transform.h:148-151); all zeros => computed numerically */
     int reverse_orientation;
     int material;                 /* index into the material array, -1 = "interface" */
     int area_light;               /* index into the area-light array, -1 = none */
@@ -120,12 +121,14 @@ typedef struct {
 
 typedef struct {
     int object_id;
-    bpt_mat4 world_from_instance;
+    bpt_mat4 world_from_instance;  /* CTM at the ObjectInstance directive */
+    bpt_mat4 instance_from_world;  /* its tracked inverse; all zeros => computed numerically */
 } bpt_instance;
 
 typedef struct {
     int type;                     /* BPT_LIGHT_UNIFORM_INFINITE | BPT_LIGHT_IMAGE_INFINITE */
-    bpt_mat4 world_from_light;
+    bpt_mat4 world_from_light;    /* CTM at the LightSource directive */
+    bpt_mat4 light_from_world;    /* its tracked inverse; all zeros => computed numerically */
     bpt_spectrum L;
     float scale;
     float illuminance;            /* <= 0: unused */

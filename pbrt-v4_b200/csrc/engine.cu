@@ -442,6 +442,10 @@ extern "C" int bpt_scene_set_camera_medium(bpt_engine *e, int medium) { if (!e) 
 static M4 ToM4(const bpt_mat4 &a) { M4 r; std::memcpy(r.m, a.m, sizeof(r.m)); return r; }
 static Mat4 ToMat4(const M4 &a) { Mat4 r; std::memcpy(r.m, a.m, sizeof(r.m)); return r; }
 static bool AllZero(const bpt_mat4 &a) { for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) if (a.m[i][j] != 0) return false; return true; }
+// A CTM as the reference holds it: the matrix with its analytically tracked inverse (Translate / Scale / Rotate / LookAt compose
+// their exact inverses, util/transform.h:148-151,  transform.cpp:36-117), so that products such as RenderFromObject() carry the
+// reference's mInv bit for bit.  Callers that have no tracked inverse pass zeros and get the numerical one.
+static Xform TrackedXform(const bpt_mat4 &m, const bpt_mat4 &inv) { return AllZero(inv) ? Xform(ToM4(m)) : Xform(ToM4(m), ToM4(inv)); }
 
 extern "C" int bpt_scene_commit(bpt_engine *e) {
     const bool timing = std::getenv("BPT_TIMING") != nullptr;
@@ -674,7 +678,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         const OwnedMesh &om = e->meshes[mi];
         if (om.m.object_id >= 0 && om.m.area_light >= 0) return e->fail(BPT_ERR_UNSUPPORTED, "area lights are not supported with object instancing");
         if (om.m.material >= (int)e->materials.size()) return e->fail(BPT_ERR_INVALID, "mesh material index out of range");
-        Xform renderFromObject(Mul(renderFromWorld.m, ToM4(om.m.world_from_object)));   // scene.h:475-477
+        Xform renderFromObject = renderFromWorld * TrackedXform(om.m.world_from_object, om.m.object_from_world);   // scene.h:475-477
         std::vector<Pt3> P(om.m.n_vertices);
         for (int v = 0; v < om.m.n_vertices; ++v) P[v] = renderFromObject(Pt3(om.P[3 * v], om.P[3 * v + 1], om.P[3 * v + 2]));
         DeviceMesh &dm = dmesh[mi];
@@ -759,7 +763,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     std::vector<ImgTables> imgTables;
     for (const OwnedLight &ol : e->lights) {
         DeviceLight dl{};
-        Xform renderFromLight(Mul(renderFromWorld.m, ToM4(ol.l.world_from_light)));
+        Xform renderFromLight = renderFromWorld * TrackedXform(ol.l.world_from_light, ol.l.light_from_world);
         dl.renderFromLight = ToMat4(renderFromLight.m); dl.lightFromRender = ToMat4(renderFromLight.mInv);
         float photometric = 0;
         for (int i = 0; i < kNLambda; ++i) photometric += cieY[i] * illum[i];
@@ -969,7 +973,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         for (const bpt_instance &in : e->instances) {
             if (!e->blas[in.object_id + 1].nodes) continue;   // empty definition
             // scene.cpp:375-393: renderFromInstance = RenderFromObject(0) * worldFromRender
-            Xform rfo(Mul(renderFromWorld.m, ToM4(in.world_from_instance)));
+            Xform rfo = renderFromWorld * TrackedXform(in.world_from_instance, in.instance_from_world);
             Xform renderFromInstance = rfo * worldFromRenderX;
             addInst(in.object_id + 1, &renderFromInstance);
         }

@@ -339,7 +339,7 @@ struct Frontend {
         if (pl.find("alpha")) { err = "alpha textures are not supported"; return false; }
         std::memset(&mr->m, 0, sizeof(mr->m));
         mr->m.n_vertices = (int)mr->P.size() / 3; mr->m.n_triangles = (int)mr->idx.size() / 3;
-        mr->m.world_from_object = ToB(gs.ctm.m);
+        mr->m.world_from_object = ToB(gs.ctm.m); mr->m.object_from_world = ToB(gs.ctm.mInv);
         mr->m.reverse_orientation = gs.reverseOrientation;
         mr->m.material = (materials[gs.material].type == BPT_MAT_INTERFACE) ? -1 : gs.material;
         mr->m.area_light = gs.areaLight;
@@ -566,7 +566,7 @@ bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::st
     if (d == "LightSource") {
         if (a.empty() || a[0] != "infinite") { err = "only \"infinite\" light sources are supported"; return false; }
         bpt_light l; std::memset(&l, 0, sizeof(l));
-        l.world_from_light = ToB(gs.ctm.m);
+        l.world_from_light = ToB(gs.ctm.m); l.light_from_world = ToB(gs.ctm.mInv);
         if (!getSpectrum(pl, "L", &l.L)) return false;
         l.scale = pl.f("scale", 1.f); l.illuminance = pl.f("illuminance", -1.f);
         std::string fn = pl.s("filename", "");
@@ -597,7 +597,7 @@ bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::st
     if (d == "ObjectEnd") { if (curObject < 0) { err = "unmatched ObjectEnd"; return false; } curObject = -1; gs = stack.back(); stack.pop_back(); return true; }
     if (d == "ObjectInstance") {
         if (a.empty() || !objectIds.count(a[0])) { err = "unknown object"; return false; }
-        bpt_instance in; in.object_id = objectIds[a[0]]; in.world_from_instance = ToB(gs.ctm.m); instances.push_back(in); return true;
+        bpt_instance in; in.object_id = objectIds[a[0]]; in.world_from_instance = ToB(gs.ctm.m); in.instance_from_world = ToB(gs.ctm.mInv); instances.push_back(in); return true;
     }
     err = "directive is not supported by this front end";
     (void)t;

@@ -42,11 +42,19 @@ def main():
     by = args[args.index("--by") + 1] if "--by" in args else "inner"
     name, ins = disasm(args[args.index("--mangled") + 1] if "--mangled" in args else kre,
                        os.path.abspath(args[args.index("--lib") + 1]) if "--lib" in args else None)
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre], capture_output=True, text=True).stdout
+    if rep.endswith(".ncu-rep"):
+        out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre], capture_output=True, text=True).stdout
+    else:   # exported on the GPU box: <prefix>.source.csv.gz holds every profiled launch
+        import gzip
+        out = gzip.open(rep + ".source.csv.gz", "rt").read()
     rows = list(csv.reader(out.splitlines()))
     secs = []; cur = None; hdr = None
     for r in rows:
-        if r and r[0] == "Kernel Name": cur = []; secs.append(cur); continue
+        if r and r[0] == "Kernel Name":
+            keep = rep.endswith(".ncu-rep") or re.search(kre, r[1] if len(r) > 1 else "")
+            cur = [] if keep else None
+            if keep: secs.append(cur)
+            continue
         if r and r[0] == "Address": hdr = r; continue
         if cur is not None and len(r) > 5: cur.append(r)
     sec = secs[launch]

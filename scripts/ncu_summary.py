@@ -1,7 +1,14 @@
 """Summarise an .ncu-rep: headline metrics per profiled launch + hot SASS regions (needs -lineinfo + --import-source)."""
 import csv, subprocess, sys, collections
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def page(rep, name):
+    """rep: an .ncu-rep, or the prefix of `<prefix>.raw.csv` / `<prefix>.source.csv.gz` exported on the GPU box (scripts/ncu_export.sh)"""
+    import gzip, os
+    if rep.endswith(".ncu-rep"):
+        return subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"], capture_output=True, text=True).stdout
+    f = rep + "." + name + ".csv"
+    return gzip.open(f + ".gz", "rt").read() if os.path.exists(f + ".gz") else open(f).read()
+raw = page(rep, "raw")
 rows = list(csv.reader(raw.splitlines()))
 hdr = rows[0]
 want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct",
@@ -15,7 +22,7 @@ for r in rows[2:]:
     for w in want:
         if w in hdr:
             print(f"  {w} = {r[hdr.index(w)]}  [{rows[1][hdr.index(w)]}]")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = page(rep, "source")
 rows = list(csv.reader(src.splitlines()))
 h = rows[1]
 iex, ith, ismp, isrc = h.index("Instructions Executed"), h.index("Avg. Threads Executed"), h.index("# Samples"), h.index("Source")
