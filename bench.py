@@ -111,61 +111,122 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def run_reference_cpu(scene_path, spp_lo, spp_hi, threads=None):
-    """Times the reference's CPU VolPathIntegrator (oracle/_ref/bin/pbrt) on the host cores: two runs at different spp so
-    that parse + BVH-build time cancels; rays = its own 'Regular ray intersection tests' statistic."""
+def _cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference_once(scene_path, spp, threads):
+    """One run of the reference's CPU VolPathIntegrator (oracle/_ref/bin/pbrt) on the bench scene file, film as in the file.
+    Rays = its own 'Regular ray intersection tests' statistic (VolPath uses Intersect for shadow rays too, SURVEY 8(d));
+    render seconds = the elapsed time its ProgressReporter prints for the render loop (util/progressreporter.cpp:140-146), which
+    excludes parsing and the BVH build; wall seconds = the whole process."""
     exe = os.path.join(ROOT, "oracle", "_ref", "bin", "pbrt")
-    if not os.path.exists(exe):
+    out_pfm = os.path.join(scene_dir(), f"ref_{os.getpid()}.pfm")
+    t0 = time.time()
+    p = subprocess.run([exe, "--stats", "--seed", "0", "--nthreads", str(threads), "--spp", str(spp), "--outfile", out_pfm, scene_path],
+                       capture_output=True, text=True)
+    wall = time.time() - t0
+    txt = p.stdout.replace("\r", "\n")
+    m = re.search(r"Regular ray intersection tests\s+(\d+)", txt + p.stderr)
+    rays = int(m.group(1)) if m else 0
+    done = re.findall(r"Rendering: \[\++\]\s+\(([0-9.]+)s\)", txt)
+    render_s = float(done[-1]) if done else 0.0
+    try:
+        os.remove(out_pfm)
+    except OSError:
+        pass
+    if p.returncode != 0 or rays == 0:
+        raise RuntimeError("reference pbrt failed: " + (p.stderr[-400:] or p.stdout[-400:]))
+    return {"spp": spp, "rays": rays, "render_s": render_s, "wall_s": wall}
+
+
+class ReferenceCPU:
+    """The reference's own CPU path on the box's host cores, on the bench workload's scene and FILM (same config as the GPU arm),
+    at a bounded sample count: the first call calibrates spp so that one render loop takes about `target_s` seconds (>= 5 s, so the
+    0.1 s resolution of the reference's own timer is <= 2 %)."""
+
+    def __init__(self, scene_path, full_spp, threads=None, target_s=7.0):
+        self.path, self.full_spp, self.target_s = scene_path, full_spp, target_s
+        self.threads = threads or os.cpu_count()
+        self.spp = None
+        self.calib = None
+
+    def available(self):
+        return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "bin", "pbrt"))
+
+    def calibrate(self):
+        c = run_reference_once(self.path, 16 if self.full_spp >= 16 else self.full_spp, self.threads)
+        rate = c["rays"] / max(c["render_s"], 0.05)            # rays / s, coarse
+        rays_per_spp = c["rays"] / c["spp"]
+        want = self.target_s * rate / rays_per_spp
+        spp = 4
+        while spp * 2 <= want and spp * 2 <= self.full_spp:
+            spp *= 2
+        self.spp, self.calib = spp, c
+        return spp
+
+    def step(self):
+        if self.spp is None:
+            self.calibrate()
+        r = run_reference_once(self.path, self.spp, self.threads)
+        # render-loop time from the reference's own timer; when it is too short to resolve, fall back to the wall clock of the
+        # process minus the calibration run's non-render part (parse + BVH build)
+        t = r["render_s"]
+        if t < 1.0:
+            t = max(r["wall_s"] - max(self.calib["wall_s"] - self.calib["render_s"], 0.0), 1e-3)
+        r["mrays"] = r["rays"] / t / 1e6
+        r["seconds"] = t
+        return r
+
+    def describe(self, runs):
+        ts = ", ".join("%.1f" % r["seconds"] for r in runs)
+        return (f"oracle/_ref/bin/pbrt (unmodified reference, CPU VolPathIntegrator), same scene and film as the GPU arm, --spp {self.spp} of "
+                f"{self.full_spp} (calibrated for ~{self.target_s:.0f} s per render loop), {len(runs)} run(s), render-loop seconds [{ts}] from the "
+                f"reference's own progress timer (parse and BVH build excluded), {runs[-1]['rays']} rays per run, {_cpu_model()}")
+
+
+def cpu_baseline(scene_path, full_spp, runs=3):
+    ref = ReferenceCPU(scene_path, full_spp)
+    if not ref.available():
         return None
-    threads = threads or os.cpu_count()
-
-    def run(spp):
-        out_pfm = os.path.join(scene_dir(), f"ref_{os.getpid()}.pfm")
-        t0 = time.time()
-        p = subprocess.run([exe, "--quiet", "--stats", "--seed", "0", "--nthreads", str(threads), "--spp", str(spp), "--outfile", out_pfm,
-                            scene_path], capture_output=True, text=True)
-        dt = time.time() - t0
-        m = re.search(r"Regular ray intersection tests\s+(\d+)", p.stdout + p.stderr)
-        return dt, (int(m.group(1)) if m else 0)
-
-    # the delta of two runs cancels parse + BVH build; on a noisy host the small run can come out slower than the large one,
-    # so retry the pair, and as a last resort fall back to the large run's whole-run rate (a lower bound: it includes the build)
-    res = None
-    for _ in range(3):
-        res = [run(spp_lo), run(spp_hi)]
-        if res[1][0] - res[0][0] > 0.02 and res[1][1] > res[0][1]:
-            break
-    d_t = res[1][0] - res[0][0]
-    d_r = res[1][1] - res[0][1]
-    if d_t > 0.02 and d_r > 0:
-        mrays = d_r / d_t / 1e6
-    else:
-        mrays = res[1][1] / max(res[1][0], 1e-9) / 1e6
-    return {"value": mrays, "unit": "Mrays/s", "cores": threads, "kind": "reference",
-            "sample": f"oracle/_ref/bin/pbrt (reference CPU VolPathIntegrator) on the bench scene at reduced film settings, "
-                      f"delta between --spp {spp_lo} ({res[0][0]:.1f}s) and --spp {spp_hi} ({res[1][0]:.1f}s) runs, {d_r} rays"}
+    rs = [ref.step() for _ in range(runs)]
+    vals = sorted(r["mrays"] for r in rs)
+    return {"value": vals[len(vals) // 2], "unit": "Mrays/s", "cores": ref.threads, "kind": "reference", "sample": ref.describe(rs),
+            "runs_mrays": [round(r["mrays"], 3) for r in rs], "spp": ref.spp}
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample of the same workload: same scene, 256x256 film region, low spp
-    path = make_scene(args.workload, spp=4, res=(256, 256))
-    vals = []
-    base = None
+    w = WORKLOADS[args.workload]
+    path = make_scene(args.workload, spp=args.spp or w["spp"])
+    ref = ReferenceCPU(path, args.spp or w["spp"])
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin/pbrt is not built (python oracle/build_ref.py)"}))
+        return
+    ref.calibrate()
+    runs = []
     for i in range(args.warmup + args.steps):
-        base = run_reference_cpu(path, 16, 64)
-        if base is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/bin/pbrt is not built (python oracle/build_ref.py)"}))
-            return
+        r = ref.step()
         if i >= args.warmup:
-            vals.append(base["value"])
+            runs.append(r)
+    vals = [r["mrays"] for r in runs]
     v = sum(vals) / len(vals)
-    base["value"] = v
+    secs = sum(r["seconds"] for r in runs) / len(runs)
+    base = {"value": v, "unit": "Mrays/s", "cores": ref.threads, "kind": "reference", "sample": ref.describe(runs),
+            "runs_mrays": [round(x, 3) for x in vals], "spp": ref.spp}
     line = {"metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "impl": "reference", "config": {"workload": WORKLOADS[args.workload]["desc"], "sample": "256x256 film, spp 16 -> 64 delta"},
+            "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": w["desc"], "spp": args.spp or w["spp"],
+                       "sample": f"same scene and {w['res'][0]}x{w['res'][1]} film, --spp {ref.spp} per step (bounded sample of the {args.spp or w['spp']} spp workload)"},
             "cpu_baseline": base, "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -368,7 +429,7 @@ def main():
                              "roofline_mrays_per_gpu": peak * 1e9 / b_ray / 1e6}}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            cpu = run_reference_cpu(make_scene(args.workload, spp=4, res=(256, 256)), 16, 64)
+            cpu = cpu_baseline(path, spp)
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_seconds * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "msamples_per_s": msamples,

@@ -1174,6 +1174,7 @@ static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int 
     auto profEnd = [&]() { if (profile) cudaEventRecord(prof.back().second.second, st); };
     const int sms = e->smCount;
     int launches = 0;
+    UploadSamplerConstants(rc.sampler, st);
     ECK(cudaEventRecord(e->ev0, st));
     // scanline bands so that a band of S samples fits in the path-state arrays
     int width = x1 - x0;
@@ -1367,6 +1368,7 @@ extern "C" int bpt_probe_sampler(bpt_engine *e, const int *pxy, const int *sidx,
     ECK(cudaMemcpy(a.p, pxy, sizeof(int) * 2 * (size_t)n, cudaMemcpyHostToDevice));
     ECK(cudaMemcpy(b.p, sidx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
     ECK(cudaMemcpy(c.p, dim, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+    UploadSamplerConstants(e->rc.sampler, e->stream);
     LaunchProbeSampler(e->rc.sampler, a.p, b.p, c.p, n, r1.p, r2.p, e->stream);
     ECK(cudaStreamSynchronize(e->stream));
     ECK(cudaMemcpy(o1, r1.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));

@@ -4,6 +4,7 @@
 
 namespace bpt {
 void UploadSobolTable(const uint32_t *t);
+void UploadSamplerConstants(const SamplerParams &sp, cudaStream_t st);
 void ConfigureKernels();
 void LaunchResetAll(const RenderCtx &rc, cudaStream_t st);
 void LaunchResetDepth(const RenderCtx &rc, int nextQ, cudaStream_t st);

@@ -113,16 +113,26 @@ BPT_HD bool IsInf_(float v) { return fabsf(v) == BPT_INFINITY; }
 #ifndef BPT_EXACT_LIBM
 #define BPT_EXACT_LIBM 1
 #endif
+// BPT_OUTLINE_LIBM: the restated routines as real functions (one copy per kernel module instead of one per call site): the
+// shading kernels are 20 k - 90 k instructions when everything is inlined, far beyond the instruction caches
+#ifndef BPT_OUTLINE_LIBM
+#define BPT_OUTLINE_LIBM 1
+#endif
+#if BPT_OUTLINE_LIBM && defined(__CUDA_ARCH__)
+#define BPT_LIBM_FN __device__ __noinline__
+#else
+#define BPT_LIBM_FN BPT_HD
+#endif
 #if BPT_EXACT_LIBM && defined(__CUDA_ARCH__)
-BPT_HD float SinF(float x) { return bpt_exact_sinf(x); }
-BPT_HD float CosF(float x) { return bpt_exact_cosf(x); }
-BPT_HD float ASinF(float x) { return bpt_exact_asinf(x); }
-BPT_HD float ACosF(float x) { return bpt_exact_acosf(x); }
-BPT_HD float ATanhF(float x) { return bpt_exact_atanhf(x); }
-BPT_HD float CoshF(float x) { return bpt_exact_coshf(x); }
-BPT_HD float ExpF(float x) { return bpt_exact_expf(x); }
-BPT_HD float LogF(float x) { return bpt_exact_logf(x); }
-BPT_HD float ATan2F(float y, float x) { return bpt_exact_atan2f(y, x); }
+BPT_LIBM_FN float SinF(float x) { return bpt_exact_sinf(x); }
+BPT_LIBM_FN float CosF(float x) { return bpt_exact_cosf(x); }
+BPT_LIBM_FN float ASinF(float x) { return bpt_exact_asinf(x); }
+BPT_LIBM_FN float ACosF(float x) { return bpt_exact_acosf(x); }
+BPT_LIBM_FN float ATanhF(float x) { return bpt_exact_atanhf(x); }
+BPT_LIBM_FN float CoshF(float x) { return bpt_exact_coshf(x); }
+BPT_LIBM_FN float ExpF(float x) { return bpt_exact_expf(x); }
+BPT_LIBM_FN float LogF(float x) { return bpt_exact_logf(x); }
+BPT_LIBM_FN float ATan2F(float y, float x) { return bpt_exact_atan2f(y, x); }
 #else
 BPT_DEF_T1(SinF, sin, sinf)
 BPT_DEF_T1(CosF, cos, cosf)

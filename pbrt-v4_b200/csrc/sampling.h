@@ -185,6 +185,20 @@ struct SamplerParams {
     int prefixDims, prefixW, prefixH, nLowDigits;
 };
 
+// BPT_OUTLINE_SAMPLER (device, the translation unit that owns the Sobol tables): ZSobol Get1D / Get2D as ONE real function
+// instead of seven inlined copies per shading kernel (ncu r02a: the shading and camera kernels stall on instruction fetch as
+// much as on memory -- 21 k and 7.5 k instructions, most of them inlined sampler and libm bodies).  The function reads the
+// sampler parameters from constant memory (c_sampler, set at every render call) and the per-dimension hashes Hash(dimension,
+// seed) from a constant table filled on the host with the same function.
+#ifndef BPT_OUTLINE_SAMPLER
+#define BPT_OUTLINE_SAMPLER 1
+#endif
+struct SamplerParams;
+#if defined(__CUDACC__) && defined(BPT_SOBOL_DEVICE_TABLE)
+__device__ __noinline__ float2 ZSobolOutlined(uint64_t mortonIndex, int pixel, int dimension, int nd);
+#endif
+constexpr int kDimHashTable = 128;   // Hash(dimension, seed) for dimension < kDimHashTable
+
 // One sampler object per path vertex evaluation: stateless function of (pixel, sampleIndex, dimension).
 struct Sampler {
     const SamplerParams *sp;
@@ -244,6 +258,11 @@ struct Sampler {
     }
     BPT_HD float Get1D() {
         if (sp->type == 1) { ++dimension; return rng.UniformFloat(); }
+#if BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
+        float2 r = ZSobolOutlined(mortonIndex, pixel, dimension, 1);
+        ++dimension;
+        return r.x;
+#endif
         uint64_t sampleIndex = GetSampleIndex();
         ++dimension;
         uint32_t sampleHash = (uint32_t)Hash_i32x2(dimension, sp->seed);
@@ -251,6 +270,11 @@ struct Sampler {
     }
     BPT_HD Vec2 Get2D() {
         if (sp->type == 1) { dimension += 2; float a = rng.UniformFloat(); float b = rng.UniformFloat(); return {a, b}; }
+#if BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
+        float2 r = ZSobolOutlined(mortonIndex, pixel, dimension, 2);
+        dimension += 2;
+        return {r.x, r.y};
+#endif
         uint64_t sampleIndex = GetSampleIndex();
         dimension += 2;
         uint64_t bits = Hash_i32x2(dimension, sp->seed);
@@ -258,6 +282,22 @@ struct Sampler {
                 SobolSampleRand(sampleIndex, 1, sp->randomize, (uint32_t)(bits >> 32))};
     }
 };
+
+#if defined(__CUDACC__) && defined(BPT_SOBOL_DEVICE_TABLE)
+__constant__ SamplerParams c_sampler;
+__constant__ uint64_t c_dimHash[kDimHashTable];
+__device__ __noinline__ float2 ZSobolOutlined(uint64_t mortonIndex, int pixel, int dimension, int nd) {
+    Sampler s;
+    s.sp = &c_sampler; s.mortonIndex = mortonIndex; s.pixel = pixel; s.dimension = dimension;
+    uint64_t sampleIndex = s.GetSampleIndex();
+    int dim = dimension + nd;
+    uint64_t bits = dim < kDimHashTable ? c_dimHash[dim] : Hash_i32x2(dim, c_sampler.seed);
+    float2 r;
+    r.x = SobolSampleRand(sampleIndex, 0, c_sampler.randomize, (uint32_t)bits);
+    r.y = nd == 2 ? SobolSampleRand(sampleIndex, 1, c_sampler.randomize, (uint32_t)(bits >> 32)) : 0.f;
+    return r;
+}
+#endif
 
 // ------------------------------------------------------------------ sampling routines
 BPT_HD float SampleVisibleWavelengths(float u) { return 538 - 138.888889f * ATanhF(0.85691062f - 1.82750197f * u); }

@@ -37,6 +37,15 @@ void UploadSobolTable(const uint32_t *t) {
     cudaMemcpyToSymbol(g_sobolByteLUT, lut, sizeof(lut));
 }
 
+// Per-render sampler constants of the outlined ZSobol function (sampling.h ZSobolOutlined): stream-ordered, so engines that share a
+// device may use different samplers
+void UploadSamplerConstants(const SamplerParams &sp, cudaStream_t st) {
+    static thread_local uint64_t hashes[kDimHashTable];
+    for (int d = 0; d < kDimHashTable; ++d) hashes[d] = Hash_i32x2(d, sp.seed);
+    cudaMemcpyToSymbolAsync(c_sampler, &sp, sizeof(SamplerParams), 0, cudaMemcpyHostToDevice, st);
+    cudaMemcpyToSymbolAsync(c_dimHash, hashes, sizeof(hashes), 0, cudaMemcpyHostToDevice, st);
+}
+
 // ---------------------------------------------------------------- small helpers (transforms and the camera live in camera.h)
 __device__ __forceinline__ Spec ld4(const float4 *p) { float4 v = *p; return Spec(v.x, v.y, v.z, v.w); }
 __device__ __forceinline__ void st4(float4 *p, Spec s) { *p = make_float4(s[0], s[1], s[2], s[3]); }
