@@ -162,6 +162,7 @@ typedef struct {
     /* per-kernel-class CUDA-event sums, filled only by a profiling render (bpt_render flags bit1) */
     double ms_trace_closest, ms_trace_shadow, ms_shade, ms_other;
     int launches_trace_closest, launches_trace_shadow;
+    double ms_medium;             /* k_sample_medium + k_medium_scatter (profiling render) */
 } bpt_stats;
 
 /* ---- lifecycle ---- */
@@ -201,6 +202,19 @@ int bpt_render(bpt_engine *e, int first_sample, int n_samples, const int *pixel_
  * (the scanline-band partition of SURVEY 8(e)); all of a rank's bands share the wavefront passes, which keeps the ray queues as
  * long as in a single-GPU render. */
 int bpt_render_bands(bpt_engine *e, int first_sample, int n_samples, int band_rows, int n_parts, int part, int flags);
+/* The same two calls on a caller-supplied CUDA stream (a cudaStream_t passed as void *; NULL = the engine's own stream) -- the
+ * `cudaStream_t` argument SURVEY 8(b) proposes; the reference issues everything on one stream with a single GPUWait() at the end
+ * (wavefront/integrator.cpp:485).  With BPT_RENDER_ASYNC in flags the call returns as soon as the kernels are enqueued (scenes
+ * without media / interface surfaces; those need a host-side queue-empty test per segment and synchronise as bpt_render does);
+ * bpt_sync() -- or any bpt_film_* / bpt_get_stats call -- waits for it. */
+#define BPT_RENDER_COUNT 1
+#define BPT_RENDER_PROFILE 2
+#define BPT_RENDER_ASYNC 4
+int bpt_render_stream(bpt_engine *e, int first_sample, int n_samples, const int *pixel_bounds, int flags, void *cuda_stream);
+int bpt_render_bands_stream(bpt_engine *e, int first_sample, int n_samples, int band_rows, int n_parts, int part, int flags, void *cuda_stream);
+int bpt_sync(bpt_engine *e);
+/* pixelsamples of the committed sampler (what `--spp` / the scene file asked for); negative before commit */
+int bpt_sampler_spp(const bpt_engine *e);
 /* GBufferFilm::GetImage (film.cpp:690-790): 25 floats per pixel of the full film, in the reference's channel order
  * R G B Albedo.{R,G,B} P.{X,Y,Z} dzdx dzdy N.{X,Y,Z} Ns.{X,Y,Z} u v Variance.{R,G,B} RelativeVariance.{R,G,B}.
  * Only valid when the film type is BPT_FILM_GBUFFER. */

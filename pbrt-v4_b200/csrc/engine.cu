@@ -72,6 +72,30 @@ struct DevBuf {
 
 }  // namespace
 
+// Large meshes are assembled on the device: the object-space vertices and the index buffer are uploaded as they come
+// (12 + 12 B per triangle for a grid mesh instead of the 48 B leaf-order-independent record) and this kernel applies
+// renderFromObject -- Transform::operator()(Point3f), util/transform.h, the same unfused float expression as Xform::operator() --
+// and writes the triangle pool records {p0 | mesh id, p1 | triangle index, p2 | class bits}.
+__global__ void k_assemble_triangles(const float *__restrict__ P, const int *__restrict__ idx, int nTris, Mat4 M, uint32_t meshId,
+                                     uint32_t cls, float4 *__restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTris) return;
+    const float (*m)[4] = M.m;
+    float4 r[3];
+    for (int k = 0; k < 3; ++k) {
+        int v = idx[3 * (size_t)t + k];
+        float x = P[3 * (size_t)v], y = P[3 * (size_t)v + 1], z = P[3 * (size_t)v + 2];
+        float xp = m[0][0] * x + m[0][1] * y + m[0][2] * z + m[0][3];
+        float yp = m[1][0] * x + m[1][1] * y + m[1][2] * z + m[1][3];
+        float zp = m[2][0] * x + m[2][1] * y + m[2][2] * z + m[2][3];
+        float wp = m[3][0] * x + m[3][1] * y + m[3][2] * z + m[3][3];
+        if (wp != 1) { xp = xp / wp; yp = yp / wp; zp = zp / wp; }
+        r[k] = make_float4(xp, yp, zp, 0.f);
+    }
+    r[0].w = __uint_as_float(meshId); r[1].w = __uint_as_float((uint32_t)t); r[2].w = __uint_as_float(cls);
+    out[3 * (size_t)t] = r[0]; out[3 * (size_t)t + 1] = r[1]; out[3 * (size_t)t + 2] = r[2];
+}
+
 struct bpt_engine {
     int device = 0;
     int smCount = 148;
@@ -94,6 +118,8 @@ struct bpt_engine {
     int cameraMedium = -1;
     // device
     DevBuf<float4> triPool;
+    DevBuf<float> rawP;              // staging of object-space vertices / indices of device-assembled meshes
+    DevBuf<int> rawIdx;
     DevBuf<DeviceMesh> dMeshes;
     DevBuf<int> indexPool;
     DevBuf<float> nPool, uvPool, specPool;
@@ -123,6 +149,7 @@ struct bpt_engine {
     DevBuf<ShadowTrItem> shadowTr;
     DevBuf<DeviceMedium> dMedia;
     DevBuf<uint32_t> zsPrefix;
+    long long zsKey[5] = {0, 0, 0, 0, 0};
     DevBuf<float4> visSurf;
     DevBuf<GBufferPixel> gbuf;
     DevBuf<float> gbufOut;
@@ -143,6 +170,9 @@ struct bpt_engine {
     int maxPaths = 0;
     bpt_stats st{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool pending = false;            // an asynchronous render (bpt_render_stream + BPT_RENDER_ASYNC) has not been waited for yet
+    int pendingLaunches = 0;
+    int committedSpp = 0;
 
     int fail(int code, const std::string &m) { err = m; return code; }
     int cudaFail(cudaError_t e, const char *what) { err = std::string(what) + ": " + cudaGetErrorString(e); return BPT_ERR_CUDA; }
@@ -640,7 +670,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     }
 
     // ---- meshes: transform to render space (TriangleMesh ctor util/mesh.cpp:25-70), build pools and lights
-    std::vector<float4> tri;
+    std::unique_ptr<float4[]> tri;   // host-assembled ranges only (untouched pages of the rest are never committed)
     std::vector<DeviceMesh> dmesh(e->meshes.size());
     std::vector<int> indexPool;
     std::vector<float> nPool, uvPool;
@@ -650,7 +680,12 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     for (const OwnedMesh &om : e->meshes) totalTris += om.m.n_triangles;
     if (totalTris == 0) return e->fail(BPT_ERR_INVALID, "scene has no triangles");
     if (totalTris > (size_t)1 << 30) return e->fail(BPT_ERR_INVALID, "too many triangles");
-    tri.reserve(3 * totalTris);
+    tri.reset(new float4[3 * totalTris]);
+    struct TriRange { size_t first; int count; bool device; size_t mesh; Mat4 M; uint32_t cls; };
+    std::vector<TriRange> triRanges;   // pool ranges in upload order: host-filled, or assembled by k_assemble_triangles
+    size_t triCursor = 0;
+    size_t devVerts = 0, devIdx = 0;
+    const int kDeviceAssembleMin = std::getenv("BPT_HOST_ASSEMBLE") ? (1 << 30) : 16384;
     e->haveAreaLights = false;
     const std::vector<float> &cieY = e->tables.F("cie_y");
     const std::vector<float> &illum = e->tables.F("srgb_illuminant");
@@ -661,7 +696,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     std::vector<size_t> meshOrder;
     std::vector<int> groupStart(nObjects + 2, 0);
     for (int g = -1; g < nObjects; ++g) {
-        groupStart[g + 1] = (int)tri.size();
+        groupStart[g + 1] = 0;
         for (size_t mi = 0; mi < e->meshes.size(); ++mi) if (e->meshes[mi].m.object_id == g) { meshOrder.push_back(mi); }
         // (group extents are fixed up after the loop below, once triangle counts are known)
     }
@@ -679,8 +714,10 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         if (om.m.object_id >= 0 && om.m.area_light >= 0) return e->fail(BPT_ERR_UNSUPPORTED, "area lights are not supported with object instancing");
         if (om.m.material >= (int)e->materials.size()) return e->fail(BPT_ERR_INVALID, "mesh material index out of range");
         Xform renderFromObject = renderFromWorld * TrackedXform(om.m.world_from_object, om.m.object_from_world);   // scene.h:475-477
-        std::vector<Pt3> P(om.m.n_vertices);
-        for (int v = 0; v < om.m.n_vertices; ++v) P[v] = renderFromObject(Pt3(om.P[3 * v], om.P[3 * v + 1], om.P[3 * v + 2]));
+        const bool deviceAssemble = om.m.area_light < 0 && om.m.n_triangles >= kDeviceAssembleMin;
+        std::vector<Pt3> P(deviceAssemble ? 0 : om.m.n_vertices);
+        if (!deviceAssemble)
+            for (int v = 0; v < om.m.n_vertices; ++v) P[v] = renderFromObject(Pt3(om.P[3 * v], om.P[3 * v + 1], om.P[3 * v + 2]));
         DeviceMesh &dm = dmesh[mi];
         dm.material = om.m.material;
         int matType = om.m.material < 0 ? MAT_INTERFACE : e->materials[om.m.material].m.type;
@@ -724,12 +761,19 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             e->haveAreaLights = true;
         }
         unsigned cls = (unsigned)matType | (emissive ? 0x100u : 0u);
+        triRanges.push_back(TriRange{triCursor, om.m.n_triangles, deviceAssemble, mi, ToMat4(renderFromObject.m), cls});
+        if (deviceAssemble) {
+            devVerts = std::max(devVerts, (size_t)om.m.n_vertices); devIdx = std::max(devIdx, (size_t)om.m.n_triangles);
+            triCursor += om.m.n_triangles;
+            continue;
+        }
         for (int t = 0; t < om.m.n_triangles; ++t) {
             Pt3 p0 = P[om.idx[3 * t]], p1 = P[om.idx[3 * t + 1]], p2 = P[om.idx[3 * t + 2]];
-            int gtri = (int)(tri.size() / 3);
-            tri.push_back(make_float4(p0.x, p0.y, p0.z, b2f((uint32_t)mi)));
-            tri.push_back(make_float4(p1.x, p1.y, p1.z, b2f((uint32_t)t)));
-            tri.push_back(make_float4(p2.x, p2.y, p2.z, b2f(cls)));
+            int gtri = (int)triCursor;
+            float4 *tp = &tri[3 * triCursor++];
+            tp[0] = make_float4(p0.x, p0.y, p0.z, b2f((uint32_t)mi));
+            tp[1] = make_float4(p1.x, p1.y, p1.z, b2f((uint32_t)t));
+            tp[2] = make_float4(p2.x, p2.y, p2.z, b2f(cls));
             if (emissive) {
                 DeviceLight dl{};
                 dl.type = LIGHT_DIFFUSE_AREA; dl.tri = gtri; dl.twoSided = al->a.two_sided; dl.LemitTable = Lrec.table;
@@ -893,7 +937,18 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         return e->fail(BPT_ERR_UNSUPPORTED, "media / interface surfaces are not supported together with object instancing");
 
     // ---- upload
-    ECK(e->triPool.upload(tri));
+    ECK(e->triPool.alloc(3 * totalTris));
+    if (devVerts) { ECK(e->rawP.alloc(3 * devVerts)); ECK(e->rawIdx.alloc(3 * devIdx)); }
+    for (const TriRange &r : triRanges) {
+        if (r.count == 0) continue;
+        if (!r.device) { ECK(cudaMemcpyAsync(e->triPool.p + 3 * r.first, tri.get() + 3 * r.first, sizeof(float4) * 3 * (size_t)r.count, cudaMemcpyHostToDevice, e->stream)); continue; }
+        const OwnedMesh &om = e->meshes[r.mesh];
+        // (pageable host memory: the copies return once staged, so the single staging pair can be reused mesh after mesh in stream order)
+        ECK(cudaMemcpyAsync(e->rawP.p, om.P.data(), sizeof(float) * 3 * (size_t)om.m.n_vertices, cudaMemcpyHostToDevice, e->stream));
+        ECK(cudaMemcpyAsync(e->rawIdx.p, om.idx.data(), sizeof(int) * 3 * (size_t)r.count, cudaMemcpyHostToDevice, e->stream));
+        k_assemble_triangles<<<(r.count + 255) / 256, 256, 0, e->stream>>>(e->rawP.p, e->rawIdx.p, r.count, r.M, (uint32_t)r.mesh, r.cls, e->triPool.p + 3 * r.first);
+    }
+    ECK(cudaStreamSynchronize(e->stream));
     ECK(e->dMeshes.upload(dmesh));
     ECK(e->indexPool.upload(indexPool));
     ECK(e->nPool.upload(nPool));
@@ -1114,9 +1169,14 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         int dims = std::min(6 + 7 * (e->integ.max_depth + 1), 64);
         size_t entries = (size_t)dims * fl.xres * fl.yres;
         if (enable && sp.type == 0 && 2 * sp.nBase4Digits <= 32 && sp.nBase4Digits > sp.nLowDigits && entries * 4 <= (size_t)2 << 30) {
+            // the table depends on (film size, digit counts, dimensions) only -- not on the seed, the scene or the sample index: a
+            // re-commit with the same film and sampler keeps it (it is 200 MB at 1024^2 and took 1/3 of a re-commit)
+            const long long key[5] = {fl.xres, fl.yres, dims, sp.nBase4Digits, sp.log2SamplesPerPixel};
+            const bool same = e->zsPrefix.p && e->zsPrefix.n == entries && std::memcmp(key, e->zsKey, sizeof(key)) == 0;
             ECK(e->zsPrefix.alloc(entries));
             sp.prefixDims = dims;
-            LaunchZSobolPrefix(sp, e->zsPrefix.p, e->smCount, e->stream);
+            if (!same) LaunchZSobolPrefix(sp, e->zsPrefix.p, e->smCount, e->stream);
+            std::memcpy(e->zsKey, key, sizeof(key));
             sp.prefix = e->zsPrefix.p;
         }
     }
@@ -1137,15 +1197,34 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     e->st.bytes_bvh_nodes = (uint64_t)e->bvh.nNodes * 80; e->st.bytes_bvh_tris = (uint64_t)e->bvh.nTris * 48;
     (void)t0; (void)t1;
     e->committed = true;
+    e->committedSpp = e->sampler.spp;
     return BPT_OK;
 }
 
 // ------------------------------------------------------------------------------------------- rendering
-static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int *pixel_bounds, int flags, int band_rows, int n_parts, int part) {
+// Waits for an asynchronous render and books its device time.
+static int Settle(bpt_engine *e) {
+    if (!e || !e->pending) return BPT_OK;
+    ECK(cudaSetDevice(e->device));
+    ECK(cudaEventSynchronize(e->ev1));
+    ECK(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->st.seconds_render += ms * 1e-3;
+    e->st.kernel_launches += e->pendingLaunches;
+    e->pending = false; e->pendingLaunches = 0;
+    return BPT_OK;
+}
+extern "C" int bpt_sync(bpt_engine *e) { return e ? Settle(e) : BPT_ERR_INVALID; }
+extern "C" int bpt_sampler_spp(const bpt_engine *e) { return e && e->committed ? e->committedSpp : BPT_ERR_INVALID; }
+
+static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int *pixel_bounds, int flags, int band_rows, int n_parts, int part,
+                      cudaStream_t userStream = nullptr) {
     if (!e) return BPT_ERR_INVALID;
     if (!e->committed) return e->fail(BPT_ERR_INVALID, "scene not committed");
     if (n_samples <= 0 || first_sample < 0) return e->fail(BPT_ERR_INVALID, "bad sample range");
     ECK(cudaSetDevice(e->device));
+    { int rcS = Settle(e); if (rcS != BPT_OK) return rcS; }
     RenderCtx &rc = e->rc;
     int x0 = rc.film.pbx0, x1 = rc.film.pbx1, y0 = rc.film.pby0, y1 = rc.film.pby1;
     if (pixel_bounds) {
@@ -1164,7 +1243,7 @@ static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int 
     if (x0 >= x1 || y0 >= y1) return BPT_OK;   // empty tile
     const bool count = flags & 1;
     const bool profile = flags & 2;
-    cudaStream_t st = e->stream;
+    cudaStream_t st = userStream ? userStream : e->stream;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof;   // (class, (start, stop))
     auto profBegin = [&](int cls) {
         if (!profile) return;
@@ -1196,7 +1275,7 @@ static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int 
             for (int depth = 0; dynamic ? depth < 100000 : depth <= maxDepth; ++depth) {
                 LaunchResetDepth(rc, next, st); ++launches;
                 profBegin(0); LaunchTraceClosest(rc, cur, count, sms, st); ++launches; profEnd();
-                if (rc.nMedia > 0) { profBegin(2); LaunchSampleMedium(rc, next, sms, st); launches += 2; profEnd(); }
+                if (rc.nMedia > 0) { profBegin(4); LaunchSampleMedium(rc, next, sms, st); launches += 2; profEnd(); }
                 if (rc.nInfinite > 0) { LaunchHandleEscaped(rc, sms, st); ++launches; }
                 if (e->haveAreaLights) { LaunchHandleEmissive(rc, sms, st); ++launches; }
                 if (!dynamic && depth == maxDepth) break;
@@ -1227,6 +1306,10 @@ static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int 
         }
     }
     ECK(cudaEventRecord(e->ev1, st));
+    if ((flags & 4) && !profile && rc.useTr == 0 && !e->raySort) {   // BPT_RENDER_ASYNC: no host round trip inside the loop above
+        e->pending = true; e->pendingLaunches = launches;
+        return BPT_OK;
+    }
     ECK(cudaStreamSynchronize(st));
     ECK(cudaGetLastError());
     float ms = 0;
@@ -1239,6 +1322,7 @@ static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int 
         if (pe.first == 0) { e->st.ms_trace_closest += pm; e->st.launches_trace_closest++; }
         else if (pe.first == 1) { e->st.ms_trace_shadow += pm; e->st.launches_trace_shadow++; }
         else if (pe.first == 3) e->st.ms_other += pm;
+        else if (pe.first == 4) e->st.ms_medium += pm;
         else e->st.ms_shade += pm;
         cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second);
     }
@@ -1252,10 +1336,18 @@ extern "C" int bpt_render_bands(bpt_engine *e, int first_sample, int n_samples, 
     if (band_rows <= 0) return e ? e->fail(BPT_ERR_INVALID, "band_rows must be positive") : BPT_ERR_INVALID;
     return RenderImpl(e, first_sample, n_samples, nullptr, flags, band_rows, n_parts, part);
 }
+extern "C" int bpt_render_stream(bpt_engine *e, int first_sample, int n_samples, const int *pixel_bounds, int flags, void *cuda_stream) {
+    return RenderImpl(e, first_sample, n_samples, pixel_bounds, flags, 0, 1, 0, (cudaStream_t)cuda_stream);
+}
+extern "C" int bpt_render_bands_stream(bpt_engine *e, int first_sample, int n_samples, int band_rows, int n_parts, int part, int flags, void *cuda_stream) {
+    if (band_rows <= 0) return e ? e->fail(BPT_ERR_INVALID, "band_rows must be positive") : BPT_ERR_INVALID;
+    return RenderImpl(e, first_sample, n_samples, nullptr, flags, band_rows, n_parts, part, (cudaStream_t)cuda_stream);
+}
 
 extern "C" int bpt_film_clear(bpt_engine *e) {
     if (!e || !e->committed) return BPT_ERR_INVALID;
     ECK(cudaSetDevice(e->device));
+    { int rcS = Settle(e); if (rcS != BPT_OK) return rcS; }
     ECK(cudaMemset(e->filmPixels.p, 0, sizeof(double4) * e->filmPixels.n));
     if (e->rc.gbuf) ECK(cudaMemset(e->gbuf.p, 0, sizeof(GBufferPixel) * e->gbuf.n));
     return BPT_OK;
@@ -1264,6 +1356,7 @@ extern "C" int bpt_film_resolve_gbuffer(bpt_engine *e, float *out25) {
     if (!e || !e->committed || !out25) return BPT_ERR_INVALID;
     if (!e->rc.gbuf) return e->fail(BPT_ERR_INVALID, "the film is not a GBufferFilm");
     ECK(cudaSetDevice(e->device));
+    { int rcS = Settle(e); if (rcS != BPT_OK) return rcS; }
     LaunchResolveGBuffer(e->filmPixels.p, e->gbuf.p, e->rc.film, e->gbufOut.p, e->smCount, e->stream);
     ECK(cudaMemcpyAsync(out25, e->gbufOut.p, sizeof(float) * e->gbufOut.n, cudaMemcpyDeviceToHost, e->stream));
     ECK(cudaStreamSynchronize(e->stream));
@@ -1272,39 +1365,45 @@ extern "C" int bpt_film_resolve_gbuffer(bpt_engine *e, float *out25) {
 extern "C" int bpt_stats_reset(bpt_engine *e) {
     if (!e || !e->committed) return BPT_ERR_INVALID;
     ECK(cudaSetDevice(e->device));
+    { int rcS = Settle(e); if (rcS != BPT_OK) return rcS; }
     ECK(cudaMemset(e->stats.p, 0, sizeof(unsigned long long) * 16));
     e->st.seconds_render = 0; e->st.kernel_launches = 0;
-    e->st.ms_trace_closest = e->st.ms_trace_shadow = e->st.ms_shade = e->st.ms_other = 0;
+    e->st.ms_trace_closest = e->st.ms_trace_shadow = e->st.ms_shade = e->st.ms_other = e->st.ms_medium = 0;
     e->st.launches_trace_closest = e->st.launches_trace_shadow = 0;
     return BPT_OK;
 }
 extern "C" int bpt_film_read(bpt_engine *e, double *out) {
     if (!e || !e->committed || !out) return BPT_ERR_INVALID;
     ECK(cudaSetDevice(e->device));
+    { int rcS = Settle(e); if (rcS != BPT_OK) return rcS; }
     ECK(cudaMemcpy(out, e->filmPixels.p, sizeof(double4) * e->filmPixels.n, cudaMemcpyDeviceToHost));
     return BPT_OK;
 }
 extern "C" int bpt_film_write(bpt_engine *e, const double *in) {
     if (!e || !e->committed || !in) return BPT_ERR_INVALID;
     ECK(cudaSetDevice(e->device));
+    { int rcS = Settle(e); if (rcS != BPT_OK) return rcS; }
     ECK(cudaMemcpy(e->filmPixels.p, in, sizeof(double4) * e->filmPixels.n, cudaMemcpyHostToDevice));
     return BPT_OK;
 }
 extern "C" int bpt_film_copy_to_device(bpt_engine *e, void *dst) {
     if (!e || !e->committed || !dst) return BPT_ERR_INVALID;
     ECK(cudaSetDevice(e->device));
+    { int rcS = Settle(e); if (rcS != BPT_OK) return rcS; }
     ECK(cudaMemcpy(dst, e->filmPixels.p, sizeof(double4) * e->filmPixels.n, cudaMemcpyDeviceToDevice));
     return BPT_OK;
 }
 extern "C" int bpt_film_copy_from_device(bpt_engine *e, const void *src) {
     if (!e || !e->committed || !src) return BPT_ERR_INVALID;
     ECK(cudaSetDevice(e->device));
+    { int rcS = Settle(e); if (rcS != BPT_OK) return rcS; }
     ECK(cudaMemcpy(e->filmPixels.p, src, sizeof(double4) * e->filmPixels.n, cudaMemcpyDeviceToDevice));
     return BPT_OK;
 }
 extern "C" int bpt_film_resolve(bpt_engine *e, float *rgb) {
     if (!e || !e->committed || !rgb) return BPT_ERR_INVALID;
     ECK(cudaSetDevice(e->device));
+    { int rcS = Settle(e); if (rcS != BPT_OK) return rcS; }
     LaunchResolveFilm(e->filmPixels.p, e->rc.film, e->filmRGB.p, e->smCount, e->stream);
     ECK(cudaStreamSynchronize(e->stream));
     ECK(cudaMemcpy(rgb, e->filmRGB.p, sizeof(float) * e->filmRGB.n, cudaMemcpyDeviceToHost));
@@ -1321,6 +1420,7 @@ extern "C" int bpt_get_stats(bpt_engine *e, bpt_stats *out) {
     if (e->committed) {
         unsigned long long h[16];
         ECK(cudaSetDevice(e->device));
+        { int rcS = Settle(e); if (rcS != BPT_OK) return rcS; }
         ECK(cudaMemcpy(h, e->stats.p, sizeof(h), cudaMemcpyDeviceToHost));
         e->st.camera_rays = h[0];
         e->st.indirect_rays = h[1] >= h[0] ? h[1] - h[0] : 0;

@@ -263,6 +263,12 @@ struct Frontend {
                 stride += tsz[t];
             }
             if ((size_t)nVerts * stride > nBytes) { err = path + ": truncated vertex data"; return false; }
+            const bool xyzOnly = stride == 12 && vp.size() == 3 && vp[0].off == 0 && vp[1].off == 4 && vp[2].off == 8 && vp[0].type == 0 &&
+                                 vp[1].type == 0 && vp[2].type == 0 && vp[0].dest == 0 && vp[1].dest == 1 && vp[2].dest == 2;
+            if (xyzOnly) {   // float x y z records: the vertex block is the P array
+                memcpy(mr->P.data(), q, 12 * (size_t)nVerts);
+                q += 12 * (size_t)nVerts;
+            } else
             for (int v = 0; v < nVerts; ++v, q += stride)
                 for (const VP &a : vp) {
                     float f = (float)load(q + a.off, a.type);
@@ -277,6 +283,17 @@ struct Frontend {
                 a.type = tcode(pp.isList ? pp.listItem : pp.type); a.cntType = pp.isList ? tcode(pp.listCount) : 0;
                 if (a.type < 0 || a.cntType < 0) { err = path + ": unknown PLY type in face element"; return false; }
                 fp.push_back(a);
+            }
+            if (fp.size() == 1 && fp[0].isList && fp[0].isIdx && fp[0].cntType == 4 && (fp[0].type == 2 || fp[0].type == 3)) {
+                // the common layout "list uchar int vertex_indices": 13-byte records, decoded without the generic per-property walk
+                if ((size_t)(end - q) < 13 * (size_t)nFaces) { err = path + ": truncated face data"; return false; }
+                mr->idx.resize(3 * (size_t)nFaces);
+                int *dst = mr->idx.data();
+                for (int f = 0; f < nFaces; ++f, q += 13, dst += 3) {
+                    if (q[0] != 3) { err = path + ": only triangle faces are supported (quads become bilinear patches in pbrt)"; return false; }
+                    memcpy(dst, q + 1, 12);
+                }
+                return true;
             }
             mr->idx.reserve(3 * (size_t)nFaces);
             for (int f = 0; f < nFaces; ++f)

@@ -22,7 +22,8 @@ class BptStats(C.Structure):
                 ("bvh_nodes", C.c_int), ("bvh_triangles", C.c_int), ("bvh_depth", C.c_int),
                 ("bytes_bvh_nodes", C.c_uint64), ("bytes_bvh_tris", C.c_uint64), ("kernel_launches", C.c_int),
                 ("ms_trace_closest", C.c_double), ("ms_trace_shadow", C.c_double), ("ms_shade", C.c_double),
-                ("ms_other", C.c_double), ("launches_trace_closest", C.c_int), ("launches_trace_shadow", C.c_int)]
+                ("ms_other", C.c_double), ("launches_trace_closest", C.c_int), ("launches_trace_shadow", C.c_int),
+                ("ms_medium", C.c_double)]
 
 
 EXPORTS = """bpt_create bpt_destroy bpt_last_error bpt_scene_begin bpt_scene_set_camera bpt_scene_set_film
@@ -30,7 +31,8 @@ bpt_scene_set_filter bpt_scene_set_sampler bpt_scene_set_integrator bpt_scene_se
 bpt_scene_add_mesh bpt_scene_add_instance bpt_scene_add_light bpt_scene_add_medium bpt_scene_set_camera_medium
 bpt_scene_commit bpt_load_pbrt bpt_load_pbrt_ex bpt_frontend_error bpt_render bpt_render_bands bpt_film_resolve_gbuffer bpt_film_clear bpt_stats_reset bpt_film_read bpt_film_write
 bpt_film_copy_to_device bpt_film_copy_from_device bpt_film_resolve bpt_film_dims bpt_get_stats bpt_trace_closest
-bpt_trace_any bpt_trace_closest_device bpt_probe_sampler bpt_probe_intersect_triangle""".split()
+bpt_trace_any bpt_trace_closest_device bpt_probe_sampler bpt_probe_intersect_triangle bpt_render_stream bpt_render_bands_stream
+bpt_sync bpt_sampler_spp""".split()
 
 
 def load_library():
@@ -51,6 +53,10 @@ def load_library():
     lib.bpt_load_pbrt_ex.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
     lib.bpt_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
     lib.bpt_render_bands.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.bpt_render_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_void_p]
+    lib.bpt_render_bands_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.bpt_sync.argtypes = [C.c_void_p]
+    lib.bpt_sampler_spp.argtypes = [C.c_void_p]
     lib.bpt_film_clear.argtypes = [C.c_void_p]
     lib.bpt_stats_reset.argtypes = [C.c_void_p]
     lib.bpt_film_read.argtypes = [C.c_void_p, C.c_void_p]
@@ -115,6 +121,20 @@ class Engine:
         if pixel_bounds is not None:
             pb = (C.c_int * 4)(*[int(v) for v in pixel_bounds])
         self._ck(self.lib.bpt_render(self.h, int(first_sample), int(n_samples), pb, (1 if count_stats else 0) | (2 if profile else 0)), "bpt_render")
+
+    def render_async(self, first_sample, n_samples, pixel_bounds=None, stream=0):
+        """Enqueue a render on `stream` (a cudaStream_t handle as int; 0 = the engine's stream) and return; sync() waits."""
+        pb = (C.c_int * 4)(*[int(v) for v in pixel_bounds]) if pixel_bounds is not None else None
+        self._ck(self.lib.bpt_render_stream(self.h, int(first_sample), int(n_samples), pb, 4, C.c_void_p(stream)), "bpt_render_stream")
+
+    def sync(self):
+        self._ck(self.lib.bpt_sync(self.h), "bpt_sync")
+
+    def sampler_spp(self):
+        v = self.lib.bpt_sampler_spp(self.h)
+        if v < 0:
+            raise BptError("bpt_sampler_spp: scene not committed")
+        return v
 
     def film_clear(self):
         self._ck(self.lib.bpt_film_clear(self.h), "bpt_film_clear")
@@ -210,11 +230,12 @@ class Engine:
 
 
 def render_pbrt(path, spp=0, seed=0, device=0):
-    """RenderWavefront equivalent: load scene, render all samples, return (image, stats)."""
+    """RenderWavefront equivalent (wavefront/wavefront.cpp:14-70): load the scene, render all of its samples (`spp` > 0 overrides
+    the file's pixelsamples like --spp), return (image, stats)."""
     e = Engine(device)
-    e.load_pbrt(path, spp=spp, seed=seed)
-    e.render(0, e.stats_spp if hasattr(e, "stats_spp") else spp, None)
-    img = e.image()
-    st = e.stats()
-    e.close()
-    return img, st
+    try:
+        e.load_pbrt(path, spp=spp, seed=seed)
+        e.render(0, e.sampler_spp(), None)
+        return e.image(), e.stats()
+    finally:
+        e.close()

@@ -162,7 +162,7 @@ def icosphere(subdiv):
     return np.array(V, dtype=np.float32), np.array(F, dtype=np.int32)
 
 
-def instanced(outdir, n_inst=100000, subdiv=3, res=(2048, 2048), spp=512, maxdepth=5, seed=99, material="coatedconductor"):
+def instanced(outdir, n_inst=100000, subdiv=3, res=(2048, 2048), spp=512, maxdepth=5, seed=99, material="coatedconductor", parts="trs"):
     """Config 4: one icosphere mesh (20*4^subdiv triangles; subdiv=3 -> 1280) as an object definition, `n_inst` instances with
     seeded random translate / rotate / scale in a 100 x 10 x 100 slab (scaled with n_inst), one quad light above."""
     os.makedirs(outdir, exist_ok=True)
@@ -185,8 +185,10 @@ def instanced(outdir, n_inst=100000, subdiv=3, res=(2048, 2048), spp=512, maxdep
         tx, ty, tz = rng.uniform(-ext, ext), rng.uniform(-0.1 * ext, 0.1 * ext), rng.uniform(-ext, ext)
         ang = rng.uniform(0, 360); ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
         sc = rng.uniform(0.35, 0.7) * (ext / 50.0) * 50.0 / (n_inst ** (1 / 3)) * 0.9
-        lines.append("AttributeBegin\n  Translate %.6f %.6f %.6f\n  Rotate %.5f %.6f %.6f %.6f\n  Scale %.6f %.6f %.6f\n  ObjectInstance \"ico\"\nAttributeEnd\n" %
-                     (tx, ty, tz, ang, ax[0], ax[1], ax[2], sc, sc, sc))
+        # `parts` selects the directives of the instance transform (parity bisection: translation / rotation / scale alone)
+        lines.append("AttributeBegin\n" + ("  Translate %.6f %.6f %.6f\n" % (tx, ty, tz) if "t" in parts else "") +
+                     ("  Rotate %.5f %.6f %.6f %.6f\n" % (ang, ax[0], ax[1], ax[2]) if "r" in parts else "") +
+                     ("  Scale %.6f %.6f %.6f\n" % (sc, sc, sc) if "s" in parts else "") + "  ObjectInstance \"ico\"\nAttributeEnd\n")
     s += "".join(lines)
     path = os.path.join(outdir, "instanced.pbrt")
     open(path, "w").write(s)

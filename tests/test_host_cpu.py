@@ -100,8 +100,16 @@ def test_bench_reference_arm_is_wired():
         pytest.skip("oracle/_ref not built")
     import bench
     path = bench.make_scene("heightfield_small", spp=4, res=(64, 64))
-    r = bench.run_reference_cpu(path, 1, 4, threads=2)
-    assert r["kind"] == "reference" and r["value"] > 0
+    ref = bench.ReferenceCPU(path, 4, threads=2, target_s=0.05)
+    assert ref.available()
+    r = ref.step()
+    assert ref.spp == 4 and r["rays"] > 0 and r["mrays"] > 0 and r["seconds"] > 0
+    # the whole arm, as the driver launches it: one JSON line on stdout
+    import json, subprocess, sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--workload", "heightfield_small"], capture_output=True, text=True, timeout=600)
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "reference" and line["e2e"]["h2d_bytes_per_step"] == 0
 
 
 def test_interleaved_band_row_map_is_a_partition():
