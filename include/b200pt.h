@@ -172,6 +172,15 @@ const char *bpt_last_error(const bpt_engine *e /* may be NULL for create errors 
 
 /* ---- scene description (copies everything) ---- */
 int bpt_scene_begin(bpt_engine *e);
+/* How the world_from_* matrices of meshes, instances, lights and media are to be read (the camera's are always world space).
+ * BPT_SPACE_WORLD (default): the CTM at the directive; the engine composes RenderFromObject() = renderFromWorld * CTM and
+ * RenderFromObject() * worldFromRender for instances exactly as BasicSceneBuilder does (scene.h:475-477, scene.cpp:375-393) --
+ * inverses recomputed from the product matrix as the reference does, so the *_from_world members are ignored there.
+ * BPT_SPACE_RENDER: the caller walks an already built BasicScene and passes ShapeSceneEntity::renderFromObject,
+ * InstanceSceneEntity::renderFromInstance, the light's / medium's renderFromObject with their inverses as they are. */
+#define BPT_SPACE_WORLD 0
+#define BPT_SPACE_RENDER 1
+int bpt_scene_set_transform_space(bpt_engine *e, int space);
 int bpt_scene_set_camera(bpt_engine *e, const bpt_camera *c);
 int bpt_scene_set_film(bpt_engine *e, const bpt_film *f);
 int bpt_scene_set_filter(bpt_engine *e, const bpt_filter *f);

@@ -14,6 +14,7 @@
 #include <vector>
 #include "../../include/b200pt.h"
 #include "bvh_build.h"
+#include "scene_xforms.h"
 #include "kernels.h"
 #include "lightbvh.h"
 #include "tables.h"
@@ -116,6 +117,7 @@ struct bpt_engine {
     std::vector<OwnedLight> lights;
     std::vector<OwnedMedium> media;
     int cameraMedium = -1;
+    int space = BPT_SPACE_WORLD;     // how the world_from_* members of the scene calls are to be read (bpt_scene_set_transform_space)
     // device
     DevBuf<float4> triPool;
     DevBuf<float> rawP;              // staging of object-space vertices / indices of device-assembled meshes
@@ -377,7 +379,7 @@ extern "C" const char *bpt_last_error(const bpt_engine *e) { return e ? e->err.c
 extern "C" int bpt_scene_begin(bpt_engine *e) {
     if (!e) return BPT_ERR_INVALID;
     e->materials.clear(); e->areaLights.clear(); e->meshes.clear(); e->instances.clear(); e->lights.clear(); e->media.clear();
-    e->haveCam = e->haveFilm = false; e->committed = false; e->cameraMedium = -1;
+    e->haveCam = e->haveFilm = false; e->committed = false; e->cameraMedium = -1; e->space = BPT_SPACE_WORLD;
     return BPT_OK;
 }
 extern "C" int bpt_scene_set_camera(bpt_engine *e, const bpt_camera *c) {
@@ -466,16 +468,15 @@ extern "C" int bpt_scene_add_medium(bpt_engine *e, const bpt_medium *m) {
     o.m.density = nullptr;
     return BPT_OK;
 }
+extern "C" int bpt_scene_set_transform_space(bpt_engine *e, int space) {
+    if (!e || (space != BPT_SPACE_WORLD && space != BPT_SPACE_RENDER)) return BPT_ERR_INVALID;
+    e->space = space;
+    return BPT_OK;
+}
 extern "C" int bpt_scene_set_camera_medium(bpt_engine *e, int medium) { if (!e) return BPT_ERR_INVALID; e->cameraMedium = medium; return BPT_OK; }
 
 // ------------------------------------------------------------------------------------------- commit
-static M4 ToM4(const bpt_mat4 &a) { M4 r; std::memcpy(r.m, a.m, sizeof(r.m)); return r; }
 static Mat4 ToMat4(const M4 &a) { Mat4 r; std::memcpy(r.m, a.m, sizeof(r.m)); return r; }
-static bool AllZero(const bpt_mat4 &a) { for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) if (a.m[i][j] != 0) return false; return true; }
-// A CTM as the reference holds it: the matrix with its analytically tracked inverse (Translate / Scale / Rotate / LookAt compose
-// their exact inverses, util/transform.h:148-151,  transform.cpp:36-117), so that products such as RenderFromObject() carry the
-// reference's mInv bit for bit.  Callers that have no tracked inverse pass zeros and get the numerical one.
-static Xform TrackedXform(const bpt_mat4 &m, const bpt_mat4 &inv) { return AllZero(inv) ? Xform(ToM4(m)) : Xform(ToM4(m), ToM4(inv)); }
 
 extern "C" int bpt_scene_commit(bpt_engine *e) {
     const bool timing = std::getenv("BPT_TIMING") != nullptr;
@@ -496,18 +497,11 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     std::string serr;
 
     // ---- camera transforms (BasicSceneBuilder::Camera scene.cpp:138-156, CameraTransform cameras.cpp, rendering space = CameraWorld)
-    Xform cameraFromWorld;
-    {
-        M4 cfw = ToM4(e->cam.camera_from_world), wfc;
-        if (AllZero(e->cam.world_from_camera)) { if (!Inverse(cfw, &wfc)) return e->fail(BPT_ERR_INVALID, "singular camera transform"); }
-        else wfc = ToM4(e->cam.world_from_camera);
-        cameraFromWorld = Xform(cfw, wfc);
-    }
-    Xform worldFromCamera = Inverse(cameraFromWorld);
-    Pt3 pCamera = worldFromCamera(Pt3(0, 0, 0));
-    Xform worldFromRender = Translate(Vec3(pCamera.x, pCamera.y, pCamera.z));
-    Xform renderFromWorld = Inverse(worldFromRender);
-    Xform renderFromCamera = renderFromWorld * worldFromCamera;
+    CameraSpaces spaces;
+    if (!ResolveCameraSpaces(e->cam, &spaces)) return e->fail(BPT_ERR_INVALID, "singular camera transform");
+    const int space = e->space;
+    const Xform &worldFromRender = spaces.worldFromRender, &renderFromWorld = spaces.renderFromWorld, &renderFromCamera = spaces.renderFromCamera;
+    (void)renderFromWorld;
 
     // ---- film / filter / sensor (film.cpp FilmBaseParameters, PixelSensor::Create, RGBFilm ctor)
     const bpt_film &fl = e->film;
@@ -713,7 +707,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         const OwnedMesh &om = e->meshes[mi];
         if (om.m.object_id >= 0 && om.m.area_light >= 0) return e->fail(BPT_ERR_UNSUPPORTED, "area lights are not supported with object instancing");
         if (om.m.material >= (int)e->materials.size()) return e->fail(BPT_ERR_INVALID, "mesh material index out of range");
-        Xform renderFromObject = renderFromWorld * TrackedXform(om.m.world_from_object, om.m.object_from_world);   // scene.h:475-477
+        Xform renderFromObject = ResolveRenderFromObject(space, spaces, om.m.world_from_object, om.m.object_from_world);   // scene.h:475-477
         const bool deviceAssemble = om.m.area_light < 0 && om.m.n_triangles >= kDeviceAssembleMin;
         std::vector<Pt3> P(deviceAssemble ? 0 : om.m.n_vertices);
         if (!deviceAssemble)
@@ -807,7 +801,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     std::vector<ImgTables> imgTables;
     for (const OwnedLight &ol : e->lights) {
         DeviceLight dl{};
-        Xform renderFromLight = renderFromWorld * TrackedXform(ol.l.world_from_light, ol.l.light_from_world);
+        Xform renderFromLight = ResolveRenderFromObject(space, spaces, ol.l.world_from_light, ol.l.light_from_world);
         dl.renderFromLight = ToMat4(renderFromLight.m); dl.lightFromRender = ToMat4(renderFromLight.mInv);
         float photometric = 0;
         for (int i = 0; i < kNLambda; ++i) photometric += cieY[i] * illum[i];
@@ -907,11 +901,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             (k == 0 ? dm.sigmaA : dm.sigmaS) = spool.addDense(v);
         }
         if (dm.type == MEDIUM_GRID) {
-            M4 wfm = ToM4(om.m.world_from_medium), mfw = ToM4(om.m.medium_from_world);
-            bool haveInv = false;
-            for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) if (mfw[a][b] != 0) haveInv = true;
-            Xform worldFromMedium = haveInv ? Xform(wfm, mfw) : Xform(wfm);
-            Xform renderFromMedium = renderFromWorld * worldFromMedium;   // RenderFromObject() (scene.h:475-477)
+            Xform renderFromMedium = ResolveRenderFromObject(space, spaces, om.m.world_from_medium, om.m.medium_from_world);   // RenderFromObject() (scene.h:475-477)
             dm.mInv = ToMat4(renderFromMedium.mInv);
             for (int k = 0; k < 3; ++k) { dm.bmin[k] = om.m.bounds[k]; dm.bmax[k] = om.m.bounds[3 + k]; }
             const int nx = om.m.nx, ny = om.m.ny, nz = om.m.nz;
@@ -1024,12 +1014,10 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             if (!BuildWideBVH(e->triPool.p + 3 * (size_t)groupStart[g], n, &e->blas[g], e->stream, berr)) return e->fail(BPT_ERR_CUDA, berr);
         }
         if (groupStart[1] > groupStart[0]) addInst(0, nullptr);
-        Xform worldFromRenderX = Inverse(renderFromWorld);
         for (const bpt_instance &in : e->instances) {
             if (!e->blas[in.object_id + 1].nodes) continue;   // empty definition
             // scene.cpp:375-393: renderFromInstance = RenderFromObject(0) * worldFromRender
-            Xform rfo = renderFromWorld * TrackedXform(in.world_from_instance, in.instance_from_world);
-            Xform renderFromInstance = rfo * worldFromRenderX;
+            Xform renderFromInstance = ResolveRenderFromInstance(space, spaces, in.world_from_instance, in.instance_from_world);
             addInst(in.object_id + 1, &renderFromInstance);
         }
         if (dinst.empty()) return e->fail(BPT_ERR_INVALID, "scene has no geometry");

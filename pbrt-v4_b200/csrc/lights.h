@@ -96,7 +96,8 @@ BPT_HD SurfaceIntr XformInteraction(const DeviceInstance &I, const SurfaceIntr &
 }
 BPT_HD Vec3 InstancedWo(const DeviceInstance &I, Vec3 rayD) {
     Vec3 dInst = XformVec(I.mInv, rayD);       // Transform::ApplyInverse(Vector3f)
-    return Normalize(XformVec(I.m, -dInst));   // ret.wo = Normalize(t(si.wo)), si.wo = -ray.d in instance space
+    // si.wo = Normalize(-ray.d) in instance space (Interaction ctor, interaction.h:32-33), then ret.wo = Normalize(t(si.wo))
+    return Normalize(XformVec(I.m, Normalize(-dInst)));
 }
 
 struct TriData { Pt3 p0, p1, p2; TriAttribs a; int mesh, triIndex; };

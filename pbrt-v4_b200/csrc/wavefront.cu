@@ -360,7 +360,9 @@ __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int
         SurfaceIntr isect = TriangleInteraction(td.p0, td.p1, td.p2, td.a, th);
         const DeviceMesh &mesh = rc.sv.meshes[td.mesh];
         float4 d4 = ps.rayD[slot];
-        Vec3 wo = -Vec3(d4.x, d4.y, d4.z);
+        // isect.wo: the Interaction constructor normalises it (interaction.h:32-33, wo(Normalize(wo))) -- not a no-op in float: a third
+        // of all unit vectors change in the last bit when normalised again, which the microfacet BxDFs see (r02c bisection)
+        Vec3 wo = Normalize(-Vec3(d4.x, d4.y, d4.z));
         if (rc.sv.instances) {
             const DeviceInstance &I = rc.sv.instances[ps.hitInst[slot]];
             if (!I.identity) { isect = XformInteraction(I, isect); wo = InstancedWo(I, Vec3(d4.x, d4.y, d4.z)); }
@@ -374,9 +376,10 @@ __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int
         const int rayMedium = rc.nMedia > 0 ? ps.medium[slot] : -1;
         if (Material::kTag == MAT_INTERFACE) {
             // isect.SkipIntersection(&ray, tHit): respawn the ray past the surface, same depth (interaction.h)
-            Pt3 o = OffsetRayOrigin(isect.pi, isect.n, -wo);
+            const Vec3 rayDir(d4.x, d4.y, d4.z);   // SpawnRay(ray.d): the ray's own (not re-normalised) direction
+            Pt3 o = OffsetRayOrigin(isect.pi, isect.n, rayDir);
             ps.rayO[slot] = make_float4(o.x, o.y, o.z, 0.f);
-            if (rc.nMedia > 0) ps.medium[slot] = SurfaceGetMedium(mesh, -wo, isect.n, rayMedium);
+            if (rc.nMedia > 0) ps.medium[slot] = SurfaceGetMedium(mesh, rayDir, isect.n, rayMedium);
             int p = WarpAggPush(&rc.counts[nextQ]);
             rc.queues[nextQ][p] = slot;
             continue;

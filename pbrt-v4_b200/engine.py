@@ -32,7 +32,7 @@ bpt_scene_add_mesh bpt_scene_add_instance bpt_scene_add_light bpt_scene_add_medi
 bpt_scene_commit bpt_load_pbrt bpt_load_pbrt_ex bpt_frontend_error bpt_render bpt_render_bands bpt_film_resolve_gbuffer bpt_film_clear bpt_stats_reset bpt_film_read bpt_film_write
 bpt_film_copy_to_device bpt_film_copy_from_device bpt_film_resolve bpt_film_dims bpt_get_stats bpt_trace_closest
 bpt_trace_any bpt_trace_closest_device bpt_probe_sampler bpt_probe_intersect_triangle bpt_render_stream bpt_render_bands_stream
-bpt_sync bpt_sampler_spp""".split()
+bpt_sync bpt_sampler_spp bpt_scene_set_transform_space""".split()
 
 
 def load_library():
