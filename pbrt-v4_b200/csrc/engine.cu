@@ -1266,7 +1266,9 @@ static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int 
                 if (rc.nMedia > 0) { profBegin(4); LaunchSampleMedium(rc, next, sms, st); launches += 2; profEnd(); }
                 if (rc.nInfinite > 0) { LaunchHandleEscaped(rc, sms, st); ++launches; }
                 if (e->haveAreaLights) { LaunchHandleEmissive(rc, sms, st); ++launches; }
-                if (!dynamic && depth == maxDepth) break;
+                // (GBufferFilm with maxdepth 0: the visible surface is still initialised at the first hit, cpu/integrators.cpp:1118-1145,
+                // before Li() returns at the depth test -- the shading kernels do both, so they run once more)
+                if (!dynamic && depth == maxDepth && !(rc.film.isGBuffer && depth == 0)) break;
                 profBegin(2);
                 for (int m = 0; m < MAT_NTAGS; ++m)
                     if (e->materialPresent[m]) { LaunchShade(rc, m, next, sms, st); ++launches; }

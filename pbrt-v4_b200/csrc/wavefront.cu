@@ -344,7 +344,8 @@ __device__ __forceinline__ void PushShadowTr(const RenderCtx &rc, int slot, Pt3 
 
 // ---------------------------------------------------------------- surface scattering, one instantiation per material
 #ifndef BPT_SHADE_CTAS
-#define BPT_SHADE_CTAS 5      // resident 128-thread CTAs per SM the shading kernels are register-limited for
+#define BPT_SHADE_CTAS 4      // resident 128-thread CTAs per SM the shading kernels are register-limited for (128 registers: no spills;
+                              // r02d sweep with the outlined sampler / libm: 3 -> ?, 4 -> 23.0 ms, 5 -> 25.9, 6 -> 26.2, 8 -> 26.4 per 64 spp)
 #endif
 template <typename Material>
 __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int nextQ) {
