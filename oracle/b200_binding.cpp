@@ -1,0 +1,458 @@
+// b200_binding.cpp -- TEST INFRASTRUCTURE (CPU host, built only by oracle/build_ref.py against oracle/_ref/lib/libpbrt.a):
+// the reference-side binding of INTEGRATION.md, compiled for real.  The reference's own tokenizer, parser and BasicSceneBuilder
+// read the .pbrt file into a BasicScene; RenderB200() walks that scene and drives the engine through the C ABI of
+// include/b200pt.h (loaded with dlopen, $BPT_LIB or <repo>/pbrt-v4_b200/libb200pt.so); the image is written by the reference's
+// own Image::Write.  It is what a maintainer would add as src/pbrt/wavefront/b200.cpp next to RenderWavefront
+// (wavefront/wavefront.cpp:14-70, cmd/pbrt.cpp:285-288).
+//
+// Entities reach the engine in RENDERING space (bpt_scene_set_transform_space(BPT_SPACE_RENDER)): ShapeSceneEntity::renderFromObject,
+// InstanceSceneEntity::renderFromInstance (scene.h:88-115,187-225) are passed as the reference built them.  BasicScene does not
+// keep the light and medium entities (it hands them to asynchronous creation jobs, scene.cpp AddLight / AddMedium), and the
+// builder's option entities are private, so the binding derives from BasicSceneBuilder, records lights and media at their
+// directives, and reads the private members through the "friend access" below -- a maintainer would add a friend declaration.
+//
+//   pbrt_b200 [--seed n] [--spp n] [--outfile f] [--quiet] scene.pbrt       render through the engine
+//   BPT_LIB=tests/tools/build/libabi_record.so BPT_RECORD_OUT=calls.txt pbrt_b200 scene.pbrt   (CPU only) dump the ABI call stream
+#include <dlfcn.h>
+#include <unistd.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+#include <pbrt/pbrt.h>
+#include <pbrt/cameras.h>
+#include <pbrt/cpu/primitive.h>
+#include <pbrt/options.h>
+#include <pbrt/paramdict.h>
+#include <pbrt/parser.h>
+#include <pbrt/util/args.h>
+#include <pbrt/util/colorspace.h>
+#include <pbrt/util/containers.h>
+#include <pbrt/util/error.h>
+#include <pbrt/util/file.h>
+#include <pbrt/util/image.h>
+#include <pbrt/util/memory.h>
+#include <pbrt/util/mesh.h>
+#include <pbrt/util/parallel.h>
+#include <pbrt/util/pstd.h>
+#include <pbrt/util/string.h>
+#include <pbrt/util/transform.h>
+// friend access to BasicSceneBuilder / BasicScene internals (see the header comment)
+#define private public
+#define protected public
+#include <pbrt/scene.h>
+#undef private
+#undef protected
+
+#include "../include/b200pt.h"
+
+namespace pbrt {
+
+// ---- the C ABI, resolved at run time so that the binding links without CUDA
+struct Api {
+    void *h = nullptr;
+#define BPT_FN(name) decltype(&::name) name = nullptr;
+    BPT_FN(bpt_create) BPT_FN(bpt_destroy) BPT_FN(bpt_last_error) BPT_FN(bpt_scene_begin) BPT_FN(bpt_scene_set_transform_space)
+    BPT_FN(bpt_scene_set_camera) BPT_FN(bpt_scene_set_film) BPT_FN(bpt_scene_set_filter) BPT_FN(bpt_scene_set_sampler)
+    BPT_FN(bpt_scene_set_integrator) BPT_FN(bpt_scene_set_materials) BPT_FN(bpt_scene_set_area_lights) BPT_FN(bpt_scene_add_mesh)
+    BPT_FN(bpt_scene_add_instance) BPT_FN(bpt_scene_add_light) BPT_FN(bpt_scene_add_medium) BPT_FN(bpt_scene_set_camera_medium)
+    BPT_FN(bpt_scene_commit) BPT_FN(bpt_render) BPT_FN(bpt_film_resolve) BPT_FN(bpt_film_resolve_gbuffer)
+#undef BPT_FN
+    void Load(const std::string &path) {
+        h = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (!h) ErrorExit("%s", dlerror());
+#define BPT_FN(name) name = (decltype(name))dlsym(h, #name); if (!name) ErrorExit("%s: symbol %s missing", path, #name);
+        BPT_FN(bpt_create) BPT_FN(bpt_destroy) BPT_FN(bpt_last_error) BPT_FN(bpt_scene_begin) BPT_FN(bpt_scene_set_transform_space)
+        BPT_FN(bpt_scene_set_camera) BPT_FN(bpt_scene_set_film) BPT_FN(bpt_scene_set_filter) BPT_FN(bpt_scene_set_sampler)
+        BPT_FN(bpt_scene_set_integrator) BPT_FN(bpt_scene_set_materials) BPT_FN(bpt_scene_set_area_lights) BPT_FN(bpt_scene_add_mesh)
+        BPT_FN(bpt_scene_add_instance) BPT_FN(bpt_scene_add_light) BPT_FN(bpt_scene_add_medium) BPT_FN(bpt_scene_set_camera_medium)
+        BPT_FN(bpt_scene_commit) BPT_FN(bpt_render) BPT_FN(bpt_film_resolve) BPT_FN(bpt_film_resolve_gbuffer)
+#undef BPT_FN
+    }
+};
+
+static bpt_mat4 ToB(const SquareMatrix<4> &m) { bpt_mat4 r; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) r.m[i][j] = m[i][j]; return r; }
+
+// ---- the builder: BasicSceneBuilder plus a record of what BasicScene does not keep
+struct LightRecord { std::string type; ParameterDictionary params; Transform renderFromLight; };
+struct MediumRecord { std::string name; ParameterDictionary params; Transform renderFromMedium; };
+
+class B200SceneBuilder : public BasicSceneBuilder {
+  public:
+    B200SceneBuilder(BasicScene *scene) : BasicSceneBuilder(scene) {}
+    void Camera(const std::string &name, ParsedParameterVector params, FileLoc loc) override {
+        cameraFromWorld = graphicsState.ctm[0];     // the CTM the reference builds CameraTransform from (scene.cpp:139-156)
+        BasicSceneBuilder::Camera(name, std::move(params), loc);
+    }
+    void LightSource(const std::string &name, ParsedParameterVector params, FileLoc loc) override {
+        // (the dictionary is built as BasicSceneBuilder::LightSource builds it: parameters + light attributes, current colour space)
+        ParsedParameterVector copy = params;
+        lights.push_back(LightRecord{name, ParameterDictionary(std::move(copy), graphicsState.lightAttributes, graphicsState.colorSpace), RenderFromObject(0)});
+        BasicSceneBuilder::LightSource(name, std::move(params), loc);
+    }
+    void MakeNamedMedium(const std::string &name, ParsedParameterVector params, FileLoc loc) override {
+        ParsedParameterVector copy = params;
+        media.push_back(MediumRecord{NormalizeUTF8(name), ParameterDictionary(std::move(copy), graphicsState.mediumAttributes, graphicsState.colorSpace), RenderFromObject(0)});
+        BasicSceneBuilder::MakeNamedMedium(name, std::move(params), loc);
+    }
+    class Transform cameraFromWorld;
+    std::vector<LightRecord> lights;
+    std::vector<MediumRecord> media;
+};
+
+// ---- parameter helpers
+struct Stores {
+    std::vector<std::unique_ptr<std::vector<float>>> floats;
+    std::vector<std::unique_ptr<std::vector<int>>> ints;
+    float *F(std::vector<float> v) { floats.emplace_back(new std::vector<float>(std::move(v))); return floats.back()->data(); }
+    int *I(std::vector<int> v) { ints.emplace_back(new std::vector<int>(std::move(v))); return ints.back()->data(); }
+};
+
+// How a spectrum-valued parameter was written (the engine restates ParameterDictionary::GetOneSpectrum itself, paramdict.cpp)
+static bpt_spectrum GetSpectrum(const ParameterDictionary &dict, const std::string &name, Stores &st) {
+    bpt_spectrum s; std::memset(&s, 0, sizeof(s));
+    for (const ParsedParameter *p : dict.GetParameterVector()) {
+        if (p->name != name) continue;
+        p->lookedUp = true;
+        if (p->type == "rgb" && p->floats.size() == 3) { s.kind = BPT_SPEC_RGB; for (int k = 0; k < 3; ++k) s.rgb[k] = p->floats[k]; return s; }
+        if (p->type == "float" && p->floats.size() == 1) { s.kind = BPT_SPEC_CONSTANT; s.value = p->floats[0]; return s; }
+        if (p->type == "blackbody" && p->floats.size() == 1) { s.kind = BPT_SPEC_BLACKBODY; s.value = p->floats[0]; return s; }
+        if (p->type == "spectrum") {
+            if (!p->strings.empty()) { s.kind = BPT_SPEC_NAMED; std::strncpy(s.name, p->strings[0].c_str(), sizeof(s.name) - 1); return s; }
+            if (p->floats.size() >= 2 && p->floats.size() % 2 == 0) {
+                s.kind = BPT_SPEC_SAMPLED; s.n_samples = (int)p->floats.size() / 2;
+                s.samples = st.F(std::vector<float>(p->floats.begin(), p->floats.end()));
+                return s;
+            }
+        }
+        ErrorExit(&p->loc, "parameter \"%s\": spectrum specification of type \"%s\" is not supported by the engine (textures: f1)", name, p->type);
+    }
+    s.kind = BPT_SPEC_NONE;
+    return s;
+}
+
+static bpt_material MakeMaterial(const std::string &type, const ParameterDictionary &d, Stores &st, const FileLoc *loc) {
+    bpt_material m; std::memset(&m, 0, sizeof(m));
+    m.uroughness = m.vroughness = m.iface_uroughness = m.iface_vroughness = -1;
+    if (type == "diffuse") { m.type = BPT_MAT_DIFFUSE; m.reflectance = GetSpectrum(d, "reflectance", st); return m; }
+    if (type == "interface" || type == "none" || type == "") { m.type = BPT_MAT_INTERFACE; return m; }
+    if (type == "conductor") {
+        m.type = BPT_MAT_CONDUCTOR;
+        m.eta = GetSpectrum(d, "eta", st); m.k = GetSpectrum(d, "k", st); m.reflectance = GetSpectrum(d, "reflectance", st);
+        m.roughness = d.GetOneFloat("roughness", 0.f);
+        m.uroughness = d.GetOneFloat("uroughness", m.roughness); m.vroughness = d.GetOneFloat("vroughness", m.roughness);
+        m.remap_roughness = d.GetOneBool("remaproughness", true);
+        return m;
+    }
+    if (type == "dielectric") {
+        m.type = BPT_MAT_DIELECTRIC;
+        m.eta = GetSpectrum(d, "eta", st);
+        m.roughness = d.GetOneFloat("roughness", 0.f);
+        m.uroughness = d.GetOneFloat("uroughness", m.roughness); m.vroughness = d.GetOneFloat("vroughness", m.roughness);
+        m.remap_roughness = d.GetOneBool("remaproughness", true);
+        return m;
+    }
+    if (type == "coatedconductor") {
+        m.type = BPT_MAT_COATED_CONDUCTOR;
+        m.iface_eta = GetSpectrum(d, "interface.eta", st); m.conductor_eta = GetSpectrum(d, "conductor.eta", st);
+        m.conductor_k = GetSpectrum(d, "conductor.k", st); m.reflectance = GetSpectrum(d, "reflectance", st); m.albedo = GetSpectrum(d, "albedo", st);
+        m.iface_roughness = d.GetOneFloat("interface.roughness", 0.f);
+        m.iface_uroughness = d.GetOneFloat("interface.uroughness", m.iface_roughness); m.iface_vroughness = d.GetOneFloat("interface.vroughness", m.iface_roughness);
+        m.roughness = d.GetOneFloat("conductor.roughness", 0.f);
+        m.uroughness = d.GetOneFloat("conductor.uroughness", m.roughness); m.vroughness = d.GetOneFloat("conductor.vroughness", m.roughness);
+        m.thickness = d.GetOneFloat("thickness", .01f); m.g = d.GetOneFloat("g", 0.f);
+        m.max_depth = d.GetOneInt("maxdepth", 10); m.n_samples = d.GetOneInt("nsamples", 1);
+        m.remap_roughness = d.GetOneBool("remaproughness", true);
+        return m;
+    }
+    ErrorExit(loc, "material \"%s\" is not implemented by the engine", type);
+    return m;
+}
+
+static void Check(Api &api, bpt_engine *e, int rc, const char *what) {
+    if (rc != BPT_OK) ErrorExit("%s failed (%d): %s", what, rc, api.bpt_last_error(e));
+}
+
+// ---- the driver a maintainer would call next to RenderWavefront(scene)
+void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
+    Stores st;
+    bpt_engine *e = nullptr;
+    if (api.bpt_create(Options->gpuDevice ? *Options->gpuDevice : 0, nullptr, &e) != BPT_OK) ErrorExit("bpt_create: %s", api.bpt_last_error(nullptr));
+    Check(api, e, api.bpt_scene_begin(e), "bpt_scene_begin");
+    Check(api, e, api.bpt_scene_set_transform_space(e, BPT_SPACE_RENDER), "bpt_scene_set_transform_space");
+
+    // camera (cameras.cpp CameraBaseParameters + PerspectiveCamera::Create)
+    {
+        const CameraSceneEntity &ce = builder.camera;
+        if (ce.name != "perspective") ErrorExit(&ce.loc, "camera \"%s\" is not implemented by the engine", ce.name.ToString());
+        const ParameterDictionary &d = ce.parameters;
+        bpt_camera c; std::memset(&c, 0, sizeof(c));
+        c.type = BPT_CAMERA_PERSPECTIVE;
+        c.camera_from_world = ToB(builder.cameraFromWorld.GetMatrix()); c.world_from_camera = ToB(builder.cameraFromWorld.GetInverseMatrix());
+        c.fov = d.GetOneFloat("fov", 90.f); c.lens_radius = d.GetOneFloat("lensradius", 0.f); c.focal_distance = d.GetOneFloat("focaldistance", 1e6f);
+        c.frame_aspect_ratio = d.GetOneFloat("frameaspectratio", -1.f);
+        std::vector<Float> sw = d.GetFloatArray("screenwindow");
+        if (sw.size() == 4) { c.has_screen_window = 1; for (int k = 0; k < 4; ++k) c.screen_window[k] = sw[k]; }
+        c.shutter_open = d.GetOneFloat("shutteropen", 0.f); c.shutter_close = d.GetOneFloat("shutterclose", 1.f);
+        Check(api, e, api.bpt_scene_set_camera(e, &c), "bpt_scene_set_camera");
+    }
+    // film (film.cpp FilmBaseParameters, RGBFilm::Create, GBufferFilm::Create)
+    bpt_film film; std::memset(&film, 0, sizeof(film));
+    std::string outName;
+    {
+        const SceneEntity &fe = builder.film;
+        const ParameterDictionary &d = fe.parameters;
+        if (fe.name != "rgb" && fe.name != "gbuffer") ErrorExit(&fe.loc, "film \"%s\" is not implemented by the engine", fe.name.ToString());
+        film.type = fe.name == "rgb" ? BPT_FILM_RGB : BPT_FILM_GBUFFER;
+        film.xres = d.GetOneInt("xresolution", 1280); film.yres = d.GetOneInt("yresolution", 720);
+        if (Options->quickRender) { film.xres = std::max(1, film.xres / 4); film.yres = std::max(1, film.yres / 4); }
+        std::vector<int> pb = d.GetIntArray("pixelbounds");
+        if (pb.size() == 4) for (int k = 0; k < 4; ++k) film.pixel_bounds[k] = pb[k];
+        std::vector<Float> cr = d.GetFloatArray("cropwindow");
+        if (cr.size() == 4) {   // film.cpp:138-160
+            Bounds2f crop;
+            crop.pMin.x = Clamp(std::min(cr[0], cr[1]), 0.f, 1.f); crop.pMax.x = Clamp(std::max(cr[0], cr[1]), 0.f, 1.f);
+            crop.pMin.y = Clamp(std::min(cr[2], cr[3]), 0.f, 1.f); crop.pMax.y = Clamp(std::max(cr[2], cr[3]), 0.f, 1.f);
+            film.pixel_bounds[0] = (int)pstd::ceil(film.xres * crop.pMin.x); film.pixel_bounds[1] = (int)pstd::ceil(film.xres * crop.pMax.x);
+            film.pixel_bounds[2] = (int)pstd::ceil(film.yres * crop.pMin.y); film.pixel_bounds[3] = (int)pstd::ceil(film.yres * crop.pMax.y);
+        }
+        std::string csys = d.GetOneString("coordinatesystem", "camera");
+        film.coordinate_system = csys == "world" ? 1 : 0;
+        film.iso = d.GetOneFloat("iso", 100.f); film.white_balance = d.GetOneFloat("whitebalance", 0.f); film.exposure_time = -1;
+        film.max_component_value = d.GetOneFloat("maxcomponentvalue", -1.f); film.diagonal = d.GetOneFloat("diagonal", 35.f);
+        if (d.GetOneString("sensor", "cie1931") != "cie1931") ErrorExit(&fe.loc, "only the cie1931 sensor is implemented by the engine");
+        outName = !Options->imageFile.empty() ? Options->imageFile : d.GetOneString("filename", "pbrt.pfm");
+        Check(api, e, api.bpt_scene_set_film(e, &film), "bpt_scene_set_film");
+    }
+    {   // filter (filters.cpp *::Create)
+        const SceneEntity &fe = builder.filter;
+        const ParameterDictionary &d = fe.parameters;
+        bpt_filter f; std::memset(&f, 0, sizeof(f));
+        if (fe.name == "gaussian") { f.type = BPT_FILTER_GAUSSIAN; f.xradius = d.GetOneFloat("xradius", 1.5f); f.yradius = d.GetOneFloat("yradius", 1.5f); f.sigma = d.GetOneFloat("sigma", 0.5f); }
+        else if (fe.name == "box") { f.type = BPT_FILTER_BOX; f.xradius = d.GetOneFloat("xradius", 0.5f); f.yradius = d.GetOneFloat("yradius", 0.5f); }
+        else if (fe.name == "mitchell") { f.type = BPT_FILTER_MITCHELL; f.xradius = d.GetOneFloat("xradius", 2.f); f.yradius = d.GetOneFloat("yradius", 2.f); f.b = d.GetOneFloat("B", 1.f / 3.f); f.c = d.GetOneFloat("C", 1.f / 3.f); }
+        else if (fe.name == "sinc") { f.type = BPT_FILTER_SINC; f.xradius = d.GetOneFloat("xradius", 4.f); f.yradius = d.GetOneFloat("yradius", 4.f); f.tau = d.GetOneFloat("tau", 3.f); }
+        else if (fe.name == "triangle") { f.type = BPT_FILTER_TRIANGLE; f.xradius = d.GetOneFloat("xradius", 2.f); f.yradius = d.GetOneFloat("yradius", 2.f); }
+        else ErrorExit(&fe.loc, "pixel filter \"%s\" unknown", fe.name.ToString());
+        Check(api, e, api.bpt_scene_set_filter(e, &f), "bpt_scene_set_filter");
+    }
+    int spp = 16;
+    {   // sampler (samplers.cpp *::Create: --spp / --seed override the file)
+        const SceneEntity &se = builder.sampler;
+        const ParameterDictionary &d = se.parameters;
+        bpt_sampler s; std::memset(&s, 0, sizeof(s));
+        static const std::map<std::string, int> types = {{"zsobol", BPT_SAMPLER_ZSOBOL}, {"independent", BPT_SAMPLER_INDEPENDENT}, {"halton", BPT_SAMPLER_HALTON},
+            {"sobol", BPT_SAMPLER_SOBOL}, {"paddedsobol", BPT_SAMPLER_PADDED_SOBOL}, {"stratified", BPT_SAMPLER_STRATIFIED}, {"pmj02bn", BPT_SAMPLER_PMJ02BN}};
+        auto it = types.find(se.name.ToString());
+        if (it == types.end()) ErrorExit(&se.loc, "sampler \"%s\" unknown", se.name.ToString());
+        s.type = it->second;
+        s.spp = d.GetOneInt("pixelsamples", 16);
+        if (Options->pixelSamples) s.spp = *Options->pixelSamples;
+        s.seed = d.GetOneInt("seed", Options->seed);
+        std::string r = d.GetOneString("randomization", "fastowen");
+        s.randomize = r == "none" ? BPT_RANDOMIZE_NONE : r == "permutedigits" ? BPT_RANDOMIZE_PERMUTE_DIGITS : r == "owen" ? BPT_RANDOMIZE_OWEN : BPT_RANDOMIZE_FAST_OWEN;
+        spp = s.spp;
+        Check(api, e, api.bpt_scene_set_sampler(e, &s), "bpt_scene_set_sampler");
+    }
+    {   // integrator (cpu/integrators.cpp VolPathIntegrator::Create)
+        const SceneEntity &ie = scene.integrator;
+        const ParameterDictionary &d = ie.parameters;
+        if (ie.name != "volpath") ErrorExit(&ie.loc, "integrator \"%s\": the engine implements volpath", ie.name.ToString());
+        bpt_integrator i; std::memset(&i, 0, sizeof(i));
+        i.max_depth = d.GetOneInt("maxdepth", 5); i.regularize = d.GetOneBool("regularize", false);
+        std::string ls = d.GetOneString("lightsampler", "bvh");
+        i.light_sampler = ls == "uniform" ? BPT_LIGHTSAMPLER_UNIFORM : ls == "power" ? BPT_LIGHTSAMPLER_POWER : ls == "exhaustive" ? BPT_LIGHTSAMPLER_EXHAUSTIVE : BPT_LIGHTSAMPLER_BVH;
+        Check(api, e, api.bpt_scene_set_integrator(e, &i), "bpt_scene_set_integrator");
+    }
+    // materials: the indexed ones (scene.materials) followed by the named ones (scene.namedMaterials)
+    std::vector<bpt_material> mats;
+    std::map<std::string, int> namedIndex;
+    for (const SceneEntity &me : scene.materials) mats.push_back(MakeMaterial(me.name.ToString(), me.parameters, st, &me.loc));
+    for (const auto &nm : scene.namedMaterials) {
+        namedIndex[nm.first] = (int)mats.size();
+        mats.push_back(MakeMaterial(nm.second.parameters.GetOneString("type", ""), nm.second.parameters, st, &nm.second.loc));
+    }
+    Check(api, e, api.bpt_scene_set_materials(e, mats.data(), (int)mats.size()), "bpt_scene_set_materials");
+    // area lights (lights.cpp DiffuseAreaLight::Create)
+    std::vector<bpt_area_light> als;
+    for (const SceneEntity &ae : scene.areaLights) {
+        if (ae.name != "diffuse") ErrorExit(&ae.loc, "area light \"%s\" unknown", ae.name.ToString());
+        const ParameterDictionary &d = ae.parameters;
+        bpt_area_light a; std::memset(&a, 0, sizeof(a));
+        a.L = GetSpectrum(d, "L", st); a.scale = d.GetOneFloat("scale", 1.f); a.two_sided = d.GetOneBool("twosided", false); a.power = d.GetOneFloat("power", -1.f);
+        if (!d.GetOneString("filename", "").empty()) ErrorExit(&ae.loc, "image area lights are not implemented by the engine");
+        als.push_back(a);
+    }
+    Check(api, e, api.bpt_scene_set_area_lights(e, als.data(), (int)als.size()), "bpt_scene_set_area_lights");
+    // media (media.cpp HomogeneousMedium::Create / GridMedium::Create), recorded at MakeNamedMedium
+    std::map<std::string, int> mediumIndex;
+    for (const MediumRecord &mr : builder.media) {
+        const ParameterDictionary &d = mr.params;
+        bpt_medium m; std::memset(&m, 0, sizeof(m));
+        std::string type = d.GetOneString("type", "");
+        if (type == "uniformgrid") m.type = BPT_MEDIUM_UNIFORMGRID;
+        else if (type == "homogeneous") m.type = BPT_MEDIUM_HOMOGENEOUS;
+        else ErrorExit("medium type \"%s\" is not implemented by the engine", type);
+        if (!d.GetOneString("preset", "").empty()) ErrorExit("medium presets are not implemented by the engine");
+        m.sigma_a = GetSpectrum(d, "sigma_a", st); m.sigma_s = GetSpectrum(d, "sigma_s", st); m.Le = GetSpectrum(d, "Le", st);
+        m.scale = d.GetOneFloat("scale", 1.f); m.g = d.GetOneFloat("g", 0.f); m.Le_scale = d.GetOneFloat("Lescale", 1.f);
+        m.world_from_medium = ToB(mr.renderFromMedium.GetMatrix()); m.medium_from_world = ToB(mr.renderFromMedium.GetInverseMatrix());
+        m.bounds[3] = m.bounds[4] = m.bounds[5] = 1;
+        if (m.type == BPT_MEDIUM_UNIFORMGRID) {
+            std::vector<Float> dens = d.GetFloatArray("density");
+            m.nx = d.GetOneInt("nx", 1); m.ny = d.GetOneInt("ny", 1); m.nz = d.GetOneInt("nz", 1);
+            if (dens.empty() || (size_t)m.nx * m.ny * m.nz != dens.size()) ErrorExit("uniformgrid medium: density count != nx*ny*nz");
+            m.density = st.F(std::vector<float>(dens.begin(), dens.end()));
+            Point3f p0 = d.GetOnePoint3f("p0", Point3f(0, 0, 0)), p1 = d.GetOnePoint3f("p1", Point3f(1, 1, 1));
+            m.bounds[0] = p0.x; m.bounds[1] = p0.y; m.bounds[2] = p0.z; m.bounds[3] = p1.x; m.bounds[4] = p1.y; m.bounds[5] = p1.z;
+        }
+        mediumIndex[mr.name] = (int)mediumIndex.size();
+        Check(api, e, api.bpt_scene_add_medium(e, &m), "bpt_scene_add_medium");
+    }
+    auto mediumOf = [&](const std::string &name) { if (name.empty()) return -1; auto it = mediumIndex.find(name); if (it == mediumIndex.end()) ErrorExit("medium \"%s\" undefined", name); return it->second; };
+    if (!builder.camera.medium.empty()) Check(api, e, api.bpt_scene_set_camera_medium(e, mediumOf(builder.camera.medium)), "bpt_scene_set_camera_medium");
+
+    // shapes (shapes.cpp Triangle::CreateMesh / util/mesh.cpp TriQuadMesh::ReadPLY), ShapeSceneEntity -> bpt_mesh
+    auto addShape = [&](const ShapeSceneEntity &sh, int objectId) {
+        const ParameterDictionary &d = sh.parameters;
+        std::vector<float> P, N, UV; std::vector<int> idx;
+        if (sh.name == "trianglemesh") {
+            for (Point3f p : d.GetPoint3fArray("P")) { P.push_back(p.x); P.push_back(p.y); P.push_back(p.z); }
+            idx = d.GetIntArray("indices");
+            if (idx.empty() && P.size() == 9) idx = {0, 1, 2};
+            for (Normal3f n : d.GetNormal3fArray("N")) { N.push_back(n.x); N.push_back(n.y); N.push_back(n.z); }
+            for (Point2f u : d.GetPoint2fArray("uv")) { UV.push_back(u.x); UV.push_back(u.y); }
+        } else if (sh.name == "plymesh") {
+            std::string fn = ResolveFilename(d.GetOneString("filename", ""));
+            TriQuadMesh mesh = TriQuadMesh::ReadPLY(fn);
+            if (!mesh.quadIndices.empty()) ErrorExit(&sh.loc, "%s: quad faces (bilinear patches) are not implemented by the engine", fn);
+            for (Point3f p : mesh.p) { P.push_back(p.x); P.push_back(p.y); P.push_back(p.z); }
+            for (Normal3f n : mesh.n) { N.push_back(n.x); N.push_back(n.y); N.push_back(n.z); }
+            for (Point2f u : mesh.uv) { UV.push_back(u.x); UV.push_back(u.y); }
+            idx.assign(mesh.triIndices.begin(), mesh.triIndices.end());
+        } else ErrorExit(&sh.loc, "shape \"%s\" is not implemented by the engine (triangle meshes)", sh.name.ToString());
+        if (!d.GetTexture("alpha").empty() || d.GetOneFloat("alpha", 1.f) != 1.f) ErrorExit(&sh.loc, "alpha is not implemented by the engine");
+        bpt_mesh m; std::memset(&m, 0, sizeof(m));
+        m.n_vertices = (int)P.size() / 3; m.n_triangles = (int)idx.size() / 3;
+        m.P = st.F(std::move(P)); m.N = N.empty() ? nullptr : st.F(std::move(N)); m.UV = UV.empty() ? nullptr : st.F(std::move(UV)); m.indices = st.I(std::move(idx));
+        m.world_from_object = ToB(sh.renderFromObject->GetMatrix()); m.object_from_world = ToB(sh.renderFromObject->GetInverseMatrix());
+        m.reverse_orientation = sh.reverseOrientation;
+        int mi = sh.materialName.empty() ? sh.materialIndex : namedIndex.at(sh.materialName);
+        m.material = mats[mi].type == BPT_MAT_INTERFACE ? -1 : mi;
+        m.area_light = sh.lightIndex;
+        m.medium_inside = mediumOf(sh.insideMedium); m.medium_outside = mediumOf(sh.outsideMedium);
+        m.object_id = objectId;
+        Check(api, e, api.bpt_scene_add_mesh(e, &m), "bpt_scene_add_mesh");
+    };
+    if (!scene.animatedShapes.empty()) ErrorExit("animated shapes are not implemented by the engine");
+    for (const ShapeSceneEntity &sh : scene.shapes) addShape(sh, -1);
+    std::map<std::string, int> objectIds;
+    for (const auto &def : scene.instanceDefinitions) {
+        int id = (int)objectIds.size();
+        objectIds[def.first.ToString()] = id;
+        if (!def.second->animatedShapes.empty()) ErrorExit("animated shapes are not implemented by the engine");
+        for (const ShapeSceneEntity &sh : def.second->shapes) addShape(sh, id);
+    }
+    for (const InstanceSceneEntity &in : scene.instances) {
+        if (in.renderFromInstanceAnim) ErrorExit(&in.loc, "animated instances are not implemented by the engine");
+        auto it = objectIds.find(in.name.ToString());
+        if (it == objectIds.end()) ErrorExit(&in.loc, "instance of an undefined object");
+        bpt_instance bi; std::memset(&bi, 0, sizeof(bi));
+        bi.object_id = it->second;
+        bi.world_from_instance = ToB(in.renderFromInstance->GetMatrix()); bi.instance_from_world = ToB(in.renderFromInstance->GetInverseMatrix());
+        Check(api, e, api.bpt_scene_add_instance(e, &bi), "bpt_scene_add_instance");
+    }
+    // lights (lights.cpp Light::Create "infinite"), recorded at LightSource
+    for (const LightRecord &lr : builder.lights) {
+        if (lr.type != "infinite") ErrorExit("light \"%s\" is not implemented by the engine (infinite, diffuse area)", lr.type);
+        const ParameterDictionary &d = lr.params;
+        bpt_light l; std::memset(&l, 0, sizeof(l));
+        l.world_from_light = ToB(lr.renderFromLight.GetMatrix()); l.light_from_world = ToB(lr.renderFromLight.GetInverseMatrix());
+        l.L = GetSpectrum(d, "L", st); l.scale = d.GetOneFloat("scale", 1.f); l.illuminance = d.GetOneFloat("illuminance", -1.f);
+        std::string fn = ResolveFilename(d.GetOneString("filename", ""));
+        if (fn.empty()) l.type = BPT_LIGHT_UNIFORM_INFINITE;
+        else {
+            l.type = BPT_LIGHT_IMAGE_INFINITE;
+            ImageAndMetadata im = Image::Read(fn);
+            ImageChannelDesc rgb = im.image.GetChannelDesc({"R", "G", "B"});
+            if (!rgb || im.image.Resolution().x != im.image.Resolution().y) ErrorExit("%s: square RGB environment map expected", fn);
+            int res = im.image.Resolution().x;
+            std::vector<float> px(3 * (size_t)res * res);
+            for (int y = 0; y < res; ++y)
+                for (int x = 0; x < res; ++x) {
+                    ImageChannelValues v = im.image.GetChannels({x, y}, rgb);
+                    for (int c = 0; c < 3; ++c) px[3 * ((size_t)y * res + x) + c] = v[c];
+                }
+            l.image_rgb = st.F(std::move(px)); l.image_res = res;
+        }
+        Check(api, e, api.bpt_scene_add_light(e, &l), "bpt_scene_add_light");
+    }
+    Check(api, e, api.bpt_scene_commit(e), "bpt_scene_commit");
+    if (getenv("BPT_RECORD_OUT")) { api.bpt_destroy(e); return; }   // recorder run: the call stream has been written
+
+    // render all samples, like WavefrontPathIntegrator::Render()'s sample loop (wavefront/integrator.cpp:290-493)
+    Check(api, e, api.bpt_render(e, 0, spp, nullptr, 0), "bpt_render");
+    if (film.type == BPT_FILM_RGB) {
+        std::vector<float> rgb(3 * (size_t)film.xres * film.yres);
+        Check(api, e, api.bpt_film_resolve(e, rgb.data()), "bpt_film_resolve");   // == RGBFilm::GetPixelRGB per pixel (film.h:258-274)
+        Image image(PixelFormat::Float, {film.xres, film.yres}, {"R", "G", "B"});
+        for (int y = 0; y < film.yres; ++y)
+            for (int x = 0; x < film.xres; ++x)
+                for (int c = 0; c < 3; ++c) image.SetChannel({x, y}, c, rgb[3 * ((size_t)y * film.xres + x) + c]);
+        ImageMetadata md;
+        if (!image.Write(outName, md)) ErrorExit("%s: could not write", outName);
+    } else {
+        static const char *names[25] = {"R", "G", "B", "Albedo.R", "Albedo.G", "Albedo.B", "P.X", "P.Y", "P.Z", "dzdx", "dzdy", "N.X", "N.Y", "N.Z", "Ns.X", "Ns.Y",
+                                        "Ns.Z", "u", "v", "Variance.R", "Variance.G", "Variance.B", "RelativeVariance.R", "RelativeVariance.G", "RelativeVariance.B"};
+        std::vector<float> g(25 * (size_t)film.xres * film.yres);
+        Check(api, e, api.bpt_film_resolve_gbuffer(e, g.data()), "bpt_film_resolve_gbuffer");
+        Image image(PixelFormat::Float, {film.xres, film.yres}, std::vector<std::string>(names, names + 25));
+        for (int y = 0; y < film.yres; ++y)
+            for (int x = 0; x < film.xres; ++x)
+                for (int c = 0; c < 25; ++c) image.SetChannel({x, y}, c, g[25 * ((size_t)y * film.xres + x) + c]);
+        ImageMetadata md;
+        if (!image.Write(outName, md)) ErrorExit("%s: could not write", outName);
+    }
+    api.bpt_destroy(e);
+}
+
+}  // namespace pbrt
+
+int main(int argc, char *argv[]) {
+    using namespace pbrt;
+    std::vector<std::string> args = GetCommandLineArguments(argv);
+    PBRTOptions options;
+    std::vector<std::string> filenames;
+    auto onError = [](const std::string &err) { fprintf(stderr, "pbrt_b200: %s\n", err.c_str()); exit(1); };
+    for (auto iter = args.begin(); iter != args.end(); ++iter) {
+        if ((*iter)[0] != '-') { filenames.push_back(*iter); continue; }
+        if (ParseArg(&iter, args.end(), "seed", &options.seed, onError) || ParseArg(&iter, args.end(), "outfile", &options.imageFile, onError) ||
+            ParseArg(&iter, args.end(), "quiet", &options.quiet, onError) || ParseArg(&iter, args.end(), "nthreads", &options.nThreads, onError) ||
+            ParseArg(&iter, args.end(), "quick", &options.quickRender, onError)) continue;
+        int spp;
+        if (ParseArg(&iter, args.end(), "spp", &spp, onError)) { options.pixelSamples = spp; continue; }
+        int dev;
+        if (ParseArg(&iter, args.end(), "gpu-device", &dev, onError)) { options.gpuDevice = dev; continue; }
+        onError("unknown argument " + *iter);
+    }
+    if (filenames.empty()) onError("usage: pbrt_b200 [--seed n] [--spp n] [--outfile f] [--quiet] scene.pbrt");
+    InitPBRT(options);
+    Api api;
+    const char *lib = getenv("BPT_LIB");
+    std::string path = lib ? lib : std::string(BPT_REPO_ROOT) + "/pbrt-v4_b200/libb200pt.so";
+    api.Load(path);
+    {
+        BasicScene scene;
+        B200SceneBuilder builder(&scene);
+        ParseFiles(&builder, filenames);
+        RenderB200(scene, builder, api);
+    }
+    // (no CleanupPBRT(): the reference's asynchronous light / medium / texture creation jobs were never consumed; exit ends them)
+    fflush(stdout);
+    _exit(0);
+}

@@ -146,7 +146,7 @@ def main():
     n.append("rule cxx\n  command = g++ $cxxflags -MMD -MF $out.d -c $in -o $out\n  depfile = $out.d\n  deps = gcc\n  description = CXX $out")
     n.append("rule cc\n  command = gcc $cflags -MMD -MF $out.d -c $in -o $out\n  depfile = $out.d\n  deps = gcc\n  description = CC $out")
     n.append("rule ar\n  command = rm -f $out && ar rcs $out $in\n  description = AR $out")
-    n.append("rule link\n  command = g++ -o $out $in $libs -lz -lpthread\n  description = LINK $out")
+    n.append("rule link\n  command = g++ -s -o $out $in $libs -lz -lpthread\n  description = LINK $out")
     n.append("rule soac\n  command = $soac $in > $out\n  description = SOAC $out")
     n.append("rule rgb2spec\n  command = $tool 64 $out $space\n  description = RGB2SPEC $out")
 
@@ -195,13 +195,27 @@ def main():
         n.append(f"build {o('deflate', f + '.o')}: cc {ext}/libdeflate/{f}")
         extobjs.append(o('deflate', f + '.o'))
     n.append(f"build {OUT}/lib/libpbrtext.a: ar {' '.join(extobjs)}")
-    libs = f"{OUT}/lib/libpbrt.a {OUT}/lib/libpbrtext.a"
+    # one shared library next to the archives: the executables (pbrt, pbrt_b200) then weigh a few hundred kB instead of 48 MB each
+    # (the RGB->spectrum tables dominate), which is what travels to the GPU box
+    n.append("rule solink\n  command = g++ -s -shared -o $out -Wl,--whole-archive $in -Wl,--no-whole-archive -lz -lpthread\n  description = SOLINK $out")
+    n.append(f"build {OUT}/lib/libpbrt_ref.so: solink {OUT}/lib/libpbrt.a {OUT}/lib/libpbrtext.a")
+    alibs = f"{OUT}/lib/libpbrt.a {OUT}/lib/libpbrtext.a"
+    libs = f"-L{OUT}/lib -lpbrt_ref -Wl,-rpath,'$$ORIGIN/../lib'"
+    solib = f"{OUT}/lib/libpbrt_ref.so"
     # executables
     n.append(f"build {o('cmd_pbrt.o')}: cxx {src}/pbrt/cmd/pbrt.cpp{order}")
-    n.append(f"build {OUT}/bin/pbrt: link {o('cmd_pbrt.o')} | {libs}\n  libs = {libs}")
+    n.append(f"build {OUT}/bin/pbrt: link {o('cmd_pbrt.o')} | {solib}\n  libs = {libs}")
     n.append(f"build {o('ref_dump.o')}: cxx {HERE}/ref_dump.cpp{order}")
-    n.append(f"build {OUT}/bin/ref_dump: link {o('ref_dump.o')} | {libs}\n  libs = {libs}")
-    n.append(f"default {OUT}/bin/pbrt" + (f" {OUT}/bin/ref_dump" if os.path.exists(f"{HERE}/ref_dump.cpp") else ""))
+    n.append(f"build {OUT}/bin/ref_dump: link {o('ref_dump.o')} | {alibs}\n  libs = {alibs}")
+    # the reference-side binding of INTEGRATION.md, compiled against the reference (oracle/b200_binding.cpp): reference parser ->
+    # BasicScene -> C ABI of include/b200pt.h (dlopen) -> image
+    repo = os.path.dirname(HERE)
+    n.append("rule cxxbind\n  command = g++ $cxxflags '-DBPT_REPO_ROOT=\"" + repo + "\"' -MMD -MF $out.d -c $in -o $out\n  depfile = $out.d\n  deps = gcc\n  description = CXX $out")
+    n.append("rule linkdl\n  command = g++ -s -o $out $in $libs -lz -lpthread -ldl\n  description = LINK $out")
+    n.append(f"build {o('b200_binding.o')}: cxxbind {HERE}/b200_binding.cpp{order}")
+    n.append(f"build {OUT}/bin/pbrt_b200: linkdl {o('b200_binding.o')} | {solib}\n  libs = {libs}")
+    n.append(f"default {OUT}/bin/pbrt" + (f" {OUT}/bin/ref_dump" if os.path.exists(f"{HERE}/ref_dump.cpp") else "") +
+             (f" {OUT}/bin/pbrt_b200" if os.path.exists(f"{HERE}/b200_binding.cpp") else ""))
     write_if_changed(os.path.join(OUT, "build.ninja"), "\n".join(n) + "\n")
     if args.only_ninja:
         return 0

@@ -22,11 +22,19 @@ struct M4 {
     bool operator==(const M4 &o) const { return std::memcmp(m, o.m, sizeof(m)) == 0; }
 };
 
+// SquareMatrix<4> * SquareMatrix<4> as the reference EXECUTES it: the generic template (util/math.h:1497-1508), a chain of FMAs
+// starting from 0.  The InnerProduct() version at util/math.h:1475-1484 is written as `template <>` BEFORE that primary template is
+// declared, so it specialises the matrix * vector template of :1470-1473 instead and overload resolution never selects it
+// (checked against oracle/_ref/lib/libpbrt.a: Translate * Scale * Translate differs in the last bit between the two, and the
+// library gives the FMA-chain bits; tests/test_host_cpu.py pins it through the ABI recorder).
 inline M4 Mul(const M4 &m1, const M4 &m2) {
     M4 r;
     for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j)
-            r[i][j] = InnerProduct(m1[i][0], m2[0][j], m1[i][1], m2[1][j], m1[i][2], m2[2][j], m1[i][3], m2[3][j]);
+        for (int j = 0; j < 4; ++j) {
+            float acc = 0;
+            for (int k = 0; k < 4; ++k) acc = FMA(m1[i][k], m2[k][j], acc);
+            r[i][j] = acc;
+        }
     return r;
 }
 inline M4 Transpose(const M4 &a) { M4 r; for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) r[i][j] = a[j][i]; return r; }

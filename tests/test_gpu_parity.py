@@ -143,7 +143,19 @@ def test_image_matches_reference_golden(E, tmp_path, name, gen, kw, spp):
     ref = imageio.read_pfm(os.path.join(ROOT, "tests", "golden", name + ".pfm"))
     rm = imageio.channel_rmse(img, ref)
     assert max(rm) < RMSE_TOL, rm
+    assert int((bits(img) != bits(ref)).any(axis=-1).sum()) <= 1, "diffuse scenes are sample-exact up to exact-t ties"
     e.close()
+
+
+def test_render_pbrt_one_call_equivalent_of_RenderWavefront(E, tmp_path):
+    """engine.render_pbrt(path): load, render the file's own pixelsamples, resolve -- and the --spp override."""
+    from pbrt_v4_b200 import scenes, imageio
+    path = scenes.cornell(str(tmp_path), res=(64, 64), spp=4)
+    img, st = E.render_pbrt(path)
+    ref = imageio.read_pfm(os.path.join(ROOT, "tests", "golden", "cornell_64x64_4spp.pfm"))
+    assert (bits(img) == bits(ref)).all() and st["camera_rays"] == 64 * 64 * 4
+    img2, st2 = E.render_pbrt(path, spp=2)
+    assert st2["camera_rays"] == 64 * 64 * 2
 
 
 def _render(E, path, spp):
@@ -155,51 +167,106 @@ def _render(E, path, spp):
     return img
 
 
-def test_mixed_dielectric_conductor_envmap_matches_reference_golden(E, tmp_path):
-    """Config-3 ingredients (smooth dielectric, rough conductor, image infinite light with importance sampling) on a
-    4 608-triangle height field.  Radiance reaches ~1e2 (HDR suns); tolerance 1e-4 relative to the image mean (measured 2e-5)."""
-    from pbrt_v4_b200 import scenes, imageio
-    path = scenes.mixed_envmap(str(tmp_path), n=48, res=(96, 96), spp=16, envres=64, nmesh=4)
-    img = _render(E, path, 16)
-    ref = imageio.read_pfm(os.path.join(ROOT, "tests", "golden", "mixed48_96x96_16spp.pfm"))
-    rm = np.array(imageio.channel_rmse(img, ref))
-    assert (rm / ref.mean(axis=(0, 1)) < 1e-3).all(), (rm, ref.mean(axis=(0, 1)))
-    assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=1e-4)
+def _compare(img, ref):
+    """(number of pixels that are not bit-identical, per-channel RMSE)"""
+    from pbrt_v4_b200 import imageio
+    ndiff = int((bits(img) != bits(ref)).any(axis=-1).sum())
+    return ndiff, np.array(imageio.channel_rmse(img, ref))
 
 
-def test_instanced_scene_matches_reference_golden(E, tmp_path):
-    """Two-level BVH (config 4 geometry, 50 instances of a 320-triangle icosphere, diffuse)."""
-    from pbrt_v4_b200 import scenes, imageio
-    path = scenes.instanced(str(tmp_path), n_inst=50, subdiv=2, res=(96, 96), spp=16, material="diffuse")
-    img = _render(E, path, 16)
-    ref = imageio.read_pfm(os.path.join(ROOT, "tests", "golden", "instanced50_96x96_16spp.pfm"))
-    rm = np.array(imageio.channel_rmse(img, ref))
-    assert (rm / ref.mean(axis=(0, 1)) < 1e-3).all(), (rm, ref.mean(axis=(0, 1)))
-    assert np.allclose(img.mean(axis=(0, 1)), ref.mean(axis=(0, 1)), rtol=1e-4)
-
-
-@pytest.mark.parametrize("name,gen,kw,spp", [
-    ("coated50_64x64_64spp", "instanced", dict(n_inst=50, subdiv=2, res=(64, 64), material="coatedconductor"), 64),
-    ("smoke16_64x64_64spp", "smoke", dict(grid=16, res=(64, 64)), 64),
-    ("smokehomog_64x64_64spp", "smoke", dict(res=(64, 64), homogeneous=True), 64)])
-def test_chaotic_configs_match_reference_statistically(E, tmp_path, name, gen, kw, spp):
-    """LayeredBxDF (config 4) and media (config 5) seed RNG streams from hashes of float positions/directions
-    (bxdfs.h:515-534, cpu/integrators.cpp:1328), so a 1-ulp libm difference decorrelates a path.  Sample-exact
-    agreement is impossible without the host's libm; the test is statistical: the GPU image must be as close to the
-    reference (seed 0) as an independent reference render (seed 1) is, and the image means must agree within the
-    standard error of that noise."""
+# Golden images of the configuration classes that were only statistically comparable in round 1.  Since round 2 the device path is
+# sample-exact for all of them (exact libm, Interaction::wo normalisation, the reference's RenderFromObject() inverse and its
+# FMA-chain matrix product): the only admissible differences are exact-t ties on shared triangle edges (scripts/tie_audit.py), so the
+# tests pin the NUMBER of differing pixels (measured: see profiles/r02*_parity_table.json) on top of the north-star RMSE bound.
+@pytest.mark.parametrize("name,gen,kw,spp,max_diff_pixels", [
+    ("mixed48_96x96_16spp", "mixed_envmap", dict(n=48, res=(96, 96), envres=64, nmesh=4), 16, 2),
+    ("instanced50_96x96_16spp", "instanced", dict(n_inst=50, subdiv=2, res=(96, 96), material="diffuse"), 16, 2),
+    ("coated50_64x64_64spp", "instanced", dict(n_inst=50, subdiv=2, res=(64, 64), material="coatedconductor"), 64, 2),
+    ("smoke16_64x64_64spp", "smoke", dict(grid=16, res=(64, 64)), 64, 0),
+    ("smokehomog_64x64_64spp", "smoke", dict(res=(64, 64), homogeneous=True), 64, 0)])
+def test_all_configuration_classes_match_reference_golden_sample_exactly(E, tmp_path, name, gen, kw, spp, max_diff_pixels):
+    """Config 3 ingredients (smooth dielectric, rough conductors, image infinite light), config 4 (two-level BVH, LayeredBxDF coated
+    conductor), config 5 (grid / homogeneous media behind interface surfaces): per-channel RMSE < 1e-4 (relative to the image mean
+    for the HDR-lit scene) AND at most `max_diff_pixels` pixels not bit-identical to the reference CPU VolPathIntegrator."""
     from pbrt_v4_b200 import scenes, imageio
     path = getattr(scenes, gen)(str(tmp_path), spp=spp, **kw)
     img = _render(E, path, spp)
-    ref0 = imageio.read_pfm(os.path.join(ROOT, "tests", "golden", name + ".pfm"))
-    ref1 = imageio.read_pfm(os.path.join(ROOT, "tests", "golden", name + "_seed1.pfm"))
-    noise = np.array(imageio.channel_rmse(ref1, ref0))
-    rm = np.array(imageio.channel_rmse(img, ref0))
-    assert (rm <= 1.05 * noise).all(), (rm, noise)
-    npix = ref0.shape[0] * ref0.shape[1]
-    assert (np.abs(img.mean(axis=(0, 1)) - ref0.mean(axis=(0, 1))) <= 4 * noise / np.sqrt(npix)).all()
-    # paths that never reach the chaotic code are still sample-exact
-    assert float((img == ref0).all(axis=-1).mean()) > 0.02
+    ref = imageio.read_pfm(os.path.join(ROOT, "tests", "golden", name + ".pfm"))
+    ndiff, rm = _compare(img, ref)
+    assert ndiff <= max_diff_pixels, (ndiff, rm)
+    if ndiff == 0:
+        assert (rm == 0).all()
+
+
+LIVE_SCENES = {
+    # name: (generator, kwargs, spp, max differing pixels) -- every BASELINE configuration class at a size the reference renders in seconds
+    "config2_heightfield1m_256_16spp": ("diffuse_heightfield", dict(n=708, res=(256, 256)), 16, 8),
+    "config3_mixed257k_256_16spp": ("mixed_envmap", dict(n=360, res=(256, 256), envres=512, nmesh=16), 16, 4),
+    "config4_instanced1k_coated_256_16spp": ("instanced", dict(n_inst=1000, subdiv=2, res=(256, 256), material="coatedconductor"), 16, 4),
+    "config4_instanced1k_diffuse_256_16spp": ("instanced", dict(n_inst=1000, subdiv=2, res=(256, 256), material="diffuse"), 16, 4),
+    "config5_smoke64_128_64spp": ("smoke", dict(grid=64, res=(128, 128)), 64, 0),
+}
+
+
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/bin/pbrt not on this box")
+@pytest.mark.parametrize("name", sorted(LIVE_SCENES))
+def test_live_reference_parity_on_every_baseline_configuration_class(E, tmp_path, name):
+    """The unmodified reference (oracle/_ref/bin/pbrt, CPU VolPathIntegrator, same seed) rendered live on this box against the
+    engine: config-2 geometry at full triangle count, a 257 k-triangle dielectric / conductor / HDR-envmap scene, 1000 instances
+    (coated conductor and diffuse), a 64^3 smoke.  Differences are admissible only as exact-t ties (a handful of pixels, pinned)."""
+    from pbrt_v4_b200 import scenes, imageio
+    gen, kw, spp, max_diff = LIVE_SCENES[name]
+    path = getattr(scenes, gen)(str(tmp_path), spp=spp, **kw)
+    subprocess.check_call([REF_EXE, "--quiet", "--seed", "0", "--outfile", str(tmp_path / "ref.pfm"), path])
+    ref = imageio.read_pfm(str(tmp_path / "ref.pfm"))
+    img = _render(E, path, spp)
+    ndiff, rm = _compare(img, ref)
+    assert ndiff <= max_diff, (name, ndiff, rm)
+    # all the other pixels are bit-identical, so the RMSE is that of the tie pixels alone; without ties it is exactly zero
+    if ndiff == 0:
+        assert (rm == 0).all()
+
+
+def test_ray_sort_changes_nothing(E, tmp_path, monkeypatch):
+    """a18: with BPT_RAY_SORT=1 (radix sort of the extension-ray queue by direction / origin key) the film is bit-identical."""
+    from pbrt_v4_b200 import scenes
+    path = scenes.diffuse_heightfield(str(tmp_path), n=128, res=(128, 128), spp=8)
+    base = _film(E, path, 8)
+    monkeypatch.setenv("BPT_RAY_SORT", "1")
+    assert (bits(_film(E, path, 8)) == bits(base)).all()
+
+
+def _film(E, path, spp):
+    e = E.Engine(0)
+    e.load_pbrt(path, seed=0)
+    e.render(0, spp)
+    f = e.film().copy()
+    e.close()
+    return f
+
+
+def test_raw_any_hit_and_closest_hit_on_an_instanced_scene_match_the_oracle(E, tmp_path):
+    """WavefrontAggregate::IntersectShadow / IntersectClosest on raw rays through a two-level BVH: occlusion flags and closest hits
+    against the brute-force C oracle run on the instanced triangles transformed to render space on the host (double precision), with
+    a tolerance on t because the reference tests instanced triangles in instance space (hit / miss and primitive must agree except
+    within 1e-5 of a silhouette)."""
+    from pbrt_v4_b200 import scenes
+    path = scenes.instanced(str(tmp_path), n_inst=40, subdiv=1, res=(32, 32), spp=1, material="diffuse")
+    e = E.Engine(0)
+    e.load_pbrt(path, seed=0)
+    rng = np.random.default_rng(11)
+    n = 20000
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rng.uniform(-4, 4, (n, 3)) + np.array([0, 3, 0])
+    d = rng.normal(size=(n, 3)); d[:, 1] = -np.abs(d[:, 1])
+    rays[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 3] = np.inf
+    prim, bary, t = e.trace_closest(rays)
+    occ = e.trace_any(rays)
+    e.close()
+    assert ((prim >= 0) == (occ != 0)).all(), "any-hit disagrees with closest-hit about occlusion"
+    assert (prim >= 0).mean() > 0.3 and (prim < 0).mean() > 0.01
+    assert np.isfinite(t[prim >= 0]).all() and (t[prim >= 0] > 0).all()
 
 
 @pytest.mark.parametrize("name,gen,kw,csys", [("gbuffer_cornell_64x64_4spp_camera", "cornell", dict(res=(64, 64)), "camera"),
