@@ -247,6 +247,7 @@ def main():
     import numpy as np
     import torch
     from pbrt_v4_b200 import engine as E
+    from pbrt_v4_b200.parallel import gather_film
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -280,6 +281,12 @@ def main():
     xres, yres = w["res"]
 
     eng = E.Engine(local_rank)
+    # builder effort by the number of samples that are going to be rendered: two treelet rounds cost ~6.5 ms per million triangles
+    # and save ~4 % of the trace time, which pays from ~100 M pixel samples per GPU (profiles/r02c sweep)
+    # (decided on the whole frame, not per GPU: exact-t ties on shared triangle edges resolve by traversal order, so the same
+    # builder setting on every N is what keeps the film -- and `film_checksum` -- identical for every N)
+    treelet_rounds = 2 if xres * yres * spp >= 100e6 else 0
+    eng.set_option("bvh_treelet_rounds", treelet_rounds)
     eng.load_pbrt(path, seed=0)
     st0 = eng.stats()
     # scanline bands, interleaved in blocks of 16 rows for load balance
@@ -293,9 +300,9 @@ def main():
             eng.render(0, spp)
         else:
             eng.render_bands(0, spp, band, world, rank)
-            # frame end: one NCCL reduce of the per-rank film accumulators (zero outside the rank's bands)
+            # frame end: one NCCL exchange of the per-rank film tiles (each rank sends the 1/N of the film it rendered)
             eng.film_to_device_ptr(film_t.data_ptr())
-            dist.reduce(film_t, dst=0, op=dist.ReduceOp.SUM)
+            gather_film(film_t, dist, band)
             if rank == 0:
                 eng.film_from_device_ptr(film_t.data_ptr())
         torch.cuda.synchronize()
@@ -370,6 +377,11 @@ def main():
            "d2h_bytes_per_step": int(img_bytes), "seconds_per_step": te, "seconds_bvh_build": st2["seconds_build"], "n_gpus": world,
            "note": "scene replicated: every rank parses and uploads it"}
 
+    # checksum of the final film of the last step (rank 0 holds the gathered film): must be the same for every N
+    film_checksum = None
+    if rank == 0:
+        import hashlib
+        film_checksum = hashlib.sha256(eng.film().tobytes()).hexdigest()[:16]
     line = None
     if rank == 0:
         # ---- roofline: counting pass (nodes / triangles per ray) + per-kernel CUDA-event timing of a full step
@@ -433,10 +445,12 @@ def main():
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_seconds * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "msamples_per_s": msamples,
-                "config": {"workload": w["desc"], "spp": spp, "rays_per_step": total_rays / args.steps, "tiling": f"{band}-row bands round-robin over ranks",
+                "config": {"workload": w["desc"], "spp": spp, "rays_per_step": total_rays / args.steps, "tiling": f"{band}-row bands round-robin over ranks, tile gather to rank 0 at frame end",
+                           "bvh_treelet_rounds": treelet_rounds,
                            "l2": "inputs larger than L2: BVH+triangles %.0f MB + path state %.0f MB per pass" % ((st0["bytes_bvh_nodes"] + st0["bytes_bvh_tris"]) / 1e6, min(32 << 20, xres * yres * spp) * 240 / 1e6),
                            "bvh": {"nodes": st0["bvh_nodes"], "depth": st0["bvh_depth"], "build_seconds": st0["seconds_build"]}},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(s_after["kernel_launches"]) * args.steps,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(s_after["kernel_launches"]),
+                "film_checksum": film_checksum,
                 "clocks": clocks.summary(), "wall_seconds_timed_region": wall_max}
         print(json.dumps(line))
     if world > 1:

@@ -170,6 +170,11 @@ int bpt_create(int cuda_device, const char *tables_path /* NULL: <lib dir>/../da
 void bpt_destroy(bpt_engine *e);
 const char *bpt_last_error(const bpt_engine *e /* may be NULL for create errors */);
 
+/* Engine options outside the scene description (kept across bpt_scene_begin).  "bvh_treelet_rounds": SAH treelet-restructuring rounds
+ * of the BVH builder, 0 = plain LBVH (fastest build), default 2, < 0 restores the default -- the build-time / trace-time trade a
+ * caller makes by how many samples it is going to render; "max_paths": path-state pool size (paths per wavefront pass). */
+int bpt_set_option(bpt_engine *e, const char *name, long long value);
+
 /* ---- scene description (copies everything) ---- */
 int bpt_scene_begin(bpt_engine *e);
 /* How the world_from_* matrices of meshes, instances, lights and media are to be read (the camera's are always world space).

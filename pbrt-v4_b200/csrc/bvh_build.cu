@@ -162,14 +162,14 @@ static bool dalloc(T **p, size_t n, char *err, cudaStream_t st = nullptr) {
     return true;
 }
 
-bool BuildWideBVH(const float4 *trisDev, int n, WideBVH *out, cudaStream_t stream, char *err, int leafMax) {
+bool BuildWideBVH(const float4 *trisDev, int n, WideBVH *out, cudaStream_t stream, char *err, int leafMax, int treeletRounds) {
     if (leafMax <= 0 || leafMax > 3) {
         leafMax = BPT_LEAF_MAX;
         if (const char *lm = std::getenv("BPT_LEAF_MAX")) leafMax = std::max(1, std::min(3, std::atoi(lm)));   // tuning / invariance tests
     }
     out->nodes = nullptr; out->tris = nullptr; out->nNodes = 0; out->nTris = n; out->depth = 0;
     if (n <= 0) { snprintf(err, 256, "BuildWideBVH: empty triangle set"); return false; }
-    int rounds = BPT_TREELET_ROUNDS;
+    int rounds = treeletRounds >= 0 ? std::min(8, treeletRounds) : BPT_TREELET_ROUNDS;
     if (const char *tr = std::getenv("BPT_TREELET_ROUNDS")) rounds = std::max(0, std::min(8, std::atoi(tr)));
     const int B = 256;
     float *cb = nullptr;

@@ -17,7 +17,8 @@ struct WideBVH {
 // leafMax: subtrees of at most this many primitives become one leaf child (1..3; 0 = default 3).  The top-level BVH of an
 // instanced scene uses 1: entering an instance (ray transform + a second traversal) is far costlier than a triangle test, so
 // every instance gets its own child box.
-bool BuildWideBVH(const float4 *trisDev, int n, WideBVH *out, cudaStream_t stream, char *err, int leafMax = 0);
+// leafMax <= 0 / treeletRounds < 0: the defaults (BPT_LEAF_MAX / BPT_TREELET_ROUNDS, overridable by the environment variables of the same names)
+bool BuildWideBVH(const float4 *trisDev, int n, WideBVH *out, cudaStream_t stream, char *err, int leafMax = 0, int treeletRounds = -1);
 void FreeWideBVH(WideBVH *b);
 
 }  // namespace bpt

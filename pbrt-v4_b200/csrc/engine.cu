@@ -175,6 +175,7 @@ struct bpt_engine {
     bool pending = false;            // an asynchronous render (bpt_render_stream + BPT_RENDER_ASYNC) has not been waited for yet
     int pendingLaunches = 0;
     int committedSpp = 0;
+    int treeletRounds = -1;          // bpt_set_option("bvh_treelet_rounds"): < 0 = builder default
 
     int fail(int code, const std::string &m) { err = m; return code; }
     int cudaFail(cudaError_t e, const char *what) { err = std::string(what) + ": " + cudaGetErrorString(e); return BPT_ERR_CUDA; }
@@ -467,6 +468,14 @@ extern "C" int bpt_scene_add_medium(bpt_engine *e, const bpt_medium *m) {
     if (m->type == BPT_MEDIUM_UNIFORMGRID) o.density.assign(m->density, m->density + (size_t)m->nx * m->ny * m->nz);
     o.m.density = nullptr;
     return BPT_OK;
+}
+// Engine options that are not part of the scene description (they survive bpt_scene_begin).
+extern "C" int bpt_set_option(bpt_engine *e, const char *name, long long value) {
+    if (!e || !name) return BPT_ERR_INVALID;
+    std::string n = name;
+    if (n == "bvh_treelet_rounds") { e->treeletRounds = (int)value; return BPT_OK; }
+    if (n == "max_paths") { if (value < 1024) return e->fail(BPT_ERR_INVALID, "max_paths too small"); e->maxPaths = (int)std::min<long long>(value, 1ll << 30); return BPT_OK; }
+    return e->fail(BPT_ERR_INVALID, "unknown option " + n);
 }
 extern "C" int bpt_scene_set_transform_space(bpt_engine *e, int space) {
     if (!e || (space != BPT_SPACE_WORLD && space != BPT_SPACE_RENDER)) return BPT_ERR_INVALID;
@@ -985,7 +994,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     const bool instanced = !e->instances.empty();
     if (!instanced) {
         if (nObjects > 0) return e->fail(BPT_ERR_INVALID, "object definitions without instances");
-        if (!BuildWideBVH(e->triPool.p, (int)totalTris, &e->bvh, e->stream, berr)) return e->fail(BPT_ERR_CUDA, berr);
+        if (!BuildWideBVH(e->triPool.p, (int)totalTris, &e->bvh, e->stream, berr, 0, e->treeletRounds)) return e->fail(BPT_ERR_CUDA, berr);
     } else {
         e->blas.resize(nObjects + 1);
         std::vector<float4> tlasPrims;
@@ -1011,7 +1020,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         for (int g = 0; g <= nObjects; ++g) {
             int n = groupStart[g + 1] - groupStart[g];
             if (n == 0) continue;
-            if (!BuildWideBVH(e->triPool.p + 3 * (size_t)groupStart[g], n, &e->blas[g], e->stream, berr)) return e->fail(BPT_ERR_CUDA, berr);
+            if (!BuildWideBVH(e->triPool.p + 3 * (size_t)groupStart[g], n, &e->blas[g], e->stream, berr, 0, e->treeletRounds)) return e->fail(BPT_ERR_CUDA, berr);
         }
         if (groupStart[1] > groupStart[0]) addInst(0, nullptr);
         for (const bpt_instance &in : e->instances) {
@@ -1024,7 +1033,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         ECK(e->dTlasPrims.upload(tlasPrims));
         {
             const char *tl = std::getenv("BPT_TLAS_LEAF");
-            if (!BuildWideBVH(e->dTlasPrims.p, (int)dinst.size(), &e->bvh, e->stream, berr, tl ? std::atoi(tl) : 1)) return e->fail(BPT_ERR_CUDA, berr);
+            if (!BuildWideBVH(e->dTlasPrims.p, (int)dinst.size(), &e->bvh, e->stream, berr, tl ? std::atoi(tl) : 1, e->treeletRounds)) return e->fail(BPT_ERR_CUDA, berr);
         }
         ECK(e->dInstances.upload(dinst));
     }

@@ -32,7 +32,7 @@ bpt_scene_add_mesh bpt_scene_add_instance bpt_scene_add_light bpt_scene_add_medi
 bpt_scene_commit bpt_load_pbrt bpt_load_pbrt_ex bpt_frontend_error bpt_render bpt_render_bands bpt_film_resolve_gbuffer bpt_film_clear bpt_stats_reset bpt_film_read bpt_film_write
 bpt_film_copy_to_device bpt_film_copy_from_device bpt_film_resolve bpt_film_dims bpt_get_stats bpt_trace_closest
 bpt_trace_any bpt_trace_closest_device bpt_probe_sampler bpt_probe_intersect_triangle bpt_render_stream bpt_render_bands_stream
-bpt_sync bpt_sampler_spp bpt_scene_set_transform_space""".split()
+bpt_sync bpt_sampler_spp bpt_scene_set_transform_space bpt_set_option""".split()
 
 
 def load_library():
@@ -56,6 +56,7 @@ def load_library():
     lib.bpt_render_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_void_p]
     lib.bpt_render_bands_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.bpt_sync.argtypes = [C.c_void_p]
+    lib.bpt_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
     lib.bpt_sampler_spp.argtypes = [C.c_void_p]
     lib.bpt_film_clear.argtypes = [C.c_void_p]
     lib.bpt_stats_reset.argtypes = [C.c_void_p]
@@ -126,6 +127,9 @@ class Engine:
         """Enqueue a render on `stream` (a cudaStream_t handle as int; 0 = the engine's stream) and return; sync() waits."""
         pb = (C.c_int * 4)(*[int(v) for v in pixel_bounds]) if pixel_bounds is not None else None
         self._ck(self.lib.bpt_render_stream(self.h, int(first_sample), int(n_samples), pb, 4, C.c_void_p(stream)), "bpt_render_stream")
+
+    def set_option(self, name, value):
+        self._ck(self.lib.bpt_set_option(self.h, name.encode(), int(value)), "bpt_set_option")
 
     def sync(self):
         self._ck(self.lib.bpt_sync(self.h), "bpt_sync")

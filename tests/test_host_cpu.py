@@ -68,7 +68,7 @@ def test_partition_bands_is_a_partition():
 GLOO_WORKER = r'''
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
-from pbrt_v4_b200.parallel import partition_bands, reduce_film
+from pbrt_v4_b200.parallel import partition_bands, reduce_film, gather_film
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
 yres, xres = 40, 24
@@ -76,9 +76,19 @@ full = torch.from_numpy(np.random.default_rng(5).random((yres, xres, 4)))       
 film = torch.zeros_like(full)
 for a, b in partition_bands(yres, world, rank, band=4):
     film[a:b] = full[a:b]                                                          # this rank's tiles, zero elsewhere
+tiles = film.clone()
 reduce_film(film, dist)
+gather_film(tiles, dist, band=4)                                                   # the tile exchange bench.py uses
+# ragged case: 40 rows in bands of 16 over 2 ranks -> 32 + 8 rows
+full2 = torch.from_numpy(np.random.default_rng(6).random((yres, xres, 4)))
+t2 = torch.zeros_like(full2)
+for a, b in partition_bands(yres, world, rank, band=16):
+    t2[a:b] = full2[a:b]
+gather_film(t2, dist, band=16)
 if rank == 0:
     assert torch.equal(film, full), "reduced film differs from the single-rank film"
+    assert torch.equal(tiles, full), "gathered film differs from the single-rank film"
+    assert torch.equal(t2, full2), "gathered film differs from the single-rank film (ragged bands)"
     print("GLOO_REDUCE_OK")
 dist.destroy_process_group()
 '''
