@@ -244,6 +244,11 @@ int bpt_film_copy_from_device(bpt_engine *e, const void *src_device_ptr);
 /* Final image, RGBFilm::GetPixelRGB (film.h:258-274): xres*yres*3 floats, output colour space. */
 int bpt_film_resolve(bpt_engine *e, float *rgb_host);
 int bpt_film_dims(const bpt_engine *e, int *xres, int *yres);
+/* The resolved film as an OpenEXR file (single-part scan-line, FLOAT, uncompressed): R G B, or GBufferFilm's 25 channels under
+ * the reference's channel names -- what RGBFilm / GBufferFilm::WriteImage hand to a denoiser (film.cpp:533-565, 688-803). */
+int bpt_film_write_exr(bpt_engine *e, const char *path);
+/* the writer alone (host only): n_channels names, pixels interleaved [y][x][channel] */
+int bpt_write_exr_file(const char *path, int width, int height, int n_channels, const char *const *names, const float *interleaved);
 int bpt_get_stats(bpt_engine *e, bpt_stats *out);
 
 /* ---- ray-level entry points (WavefrontAggregate::IntersectClosest / IntersectShadow on raw rays) ---- */

@@ -69,7 +69,10 @@ BPT_HD CamSample GetCameraSample(const SamplerParams &sp, const DeviceFilter &fi
     cs.lu = sampler.Get1D();
     Vec2 uf = sampler.Get2D();
     Vec2 fp;
-    if (filter.sampled) {
+    if (filter.sampled == 2) {   // TriangleFilter::Sample (filters.h:224-227): SampleTent per axis, weight 1
+        fp = Vec2(SampleTent(uf.x, filter.radiusX), SampleTent(uf.y, filter.radiusY));
+        cs.fweight = 1;
+    } else if (filter.sampled) {
         float pdf; int ou, ov;
         fp = PC2DSample(filter.distrib, uf, &pdf, &ou, &ov);
         cs.fweight = filter.f[ov * filter.nx + ou] / pdf;

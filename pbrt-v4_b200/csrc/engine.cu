@@ -15,6 +15,7 @@
 #include "../../include/b200pt.h"
 #include "bvh_build.h"
 #include "scene_xforms.h"
+#include "exr_writer.h"
 #include "kernels.h"
 #include "lightbvh.h"
 #include "tables.h"
@@ -396,7 +397,8 @@ extern "C" int bpt_scene_set_film(bpt_engine *e, const bpt_film *f) {
 }
 extern "C" int bpt_scene_set_filter(bpt_engine *e, const bpt_filter *f) {
     if (!e || !f) return BPT_ERR_INVALID;
-    if (f->type != BPT_FILTER_GAUSSIAN && f->type != BPT_FILTER_BOX) return e->fail(BPT_ERR_UNSUPPORTED, "filter not implemented (gaussian, box)");
+    if (f->type < BPT_FILTER_BOX || f->type > BPT_FILTER_TRIANGLE) return e->fail(BPT_ERR_INVALID, "unknown filter type");
+    if (!(f->xradius > 0) || !(f->yradius > 0)) return e->fail(BPT_ERR_INVALID, "filter radius must be positive");
     e->filter = *f; return BPT_OK;
 }
 extern "C" int bpt_scene_set_sampler(bpt_engine *e, const bpt_sampler *s) {
@@ -542,18 +544,44 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     DeviceFilter dflt{};
     FilterTables ft;
     dflt.radiusX = e->filter.xradius; dflt.radiusY = e->filter.yradius;
-    if (e->filter.type == BPT_FILTER_GAUSSIAN) {
-        float sigma = e->filter.sigma, rx = e->filter.xradius, ry = e->filter.yradius;
-        float expX = Gaussian(rx, 0, sigma), expY = Gaussian(ry, 0, sigma);
-        ft.nx = int(32 * rx); ft.ny = int(32 * ry);
-        ft.f.resize((size_t)ft.nx * ft.ny);
-        for (int y = 0; y < ft.ny; ++y)
-            for (int x = 0; x < ft.nx; ++x) {
-                float px = Lerp((x + 0.5f) / ft.nx, -rx, rx), py = Lerp((y + 0.5f) / ft.ny, -ry, ry);
-                ft.f[(size_t)y * ft.nx + x] = stdmax(0.f, Gaussian(px, 0, sigma) - expX) * stdmax(0.f, Gaussian(py, 0, sigma) - expY);
+    // FilterSampler (filters.cpp:96-118) for the filters the reference samples from a table: Gaussian, Mitchell, LanczosSinc --
+    // the unnormalised filter tabulated at 32 samples per unit radius, PiecewiseConstant2D over |f| (sampling.h), weight f / pdf
+    // (signed for the negative lobes of Mitchell and sinc).  Box and Triangle are sampled analytically on the device (filters.h).
+    {
+        const int type = e->filter.type;
+        const float rx = e->filter.xradius, ry = e->filter.yradius;
+        // Mitchell1D (filters.h:147-160), WindowedSinc / Sinc / SinXOverX (util/math.h:381-398)
+        const float B = e->filter.b, Cc = e->filter.c, tau = e->filter.tau;
+        auto mitchell1D = [&](float x) {
+            x = std::abs(x);
+            if (x <= 1) return ((12 - 9 * B - 6 * Cc) * x * x * x + (-18 + 12 * B + 6 * Cc) * x * x + (6 - 2 * B)) * (1.f / 6.f);
+            else if (x <= 2) return ((-B - 6 * Cc) * x * x * x + (6 * B + 30 * Cc) * x * x + (-12 * B - 48 * Cc) * x + (8 * B + 24 * Cc)) * (1.f / 6.f);
+            else return 0.f;
+        };
+        auto sinXOverX = [](float x) { if (1 - x * x == 1) return 1.f; return std::sin(x) / x; };
+        auto sinc = [&](float x) { return sinXOverX(kPi * x); };
+        auto windowedSinc = [&](float x, float radius) { if (std::abs(x) > radius) return 0.f; return sinc(x) * sinc(x / tau); };
+        const float sigma = e->filter.sigma;
+        const float expX = type == BPT_FILTER_GAUSSIAN ? Gaussian(rx, 0, sigma) : 0.f, expY = type == BPT_FILTER_GAUSSIAN ? Gaussian(ry, 0, sigma) : 0.f;
+        auto evaluate = [&](float px, float py) -> float {
+            switch (type) {
+            case BPT_FILTER_GAUSSIAN: return stdmax(0.f, Gaussian(px, 0, sigma) - expX) * stdmax(0.f, Gaussian(py, 0, sigma) - expY);
+            case BPT_FILTER_MITCHELL: return mitchell1D(2 * px / rx) * mitchell1D(2 * py / ry);
+            default: return windowedSinc(px, rx) * windowedSinc(py, ry);
             }
-        BuildPC2D(ft.f, ft.nx, ft.ny, -rx, rx, -ry, ry, &ft);
-        dflt.sampled = 1; dflt.nx = ft.nx; dflt.ny = ft.ny;
+        };
+        if (type == BPT_FILTER_GAUSSIAN || type == BPT_FILTER_MITCHELL || type == BPT_FILTER_SINC) {
+            ft.nx = int(32 * rx); ft.ny = int(32 * ry);
+            if (ft.nx < 1 || ft.ny < 1) return e->fail(BPT_ERR_INVALID, "filter radius too small for the sampling table");
+            ft.f.resize((size_t)ft.nx * ft.ny);
+            for (int y = 0; y < ft.ny; ++y)
+                for (int x = 0; x < ft.nx; ++x) {
+                    float px = Lerp((x + 0.5f) / ft.nx, -rx, rx), py = Lerp((y + 0.5f) / ft.ny, -ry, ry);
+                    ft.f[(size_t)y * ft.nx + x] = evaluate(px, py);
+                }
+            BuildPC2D(ft.f, ft.nx, ft.ny, -rx, rx, -ry, ry, &ft);
+            dflt.sampled = 1; dflt.nx = ft.nx; dflt.ny = ft.ny;
+        } else dflt.sampled = type == BPT_FILTER_TRIANGLE ? 2 : 0;
     }
 
     // ---- projective camera (cameras.h:254-273, PerspectiveCamera::Create cameras.cpp)
@@ -1406,6 +1434,37 @@ extern "C" int bpt_film_resolve(bpt_engine *e, float *rgb) {
     LaunchResolveFilm(e->filmPixels.p, e->rc.film, e->filmRGB.p, e->smCount, e->stream);
     ECK(cudaStreamSynchronize(e->stream));
     ECK(cudaMemcpy(rgb, e->filmRGB.p, sizeof(float) * e->filmRGB.n, cudaMemcpyDeviceToHost));
+    return BPT_OK;
+}
+// Host-only entry point of the writer (CPU-testable, no engine needed)
+extern "C" int bpt_write_exr_file(const char *path, int width, int height, int n_channels, const char *const *names, const float *interleaved) {
+    if (!path || !names) return BPT_ERR_INVALID;
+    std::vector<std::string> nm(names, names + std::max(0, n_channels));
+    std::string err;
+    return WriteEXR(path, width, height, nm, interleaved, {}, &err) ? BPT_OK : BPT_ERR_IO;
+}
+// RGBFilm::WriteImage / GBufferFilm::WriteImage (film.cpp:533-565, 688-803): the resolved film as an OpenEXR file -- channels R G B, or
+// the 25 GBuffer channels under the reference's names -- with the reference's pixelBounds / fullResolution / samplesPerPixel metadata
+extern "C" int bpt_film_write_exr(bpt_engine *e, const char *path) {
+    if (!e || !e->committed || !path) return BPT_ERR_INVALID;
+    ECK(cudaSetDevice(e->device));
+    { int rcS = Settle(e); if (rcS != BPT_OK) return rcS; }
+    const int w = e->film.xres, h = e->film.yres;
+    static const char *gb[25] = {"R", "G", "B", "Albedo.R", "Albedo.G", "Albedo.B", "P.X", "P.Y", "P.Z", "dzdx", "dzdy", "N.X", "N.Y", "N.Z", "Ns.X", "Ns.Y",
+                                 "Ns.Z", "u", "v", "Variance.R", "Variance.G", "Variance.B", "RelativeVariance.R", "RelativeVariance.G", "RelativeVariance.B"};
+    std::vector<std::string> names;
+    std::vector<float> px;
+    int rc;
+    if (e->rc.film.isGBuffer) { names.assign(gb, gb + 25); px.resize(25 * (size_t)w * h); rc = bpt_film_resolve_gbuffer(e, px.data()); }
+    else { names = {"R", "G", "B"}; px.resize(3 * (size_t)w * h); rc = bpt_film_resolve(e, px.data()); }
+    if (rc != BPT_OK) return rc;
+    std::vector<ExrAttr> extra;
+    auto bytes = [](const void *p, size_t n) { return std::vector<unsigned char>((const unsigned char *)p, (const unsigned char *)p + n); };
+    { int32_t b[4] = {e->rc.film.pbx0, e->rc.film.pby0, e->rc.film.pbx1 - 1, e->rc.film.pby1 - 1}; extra.push_back({"pixelBounds", "box2i", bytes(b, 16)}); }
+    { int32_t r[2] = {w, h}; extra.push_back({"fullResolution", "v2i", bytes(r, 8)}); }
+    { int32_t s = e->committedSpp; extra.push_back({"samplesPerPixel", "int", bytes(&s, 4)}); }
+    std::string err;
+    if (!WriteEXR(path, w, h, names, px.data(), extra, &err)) return e->fail(BPT_ERR_IO, err);
     return BPT_OK;
 }
 extern "C" int bpt_film_dims(const bpt_engine *e, int *xres, int *yres) {

@@ -516,7 +516,10 @@ bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::st
         std::string ty = a.empty() ? "gaussian" : a[0];
         if (ty == "gaussian") { filter.type = BPT_FILTER_GAUSSIAN; filter.xradius = pl.f("xradius", 1.5f); filter.yradius = pl.f("yradius", 1.5f); filter.sigma = pl.f("sigma", 0.5f); }
         else if (ty == "box") { filter.type = BPT_FILTER_BOX; filter.xradius = pl.f("xradius", 0.5f); filter.yradius = pl.f("yradius", 0.5f); }
-        else { err = "pixel filter \"" + ty + "\" is not supported (gaussian, box)"; return false; }
+        else if (ty == "mitchell") { filter.type = BPT_FILTER_MITCHELL; filter.xradius = pl.f("xradius", 2.f); filter.yradius = pl.f("yradius", 2.f); filter.b = pl.f("B", 1.f / 3.f); filter.c = pl.f("C", 1.f / 3.f); }
+        else if (ty == "sinc") { filter.type = BPT_FILTER_SINC; filter.xradius = pl.f("xradius", 4.f); filter.yradius = pl.f("yradius", 4.f); filter.tau = pl.f("tau", 3.f); }
+        else if (ty == "triangle") { filter.type = BPT_FILTER_TRIANGLE; filter.xradius = pl.f("xradius", 2.f); filter.yradius = pl.f("yradius", 2.f); }
+        else { err = "pixel filter \"" + ty + "\" is unknown (box, gaussian, mitchell, sinc, triangle)"; return false; }
         haveFilter = true; return true;
     }
     if (d == "Integrator") {

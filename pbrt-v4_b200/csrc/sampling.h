@@ -337,6 +337,18 @@ BPT_HD float SampleLinear(float u, float a, float b) {
     float x = u * (a + b) / (a + sqrtf(Lerp(u, Sqr(a), Sqr(b))));
     return stdmin(x, kOneMinusEpsilon);
 }
+// SampleTent (util/sampling.h:196-201) with SampleDiscrete({0.5, 0.5}, u, nullptr, &u) (util/sampling.h:79-113) written out
+BPT_HD float SampleTent(float u, float r) {
+    const float sumWeights = 0.5f + 0.5f;
+    float up = u * sumWeights;
+    if (up == sumWeights) up = NextFloatDown(up);
+    int offset = 0;
+    float sum = 0;
+    while (sum + 0.5f <= up) { sum += 0.5f; ++offset; }
+    u = stdmin((up - sum) / 0.5f, kOneMinusEpsilon);
+    if (offset == 0) return -r + r * SampleLinear(u, 0, 1);
+    return r * SampleLinear(u, 1, 0);
+}
 BPT_HD float BilinearPDF(Vec2 p, const float w[4]) {
     if (p.x < 0 || p.x > 1 || p.y < 0 || p.y > 1) return 0;
     if (w[0] + w[1] + w[2] + w[3] == 0) return 1;

@@ -54,7 +54,7 @@ struct DeviceFilter {          // FilterSampler tables (filters.cpp FilterSample
     const float *f;            // ny*nx tabulated filter values
     int nx, ny;
     float radiusX, radiusY;
-    int sampled;               // 0: box/triangle analytic sampling not used; 1: FilterSampler
+    int sampled;               // 0: BoxFilter::Sample  1: FilterSampler table (gaussian, mitchell, sinc)  2: TriangleFilter::Sample
 };
 
 struct DeviceMaterial {

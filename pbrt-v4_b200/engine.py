@@ -32,7 +32,7 @@ bpt_scene_add_mesh bpt_scene_add_instance bpt_scene_add_light bpt_scene_add_medi
 bpt_scene_commit bpt_load_pbrt bpt_load_pbrt_ex bpt_frontend_error bpt_render bpt_render_bands bpt_film_resolve_gbuffer bpt_film_clear bpt_stats_reset bpt_film_read bpt_film_write
 bpt_film_copy_to_device bpt_film_copy_from_device bpt_film_resolve bpt_film_dims bpt_get_stats bpt_trace_closest
 bpt_trace_any bpt_trace_closest_device bpt_probe_sampler bpt_probe_intersect_triangle bpt_render_stream bpt_render_bands_stream
-bpt_sync bpt_sampler_spp bpt_scene_set_transform_space bpt_set_option""".split()
+bpt_sync bpt_sampler_spp bpt_scene_set_transform_space bpt_set_option bpt_film_write_exr bpt_write_exr_file""".split()
 
 
 def load_library():
@@ -56,6 +56,8 @@ def load_library():
     lib.bpt_render_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_void_p]
     lib.bpt_render_bands_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.bpt_sync.argtypes = [C.c_void_p]
+    lib.bpt_film_write_exr.argtypes = [C.c_void_p, C.c_char_p]
+    lib.bpt_write_exr_file.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_void_p]
     lib.bpt_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
     lib.bpt_sampler_spp.argtypes = [C.c_void_p]
     lib.bpt_film_clear.argtypes = [C.c_void_p]
@@ -130,6 +132,10 @@ class Engine:
 
     def set_option(self, name, value):
         self._ck(self.lib.bpt_set_option(self.h, name.encode(), int(value)), "bpt_set_option")
+
+    def write_exr(self, path):
+        """Film "rgb" -> R G B, Film "gbuffer" -> the 25 reference channels, as an uncompressed FLOAT OpenEXR file."""
+        self._ck(self.lib.bpt_film_write_exr(self.h, os.fspath(path).encode()), "bpt_film_write_exr")
 
     def sync(self):
         self._ck(self.lib.bpt_sync(self.h), "bpt_sync")

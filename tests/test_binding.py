@@ -41,6 +41,13 @@ def _scenes():
         "smoke_homogeneous": lambda d: scenes.smoke(d, res=(64, 64), spp=4, homogeneous=True),
         "gbuffer_world": lambda d: scenes.as_gbuffer(scenes.cornell(d, res=(64, 64), spp=4), "world"),
     }
+    def filtered(d, flt):
+        p = scenes.cornell(d, res=(32, 32), spp=1)
+        txt = open(p).read().replace("WorldBegin", "PixelFilter " + flt + "\nWorldBegin")
+        open(p, "w").write(txt)
+        return p
+    for k, flt in enumerate(['"box"', '"triangle" "float xradius" 1.5', '"mitchell" "float B" 0.2', '"sinc" "float tau" 2']):
+        cases["filter_%d" % k] = (lambda d, flt=flt: filtered(d, flt))
     for parts in ("t", "s", "r", "ts", "tr", "rs", "trs"):   # every combination of translate / rotate / scale in the instance transform
         cases["instances_" + parts] = (lambda d, parts=parts: scenes.instanced(d, n_inst=40, subdiv=1, res=(32, 32), spp=1, material="diffuse", parts=parts))
     return cases

@@ -291,6 +291,38 @@ def test_gbuffer_film_matches_reference_golden(E, tmp_path, name, gen, kw, csys)
 
 
 @pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/bin/pbrt not on this box")
+@pytest.mark.parametrize("flt", ['"box"', '"triangle"', '"mitchell"', '"sinc"', '"gaussian" "float sigma" 0.8 "float xradius" 2',
+                                 '"mitchell" "float B" 0.2 "float C" 0.4 "float xradius" 1.5 "float yradius" 2.5'])
+def test_every_pixel_filter_of_the_dispatch_surface_matches_the_live_reference(E, tmp_path, flt):
+    """Filter {Box, Gaussian, Mitchell, LanczosSinc, Triangle} (base/filter.h:25): FilterSampler tables for the sampled ones (signed
+    weights for the negative lobes), analytic sampling for box and triangle -- Cornell box, bit-identical to the reference."""
+    from pbrt_v4_b200 import scenes, imageio
+    path = scenes.cornell(str(tmp_path), res=(48, 48), spp=8)
+    s = open(path).read().replace("WorldBegin", "PixelFilter " + flt + "\nWorldBegin")
+    open(path, "w").write(s)
+    subprocess.check_call([REF_EXE, "--quiet", "--seed", "0", "--outfile", str(tmp_path / "ref.pfm"), path])
+    ref = imageio.read_pfm(str(tmp_path / "ref.pfm"))
+    img = _render(E, path, 8)
+    assert (bits(img) == bits(ref)).all(), flt
+
+
+def test_film_write_exr_carries_the_resolved_channels(E, tmp_path):
+    """bpt_film_write_exr: the 25 GBuffer channels (and R G B for Film "rgb") in the file == bpt_film_resolve[_gbuffer]."""
+    from pbrt_v4_b200 import scenes, imageio
+    path = scenes.as_gbuffer(scenes.cornell(str(tmp_path), res=(64, 64), spp=4), "camera")
+    e = E.Engine(0)
+    e.load_pbrt(path, seed=0)
+    e.render(0, 4)
+    g = e.gbuffer()
+    e.write_exr(tmp_path / "g.exr")
+    e.close()
+    names, back, attrs = imageio.read_exr(tmp_path / "g.exr")
+    assert sorted(names) == sorted(E.Engine.GBUFFER_CHANNELS) and "samplesPerPixel" in attrs and "pixelBounds" in attrs
+    for k, nm in enumerate(names):
+        assert (bits(back[..., k]) == bits(g[..., E.Engine.GBUFFER_CHANNELS.index(nm)])).all(), nm
+
+
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/bin/pbrt not on this box")
 def test_image_matches_live_reference_on_32k_triangle_heightfield(E, tmp_path):
     from pbrt_v4_b200 import scenes, imageio
     path = scenes.diffuse_heightfield(str(tmp_path), n=128, res=(192, 192), spp=64)

@@ -166,3 +166,34 @@ def test_bvh_builder_core_builds_valid_trees_and_treelets_lower_the_sah_cost(bvh
         per_axis = run("0", "peraxis")
         assert plain["sah_internal_area_sum"] < 0.7 * per_axis["sah_internal_area_sum"]
         assert opt["camera"]["nodes_per_ray"] < per_axis["camera"]["nodes_per_ray"]
+
+
+GBUFFER_NAMES = ["R", "G", "B", "Albedo.R", "Albedo.G", "Albedo.B", "P.X", "P.Y", "P.Z", "dzdx", "dzdy", "N.X", "N.Y", "N.Z", "Ns.X", "Ns.Y",
+                 "Ns.Z", "u", "v", "Variance.R", "Variance.G", "Variance.B", "RelativeVariance.R", "RelativeVariance.G", "RelativeVariance.B"]
+
+
+def test_exr_writer_is_read_back_by_openexr_and_by_an_independent_parser(tmp_path, engine_module):
+    """csrc/exr_writer.h (f2: the multi-channel EXR a denoiser reads, film.cpp:688-803): an RGB file is read by OpenCV's bundled
+    OpenEXR library bit for bit, and the 25-channel GBuffer layout by an independent parser of the file format (channels stored
+    alphabetically, found by name)."""
+    from pbrt_v4_b200 import imageio
+    rng = np.random.default_rng(2)
+    rgb = rng.normal(size=(9, 6, 3)).astype(np.float32)
+    rgb[0, 0] = [np.inf, -0.0, 1e-42]    # specials survive (FLOAT channels, no compression)
+    imageio.write_exr(tmp_path / "rgb.exr", rgb, ["R", "G", "B"])
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    try:
+        import cv2
+        a = cv2.imread(str(tmp_path / "rgb.exr"), cv2.IMREAD_UNCHANGED)
+    except Exception:
+        a = None
+    if a is not None:
+        assert a.dtype == np.float32 and (a[..., ::-1].copy().view(np.uint32) == rgb.view(np.uint32)).all()
+    g = rng.normal(size=(5, 7, 25)).astype(np.float32)
+    imageio.write_exr(tmp_path / "g.exr", g, GBUFFER_NAMES)
+    names, back, attrs = imageio.read_exr(tmp_path / "g.exr")
+    assert sorted(names) == sorted(GBUFFER_NAMES) and names == sorted(names)
+    for k, nm in enumerate(names):
+        assert (back[..., k].view(np.uint32) == g[..., GBUFFER_NAMES.index(nm)].view(np.uint32)).all(), nm
+    for req in ("channels", "compression", "dataWindow", "displayWindow", "lineOrder", "pixelAspectRatio", "screenWindowCenter", "screenWindowWidth"):
+        assert req in attrs
