@@ -137,8 +137,8 @@ typedef struct {
 } bpt_light;
 
 enum { BPT_MEDIUM_UNIFORMGRID = 0, BPT_MEDIUM_HOMOGENEOUS = 1 };
-/* Medium (media.h:217-352: HomogeneousMedium, GridMedium; created in media.cpp:165-201,249-330).  Emission is not supported:
- * Le must be BPT_SPEC_NONE. */
+/* Medium (media.h:217-352: HomogeneousMedium, GridMedium; created in media.cpp:165-201,249-330), emission through "Le" / "Lescale"
+ * (no "temperature" grids). */
 typedef struct {
     int type;                     /* BPT_MEDIUM_* */
     bpt_mat4 world_from_medium;   /* CTM at MakeNamedMedium */
@@ -147,7 +147,8 @@ typedef struct {
     float scale, g;
     float bounds[6];              /* p0, p1 */
     const float *density; int nx, ny, nz;
-    bpt_spectrum Le; float Le_scale;
+    bpt_spectrum Le; float Le_scale;                /* emission: "Le" (BPT_SPEC_NONE: none) and, homogeneous, the float "Lescale" */
+    const float *Le_scale_grid;                      /* uniformgrid: the "Lescale" float array (nx*ny*nz values) or NULL */
 } bpt_medium;
 
 typedef struct {

@@ -300,7 +300,9 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
         else ErrorExit("medium type \"%s\" is not implemented by the engine", type);
         if (!d.GetOneString("preset", "").empty()) ErrorExit("medium presets are not implemented by the engine");
         m.sigma_a = GetSpectrum(d, "sigma_a", st); m.sigma_s = GetSpectrum(d, "sigma_s", st); m.Le = GetSpectrum(d, "Le", st);
-        m.scale = d.GetOneFloat("scale", 1.f); m.g = d.GetOneFloat("g", 0.f); m.Le_scale = d.GetOneFloat("Lescale", 1.f);
+        m.scale = d.GetOneFloat("scale", 1.f); m.g = d.GetOneFloat("g", 0.f);
+        m.Le_scale = m.type == BPT_MEDIUM_HOMOGENEOUS ? d.GetOneFloat("Lescale", 1.f) : 1.f;
+        if (!d.GetFloatArray("temperature").empty()) ErrorExit("temperature grids are not implemented by the engine");
         m.world_from_medium = ToB(mr.renderFromMedium.GetMatrix()); m.medium_from_world = ToB(mr.renderFromMedium.GetInverseMatrix());
         m.bounds[3] = m.bounds[4] = m.bounds[5] = 1;
         if (m.type == BPT_MEDIUM_UNIFORMGRID) {
@@ -308,6 +310,11 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
             m.nx = d.GetOneInt("nx", 1); m.ny = d.GetOneInt("ny", 1); m.nz = d.GetOneInt("nz", 1);
             if (dens.empty() || (size_t)m.nx * m.ny * m.nz != dens.size()) ErrorExit("uniformgrid medium: density count != nx*ny*nz");
             m.density = st.F(std::vector<float>(dens.begin(), dens.end()));
+            std::vector<Float> les = d.GetFloatArray("Lescale");
+            if (!les.empty()) {
+                if (les.size() != dens.size()) ErrorExit("uniformgrid medium: \"Lescale\" count != nx*ny*nz");
+                m.Le_scale_grid = st.F(std::vector<float>(les.begin(), les.end()));
+            }
             Point3f p0 = d.GetOnePoint3f("p0", Point3f(0, 0, 0)), p1 = d.GetOnePoint3f("p1", Point3f(1, 1, 1));
             m.bounds[0] = p0.x; m.bounds[1] = p0.y; m.bounds[2] = p0.z; m.bounds[3] = p1.x; m.bounds[4] = p1.y; m.bounds[5] = p1.z;
         }

@@ -51,7 +51,7 @@ struct OwnedLight {
     std::vector<float> image;
 };
 struct OwnedAreaLight { bpt_area_light a; OwnedSpectrum L; };
-struct OwnedMedium { bpt_medium m; OwnedSpectrum sigma_a, sigma_s; std::vector<float> density; };
+struct OwnedMedium { bpt_medium m; OwnedSpectrum sigma_a, sigma_s, Le; std::vector<float> density, leScale; };
 
 template <typename T>
 struct DevBuf {
@@ -462,13 +462,13 @@ extern "C" int bpt_scene_add_light(bpt_engine *e, const bpt_light *l) {
 extern "C" int bpt_scene_add_medium(bpt_engine *e, const bpt_medium *m) {
     if (!e || !m) return BPT_ERR_INVALID;
     if (m->type != BPT_MEDIUM_UNIFORMGRID && m->type != BPT_MEDIUM_HOMOGENEOUS) return e->fail(BPT_ERR_UNSUPPORTED, "medium type not implemented (homogeneous, uniformgrid)");
-    if (m->Le.kind != BPT_SPEC_NONE) return e->fail(BPT_ERR_UNSUPPORTED, "emissive media are not implemented");
     if (m->type == BPT_MEDIUM_UNIFORMGRID && (!m->density || m->nx <= 0 || m->ny <= 0 || m->nz <= 0)) return e->fail(BPT_ERR_INVALID, "uniformgrid medium needs a density grid");
     e->media.emplace_back();
     OwnedMedium &o = e->media.back();
-    o.m = *m; o.sigma_a.Set(m->sigma_a); o.sigma_s.Set(m->sigma_s);
+    o.m = *m; o.sigma_a.Set(m->sigma_a); o.sigma_s.Set(m->sigma_s); o.Le.Set(m->Le);
     if (m->type == BPT_MEDIUM_UNIFORMGRID) o.density.assign(m->density, m->density + (size_t)m->nx * m->ny * m->nz);
-    o.m.density = nullptr;
+    if (m->type == BPT_MEDIUM_UNIFORMGRID && m->Le_scale_grid) o.leScale.assign(m->Le_scale_grid, m->Le_scale_grid + (size_t)m->nx * m->ny * m->nz);
+    o.m.density = nullptr; o.m.Le_scale_grid = nullptr;
     return BPT_OK;
 }
 // Engine options that are not part of the scene description (they survive bpt_scene_begin).
@@ -937,6 +937,32 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             for (float &x : v) x *= om.m.scale;
             (k == 0 ? dm.sigmaA : dm.sigmaS) = spool.addDense(v);
         }
+        // emission (HomogeneousMedium::Create media.cpp:165-201, GridMedium::Create :249-330): Le is an illuminant spectrum normalised
+        // by its photometric integral; homogeneous media fold Lescale into the table, grid media keep it in the LeScale grid
+        dm.Le = -1;
+        std::vector<float> leGrid;
+        if (om.Le.s.kind != BPT_SPEC_NONE) {
+            SpectrumRec r; std::string serr;
+            if (!MakeSpectrumRec(e, om.Le, ST_ILLUMINANT, spool, &r, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, "medium Le: " + serr);
+            std::vector<float> v(kNLambda);
+            for (int l = 0; l < kNLambda; ++l) v[l] = EvalRecAt(r, spool.pool, (float)(kLambdaMin + l));
+            float maxV = *std::max_element(v.begin(), v.end());
+            if (maxV > 0) {
+                // SpectrumToPhotometric (util/spectrum.cpp): an RGBIlluminantSpectrum contributes its illuminant only
+                float photometric = 0;
+                if (om.Le.s.kind == BPT_SPEC_RGB) { for (int l = 0; l < kNLambda; ++l) photometric += cieY[l] * illum[l]; }
+                else { for (int l = 0; l < kNLambda; ++l) photometric += cieY[l] * v[l]; }
+                if (dm.type == MEDIUM_HOMOGENEOUS) {
+                    float LeScale = om.m.Le_scale / photometric;
+                    for (float &x : v) x *= LeScale;
+                } else {
+                    float LeNorm = 1 / photometric;
+                    if (om.leScale.empty()) leGrid = {LeNorm};
+                    else { leGrid = om.leScale; for (float &x : leGrid) x *= LeNorm; }
+                }
+                dm.Le = spool.addDense(v);
+            }
+        }
         if (dm.type == MEDIUM_GRID) {
             Xform renderFromMedium = ResolveRenderFromObject(space, spaces, om.m.world_from_medium, om.m.medium_from_world);   // RenderFromObject() (scene.h:475-477)
             dm.mInv = ToMat4(renderFromMedium.mInv);
@@ -953,6 +979,12 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             e->mediumBufs.emplace_back(new DevBuf<float>());
             ECK(e->mediumBufs.back()->upload(maj));
             dm.majorant = e->mediumBufs.back()->p;
+            if (dm.Le >= 0) {
+                e->mediumBufs.emplace_back(new DevBuf<float>());
+                ECK(e->mediumBufs.back()->upload(leGrid));
+                dm.leScale = e->mediumBufs.back()->p;
+                if (leGrid.size() == 1) dm.lnx = dm.lny = dm.lnz = 1; else { dm.lnx = nx; dm.lny = ny; dm.lnz = nz; }
+            }
         }
     }
     ECK(e->dMedia.upload(dmedia));

@@ -1,7 +1,7 @@
 // media.h -- participating media on the path, float-exact restatement of the reference's CPU semantics:
 //   HGPhaseFunction / HenyeyGreenstein / SampleHenyeyGreenstein   media.h:43-71, util/scattering.h:49-58, util/sampling.cpp:348-372
 //   HomogeneousMajorantIterator, DDAMajorantIterator              media.h:80-102, 136-214
-//   HomogeneousMedium / GridMedium ::SamplePoint / ::SampleRay    media.h:217-262, 265-352 (no emission: Le is rejected at intake)
+//   HomogeneousMedium / GridMedium ::SamplePoint / ::SampleRay    media.h:217-262, 265-352 (emission: Le / Lescale; no temperature grids)
 //   SampledGrid<Float>::Lookup (trilinear, zero outside)          util/containers.h:803-835
 //   Bounds3f::IntersectP(o, d, tMax, &t0, &t1), Bounds3f::Offset  util/vecmath.h:1547-1571, 1323-1332
 //   SampleT_maj                                                   media.h:736-800
@@ -27,6 +27,10 @@ struct DeviceMedium {
     int nx, ny, nz;
     const float *majorant;       // mres^3 maximum densities (MajorantGrid::voxels)
     int mres[3];
+    // emission (media.h:223-246 homogeneous: Le_spec scaled by Lescale / photometric norm; :296-318 grid: LeScale grid x Le_spec)
+    int Le;                      // offset of the 471-entry Le_spec table, -1: the medium does not emit
+    const float *leScale;        // GridMedium::LeScale (SampledGrid<Float>), lnx*lny*lnz
+    int lnx, lny, lnz;
 };
 
 // ------------------------------------------------------------------ phase function
@@ -217,18 +221,44 @@ BPT_HD MajorantIter MediumSampleRay(const DeviceMedium &m, const float *specPool
     return it;
 }
 
-struct MediumProps { Spec sigma_a, sigma_s; };
+struct MediumProps { Spec sigma_a, sigma_s, Le; };
+// SampledGrid<Float>::Lookup (util/containers.h:803-835) over an arbitrary grid: trilinear, zero outside
+BPT_HD float ScalarGridLookup(const float *g, int nx, int ny, int nz, Vec3 p) {
+    auto fetch = [&](int x, int y, int z) -> float {
+        if (x < 0 || y < 0 || z < 0 || x >= nx || y >= ny || z >= nz) return 0.f;
+        size_t i = ((size_t)z * ny + y) * nx + x;
+#if defined(__CUDA_ARCH__)
+        return __ldg(g + i);
+#else
+        return g[i];
+#endif
+    };
+    float sx = p.x * nx - .5f, sy = p.y * ny - .5f, sz = p.z * nz - .5f;
+    float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
+    int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    float dx = sx - (float)ix, dy = sy - (float)iy, dz = sz - (float)iz;
+    float d00 = Lerp(dx, fetch(ix, iy, iz), fetch(ix + 1, iy, iz));
+    float d10 = Lerp(dx, fetch(ix, iy + 1, iz), fetch(ix + 1, iy + 1, iz));
+    float d01 = Lerp(dx, fetch(ix, iy, iz + 1), fetch(ix + 1, iy, iz + 1));
+    float d11 = Lerp(dx, fetch(ix, iy + 1, iz + 1), fetch(ix + 1, iy + 1, iz + 1));
+    return Lerp(dz, Lerp(dy, d00, d10), Lerp(dy, d01, d11));
+}
 BPT_HD MediumProps MediumSamplePoint(const DeviceMedium &m, const float *specPool, Pt3 p, const Wavelengths &wl) {
     MediumProps mp;
     mp.sigma_a = DenseSample(specPool + m.sigmaA, wl);
     mp.sigma_s = DenseSample(specPool + m.sigmaS, wl);
+    mp.Le = Spec(0.f);
     if (m.type == MEDIUM_GRID) {
         Pt3 pm = ApplyInversePoint(m.mInv, p);
         Vec3 po = BoundsOffset(m.bmin, m.bmax, pm);
         float d = GridLookup(m, po);
         mp.sigma_a *= d;
         mp.sigma_s *= d;
-    }
+        if (m.Le >= 0) {   // GridMedium::SamplePoint: scale = LeScale.Lookup(p); if (scale > 0) Le = scale * Le_spec.Sample(lambda)
+            float scale = ScalarGridLookup(m.leScale, m.lnx, m.lny, m.lnz, po);
+            if (scale > 0) mp.Le = DenseSample(specPool + m.Le, wl) * scale;
+        }
+    } else if (m.Le >= 0) mp.Le = DenseSample(specPool + m.Le, wl);   // HomogeneousMedium: Le_spec already scaled
     return mp;
 }
 

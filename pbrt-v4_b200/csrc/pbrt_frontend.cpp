@@ -558,17 +558,23 @@ bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::st
         else { err = "medium type \"" + type + "\" is not supported (homogeneous, uniformgrid)"; return false; }
         if (pl.find("preset")) { err = "medium presets are not supported"; return false; }
         if (!getSpectrum(pl, "sigma_a", &m.sigma_a) || !getSpectrum(pl, "sigma_s", &m.sigma_s) || !getSpectrum(pl, "Le", &m.Le)) return false;
-        m.scale = pl.f("scale", 1.f); m.g = pl.f("g", 0.f); m.Le_scale = pl.f("Lescale", 1.f);
+        m.scale = pl.f("scale", 1.f); m.g = pl.f("g", 0.f);
+        m.Le_scale = m.type == BPT_MEDIUM_HOMOGENEOUS ? pl.f("Lescale", 1.f) : 1.f;
         m.world_from_medium = ToB(gs.ctm.m); m.medium_from_world = ToB(gs.ctm.mInv);
         m.bounds[0] = m.bounds[1] = m.bounds[2] = 0; m.bounds[3] = m.bounds[4] = m.bounds[5] = 1;
         if (m.type == BPT_MEDIUM_UNIFORMGRID) {
             Param *dn = pl.find("density");
             if (!dn || dn->nums.empty()) { err = "uniformgrid medium: no \"density\" values"; return false; }
-            if (pl.find("temperature")) { err = "emissive grid media are not supported"; return false; }
+            if (pl.find("temperature")) { err = "temperature grids are not supported"; return false; }
             m.nx = pl.i("nx", 1); m.ny = pl.i("ny", 1); m.nz = pl.i("nz", 1);
             if ((size_t)m.nx * m.ny * m.nz != dn->nums.size()) { err = "uniformgrid medium: density count != nx*ny*nz"; return false; }
             densityStore.emplace_back(new std::vector<float>(dn->nums.begin(), dn->nums.end()));
             m.density = densityStore.back()->data();
+            if (Param *ls = pl.find("Lescale")) {   // GridMedium: a float array, one value per density sample (media.cpp:293-306)
+                if (ls->nums.size() != dn->nums.size()) { err = "uniformgrid medium: \"Lescale\" count != nx*ny*nz"; return false; }
+                densityStore.emplace_back(new std::vector<float>(ls->nums.begin(), ls->nums.end()));
+                m.Le_scale_grid = densityStore.back()->data();
+            }
             if (Param *q = pl.find("p0")) { if (q->nums.size() != 3) { err = "p0 needs three values"; return false; } for (int k = 0; k < 3; ++k) m.bounds[k] = (float)q->nums[k]; }
             if (Param *q = pl.find("p1")) { if (q->nums.size() != 3) { err = "p1 needs three values"; return false; } for (int k = 0; k < 3; ++k) m.bounds[3 + k] = (float)q->nums[k]; }
         }

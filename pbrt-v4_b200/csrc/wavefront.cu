@@ -608,7 +608,17 @@ __global__ void __launch_bounds__(128, BPT_MEDIUM_CTAS) k_sample_medium(RenderCt
             if (!beta.IsNonZero()) { slot = -1; continue; }   // terminated
             MediumProps mp = MediumSamplePoint(rc.media[mediumId], rc.sv.specPool, p, wl);
             Spec sigma_maj = trk.seg.sigma_maj, T_maj = trk.T_maj;
-            // (no emission: media with Le are rejected at scene intake)
+            // Handle medium emission (cpu/integrators.cpp:989-1000): added before the absorption / scattering / null decision
+            if (depth < maxDepth && mp.Le.IsNonZero()) {
+                float pdfE = sigma_maj[0] * T_maj[0];
+                Spec betap = beta * T_maj / pdfE;
+                Spec r_e = r_u * sigma_maj * T_maj / pdfE;
+                if (r_e.IsNonZero()) {
+                    Spec Lm = ld4(&ps.L[slot]);
+                    Lm += betap * mp.sigma_a * mp.Le / r_e.Average();
+                    st4(&ps.L[slot], Lm);
+                }
+            }
             float pAbsorb = mp.sigma_a[0] / sigma_maj[0];
             float pScatter = mp.sigma_s[0] / sigma_maj[0];
             float pNull = stdmax(0.f, 1 - pAbsorb - pScatter);

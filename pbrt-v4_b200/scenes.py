@@ -220,15 +220,18 @@ def smoke_density(grid=256, seed=7):
     return d.astype(np.float32)   # indexed [z][y][x]: x fastest, as GridMedium expects
 
 
-def smoke(outdir, grid=256, res=(1024, 1024), spp=2048, maxdepth=5, seed=7, homogeneous=False):
+def smoke(outdir, grid=256, res=(1024, 1024), spp=2048, maxdepth=5, seed=7, homogeneous=False, emission=None):
     """Config 5: grid-density smoke (sigma_a = 2, sigma_s = 8, g = 0.3) inside a unit box with the "interface" material,
-    diffuse floor, quad light; null-scattering VolPath."""
+    diffuse floor, quad light; null-scattering VolPath.  `emission`: None, "le" (an RGB "Le" on the medium; homogeneous media also get
+    a "Lescale") or "grid" (uniformgrid: "Le" plus a per-voxel "Lescale" array = the density, so that the dense core glows)."""
     os.makedirs(outdir, exist_ok=True)
     s = _header(res, spp, maxdepth, ((0, 1.1, 3.0), (0, 0.55, 0)), 38)
     quad = "Shape \"trianglemesh\" \"integer indices\" [0 1 2 0 2 3] \"point3 P\" [%s]\n"
     s += "AttributeBegin\n  Translate -0.5 0.05 -0.5\n"
     if homogeneous:
         s += "  MakeNamedMedium \"smoke\" \"string type\" \"homogeneous\" \"rgb sigma_a\" [2 2 2] \"rgb sigma_s\" [8 8 8] \"float g\" 0.3 \"float scale\" 0.25\n"
+        if emission:
+            s += "    \"rgb Le\" [1.0 0.55 0.2] \"float Lescale\" 3\n"
     else:
         d = smoke_density(grid, seed)
         s += (f"  MakeNamedMedium \"smoke\" \"string type\" \"uniformgrid\" \"rgb sigma_a\" [2 2 2] \"rgb sigma_s\" [8 8 8] \"float g\" 0.3\n"
@@ -236,6 +239,10 @@ def smoke(outdir, grid=256, res=(1024, 1024), spp=2048, maxdepth=5, seed=7, homo
         flat = d.reshape(-1)
         s += "\n".join(" ".join(repr(float(v)) for v in flat[i:i + 16]) for i in range(0, flat.size, 16))
         s += "\n    ]\n"
+        if emission:
+            s += "    \"rgb Le\" [1.0 0.55 0.2]\n"
+        if emission == "grid":
+            s += "    \"float Lescale\" [\n" + "\n".join(" ".join(repr(float(4 * v)) for v in flat[i:i + 16]) for i in range(0, flat.size, 16)) + "\n    ]\n"
     s += "AttributeEnd\n"
     s += "AttributeBegin\n  AreaLightSource \"diffuse\" \"rgb L\" [30 28 24]\n  Material \"diffuse\" \"rgb reflectance\" [0 0 0]\n  "
     s += quad % "-0.4 2.2 -0.4  0.4 2.2 -0.4  0.4 2.2 0.4  -0.4 2.2 0.4"

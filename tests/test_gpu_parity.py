@@ -205,6 +205,11 @@ LIVE_SCENES = {
     "config4_instanced1k_coated_256_16spp": ("instanced", dict(n_inst=1000, subdiv=2, res=(256, 256), material="coatedconductor"), 16, 4),
     "config4_instanced1k_diffuse_256_16spp": ("instanced", dict(n_inst=1000, subdiv=2, res=(256, 256), material="diffuse"), 16, 4),
     "config5_smoke64_128_64spp": ("smoke", dict(grid=64, res=(128, 128)), 64, 0),
+    # emissive media (cpu/integrators.cpp:989-1000; media.h:223-246, 296-318): "Le" on a homogeneous medium, on a grid medium, and
+    # with a per-voxel "Lescale" array
+    "emissive_homogeneous_64_32spp": ("smoke", dict(res=(64, 64), homogeneous=True, emission="le"), 32, 0),
+    "emissive_grid16_64_32spp": ("smoke", dict(grid=16, res=(64, 64), emission="le"), 32, 0),
+    "emissive_gridscale16_64_32spp": ("smoke", dict(grid=16, res=(64, 64), emission="grid"), 32, 0),
 }
 
 

@@ -27,7 +27,7 @@ namespace {
 struct Spec { bpt_spectrum s; std::vector<float> samples; };
 struct Mesh { bpt_mesh m; std::vector<float> P, N, UV; std::vector<int> idx; };
 struct Light { bpt_light l; std::vector<float> img; Spec L; };
-struct Medium { bpt_medium m; std::vector<float> density; Spec sa, ss, Le; };
+struct Medium { bpt_medium m; std::vector<float> density, leScale; Spec sa, ss, Le; };
 struct Material { bpt_material m; Spec sp[8]; };
 struct AreaLight { bpt_area_light a; Spec L; };
 }  // namespace
@@ -124,6 +124,7 @@ int bpt_scene_add_light(bpt_engine *e, const bpt_light *l) {
 int bpt_scene_add_medium(bpt_engine *e, const bpt_medium *m) {
     e->media.emplace_back(); Medium &o = e->media.back(); o.m = *m; o.sa = Own(m->sigma_a); o.ss = Own(m->sigma_s); o.Le = Own(m->Le);
     if (m->density) o.density.assign(m->density, m->density + (size_t)m->nx * m->ny * m->nz);
+    if (m->Le_scale_grid) o.leScale.assign(m->Le_scale_grid, m->Le_scale_grid + (size_t)m->nx * m->ny * m->nz);
     return BPT_OK;
 }
 int bpt_scene_set_camera_medium(bpt_engine *e, int m) { e->cameraMedium = m; return BPT_OK; }
@@ -160,7 +161,8 @@ int bpt_scene_commit(bpt_engine *e) {
         const Medium &md = e->media[id];
         Xform rfm = ResolveRenderFromObject(e->space, cs, md.m.world_from_medium, md.m.medium_from_world);
         char b[96]; snprintf(b, sizeof(b), " grid=%dx%dx%d:%016" PRIx64, md.m.nx, md.m.ny, md.m.nz, Fnv(md.density.data(), md.density.size() * 4));
-        std::string s = "medium{type=" + std::to_string(md.m.type) + " sa=" + S(md.sa) + " ss=" + S(md.ss) + " Le=" + S(md.Le) + " scale=" + F(md.m.scale) + " g=" + F(md.m.g);
+        std::string s = "medium{type=" + std::to_string(md.m.type) + " sa=" + S(md.sa) + " ss=" + S(md.ss) + " Le=" + S(md.Le) + " scale=" + F(md.m.scale) + " g=" + F(md.m.g) +
+                        " Lescale=" + F(md.Le.s.kind == BPT_SPEC_NONE ? 1.f : md.m.Le_scale) + ":" + std::to_string(md.leScale.empty() ? 0ull : (unsigned long long)Fnv(md.leScale.data(), md.leScale.size() * 4));
         if (md.m.type == BPT_MEDIUM_UNIFORMGRID) {
             s += b; s += " bounds=";
             for (int k = 0; k < 6; ++k) s += F(md.m.bounds[k]) + (k < 5 ? "," : "");
