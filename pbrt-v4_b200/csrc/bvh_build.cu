@@ -10,6 +10,7 @@
 //      subtrees of <= 3 triangles become leaf children, octant slot assignment, 8-bit box quantisation
 // The hierarchy only decides which triangles are tested; the hit record does not depend on it.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -115,35 +116,56 @@ __global__ void bottom_up_kernel(Tree T, const float4 *__restrict__ tris, const 
 }
 
 // Treelet restructuring, level-synchronous: nodes of equal height root disjoint subtrees, and restructuring the treelet of a node
-// only rewires nodes strictly inside its subtree, so all treelet roots of one height are processed by one launch (one thread per
+// only rewires nodes strictly inside its subtree, so all treelet roots of one height are processed together (one thread per
 // treelet, every lane busy), heights ascending (children before parents).  The first version climbed the tree inside the
 // bottom-up kernel -- one live lane per warp near the top: 32 ms for 1 M triangles, 290 ms for 10 M (profiles/r02a sweep).
 constexpr int kMaxLevels = 128;
-__global__ void level_count_kernel(const int *__restrict__ cnt, const int *__restrict__ height, int nInternal, int gamma, int *levelCount) {
-    __shared__ int h[kMaxLevels];
-    for (int k = threadIdx.x; k < kMaxLevels; k += blockDim.x) h[k] = 0;
+constexpr int kTreeletBlock = 64;
+// One cooperative launch per restructuring round: histogram of the treelet roots by height, offsets, scatter into per-level lists,
+// then the levels in ascending order with a grid-wide barrier between them.  No host round trip and no launch per level: two
+// rounds used to be ~200 launches + 2 host syncs, which is what a 1 k-triangle object definition or a 20 k-instance top level paid
+// (20 ms per re-commit of the 20 k-instance scene, profiles/r02g).  The DP tables of OptimizeTreelet live in shared memory.
+__global__ void __launch_bounds__(kTreeletBlock) treelet_round_kernel(Tree T, const int *height, int gamma,
+                                                                     int *levels /* count | offset | cursor, kMaxLevels each */, int *list) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ float s_copt[(1 << kTreeletLeaves) * kTreeletBlock];
+    __shared__ unsigned char s_popt[(1 << kTreeletLeaves) * kTreeletBlock];
+    __shared__ int s_h[kMaxLevels], s_base[kMaxLevels];
+    const int nInternal = T.n - 1;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nThreads = gridDim.x * blockDim.x;
+    int *levelCount = levels, *levelOffset = levels + kMaxLevels, *levelCursor = levels + 2 * kMaxLevels;
+    // (levels[] is zeroed by the host with a memset before the launch)
+    // ---- histogram
+    for (int k = threadIdx.x; k < kMaxLevels; k += blockDim.x) s_h[k] = 0;
     __syncthreads();
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nInternal && cnt[i] >= gamma) atomicAdd(&h[min(height[i], kMaxLevels - 1)], 1);
+    for (int i = tid; i < nInternal; i += nThreads)
+        if (__ldcg(T.cnt + i) >= gamma) atomicAdd(&s_h[min(__ldcg(height + i), kMaxLevels - 1)], 1);
     __syncthreads();
-    for (int k = threadIdx.x; k < kMaxLevels; k += blockDim.x) if (h[k]) atomicAdd(&levelCount[k], h[k]);
-}
-__global__ void level_scatter_kernel(const int *__restrict__ cnt, const int *__restrict__ height, int nInternal, int gamma,
-                                     const int *__restrict__ levelOffset, int *levelCursor, int *list) {
-    __shared__ int h[kMaxLevels], base[kMaxLevels];
-    for (int k = threadIdx.x; k < kMaxLevels; k += blockDim.x) h[k] = 0;
+    for (int k = threadIdx.x; k < kMaxLevels; k += blockDim.x) if (s_h[k]) atomicAdd(&levelCount[k], s_h[k]);
+    grid.sync();
+    // ---- offsets (every block computes them for itself: 128 values)
+    if (threadIdx.x == 0) { int acc = 0; for (int k = 0; k < kMaxLevels; ++k) { s_base[k] = acc; acc += __ldcg(levelCount + k); } }
     __syncthreads();
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int lvl = -1, local = 0;
-    if (i < nInternal && cnt[i] >= gamma) { lvl = min(height[i], kMaxLevels - 1); local = atomicAdd(&h[lvl], 1); }
-    __syncthreads();
-    for (int k = threadIdx.x; k < kMaxLevels; k += blockDim.x) if (h[k]) base[k] = atomicAdd(&levelCursor[k], h[k]);
-    __syncthreads();
-    if (lvl >= 0) list[levelOffset[lvl] + base[lvl] + local] = i;
-}
-__global__ void treelet_level_kernel(Tree T, const int *__restrict__ list, int count) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) OptimizeTreelet(T, list[i]);
+    if (blockIdx.x == 0) for (int k = threadIdx.x; k < kMaxLevels; k += blockDim.x) levelOffset[k] = s_base[k];
+    // ---- scatter
+    for (int i = tid; i < nInternal; i += nThreads)
+        if (__ldcg(T.cnt + i) >= gamma) {
+            int lvl = min(__ldcg(height + i), kMaxLevels - 1);
+            int pos = atomicAdd(&levelCursor[lvl], 1);
+            list[s_base[lvl] + pos] = i;
+        }
+    grid.sync();
+    // ---- levels, ascending
+    float *copt = s_copt + threadIdx.x;
+    unsigned char *popt = s_popt + threadIdx.x;
+    for (int lvl = 0; lvl < kMaxLevels; ++lvl) {
+        const int n = __ldcg(levelCount + lvl);
+        if (n == 0) continue;                       // (uniform over the grid)
+        const int off = s_base[lvl];
+        for (int i = tid; i < n; i += nThreads) OptimizeTreelet<kTreeletBlock>(T, __ldcg(list + off + i), copt, popt);
+        grid.sync();
+    }
 }
 
 // ---- collapse (bvh_build_core.h CollapseOne), one thread per wide node of the current level
@@ -206,25 +228,23 @@ bool BuildWideBVH(const float4 *trisDev, int n, WideBVH *out, cudaStream_t strea
     int gamma = kTreeletLeaves;
     CK(cudaMemsetAsync(flags, 0, sizeof(int) * n, stream));
     bottom_up_kernel<true><<<(n + 127) / 128, 128, 0, stream>>>(T, trisDev, svals, flags, height);
-    for (int r = 0; r < rounds && n > kTreeletLeaves; ++r, gamma *= 2) {
-        if (r > 0) {   // heights of the restructured tree
-            CK(cudaMemsetAsync(flags, 0, sizeof(int) * n, stream));
-            bottom_up_kernel<false><<<(n + 127) / 128, 128, 0, stream>>>(T, trisDev, svals, flags, height);
+    if (rounds > 0 && n > kTreeletLeaves) {
+        int dev = 0, sms = 0, perSM = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, treelet_round_kernel, kTreeletBlock, 0));
+        // cooperative grid: all blocks resident; small trees get a small grid (the barriers are cheaper)
+        int blocks = std::max(1, std::min(sms * std::max(perSM, 1), (n / 4 + kTreeletBlock - 1) / kTreeletBlock));
+        for (int r = 0; r < rounds; ++r, gamma *= 2) {
+            if (r > 0) {   // heights of the restructured tree
+                CK(cudaMemsetAsync(flags, 0, sizeof(int) * n, stream));
+                bottom_up_kernel<false><<<(n + 127) / 128, 128, 0, stream>>>(T, trisDev, svals, flags, height);
+            }
+            CK(cudaMemsetAsync(levels, 0, sizeof(int) * 3 * kMaxLevels, stream));
+            int gammaArg = gamma;
+            void *args[] = {(void *)&T, (void *)&height, (void *)&gammaArg, (void *)&levels, (void *)&levelList};
+            CK(cudaLaunchCooperativeKernel((const void *)treelet_round_kernel, dim3(blocks), dim3(kTreeletBlock), args, 0, stream));
         }
-        int hostLevels[2 * kMaxLevels];
-        CK(cudaMemsetAsync(levels, 0, sizeof(int) * 3 * kMaxLevels, stream));
-        level_count_kernel<<<(n - 1 + 255) / 256, 256, 0, stream>>>(cnt, height, n - 1, gamma, levels);
-        CK(cudaMemcpyAsync(hostLevels, levels, sizeof(int) * kMaxLevels, cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
-        int total = 0;
-        for (int k = 0; k < kMaxLevels; ++k) { hostLevels[kMaxLevels + k] = total; total += hostLevels[k]; }
-        if (total == 0) break;
-        CK(cudaMemcpyAsync(levels + kMaxLevels, hostLevels + kMaxLevels, sizeof(int) * kMaxLevels, cudaMemcpyHostToDevice, stream));
-        level_scatter_kernel<<<(n - 1 + 255) / 256, 256, 0, stream>>>(cnt, height, n - 1, gamma, levels + kMaxLevels, levels + 2 * kMaxLevels, levelList);
-        // (the clamped top bin may mix heights >= kMaxLevels - 1: never reached by a radix tree over 63-bit keys of < 2^31 primitives)
-        for (int k = 0; k < kMaxLevels; ++k)
-            if (hostLevels[k] > 0)
-                treelet_level_kernel<<<(hostLevels[k] + 63) / 64, 64, 0, stream>>>(T, levelList + hostLevels[kMaxLevels + k], hostLevels[k]);
     }
     // collapse, level by level
     int hostCounters[4] = {1, 0, 0, 0};   // root wide node is node 0

@@ -114,7 +114,12 @@ BPT_HD void RadixTreeNode(const uint64_t *keys, int n, int i, int *lc, int *rc) 
 // internal nodes -- is found by dynamic programming over all subsets, and the treelet's internal nodes are rewired in place
 // when that lowers the cost.  Returns true if the tree was changed.  Called for a node only after both its subtrees are final.
 constexpr int kTreeletLeaves = 7;
-BPT_HD bool OptimizeTreelet(const Tree &T, int root) {
+// copt / popt: the dynamic-programming tables over the 2^7 leaf subsets, element s at [s * STRIDE].  The CUDA kernel keeps them in
+// shared memory, one column per thread (STRIDE = block size: conflict-free, and no 1.1 KB-per-thread local-memory frame -- with the
+// tables in local memory the restructuring pass was memory-bound: 3.2 ms per round for 1 M triangles, profiles/r02g); the host
+// harness passes plain arrays (STRIDE = 1).  Subset areas are recomputed from the leaf boxes (registers) where they are needed.
+template <int STRIDE>
+BPT_HD bool OptimizeTreelet(const Tree &T, int root, float *copt, unsigned char *popt) {
     const int nInternalTotal = T.n - 1;
     int leaf[kTreeletLeaves], inner[kTreeletLeaves - 1];
     float4 lmn[kTreeletLeaves], lmx[kTreeletLeaves];
@@ -143,14 +148,13 @@ BPT_HD bool OptimizeTreelet(const Tree &T, int root) {
     }
     if (nl < 4) return false;   // 3 leaves or fewer: nothing a different topology could gain that the next level up does not see
     const unsigned full = (1u << nl) - 1u;
-    float area[1 << kTreeletLeaves], copt[1 << kTreeletLeaves];
-    unsigned char popt[1 << kTreeletLeaves];
-    for (unsigned s = 1; s <= full; ++s) {
+    auto subsetArea = [&](unsigned sub) {
         float4 mn = make_float4(3.4e38f, 3.4e38f, 3.4e38f, 0), mx = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, 0);
-        for (int k = 0; k < nl; ++k) if (s >> k & 1) { mn = Min4(mn, lmn[k]); mx = Max4(mx, lmx[k]); }
-        area[s] = HalfArea(mn, mx);
-    }
-    for (int k = 0; k < nl; ++k) copt[1u << k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < kTreeletLeaves; ++k) if (k < nl && (sub >> k & 1)) { mn = Min4(mn, lmn[k]); mx = Max4(mx, lmx[k]); }
+        return HalfArea(mn, mx);
+    };
+    for (int k = 0; k < nl; ++k) copt[(1u << k) * STRIDE] = 0.f;
     for (int sz = 2; sz <= nl; ++sz) {
         for (unsigned s = 1; s <= full; ++s) {
             if (Popc32(s) != sz) continue;
@@ -158,15 +162,15 @@ BPT_HD bool OptimizeTreelet(const Tree &T, int root) {
             unsigned delta = (s - 1) & s;          // s without its lowest bit: partitions enumerated once (lowest bit stays in s ^ p)
             unsigned p = (0u - delta) & s;
             do {
-                float c = copt[p] + copt[s ^ p];
+                float c = copt[p * STRIDE] + copt[(s ^ p) * STRIDE];
                 if (c < best) { best = c; bp = p; }
                 p = (p - delta) & s;
             } while (p != 0);
-            copt[s] = area[s] + best;
-            popt[s] = (unsigned char)bp;
+            copt[s * STRIDE] = subsetArea(s) + best;
+            popt[s * STRIDE] = (unsigned char)bp;
         }
     }
-    if (!(copt[full] < curCost * 0.9999f)) return false;
+    if (!(copt[full * STRIDE] < curCost * 0.9999f)) return false;
     // rewire: internal ids are reused, root keeps its id (and its box and count)
     unsigned stackS[kTreeletLeaves]; int stackId[kTreeletLeaves];
     int sp = 0, nextI = 1;
@@ -174,7 +178,7 @@ BPT_HD bool OptimizeTreelet(const Tree &T, int root) {
     while (sp > 0) {
         --sp;
         unsigned s = stackS[sp]; int id = stackId[sp];
-        unsigned part[2] = {popt[s], s ^ (unsigned)popt[s]};
+        unsigned part[2] = {popt[s * STRIDE], s ^ (unsigned)popt[s * STRIDE]};
         int cid[2];
         for (int c = 0; c < 2; ++c) {
             unsigned ps = part[c];
@@ -192,6 +196,12 @@ BPT_HD bool OptimizeTreelet(const Tree &T, int root) {
         BVHB_ST(T.left + id, cid[0]); BVHB_ST(T.right + id, cid[1]);
     }
     return true;
+}
+// plain-array form (host harness)
+inline bool OptimizeTreelet(const Tree &T, int root) {
+    float copt[1 << kTreeletLeaves];
+    unsigned char popt[1 << kTreeletLeaves];
+    return OptimizeTreelet<1>(T, root, copt, popt);
 }
 
 // ---- collapse of the binary tree into the 8-wide compressed nodes of bvh.cuh, one call per wide node

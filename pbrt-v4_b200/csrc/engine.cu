@@ -98,6 +98,54 @@ __global__ void k_assemble_triangles(const float *__restrict__ P, const int *__r
     out[3 * (size_t)t] = r[0]; out[3 * (size_t)t + 1] = r[1]; out[3 * (size_t)t + 2] = r[2];
 }
 
+// Tight bounds of an instance for the top-level BVH: the object's triangles taken through renderFromInstance vertex by vertex.
+// The reference bounds a TransformedPrimitive by the transformed corners of the object's AABB ((*renderFromPrimitive)(primitive.Bounds()),
+// cpu/primitive.cpp:106-110), which for a rotated instance of a round object is up to sqrt(3) larger per axis -- and every false
+// overlap is an instance entry (ray transform + BLAS root visit) at the bottom of the traversal's lane utilisation (ncu r02g: 46 % of
+// the two-level kernel's instructions run with 4-8 lanes).  Bounds only cull: the hit found is the same (tests compare bit for bit).
+// The scene bounds the infinite lights are preprocessed with stay the reference's (union of the loose bounds).
+__global__ void k_instance_bounds(const float4 *__restrict__ triPool, const DeviceInstance *__restrict__ inst, const int *__restrict__ instFirstTri,
+                                  const int *__restrict__ instTriCount, int nInst, float4 *__restrict__ tlasPrims) {
+    const int i = blockIdx.x;
+    if (i >= nInst) return;
+    const float (*m)[4] = inst[i].m.m;
+    float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    const float4 *t = triPool + 3 * (size_t)instFirstTri[i];
+    const int nv = 3 * instTriCount[i];
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        float4 p = t[v];
+        float xp = m[0][0] * p.x + m[0][1] * p.y + m[0][2] * p.z + m[0][3];
+        float yp = m[1][0] * p.x + m[1][1] * p.y + m[1][2] * p.z + m[1][3];
+        float zp = m[2][0] * p.x + m[2][1] * p.y + m[2][2] * p.z + m[2][3];
+        float wp = m[3][0] * p.x + m[3][1] * p.y + m[3][2] * p.z + m[3][3];
+        if (wp != 1) { xp /= wp; yp /= wp; zp /= wp; }
+        lo[0] = fminf(lo[0], xp); lo[1] = fminf(lo[1], yp); lo[2] = fminf(lo[2], zp);
+        hi[0] = fmaxf(hi[0], xp); hi[1] = fmaxf(hi[1], yp); hi[2] = fmaxf(hi[2], zp);
+    }
+    __shared__ float s[6][32];
+    for (int k = 0; k < 3; ++k)
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if ((threadIdx.x & 31) == 0) for (int k = 0; k < 3; ++k) { s[k][w] = lo[k]; s[3 + k][w] = hi[k]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int ww = 1; ww < nw; ++ww) for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], s[k][ww]); hi[k] = fmaxf(hi[k], s[3 + k][ww]); }
+        // the hit is computed in instance space from the inverse-transformed ray: leave room for the rounding of this forward transform
+        for (int k = 0; k < 3; ++k) { float pad = 1e-5f * fmaxf(fmaxf(fabsf(lo[k]), fabsf(hi[k])), hi[k] - lo[k]); lo[k] -= pad; hi[k] += pad; }
+        float4 old0 = tlasPrims[3 * (size_t)i];
+        // never larger than the reference-style bounds already there (the intersection of two valid bounds is a valid bound)
+        float4 old1 = tlasPrims[3 * (size_t)i + 1];
+        lo[0] = fmaxf(lo[0], old0.x); lo[1] = fmaxf(lo[1], old0.y); lo[2] = fmaxf(lo[2], old0.z);
+        hi[0] = fminf(hi[0], old1.x); hi[1] = fminf(hi[1], old1.y); hi[2] = fminf(hi[2], old1.z);
+        tlasPrims[3 * (size_t)i] = make_float4(lo[0], lo[1], lo[2], old0.w);
+        tlasPrims[3 * (size_t)i + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+        tlasPrims[3 * (size_t)i + 2] = make_float4(lo[0], lo[1], lo[2], 0.f);
+    }
+}
+
 struct bpt_engine {
     int device = 0;
     int smCount = 148;
@@ -146,6 +194,7 @@ struct bpt_engine {
     DevBuf<DeviceImageLight> dImageLights;
     DevBuf<DeviceInstance> dInstances;
     DevBuf<float4> dTlasPrims;
+    DevBuf<int> dInstFirstTri, dInstTriCount;
     DevBuf<int> hitInst;
     DevBuf<float> hitT;
     DevBuf<int> pathMedium;
@@ -1058,6 +1107,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     } else {
         e->blas.resize(nObjects + 1);
         std::vector<float4> tlasPrims;
+        std::vector<int> instGroup;
         auto addInst = [&](int group, const Xform *T) {
             const WideBVH &b = e->blas[group];
             DeviceInstance di{};
@@ -1072,6 +1122,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             } else { M4 I; di.m = ToMat4(I); di.mInv = ToMat4(I); }
             int id = (int)dinst.size();
             dinst.push_back(di);
+            instGroup.push_back(group);
             // top-level "primitive": a degenerate triangle whose bounds are the instance bounds; p0.w carries the instance id
             tlasPrims.push_back(make_float4(bb.pMin.x, bb.pMin.y, bb.pMin.z, b2f((uint32_t)id)));
             tlasPrims.push_back(make_float4(bb.pMax.x, bb.pMax.y, bb.pMax.z, 0.f));
@@ -1091,11 +1142,26 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         }
         if (dinst.empty()) return e->fail(BPT_ERR_INVALID, "scene has no geometry");
         ECK(e->dTlasPrims.upload(tlasPrims));
+        ECK(e->dInstances.upload(dinst));
+        // scene bounds as the reference computes them (union of the transformed object AABBs): what the infinite lights see
+        Bounds3 looseScene;
+        for (size_t k = 0; k < dinst.size(); ++k) {
+            looseScene = Union(looseScene, Pt3(tlasPrims[3 * k].x, tlasPrims[3 * k].y, tlasPrims[3 * k].z));
+            looseScene = Union(looseScene, Pt3(tlasPrims[3 * k + 1].x, tlasPrims[3 * k + 1].y, tlasPrims[3 * k + 1].z));
+        }
+        if (!std::getenv("BPT_LOOSE_INSTANCE_BOUNDS")) {
+            std::vector<int> first(dinst.size()), count(dinst.size());
+            for (size_t k = 0; k < dinst.size(); ++k) { first[k] = groupStart[instGroup[k]]; count[k] = groupStart[instGroup[k] + 1] - groupStart[instGroup[k]]; }
+            ECK(e->dInstFirstTri.upload(first)); ECK(e->dInstTriCount.upload(count));
+            k_instance_bounds<<<(unsigned)dinst.size(), 128, 0, e->stream>>>(e->triPool.p, e->dInstances.p, e->dInstFirstTri.p, e->dInstTriCount.p, (int)dinst.size(), e->dTlasPrims.p);
+        }
         {
             const char *tl = std::getenv("BPT_TLAS_LEAF");
             if (!BuildWideBVH(e->dTlasPrims.p, (int)dinst.size(), &e->bvh, e->stream, berr, tl ? std::atoi(tl) : 1, e->treeletRounds)) return e->fail(BPT_ERR_CUDA, berr);
         }
-        ECK(e->dInstances.upload(dinst));
+        // (the top-level root now carries the tight bounds; the scene bounds stay the reference's)
+        e->bvh.bmin[0] = looseScene.pMin.x; e->bvh.bmin[1] = looseScene.pMin.y; e->bvh.bmin[2] = looseScene.pMin.z;
+        e->bvh.bmax[0] = looseScene.pMax.x; e->bvh.bmax[1] = looseScene.pMax.y; e->bvh.bmax[2] = looseScene.pMax.z;
     }
     ECK(cudaStreamSynchronize(e->stream));
     auto tb1 = std::chrono::steady_clock::now();
