@@ -163,7 +163,34 @@ __global__ void __launch_bounds__(kTreeletBlock) treelet_round_kernel(Tree T, co
         const int n = __ldcg(levelCount + lvl);
         if (n == 0) continue;                       // (uniform over the grid)
         const int off = s_base[lvl];
-        for (int i = tid; i < n; i += nThreads) OptimizeTreelet<kTreeletBlock>(T, __ldcg(list + off + i), copt, popt);
+        if (n >= nThreads / 32) {
+            for (int i = tid; i < n; i += nThreads) OptimizeTreelet<kTreeletBlock>(T, __ldcg(list + off + i), copt, popt);
+        } else {
+            // few treelets at this height (the upper levels: ~40 heights with a handful of nodes each): one WARP per treelet, the
+            // subsets of each size spread over the lanes -- the sequential DP of one thread (~60 us) was the critical path of the
+            // round (40 levels x 60 us of a 3 ms round for 1 M triangles)
+            const int lane = threadIdx.x & 31, warp = tid >> 5, nWarps = nThreads >> 5;
+            float *wc = s_copt + (threadIdx.x >> 5) * (1 << kTreeletLeaves);
+            unsigned char *wp = s_popt + (threadIdx.x >> 5) * (1 << kTreeletLeaves);
+            for (int i = warp; i < n; i += nWarps) {
+                const int root = __ldcg(list + off + i);
+                Treelet t;
+                FormTreelet(T, root, t);          // (all lanes: same addresses, one transaction each)
+                const int nl = t.nl;
+                if (nl >= 4) {
+                    const unsigned full = (1u << nl) - 1u;
+                    if (lane < nl) wc[1u << lane] = 0.f;
+                    __syncwarp();
+                    for (int sz = 2; sz <= nl; ++sz) {
+                        for (unsigned sset = lane + 1; sset <= full; sset += 32)
+                            if (__popc(sset) == sz) TreeletSolveSubset<1>(t, sset, wc, wp);
+                        __syncwarp();
+                    }
+                    if (lane == 0 && wc[full] < t.curCost * 0.9999f) RewireTreelet<1>(T, root, t, wp);
+                }
+                __syncwarp();
+            }
+        }
         grid.sync();
     }
 }

@@ -118,19 +118,23 @@ constexpr int kTreeletLeaves = 7;
 // shared memory, one column per thread (STRIDE = block size: conflict-free, and no 1.1 KB-per-thread local-memory frame -- with the
 // tables in local memory the restructuring pass was memory-bound: 3.2 ms per round for 1 M triangles, profiles/r02g); the host
 // harness passes plain arrays (STRIDE = 1).  Subset areas are recomputed from the leaf boxes (registers) where they are needed.
-template <int STRIDE>
-BPT_HD bool OptimizeTreelet(const Tree &T, int root, float *copt, unsigned char *popt) {
-    const int nInternalTotal = T.n - 1;
+struct Treelet {
     int leaf[kTreeletLeaves], inner[kTreeletLeaves - 1];
     float4 lmn[kTreeletLeaves], lmx[kTreeletLeaves];
+    int nl;
+    float curCost;
+};
+// grow the treelet rooted at `root` to (up to) 7 leaves by repeatedly opening the leaf with the largest surface area
+BPT_HD void FormTreelet(const Tree &T, int root, Treelet &t) {
+    const int nInternalTotal = T.n - 1;
     float larea[kTreeletLeaves];
     int nl = 0, ni = 0;
     auto addLeaf = [&](int id) {
-        leaf[nl] = id; lmn[nl] = BVHB_LD(T.nmin + id); lmx[nl] = BVHB_LD(T.nmax + id);
-        larea[nl] = id < nInternalTotal ? HalfArea(lmn[nl], lmx[nl]) : -1.f;   // real leaves cannot be opened
+        t.leaf[nl] = id; t.lmn[nl] = BVHB_LD(T.nmin + id); t.lmx[nl] = BVHB_LD(T.nmax + id);
+        larea[nl] = id < nInternalTotal ? HalfArea(t.lmn[nl], t.lmx[nl]) : -1.f;   // real leaves cannot be opened
         ++nl;
     };
-    inner[ni++] = root;
+    t.inner[ni++] = root;
     addLeaf(BVHB_LD(T.left + root));
     addLeaf(BVHB_LD(T.right + root));
     float curCost = HalfArea(BVHB_LD(T.nmin + root), BVHB_LD(T.nmax + root));
@@ -138,40 +142,41 @@ BPT_HD bool OptimizeTreelet(const Tree &T, int root, float *copt, unsigned char 
         int best = -1; float bestA = -1.f;
         for (int k = 0; k < nl; ++k) if (larea[k] > bestA) { bestA = larea[k]; best = k; }
         if (best < 0) break;
-        int b = leaf[best];
+        int b = t.leaf[best];
         curCost += larea[best];
-        inner[ni++] = b;
+        t.inner[ni++] = b;
         int l = BVHB_LD(T.left + b), r = BVHB_LD(T.right + b);
-        leaf[best] = l; lmn[best] = BVHB_LD(T.nmin + l); lmx[best] = BVHB_LD(T.nmax + l);
-        larea[best] = l < nInternalTotal ? HalfArea(lmn[best], lmx[best]) : -1.f;
+        t.leaf[best] = l; t.lmn[best] = BVHB_LD(T.nmin + l); t.lmx[best] = BVHB_LD(T.nmax + l);
+        larea[best] = l < nInternalTotal ? HalfArea(t.lmn[best], t.lmx[best]) : -1.f;
         addLeaf(r);
     }
-    if (nl < 4) return false;   // 3 leaves or fewer: nothing a different topology could gain that the next level up does not see
-    const unsigned full = (1u << nl) - 1u;
-    auto subsetArea = [&](unsigned sub) {
-        float4 mn = make_float4(3.4e38f, 3.4e38f, 3.4e38f, 0), mx = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, 0);
+    t.nl = nl; t.curCost = curCost;
+}
+BPT_HD float TreeletSubsetArea(const Treelet &t, unsigned sub) {
+    float4 mn = make_float4(3.4e38f, 3.4e38f, 3.4e38f, 0), mx = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, 0);
 #pragma unroll
-        for (int k = 0; k < kTreeletLeaves; ++k) if (k < nl && (sub >> k & 1)) { mn = Min4(mn, lmn[k]); mx = Max4(mx, lmx[k]); }
-        return HalfArea(mn, mx);
-    };
-    for (int k = 0; k < nl; ++k) copt[(1u << k) * STRIDE] = 0.f;
-    for (int sz = 2; sz <= nl; ++sz) {
-        for (unsigned s = 1; s <= full; ++s) {
-            if (Popc32(s) != sz) continue;
-            float best = 3.4e38f; unsigned bp = 0;
-            unsigned delta = (s - 1) & s;          // s without its lowest bit: partitions enumerated once (lowest bit stays in s ^ p)
-            unsigned p = (0u - delta) & s;
-            do {
-                float c = copt[p * STRIDE] + copt[(s ^ p) * STRIDE];
-                if (c < best) { best = c; bp = p; }
-                p = (p - delta) & s;
-            } while (p != 0);
-            copt[s * STRIDE] = subsetArea(s) + best;
-            popt[s * STRIDE] = (unsigned char)bp;
-        }
-    }
-    if (!(copt[full * STRIDE] < curCost * 0.9999f)) return false;
-    // rewire: internal ids are reused, root keeps its id (and its box and count)
+    for (int k = 0; k < kTreeletLeaves; ++k) if (k < t.nl && (sub >> k & 1)) { mn = Min4(mn, t.lmn[k]); mx = Max4(mx, t.lmx[k]); }
+    return HalfArea(mn, mx);
+}
+// best split of subset s given the optimal costs of all smaller subsets: copt[s] = area(s) + min over partitions
+template <int STRIDE>
+BPT_HD void TreeletSolveSubset(const Treelet &t, unsigned s, float *copt, unsigned char *popt) {
+    float best = 3.4e38f; unsigned bp = 0;
+    unsigned delta = (s - 1) & s;          // s without its lowest bit: partitions enumerated once (lowest bit stays in s ^ p)
+    unsigned p = (0u - delta) & s;
+    do {
+        float c = copt[p * STRIDE] + copt[(s ^ p) * STRIDE];
+        if (c < best) { best = c; bp = p; }
+        p = (p - delta) & s;
+    } while (p != 0);
+    copt[s * STRIDE] = TreeletSubsetArea(t, s) + best;
+    popt[s * STRIDE] = (unsigned char)bp;
+}
+// rewire: internal ids are reused, root keeps its id (and its box and count)
+template <int STRIDE>
+BPT_HD void RewireTreelet(const Tree &T, int root, const Treelet &t, const unsigned char *popt) {
+    const int nl = t.nl;
+    const unsigned full = (1u << nl) - 1u;
     unsigned stackS[kTreeletLeaves]; int stackId[kTreeletLeaves];
     int sp = 0, nextI = 1;
     stackS[sp] = full; stackId[sp] = root; ++sp;
@@ -182,12 +187,12 @@ BPT_HD bool OptimizeTreelet(const Tree &T, int root, float *copt, unsigned char 
         int cid[2];
         for (int c = 0; c < 2; ++c) {
             unsigned ps = part[c];
-            if ((ps & (ps - 1)) == 0) cid[c] = leaf[Ctz32(ps)];
+            if ((ps & (ps - 1)) == 0) cid[c] = t.leaf[Ctz32(ps)];
             else {
-                cid[c] = inner[nextI++];
+                cid[c] = t.inner[nextI++];
                 float4 mn = make_float4(3.4e38f, 3.4e38f, 3.4e38f, 0), mx = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, 0);
                 int count = 0;
-                for (int k = 0; k < nl; ++k) if (ps >> k & 1) { mn = Min4(mn, lmn[k]); mx = Max4(mx, lmx[k]); count += BVHB_LD(T.cnt + leaf[k]); }
+                for (int k = 0; k < nl; ++k) if (ps >> k & 1) { mn = Min4(mn, t.lmn[k]); mx = Max4(mx, t.lmx[k]); count += BVHB_LD(T.cnt + t.leaf[k]); }
                 BVHB_ST(T.nmin + cid[c], mn); BVHB_ST(T.nmax + cid[c], mx); BVHB_ST(T.cnt + cid[c], count);
                 stackS[sp] = ps; stackId[sp] = cid[c]; ++sp;
             }
@@ -195,6 +200,20 @@ BPT_HD bool OptimizeTreelet(const Tree &T, int root, float *copt, unsigned char 
         }
         BVHB_ST(T.left + id, cid[0]); BVHB_ST(T.right + id, cid[1]);
     }
+}
+template <int STRIDE>
+BPT_HD bool OptimizeTreelet(const Tree &T, int root, float *copt, unsigned char *popt) {
+    Treelet t;
+    FormTreelet(T, root, t);
+    const int nl = t.nl;
+    if (nl < 4) return false;   // 3 leaves or fewer: nothing a different topology could gain that the next level up does not see
+    const unsigned full = (1u << nl) - 1u;
+    for (int k = 0; k < nl; ++k) copt[(1u << k) * STRIDE] = 0.f;
+    for (int sz = 2; sz <= nl; ++sz)
+        for (unsigned s = 1; s <= full; ++s)
+            if (Popc32(s) == sz) TreeletSolveSubset<STRIDE>(t, s, copt, popt);
+    if (!(copt[full * STRIDE] < t.curCost * 0.9999f)) return false;
+    RewireTreelet<STRIDE>(T, root, t, popt);
     return true;
 }
 // plain-array form (host harness)

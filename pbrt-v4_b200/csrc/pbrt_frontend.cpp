@@ -10,6 +10,10 @@
 //            LightSource("infinite") Shape("trianglemesh"|"plymesh") ObjectBegin/End ObjectInstance
 //            MakeNamedMedium MediumInterface Include
 // Anything else is an error (never silently ignored), matching the reference's ErrorExit behaviour.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <cmath>
 #include <chrono>
 #include <cstdio>
@@ -26,6 +30,10 @@
 
 using namespace bpt;
 
+#ifdef BPT_FRONTEND_IN_LIBRARY
+// (engine.cu) moves the mesh arrays into the engine; the stand-alone build of this file for the ABI recorder uses the public call
+int bpt_internal_add_mesh_move(bpt_engine *e, const bpt_mesh *m, std::vector<float> &&P, std::vector<float> &&N, std::vector<float> &&UV, std::vector<int> &&idx);
+#endif
 namespace {
 
 struct Param {
@@ -227,14 +235,20 @@ struct Frontend {
         if (binary) {
             // fast path: the body is read in one go and decoded with precomputed per-property offsets (the generic
             // stream reader below costs ~0.25 s per million triangles, which is half a bench step)
+            // the body is decoded straight out of a read-only mapping of the file (no 19 MB staging vector to allocate, zero and fill)
             std::streampos here = in.tellg();
-            in.seekg(0, std::ios::end);
-            size_t nBytes = (size_t)(in.tellg() - here);
-            in.seekg(here);
-            std::vector<unsigned char> body(nBytes);
-            in.read((char *)body.data(), (std::streamsize)nBytes);
-            if (!in) { err = path + ": truncated PLY body"; return false; }
-            const unsigned char *q = body.data(), *end = q + nBytes;
+            struct Mapping {
+                void *base = MAP_FAILED; size_t len = 0; int fd = -1;
+                ~Mapping() { if (base != MAP_FAILED) munmap(base, len); if (fd >= 0) close(fd); }
+            } map;
+            map.fd = open(path.c_str(), O_RDONLY);
+            struct stat sb;
+            if (map.fd < 0 || fstat(map.fd, &sb) != 0 || (size_t)sb.st_size < (size_t)here) { err = path + ": cannot map PLY body"; return false; }
+            map.len = (size_t)sb.st_size;
+            map.base = mmap(nullptr, map.len, PROT_READ, MAP_PRIVATE | MAP_POPULATE, map.fd, 0);
+            if (map.base == MAP_FAILED) { err = path + ": cannot map PLY body"; return false; }
+            size_t nBytes = map.len - (size_t)here;
+            const unsigned char *q = (const unsigned char *)map.base + (size_t)here, *end = q + nBytes;
             auto tcode = [&](const std::string &t) { if (t == "float" || t == "float32") return 0; if (t == "double" || t == "float64") return 1; if (t == "int" || t == "int32") return 2;
                                                       if (t == "uint" || t == "uint32") return 3; if (t == "uchar" || t == "uint8") return 4; if (t == "char" || t == "int8") return 5;
                                                       if (t == "short" || t == "int16") return 6; if (t == "ushort" || t == "uint16") return 7; return -1; };
@@ -649,8 +663,12 @@ bool Frontend::finish() {
     }
     for (auto &m : meshes) {
         bpt_mesh bm = m->m;
+#ifdef BPT_FRONTEND_IN_LIBRARY
+        if (!ck(bpt_internal_add_mesh_move(e, &bm, std::move(m->P), std::move(m->N), std::move(m->UV), std::move(m->idx)))) return false;
+#else
         bm.P = m->P.data(); bm.N = m->N.empty() ? nullptr : m->N.data(); bm.UV = m->UV.empty() ? nullptr : m->UV.data(); bm.indices = m->idx.data();
         if (!ck(bpt_scene_add_mesh(e, &bm))) return false;
+#endif
     }
     for (auto &in : instances) if (!ck(bpt_scene_add_instance(e, &in))) return false;
     for (auto &l : lights) if (!ck(bpt_scene_add_light(e, &l))) return false;
