@@ -117,6 +117,8 @@ typedef struct {
     int area_light;               /* index into the area-light array, -1 = none */
     int medium_inside, medium_outside;   /* -1 = none */
     int object_id;                /* -1: top-level shape; >= 0: belongs to instance definition object_id */
+    int has_alpha;                /* Shape "float alpha" < 1: the stochastic alpha test of GeometricPrimitive::Intersect (cpu/primitive.cpp:56-75) */
+    float alpha;                  /* constant alpha (texture-valued alpha: not implemented) */
 } bpt_mesh;
 
 typedef struct {

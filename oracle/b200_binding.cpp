@@ -343,8 +343,9 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
             for (Point2f u : mesh.uv) { UV.push_back(u.x); UV.push_back(u.y); }
             idx.assign(mesh.triIndices.begin(), mesh.triIndices.end());
         } else ErrorExit(&sh.loc, "shape \"%s\" is not implemented by the engine (triangle meshes)", sh.name.ToString());
-        if (!d.GetTexture("alpha").empty() || d.GetOneFloat("alpha", 1.f) != 1.f) ErrorExit(&sh.loc, "alpha is not implemented by the engine");
+        if (!d.GetTexture("alpha").empty()) ErrorExit(&sh.loc, "texture-valued alpha is not implemented by the engine");
         bpt_mesh m; std::memset(&m, 0, sizeof(m));
+        if (Float alpha = d.GetOneFloat("alpha", 1.f); alpha < 1.f) { m.has_alpha = 1; m.alpha = alpha; }   // getAlphaTexture (scene.cpp)
         m.n_vertices = (int)P.size() / 3; m.n_triangles = (int)idx.size() / 3;
         m.P = st.F(std::move(P)); m.N = N.empty() ? nullptr : st.F(std::move(N)); m.UV = UV.empty() ? nullptr : st.F(std::move(UV)); m.indices = st.I(std::move(idx));
         m.world_from_object = ToB(sh.renderFromObject->GetMatrix()); m.object_from_world = ToB(sh.renderFromObject->GetInverseMatrix());

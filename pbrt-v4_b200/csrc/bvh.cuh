@@ -27,6 +27,7 @@ struct BVHView {
     const float4 *nodes;      // 5 float4 per wide node; node 0 = root (instanced scenes: the top-level BVH over instances)
     const float4 *tris;       // 3 float4 per triangle in leaf order (p0.w = original triangle id; top level: instance id)
     const DeviceInstance *instances;   // non-null: two-level scene
+    const float *meshAlpha;            // per mesh id: constant alpha of alpha-tested meshes (class bit 30 of the leaf record)
 };
 
 #define BPT_STACK_SIZE 40
@@ -123,6 +124,23 @@ BPT_D bool IntersectTrianglePre(const RayPre &r, float tMax, Pt3 p0, Pt3 p1, Pt3
     return true;
 }
 
+// GeometricPrimitive::Intersect's stochastic alpha test (cpu/primitive.cpp:56-75): the hit is ignored when HashFloat(ray.o, ray.d) > alpha
+// -- a function of the ray the primitive sees (the instance-space ray inside an instance) and of the mesh, so a ray either passes
+// through every triangle of an alpha mesh or hits them.  The reference then re-intersects the SAME shape from behind the hit
+// (`Intersect(rNext, ...)` on this primitive), which a planar triangle cannot satisfy: the triangle simply does not count.
+constexpr unsigned kClsAlpha = 0x40000000u;
+BPT_D bool AlphaRejects(const BVHView &bvh, const RayPre &r, unsigned cls, float meshIdBits) {
+    if (!(cls & kClsAlpha)) return false;
+    float a = __ldg(bvh.meshAlpha + __float_as_int(meshIdBits));
+    if (a >= 1) return false;
+    float u = 1.f;
+    if (a > 0) {
+        uint64_t w[3] = {(uint64_t)f2b(r.o.x) | ((uint64_t)f2b(r.o.y) << 32), (uint64_t)f2b(r.o.z) | ((uint64_t)f2b(r.d.x) << 32),
+                         (uint64_t)f2b(r.d.y) | ((uint64_t)f2b(r.d.z) << 32)};
+        u = (float)(uint32_t)MurmurHash64A(w, 24, 0) * 0x1p-32f;
+    }
+    return u > a;
+}
 BPT_D unsigned ExtractByte(unsigned x, unsigned i) { return (x >> (i * 8)) & 0xff; }
 BPT_D unsigned SignExtendS8x4(unsigned x) {
     unsigned r;
@@ -251,7 +269,8 @@ BPT_D void TraceRay(const BVHView &bvh, Pt3 o, Vec3 d, float tMax, HitRec *rec, 
             if (COUNT) ++*nTris;
             TriHit th;
             if (!(__float_as_uint(b.w) & 0x80000000u) &&
-                IntersectTrianglePre(rp, rec->t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th)) {
+                IntersectTrianglePre(rp, rec->t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th) &&
+                !AlphaRejects(bvh, rp, __float_as_uint(b.w), c.w)) {
                 rec->tri = (int)tri; rec->b0 = th.b0; rec->b1 = th.b1; rec->b2 = th.b2; rec->t = th.t;
                 if (ANYHIT) return;
                 tBox = th.t * (1 + 2 * gamma_n(3));
@@ -457,7 +476,8 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
 #else
                     TriHit th;
                     if (!(__float_as_uint(b.w) & 0x80000000u) &&
-                        IntersectTrianglePre(rp, rec.t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th)) {
+                        IntersectTrianglePre(rp, rec.t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th) &&
+                        !AlphaRejects(bvh, rp, __float_as_uint(b.w), c.w)) {
                         rec.tri = (int)tri; rec.b0 = th.b0; rec.b1 = th.b1; rec.b2 = th.b2; rec.t = th.t;
                         if (ANYHIT) { finished = true; head = tail; }
                         else tBox = th.t * (1 + 2 * gamma_n(3));
@@ -633,7 +653,8 @@ BPT_D void TraversePersistentInst(const BVHView &bvh, const DeviceInstance *inst
                     if (COUNT) ++*nTris;
                     TriHit th;
                     if (!(__float_as_uint(b.w) & 0x80000000u) &&
-                        IntersectTrianglePre(rp, rec.t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th)) {
+                        IntersectTrianglePre(rp, rec.t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th) &&
+                        !AlphaRejects(bvh, rp, __float_as_uint(b.w), c.w)) {
                         rec.tri = (int)tri; rec.b0 = th.b0; rec.b1 = th.b1; rec.b2 = th.b2; rec.t = th.t; rec.inst = inst;
                         hitHere = true;
                         if (ANYHIT) { finished = true; head = tail; }

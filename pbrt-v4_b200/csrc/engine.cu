@@ -172,6 +172,7 @@ struct bpt_engine {
     DevBuf<float> rawP;              // staging of object-space vertices / indices of device-assembled meshes
     DevBuf<int> rawIdx;
     DevBuf<DeviceMesh> dMeshes;
+    DevBuf<float> dMeshAlpha;        // per mesh: constant alpha of the stochastic alpha test (1 = none)
     DevBuf<int> indexPool;
     DevBuf<float> nPool, uvPool, specPool;
     DevBuf<DeviceMaterial> dMaterials;
@@ -767,6 +768,8 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     }
 
     // ---- meshes: transform to render space (TriangleMesh ctor util/mesh.cpp:25-70), build pools and lights
+    std::vector<float> meshAlpha(e->meshes.size(), 1.f);
+    bool anyAlpha = false;
     std::unique_ptr<float4[]> tri;   // host-assembled ranges only (untouched pages of the rest are never committed)
     std::vector<DeviceMesh> dmesh(e->meshes.size());
     std::vector<int> indexPool;
@@ -858,6 +861,9 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             e->haveAreaLights = true;
         }
         unsigned cls = (unsigned)matType | (emissive ? 0x100u : 0u);
+        const bool alphaTested = om.m.has_alpha && om.m.alpha < 1;
+        if (alphaTested) { cls |= kClsAlpha; anyAlpha = true; }
+        meshAlpha[mi] = alphaTested ? om.m.alpha : 1.f;
         triRanges.push_back(TriRange{triCursor, om.m.n_triangles, deviceAssemble, mi, ToMat4(renderFromObject.m), cls});
         if (deviceAssemble) {
             devVerts = std::max(devVerts, (size_t)om.m.n_vertices); devIdx = std::max(devIdx, (size_t)om.m.n_triangles);
@@ -1075,6 +1081,8 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     }
     ECK(cudaStreamSynchronize(e->stream));
     ECK(e->dMeshes.upload(dmesh));
+    ECK(e->dMeshAlpha.upload(meshAlpha));
+    (void)anyAlpha;
     ECK(e->indexPool.upload(indexPool));
     ECK(e->nPool.upload(nPool));
     ECK(e->uvPool.upload(uvPool));
@@ -1242,7 +1250,6 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     rc.ps.ctx1 = f4 + 10 * (size_t)maxPaths; rc.ps.ctx2 = f4 + 11 * (size_t)maxPaths;
     rc.ps.misc = e->stateMisc.p; rc.ps.aux = e->stateAux.p;
     if (df.isGBuffer) {
-        if (!e->media.empty() || e->materialPresent[MAT_INTERFACE]) return e->fail(BPT_ERR_UNSUPPORTED, "GBufferFilm with media / interface surfaces is not implemented");
         ECK(e->visSurf.alloc((size_t)maxPaths * 6));
         ECK(e->gbuf.alloc((size_t)fl.xres * fl.yres));
         ECK(cudaMemset(e->gbuf.p, 0, sizeof(GBufferPixel) * (size_t)fl.xres * fl.yres));
@@ -1287,6 +1294,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     }
     rc.bvh.nodes = e->bvh.nodes; rc.bvh.tris = e->bvh.tris;
     rc.bvh.instances = instanced ? e->dInstances.p : nullptr;
+    rc.bvh.meshAlpha = e->dMeshAlpha.p;
     ECK(e->hitInst.alloc(instanced ? maxPaths : 1));
     rc.ps.hitInst = e->hitInst.p;
     SceneView &sv = rc.sv;

@@ -396,9 +396,12 @@ __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int
         if (rc.film.isGBuffer && depth == 0) {
             Sampler camSampler;
             CamSample cs = GetCameraSample(rc.sampler, rc.filter, camSampler, px, py, (int)misc.y);
-            float4 o4 = ps.rayO[slot];
-            Vec3 rd(d4.x, d4.y, d4.z);
-            RayDiffs rdif = CameraRayDifferentials(rc.camera, cs, Pt3(o4.x, o4.y, o4.z), rd);
+            // the differentials were scaled about the CAMERA ray (ScaleDifferentials right after GenerateRayDifferential) and
+            // SkipIntersection leaves them alone when it respawns the ray behind an interface surface (interaction.h): regenerate
+            // the camera ray instead of reading the current segment's origin
+            Pt3 oCam; Vec3 rd;
+            GenerateCameraRay(rc.camera, cs.pFilm, cs.pLens, &oCam, &rd);
+            RayDiffs rdif = CameraRayDifferentials(rc.camera, cs, oCam, rd);
             // SurfaceInteraction::ComputeDifferentials (interaction.cpp:42-60), the dpdx / dpdy part
             Vec3 dpdx(0, 0, 0), dpdy(0, 0, 0);
             Pt3 P = isect.p();

@@ -54,6 +54,21 @@ def cornell(outdir, res=(256, 256), spp=64, maxdepth=5):
     return path
 
 
+def cornell_alpha(outdir, res=(96, 96), spp=16, maxdepth=5):
+    """Cornell box with two alpha-tested panels (constant "float alpha" 0.5 and 0.25: GeometricPrimitive's stochastic alpha test,
+    cpu/primitive.cpp:56-75), one of them inside an object instance so that the test hashes the instance-space ray."""
+    path = cornell(outdir, res=res, spp=spp, maxdepth=maxdepth)
+    s = open(path).read()
+    s += ("Material \"diffuse\" \"rgb reflectance\" [0.2 0.3 0.8]\n"
+          "Shape \"trianglemesh\" \"float alpha\" 0.5 \"integer indices\" [0 1 2 0 2 3] \"point3 P\" [-0.6 0.3 0.2  0.2 0.3 0.2  0.2 1.3 0.2  -0.6 1.3 0.2]\n"
+          "AttributeBegin\n  Material \"conductor\" \"float roughness\" 0.2\n  ObjectBegin \"panel\"\n"
+          "    Shape \"trianglemesh\" \"float alpha\" 0.25 \"integer indices\" [0 1 2 0 2 3] \"point3 P\" [-0.3 -0.3 0  0.3 -0.3 0  0.3 0.3 0  -0.3 0.3 0]\n"
+          "  ObjectEnd\nAttributeEnd\n"
+          "AttributeBegin\n  Translate 0.45 0.8 -0.2\n  Rotate 35 0.2 1 0.1\n  Scale 1.2 1.5 1\n  ObjectInstance \"panel\"\nAttributeEnd\n")
+    open(path, "w").write(s)
+    return path
+
+
 def heightfield_mesh(n, seed=1234, amp=0.05, noise=0.01):
     g = np.linspace(-1.0, 1.0, n, dtype=np.float64)
     X, Z = np.meshgrid(g, g, indexing="xy")

@@ -39,6 +39,7 @@ def _scenes():
         "instanced_coated": lambda d: scenes.instanced(d, n_inst=50, subdiv=2, res=(64, 64), spp=4, material="coatedconductor"),
         "smoke_grid": lambda d: scenes.smoke(d, grid=16, res=(64, 64), spp=4),
         "smoke_homogeneous": lambda d: scenes.smoke(d, res=(64, 64), spp=4, homogeneous=True),
+        "alpha_tested_panels": lambda d: scenes.cornell_alpha(d, res=(32, 32), spp=1),
         "gbuffer_world": lambda d: scenes.as_gbuffer(scenes.cornell(d, res=(64, 64), spp=4), "world"),
         "smoke_emissive_homogeneous": lambda d: scenes.smoke(d, res=(32, 32), spp=1, homogeneous=True, emission="le"),
         "smoke_emissive_grid": lambda d: scenes.smoke(d, grid=8, res=(32, 32), spp=1, emission="grid"),

@@ -205,6 +205,8 @@ LIVE_SCENES = {
     "config4_instanced1k_coated_256_16spp": ("instanced", dict(n_inst=1000, subdiv=2, res=(256, 256), material="coatedconductor"), 16, 4),
     "config4_instanced1k_diffuse_256_16spp": ("instanced", dict(n_inst=1000, subdiv=2, res=(256, 256), material="diffuse"), 16, 4),
     "config5_smoke64_128_64spp": ("smoke", dict(grid=64, res=(128, 128)), 64, 0),
+    # a6: alpha-tested primitives (constant alpha), top-level and instanced -- closest-hit and shadow rays take the same test
+    "alpha_tested_panels_96_16spp": ("cornell_alpha", dict(res=(96, 96)), 16, 0),
     # emissive media (cpu/integrators.cpp:989-1000; media.h:223-246, 296-318): "Le" on a homogeneous medium, on a grid medium, and
     # with a per-voxel "Lescale" array
     "emissive_homogeneous_64_32spp": ("smoke", dict(res=(64, 64), homogeneous=True, emission="le"), 32, 0),
@@ -309,6 +311,28 @@ def test_every_pixel_filter_of_the_dispatch_surface_matches_the_live_reference(E
     ref = imageio.read_pfm(str(tmp_path / "ref.pfm"))
     img = _render(E, path, 8)
     assert (bits(img) == bits(ref)).all(), flt
+
+
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/bin/pbrt not on this box")
+def test_gbuffer_film_with_media_and_interface_surfaces_matches_the_live_reference(E, tmp_path):
+    """GBufferFilm on the smoke scene: the first surface hit lies behind an "interface" surface (the medium's box), so the visible
+    surface is recorded after SkipIntersection respawned the ray -- the ray differentials must still be the camera ray's
+    (interaction.h SkipIntersection replaces only the Ray part).  Geometry channels bit-identical, colour within 1e-4."""
+    from pbrt_v4_b200 import scenes, imageio
+    path = scenes.as_gbuffer(scenes.smoke(str(tmp_path), grid=16, res=(48, 48), spp=8), "world")
+    subprocess.check_call([REF_EXE, "--quiet", "--seed", "0", "--outfile", str(tmp_path / "ref.exr"), path])
+    names, ref = imageio.read_raw_channels(str(tmp_path / "ref.exr"))
+    e = E.Engine(0)
+    e.load_pbrt(path, seed=0)
+    e.render(0, 8)
+    g = e.gbuffer()
+    e.close()
+    assert names == E.Engine.GBUFFER_CHANNELS
+    for c, nm in enumerate(names):
+        if nm.split(".")[0] in ("P", "dzdx", "dzdy", "N", "Ns", "u", "v"):
+            assert (bits(g[..., c]) == bits(ref[..., c])).all(), nm
+        else:
+            assert np.sqrt(((g[..., c] - ref[..., c]) ** 2).mean()) < RMSE_TOL, nm
 
 
 def test_film_write_exr_carries_the_resolved_channels(E, tmp_path):

@@ -178,7 +178,7 @@ int bpt_scene_commit(bpt_engine *e) {
         snprintf(b, sizeof(b), " P=%016" PRIx64 " N=%016" PRIx64 " UV=%016" PRIx64 " idx=%016" PRIx64, Fnv(ms.P.data(), ms.P.size() * 4),
                  ms.N.empty() ? 0 : Fnv(ms.N.data(), ms.N.size() * 4), ms.UV.empty() ? 0 : Fnv(ms.UV.data(), ms.UV.size() * 4), Fnv(ms.idx.data(), ms.idx.size() * 4));
         s += b;
-        s += " renderFromObject{" + X(rfo) + "} reverse=" + std::to_string(m.reverse_orientation != 0);
+        s += " renderFromObject{" + X(rfo) + "} reverse=" + std::to_string(m.reverse_orientation != 0) + " alpha=" + (m.has_alpha ? F(m.alpha) : std::string("none"));
         Material iface; std::memset(&iface.m, 0, sizeof(iface.m)); iface.m.type = BPT_MAT_INTERFACE;
         const Material &mt = m.material < 0 ? iface : e->materials[m.material];
         s += " " + Mat(mt);
