@@ -82,7 +82,11 @@ typedef struct {
 } bpt_film;
 
 typedef struct { int type; float xradius, yradius; float sigma, b, c, tau; } bpt_filter;
-typedef struct { int type; int spp; int seed; int randomize; } bpt_sampler;
+typedef struct {
+    int type;                     /* BPT_SAMPLER_*: ZSOBOL, INDEPENDENT, STRATIFIED, PADDED_SOBOL are implemented */
+    int spp; int seed; int randomize;
+    int x_samples, y_samples, jitter;   /* STRATIFIED (samplers.cpp:297-319); spp is x_samples * y_samples then */
+} bpt_sampler;
 typedef struct { int max_depth; int regularize; int light_sampler; } bpt_integrator;
 
 typedef struct {

@@ -256,6 +256,16 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
         s.seed = d.GetOneInt("seed", Options->seed);
         std::string r = d.GetOneString("randomization", "fastowen");
         s.randomize = r == "none" ? BPT_RANDOMIZE_NONE : r == "permutedigits" ? BPT_RANDOMIZE_PERMUTE_DIGITS : r == "owen" ? BPT_RANDOMIZE_OWEN : BPT_RANDOMIZE_FAST_OWEN;
+        if (s.type == BPT_SAMPLER_STRATIFIED) {   // StratifiedSampler::Create (samplers.cpp:297-319)
+            s.jitter = d.GetOneBool("jitter", true);
+            s.x_samples = d.GetOneInt("xsamples", 4); s.y_samples = d.GetOneInt("ysamples", 4);
+            if (Options->pixelSamples) {
+                int nSamples = *Options->pixelSamples, div = (int)std::sqrt(nSamples);
+                while (nSamples % div) --div;
+                s.x_samples = nSamples / div; s.y_samples = nSamples / s.x_samples;
+            }
+            s.spp = s.x_samples * s.y_samples;
+        }
         spp = s.spp;
         Check(api, e, api.bpt_scene_set_sampler(e, &s), "bpt_scene_set_sampler");
     }

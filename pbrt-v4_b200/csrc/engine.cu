@@ -453,9 +453,15 @@ extern "C" int bpt_scene_set_filter(bpt_engine *e, const bpt_filter *f) {
 }
 extern "C" int bpt_scene_set_sampler(bpt_engine *e, const bpt_sampler *s) {
     if (!e || !s) return BPT_ERR_INVALID;
-    if (s->type != BPT_SAMPLER_ZSOBOL && s->type != BPT_SAMPLER_INDEPENDENT) return e->fail(BPT_ERR_UNSUPPORTED, "sampler not implemented (zsobol, independent)");
-    if (s->spp <= 0) return e->fail(BPT_ERR_INVALID, "spp must be positive");
-    e->sampler = *s; return BPT_OK;
+    if (s->type != BPT_SAMPLER_ZSOBOL && s->type != BPT_SAMPLER_INDEPENDENT && s->type != BPT_SAMPLER_STRATIFIED && s->type != BPT_SAMPLER_PADDED_SOBOL)
+        return e->fail(BPT_ERR_UNSUPPORTED, "sampler not implemented (zsobol, independent, stratified, paddedsobol)");
+    e->sampler = *s;
+    if (s->type == BPT_SAMPLER_STRATIFIED) {
+        if (s->x_samples <= 0 || s->y_samples <= 0) return e->fail(BPT_ERR_INVALID, "stratified sampler: xsamples and ysamples must be positive");
+        e->sampler.spp = s->x_samples * s->y_samples;   // StratifiedSampler::SamplesPerPixel()
+    }
+    if (e->sampler.spp <= 0) return e->fail(BPT_ERR_INVALID, "spp must be positive");
+    return BPT_OK;
 }
 extern "C" int bpt_scene_set_integrator(bpt_engine *e, const bpt_integrator *i) {
     if (!e || !i) return BPT_ERR_INVALID;
@@ -678,7 +684,8 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
 
     // ---- sampler (samplers.h:228-239)
     SamplerParams sp{};
-    sp.type = e->sampler.type == BPT_SAMPLER_ZSOBOL ? 0 : 1;
+    sp.type = e->sampler.type == BPT_SAMPLER_ZSOBOL ? 0 : e->sampler.type == BPT_SAMPLER_STRATIFIED ? 2 : e->sampler.type == BPT_SAMPLER_PADDED_SOBOL ? 3 : 1;
+    sp.xSamples = e->sampler.x_samples; sp.ySamples = e->sampler.y_samples; sp.jitter = e->sampler.jitter;
     sp.randomize = e->sampler.randomize;
     sp.seed = e->sampler.seed;
     sp.samplesPerPixel = e->sampler.spp;
@@ -1274,7 +1281,8 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     ECK(e->shadowTr.alloc(rc.useTr ? maxPaths : 1));
     rc.shadowItems = e->shadowItems.p;
     rc.shadowTr = e->shadowTr.p;
-    ECK(e->hitT.alloc(rc.nMedia > 0 ? maxPaths : 1));
+    rc.storeHitT = (df.isGBuffer && e->haveInterface) ? 1 : 0;   // SkipIntersection advances the ray differentials by tHit (GBufferFilm only)
+    ECK(e->hitT.alloc((rc.nMedia > 0 || rc.storeHitT) ? maxPaths : 1));
     ECK(e->pathMedium.alloc(rc.nMedia > 0 ? maxPaths : 1));
     rc.ps.hitT = e->hitT.p; rc.ps.medium = e->pathMedium.p;
     ECK(e->counts.alloc(Q_NCOUNTERS));

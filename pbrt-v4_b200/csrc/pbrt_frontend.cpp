@@ -538,8 +538,14 @@ bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::st
         std::memset(&sampler, 0, sizeof(sampler));
         std::string ty = a.empty() ? "zsobol" : a[0];
         if (ty == "zsobol") sampler.type = BPT_SAMPLER_ZSOBOL; else if (ty == "independent") sampler.type = BPT_SAMPLER_INDEPENDENT;
-        else { err = "sampler \"" + ty + "\" is not supported (zsobol, independent)"; return false; }
+        else if (ty == "paddedsobol") sampler.type = BPT_SAMPLER_PADDED_SOBOL; else if (ty == "stratified") sampler.type = BPT_SAMPLER_STRATIFIED;
+        else { err = "sampler \"" + ty + "\" is not supported (zsobol, independent, stratified, paddedsobol)"; return false; }
         sampler.spp = pl.i("pixelsamples", 16); sampler.seed = pl.i("seed", seedOption);
+        if (sampler.type == BPT_SAMPLER_STRATIFIED) {   // StratifiedSampler::Create (samplers.cpp:297-319)
+            sampler.jitter = pl.b("jitter", true);
+            sampler.x_samples = pl.i("xsamples", 4); sampler.y_samples = pl.i("ysamples", 4);
+            sampler.spp = sampler.x_samples * sampler.y_samples;
+        }
         std::string r = pl.s("randomization", "fastowen");
         sampler.randomize = r == "none" ? BPT_RANDOMIZE_NONE : r == "permutedigits" ? BPT_RANDOMIZE_PERMUTE_DIGITS : r == "owen" ? BPT_RANDOMIZE_OWEN : BPT_RANDOMIZE_FAST_OWEN;
         haveSampler = true; return true;
@@ -670,8 +676,18 @@ bool Frontend::finish() {
     if (!ck(bpt_scene_begin(e))) return false;
     if (!ck(bpt_scene_set_camera(e, &cam)) || !ck(bpt_scene_set_film(e, &film))) return false;
     if (haveFilter && !ck(bpt_scene_set_filter(e, &filter))) return false;
-    if (haveSampler) { if (sppOverride > 0) sampler.spp = sppOverride; if (!ck(bpt_scene_set_sampler(e, &sampler))) return false; }
-    else if (sppOverride > 0 || seedOption) { bpt_sampler s{BPT_SAMPLER_ZSOBOL, sppOverride > 0 ? sppOverride : 16, seedOption, BPT_RANDOMIZE_FAST_OWEN}; if (!ck(bpt_scene_set_sampler(e, &s))) return false; }
+    if (haveSampler) {
+        if (sppOverride > 0) {
+            sampler.spp = sppOverride;
+            if (sampler.type == BPT_SAMPLER_STRATIFIED) {   // --spp: the most square factorisation (samplers.cpp:302-313)
+                int div = (int)std::sqrt((double)sppOverride);
+                while (sppOverride % div) --div;
+                sampler.x_samples = sppOverride / div; sampler.y_samples = sppOverride / sampler.x_samples;
+            }
+        }
+        if (!ck(bpt_scene_set_sampler(e, &sampler))) return false;
+    }
+    else if (sppOverride > 0 || seedOption) { bpt_sampler s{BPT_SAMPLER_ZSOBOL, sppOverride > 0 ? sppOverride : 16, seedOption, BPT_RANDOMIZE_FAST_OWEN, 0, 0, 0}; if (!ck(bpt_scene_set_sampler(e, &s))) return false; }
     if (haveInteg && !ck(bpt_scene_set_integrator(e, &integ))) return false;
     if (!ck(bpt_scene_set_materials(e, materials.data(), (int)materials.size()))) return false;
     if (!ck(bpt_scene_set_area_lights(e, areaLights.data(), (int)areaLights.size()))) return false;

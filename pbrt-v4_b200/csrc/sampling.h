@@ -171,8 +171,26 @@ BPT_HD uint64_t LeftShift2(uint64_t x) {
 }
 BPT_HD uint64_t EncodeMorton2(uint32_t x, uint32_t y) { return (LeftShift2(y) << 1) | LeftShift2(x); }
 
+// PermutationElement (util/math.h:726-755): the i-th element of a hashed permutation of [0, l)
+BPT_HD int PermutationElement(uint32_t i, uint32_t l, uint32_t p) {
+    uint32_t w = l - 1;
+    w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    do {
+        i ^= p; i *= 0xe170893d; i ^= p >> 16; i ^= (i & w) >> 4; i ^= p >> 8; i *= 0x0929eb3f; i ^= p >> 23; i ^= (i & w) >> 1;
+        i *= 1 | p >> 27; i *= 0x6935fa69; i ^= (i & w) >> 11; i *= 0x74dcb303; i ^= (i & w) >> 2; i *= 0x9e501cc3; i ^= (i & w) >> 2;
+        i *= 0xc860a3df; i &= w; i ^= i >> 5;
+    } while (i >= l);
+    return (int)((i + p) % l);
+}
+// Hash(Point2i pixel, int dimension, int seed) (util/hash.h:99-107: the arguments packed back to back, 16 bytes)
+BPT_HD uint64_t Hash_pixel_dim_seed(int px, int py, int dimension, int seed) {
+    uint64_t w[2] = {(uint64_t)(uint32_t)px | ((uint64_t)(uint32_t)py << 32), (uint64_t)(uint32_t)dimension | ((uint64_t)(uint32_t)seed << 32)};
+    return MurmurHash64A(w, 16, 0);
+}
+
 struct SamplerParams {
-    int type;                  // 0 = zsobol, 1 = independent
+    int type;                  // 0 = zsobol, 1 = independent, 2 = stratified, 3 = paddedsobol
+    int xSamples, ySamples, jitter;   // stratified (samplers.h:568-625)
     int randomize;             // RandomizeStrategy
     int seed;
     int log2SamplesPerPixel;
@@ -205,17 +223,19 @@ struct Sampler {
     uint64_t mortonIndex;
     int dimension;
     int pixel;   // index into SamplerParams::prefix, -1: no table / pixel outside the film
-    RNG rng;   // independent sampler only
-    BPT_HD void StartPixelSample(const SamplerParams *params, int px, int py, int index, int dim) {
+    int px, py, sampleIndex;   // stratified / paddedsobol
+    RNG rng;   // independent and stratified samplers
+    BPT_HD void StartPixelSample(const SamplerParams *params, int pxIn, int pyIn, int index, int dim) {
         sp = params;
         dimension = dim;
         pixel = -1;
+        px = pxIn; py = pyIn; sampleIndex = index;
         if (sp->type == 0) {
-            mortonIndex = (EncodeMorton2((uint32_t)px, (uint32_t)py) << sp->log2SamplesPerPixel) | (uint64_t)index;
-            if (sp->prefix && px >= 0 && py >= 0 && px < sp->prefixW && py < sp->prefixH) pixel = py * sp->prefixW + px;
-        } else {
-            // IndependentSampler::StartPixelSample (samplers.h:457-460): Hash(Point2i p, int seed)
-            uint64_t w[2] = {(uint64_t)(uint32_t)px | ((uint64_t)(uint32_t)py << 32), (uint64_t)(uint32_t)sp->seed};
+            mortonIndex = (EncodeMorton2((uint32_t)pxIn, (uint32_t)pyIn) << sp->log2SamplesPerPixel) | (uint64_t)index;
+            if (sp->prefix && pxIn >= 0 && pyIn >= 0 && pxIn < sp->prefixW && pyIn < sp->prefixH) pixel = pyIn * sp->prefixW + pxIn;
+        } else if (sp->type != 3) {   // (PaddedSobolSampler::StartPixelSample, samplers.h:389-393, keeps no other state)
+            // IndependentSampler / StratifiedSampler::StartPixelSample (samplers.h:457-460, 586-592): Hash(Point2i p, int seed)
+            uint64_t w[2] = {(uint64_t)(uint32_t)pxIn | ((uint64_t)(uint32_t)pyIn << 32), (uint64_t)(uint32_t)sp->seed};
             uint64_t h = MurmurHash64A(w, 12, 0);
             rng.SetSequence(h, MixBits(h));
             rng.Advance((int64_t)((uint64_t)index * 65536ull + (uint64_t)dim));
@@ -256,8 +276,38 @@ struct Sampler {
         }
         return sampleIndex;
     }
+    // StratifiedSampler::Get1D / Get2D (samplers.h:595-618), PaddedSobolSampler::Get1D / Get2D (samplers.h:395-421)
+    BPT_HD float OtherGet1D() {
+        uint64_t hash = Hash_pixel_dim_seed(px, py, dimension, sp->seed);
+        if (sp->type == 2) {
+            int n = sp->xSamples * sp->ySamples;
+            int stratum = PermutationElement((uint32_t)sampleIndex, (uint32_t)n, (uint32_t)hash);
+            ++dimension;
+            float delta = sp->jitter ? rng.UniformFloat() : 0.5f;
+            return (stratum + delta) / n;
+        }
+        int index = PermutationElement((uint32_t)sampleIndex, (uint32_t)sp->samplesPerPixel, (uint32_t)hash);
+        ++dimension;
+        return SobolSampleRand((uint64_t)index, 0, sp->randomize, (uint32_t)(hash >> 32));
+    }
+    BPT_HD Vec2 OtherGet2D() {
+        uint64_t hash = Hash_pixel_dim_seed(px, py, dimension, sp->seed);
+        if (sp->type == 2) {
+            int n = sp->xSamples * sp->ySamples;
+            int stratum = PermutationElement((uint32_t)sampleIndex, (uint32_t)n, (uint32_t)hash);
+            dimension += 2;
+            int x = stratum % sp->xSamples, y = stratum / sp->xSamples;
+            float dx = sp->jitter ? rng.UniformFloat() : 0.5f;
+            float dy = sp->jitter ? rng.UniformFloat() : 0.5f;
+            return {(x + dx) / sp->xSamples, (y + dy) / sp->ySamples};
+        }
+        int index = PermutationElement((uint32_t)sampleIndex, (uint32_t)sp->samplesPerPixel, (uint32_t)hash);
+        dimension += 2;
+        return {SobolSampleRand((uint64_t)index, 0, sp->randomize, (uint32_t)hash), SobolSampleRand((uint64_t)index, 1, sp->randomize, (uint32_t)(hash >> 32))};
+    }
     BPT_HD float Get1D() {
         if (sp->type == 1) { ++dimension; return rng.UniformFloat(); }
+        if (sp->type >= 2) return OtherGet1D();
 #if BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
         float2 r = ZSobolOutlined(mortonIndex, pixel, dimension, 1);
         ++dimension;
@@ -270,6 +320,7 @@ struct Sampler {
     }
     BPT_HD Vec2 Get2D() {
         if (sp->type == 1) { dimension += 2; float a = rng.UniformFloat(); float b = rng.UniformFloat(); return {a, b}; }
+        if (sp->type >= 2) return OtherGet2D();
 #if BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
         float2 r = ZSobolOutlined(mortonIndex, pixel, dimension, 2);
         dimension += 2;

@@ -140,7 +140,10 @@ __global__ void __launch_bounds__(256) k_generate_camera_rays(RenderCtx rc, int 
         ps.misc[slot] = make_uint4((unsigned)px | ((unsigned)py << 16), (unsigned)sampleIndex, (unsigned)sampler.dimension, 0u);
         ps.aux[slot] = make_float2(1.f, fweight);
         if (rc.nMedia > 0) ps.medium[slot] = rc.cameraMedium;   // CameraBase::medium (cameras.h)
-        if (rc.film.isGBuffer) ps.vs[slot] = make_float4(0, 0, 0, 0);   // VisibleSurface::set = false
+        if (rc.film.isGBuffer) {
+            ps.vs[slot] = make_float4(0, 0, 0, 0);   // VisibleSurface::set = false
+            if (rc.storeHitT) { ps.vs[3 * (size_t)rc.maxPaths + slot] = make_float4(0, 0, 0, 0); ps.vs[4 * (size_t)rc.maxPaths + slot] = make_float4(0, 0, 0, 0); }
+        }
         rc.queues[Q_RAY0][slot] = slot;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -185,6 +188,7 @@ __global__ void __launch_bounds__(128, BPT_TRACE_CTAS) k_trace_closest(RenderCtx
             int orig = __float_as_int(__ldg(tp).w);
             unsigned cls = __float_as_uint(__ldg(tp + 1).w);
             rc.ps.hit[slot] = make_float4(__int_as_float(orig), rec.b0, rec.b1, rec.b2);
+            if (rc.storeHitT) rc.ps.hitT[slot] = rec.t;
             if (cls & 0x100u) { int p = WarpAggPush(&rc.counts[Q_HITLIGHT]); rc.queues[Q_HITLIGHT][p] = slot; }
             unsigned mt = cls & 0xffu;
             int p = WarpAggPush(&rc.counts[Q_MAT0 + mt]);
@@ -378,6 +382,22 @@ __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int
         if (Material::kTag == MAT_INTERFACE) {
             // isect.SkipIntersection(&ray, tHit): respawn the ray past the surface, same depth (interaction.h)
             const Vec3 rayDir(d4.x, d4.y, d4.z);   // SpawnRay(ray.d): the ray's own (not re-normalised) direction
+            if (rc.film.isGBuffer && depth == 0) {
+                // SurfaceInteraction::SkipIntersection (interaction.cpp:91-97): rxOrigin += t * rxDirection, ryOrigin likewise.  The running
+                // origins live in the (still unused) dpdx / dpdy slots of the visible-surface record, .w = 1 once initialised.
+                const size_t M = (size_t)rc.maxPaths;
+                Sampler camSampler;
+                CamSample cs = GetCameraSample(rc.sampler, rc.filter, camSampler, px, py, (int)misc.y);
+                Pt3 oCam; Vec3 dCam;
+                GenerateCameraRay(rc.camera, cs.pFilm, cs.pLens, &oCam, &dCam);
+                RayDiffs rdif = CameraRayDifferentials(rc.camera, cs, oCam, dCam);
+                float4 sx = ps.vs[3 * M + slot], sy = ps.vs[4 * M + slot];
+                Pt3 rxO = sx.w != 0 ? Pt3(sx.x, sx.y, sx.z) : rdif.rxO, ryO = sy.w != 0 ? Pt3(sy.x, sy.y, sy.z) : rdif.ryO;
+                const float t = ps.hitT[slot];
+                rxO = rxO + rdif.rxD * t; ryO = ryO + rdif.ryD * t;
+                ps.vs[3 * M + slot] = make_float4(rxO.x, rxO.y, rxO.z, 1.f);
+                ps.vs[4 * M + slot] = make_float4(ryO.x, ryO.y, ryO.z, 1.f);
+            }
             Pt3 o = OffsetRayOrigin(isect.pi, isect.n, rayDir);
             ps.rayO[slot] = make_float4(o.x, o.y, o.z, 0.f);
             if (rc.nMedia > 0) ps.medium[slot] = SurfaceGetMedium(mesh, rayDir, isect.n, rayMedium);
@@ -402,6 +422,12 @@ __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int
             Pt3 oCam; Vec3 rd;
             GenerateCameraRay(rc.camera, cs.pFilm, cs.pLens, &oCam, &rd);
             RayDiffs rdif = CameraRayDifferentials(rc.camera, cs, oCam, rd);
+            if (rc.storeHitT) {   // differentials advanced by interface crossings (k_shade<Interface>)
+                const size_t M = (size_t)rc.maxPaths;
+                float4 sx = ps.vs[3 * M + slot], sy = ps.vs[4 * M + slot];
+                if (sx.w != 0) rdif.rxO = Pt3(sx.x, sx.y, sx.z);
+                if (sy.w != 0) rdif.ryO = Pt3(sy.x, sy.y, sy.z);
+            }
             // SurfaceInteraction::ComputeDifferentials (interaction.cpp:42-60), the dpdx / dpdy part
             Vec3 dpdx(0, 0, 0), dpdy(0, 0, 0);
             Pt3 P = isect.p();

@@ -60,6 +60,7 @@ struct RenderCtx {
     int nMedia;
     int cameraMedium;
     int useTr;                         // scene has media or interface surfaces: shadow rays run the transmittance loop
+    int storeHitT;                     // GBufferFilm + interface surfaces: tHit of every closest hit is kept in ps.hitT
     int *counts;                       // Q_NCOUNTERS ints
     unsigned long long *stats;         // [0] camera rays [1] indirect rays [2] shadow rays [3] nodes [4] tris [5] counted rays
     BVHView bvh;

@@ -51,6 +51,15 @@ def _scenes():
         return p
     for k, flt in enumerate(['"box"', '"triangle" "float xradius" 1.5', '"mitchell" "float B" 0.2', '"sinc" "float tau" 2']):
         cases["filter_%d" % k] = (lambda d, flt=flt: filtered(d, flt))
+    def with_sampler(d, smp):
+        p = scenes.cornell(d, res=(32, 32), spp=4)
+        txt = open(p).read()
+        a = txt.index("Sampler "); b = txt.index("\n", a)
+        open(p, "w").write(txt[:a] + "Sampler " + smp + txt[b:])
+        return p
+    for k, smp in enumerate(['"paddedsobol" "integer pixelsamples" 8', '"paddedsobol" "integer pixelsamples" 4 "string randomization" "owen"',
+                             '"stratified" "integer xsamples" 3 "integer ysamples" 2', '"stratified" "bool jitter" false', '"independent" "integer pixelsamples" 5']):
+        cases["sampler_%d" % k] = (lambda d, smp=smp: with_sampler(d, smp))
     for parts in ("t", "s", "r", "ts", "tr", "rs", "trs"):   # every combination of translate / rotate / scale in the instance transform
         cases["instances_" + parts] = (lambda d, parts=parts: scenes.instanced(d, n_inst=40, subdiv=1, res=(32, 32), spp=1, material="diffuse", parts=parts))
     return cases

@@ -335,6 +335,29 @@ def test_gbuffer_film_with_media_and_interface_surfaces_matches_the_live_referen
             assert np.sqrt(((g[..., c] - ref[..., c]) ** 2).mean()) < RMSE_TOL, nm
 
 
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/bin/pbrt not on this box")
+@pytest.mark.parametrize("smp", ['"paddedsobol" "integer pixelsamples" 8', '"paddedsobol" "integer pixelsamples" 16 "string randomization" "owen"',
+                                 '"paddedsobol" "integer pixelsamples" 8 "string randomization" "permutedigits"',
+                                 '"stratified" "integer xsamples" 3 "integer ysamples" 2', '"stratified" "bool jitter" false',
+                                 '"independent" "integer pixelsamples" 6', '"zsobol" "integer pixelsamples" 8 "string randomization" "owen"'])
+def test_samplers_of_the_dispatch_surface_match_the_live_reference(E, tmp_path, smp):
+    """Sampler {Independent, Stratified, PaddedSobol, ZSobol} (base/sampler.h:40-42; samplers.h:367-470, 568-625): every sampler is a
+    stateless function of (pixel, sample index, dimension), so a whole Cornell render must be bit-identical to the reference's."""
+    from pbrt_v4_b200 import scenes, imageio
+    path = scenes.cornell(str(tmp_path), res=(48, 48), spp=8)
+    txt = open(path).read()
+    a = txt.index("Sampler "); b = txt.index("\n", a)
+    open(path, "w").write(txt[:a] + "Sampler " + smp + txt[b:])
+    subprocess.check_call([REF_EXE, "--quiet", "--seed", "0", "--outfile", str(tmp_path / "ref.pfm"), path])
+    ref = imageio.read_pfm(str(tmp_path / "ref.pfm"))
+    e = E.Engine(0)
+    e.load_pbrt(path, seed=0)
+    e.render(0, e.sampler_spp())
+    img = e.image()
+    e.close()
+    assert (bits(img) == bits(ref)).all(), smp
+
+
 def test_film_write_exr_carries_the_resolved_channels(E, tmp_path):
     """bpt_film_write_exr: the 25 GBuffer channels (and R G B for Film "rgb") in the file == bpt_film_resolve[_gbuffer]."""
     from pbrt_v4_b200 import scenes, imageio
