@@ -99,6 +99,10 @@ typedef struct {
     float iface_roughness, iface_uroughness, iface_vroughness, thickness, g;
     bpt_spectrum iface_eta, conductor_eta, conductor_k, albedo;
     int max_depth, n_samples;
+    /* coateddiffuse uses reflectance, roughness / uroughness / vroughness (the interface), thickness, eta, g, albedo, max_depth, n_samples;
+     * thindielectric uses eta; diffusetransmission uses reflectance, transmittance and scale (<= 0 means 1) */
+    bpt_spectrum transmittance;
+    float scale;
 } bpt_material;
 
 typedef struct {

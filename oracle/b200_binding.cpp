@@ -170,6 +170,23 @@ static bpt_material MakeMaterial(const std::string &type, const ParameterDiction
         m.remap_roughness = d.GetOneBool("remaproughness", true);
         return m;
     }
+    if (type == "coateddiffuse") {
+        m.type = BPT_MAT_COATED_DIFFUSE;
+        m.reflectance = GetSpectrum(d, "reflectance", st); m.eta = GetSpectrum(d, "eta", st); m.albedo = GetSpectrum(d, "albedo", st);
+        m.roughness = d.GetOneFloat("roughness", 0.f);
+        m.uroughness = d.GetOneFloat("uroughness", m.roughness); m.vroughness = d.GetOneFloat("vroughness", m.roughness);
+        m.thickness = d.GetOneFloat("thickness", .01f); m.g = d.GetOneFloat("g", 0.f);
+        m.max_depth = d.GetOneInt("maxdepth", 10); m.n_samples = d.GetOneInt("nsamples", 1);
+        m.remap_roughness = d.GetOneBool("remaproughness", true);
+        return m;
+    }
+    if (type == "diffusetransmission") {
+        m.type = BPT_MAT_DIFFUSE_TRANSMISSION;
+        m.reflectance = GetSpectrum(d, "reflectance", st); m.transmittance = GetSpectrum(d, "transmittance", st);
+        m.scale = d.GetOneFloat("scale", 1.f);
+        return m;
+    }
+    if (type == "thindielectric") { m.type = BPT_MAT_THIN_DIELECTRIC; m.eta = GetSpectrum(d, "eta", st); return m; }
     ErrorExit(loc, "material \"%s\" is not implemented by the engine", type);
     return m;
 }

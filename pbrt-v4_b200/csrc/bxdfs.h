@@ -616,6 +616,66 @@ struct LayeredBxDF {
     }
 };
 typedef LayeredBxDF<DielectricBxDF, ConductorBxDF> CoatedConductorBxDF;
+typedef LayeredBxDF<DielectricBxDF, DiffuseBxDF> CoatedDiffuseBxDF;   // bxdfs.h:905-912 (both are two-sided)
+
+// DiffuseTransmissionBxDF (bxdfs.h:85-165)
+struct DiffuseTransmissionBxDF {
+    Spec R, T;
+    BPT_HD int Flags() const { return (R.IsNonZero() ? BXDF_DIFFUSE_REFLECTION : BXDF_UNSET) | (T.IsNonZero() ? BXDF_DIFFUSE_TRANSMISSION : BXDF_UNSET); }
+    BPT_HD Spec f(Vec3 wo, Vec3 wi, int mode) const { return SameHemisphere(wo, wi) ? (R * kInvPi) : (T * kInvPi); }
+    BPT_HD BSDFSample Sample_f(Vec3 wo, float uc, Vec2 u, int mode, int sampleFlags = REFLTRANS_ALL) const {
+        float pr = R.MaxComponentValue(), pt = T.MaxComponentValue();
+        if (!(sampleFlags & REFLTRANS_REFLECTION)) pr = 0;
+        if (!(sampleFlags & REFLTRANS_TRANSMISSION)) pt = 0;
+        if (pr == 0 && pt == 0) return BSDFSample();
+        if (uc < pr / (pr + pt)) {
+            Vec3 wi = SampleCosineHemisphere(u);
+            if (wo.z < 0) wi.z *= -1;
+            float pdf = CosineHemispherePDF(AbsCosTheta(wi)) * pr / (pr + pt);
+            return BSDFSample(f(wo, wi, mode), wi, pdf, BXDF_DIFFUSE_REFLECTION);
+        } else {
+            Vec3 wi = SampleCosineHemisphere(u);
+            if (wo.z > 0) wi.z *= -1;
+            float pdf = CosineHemispherePDF(AbsCosTheta(wi)) * pt / (pr + pt);
+            return BSDFSample(f(wo, wi, mode), wi, pdf, BXDF_DIFFUSE_TRANSMISSION);
+        }
+    }
+    BPT_HD float PDF(Vec3 wo, Vec3 wi, int mode, int sampleFlags = REFLTRANS_ALL) const {
+        float pr = R.MaxComponentValue(), pt = T.MaxComponentValue();
+        if (!(sampleFlags & REFLTRANS_REFLECTION)) pr = 0;
+        if (!(sampleFlags & REFLTRANS_TRANSMISSION)) pt = 0;
+        if (pr == 0 && pt == 0) return 0;
+        if (SameHemisphere(wo, wi)) return pr / (pr + pt) * CosineHemispherePDF(AbsCosTheta(wi));
+        else return pt / (pr + pt) * CosineHemispherePDF(AbsCosTheta(wi));
+    }
+    BPT_HD void Regularize() {}
+};
+
+// ThinDielectricBxDF (bxdfs.h:209-277)
+struct ThinDielectricBxDF {
+    float eta;
+    BPT_HD int Flags() const { return BXDF_REFLECTION | BXDF_TRANSMISSION | BXDF_SPECULAR; }
+    BPT_HD Spec f(Vec3, Vec3, int) const { return Spec(0.f); }
+    BPT_HD BSDFSample Sample_f(Vec3 wo, float uc, Vec2 u, int mode, int sampleFlags = REFLTRANS_ALL) const {
+        float R = FrDielectric(AbsCosTheta(wo), eta), T = 1 - R;
+        if (R < 1) { R += Sqr(T) * R / (1 - Sqr(R)); T = 1 - R; }
+        float pr = R, pt = T;
+        if (!(sampleFlags & REFLTRANS_REFLECTION)) pr = 0;
+        if (!(sampleFlags & REFLTRANS_TRANSMISSION)) pt = 0;
+        if (pr == 0 && pt == 0) return BSDFSample();
+        if (uc < pr / (pr + pt)) {
+            Vec3 wi(-wo.x, -wo.y, wo.z);
+            Spec fr(R / AbsCosTheta(wi));
+            return BSDFSample(fr, wi, pr / (pr + pt), BXDF_SPECULAR_REFLECTION);
+        } else {
+            Vec3 wi = -wo;
+            Spec ft(T / AbsCosTheta(wi));
+            return BSDFSample(ft, wi, pt / (pr + pt), BXDF_SPECULAR_TRANSMISSION);
+        }
+    }
+    BPT_HD float PDF(Vec3, Vec3, int, int = REFLTRANS_ALL) const { return 0; }
+    BPT_HD void Regularize() {}
+};
 
 // ---------------------------------------------------------------- BSDF frame wrapper (bsdf.h)
 template <typename BxDF>

@@ -38,7 +38,7 @@ struct OwnedSpectrum {
 };
 struct OwnedMaterial {
     bpt_material m;
-    OwnedSpectrum reflectance, eta, k, iface_eta, conductor_eta, conductor_k, albedo;
+    OwnedSpectrum reflectance, eta, k, iface_eta, conductor_eta, conductor_k, albedo, transmittance;
 };
 struct OwnedMesh {
     bpt_mesh m;
@@ -477,7 +477,7 @@ extern "C" int bpt_scene_set_materials(bpt_engine *e, const bpt_material *m, int
         OwnedMaterial &o = e->materials[i];
         o.m = m[i];
         o.reflectance.Set(m[i].reflectance); o.eta.Set(m[i].eta); o.k.Set(m[i].k); o.iface_eta.Set(m[i].iface_eta);
-        o.conductor_eta.Set(m[i].conductor_eta); o.conductor_k.Set(m[i].conductor_k); o.albedo.Set(m[i].albedo);
+        o.conductor_eta.Set(m[i].conductor_eta); o.conductor_k.Set(m[i].conductor_k); o.albedo.Set(m[i].albedo); o.transmittance.Set(m[i].transmittance);
     }
     return BPT_OK;
 }
@@ -768,6 +768,36 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             else if (!MakeSpectrumRec(e, om.albedo, ST_ALBEDO, spool, &dm.albedo, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
             dm.flags = om.m.remap_roughness ? 1 : 0;
             dm.optionsSeed = e->sampler.seed;
+            break;
+        }
+        case BPT_MAT_COATED_DIFFUSE: {   // CoatedDiffuseMaterial::Create (materials.cpp:301-345)
+            if (om.reflectance.s.kind == BPT_SPEC_NONE) { dm.reflectance.kind = SPEC_CONSTANT; dm.reflectance.c0 = 0.5f; }
+            else if (!MakeSpectrumRec(e, om.reflectance, ST_ALBEDO, spool, &dm.reflectance, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
+            dm.uroughness = om.m.uroughness >= 0 ? om.m.uroughness : om.m.roughness;
+            dm.vroughness = om.m.vroughness >= 0 ? om.m.vroughness : om.m.roughness;
+            dm.thickness = om.m.thickness > 0 ? om.m.thickness : .01f;
+            if (om.eta.s.kind == BPT_SPEC_NONE) { dm.eta.kind = SPEC_CONSTANT; dm.eta.c0 = 1.5f; }
+            else if (!MakeSpectrumRec(e, om.eta, ST_UNBOUNDED, spool, &dm.eta, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
+            dm.maxDepth = om.m.max_depth > 0 ? om.m.max_depth : 10;
+            dm.nSamples = om.m.n_samples > 0 ? om.m.n_samples : 1;
+            dm.g = om.m.g;
+            if (om.albedo.s.kind == BPT_SPEC_NONE) { dm.albedo.kind = SPEC_CONSTANT; dm.albedo.c0 = 0.f; }
+            else if (!MakeSpectrumRec(e, om.albedo, ST_ALBEDO, spool, &dm.albedo, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
+            dm.flags = om.m.remap_roughness ? 1 : 0;
+            dm.optionsSeed = e->sampler.seed;
+            break;
+        }
+        case BPT_MAT_DIFFUSE_TRANSMISSION: {   // DiffuseTransmissionMaterial::Create (materials.cpp:575-596)
+            if (om.reflectance.s.kind == BPT_SPEC_NONE) { dm.reflectance.kind = SPEC_CONSTANT; dm.reflectance.c0 = 0.25f; }
+            else if (!MakeSpectrumRec(e, om.reflectance, ST_ALBEDO, spool, &dm.reflectance, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
+            if (om.transmittance.s.kind == BPT_SPEC_NONE) { dm.transmittance.kind = SPEC_CONSTANT; dm.transmittance.c0 = 0.25f; }
+            else if (!MakeSpectrumRec(e, om.transmittance, ST_ALBEDO, spool, &dm.transmittance, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
+            dm.scale = om.m.scale > 0 ? om.m.scale : 1.f;
+            break;
+        }
+        case BPT_MAT_THIN_DIELECTRIC: {   // ThinDielectricMaterial::Create: "eta" float or spectrum, default 1.5
+            if (om.eta.s.kind == BPT_SPEC_NONE) { dm.eta.kind = SPEC_CONSTANT; dm.eta.c0 = 1.5f; }
+            else if (!MakeSpectrumRec(e, om.eta, ST_UNBOUNDED, spool, &dm.eta, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
             break;
         }
         default: return e->fail(BPT_ERR_UNSUPPORTED, "material type not implemented yet");

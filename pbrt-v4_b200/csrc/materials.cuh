@@ -105,6 +105,53 @@ struct CoatedConductorMaterialEval {
     }
 };
 
+// CoatedDiffuseMaterial::GetBxDF (materials.cpp:255-283)
+struct CoatedDiffuseMaterialEval {
+    static constexpr int kTag = MAT_COATED_DIFFUSE;
+    typedef CoatedDiffuseBxDF BxDF;
+    BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged) {
+        Spec r = ClampSpec(EvalSpectrum(m.reflectance, sv.specPool, wl), 0, 1);
+        float urough = m.uroughness, vrough = m.vroughness;
+        if (m.flags & 1) { urough = TRDist::RoughnessToAlpha(urough); vrough = TRDist::RoughnessToAlpha(vrough); }
+        TRDist distrib(urough, vrough);
+        float thick = m.thickness;
+        float sampledEta = EvalSpectrumAt(m.eta, sv.specPool, wl.lambda[0]);
+        if (m.eta.kind != SPEC_CONSTANT) { wl.TerminateSecondary(); *lambdaChanged = true; }
+        if (sampledEta == 0) sampledEta = 1;
+        Spec a = ClampSpec(EvalSpectrum(m.albedo, sv.specPool, wl), 0, 1);
+        float gg = Clampf(m.g, -1, 1);
+        CoatedDiffuseBxDF b;
+        b.top.eta = sampledEta; b.top.mfDistrib = distrib;
+        b.bottom.R = r;
+        b.thickness = stdmax(thick, FLT_MIN); b.albedo = a; b.g = gg; b.maxDepth = m.maxDepth; b.nSamples = m.nSamples;
+        b.seed = m.optionsSeed;
+        return b;
+    }
+};
+
+// DiffuseTransmissionMaterial::GetBxDF (materials.h:815-821)
+struct DiffuseTransmissionMaterialEval {
+    static constexpr int kTag = MAT_DIFFUSE_TRANSMISSION;
+    typedef DiffuseTransmissionBxDF BxDF;
+    BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged) {
+        Spec r = ClampSpec(EvalSpectrum(m.reflectance, sv.specPool, wl) * m.scale, 0, 1);
+        Spec t = ClampSpec(EvalSpectrum(m.transmittance, sv.specPool, wl) * m.scale, 0, 1);
+        return DiffuseTransmissionBxDF{r, t};
+    }
+};
+
+// ThinDielectricMaterial::GetBxDF (materials.h:226-240)
+struct ThinDielectricMaterialEval {
+    static constexpr int kTag = MAT_THIN_DIELECTRIC;
+    typedef ThinDielectricBxDF BxDF;
+    BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged) {
+        float sampledEta = EvalSpectrumAt(m.eta, sv.specPool, wl.lambda[0]);
+        if (m.eta.kind != SPEC_CONSTANT) { wl.TerminateSecondary(); *lambdaChanged = true; }
+        if (sampledEta == 0) sampledEta = 1;
+        return ThinDielectricBxDF{sampledEta};
+    }
+};
+
 struct InterfaceMaterialEval {
     static constexpr int kTag = MAT_INTERFACE;
     typedef DiffuseBxDF BxDF;

@@ -189,6 +189,26 @@ struct Frontend {
             m->remap_roughness = pl.b("remaproughness", true);
             return true;
         }
+        if (type == "coateddiffuse") {
+            m->type = BPT_MAT_COATED_DIFFUSE;
+            if (!getSpectrum(pl, "reflectance", &m->reflectance) || !getSpectrum(pl, "eta", &m->eta) || !getSpectrum(pl, "albedo", &m->albedo)) return false;
+            m->roughness = pl.f("roughness", 0.f);
+            m->uroughness = pl.f("uroughness", m->roughness); m->vroughness = pl.f("vroughness", m->roughness);
+            m->thickness = pl.f("thickness", .01f); m->g = pl.f("g", 0.f);
+            m->max_depth = pl.i("maxdepth", 10); m->n_samples = pl.i("nsamples", 1);
+            m->remap_roughness = pl.b("remaproughness", true);
+            return true;
+        }
+        if (type == "diffusetransmission") {
+            m->type = BPT_MAT_DIFFUSE_TRANSMISSION;
+            if (!getSpectrum(pl, "reflectance", &m->reflectance) || !getSpectrum(pl, "transmittance", &m->transmittance)) return false;
+            m->scale = pl.f("scale", 1.f);
+            return true;
+        }
+        if (type == "thindielectric") {
+            m->type = BPT_MAT_THIN_DIELECTRIC;
+            return getSpectrum(pl, "eta", &m->eta);
+        }
         err = "material \"" + type + "\" is not supported by this front end";
         return false;
     }

@@ -69,6 +69,8 @@ struct DeviceMaterial {
     int maxDepth, nSamples;
     int useReflectance;        // conductor specified by "reflectance" instead of eta/k
     int optionsSeed;           // Options->seed (LayeredBxDF seeds its RNG with it, bxdfs.h:510)
+    SpectrumRec transmittance; // diffusetransmission
+    float scale;               // diffusetransmission "scale"
 };
 
 struct DeviceMesh {

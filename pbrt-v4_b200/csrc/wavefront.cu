@@ -1139,11 +1139,17 @@ void LaunchShade(const RenderCtx &rc, int materialTag, int nextQ, int sms, cudaS
     case MAT_CONDUCTOR: k_shade<ConductorMaterialEval><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
     case MAT_DIELECTRIC: k_shade<DielectricMaterialEval><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
     case MAT_COATED_CONDUCTOR: k_shade<CoatedConductorMaterialEval><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_COATED_DIFFUSE: k_shade<CoatedDiffuseMaterialEval><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_DIFFUSE_TRANSMISSION: k_shade<DiffuseTransmissionMaterialEval><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_THIN_DIELECTRIC: k_shade<ThinDielectricMaterialEval><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
     case MAT_INTERFACE: k_shade<InterfaceMaterialEval><<<GridFor(sms, 4), 128, 0, st>>>(rc, nextQ); break;
     default: break;
     }
 }
-bool ShadeSupported(int materialTag) { return materialTag == MAT_DIFFUSE || materialTag == MAT_INTERFACE || materialTag == MAT_CONDUCTOR || materialTag == MAT_DIELECTRIC || materialTag == MAT_COATED_CONDUCTOR; }
+bool ShadeSupported(int materialTag) {
+    return materialTag == MAT_DIFFUSE || materialTag == MAT_INTERFACE || materialTag == MAT_CONDUCTOR || materialTag == MAT_DIELECTRIC || materialTag == MAT_COATED_CONDUCTOR ||
+           materialTag == MAT_COATED_DIFFUSE || materialTag == MAT_DIFFUSE_TRANSMISSION || materialTag == MAT_THIN_DIELECTRIC;
+}
 void LaunchUpdateFilm(const RenderCtx &rc, int x0, int x1, int y0, int y1, int nSamples, int sms, cudaStream_t st) {
     k_update_film<<<GridFor(sms, 8), 256, 0, st>>>(rc, x0, x1, y0, y1, nSamples);
 }

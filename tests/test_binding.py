@@ -51,6 +51,15 @@ def _scenes():
         return p
     for k, flt in enumerate(['"box"', '"triangle" "float xradius" 1.5', '"mitchell" "float B" 0.2', '"sinc" "float tau" 2']):
         cases["filter_%d" % k] = (lambda d, flt=flt: filtered(d, flt))
+    def with_material(d, mat):
+        p = scenes.cornell(d, res=(32, 32), spp=1)
+        txt = open(p).read().replace('Material "diffuse" "rgb reflectance" [0.73 0.73 0.73]', "Material " + mat)
+        open(p, "w").write(txt)
+        return p
+    for k, mat in enumerate(['"coateddiffuse" "rgb reflectance" [0.2 0.5 0.7] "float roughness" 0.1 "float thickness" 0.02',
+                             '"coateddiffuse" "float g" 0.3 "rgb albedo" [0.4 0.4 0.2] "integer maxdepth" 6 "integer nsamples" 2',
+                             '"thindielectric" "float eta" 1.3', '"diffusetransmission" "rgb reflectance" [0.3 0.2 0.1] "rgb transmittance" [0.5 0.6 0.7] "float scale" 1.2']):
+        cases["material_%d" % k] = (lambda d, mat=mat: with_material(d, mat))
     def with_sampler(d, smp):
         p = scenes.cornell(d, res=(32, 32), spp=4)
         txt = open(p).read()

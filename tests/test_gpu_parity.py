@@ -358,6 +358,25 @@ def test_samplers_of_the_dispatch_surface_match_the_live_reference(E, tmp_path, 
     assert (bits(img) == bits(ref)).all(), smp
 
 
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/bin/pbrt not on this box")
+@pytest.mark.parametrize("mat", ['"coateddiffuse" "rgb reflectance" [0.2 0.5 0.7] "float roughness" 0.1',
+                                 '"coateddiffuse" "float g" 0.3 "rgb albedo" [0.4 0.4 0.2] "integer maxdepth" 6 "integer nsamples" 2 "float roughness" 0.3',
+                                 '"thindielectric" "float eta" 1.3', '"thindielectric" "spectrum eta" "glass-BK7"',
+                                 '"diffusetransmission" "rgb reflectance" [0.3 0.2 0.1] "rgb transmittance" [0.5 0.6 0.7] "float scale" 1.2',
+                                 '"diffusetransmission"'])
+def test_more_materials_of_the_dispatch_surface_match_the_live_reference(E, tmp_path, mat):
+    """f4: CoatedDiffuse (LayeredBxDF<Dielectric, Diffuse>), ThinDielectric, DiffuseTransmission (base/material.h:36-39) on the walls
+    of the Cornell box, bit-identical to the reference."""
+    from pbrt_v4_b200 import scenes, imageio
+    path = scenes.cornell(str(tmp_path), res=(48, 48), spp=16)
+    txt = open(path).read().replace('Material "diffuse" "rgb reflectance" [0.73 0.73 0.73]', "Material " + mat)
+    open(path, "w").write(txt)
+    subprocess.check_call([REF_EXE, "--quiet", "--seed", "0", "--outfile", str(tmp_path / "ref.pfm"), path])
+    ref = imageio.read_pfm(str(tmp_path / "ref.pfm"))
+    img = _render(E, path, 16)
+    assert (bits(img) == bits(ref)).all(), (mat, int((bits(img) != bits(ref)).any(axis=-1).sum()))
+
+
 def test_film_write_exr_carries_the_resolved_channels(E, tmp_path):
     """bpt_film_write_exr: the 25 GBuffer channels (and R G B for Film "rgb") in the file == bpt_film_resolve[_gbuffer]."""
     from pbrt_v4_b200 import scenes, imageio

@@ -72,6 +72,12 @@ static std::string Mat(const Material &mt) {
     const bpt_material &m = mt.m;
     std::string s = "mat{type=" + std::to_string(m.type);
     if (m.type == BPT_MAT_INTERFACE) return s + "}";
+    if (m.type == BPT_MAT_THIN_DIELECTRIC) return s + " eta=" + S(mt.sp[1]) + "}";
+    if (m.type == BPT_MAT_DIFFUSE_TRANSMISSION) return s + " refl=" + S(mt.sp[0]) + " trans=" + S(mt.sp[7]) + " scale=" + F(m.scale > 0 ? m.scale : 1.f) + "}";
+    if (m.type == BPT_MAT_COATED_DIFFUSE)
+        return s + " refl=" + S(mt.sp[0]) + " eta=" + S(mt.sp[1]) + " rough=" + F(m.roughness) + "," + F(m.uroughness) + "," + F(m.vroughness) + " remap=" +
+               std::to_string(m.remap_roughness != 0) + " thick=" + F(m.thickness) + " g=" + F(m.g) + " albedo=" + S(mt.sp[6]) + " depth=" + std::to_string(m.max_depth) +
+               " ns=" + std::to_string(m.n_samples) + "}";
     s += " refl=" + S(mt.sp[0]) + " eta=" + S(mt.sp[1]) + " k=" + S(mt.sp[2]);
     if (m.type != BPT_MAT_DIFFUSE)
         s += " rough=" + F(m.roughness) + "," + F(m.uroughness) + "," + F(m.vroughness) + " remap=" + std::to_string(m.remap_roughness != 0);
@@ -97,8 +103,8 @@ int bpt_scene_set_materials(bpt_engine *e, const bpt_material *m, int n) {
     e->materials.resize(n);
     for (int i = 0; i < n; ++i) {
         Material &o = e->materials[i]; o.m = m[i];
-        const bpt_spectrum *sp[7] = {&m[i].reflectance, &m[i].eta, &m[i].k, &m[i].iface_eta, &m[i].conductor_eta, &m[i].conductor_k, &m[i].albedo};
-        for (int k = 0; k < 7; ++k) o.sp[k] = Own(*sp[k]);
+        const bpt_spectrum *sp[8] = {&m[i].reflectance, &m[i].eta, &m[i].k, &m[i].iface_eta, &m[i].conductor_eta, &m[i].conductor_k, &m[i].albedo, &m[i].transmittance};
+        for (int k = 0; k < 8; ++k) o.sp[k] = Own(*sp[k]);
     }
     return BPT_OK;
 }
