@@ -136,14 +136,19 @@ typedef struct {
 } bpt_instance;
 
 typedef struct {
-    int type;                     /* BPT_LIGHT_UNIFORM_INFINITE | BPT_LIGHT_IMAGE_INFINITE */
+    int type;                     /* BPT_LIGHT_UNIFORM_INFINITE | _IMAGE_INFINITE | _POINT | _SPOT | _DISTANT */
     bpt_mat4 world_from_light;    /* CTM at the LightSource directive */
     bpt_mat4 light_from_world;    /* its tracked inverse; all zeros => computed numerically */
-    bpt_spectrum L;
+    bpt_spectrum L;               /* "L" (infinite, distant) or "I" (point, spot); BPT_SPEC_NONE: the colour space's illuminant */
     float scale;
-    float illuminance;            /* <= 0: unused */
+    float illuminance;            /* infinite, distant: <= 0: unused */
     const float *image_rgb;       /* IMAGE_INFINITE: res*res*3 floats, equal-area octahedral parameterisation */
     int image_res;
+    /* point / spot / distant lights (lights.cpp:192-213, 246-276, 1433-1464): the parameters as the scene file gives them; the
+     * engine composes renderFromLight with Translate(from) / the spot's frame / the distant light's frame as the reference does */
+    float from[3], to[3];         /* defaults (0,0,0), (0,0,1) */
+    float power;                  /* point, spot: <= 0: unused */
+    float cone_angle, cone_delta; /* spot: "coneangle" (30), "conedeltaangle" (5), degrees */
 } bpt_light;
 
 enum { BPT_MEDIUM_UNIFORMGRID = 0, BPT_MEDIUM_HOMOGENEOUS = 1 };

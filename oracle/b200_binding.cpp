@@ -404,11 +404,26 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
     }
     // lights (lights.cpp Light::Create "infinite"), recorded at LightSource
     for (const LightRecord &lr : builder.lights) {
-        if (lr.type != "infinite") ErrorExit("light \"%s\" is not implemented by the engine (infinite, diffuse area)", lr.type);
+        if (lr.type != "infinite" && lr.type != "point" && lr.type != "spot" && lr.type != "distant")
+            ErrorExit("light \"%s\" is not implemented by the engine (infinite, point, spot, distant, diffuse area)", lr.type);
         const ParameterDictionary &d = lr.params;
         bpt_light l; std::memset(&l, 0, sizeof(l));
         l.world_from_light = ToB(lr.renderFromLight.GetMatrix()); l.light_from_world = ToB(lr.renderFromLight.GetInverseMatrix());
-        l.L = GetSpectrum(d, "L", st); l.scale = d.GetOneFloat("scale", 1.f); l.illuminance = d.GetOneFloat("illuminance", -1.f);
+        l.scale = d.GetOneFloat("scale", 1.f);
+        if (lr.type != "infinite") {
+            // the parameters PointLight / SpotLight / DistantLight::Create read (lights.cpp:192-213, 1433-1464, 246-276)
+            l.type = lr.type == "point" ? BPT_LIGHT_POINT : lr.type == "spot" ? BPT_LIGHT_SPOT : BPT_LIGHT_DISTANT;
+            l.L = GetSpectrum(d, lr.type == "distant" ? "L" : "I", st);
+            Point3f from = d.GetOnePoint3f("from", Point3f(0, 0, 0));
+            Point3f to = lr.type == "point" ? Point3f(0, 0, 1) : d.GetOnePoint3f("to", Point3f(0, 0, 1));
+            for (int k = 0; k < 3; ++k) { l.from[k] = from[k]; l.to[k] = to[k]; }
+            l.power = lr.type == "distant" ? -1.f : d.GetOneFloat("power", -1.f);
+            l.illuminance = lr.type == "distant" ? d.GetOneFloat("illuminance", -1.f) : -1.f;
+            if (lr.type == "spot") { l.cone_angle = d.GetOneFloat("coneangle", 30.f); l.cone_delta = d.GetOneFloat("conedeltaangle", 5.f); }
+            Check(api, e, api.bpt_scene_add_light(e, &l), "bpt_scene_add_light");
+            continue;
+        }
+        l.L = GetSpectrum(d, "L", st); l.illuminance = d.GetOneFloat("illuminance", -1.f);
         std::string fn = ResolveFilename(d.GetOneString("filename", ""));
         if (fn.empty()) l.type = BPT_LIGHT_UNIFORM_INFINITE;
         else {

@@ -524,7 +524,10 @@ extern "C" int bpt_scene_add_instance(bpt_engine *e, const bpt_instance *i) {
 }
 extern "C" int bpt_scene_add_light(bpt_engine *e, const bpt_light *l) {
     if (!e || !l) return BPT_ERR_INVALID;
-    if (l->type != BPT_LIGHT_UNIFORM_INFINITE && l->type != BPT_LIGHT_IMAGE_INFINITE) return e->fail(BPT_ERR_UNSUPPORTED, "light type not implemented");
+    if (l->type != BPT_LIGHT_UNIFORM_INFINITE && l->type != BPT_LIGHT_IMAGE_INFINITE && l->type != BPT_LIGHT_POINT &&
+        l->type != BPT_LIGHT_SPOT && l->type != BPT_LIGHT_DISTANT)
+        return e->fail(BPT_ERR_UNSUPPORTED, "light type not implemented (infinite, point, spot, distant; area lights through bpt_scene_set_area_lights)");
+    if (l->type == BPT_LIGHT_SPOT && l->cone_delta < 0) return e->fail(BPT_ERR_INVALID, "spot light: falloff start beyond the cone angle");
     e->lights.emplace_back();
     OwnedLight &o = e->lights.back();
     o.l = *l; o.L.Set(l->L);
@@ -952,6 +955,65 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         float photometric = 0;
         for (int i = 0; i < kNLambda; ++i) photometric += cieY[i] * illum[i];
         float scale = ol.l.scale;
+        if (ol.l.type == BPT_LIGHT_POINT || ol.l.type == BPT_LIGHT_SPOT || ol.l.type == BPT_LIGHT_DISTANT) {
+            // PointLight / SpotLight / DistantLight::Create (lights.cpp:192-213, 1433-1464, 246-276) and ::Bounds (:168-173, 1370-1380)
+            std::vector<float> dense(kNLambda);
+            float ph = 0;
+            if (ol.L.s.kind == BPT_SPEC_NONE) { dense = illum; ph = photometric; }
+            else {
+                SpectrumRec Lr{};
+                if (!MakeSpectrumRec(e, ol.L, ST_ILLUMINANT, spool, &Lr, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
+                for (int i = 0; i < kNLambda; ++i) dense[i] = EvalRecAt(Lr, spool.pool, (float)(kLambdaMin + i));
+                if (ol.L.s.kind == BPT_SPEC_RGB) ph = photometric; else for (int i = 0; i < kNLambda; ++i) ph += cieY[i] * dense[i];
+            }
+            scale /= ph;
+            dl.LemitTable = spool.addDense(dense);
+            const float maxValue = *std::max_element(dense.begin(), dense.end());
+            const Pt3 from(ol.l.from[0], ol.l.from[1], ol.l.from[2]), to(ol.l.to[0], ol.l.to[1], ol.l.to[2]);
+            Xform fin;
+            if (ol.l.type == BPT_LIGHT_POINT) {
+                dl.type = LIGHT_POINT;
+                if (ol.l.power > 0) { float k_e = 4 * kPi; scale *= ol.l.power / k_e; }
+                fin = renderFromLight * Translate(Vec3(from.x, from.y, from.z));
+                dl.p = fin(Pt3(0, 0, 0));
+                float phi = 4 * kPi * scale * maxValue;
+                lbounds.push_back(LightBoundsH(Bounds3(dl.p, dl.p), Vec3(0, 0, 1), phi, std::cos(kPi), std::cos(kPi / 2), false));
+            } else if (ol.l.type == BPT_LIGHT_SPOT) {
+                dl.type = LIGHT_SPOT;
+                const float coneangle = ol.l.cone_angle, conedelta = ol.l.cone_delta;
+                Frame fz = Frame::FromZ(Normalize(to - from));
+                Xform dirToZ(M4(fz.x.x, fz.x.y, fz.x.z, 0, fz.y.x, fz.y.y, fz.y.z, 0, fz.z.x, fz.z.y, fz.z.z, 0, 0, 0, 0, 1));
+                Xform t = Translate(Vec3(from.x, from.y, from.z)) * Inverse(dirToZ);
+                fin = renderFromLight * t;
+                if (ol.l.power > 0) {
+                    float cosFalloffEnd = std::cos(Radians(coneangle));
+                    float cosFalloffStart = std::cos(Radians(coneangle - conedelta));
+                    float k_e = 2 * kPi * ((1 - cosFalloffStart) + (cosFalloffStart - cosFalloffEnd) / 2);
+                    scale *= ol.l.power / k_e;
+                }
+                dl.cosFalloffEnd = std::cos(Radians(coneangle));
+                dl.cosFalloffStart = std::cos(Radians(coneangle - conedelta));
+                dl.p = fin(Pt3(0, 0, 0));
+                Vec3 w = Normalize(fin(Vec3(0, 0, 1)));
+                float phi = scale * maxValue * 4 * kPi;
+                float cosTheta_e = std::cos(std::acos(dl.cosFalloffEnd) - std::acos(dl.cosFalloffStart));
+                if (cosTheta_e == 1 && dl.cosFalloffEnd != dl.cosFalloffStart) cosTheta_e = 0.999f;
+                lbounds.push_back(LightBoundsH(Bounds3(dl.p, dl.p), w, phi, dl.cosFalloffStart, cosTheta_e, false));
+            } else {
+                dl.type = LIGHT_DISTANT;
+                Vec3 w = Normalize(from - to), v1, v2;
+                CoordinateSystem(w, &v1, &v2);
+                Xform t(M4(v1.x, v2.x, w.x, 0, v1.y, v2.y, w.y, 0, v1.z, v2.z, w.z, 0, 0, 0, 0, 1));
+                fin = renderFromLight * t;
+                if (ol.l.illuminance > 0) scale *= ol.l.illuminance;
+                dl.w = Normalize(fin(Vec3(0, 0, 1)));
+                lbounds.push_back(LightBoundsH());   // DistantLight::Bounds() is empty (lights.h:273)
+            }
+            dl.renderFromLight = ToMat4(fin.m); dl.lightFromRender = ToMat4(fin.mInv);
+            dl.scale = scale;
+            dlights.push_back(dl);
+            continue;
+        }
         if (ol.l.type == BPT_LIGHT_UNIFORM_INFINITE) {
             dl.type = LIGHT_UNIFORM_INFINITE;
             std::vector<float> dense(kNLambda);
@@ -1008,12 +1070,14 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     }
     // a scene without lights is legal (it renders black; the raw ray entry points still work)
 
-    // ---- light sampler (wavefront/integrator.cpp:182-186: uniform when there is exactly one light)
+    // ---- light sampler: LightSampler::Create(strategy, lights) as the CPU VolPathIntegrator does (cpu/integrators.h:270) -- the parity
+    // oracle.  (The reference's wavefront integrator swaps in a uniform sampler when there is exactly one light,
+    // wavefront/integrator.cpp:182-186; with one bounded light that differs from the BVH sampler wherever the light's importance is
+    // zero, so the CPU behaviour is the one followed.)
     LightBVHBuilder lb;
     DeviceLightSampler dls{};
     dls.nLights = (int)dlights.size();
     int lsType = e->integ.light_sampler;
-    if (dlights.size() == 1) lsType = BPT_LIGHTSAMPLER_UNIFORM;
     dls.type = lsType;
     if (lsType == BPT_LIGHTSAMPLER_BVH) lb.Build(lbounds);
     else {

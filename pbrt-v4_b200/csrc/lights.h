@@ -236,6 +236,9 @@ BPT_HD Spec ImageLe(const SceneView &sv, const DeviceLight &light, Vec2 uv, cons
     return light.scale * (s * DenseSample(sv.illumD65, wl));
 }
 BPT_HD Spec InfiniteLightLe(const SceneView &sv, const DeviceLight &light, Vec3 rd, const Wavelengths &wl) {
+    // a DistantLight has no bounds and therefore sits in the light sampler's list of infinite lights (lightsamplers.cpp:63-72), but it
+    // is not LightType::Infinite: the integrator's own list (cpu/integrators.cpp:79-83) leaves it out, escaped rays see nothing of it
+    if (light.type == LIGHT_DISTANT) return Spec(0.f);
     if (light.type == LIGHT_UNIFORM_INFINITE) return light.scale * DenseSample(sv.specPool + light.LemitTable, wl);
     Vec3 wLight = Normalize(ApplyM3(light.lightFromRender, rd));
     return ImageLe(sv, light, EqualAreaSphereToSquare(wLight), wl);
@@ -262,6 +265,45 @@ BPT_HD LightLiSample InfiniteLightSampleLi(const SceneView &sv, const DeviceLigh
     ls.wi = wi;
     ls.pLight = Pt3i(ctx.p() + wi * (2 * light.sceneRadius));
     ls.nLight = Nrm3(0, 0, 0);
+    ls.valid = true;
+    return ls;
+}
+
+// PointLight / SpotLight / DistantLight::SampleLi (lights.h:221-228, 771-783, 282-289; SpotLight::I lights.cpp:1360-1363):
+// pdf = 1, the reference point carries no normal and no error bounds.
+BPT_HD bool IsDeltaLight(int type) { return type == LIGHT_POINT || type == LIGHT_SPOT || type == LIGHT_DISTANT; }
+BPT_HD LightLiSample DeltaLightSampleLi(const SceneView &sv, const DeviceLight &light, const LightSampleContext &ctx,
+                                        const Wavelengths &wl) {
+    LightLiSample ls;
+    ls.valid = false;
+    ls.pdf = 1;
+    ls.nLight = Nrm3(0, 0, 0);
+    if (light.type == LIGHT_DISTANT) {
+        Vec3 wi = light.w;
+        ls.pLight = Pt3i(ctx.p() + wi * (2 * light.sceneRadius));
+        ls.L = light.scale * DenseSample(sv.specPool + light.LemitTable, wl);
+        ls.wi = wi;
+        ls.valid = true;
+        return ls;
+    }
+    Pt3 p = light.p;
+    Vec3 wi = Normalize(p - ctx.p());
+    Spec I;
+    if (light.type == LIGHT_SPOT) {
+        Vec3 wLight = Normalize(ApplyM3(light.lightFromRender, -wi));
+        float a = light.cosFalloffEnd, b = light.cosFalloffStart, x = wLight.z, smooth;
+        if (a == b) smooth = (x < a) ? 0.f : 1.f;
+        else {
+            float t = Clampf((x - a) / (b - a), 0.f, 1.f);
+            smooth = t * t * (3 - 2 * t);
+        }
+        I = (smooth * light.scale) * DenseSample(sv.specPool + light.LemitTable, wl);
+    } else
+        I = light.scale * DenseSample(sv.specPool + light.LemitTable, wl);
+    ls.L = I / DistanceSquared(p, ctx.p());
+    if (light.type == LIGHT_SPOT && !ls.L.IsNonZero()) return ls;
+    ls.wi = wi;
+    ls.pLight = Pt3i(p);
     ls.valid = true;
     return ls;
 }

@@ -649,11 +649,31 @@ bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::st
         areaLights.push_back(al); gs.areaLight = (int)areaLights.size() - 1; return true;
     }
     if (d == "LightSource") {
-        if (a.empty() || a[0] != "infinite") { err = "only \"infinite\" light sources are supported"; return false; }
+        if (a.empty() || (a[0] != "infinite" && a[0] != "point" && a[0] != "spot" && a[0] != "distant")) {
+            err = "light sources supported: \"infinite\", \"point\", \"spot\", \"distant\""; return false;
+        }
         bpt_light l; std::memset(&l, 0, sizeof(l));
         l.world_from_light = ToB(gs.ctm.m); l.light_from_world = ToB(gs.ctm.mInv);
+        l.scale = pl.f("scale", 1.f);
+        if (a[0] != "infinite") {
+            // PointLight / SpotLight / DistantLight::Create (lights.cpp:192-213, 1433-1464, 246-276)
+            auto point = [&](const char *name, float *out, float dx, float dy, float dz) {
+                out[0] = dx; out[1] = dy; out[2] = dz;
+                Param *q = pl.find(name);
+                if (q && q->nums.size() >= 3) for (int k = 0; k < 3; ++k) out[k] = (float)q->nums[k];
+            };
+            l.type = a[0] == "point" ? BPT_LIGHT_POINT : a[0] == "spot" ? BPT_LIGHT_SPOT : BPT_LIGHT_DISTANT;
+            if (!getSpectrum(pl, a[0] == "distant" ? "L" : "I", &l.L)) return false;
+            point("from", l.from, 0, 0, 0);
+            l.to[2] = 1;
+            if (a[0] != "point") point("to", l.to, 0, 0, 1);
+            l.power = a[0] == "distant" ? -1.f : pl.f("power", -1.f);
+            l.illuminance = a[0] == "distant" ? pl.f("illuminance", -1.f) : -1.f;
+            if (a[0] == "spot") { l.cone_angle = pl.f("coneangle", 30.f); l.cone_delta = pl.f("conedeltaangle", 5.f); }
+            lights.push_back(l); return true;
+        }
         if (!getSpectrum(pl, "L", &l.L)) return false;
-        l.scale = pl.f("scale", 1.f); l.illuminance = pl.f("illuminance", -1.f);
+        l.illuminance = pl.f("illuminance", -1.f);
         std::string fn = pl.s("filename", "");
         if (fn.empty()) l.type = BPT_LIGHT_UNIFORM_INFINITE;
         else {

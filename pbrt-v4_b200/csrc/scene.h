@@ -95,6 +95,10 @@ struct DeviceLight {
     Pt3 sceneCenter;
     int image;                 // ImageInfinite: index of image record
     Mat4 renderFromLight, lightFromRender;
+    // point / spot: p = renderFromLight(Point3f(0,0,0)); distant: w = Normalize(renderFromLight(Vector3f(0,0,1))) (host, once)
+    Pt3 p;
+    Vec3 w;
+    float cosFalloffStart, cosFalloffEnd;   // SpotLight (lights.cpp:1345-1354)
 };
 
 // Light BVH node with CompactLightBounds already de-quantised on the host (lightsamplers.h:104-200):

@@ -488,12 +488,15 @@ __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int
                 const DeviceLight &light = rc.sv.lights[lightIndex];
                 LightLiSample ls;
                 if (light.type == LIGHT_DIFFUSE_AREA) ls = AreaLightSampleLi(rc.sv, light, ctx, uLight, wl);
+                else if (IsDeltaLight(light.type)) ls = DeltaLightSampleLi(rc.sv, light, ctx, wl);
                 else ls = InfiniteLightSampleLi(rc.sv, light, ctx, uLight, wl);
                 if (ls.valid && ls.L.IsNonZero() && ls.pdf != 0) {
                     float p_l = lightPMF * ls.pdf;
                     Vec3 wi = ls.wi;
                     Spec f_hat = bsdf.f(wo, wi) * AbsDot(wi, isect.ns);
-                    float scatterPDF = bsdf.PDF(wo, wi);
+                    // delta lights: the estimate divides by r_l.Average() alone (cpu/integrators.cpp:1385-1388); a zero scattering
+                    // pdf makes r_u vanish in (r_l + r_u) and gives the same bits
+                    float scatterPDF = IsDeltaLight(light.type) ? 0.f : bsdf.PDF(wo, wi);
                     if (f_hat.IsNonZero()) {
                         // lightRay = intr.SpawnRayTo(ls->pLight)  (ray.h:94-101, both ends offset)
                         Pt3 pf, pt;
@@ -732,12 +735,15 @@ __global__ void __launch_bounds__(128) k_medium_scatter(RenderCtx rc, int nextQ)
             const DeviceLight &light = rc.sv.lights[lightIndex];
             LightLiSample ls;
             if (light.type == LIGHT_DIFFUSE_AREA) ls = AreaLightSampleLi(rc.sv, light, ctx, uLight, wl);
+            else if (IsDeltaLight(light.type)) ls = DeltaLightSampleLi(rc.sv, light, ctx, wl);
             else ls = InfiniteLightSampleLi(rc.sv, light, ctx, uLight, wl);
             if (ls.valid && ls.L.IsNonZero() && ls.pdf != 0) {
                 float p_l = lightPMF * ls.pdf;
                 float ph = PhaseHG_p(med.g, wo, ls.wi);
                 Spec f_hat(ph);
-                float scatterPDF = ph;
+                // delta lights: the estimate divides by r_l.Average() alone (cpu/integrators.cpp:1385-1388); a zero scattering pdf
+                // makes r_u vanish in (r_l + r_u) and gives the same bits
+                float scatterPDF = IsDeltaLight(light.type) ? 0.f : ph;
                 if (f_hat.IsNonZero()) {
                     Nrm3 nL = light.type == LIGHT_DIFFUSE_AREA ? ls.nLight : Nrm3(0, 0, 0);
                     Pt3 pf = OffsetRayOrigin(ctx.pi, ctx.n, ls.pLight.p() - ctx.pi.p());

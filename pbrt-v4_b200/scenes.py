@@ -69,6 +69,35 @@ def cornell_alpha(outdir, res=(96, 96), spp=16, maxdepth=5):
     return path
 
 
+LIGHT_SETS = {
+    # point / spot / distant lights (lights.cpp:192-213, 1433-1464, 246-276), alone (a one-leaf light BVH), together with the quad
+    # light (a real light BVH: bounds, cones, importance), and under transforms / with "power" / "illuminance" normalisation
+    "point": 'LightSource "point" "point3 from" [0.3 1.6 0.4] "rgb I" [3 2.5 2]\n',
+    "spot": 'LightSource "spot" "point3 from" [-0.5 1.9 0.6] "point3 to" [0.2 0 -0.3] "float coneangle" 35 "float conedeltaangle" 10 "rgb I" [12 12 10]\n',
+    "distant": 'LightSource "distant" "point3 from" [0.4 1 0.7] "point3 to" [0 0 0] "rgb L" [1.5 1.4 1.2]\n',
+    "all": ('AttributeBegin\n  Translate 0.1 0.2 0.05\n  Rotate 20 0 1 0\n  LightSource "point" "point3 from" [0.3 1.4 0.4] "blackbody I" 3200 "float power" 40\nAttributeEnd\n'
+            'LightSource "spot" "point3 from" [-0.5 1.9 0.6] "point3 to" [0.2 0 -0.3] "float power" 60 "float scale" 0.5\n'
+            'AttributeBegin\n  Rotate -15 1 0 0\n  LightSource "distant" "point3 to" [0.1 -1 -0.4] "float illuminance" 2\nAttributeEnd\n'
+            'LightSource "point" "point3 from" [0 0.9 0.9] "float scale" 2\n'),
+}
+
+
+def cornell_lights(outdir, lights="all", area=True, res=(64, 64), spp=16, maxdepth=5):
+    """Cornell box lit by LIGHT_SETS[lights] (in front of the open side the distant light and the off-centre point lights reach the
+    walls directly), with or without the quad area light, plus a rough conductor panel that casts shadows."""
+    path = cornell(outdir, res=res, spp=spp, maxdepth=maxdepth)
+    s = open(path).read()
+    if not area:
+        a = s.index("AttributeBegin\n  AreaLightSource"); b = s.index("AttributeEnd\n", a) + len("AttributeEnd\n")
+        s = s[:a] + s[b:]
+    a = s.index("WorldBegin\n") + len("WorldBegin\n")
+    s = s[:a] + LIGHT_SETS[lights] + s[a:]
+    s += ("Material \"conductor\" \"float roughness\" 0.3\n"
+          "Shape \"trianglemesh\" \"integer indices\" [0 1 2 0 2 3] \"point3 P\" [-0.5 0.55 -0.3  0.3 0.6 -0.45  0.35 0.62 0.25  -0.45 0.5 0.3]\n")
+    open(path, "w").write(s)
+    return path
+
+
 def heightfield_mesh(n, seed=1234, amp=0.05, noise=0.01):
     g = np.linspace(-1.0, 1.0, n, dtype=np.float64)
     X, Z = np.meshgrid(g, g, indexing="xy")

@@ -222,8 +222,12 @@ int bpt_scene_commit(bpt_engine *e) {
     }
     for (const Light &l : e->lights) {
         Xform rfl = ResolveRenderFromObject(e->space, cs, l.l.world_from_light, l.l.light_from_world);
-        fprintf(f, "light type=%d renderFromLight{%s} L=%s scale=%s illuminance=%s image=%d:%016" PRIx64 "\n", l.l.type, X(rfl).c_str(), S(l.L).c_str(), F(l.l.scale).c_str(),
+        fprintf(f, "light type=%d renderFromLight{%s} L=%s scale=%s illuminance=%s image=%d:%016" PRIx64, l.l.type, X(rfl).c_str(), S(l.L).c_str(), F(l.l.scale).c_str(),
                 F(l.l.illuminance > 0 ? l.l.illuminance : -1.f).c_str(), l.l.image_res, l.img.empty() ? 0 : Fnv(l.img.data(), l.img.size() * 4));
+        if (l.l.type == BPT_LIGHT_POINT || l.l.type == BPT_LIGHT_SPOT || l.l.type == BPT_LIGHT_DISTANT)
+            fprintf(f, " from=%s,%s,%s to=%s,%s,%s power=%s cone=%s,%s", F(l.l.from[0]).c_str(), F(l.l.from[1]).c_str(), F(l.l.from[2]).c_str(), F(l.l.to[0]).c_str(),
+                    F(l.l.to[1]).c_str(), F(l.l.to[2]).c_str(), F(l.l.power > 0 ? l.l.power : -1.f).c_str(), F(l.l.cone_angle).c_str(), F(l.l.cone_delta).c_str());
+        fprintf(f, "\n");
     }
     if (path) fclose(f);
     return BPT_OK;
