@@ -103,7 +103,29 @@ typedef struct {
      * thindielectric uses eta; diffusetransmission uses reflectance, transmittance and scale (<= 0 means 1) */
     bpt_spectrum transmittance;
     float scale;
+    /* image textures in place of constants: 0 = none, k > 0 = texture k-1 of bpt_scene_set_textures.  "reflectance" / "transmittance"
+     * spectrum textures (albedo), "roughness" / "uroughness" / "vroughness" float textures of conductor, dielectric, coateddiffuse,
+     * and the "displacement" float texture of bump mapping (materials.h:107-138) */
+    int reflectance_tex, transmittance_tex, uroughness_tex, vroughness_tex, displacement_tex;
 } bpt_material;
+
+/* Texture "imagemap" (FloatImageTexture / SpectrumImageTexture, textures.h:525-626) with a "uv" mapping (textures.h:86-106).  The image
+ * is handed over as the reference's Image holds it after reading the file (util/image.cpp:877-921): 8-bit texels with their colour
+ * encoding, or 32-bit float; 1 ("Y"), 3 (RGB) or 4 (RGBA) interleaved channels, top row first.  The engine builds the MIP pyramid. */
+enum { BPT_TEXFILTER_POINT = 0, BPT_TEXFILTER_BILINEAR = 1, BPT_TEXFILTER_TRILINEAR = 2, BPT_TEXFILTER_EWA = 3 };
+enum { BPT_TEXWRAP_BLACK = 0, BPT_TEXWRAP_CLAMP = 1, BPT_TEXWRAP_REPEAT = 2 };
+enum { BPT_IMAGE_U8 = 0, BPT_IMAGE_F32 = 1 };
+enum { BPT_ENCODING_LINEAR = 0, BPT_ENCODING_SRGB = 1 };
+typedef struct {
+    int format, encoding;         /* BPT_IMAGE_*, BPT_ENCODING_* (8-bit texels only) */
+    int xres, yres, n_channels;
+    const void *pixels;           /* copied */
+    int filter;                   /* "filter": BPT_TEXFILTER_* (the reference's default is bilinear) */
+    float max_anisotropy;         /* "maxanisotropy" (8) */
+    int wrap;                     /* "wrap": BPT_TEXWRAP_* (repeat) */
+    float scale; int invert;      /* "scale" (1), "invert" */
+    float su, sv, du, dv;         /* "uscale" "vscale" "udelta" "vdelta" */
+} bpt_texture;
 
 typedef struct {
     bpt_spectrum L;               /* BPT_SPEC_NONE => colour-space illuminant */
@@ -208,6 +230,7 @@ int bpt_scene_set_filter(bpt_engine *e, const bpt_filter *f);
 int bpt_scene_set_sampler(bpt_engine *e, const bpt_sampler *s);
 int bpt_scene_set_integrator(bpt_engine *e, const bpt_integrator *i);
 int bpt_scene_set_materials(bpt_engine *e, const bpt_material *m, int n);
+int bpt_scene_set_textures(bpt_engine *e, const bpt_texture *t, int n);
 int bpt_scene_set_area_lights(bpt_engine *e, const bpt_area_light *a, int n);
 int bpt_scene_add_mesh(bpt_engine *e, const bpt_mesh *m);
 int bpt_scene_add_instance(bpt_engine *e, const bpt_instance *i);

@@ -72,6 +72,9 @@
 #include <pbrt/util/spectrum.h>
 #undef private
 #undef protected
+// the EWA weight table is a file-scope static of the reference's mipmap.cpp (printed there with nine digits, not reproducible from
+// its generating formula): compile that source file into this tool, where it lies, to dump the table
+#include <pbrt/util/mipmap.cpp>
 
 #include <cstdio>
 #include <cstring>
@@ -123,6 +126,8 @@ static void DumpTables(const char *path) {
     const float *cd = &sRGBToSpectrumTable_Data[0][0][0][0][0];
     b.f32("rgb2spec_srgb_coeffs", std::vector<float>(cd, cd + 3 * 64 * 64 * 64 * 3));
     b.u32("sobol32_2x52", std::vector<uint32_t>(SobolMatrices32, SobolMatrices32 + 2 * SobolMatrixSize));
+    b.f32("mip_filter_lut", std::vector<float>(MIPFilterLUT, MIPFilterLUT + MIPFilterLUTSize));
+    b.f32("srgb8_to_linear", std::vector<float>(SRGBToLinearLUT, SRGBToLinearLUT + 256));
     // named spectra (piecewise linear): lambdas then values
     const char *names[] = {"metal-Cu-eta", "metal-Cu-k", "metal-Au-eta", "metal-Au-k", "metal-Ag-eta", "metal-Ag-k",
                            "metal-Al-eta", "metal-Al-k", "glass-BK7", "glass-BAF10", "glass-F11", "stdillum-D65",
@@ -639,6 +644,110 @@ static void DumpGolden(const char *path) {
         }
         b.f32("mat_in", in);
         b.f32("mat_out", out);
+    }
+    // Image textures: MIPMap::Filter<RGB> / <Float> (pyramid generation incl. resize of non-power-of-two images and 8-bit re-encoding
+    // of the levels; point / bilinear / trilinear / EWA; repeat / clamp / black) on three synthetic images.  (appended last)
+    {
+        Allocator alloc;
+        struct Img { int w, h, nc; bool is8; };
+        const Img imgs[3] = {{13, 9, 3, true}, {16, 8, 1, false}, {8, 8, 4, true}};
+        std::vector<float> q;
+        const int nQ = 48;
+        for (int i = 0; i < nQ; ++i) {
+            float s = -0.5f + 2 * rng.Uniform<float>(), t = -0.5f + 2 * rng.Uniform<float>();
+            auto mag = [&]() { return (rng.Uniform<float>() < 0.1f ? 0.f : std::pow(10.f, -3 + 3 * rng.Uniform<float>())) * (rng.Uniform<float>() < 0.5f ? -1.f : 1.f); };
+            q.insert(q.end(), {s, t, mag(), mag(), mag(), mag()});
+        }
+        b.f32("tex_queries", q);
+        for (int k = 0; k < 3; ++k) {
+            const Img &im = imgs[k];
+            std::vector<float> pix((size_t)im.w * im.h * im.nc);
+            for (float &v : pix) v = im.is8 ? (float)(int)std::min(255.f, 256 * rng.Uniform<float>()) : 2 * rng.Uniform<float>();
+            b.f32(StringPrintf("tex%d_pixels", k).c_str(), pix);
+            std::vector<std::string> names = im.nc == 1 ? std::vector<std::string>{"Y"} : im.nc == 3 ? std::vector<std::string>{"R", "G", "B"}
+                                                                                                 : std::vector<std::string>{"R", "G", "B", "A"};
+            std::vector<float> out;
+            for (int wrap = 0; wrap < 3; ++wrap)
+                for (int filt = 0; filt < 4; ++filt) {
+                    if (wrap == 0 && k == 0) {   // the reference aborts when it resizes a non-power-of-two image under WrapMode::Black (util/image.cpp:114)
+                        for (int i = 0; i < 4 * nQ; ++i) out.push_back(-1.f);
+                        continue;
+                    }
+                    Image image(im.is8 ? PixelFormat::U256 : PixelFormat::Float, Point2i(im.w, im.h), names, im.is8 ? ColorEncoding::sRGB : ColorEncoding());
+                    for (size_t i = 0; i < pix.size(); ++i) {
+                        if (im.is8) ((uint8_t *)image.RawPointer({0, 0}))[i] = (uint8_t)pix[i];
+                        else ((float *)image.RawPointer({0, 0}))[i] = pix[i];
+                    }
+                    MIPMapFilterOptions opt;
+                    opt.filter = (FilterFunction)filt; opt.maxAnisotropy = 8.f;
+                    MIPMap mip(image, RGBColorSpace::sRGB, (WrapMode)wrap, alloc, opt);
+                    for (int i = 0; i < nQ; ++i) {
+                        const float *a = &q[6 * i];
+                        RGB c = mip.Filter<RGB>(Point2f(a[0], a[1]), Vector2f(a[2], a[3]), Vector2f(a[4], a[5]));
+                        Float f = mip.Filter<Float>(Point2f(a[0], a[1]), Vector2f(a[2], a[3]), Vector2f(a[4], a[5]));
+                        out.insert(out.end(), {c.r, c.g, c.b, f});
+                    }
+                }
+            b.f32(StringPrintf("tex%d_out", k).c_str(), out);
+        }
+    }
+    // Differentials for texture filtering: CameraBase::FindMinimumDifferentials, Camera::Approximate_dp_dxy,
+    // SurfaceInteraction::ComputeDifferentials (with and without ray differentials) and SpawnRay's specular differentials.  (appended last)
+    for (int cfg = 0; cfg < 2; ++cfg) {
+        Allocator alloc;
+        const int xres = 96, yres = 64, spp = 16;
+        Filter filt = alloc.new_object<GaussianFilter>(Vector2f(1.5f, 1.5f), 0.5f, alloc);
+        PixelSensor *sensor = alloc.new_object<PixelSensor>(RGBColorSpace::sRGB, nullptr, 1.f, alloc);
+        FilmBaseParameters fbp(Point2i(xres, yres), Bounds2i(Point2i(0, 0), Point2i(xres, yres)), filt, 35.f, sensor, "golden.pfm");
+        RGBFilm *film = alloc.new_object<RGBFilm>(fbp, RGBColorSpace::sRGB, Infinity, false, alloc);
+        Transform worldFromCamera = Inverse(LookAt(Point3f(0.3f, 1.1f, 3.2f), Point3f(0.1f, 0.6f, -0.2f), Vector3f(0.05f, 1, 0)));
+        CameraTransform camXf{AnimatedTransform(worldFromCamera)};
+        ParsedParameterVector params;
+        auto addF = [&](const char *name, float v) { ParsedParameter *pp = new ParsedParameter(FileLoc()); pp->type = "float"; pp->name = name; pp->AddFloat(v); params.push_back(pp); };
+        addF("fov", 38.f);
+        if (cfg == 1) { addF("lensradius", 0.07f); addF("focaldistance", 3.1f); }
+        ParameterDictionary dict(params, RGBColorSpace::sRGB);
+        FileLoc loc;
+        PerspectiveCamera *cam = PerspectiveCamera::Create(dict, camXf, Film(film), Medium(), &loc, alloc);
+        std::vector<float> cp;
+        auto pushM = [&](const SquareMatrix<4> &t) { for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) cp.push_back(t[i][j]); };
+        cp.insert(cp.end(), {(float)xres, (float)yres, (float)spp, cam->lensRadius, cam->focalDistance});
+        pushM(cam->cameraFromRaster.GetMatrix());
+        pushM(cam->cameraTransform.RenderFromCamera().startTransform.GetMatrix());
+        pushM(cam->cameraTransform.RenderFromCamera().startTransform.GetInverseMatrix());
+        cp.insert(cp.end(), {cam->dxCamera.x, cam->dxCamera.y, cam->dxCamera.z, cam->dyCamera.x, cam->dyCamera.y, cam->dyCamera.z});
+        for (Vector3f v : {cam->minPosDifferentialX, cam->minPosDifferentialY, cam->minDirDifferentialX, cam->minDirDifferentialY}) cp.insert(cp.end(), {v.x, v.y, v.z});
+        b.f32(StringPrintf("diff%d_params", cfg).c_str(), cp);
+        std::vector<float> in, out;
+        for (int qi = 0; qi < 256; ++qi) {
+            auto r = [&]() { return 2 * rng.Uniform<float>() - 1; };
+            Point3f p(1.5f * r(), 1 + r(), 1.5f * r());
+            Vector3f dpdu(r(), r(), r()), dpdv(r(), r(), r());
+            Normal3f dndu(0.3f * r(), 0.3f * r(), 0.3f * r()), dndv(0.3f * r(), 0.3f * r(), 0.3f * r());
+            Vector3f wo = Normalize(Vector3f(r(), r(), r()));
+            SurfaceInteraction si(Point3fi(p), Point2f(rng.Uniform<float>(), rng.Uniform<float>()), wo, dpdu, dpdv, dndu, dndv, 0.f, false);
+            RayDifferential ray(Point3f(0.3f, 1.1f, 3.2f), -wo);
+            const int mode = qi % 4;   // 0: no differentials (Approximate_dp_dxy)  1..3: ray differentials, then reflection / transmission / diffuse
+            if (mode) {
+                ray.hasDifferentials = true;
+                ray.rxOrigin = ray.o + 0.01f * Vector3f(r(), r(), r()); ray.ryOrigin = ray.o + 0.01f * Vector3f(r(), r(), r());
+                ray.rxDirection = ray.d + 0.02f * Vector3f(r(), r(), r()); ray.ryDirection = ray.d + 0.02f * Vector3f(r(), r(), r());
+            }
+            si.ComputeDifferentials(ray, Camera(cam), spp);
+            Vector3f wi = Normalize(Vector3f(r(), r(), r()));
+            Float eta = 1 + rng.Uniform<float>();
+            int flags = mode == 1 ? (int)BxDFFlags::SpecularReflection : mode == 2 ? (int)BxDFFlags::SpecularTransmission : (int)BxDFFlags::DiffuseReflection;
+            RayDifferential rd = si.SpawnRay(ray, BSDF(), wi, flags, eta);
+            in.insert(in.end(), {p.x, p.y, p.z, dpdu.x, dpdu.y, dpdu.z, dpdv.x, dpdv.y, dpdv.z, dndu.x, dndu.y, dndu.z, dndv.x, dndv.y, dndv.z, wo.x, wo.y, wo.z,
+                                 ray.hasDifferentials ? 1.f : 0.f, ray.rxOrigin.x, ray.rxOrigin.y, ray.rxOrigin.z, ray.ryOrigin.x, ray.ryOrigin.y, ray.ryOrigin.z,
+                                 ray.rxDirection.x, ray.rxDirection.y, ray.rxDirection.z, ray.ryDirection.x, ray.ryDirection.y, ray.ryDirection.z,
+                                 wi.x, wi.y, wi.z, eta, (float)flags, si.n.x, si.n.y, si.n.z, si.shading.n.x, si.shading.n.y, si.shading.n.z});
+            out.insert(out.end(), {si.dpdx.x, si.dpdx.y, si.dpdx.z, si.dpdy.x, si.dpdy.y, si.dpdy.z, si.dudx, si.dudy, si.dvdx, si.dvdy,
+                                   rd.hasDifferentials ? 1.f : 0.f, rd.rxOrigin.x, rd.rxOrigin.y, rd.rxOrigin.z, rd.ryOrigin.x, rd.ryOrigin.y, rd.ryOrigin.z,
+                                   rd.rxDirection.x, rd.rxDirection.y, rd.rxDirection.z, rd.ryDirection.x, rd.ryDirection.y, rd.ryDirection.z});
+        }
+        b.f32(StringPrintf("diff%d_in", cfg).c_str(), in);
+        b.f32(StringPrintf("diff%d_out", cfg).c_str(), out);
     }
 }
 

@@ -107,7 +107,7 @@ BPT_HD void GenerateCameraRay(const DeviceCamera &cam, Vec2 pFilm, Vec2 pLens, P
 // (PerspectiveCamera::GenerateRayDifferential cameras.cpp:450-477, Transform::operator()(RayDifferential) util/transform.h,
 // RayDifferential::ScaleDifferentials ray.h:53-58).  o, d: the main ray in render space.
 struct RayDiffs { Pt3 rxO, ryO; Vec3 rxD, ryD; };
-BPT_HD RayDiffs CameraRayDifferentials(const DeviceCamera &cam, const CamSample &cs, Pt3 o, Vec3 d) {
+BPT_HD RayDiffs CameraRayDifferentials(const DeviceCamera &cam, const CamSample &cs, Pt3 o, Vec3 d, bool scaleDifferentials = true) {
     Pt3 pCamera = XformPoint(cam.cameraFromRaster, Pt3(cs.pFilm.x, cs.pFilm.y, 0));
     RayDiffs r;
     if (cam.lensRadius > 0) {
@@ -130,11 +130,41 @@ BPT_HD RayDiffs CameraRayDifferentials(const DeviceCamera &cam, const CamSample 
     }
     r.rxO = XformPoint(cam.renderFromCamera, r.rxO); r.ryO = XformPoint(cam.renderFromCamera, r.ryO);
     r.rxD = XformVector(cam.renderFromCamera, r.rxD); r.ryD = XformVector(cam.renderFromCamera, r.ryD);
+    if (!scaleDifferentials) return r;   // CameraBase::FindMinimumDifferentials looks at the camera's own differentials
     float s = cam.rayDiffScale;
     r.rxO = o + (r.rxO - o) * s; r.ryO = o + (r.ryO - o) * s;
     r.rxD = d + (r.rxD - d) * s; r.ryD = d + (r.ryD - d) * s;
     return r;
 }
 
+
+// CameraBase::FindMinimumDifferentials (cameras.cpp:154-200): the smallest position / direction differentials over 512 camera rays
+// along the film diagonal, in camera space; Camera::Approximate_dp_dxy starts from them.  cameraFromRender = renderFromCamera's inverse.
+inline void FindMinimumDifferentials(DeviceCamera *cam, int fullResX, int fullResY) {
+    const float inf = BPT_INFINITY;
+    cam->minPosDifferentialX = cam->minPosDifferentialY = cam->minDirDifferentialX = cam->minDirDifferentialY = Vec3(inf, inf, inf);
+    CamSample cs{};
+    cs.pLens = Vec2(0.5f, 0.5f);
+    cs.time = 0.5f;
+    const int n = 512;
+    for (int i = 0; i < n; ++i) {
+        cs.pFilm.x = float(i) / (n - 1) * fullResX;
+        cs.pFilm.y = float(i) / (n - 1) * fullResY;
+        Pt3 o; Vec3 d;
+        GenerateCameraRay(*cam, cs.pFilm, cs.pLens, &o, &d);
+        RayDiffs rd = CameraRayDifferentials(*cam, cs, o, d, false);
+        Vec3 dox = XformVector(cam->cameraFromRender, rd.rxO - o);
+        if (Length(dox) < Length(cam->minPosDifferentialX)) cam->minPosDifferentialX = dox;
+        Vec3 doy = XformVector(cam->cameraFromRender, rd.ryO - o);
+        if (Length(doy) < Length(cam->minPosDifferentialY)) cam->minPosDifferentialY = doy;
+        d = Normalize(d);
+        Vec3 rxD = Normalize(rd.rxD), ryD = Normalize(rd.ryD);
+        Frame f = Frame::FromZ(d);
+        Vec3 df = f.ToLocal(d);
+        Vec3 dxf = Normalize(f.ToLocal(rxD)), dyf = Normalize(f.ToLocal(ryD));
+        if (Length(dxf - df) < Length(cam->minDirDifferentialX)) cam->minDirDifferentialX = dxf - df;
+        if (Length(dyf - df) < Length(cam->minDirDifferentialY)) cam->minDirDifferentialY = dyf - df;
+    }
+}
 
 }  // namespace bpt

@@ -15,6 +15,8 @@
 #include "../../include/b200pt.h"
 #include "bvh_build.h"
 #include "scene_xforms.h"
+#include "texture_host.h"
+#include "camera.h"
 #include "exr_writer.h"
 #include "kernels.h"
 #include "lightbvh.h"
@@ -51,6 +53,7 @@ struct OwnedLight {
     std::vector<float> image;
 };
 struct OwnedAreaLight { bpt_area_light a; OwnedSpectrum L; };
+struct OwnedTexture { bpt_texture t; HostImage img; };
 struct OwnedMedium { bpt_medium m; OwnedSpectrum sigma_a, sigma_s, Le; std::vector<float> density, leScale; };
 
 template <typename T>
@@ -176,6 +179,12 @@ struct bpt_engine {
     DevBuf<int> indexPool;
     DevBuf<float> nPool, uvPool, specPool;
     DevBuf<DeviceMaterial> dMaterials;
+    std::vector<OwnedTexture> textures;
+    DevBuf<float> dTexels, dEwaLUT;
+    DevBuf<DeviceMIPLevel> dMipLevels;
+    DevBuf<DeviceTexture> dTextures;
+    DevBuf<float4> rayDiffs;
+    bool haveTextures = false;
     DevBuf<DeviceLight> dLights;
     DevBuf<DeviceLightBVHNode> dLightNodes;
     DevBuf<int> dInfinite, dLightInBVH;
@@ -332,6 +341,26 @@ bool MakeSpectrumRec(const bpt_engine *e, const OwnedSpectrum &os, SpecType type
         out->kind = SPEC_PIECEWISE; out->n = n; out->table = sp.addDense(v);
         return true;
     }
+    case BPT_SPEC_BLACKBODY: {
+        // BlackbodySpectrum (util/spectrum.h:69-82, 497-520), densely sampled the way LightBase::LookupSpectrum stores emission spectra;
+        // elsewhere the reference evaluates it at the sampled wavelengths themselves
+        if (type != ST_ILLUMINANT) { *err = "blackbody spectra are supported for emission only"; return false; }
+        const float T = s.value;
+        auto blackbody = [](float lambda, float T) -> float {
+            if (T <= 0) return 0;
+            const float c = 299792458.f, h = 6.62606957e-34f, kb = 1.3806488e-23f;
+            float l = lambda * 1e-9f;
+            float l2 = l * l * 1.f;
+            float l5 = l2 * l2 * l;
+            return (2 * h * c * c) / (l5 * (FastExp((h * c) / (l * kb * T)) - 1));
+        };
+        float lambdaMax = 2.8977721e-3f / T;
+        float normalizationFactor = 1 / blackbody(lambdaMax * 1e9f, T);
+        std::vector<float> v(kNLambda);
+        for (int i = 0; i < kNLambda; ++i) v[i] = blackbody((float)(kLambdaMin + i), T) * normalizationFactor;
+        out->kind = SPEC_DENSE; out->table = sp.addDense(v);
+        return true;
+    }
     default: *err = "unsupported spectrum kind"; return false;
     }
 }
@@ -403,6 +432,7 @@ extern "C" int bpt_create(int cuda_device, const char *tables_path, bpt_engine *
         }
     }
     UploadSobolTable(e->tables.u32.at("sobol32_2x52").data());
+    UploadSobolTableTex(e->tables.u32.at("sobol32_2x52").data());
     ConfigureKernels();
     // defaults (scene.cpp / film.cpp / samplers.cpp defaults)
     e->filter = bpt_filter{BPT_FILTER_GAUSSIAN, 1.5f, 1.5f, 0.5f, 1.f / 3.f, 1.f / 3.f, 3.f};
@@ -478,6 +508,27 @@ extern "C" int bpt_scene_set_materials(bpt_engine *e, const bpt_material *m, int
         o.m = m[i];
         o.reflectance.Set(m[i].reflectance); o.eta.Set(m[i].eta); o.k.Set(m[i].k); o.iface_eta.Set(m[i].iface_eta);
         o.conductor_eta.Set(m[i].conductor_eta); o.conductor_k.Set(m[i].conductor_k); o.albedo.Set(m[i].albedo); o.transmittance.Set(m[i].transmittance);
+    }
+    return BPT_OK;
+}
+extern "C" int bpt_scene_set_textures(bpt_engine *e, const bpt_texture *t, int n) {
+    if (!e || (n > 0 && !t)) return BPT_ERR_INVALID;
+    e->textures.clear();
+    e->textures.resize(n);
+    for (int i = 0; i < n; ++i) {
+        const bpt_texture &b = t[i];
+        if (!b.pixels || b.xres <= 0 || b.yres <= 0 || (b.n_channels != 1 && b.n_channels != 3 && b.n_channels != 4))
+            return e->fail(BPT_ERR_INVALID, "texture image: 1, 3 or 4 channels of 8-bit or float texels expected");
+        if (b.format != BPT_IMAGE_U8 && b.format != BPT_IMAGE_F32) return e->fail(BPT_ERR_UNSUPPORTED, "texture image format not implemented (8-bit, float)");
+        if (b.filter < BPT_TEXFILTER_POINT || b.filter > BPT_TEXFILTER_EWA || b.wrap < BPT_TEXWRAP_BLACK || b.wrap > BPT_TEXWRAP_REPEAT)
+            return e->fail(BPT_ERR_INVALID, "texture filter / wrap mode out of range");
+        OwnedTexture &o = e->textures[i];
+        o.t = b; o.t.pixels = nullptr;
+        HostImage &im = o.img;
+        im.xres = b.xres; im.yres = b.yres; im.nc = b.n_channels;
+        const size_t cnt = (size_t)b.xres * b.yres * b.n_channels;
+        if (b.format == BPT_IMAGE_U8) { im.is8 = true; im.srgb = b.encoding == BPT_ENCODING_SRGB; im.p8.assign((const uint8_t *)b.pixels, (const uint8_t *)b.pixels + cnt); }
+        else { im.is8 = false; im.p32.assign((const float *)b.pixels, (const float *)b.pixels + cnt); }
     }
     return BPT_OK;
 }
@@ -683,6 +734,11 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         Pt3 c0 = cameraFromRaster(Pt3(0, 0, 0)), cx = cameraFromRaster(Pt3(1, 0, 0)), cy = cameraFromRaster(Pt3(0, 1, 0));
         dc.dxCamera = cx - c0; dc.dyCamera = cy - c0;
         dc.rayDiffScale = std::max(.125f, 1 / std::sqrt((float)std::max(1, e->sampler.spp)));
+        if (!e->textures.empty()) {   // Camera::Approximate_dp_dxy needs these; only texture filtering reads them
+            dc.cameraFromRender = ToMat4(renderFromCamera.mInv);
+            dc.sppScale = std::max(.125f, 1 / std::sqrt((float)std::max(1, e->sampler.spp)));
+            FindMinimumDifferentials(&dc, fl.xres, fl.yres);
+        }
     }
 
     // ---- sampler (samplers.h:228-239)
@@ -805,6 +861,26 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         }
         default: return e->fail(BPT_ERR_UNSUPPORTED, "material type not implemented yet");
         }
+        // image textures in place of constants; which parameters a material reads as textures follows its Create() in materials.cpp
+        auto texId = [&](int id, int *out) -> bool {
+            *out = -1;
+            if (id == 0) return true;
+            if (id < 0 || id > (int)e->textures.size()) return false;
+            *out = id - 1;
+            return true;
+        };
+        if (!texId(om.m.reflectance_tex, &dm.reflectanceTex) || !texId(om.m.transmittance_tex, &dm.transmittanceTex) ||
+            !texId(om.m.uroughness_tex, &dm.uroughnessTex) || !texId(om.m.vroughness_tex, &dm.vroughnessTex) ||
+            !texId(om.m.displacement_tex, &dm.displacementTex))
+            return e->fail(BPT_ERR_INVALID, "material refers to a texture that was not set");
+        const int mt = om.m.type;
+        const bool reflOK = mt == BPT_MAT_DIFFUSE || mt == BPT_MAT_COATED_DIFFUSE || mt == BPT_MAT_DIFFUSE_TRANSMISSION || mt == BPT_MAT_CONDUCTOR ||
+                            mt == BPT_MAT_COATED_CONDUCTOR;
+        const bool roughOK = mt == BPT_MAT_CONDUCTOR || mt == BPT_MAT_DIELECTRIC || mt == BPT_MAT_COATED_DIFFUSE || mt == BPT_MAT_COATED_CONDUCTOR;
+        if ((dm.reflectanceTex >= 0 && !reflOK) || (dm.transmittanceTex >= 0 && mt != BPT_MAT_DIFFUSE_TRANSMISSION) ||
+            ((dm.uroughnessTex >= 0 || dm.vroughnessTex >= 0) && !roughOK) || (dm.displacementTex >= 0 && mt == BPT_MAT_INTERFACE))
+            return e->fail(BPT_ERR_UNSUPPORTED, "texture on a material parameter that does not take one");
+        if (dm.reflectanceTex >= 0 && (mt == BPT_MAT_CONDUCTOR || mt == BPT_MAT_COATED_CONDUCTOR)) dm.useReflectance = 1;
     }
 
     // ---- meshes: transform to render space (TriangleMesh ctor util/mesh.cpp:25-70), build pools and lights
@@ -1325,7 +1401,41 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         dimg.push_back(di);
     }
     ECK(e->dImageLights.upload(dimg));
-    if (!dimg.empty() && e->dRgb2spec.n == 0) {
+    // ---- image textures: MIP pyramids (Image::GeneratePyramid restated in texture_host.h), decoded to float
+    e->haveTextures = !e->textures.empty();
+    if (e->haveTextures) {
+        if (!e->tables.f32.count("srgb8_to_linear") || !e->tables.f32.count("mip_filter_lut"))
+            return e->fail(BPT_ERR_IO, "tables blob lacks the texture tables (regenerate it with oracle/_ref/bin/ref_dump tables)");
+        texhost::Pyramid pyr{e->tables.F("srgb8_to_linear").data()};
+        std::vector<DeviceTexture> dtex(e->textures.size());
+        std::vector<std::vector<HostMIPLevel>> pyramids(e->textures.size());
+        size_t nTexels = 0, nLevels = 0;
+        for (size_t i = 0; i < e->textures.size(); ++i) {
+            HostImage im = e->textures[i].img;
+            DropOpaqueAlpha(&im);
+            pyramids[i] = pyr.Generate(im, e->textures[i].t.wrap);
+            const bpt_texture &b = e->textures[i].t;
+            DeviceTexture &d = dtex[i];
+            d.firstLevel = (int)nLevels; d.nLevels = (int)pyramids[i].size(); d.nc = im.nc;
+            d.wrap = b.wrap; d.filter = b.filter; d.maxAnisotropy = b.max_anisotropy;
+            d.su = b.su; d.sv = b.sv; d.du = b.du; d.dv = b.dv; d.scale = b.scale; d.invert = b.invert; d.pad = 0;
+            for (const HostMIPLevel &lv : pyramids[i]) nTexels += lv.texels.size();
+            nLevels += pyramids[i].size();
+        }
+        ECK(e->dTexels.alloc(nTexels));
+        std::vector<DeviceMIPLevel> dlev;
+        std::vector<float> all; all.reserve(nTexels);
+        for (auto &py : pyramids)
+            for (const HostMIPLevel &lv : py) {
+                dlev.push_back(DeviceMIPLevel{e->dTexels.p + all.size(), lv.xres, lv.yres});
+                all.insert(all.end(), lv.texels.begin(), lv.texels.end());
+            }
+        ECK(cudaMemcpy(e->dTexels.p, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice));
+        ECK(e->dMipLevels.upload(dlev));
+        ECK(e->dTextures.upload(dtex));
+        ECK(e->dEwaLUT.upload(e->tables.F("mip_filter_lut")));
+    }
+    if ((!dimg.empty() || e->haveTextures) && e->dRgb2spec.n == 0) {
         std::vector<float> t(e->tables.F("rgb2spec_srgb_scale"));
         t.insert(t.end(), e->tables.F("rgb2spec_srgb_coeffs").begin(), e->tables.F("rgb2spec_srgb_coeffs").end());
         ECK(e->dRgb2spec.upload(t));
@@ -1375,7 +1485,10 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     ECK(e->shadowTr.alloc(rc.useTr ? maxPaths : 1));
     rc.shadowItems = e->shadowItems.p;
     rc.shadowTr = e->shadowTr.p;
-    rc.storeHitT = (df.isGBuffer && e->haveInterface) ? 1 : 0;   // SkipIntersection advances the ray differentials by tHit (GBufferFilm only)
+    // SkipIntersection advances the ray differentials by tHit (read by GBufferFilm's dzdx / dzdy and by texture filtering)
+    rc.storeHitT = ((df.isGBuffer || e->haveTextures) && e->haveInterface) ? 1 : 0;
+    ECK(e->rayDiffs.alloc(e->haveTextures ? (size_t)maxPaths * 4 : 1));
+    rc.ps.rdiff = e->haveTextures ? e->rayDiffs.p : nullptr;
     ECK(e->hitT.alloc((rc.nMedia > 0 || rc.storeHitT) ? maxPaths : 1));
     ECK(e->pathMedium.alloc(rc.nMedia > 0 ? maxPaths : 1));
     rc.ps.hitT = e->hitT.p; rc.ps.medium = e->pathMedium.p;
@@ -1408,6 +1521,8 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     sv.imageLights = e->dImageLights.p;
     sv.instances = instanced ? e->dInstances.p : nullptr;
     sv.cieX = e->dTables.p; sv.cieY = e->dTables.p + kNLambda; sv.cieZ = e->dTables.p + 2 * kNLambda; sv.illumD65 = e->dTables.p + 3 * kNLambda;
+    sv.textures = e->haveTextures ? e->dTextures.p : nullptr; sv.mipLevels = e->haveTextures ? e->dMipLevels.p : nullptr;
+    sv.ewaLUT = e->haveTextures ? e->dEwaLUT.p : nullptr;
     sv.rgb2specScale = e->dRgb2spec.n ? e->dRgb2spec.p : nullptr; sv.rgb2specCoeffs = e->dRgb2spec.n ? e->dRgb2spec.p + 64 : nullptr;
     sv.nLights = (int)dlights.size();
     // ZSobol digit-prefix table: [dimension][pixel] uint32 (only when the permuted index fits in 32 bits)
@@ -1504,6 +1619,7 @@ static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int 
     const int sms = e->smCount;
     int launches = 0;
     UploadSamplerConstants(rc.sampler, st);
+    if (e->haveTextures) UploadSamplerConstantsTex(rc.sampler, st);
     ECK(cudaEventRecord(e->ev0, st));
     // scanline bands so that a band of S samples fits in the path-state arrays
     int width = x1 - x0;
@@ -1533,7 +1649,7 @@ static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int 
                 if (!dynamic && depth == maxDepth && !(rc.film.isGBuffer && depth == 0)) break;
                 profBegin(2);
                 for (int m = 0; m < MAT_NTAGS; ++m)
-                    if (e->materialPresent[m]) { LaunchShade(rc, m, next, sms, st); ++launches; }
+                    if (e->materialPresent[m]) { if (e->haveTextures) LaunchShadeTex(rc, m, next, sms, st); else LaunchShade(rc, m, next, sms, st); ++launches; }
                 profEnd();
                 profBegin(1);
                 if (rc.useTr) LaunchTraceShadowTr(rc, sms, st); else LaunchTraceShadow(rc, count, sms, st);
@@ -1752,6 +1868,7 @@ extern "C" int bpt_probe_sampler(bpt_engine *e, const int *pxy, const int *sidx,
     ECK(cudaMemcpy(b.p, sidx, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
     ECK(cudaMemcpy(c.p, dim, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
     UploadSamplerConstants(e->rc.sampler, e->stream);
+    if (e->haveTextures) UploadSamplerConstantsTex(e->rc.sampler, e->stream);
     LaunchProbeSampler(e->rc.sampler, a.p, b.p, c.p, n, r1.p, r2.p, e->stream);
     ECK(cudaStreamSynchronize(e->stream));
     ECK(cudaMemcpy(o1, r1.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));

@@ -6,6 +6,11 @@ namespace bpt {
 void UploadSobolTable(const uint32_t *t);
 void UploadSamplerConstants(const SamplerParams &sp, cudaStream_t st);
 void ConfigureKernels();
+// shade_tex.cu: the TEX = true instantiations of k_shade (image textures, bump mapping, ray differentials) with their own copies of the
+// sampler constants
+void UploadSobolTableTex(const uint32_t *t);
+void UploadSamplerConstantsTex(const SamplerParams &sp, cudaStream_t st);
+void LaunchShadeTex(const RenderCtx &rc, int materialTag, int nextQ, int sms, cudaStream_t st);
 void LaunchResetAll(const RenderCtx &rc, cudaStream_t st);
 void LaunchResetDepth(const RenderCtx &rc, int nextQ, cudaStream_t st);
 void LaunchGenerateCameraRays(const RenderCtx &rc, int x0, int x1, int y0, int y1, int firstSample, int nSamples, int sms, cudaStream_t st);

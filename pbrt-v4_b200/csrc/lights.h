@@ -36,6 +36,9 @@ struct SceneView {
     const float *rgb2specScale;      // 64 z-nodes
     const float *rgb2specCoeffs;     // [3][64][64][64][3]
     int nLights;
+    const DeviceTexture *textures;    // image textures (null: none)
+    const DeviceMIPLevel *mipLevels;
+    const float *ewaLUT;              // MIPFilterLUT, 128 entries (util/mipmap.cpp:59)
 };
 
 #if defined(__CUDACC__)
@@ -92,6 +95,12 @@ BPT_HD SurfaceIntr XformInteraction(const DeviceInstance &I, const SurfaceIntr &
     r.ns = Normalize(XformNrm(I.mInv, si.ns));
     r.dpdus = XformVec(I.m, si.dpdus);
     r.ns = FaceForward(r.ns, r.n);
+    return r;
+}
+BPT_HD SurfaceExtras XformExtras(const DeviceInstance &I, const SurfaceExtras &e) {
+    SurfaceExtras r;
+    r.dpdu = XformVec(I.m, e.dpdu); r.dpdv = XformVec(I.m, e.dpdv); r.dpdvs = XformVec(I.m, e.dpdvs);
+    r.dndus = XformNrm(I.mInv, e.dndus); r.dndvs = XformNrm(I.mInv, e.dndvs);
     return r;
 }
 BPT_HD Vec3 InstancedWo(const DeviceInstance &I, Vec3 rayD) {
@@ -272,22 +281,28 @@ BPT_HD LightLiSample InfiniteLightSampleLi(const SceneView &sv, const DeviceLigh
 // PointLight / SpotLight / DistantLight::SampleLi (lights.h:221-228, 771-783, 282-289; SpotLight::I lights.cpp:1360-1363):
 // pdf = 1, the reference point carries no normal and no error bounds.
 BPT_HD bool IsDeltaLight(int type) { return type == LIGHT_POINT || type == LIGHT_SPOT || type == LIGHT_DISTANT; }
-BPT_HD LightLiSample DeltaLightSampleLi(const SceneView &sv, const DeviceLight &light, const LightSampleContext &ctx,
-                                        const Wavelengths &wl) {
+// Outlined on the device: scenes without delta lights must not pay registers for it in the shading kernels (r02p: inlined, it cost
+// k_shade<Diffuse> 11 % through spills).
+#if defined(__CUDACC__)
+#define BPT_OUTLINED_FN inline __host__ __device__ __noinline__
+#else
+#define BPT_OUTLINED_FN inline
+#endif
+BPT_OUTLINED_FN LightLiSample DeltaLightSampleLi(const float *specPool, const DeviceLight &light, Pt3 ctxP, const Wavelengths &wl) {
     LightLiSample ls;
     ls.valid = false;
     ls.pdf = 1;
     ls.nLight = Nrm3(0, 0, 0);
     if (light.type == LIGHT_DISTANT) {
         Vec3 wi = light.w;
-        ls.pLight = Pt3i(ctx.p() + wi * (2 * light.sceneRadius));
-        ls.L = light.scale * DenseSample(sv.specPool + light.LemitTable, wl);
+        ls.pLight = Pt3i(ctxP + wi * (2 * light.sceneRadius));
+        ls.L = light.scale * DenseSample(specPool + light.LemitTable, wl);
         ls.wi = wi;
         ls.valid = true;
         return ls;
     }
     Pt3 p = light.p;
-    Vec3 wi = Normalize(p - ctx.p());
+    Vec3 wi = Normalize(p - ctxP);
     Spec I;
     if (light.type == LIGHT_SPOT) {
         Vec3 wLight = Normalize(ApplyM3(light.lightFromRender, -wi));
@@ -297,10 +312,10 @@ BPT_HD LightLiSample DeltaLightSampleLi(const SceneView &sv, const DeviceLight &
             float t = Clampf((x - a) / (b - a), 0.f, 1.f);
             smooth = t * t * (3 - 2 * t);
         }
-        I = (smooth * light.scale) * DenseSample(sv.specPool + light.LemitTable, wl);
+        I = (smooth * light.scale) * DenseSample(specPool + light.LemitTable, wl);
     } else
-        I = light.scale * DenseSample(sv.specPool + light.LemitTable, wl);
-    ls.L = I / DistanceSquared(p, ctx.p());
+        I = light.scale * DenseSample(specPool + light.LemitTable, wl);
+    ls.L = I / DistanceSquared(p, ctxP);
     if (light.type == LIGHT_SPOT && !ls.L.IsNonZero()) return ls;
     ls.wi = wi;
     ls.pLight = Pt3i(p);

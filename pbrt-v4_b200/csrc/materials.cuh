@@ -4,20 +4,31 @@
 //   ConductorMaterial::GetBxDF        materials.h:491-513
 //   DielectricMaterial::GetBxDF       materials.h:182-203
 //   CoatedConductorMaterial::GetBxDF  materials.cpp:346-398
-// Textures on this path are constant (SpectrumConstantTexture / FloatConstantTexture), i.e. what
-// BasicTextureEvaluator handles (textures.h:1158-1213).
+// GetBxDF<false>: every parameter is a constant (SpectrumConstantTexture / FloatConstantTexture), i.e. what BasicTextureEvaluator
+// handles (textures.h:1158-1213).  GetBxDF<true>: reflectance / transmittance / roughness parameters may be image textures evaluated
+// at the TextureEvalContext of the hit (UniversalTextureEvaluator).
 #pragma once
 #include "scene.h"
 #include "lights.h"
 #include "bxdfs.h"
+#include "texture.h"
 
 namespace bpt {
+
+template <bool TEX> BPT_HD Spec MatSpectrum(const SpectrumRec &rec, int tex, const SceneView &sv, const Wavelengths &wl, const TexEvalCtx *tc) {
+    if (TEX && tex >= 0) return EvalSpectrumImageTexture(sv, sv.textures[tex], *tc, wl, TEXSPEC_ALBEDO);
+    return EvalSpectrum(rec, sv.specPool, wl);
+}
+template <bool TEX> BPT_HD float MatFloat(float v, int tex, const SceneView &sv, const TexEvalCtx *tc) {
+    if (TEX && tex >= 0) return EvalFloatImageTexture(sv, sv.textures[tex], *tc);
+    return v;
+}
 
 struct DiffuseMaterialEval {
     static constexpr int kTag = MAT_DIFFUSE;
     typedef DiffuseBxDF BxDF;
-    BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged) {
-        Spec r = ClampSpec(EvalSpectrum(m.reflectance, sv.specPool, wl), 0, 1);
+    template <bool TEX> BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged, const TexEvalCtx *tc) {
+        Spec r = ClampSpec(MatSpectrum<TEX>(m.reflectance, m.reflectanceTex, sv, wl, tc), 0, 1);
         return DiffuseBxDF{r};
     }
 };
@@ -36,15 +47,15 @@ BPT_HD float EvalSpectrumAt(const SpectrumRec &s, const float *pool, float lambd
 struct ConductorMaterialEval {
     static constexpr int kTag = MAT_CONDUCTOR;
     typedef ConductorBxDF BxDF;
-    BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged) {
-        float uRough = m.uroughness, vRough = m.vroughness;
+    template <bool TEX> BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged, const TexEvalCtx *tc) {
+        float uRough = MatFloat<TEX>(m.uroughness, m.uroughnessTex, sv, tc), vRough = MatFloat<TEX>(m.vroughness, m.vroughnessTex, sv, tc);
         if (m.flags & 1) { uRough = TRDist::RoughnessToAlpha(uRough); vRough = TRDist::RoughnessToAlpha(vRough); }
         Spec etas, ks;
         if (!m.useReflectance) {
             etas = EvalSpectrum(m.eta, sv.specPool, wl);
             ks = EvalSpectrum(m.k, sv.specPool, wl);
         } else {
-            Spec r = ClampSpec(EvalSpectrum(m.reflectance, sv.specPool, wl), 0, .9999f);
+            Spec r = ClampSpec(MatSpectrum<TEX>(m.reflectance, m.reflectanceTex, sv, wl, tc), 0, .9999f);
             etas = Spec(1.f);
             ks = 2 * SqrtSpec(r) / SqrtSpec(ClampZero(Spec(1) - r));
         }
@@ -57,11 +68,11 @@ struct ConductorMaterialEval {
 struct DielectricMaterialEval {
     static constexpr int kTag = MAT_DIELECTRIC;
     typedef DielectricBxDF BxDF;
-    BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged) {
+    template <bool TEX> BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged, const TexEvalCtx *tc) {
         float sampledEta = EvalSpectrumAt(m.eta, sv.specPool, wl.lambda[0]);
         if (m.eta.kind != SPEC_CONSTANT) { wl.TerminateSecondary(); *lambdaChanged = true; }
         if (sampledEta == 0) sampledEta = 1;
-        float urough = m.uroughness, vrough = m.vroughness;
+        float urough = MatFloat<TEX>(m.uroughness, m.uroughnessTex, sv, tc), vrough = MatFloat<TEX>(m.vroughness, m.vroughnessTex, sv, tc);
         if (m.flags & 1) { urough = TRDist::RoughnessToAlpha(urough); vrough = TRDist::RoughnessToAlpha(vrough); }
         DielectricBxDF b;
         b.eta = sampledEta; b.mfDistrib = TRDist(urough, vrough);
@@ -72,7 +83,7 @@ struct DielectricMaterialEval {
 struct CoatedConductorMaterialEval {
     static constexpr int kTag = MAT_COATED_CONDUCTOR;
     typedef CoatedConductorBxDF BxDF;
-    BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged) {
+    template <bool TEX> BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged, const TexEvalCtx *tc) {
         float iurough = m.iface_uroughness, ivrough = m.iface_vroughness;
         if (m.flags & 1) { iurough = TRDist::RoughnessToAlpha(iurough); ivrough = TRDist::RoughnessToAlpha(ivrough); }
         TRDist interfaceDistrib(iurough, ivrough);
@@ -85,13 +96,13 @@ struct CoatedConductorMaterialEval {
             ce = EvalSpectrum(m.eta, sv.specPool, wl);
             ck = EvalSpectrum(m.k, sv.specPool, wl);
         } else {
-            Spec r = ClampSpec(EvalSpectrum(m.reflectance, sv.specPool, wl), 0, .9999f);
+            Spec r = ClampSpec(MatSpectrum<TEX>(m.reflectance, m.reflectanceTex, sv, wl, tc), 0, .9999f);
             ce = Spec(1.f);
             ck = 2 * SqrtSpec(r) / SqrtSpec(ClampZero(Spec(1) - r));
         }
         ce /= ieta;
         ck /= ieta;
-        float curough = m.uroughness, cvrough = m.vroughness;
+        float curough = MatFloat<TEX>(m.uroughness, m.uroughnessTex, sv, tc), cvrough = MatFloat<TEX>(m.vroughness, m.vroughnessTex, sv, tc);
         if (m.flags & 1) { curough = TRDist::RoughnessToAlpha(curough); cvrough = TRDist::RoughnessToAlpha(cvrough); }
         TRDist conductorDistrib(curough, cvrough);
         Spec a = ClampSpec(EvalSpectrum(m.albedo, sv.specPool, wl), 0, 1);
@@ -109,9 +120,9 @@ struct CoatedConductorMaterialEval {
 struct CoatedDiffuseMaterialEval {
     static constexpr int kTag = MAT_COATED_DIFFUSE;
     typedef CoatedDiffuseBxDF BxDF;
-    BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged) {
-        Spec r = ClampSpec(EvalSpectrum(m.reflectance, sv.specPool, wl), 0, 1);
-        float urough = m.uroughness, vrough = m.vroughness;
+    template <bool TEX> BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged, const TexEvalCtx *tc) {
+        Spec r = ClampSpec(MatSpectrum<TEX>(m.reflectance, m.reflectanceTex, sv, wl, tc), 0, 1);
+        float urough = MatFloat<TEX>(m.uroughness, m.uroughnessTex, sv, tc), vrough = MatFloat<TEX>(m.vroughness, m.vroughnessTex, sv, tc);
         if (m.flags & 1) { urough = TRDist::RoughnessToAlpha(urough); vrough = TRDist::RoughnessToAlpha(vrough); }
         TRDist distrib(urough, vrough);
         float thick = m.thickness;
@@ -133,9 +144,9 @@ struct CoatedDiffuseMaterialEval {
 struct DiffuseTransmissionMaterialEval {
     static constexpr int kTag = MAT_DIFFUSE_TRANSMISSION;
     typedef DiffuseTransmissionBxDF BxDF;
-    BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged) {
-        Spec r = ClampSpec(EvalSpectrum(m.reflectance, sv.specPool, wl) * m.scale, 0, 1);
-        Spec t = ClampSpec(EvalSpectrum(m.transmittance, sv.specPool, wl) * m.scale, 0, 1);
+    template <bool TEX> BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged, const TexEvalCtx *tc) {
+        Spec r = ClampSpec(MatSpectrum<TEX>(m.reflectance, m.reflectanceTex, sv, wl, tc) * m.scale, 0, 1);
+        Spec t = ClampSpec(MatSpectrum<TEX>(m.transmittance, m.transmittanceTex, sv, wl, tc) * m.scale, 0, 1);
         return DiffuseTransmissionBxDF{r, t};
     }
 };
@@ -144,7 +155,7 @@ struct DiffuseTransmissionMaterialEval {
 struct ThinDielectricMaterialEval {
     static constexpr int kTag = MAT_THIN_DIELECTRIC;
     typedef ThinDielectricBxDF BxDF;
-    BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged) {
+    template <bool TEX> BPT_HD static BxDF GetBxDF(const DeviceMaterial &m, const SceneView &sv, Wavelengths &wl, bool *lambdaChanged, const TexEvalCtx *tc) {
         float sampledEta = EvalSpectrumAt(m.eta, sv.specPool, wl.lambda[0]);
         if (m.eta.kind != SPEC_CONSTANT) { wl.TerminateSecondary(); *lambdaChanged = true; }
         if (sampledEta == 0) sampledEta = 1;
@@ -155,7 +166,7 @@ struct ThinDielectricMaterialEval {
 struct InterfaceMaterialEval {
     static constexpr int kTag = MAT_INTERFACE;
     typedef DiffuseBxDF BxDF;
-    BPT_HD static BxDF GetBxDF(const DeviceMaterial &, const SceneView &, Wavelengths &, bool *) { return DiffuseBxDF{Spec(0.f)}; }
+    template <bool TEX> BPT_HD static BxDF GetBxDF(const DeviceMaterial &, const SceneView &, Wavelengths &, bool *, const TexEvalCtx *) { return DiffuseBxDF{Spec(0.f)}; }
 };
 
 }  // namespace bpt

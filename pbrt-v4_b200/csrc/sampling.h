@@ -213,7 +213,7 @@ struct SamplerParams {
 #endif
 struct SamplerParams;
 #if defined(__CUDACC__) && defined(BPT_SOBOL_DEVICE_TABLE)
-__device__ __noinline__ float2 ZSobolOutlined(uint64_t mortonIndex, int pixel, int dimension, int nd);
+static __device__ __noinline__ float2 ZSobolOutlined(uint64_t mortonIndex, int pixel, int dimension, int nd);
 #endif
 constexpr int kDimHashTable = 128;   // Hash(dimension, seed) for dimension < kDimHashTable
 
@@ -337,7 +337,7 @@ struct Sampler {
 #if defined(__CUDACC__) && defined(BPT_SOBOL_DEVICE_TABLE)
 __constant__ SamplerParams c_sampler;
 __constant__ uint64_t c_dimHash[kDimHashTable];
-__device__ __noinline__ float2 ZSobolOutlined(uint64_t mortonIndex, int pixel, int dimension, int nd) {
+static __device__ __noinline__ float2 ZSobolOutlined(uint64_t mortonIndex, int pixel, int dimension, int nd) {
     Sampler s;
     s.sp = &c_sampler; s.mortonIndex = mortonIndex; s.pixel = pixel; s.dimension = dimension;
     uint64_t sampleIndex = s.GetSampleIndex();

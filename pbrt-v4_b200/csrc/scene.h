@@ -25,6 +25,11 @@ struct DeviceCamera {
     int type, pad;
     Vec3 dxCamera, dyCamera;    // PerspectiveCamera::dxCamera / dyCamera (cameras.h:347-351), used for GBufferFilm ray differentials
     float rayDiffScale;         // max(.125, 1 / sqrt(spp))  (cpu/integrators.cpp:251-254)
+    // Camera::Approximate_dp_dxy (cameras.h:155-183), scenes with textures only: the minimum differentials found by
+    // CameraBase::FindMinimumDifferentials (cameras.cpp:154-200), the inverse camera transform and the spp scale
+    Mat4 cameraFromRender;
+    Vec3 minPosDifferentialX, minPosDifferentialY, minDirDifferentialX, minDirDifferentialY;
+    float sppScale;             // max(.125, 1 / sqrt(samplesPerPixel))
 };
 
 struct DeviceFilm {
@@ -57,6 +62,20 @@ struct DeviceFilter {          // FilterSampler tables (filters.cpp FilterSample
     int sampled;               // 0: BoxFilter::Sample  1: FilterSampler table (gaussian, mitchell, sinc)  2: TriangleFilter::Sample
 };
 
+// One level of an image texture's MIP pyramid (Image::GeneratePyramid), texels decoded to float, nc interleaved channels
+struct DeviceMIPLevel { const float *texels; int xres, yres; };
+// FloatImageTexture / SpectrumImageTexture with a UVMapping (textures.h:86-106, 525-626)
+struct DeviceTexture {
+    int firstLevel, nLevels;   // into SceneView::mipLevels
+    int nc;                    // channels of the image (1, 3 or 4)
+    int wrap, filter;          // WrapMode, FilterFunction
+    float maxAnisotropy;
+    float su, sv, du, dv;
+    float scale;
+    int invert;
+    int pad;
+};
+
 struct DeviceMaterial {
     int type;                  // MaterialTag
     int flags;                 // bit0: remaproughness
@@ -71,6 +90,8 @@ struct DeviceMaterial {
     int optionsSeed;           // Options->seed (LayeredBxDF seeds its RNG with it, bxdfs.h:510)
     SpectrumRec transmittance; // diffusetransmission
     float scale;               // diffusetransmission "scale"
+    // image textures in place of the constants above (-1: the constant) and the "displacement" float texture of bump mapping
+    int reflectanceTex, transmittanceTex, uroughnessTex, vroughnessTex, displacementTex;
 };
 
 struct DeviceMesh {

@@ -82,7 +82,15 @@ struct TriAttribs {
     Vec2 uv0, uv1, uv2;
 };
 
-BPT_HD SurfaceIntr TriangleInteraction(Pt3 p0, Pt3 p1, Pt3 p2, const TriAttribs &a, TriHit ti) {
+// The members of SurfaceInteraction only texture filtering and bump mapping read (interaction.h: dpdu, dpdv, shading.dpdv,
+// shading.dndu / dndv); filled when the caller passes a record
+struct SurfaceExtras {
+    Vec3 dpdu, dpdv;     // geometric
+    Vec3 dpdvs;          // shading.dpdv
+    Nrm3 dndus, dndvs;   // shading.dndu, shading.dndv
+};
+
+BPT_HD SurfaceIntr TriangleInteraction(Pt3 p0, Pt3 p1, Pt3 p2, const TriAttribs &a, TriHit ti, SurfaceExtras *ex = nullptr) {
     Vec2 uv0(0, 0), uv1(1, 0), uv2(1, 1);
     if (a.hasUV) { uv0 = a.uv0; uv1 = a.uv1; uv2 = a.uv2; }
     Vec2 duv02(uv0.x - uv2.x, uv0.y - uv2.y), duv12(uv1.x - uv2.x, uv1.y - uv2.y);
@@ -121,6 +129,7 @@ BPT_HD SurfaceIntr TriangleInteraction(Pt3 p0, Pt3 p1, Pt3 p2, const TriAttribs 
     isect.dpdus = dpdu;
     isect.n = isect.ns = Nrm3(Normalize(Cross(dp02, dp12)));
     if (a.flipNormal) isect.n = isect.ns = -isect.n;
+    if (ex) { ex->dpdu = dpdu; ex->dpdv = dpdv; ex->dpdvs = dpdv; ex->dndus = ex->dndvs = Nrm3(0, 0, 0); }
     if (a.hasN) {
         Nrm3 ns = ti.b0 * a.n0 + ti.b1 * a.n1 + ti.b2 * a.n2;
         ns = LengthSquared(ns) > 0 ? Normalize(ns) : isect.n;
@@ -132,6 +141,26 @@ BPT_HD SurfaceIntr TriangleInteraction(Pt3 p0, Pt3 p1, Pt3 p2, const TriAttribs 
         isect.ns = ns;
         isect.n = FaceForward(isect.n, isect.ns);
         isect.dpdus = ss;
+        if (ex) {
+            // dndu / dndv of the interpolated normal (shapes.h:967-1000)
+            ex->dpdvs = ts;
+            Nrm3 dn1 = a.n0 - a.n2, dn2 = a.n1 - a.n2;
+            if (degenerateUV) {
+                Vec3 dn = Cross(V(a.n2 - a.n0), V(a.n1 - a.n0));
+                if (LengthSquared(dn) == 0) ex->dndus = ex->dndvs = Nrm3(0, 0, 0);
+                else {
+                    Vec3 dnu, dnv;
+                    CoordinateSystem(dn, &dnu, &dnv);
+                    ex->dndus = Nrm3(dnu); ex->dndvs = Nrm3(dnv);
+                }
+            } else {
+                float invDet = 1 / determinant;
+                ex->dndus = Nrm3(DifferenceOfProducts(duv12.y, dn1.x, duv02.y, dn2.x), DifferenceOfProducts(duv12.y, dn1.y, duv02.y, dn2.y),
+                                 DifferenceOfProducts(duv12.y, dn1.z, duv02.y, dn2.z)) * invDet;
+                ex->dndvs = Nrm3(DifferenceOfProducts(duv02.x, dn2.x, duv12.x, dn1.x), DifferenceOfProducts(duv02.x, dn2.y, duv12.x, dn1.y),
+                                 DifferenceOfProducts(duv02.x, dn2.z, duv12.x, dn1.z)) * invDet;
+            }
+        }
     }
     return isect;
 }

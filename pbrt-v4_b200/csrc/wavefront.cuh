@@ -33,7 +33,9 @@ struct PathState {
     float4 *ctx2;        //              n.z, ns.x, ns.y, ns.z
     float4 *vs;          // GBufferFilm only: VisibleSurface of the path, 6 float4 per slot in arrays of maxPaths:
                          //   [0] p.xyz | set  [1] n.xyz | u  [2] ns.xyz | v  [3] dpdx  [4] dpdy  [5] albedo
-    uint4 *misc;         // px | py << 16, sampleIndex, sampler dimension, depth | specularBounce << 8 | anyNonSpecular << 9
+    float4 *rdiff;       // scenes with textures only: the ray's differentials rxOrigin, ryOrigin, rxDirection, ryDirection (4 arrays of
+                         //   maxPaths) while misc.w says they are stored (shade.cuh: kPathStoredDiffs)
+    uint4 *misc;         // px | py << 16, sampleIndex, sampler dimension, depth | specularBounce << 8 | anyNonSpecular << 9 | diff state
     float2 *aux;         // etaScale, filterWeight
 };
 

@@ -54,16 +54,16 @@ int main() {
         sv.specPool = pool.data();
         std::vector<float> mine;
         bool ch;
-        { Wavelengths wl = Wavelengths::SampleVisible(in[q]); ConductorBxDF b = ConductorMaterialEval::GetBxDF(condSpectral, sv, wl, &ch);
+        { Wavelengths wl = Wavelengths::SampleVisible(in[q]); ConductorBxDF b = ConductorMaterialEval::GetBxDF<false>(condSpectral, sv, wl, &ch, nullptr);
           mine.insert(mine.end(), {b.mfDistrib.alpha_x, b.mfDistrib.alpha_y, b.eta[0], b.eta[3], b.k[0], b.k[3], wl.pdf[0], wl.pdf[3]}); }
-        { Wavelengths wl = Wavelengths::SampleVisible(in[q]); ConductorBxDF b = ConductorMaterialEval::GetBxDF(condRefl, sv, wl, &ch);
+        { Wavelengths wl = Wavelengths::SampleVisible(in[q]); ConductorBxDF b = ConductorMaterialEval::GetBxDF<false>(condRefl, sv, wl, &ch, nullptr);
           mine.insert(mine.end(), {b.mfDistrib.alpha_x, b.mfDistrib.alpha_y, b.eta[0], b.eta[3], b.k[0], b.k[3], wl.pdf[0], wl.pdf[3]}); }
-        { Wavelengths wl = Wavelengths::SampleVisible(in[q]); DielectricBxDF b = DielectricMaterialEval::GetBxDF(dielConst, sv, wl, &ch);
+        { Wavelengths wl = Wavelengths::SampleVisible(in[q]); DielectricBxDF b = DielectricMaterialEval::GetBxDF<false>(dielConst, sv, wl, &ch, nullptr);
           mine.insert(mine.end(), {b.mfDistrib.alpha_x, b.mfDistrib.alpha_y, b.eta, wl.pdf[0], wl.pdf[3]}); }
-        { Wavelengths wl = Wavelengths::SampleVisible(in[q]); DielectricBxDF b = DielectricMaterialEval::GetBxDF(dielDisp, sv, wl, &ch);
+        { Wavelengths wl = Wavelengths::SampleVisible(in[q]); DielectricBxDF b = DielectricMaterialEval::GetBxDF<false>(dielDisp, sv, wl, &ch, nullptr);
           mine.insert(mine.end(), {b.mfDistrib.alpha_x, b.mfDistrib.alpha_y, b.eta, wl.pdf[0], wl.pdf[3]}); }
         for (int c = 0; c < 2; ++c) {
-            Wavelengths wl = Wavelengths::SampleVisible(in[q]); CoatedConductorBxDF b = CoatedConductorMaterialEval::GetBxDF(c ? coated2 : coated, sv, wl, &ch);
+            Wavelengths wl = Wavelengths::SampleVisible(in[q]); CoatedConductorBxDF b = CoatedConductorMaterialEval::GetBxDF<false>(c ? coated2 : coated, sv, wl, &ch, nullptr);
             mine.insert(mine.end(), {b.top.mfDistrib.alpha_x, b.top.mfDistrib.alpha_y, b.top.eta, b.bottom.mfDistrib.alpha_x, b.bottom.mfDistrib.alpha_y, b.bottom.eta[0],
                                      b.bottom.eta[3], b.bottom.k[0], b.bottom.k[3], b.thickness, b.g, b.albedo[0], (float)b.maxDepth, (float)b.nSamples, wl.pdf[0], wl.pdf[3]});
         }
