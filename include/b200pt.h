@@ -107,6 +107,7 @@ typedef struct {
      * spectrum textures (albedo), "roughness" / "uroughness" / "vroughness" float textures of conductor, dielectric, coateddiffuse,
      * and the "displacement" float texture of bump mapping (materials.h:107-138) */
     int reflectance_tex, transmittance_tex, uroughness_tex, vroughness_tex, displacement_tex;
+    int normal_map_tex;           /* "normalmap": a BPT_TEXTURE_NORMALMAP entry of bpt_scene_set_textures (materials.h:86-105) */
 } bpt_material;
 
 /* Texture "imagemap" (FloatImageTexture / SpectrumImageTexture, textures.h:525-626) with a "uv" mapping (textures.h:86-106).  The image
@@ -125,7 +126,10 @@ typedef struct {
     int wrap;                     /* "wrap": BPT_TEXWRAP_* (repeat) */
     float scale; int invert;      /* "scale" (1), "invert" */
     float su, sv, du, dv;         /* "uscale" "vscale" "udelta" "vdelta" */
+    int kind;                     /* BPT_TEXTURE_IMAGEMAP, or BPT_TEXTURE_NORMALMAP: the RGB image of a material's "normalmap" (read with the
+                                   * linear encoding, looked up bilinearly without a pyramid; only the image fields are used) */
 } bpt_texture;
+enum { BPT_TEXTURE_IMAGEMAP = 0, BPT_TEXTURE_NORMALMAP = 1 };
 
 typedef struct {
     bpt_spectrum L;               /* BPT_SPEC_NONE => colour-space illuminant */

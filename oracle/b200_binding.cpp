@@ -59,7 +59,7 @@ struct Api {
 #define BPT_FN(name) decltype(&::name) name = nullptr;
     BPT_FN(bpt_create) BPT_FN(bpt_destroy) BPT_FN(bpt_last_error) BPT_FN(bpt_scene_begin) BPT_FN(bpt_scene_set_transform_space)
     BPT_FN(bpt_scene_set_camera) BPT_FN(bpt_scene_set_film) BPT_FN(bpt_scene_set_filter) BPT_FN(bpt_scene_set_sampler)
-    BPT_FN(bpt_scene_set_integrator) BPT_FN(bpt_scene_set_materials) BPT_FN(bpt_scene_set_area_lights) BPT_FN(bpt_scene_add_mesh)
+    BPT_FN(bpt_scene_set_integrator) BPT_FN(bpt_scene_set_materials) BPT_FN(bpt_scene_set_textures) BPT_FN(bpt_scene_set_area_lights) BPT_FN(bpt_scene_add_mesh)
     BPT_FN(bpt_scene_add_instance) BPT_FN(bpt_scene_add_light) BPT_FN(bpt_scene_add_medium) BPT_FN(bpt_scene_set_camera_medium)
     BPT_FN(bpt_scene_commit) BPT_FN(bpt_render) BPT_FN(bpt_film_resolve) BPT_FN(bpt_film_resolve_gbuffer)
 #undef BPT_FN
@@ -69,7 +69,7 @@ struct Api {
 #define BPT_FN(name) name = (decltype(name))dlsym(h, #name); if (!name) ErrorExit("%s: symbol %s missing", path, #name);
         BPT_FN(bpt_create) BPT_FN(bpt_destroy) BPT_FN(bpt_last_error) BPT_FN(bpt_scene_begin) BPT_FN(bpt_scene_set_transform_space)
         BPT_FN(bpt_scene_set_camera) BPT_FN(bpt_scene_set_film) BPT_FN(bpt_scene_set_filter) BPT_FN(bpt_scene_set_sampler)
-        BPT_FN(bpt_scene_set_integrator) BPT_FN(bpt_scene_set_materials) BPT_FN(bpt_scene_set_area_lights) BPT_FN(bpt_scene_add_mesh)
+        BPT_FN(bpt_scene_set_integrator) BPT_FN(bpt_scene_set_materials) BPT_FN(bpt_scene_set_textures) BPT_FN(bpt_scene_set_area_lights) BPT_FN(bpt_scene_add_mesh)
         BPT_FN(bpt_scene_add_instance) BPT_FN(bpt_scene_add_light) BPT_FN(bpt_scene_add_medium) BPT_FN(bpt_scene_set_camera_medium)
         BPT_FN(bpt_scene_commit) BPT_FN(bpt_render) BPT_FN(bpt_film_resolve) BPT_FN(bpt_film_resolve_gbuffer)
 #undef BPT_FN
@@ -81,6 +81,7 @@ static bpt_mat4 ToB(const SquareMatrix<4> &m) { bpt_mat4 r; for (int i = 0; i < 
 // ---- the builder: BasicSceneBuilder plus a record of what BasicScene does not keep
 struct LightRecord { std::string type; ParameterDictionary params; Transform renderFromLight; };
 struct MediumRecord { std::string name; ParameterDictionary params; Transform renderFromMedium; };
+struct TextureRecord { std::string name, type, texname; ParameterDictionary params; FileLoc loc; };
 
 class B200SceneBuilder : public BasicSceneBuilder {
   public:
@@ -100,7 +101,14 @@ class B200SceneBuilder : public BasicSceneBuilder {
         media.push_back(MediumRecord{NormalizeUTF8(name), ParameterDictionary(std::move(copy), graphicsState.mediumAttributes, graphicsState.colorSpace), RenderFromObject(0)});
         BasicSceneBuilder::MakeNamedMedium(name, std::move(params), loc);
     }
+    void Texture(const std::string &name, const std::string &type, const std::string &texname, ParsedParameterVector params, FileLoc loc) override {
+        // BasicScene hands image textures to loading jobs and keeps no entity for them (scene.cpp:912-1010): record the directive
+        ParsedParameterVector copy = params;
+        textures.push_back(TextureRecord{NormalizeUTF8(name), type, texname, ParameterDictionary(std::move(copy), graphicsState.textureAttributes, graphicsState.colorSpace), loc});
+        BasicSceneBuilder::Texture(name, type, texname, std::move(params), loc);
+    }
     class Transform cameraFromWorld;
+    std::vector<TextureRecord> textures;
     std::vector<LightRecord> lights;
     std::vector<MediumRecord> media;
 };
@@ -136,35 +144,80 @@ static bpt_spectrum GetSpectrum(const ParameterDictionary &dict, const std::stri
     return s;
 }
 
-static bpt_material MakeMaterial(const std::string &type, const ParameterDictionary &d, Stores &st, const FileLoc *loc) {
+// Material parameters that name a texture ("texture reflectance" "name"): the id (index + 1) the texture got in bpt_scene_set_textures
+struct TexIds { std::map<std::string, int> floats, spectra; std::function<int(const std::string &)> normalMap; };
+static const ParsedParameter *FindParam(const ParameterDictionary &dict, const std::string &name) {
+    for (const ParsedParameter *p : dict.GetParameterVector()) if (p->name == name) return p;
+    return nullptr;
+}
+static bpt_spectrum GetSpectrumOrTexture(const ParameterDictionary &d, const std::string &name, Stores &st, const TexIds &tx, int *tex, const FileLoc *loc) {
+    *tex = 0;
+    const ParsedParameter *p = FindParam(d, name);
+    if (p && p->type == "texture") {
+        p->lookedUp = true;
+        auto it = p->strings.empty() ? tx.spectra.end() : tx.spectra.find(p->strings[0]);
+        if (it == tx.spectra.end()) ErrorExit(loc, "parameter \"%s\": unknown spectrum texture", name);
+        *tex = it->second;
+        bpt_spectrum s; std::memset(&s, 0, sizeof(s));
+        return s;
+    }
+    return GetSpectrum(d, name, st);
+}
+static float GetFloatOrTexture(const ParameterDictionary &d, const std::string &name, float dflt, const TexIds &tx, int *tex, const FileLoc *loc) {
+    *tex = 0;
+    const ParsedParameter *p = FindParam(d, name);
+    if (p && p->type == "texture") {
+        p->lookedUp = true;
+        auto it = p->strings.empty() ? tx.floats.end() : tx.floats.find(p->strings[0]);
+        if (it == tx.floats.end()) ErrorExit(loc, "parameter \"%s\": unknown float texture", name);
+        *tex = it->second;
+        return dflt;
+    }
+    return d.GetOneFloat(name, dflt);
+}
+// "roughness" / "uroughness" / "vroughness" as the materials' Create() functions resolve them (materials.cpp)
+static void GetRoughness(const ParameterDictionary &d, const std::string &prefix, const TexIds &tx, float *rough, float *u, float *v, int *utex, int *vtex, const FileLoc *loc) {
+    int rt = 0, ut = 0, vt = 0;
+    *rough = GetFloatOrTexture(d, prefix + "roughness", 0.f, tx, &rt, loc);
+    const bool haveU = FindParam(d, prefix + "uroughness") != nullptr, haveV = FindParam(d, prefix + "vroughness") != nullptr;
+    *u = GetFloatOrTexture(d, prefix + "uroughness", *rough, tx, &ut, loc);
+    *v = GetFloatOrTexture(d, prefix + "vroughness", *rough, tx, &vt, loc);
+    if (utex) { *utex = haveU ? ut : rt; *vtex = haveV ? vt : rt; }
+    else if (rt || ut || vt) ErrorExit(loc, "parameter \"%sroughness\": textures are not implemented by the engine here", prefix);
+}
+
+static bpt_material MakeMaterial(const std::string &type, const ParameterDictionary &d, Stores &st, const TexIds &tx, const FileLoc *loc) {
     bpt_material m; std::memset(&m, 0, sizeof(m));
     m.uroughness = m.vroughness = m.iface_uroughness = m.iface_vroughness = -1;
-    if (type == "diffuse") { m.type = BPT_MAT_DIFFUSE; m.reflectance = GetSpectrum(d, "reflectance", st); return m; }
+    if (std::string nm = ResolveFilename(d.GetOneString("normalmap", "")); !nm.empty()) m.normal_map_tex = tx.normalMap(nm);
+    if (const ParsedParameter *p = FindParam(d, "displacement")) {
+        auto it = (p->type != "texture" || p->strings.empty()) ? tx.floats.end() : tx.floats.find(p->strings[0]);
+        if (it == tx.floats.end()) ErrorExit(loc, "\"displacement\" must name a float texture");
+        p->lookedUp = true;
+        m.displacement_tex = it->second;
+    }
+    if (type == "diffuse") { m.type = BPT_MAT_DIFFUSE; m.reflectance = GetSpectrumOrTexture(d, "reflectance", st, tx, &m.reflectance_tex, loc); return m; }
     if (type == "interface" || type == "none" || type == "") { m.type = BPT_MAT_INTERFACE; return m; }
     if (type == "conductor") {
         m.type = BPT_MAT_CONDUCTOR;
-        m.eta = GetSpectrum(d, "eta", st); m.k = GetSpectrum(d, "k", st); m.reflectance = GetSpectrum(d, "reflectance", st);
-        m.roughness = d.GetOneFloat("roughness", 0.f);
-        m.uroughness = d.GetOneFloat("uroughness", m.roughness); m.vroughness = d.GetOneFloat("vroughness", m.roughness);
+        m.eta = GetSpectrum(d, "eta", st); m.k = GetSpectrum(d, "k", st); m.reflectance = GetSpectrumOrTexture(d, "reflectance", st, tx, &m.reflectance_tex, loc);
+        GetRoughness(d, "", tx, &m.roughness, &m.uroughness, &m.vroughness, &m.uroughness_tex, &m.vroughness_tex, loc);
         m.remap_roughness = d.GetOneBool("remaproughness", true);
         return m;
     }
     if (type == "dielectric") {
         m.type = BPT_MAT_DIELECTRIC;
         m.eta = GetSpectrum(d, "eta", st);
-        m.roughness = d.GetOneFloat("roughness", 0.f);
-        m.uroughness = d.GetOneFloat("uroughness", m.roughness); m.vroughness = d.GetOneFloat("vroughness", m.roughness);
+        GetRoughness(d, "", tx, &m.roughness, &m.uroughness, &m.vroughness, &m.uroughness_tex, &m.vroughness_tex, loc);
         m.remap_roughness = d.GetOneBool("remaproughness", true);
         return m;
     }
     if (type == "coatedconductor") {
         m.type = BPT_MAT_COATED_CONDUCTOR;
         m.iface_eta = GetSpectrum(d, "interface.eta", st); m.conductor_eta = GetSpectrum(d, "conductor.eta", st);
-        m.conductor_k = GetSpectrum(d, "conductor.k", st); m.reflectance = GetSpectrum(d, "reflectance", st); m.albedo = GetSpectrum(d, "albedo", st);
-        m.iface_roughness = d.GetOneFloat("interface.roughness", 0.f);
-        m.iface_uroughness = d.GetOneFloat("interface.uroughness", m.iface_roughness); m.iface_vroughness = d.GetOneFloat("interface.vroughness", m.iface_roughness);
-        m.roughness = d.GetOneFloat("conductor.roughness", 0.f);
-        m.uroughness = d.GetOneFloat("conductor.uroughness", m.roughness); m.vroughness = d.GetOneFloat("conductor.vroughness", m.roughness);
+        m.conductor_k = GetSpectrum(d, "conductor.k", st); m.reflectance = GetSpectrumOrTexture(d, "reflectance", st, tx, &m.reflectance_tex, loc); m.albedo = GetSpectrum(d, "albedo", st);
+        GetRoughness(d, "interface.", tx, &m.iface_roughness, &m.iface_uroughness, &m.iface_vroughness, nullptr, nullptr, loc);
+        GetRoughness(d, "conductor.", tx, &m.roughness, &m.uroughness, &m.vroughness, &m.uroughness_tex, &m.vroughness_tex, loc);
         m.thickness = d.GetOneFloat("thickness", .01f); m.g = d.GetOneFloat("g", 0.f);
         m.max_depth = d.GetOneInt("maxdepth", 10); m.n_samples = d.GetOneInt("nsamples", 1);
         m.remap_roughness = d.GetOneBool("remaproughness", true);
@@ -172,9 +225,8 @@ static bpt_material MakeMaterial(const std::string &type, const ParameterDiction
     }
     if (type == "coateddiffuse") {
         m.type = BPT_MAT_COATED_DIFFUSE;
-        m.reflectance = GetSpectrum(d, "reflectance", st); m.eta = GetSpectrum(d, "eta", st); m.albedo = GetSpectrum(d, "albedo", st);
-        m.roughness = d.GetOneFloat("roughness", 0.f);
-        m.uroughness = d.GetOneFloat("uroughness", m.roughness); m.vroughness = d.GetOneFloat("vroughness", m.roughness);
+        m.reflectance = GetSpectrumOrTexture(d, "reflectance", st, tx, &m.reflectance_tex, loc); m.eta = GetSpectrum(d, "eta", st); m.albedo = GetSpectrum(d, "albedo", st);
+        GetRoughness(d, "", tx, &m.roughness, &m.uroughness, &m.vroughness, &m.uroughness_tex, &m.vroughness_tex, loc);
         m.thickness = d.GetOneFloat("thickness", .01f); m.g = d.GetOneFloat("g", 0.f);
         m.max_depth = d.GetOneInt("maxdepth", 10); m.n_samples = d.GetOneInt("nsamples", 1);
         m.remap_roughness = d.GetOneBool("remaproughness", true);
@@ -182,7 +234,8 @@ static bpt_material MakeMaterial(const std::string &type, const ParameterDiction
     }
     if (type == "diffusetransmission") {
         m.type = BPT_MAT_DIFFUSE_TRANSMISSION;
-        m.reflectance = GetSpectrum(d, "reflectance", st); m.transmittance = GetSpectrum(d, "transmittance", st);
+        m.reflectance = GetSpectrumOrTexture(d, "reflectance", st, tx, &m.reflectance_tex, loc);
+        m.transmittance = GetSpectrumOrTexture(d, "transmittance", st, tx, &m.transmittance_tex, loc);
         m.scale = d.GetOneFloat("scale", 1.f);
         return m;
     }
@@ -296,14 +349,79 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
         i.light_sampler = ls == "uniform" ? BPT_LIGHTSAMPLER_UNIFORM : ls == "power" ? BPT_LIGHTSAMPLER_POWER : ls == "exhaustive" ? BPT_LIGHTSAMPLER_EXHAUSTIVE : BPT_LIGHTSAMPLER_BVH;
         Check(api, e, api.bpt_scene_set_integrator(e, &i), "bpt_scene_set_integrator");
     }
+    // textures (FloatImageTexture::Create / SpectrumImageTexture::Create, textures.cpp:410-500), recorded at Texture; the image as
+    // Image::Read returns it (MIPMap::CreateFromFile, util/mipmap.cpp:349-381)
+    TexIds tx;
+    std::vector<bpt_texture> texs;
+    std::vector<std::unique_ptr<std::vector<uint8_t>>> texelStore;
+    for (const TextureRecord &tr : builder.textures) {
+        if (tr.texname != "imagemap") ErrorExit(&tr.loc, "texture class \"%s\" is not implemented by the engine (imagemap)", tr.texname);
+        const ParameterDictionary &d = tr.params;
+        if (d.GetOneString("mapping", "uv") != "uv") ErrorExit(&tr.loc, "only the \"uv\" texture mapping is implemented by the engine");
+        bpt_texture t; std::memset(&t, 0, sizeof(t));
+        t.su = d.GetOneFloat("uscale", 1.f); t.sv = d.GetOneFloat("vscale", 1.f); t.du = d.GetOneFloat("udelta", 0.f); t.dv = d.GetOneFloat("vdelta", 0.f);
+        t.max_anisotropy = d.GetOneFloat("maxanisotropy", 8.f);
+        pstd::optional<FilterFunction> ff = ParseFilter(d.GetOneString("filter", "bilinear"));
+        if (!ff) ErrorExit(&tr.loc, "filter function unknown");
+        t.filter = (int)*ff;
+        pstd::optional<WrapMode> wm = ParseWrapMode(d.GetOneString("wrap", "repeat").c_str());
+        if (!wm || *wm == WrapMode::OctahedralSphere) ErrorExit(&tr.loc, "wrap mode unknown");
+        t.wrap = (int)*wm;
+        t.scale = d.GetOneFloat("scale", 1.f); t.invert = d.GetOneBool("invert", false);
+        std::string filename = ResolveFilename(d.GetOneString("filename", ""));
+        std::string enc = d.GetOneString("encoding", HasExtension(filename, "png") ? "sRGB" : "linear");
+        if (enc != "sRGB" && enc != "linear") ErrorExit(&tr.loc, "texture encoding \"%s\" is not implemented by the engine", enc);
+        t.encoding = enc == "sRGB" ? BPT_ENCODING_SRGB : BPT_ENCODING_LINEAR;
+        ImageAndMetadata im = Image::Read(filename, Allocator(), ColorEncoding::Get(enc, Allocator()));
+        Image &image = im.image;
+        if (image.NChannels() != 1) {
+            ImageChannelDesc rgba = image.GetChannelDesc({"R", "G", "B", "A"}), rgb = image.GetChannelDesc({"R", "G", "B"});
+            if (rgba) image = image.SelectChannels(rgba);
+            else if (rgb) image = image.SelectChannels(rgb);
+            else ErrorExit(&tr.loc, "%s: image doesn't have R, G, and B channels", filename);
+        }
+        t.xres = image.Resolution().x; t.yres = image.Resolution().y; t.n_channels = image.NChannels();
+        const size_t count = (size_t)t.xres * t.yres * t.n_channels;
+        if (image.Format() == PixelFormat::U256) {
+            t.format = BPT_IMAGE_U8;
+            texelStore.emplace_back(new std::vector<uint8_t>((const uint8_t *)image.RawPointer({0, 0}), (const uint8_t *)image.RawPointer({0, 0}) + count));
+        } else if (image.Format() == PixelFormat::Float) {
+            t.format = BPT_IMAGE_F32;
+            texelStore.emplace_back(new std::vector<uint8_t>((const uint8_t *)image.RawPointer({0, 0}), (const uint8_t *)image.RawPointer({0, 0}) + count * sizeof(float)));
+        } else ErrorExit(&tr.loc, "%s: half-precision texture images are not implemented by the engine", filename);
+        t.pixels = texelStore.back()->data();
+        texs.push_back(t);
+        (tr.type == "float" ? tx.floats : tx.spectra)[tr.name] = (int)texs.size();
+    }
+    // normal maps (BasicScene::startLoadingNormalMaps, scene.cpp:886-910): the file read with the linear encoding, R G B selected
+    std::map<std::string, int> normalMapIds;
+    tx.normalMap = [&](const std::string &filename) -> int {
+        auto it = normalMapIds.find(filename);
+        if (it != normalMapIds.end()) return it->second;
+        ImageAndMetadata im = Image::Read(filename, Allocator(), ColorEncoding::Linear);
+        ImageChannelDesc rgb = im.image.GetChannelDesc({"R", "G", "B"});
+        if (!rgb) ErrorExit("%s: normal map image must contain R, G, and B channels", filename);
+        Image image = im.image.SelectChannels(rgb);
+        bpt_texture t; std::memset(&t, 0, sizeof(t));
+        t.kind = BPT_TEXTURE_NORMALMAP; t.encoding = BPT_ENCODING_LINEAR; t.wrap = BPT_TEXWRAP_REPEAT; t.filter = BPT_TEXFILTER_BILINEAR; t.scale = 1; t.su = t.sv = 1;
+        t.xres = image.Resolution().x; t.yres = image.Resolution().y; t.n_channels = 3;
+        const size_t count = (size_t)t.xres * t.yres * 3;
+        if (image.Format() == PixelFormat::U256) { t.format = BPT_IMAGE_U8; texelStore.emplace_back(new std::vector<uint8_t>((const uint8_t *)image.RawPointer({0, 0}), (const uint8_t *)image.RawPointer({0, 0}) + count)); }
+        else if (image.Format() == PixelFormat::Float) { t.format = BPT_IMAGE_F32; texelStore.emplace_back(new std::vector<uint8_t>((const uint8_t *)image.RawPointer({0, 0}), (const uint8_t *)image.RawPointer({0, 0}) + count * sizeof(float))); }
+        else ErrorExit("%s: half-precision images are not implemented by the engine", filename);
+        t.pixels = texelStore.back()->data();
+        texs.push_back(t);
+        return normalMapIds[filename] = (int)texs.size();
+    };
     // materials: the indexed ones (scene.materials) followed by the named ones (scene.namedMaterials)
     std::vector<bpt_material> mats;
     std::map<std::string, int> namedIndex;
-    for (const SceneEntity &me : scene.materials) mats.push_back(MakeMaterial(me.name.ToString(), me.parameters, st, &me.loc));
+    for (const SceneEntity &me : scene.materials) mats.push_back(MakeMaterial(me.name.ToString(), me.parameters, st, tx, &me.loc));
     for (const auto &nm : scene.namedMaterials) {
         namedIndex[nm.first] = (int)mats.size();
-        mats.push_back(MakeMaterial(nm.second.parameters.GetOneString("type", ""), nm.second.parameters, st, &nm.second.loc));
+        mats.push_back(MakeMaterial(nm.second.parameters.GetOneString("type", ""), nm.second.parameters, st, tx, &nm.second.loc));
     }
+    if (!texs.empty()) Check(api, e, api.bpt_scene_set_textures(e, texs.data(), (int)texs.size()), "bpt_scene_set_textures");
     Check(api, e, api.bpt_scene_set_materials(e, mats.data(), (int)mats.size()), "bpt_scene_set_materials");
     // area lights (lights.cpp DiffuseAreaLight::Create)
     std::vector<bpt_area_light> als;

@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             sys.stderr.write(out.decode())
             raise RuntimeError(f"nvcc failed on {s}")
-    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-ldl"]
+    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-ldl", "-lz"]
     subprocess.check_call(cmd)
     return OUT
 

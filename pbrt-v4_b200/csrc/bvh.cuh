@@ -129,17 +129,21 @@ BPT_D bool IntersectTrianglePre(const RayPre &r, float tMax, Pt3 p0, Pt3 p1, Pt3
 // through every triangle of an alpha mesh or hits them.  The reference then re-intersects the SAME shape from behind the hit
 // (`Intersect(rNext, ...)` on this primitive), which a planar triangle cannot satisfy: the triangle simply does not count.
 constexpr unsigned kClsAlpha = 0x40000000u;
-BPT_D bool AlphaRejects(const BVHView &bvh, const RayPre &r, unsigned cls, float meshIdBits) {
-    if (!(cls & kClsAlpha)) return false;
-    float a = __ldg(bvh.meshAlpha + __float_as_int(meshIdBits));
+// The hash is a real (outlined) function: scenes without alpha-tested meshes only pay the class-bit test in the traversal loops
+// (inlined, it cost the closest-hit kernel 4 % through registers, r02l vs r02k).
+static __device__ __noinline__ bool AlphaHashRejects(const float *meshAlpha, int mesh, float ox, float oy, float oz, float dx, float dy, float dz) {
+    float a = __ldg(meshAlpha + mesh);
     if (a >= 1) return false;
     float u = 1.f;
     if (a > 0) {
-        uint64_t w[3] = {(uint64_t)f2b(r.o.x) | ((uint64_t)f2b(r.o.y) << 32), (uint64_t)f2b(r.o.z) | ((uint64_t)f2b(r.d.x) << 32),
-                         (uint64_t)f2b(r.d.y) | ((uint64_t)f2b(r.d.z) << 32)};
+        uint64_t w[3] = {(uint64_t)f2b(ox) | ((uint64_t)f2b(oy) << 32), (uint64_t)f2b(oz) | ((uint64_t)f2b(dx) << 32), (uint64_t)f2b(dy) | ((uint64_t)f2b(dz) << 32)};
         u = (float)(uint32_t)MurmurHash64A(w, 24, 0) * 0x1p-32f;
     }
     return u > a;
+}
+BPT_D bool AlphaRejects(const BVHView &bvh, const RayPre &r, unsigned cls, float meshIdBits) {
+    if (!(cls & kClsAlpha)) return false;
+    return AlphaHashRejects(bvh.meshAlpha, __float_as_int(meshIdBits), r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
 }
 BPT_D unsigned ExtractByte(unsigned x, unsigned i) { return (x >> (i * 8)) & 0xff; }
 BPT_D unsigned SignExtendS8x4(unsigned x) {

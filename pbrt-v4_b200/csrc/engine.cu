@@ -871,7 +871,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         };
         if (!texId(om.m.reflectance_tex, &dm.reflectanceTex) || !texId(om.m.transmittance_tex, &dm.transmittanceTex) ||
             !texId(om.m.uroughness_tex, &dm.uroughnessTex) || !texId(om.m.vroughness_tex, &dm.vroughnessTex) ||
-            !texId(om.m.displacement_tex, &dm.displacementTex))
+            !texId(om.m.displacement_tex, &dm.displacementTex) || !texId(om.m.normal_map_tex, &dm.normalMapTex))
             return e->fail(BPT_ERR_INVALID, "material refers to a texture that was not set");
         const int mt = om.m.type;
         const bool reflOK = mt == BPT_MAT_DIFFUSE || mt == BPT_MAT_COATED_DIFFUSE || mt == BPT_MAT_DIFFUSE_TRANSMISSION || mt == BPT_MAT_CONDUCTOR ||
@@ -880,6 +880,11 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         if ((dm.reflectanceTex >= 0 && !reflOK) || (dm.transmittanceTex >= 0 && mt != BPT_MAT_DIFFUSE_TRANSMISSION) ||
             ((dm.uroughnessTex >= 0 || dm.vroughnessTex >= 0) && !roughOK) || (dm.displacementTex >= 0 && mt == BPT_MAT_INTERFACE))
             return e->fail(BPT_ERR_UNSUPPORTED, "texture on a material parameter that does not take one");
+        auto kindOf = [&](int t) { return t < 0 ? -1 : e->textures[t].t.kind; };
+        if (kindOf(dm.normalMapTex) == BPT_TEXTURE_IMAGEMAP || kindOf(dm.reflectanceTex) == BPT_TEXTURE_NORMALMAP || kindOf(dm.transmittanceTex) == BPT_TEXTURE_NORMALMAP ||
+            kindOf(dm.uroughnessTex) == BPT_TEXTURE_NORMALMAP || kindOf(dm.vroughnessTex) == BPT_TEXTURE_NORMALMAP || kindOf(dm.displacementTex) == BPT_TEXTURE_NORMALMAP ||
+            (dm.normalMapTex >= 0 && mt == BPT_MAT_INTERFACE))
+            return e->fail(BPT_ERR_INVALID, "normal-map images and imagemap textures are not interchangeable");
         if (dm.reflectanceTex >= 0 && (mt == BPT_MAT_CONDUCTOR || mt == BPT_MAT_COATED_CONDUCTOR)) dm.useReflectance = 1;
     }
 
@@ -1412,8 +1417,20 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         size_t nTexels = 0, nLevels = 0;
         for (size_t i = 0; i < e->textures.size(); ++i) {
             HostImage im = e->textures[i].img;
-            DropOpaqueAlpha(&im);
-            pyramids[i] = pyr.Generate(im, e->textures[i].t.wrap);
+            if (e->textures[i].t.kind == BPT_TEXTURE_NORMALMAP) {
+                // the image itself, RGB channels (BasicScene::startLoadingNormalMaps, scene.cpp:886-910), decoded as Image::GetChannel does
+                if (im.nc < 3) return e->fail(BPT_ERR_INVALID, "normal map image must contain R, G, and B channels");
+                HostMIPLevel lv; lv.xres = im.xres; lv.yres = im.yres; lv.texels.resize((size_t)im.xres * im.yres * 3);
+                for (size_t px = 0; px < (size_t)im.xres * im.yres; ++px)
+                    for (int c = 0; c < 3; ++c) lv.texels[3 * px + c] = im.is8 ? pyr.Decode(im, im.p8[px * im.nc + c]) : im.p32[px * im.nc + c];
+                im.nc = 3;
+                pyramids[i].push_back(std::move(lv));
+            } else {
+                if (e->textures[i].t.wrap == BPT_TEXWRAP_BLACK && ((im.xres & (im.xres - 1)) || (im.yres & (im.yres - 1))))
+                    return e->fail(BPT_ERR_UNSUPPORTED, "wrap mode \"black\" on an image whose sides are not powers of two (the reference aborts on it, util/image.cpp:114)");
+                DropOpaqueAlpha(&im);
+                pyramids[i] = pyr.Generate(im, e->textures[i].t.wrap);
+            }
             const bpt_texture &b = e->textures[i].t;
             DeviceTexture &d = dtex[i];
             d.firstLevel = (int)nLevels; d.nLevels = (int)pyramids[i].size(); d.nc = im.nc;

@@ -26,6 +26,7 @@
 #include <sstream>
 #include <string>
 #include <vector>
+#include <zlib.h>
 #include "../../include/b200pt.h"
 #include "xform.h"
 
@@ -127,6 +128,11 @@ struct Frontend {
     std::string cameraMediumName;
     int seedOption = 0;
     int sppOverride = 0;
+    // Texture "name" "float" | "spectrum" "imagemap": one bpt_texture per directive; material parameters of type "texture" refer to them
+    std::vector<bpt_texture> textures;
+    std::vector<std::unique_ptr<std::vector<unsigned char>>> texelStore;
+    std::map<std::string, int> floatTextures, spectrumTextures;   // name -> index + 1
+    std::map<std::string, int> normalMaps;                        // resolved file name -> index + 1
 
     bool fail(const Tokenizer &t, const std::string &m) { err = t.file + ":" + std::to_string(t.line) + ": " + m; return false; }
 
@@ -150,39 +156,207 @@ struct Frontend {
         return false;
     }
 
+    // "texture <name>" in place of a spectrum / float parameter: the id (index + 1) of the named texture, the constant left unset
+    bool getSpectrumOrTexture(ParamList &pl, const std::string &name, bpt_spectrum *out, int *tex) {
+        *tex = 0;
+        Param *q = pl.find(name);
+        if (q && q->type == "texture") {
+            std::memset(out, 0, sizeof(*out));
+            out->kind = BPT_SPEC_NONE;
+            if (q->strs.empty() || !spectrumTextures.count(q->strs[0])) { err = "parameter \"" + name + "\": unknown spectrum texture"; return false; }
+            *tex = spectrumTextures[q->strs[0]];
+            return true;
+        }
+        return getSpectrum(pl, name, out);
+    }
+    bool getFloatOrTexture(ParamList &pl, const std::string &name, float dflt, float *v, int *tex) {
+        *tex = 0; *v = dflt;
+        Param *q = pl.find(name);
+        if (!q) return true;
+        if (q->type == "texture") {
+            if (q->strs.empty() || !floatTextures.count(q->strs[0])) { err = "parameter \"" + name + "\": unknown float texture"; return false; }
+            *tex = floatTextures[q->strs[0]];
+            return true;
+        }
+        if (!q->nums.empty()) *v = (float)q->nums[0];
+        return true;
+    }
+    // "roughness" / "uroughness" / "vroughness" as ConductorMaterial::Create and friends resolve them (materials.cpp): the u / v
+    // parameter wins, otherwise both take "roughness" (constant or texture)
+    bool getRoughness(ParamList &pl, const std::string &prefix, float *rough, float *u, float *v, int *utex, int *vtex) {
+        int rt = 0, ut = 0, vt = 0;
+        float r = 0, uu = 0, vv = 0;
+        if (!getFloatOrTexture(pl, prefix + "roughness", 0.f, &r, &rt)) return false;
+        bool haveU = pl.find(prefix + "uroughness") != nullptr, haveV = pl.find(prefix + "vroughness") != nullptr;
+        if (!getFloatOrTexture(pl, prefix + "uroughness", r, &uu, &ut) || !getFloatOrTexture(pl, prefix + "vroughness", r, &vv, &vt)) return false;
+        *rough = r; *u = uu; *v = vv;
+        if (utex) { *utex = haveU ? ut : rt; *vtex = haveV ? vt : rt; }
+        else if (rt || ut || vt) { err = "parameter \"" + prefix + "roughness\": textures are not supported here"; return false; }
+        return true;
+    }
+    bool getDisplacement(ParamList &pl, bpt_material *m) {
+        // "string normalmap": the image is read with the linear encoding (BasicScene::startLoadingNormalMaps); one entry per file
+        std::string nm = pl.s("normalmap", "");
+        if (!nm.empty()) {
+            if (nm[0] != '/') nm = baseDir + "/" + nm;
+            if (!normalMaps.count(nm)) {
+                bpt_texture t; std::memset(&t, 0, sizeof(t));
+                t.kind = BPT_TEXTURE_NORMALMAP; t.encoding = BPT_ENCODING_LINEAR; t.wrap = BPT_TEXWRAP_REPEAT; t.filter = BPT_TEXFILTER_BILINEAR; t.scale = 1; t.su = t.sv = 1;
+                const bool png = nm.size() > 4 && (nm.substr(nm.size() - 4) == ".png" || nm.substr(nm.size() - 4) == ".PNG");
+                if (png ? !readPNG(nm, &t) : !readPFMTexture(nm, &t)) return false;
+                if (t.n_channels < 3) { err = nm + ": normal map image must contain R, G, and B channels"; return false; }
+                textures.push_back(t);
+                normalMaps[nm] = (int)textures.size();
+            }
+            m->normal_map_tex = normalMaps[nm];
+        }
+        Param *q = pl.find("displacement");
+        if (!q) return true;
+        if (q->type != "texture" || q->strs.empty() || !floatTextures.count(q->strs[0])) { err = "\"displacement\" must name a float texture"; return false; }
+        m->displacement_tex = floatTextures[q->strs[0]];
+        return true;
+    }
+
+    // ---- image files for textures: what Image::Read returns for .png (8-bit) and .pfm (util/image.cpp:1260-1365, ReadPFM)
+    static uint32_t be32(const unsigned char *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+    bool readPNG(const std::string &path, bpt_texture *t) {
+        std::ifstream in(path, std::ios::binary);
+        if (!in) { err = "cannot open " + path; return false; }
+        std::string buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+        const unsigned char *d = (const unsigned char *)buf.data();
+        static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+        if (buf.size() < 33 || std::memcmp(d, sig, 8) != 0) { err = path + ": not a PNG file"; return false; }
+        uint32_t w = 0, h = 0; int depth = 0, ctype = 0, interlace = 0;
+        std::string idat;
+        for (size_t pos = 8; pos + 12 <= buf.size();) {
+            uint32_t len = be32(d + pos);
+            if (pos + 12 + len > buf.size()) { err = path + ": truncated PNG"; return false; }
+            const unsigned char *ty = d + pos + 4, *body = d + pos + 8;
+            if (!std::memcmp(ty, "IHDR", 4)) { w = be32(body); h = be32(body + 4); depth = body[8]; ctype = body[9]; interlace = body[12]; }
+            else if (!std::memcmp(ty, "IDAT", 4)) idat.append((const char *)body, len);
+            else if (!std::memcmp(ty, "IEND", 4)) break;
+            pos += 12 + len;
+        }
+        if (depth != 8 || interlace != 0 || (ctype != 0 && ctype != 2 && ctype != 4 && ctype != 6)) {
+            err = path + ": only non-interlaced 8-bit grey / grey+alpha / RGB / RGBA PNG files are supported"; return false;
+        }
+        const int fileCh = ctype == 0 ? 1 : ctype == 4 ? 2 : ctype == 2 ? 3 : 4;
+        const size_t stride = (size_t)w * fileCh;
+        std::vector<unsigned char> raw((stride + 1) * h);
+        uLongf rawLen = (uLongf)raw.size();
+        if (uncompress(raw.data(), &rawLen, (const Bytef *)idat.data(), (uLong)idat.size()) != Z_OK || rawLen != raw.size()) { err = path + ": PNG data does not inflate"; return false; }
+        std::vector<unsigned char> img(stride * h);
+        for (uint32_t y = 0; y < h; ++y) {
+            const unsigned char *src = raw.data() + (stride + 1) * y;
+            unsigned char *dst = img.data() + stride * y;
+            const unsigned char *up = y ? dst - stride : nullptr;
+            const int ft = src[0];
+            for (size_t i = 0; i < stride; ++i) {
+                int a = i >= (size_t)fileCh ? dst[i - fileCh] : 0, b = up ? up[i] : 0, c = (up && i >= (size_t)fileCh) ? up[i - fileCh] : 0, x = src[1 + i], v;
+                switch (ft) {
+                case 0: v = x; break;
+                case 1: v = x + a; break;
+                case 2: v = x + b; break;
+                case 3: v = x + ((a + b) >> 1); break;
+                case 4: { int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c); v = x + ((pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c)); break; }
+                default: err = path + ": bad PNG filter type"; return false;
+                }
+                dst[i] = (unsigned char)v;
+            }
+        }
+        // grey+alpha is decoded as grey (the reference asks lodepng for LCT_GREY)
+        int nc = fileCh == 2 ? 1 : fileCh;
+        texelStore.emplace_back(new std::vector<unsigned char>((size_t)w * h * nc));
+        std::vector<unsigned char> &px = *texelStore.back();
+        if (fileCh == 2) for (size_t i = 0; i < (size_t)w * h; ++i) px[i] = img[2 * i];
+        else px = img;
+        t->format = BPT_IMAGE_U8; t->xres = (int)w; t->yres = (int)h; t->n_channels = nc; t->pixels = px.data();
+        return true;
+    }
+    bool readPFMTexture(const std::string &path, bpt_texture *t) {
+        FILE *f = std::fopen(path.c_str(), "rb");
+        if (!f) { err = "cannot open " + path; return false; }
+        char hdr[3]; int w, h; float sc;
+        if (std::fscanf(f, "%2s %d %d %f", hdr, &w, &h, &sc) != 4 || (std::strcmp(hdr, "PF") != 0 && std::strcmp(hdr, "Pf") != 0)) { std::fclose(f); err = path + ": PFM header expected"; return false; }
+        std::fgetc(f);
+        if (sc > 0) { std::fclose(f); err = path + ": big-endian PFM not supported"; return false; }
+        const int nc = std::strcmp(hdr, "PF") == 0 ? 3 : 1;
+        texelStore.emplace_back(new std::vector<unsigned char>((size_t)w * h * nc * sizeof(float)));
+        float *px = (float *)texelStore.back()->data();
+        std::vector<float> row((size_t)w * nc);
+        for (int y = h - 1; y >= 0; --y) {   // bottom-to-top rows, scaled by |scale| (ReadPFM)
+            if (std::fread(row.data(), 4, row.size(), f) != row.size()) { std::fclose(f); err = path + ": truncated"; return false; }
+            for (size_t k = 0; k < row.size(); ++k) px[(size_t)y * w * nc + k] = row[k] * std::abs(sc);
+        }
+        std::fclose(f);
+        t->format = BPT_IMAGE_F32; t->xres = w; t->yres = h; t->n_channels = nc; t->pixels = px;
+        return true;
+    }
+    // FloatImageTexture::Create / SpectrumImageTexture::Create (textures.cpp:410-500) with TextureMapping2D "uv"
+    bool makeTexture(const std::vector<std::string> &a, ParamList &pl) {
+        if (a.size() < 3) { err = "Texture \"name\" \"float|spectrum\" \"imagemap\" expected"; return false; }
+        if (a[1] != "float" && a[1] != "spectrum") { err = "texture value type must be float or spectrum"; return false; }
+        if (a[2] != "imagemap") { err = "texture class \"" + a[2] + "\" is not supported by this front end (imagemap)"; return false; }
+        if (pl.s("mapping", "uv") != "uv") { err = "only the \"uv\" texture mapping is supported"; return false; }
+        bpt_texture t; std::memset(&t, 0, sizeof(t));
+        t.su = pl.f("uscale", 1.f); t.sv = pl.f("vscale", 1.f); t.du = pl.f("udelta", 0.f); t.dv = pl.f("vdelta", 0.f);
+        t.max_anisotropy = pl.f("maxanisotropy", 8.f);
+        std::string filter = pl.s("filter", "bilinear");
+        if (filter == "ewa" || filter == "EWA") t.filter = BPT_TEXFILTER_EWA;
+        else if (filter == "trilinear") t.filter = BPT_TEXFILTER_TRILINEAR;
+        else if (filter == "bilinear") t.filter = BPT_TEXFILTER_BILINEAR;
+        else if (filter == "point") t.filter = BPT_TEXFILTER_POINT;
+        else { err = filter + ": filter function unknown"; return false; }
+        std::string wrap = pl.s("wrap", "repeat");
+        if (wrap == "clamp") t.wrap = BPT_TEXWRAP_CLAMP; else if (wrap == "repeat") t.wrap = BPT_TEXWRAP_REPEAT; else if (wrap == "black") t.wrap = BPT_TEXWRAP_BLACK;
+        else { err = wrap + ": wrap mode unknown"; return false; }
+        t.scale = pl.f("scale", 1.f); t.invert = pl.b("invert", false);
+        std::string fn = pl.s("filename", "");
+        if (fn.empty()) { err = "imagemap texture without a filename"; return false; }
+        if (fn[0] != '/') fn = baseDir + "/" + fn;
+        auto hasExt = [&](const char *e) { size_t n = std::strlen(e); if (fn.size() < n) return false; for (size_t i = 0; i < n; ++i) if (std::tolower((unsigned char)fn[fn.size() - n + i]) != e[i]) return false; return true; };
+        const bool png = hasExt(".png");
+        std::string enc = pl.s("encoding", png ? "sRGB" : "linear");
+        if (enc == "sRGB") t.encoding = BPT_ENCODING_SRGB; else if (enc == "linear") t.encoding = BPT_ENCODING_LINEAR;
+        else { err = "texture encoding \"" + enc + "\" is not supported (sRGB, linear)"; return false; }
+        if (png) { if (!readPNG(fn, &t)) return false; }
+        else if (hasExt(".pfm")) { if (!readPFMTexture(fn, &t)) return false; }
+        else { err = fn + ": texture images are read from .png (8-bit) and .pfm files"; return false; }
+        textures.push_back(t);
+        (a[1] == "float" ? floatTextures : spectrumTextures)[a[0]] = (int)textures.size();
+        return true;
+    }
+
     bool makeMaterial(const std::string &type, ParamList &pl, bpt_material *m) {
         std::memset(m, 0, sizeof(*m));
         m->uroughness = m->vroughness = m->iface_uroughness = m->iface_vroughness = -1;
+        if (!getDisplacement(pl, m)) return false;
         if (type == "diffuse") {
             m->type = BPT_MAT_DIFFUSE;
-            return getSpectrum(pl, "reflectance", &m->reflectance);
+            return getSpectrumOrTexture(pl, "reflectance", &m->reflectance, &m->reflectance_tex);
         }
         if (type == "interface" || type == "none" || type == "") { m->type = BPT_MAT_INTERFACE; return true; }
         if (type == "conductor") {
             m->type = BPT_MAT_CONDUCTOR;
-            if (!getSpectrum(pl, "eta", &m->eta) || !getSpectrum(pl, "k", &m->k) || !getSpectrum(pl, "reflectance", &m->reflectance)) return false;
-            m->roughness = pl.f("roughness", 0.f);
-            m->uroughness = pl.f("uroughness", m->roughness); m->vroughness = pl.f("vroughness", m->roughness);
+            if (!getSpectrum(pl, "eta", &m->eta) || !getSpectrum(pl, "k", &m->k) || !getSpectrumOrTexture(pl, "reflectance", &m->reflectance, &m->reflectance_tex)) return false;
+            if (!getRoughness(pl, "", &m->roughness, &m->uroughness, &m->vroughness, &m->uroughness_tex, &m->vroughness_tex)) return false;
             m->remap_roughness = pl.b("remaproughness", true);
             return true;
         }
         if (type == "dielectric") {
             m->type = BPT_MAT_DIELECTRIC;
             if (!getSpectrum(pl, "eta", &m->eta)) return false;
-            m->roughness = pl.f("roughness", 0.f);
-            m->uroughness = pl.f("uroughness", m->roughness); m->vroughness = pl.f("vroughness", m->roughness);
+            if (!getRoughness(pl, "", &m->roughness, &m->uroughness, &m->vroughness, &m->uroughness_tex, &m->vroughness_tex)) return false;
             m->remap_roughness = pl.b("remaproughness", true);
             return true;
         }
         if (type == "coatedconductor") {
             m->type = BPT_MAT_COATED_CONDUCTOR;
             if (!getSpectrum(pl, "interface.eta", &m->iface_eta) || !getSpectrum(pl, "conductor.eta", &m->conductor_eta) ||
-                !getSpectrum(pl, "conductor.k", &m->conductor_k) || !getSpectrum(pl, "reflectance", &m->reflectance) ||
+                !getSpectrum(pl, "conductor.k", &m->conductor_k) || !getSpectrumOrTexture(pl, "reflectance", &m->reflectance, &m->reflectance_tex) ||
                 !getSpectrum(pl, "albedo", &m->albedo)) return false;
-            m->iface_roughness = pl.f("interface.roughness", 0.f);
-            m->iface_uroughness = pl.f("interface.uroughness", m->iface_roughness); m->iface_vroughness = pl.f("interface.vroughness", m->iface_roughness);
-            m->roughness = pl.f("conductor.roughness", 0.f);
-            m->uroughness = pl.f("conductor.uroughness", m->roughness); m->vroughness = pl.f("conductor.vroughness", m->roughness);
+            if (!getRoughness(pl, "interface.", &m->iface_roughness, &m->iface_uroughness, &m->iface_vroughness, nullptr, nullptr)) return false;
+            if (!getRoughness(pl, "conductor.", &m->roughness, &m->uroughness, &m->vroughness, &m->uroughness_tex, &m->vroughness_tex)) return false;
             m->thickness = pl.f("thickness", .01f);
             m->g = pl.f("g", 0.f);
             m->max_depth = pl.i("maxdepth", 10); m->n_samples = pl.i("nsamples", 1);
@@ -191,9 +365,8 @@ struct Frontend {
         }
         if (type == "coateddiffuse") {
             m->type = BPT_MAT_COATED_DIFFUSE;
-            if (!getSpectrum(pl, "reflectance", &m->reflectance) || !getSpectrum(pl, "eta", &m->eta) || !getSpectrum(pl, "albedo", &m->albedo)) return false;
-            m->roughness = pl.f("roughness", 0.f);
-            m->uroughness = pl.f("uroughness", m->roughness); m->vroughness = pl.f("vroughness", m->roughness);
+            if (!getSpectrumOrTexture(pl, "reflectance", &m->reflectance, &m->reflectance_tex) || !getSpectrum(pl, "eta", &m->eta) || !getSpectrum(pl, "albedo", &m->albedo)) return false;
+            if (!getRoughness(pl, "", &m->roughness, &m->uroughness, &m->vroughness, &m->uroughness_tex, &m->vroughness_tex)) return false;
             m->thickness = pl.f("thickness", .01f); m->g = pl.f("g", 0.f);
             m->max_depth = pl.i("maxdepth", 10); m->n_samples = pl.i("nsamples", 1);
             m->remap_roughness = pl.b("remaproughness", true);
@@ -201,7 +374,8 @@ struct Frontend {
         }
         if (type == "diffusetransmission") {
             m->type = BPT_MAT_DIFFUSE_TRANSMISSION;
-            if (!getSpectrum(pl, "reflectance", &m->reflectance) || !getSpectrum(pl, "transmittance", &m->transmittance)) return false;
+            if (!getSpectrumOrTexture(pl, "reflectance", &m->reflectance, &m->reflectance_tex) ||
+                !getSpectrumOrTexture(pl, "transmittance", &m->transmittance, &m->transmittance_tex)) return false;
             m->scale = pl.f("scale", 1.f);
             return true;
         }
@@ -591,6 +765,7 @@ bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::st
         haveInteg = true; return true;
     }
     if (d == "WorldBegin") { inWorld = true; gs.ctm = Xform(); namedCS["world"] = gs.ctm; return true; }
+    if (d == "Texture") return makeTexture(a, pl);
     if (d == "Material") {
         bpt_material m;
         if (!makeMaterial(a.empty() ? "diffuse" : a[0], pl, &m)) return false;
@@ -729,6 +904,7 @@ bool Frontend::finish() {
     }
     else if (sppOverride > 0 || seedOption) { bpt_sampler s{BPT_SAMPLER_ZSOBOL, sppOverride > 0 ? sppOverride : 16, seedOption, BPT_RANDOMIZE_FAST_OWEN, 0, 0, 0}; if (!ck(bpt_scene_set_sampler(e, &s))) return false; }
     if (haveInteg && !ck(bpt_scene_set_integrator(e, &integ))) return false;
+    if (!textures.empty() && !ck(bpt_scene_set_textures(e, textures.data(), (int)textures.size()))) return false;
     if (!ck(bpt_scene_set_materials(e, materials.data(), (int)materials.size()))) return false;
     if (!ck(bpt_scene_set_area_lights(e, areaLights.data(), (int)areaLights.size()))) return false;
     for (auto &m : media) if (!ck(bpt_scene_add_medium(e, &m))) return false;

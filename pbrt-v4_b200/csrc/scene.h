@@ -92,6 +92,7 @@ struct DeviceMaterial {
     float scale;               // diffusetransmission "scale"
     // image textures in place of the constants above (-1: the constant) and the "displacement" float texture of bump mapping
     int reflectanceTex, transmittanceTex, uroughnessTex, vroughnessTex, displacementTex;
+    int normalMapTex;          // "normalmap" image (one level, RGB, linear)
 };
 
 struct DeviceMesh {

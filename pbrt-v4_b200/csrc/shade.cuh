@@ -180,7 +180,24 @@ __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int
             uvd = ComputeDifferentials(rc.camera, isect, ex, rdiffs);
             tc.p = isect.p(); tc.dpdx = uvd.dpdx; tc.dpdy = uvd.dpdy; tc.n = isect.n; tc.uv = isect.uv;
             tc.dudx = uvd.dudx; tc.dudy = uvd.dudy; tc.dvdx = uvd.dvdx; tc.dvdy = uvd.dvdy;
-            if (mat.displacementTex >= 0) {
+            if (mat.normalMapTex >= 0) {
+                // NormalMap (materials.h:86-105): tangent-space normal from the image (bilinear, repeat), then dpdu / dpdv that give it
+                const DeviceTexture &nm = rc.sv.textures[mat.normalMapTex];
+                const DeviceMIPLevel &lv = rc.sv.mipLevels[nm.firstLevel];
+                Vec2 uvn(tc.uv.x, 1 - tc.uv.y);
+                Vec3 nsl(2 * MipBilerpChannel(lv, 3, uvn, 0, TEXWRAP_REPEAT) - 1, 2 * MipBilerpChannel(lv, 3, uvn, 1, TEXWRAP_REPEAT) - 1,
+                         2 * MipBilerpChannel(lv, 3, uvn, 2, TEXWRAP_REPEAT) - 1);
+                nsl = Normalize(nsl);
+                Frame frame = Frame::FromXZ(Normalize(isect.dpdus), V(isect.ns));
+                nsl = frame.FromLocal(nsl);
+                float ulen = Length(isect.dpdus), vlen = Length(ex.dpdvs);
+                Vec3 dpdu = Normalize(GramSchmidt(isect.dpdus, nsl)) * ulen;
+                Vec3 dpdv = Normalize(Cross(nsl, dpdu)) * vlen;
+                Nrm3 ns(Normalize(Cross(dpdu, dpdv)));
+                isect.ns = FaceForward(ns, isect.n);
+                while (LengthSquared(dpdu) > 1e16f || LengthSquared(dpdv) > 1e16f) { dpdu = dpdu / 1e8f; dpdv = dpdv / 1e8f; }
+                isect.dpdus = dpdu; ex.dpdvs = dpdv;
+            } else if (mat.displacementTex >= 0) {
                 // BumpMap (materials.h:107-138) + SetShadingGeometry(ns, dpdu, dpdv, shading.dndu, shading.dndv, false)
                 const DeviceTexture &disp = rc.sv.textures[mat.displacementTex];
                 TexEvalCtx shifted = tc;

@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(128, BPT_MEDIUM_CTAS) k_sample_medium(RenderCt
                         // real scattering: SampleLd + phase sampling run in k_medium_scatter (MediumScatterQueue)
                         st4(&ps.beta[slot], beta); st4(&ps.r_u[slot], r_u);
                         StoreCtx(ps, slot, Pt3i(p), Nrm3(0, 0, 0), Nrm3(0, 0, 0));
-                        ps.misc[slot] = make_uint4(misc.x, misc.y, (unsigned)dimension, (unsigned)depth | (misc.w & 0x300u));
+                        ps.misc[slot] = make_uint4(misc.x, misc.y, (unsigned)dimension, (unsigned)depth | (misc.w & 0xf00u));
                         int q = WarpAggPush(&rc.counts[Q_MSCATTER]);
                         rc.queues[Q_MSCATTER][q] = slot;
                     }
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(128, BPT_MEDIUM_CTAS) k_sample_medium(RenderCt
             r_u *= T_maj / T_maj[0];
             r_l *= T_maj / T_maj[0];
             st4(&ps.beta[slot], beta); st4(&ps.r_u[slot], r_u); st4(&ps.r_l[slot], r_l);
-            ps.misc[slot] = make_uint4(misc.x, misc.y, (unsigned)dimension, (unsigned)depth | (misc.w & 0x300u));
+            ps.misc[slot] = make_uint4(misc.x, misc.y, (unsigned)dimension, (unsigned)depth | (misc.w & 0xf00u));
             // surviving unscattered ray: hand over to the surface queues (what the closest-hit commit does for vacuum rays)
             int tri = __float_as_int(ps.hit[slot].x);
             if (tri < 0) {

@@ -98,6 +98,99 @@ def cornell_lights(outdir, lights="all", area=True, res=(64, 64), spp=16, maxdep
     return path
 
 
+def write_png(path, img):
+    """8-bit PNG (grey HxW, grey+alpha HxWx2, RGB HxWx3 or RGBA HxWx4), filter type 0 rows, zlib level 6."""
+    import struct, zlib
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    if img.ndim == 2:
+        img = img[..., None]
+    h, w, c = img.shape
+    ctype = {1: 0, 2: 4, 3: 2, 4: 6}[c]
+    raw = b"".join(b"\0" + img[y].tobytes() for y in range(h))
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+
+
+def write_pfm(path, img):
+    """PFM ("Pf" one channel HxW, "PF" RGB HxWx3), little-endian, bottom row first."""
+    img = np.ascontiguousarray(img, dtype="<f4")
+    h, w = img.shape[:2]
+    with open(path, "wb") as f:
+        f.write(("%s\n%d %d\n-1.0\n" % ("Pf" if img.ndim == 2 else "PF", w, h)).encode())
+        f.write(img[::-1].tobytes())
+
+
+def texture_images(outdir, seed=5):
+    """The images of the textured test scenes: an RGB PNG whose sides are not powers of two (the pyramid is built from a resized
+    copy), a grey PNG, an RGBA PNG with an opaque alpha channel, a one-channel float PFM height map and an RGB float PFM."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    os.makedirs(outdir, exist_ok=True)
+    y, x = np.mgrid[0:37, 0:53]
+    checker = (((x // 6) + (y // 5)) % 2).astype(np.float64)
+    rgb = np.stack([0.15 + 0.7 * checker, 0.25 + 0.5 * np.sin(x / 5.0) ** 2, 0.2 + 0.6 * (y / 36.0)], -1) + 0.08 * rng.random((37, 53, 3))
+    write_png(os.path.join(outdir, "albedo.png"), np.clip(rgb * 255, 0, 255))
+    g = 0.5 + 0.5 * np.sin(np.mgrid[0:32, 0:32][1] / 3.0) * np.cos(np.mgrid[0:32, 0:32][0] / 4.0)
+    write_png(os.path.join(outdir, "grey.png"), np.clip(g * 255, 0, 255))
+    rgba = np.concatenate([np.clip(rng.random((16, 16, 3)) * 255, 0, 255), np.full((16, 16, 1), 255.0)], -1)
+    write_png(os.path.join(outdir, "rgba.png"), rgba)
+    yy, xx = np.mgrid[0:64, 0:64] / 64.0
+    height = 0.03 * (np.sin(14 * xx) * np.sin(11 * yy) + 0.3 * rng.random((64, 64)))
+    write_pfm(os.path.join(outdir, "height.pfm"), height)
+    write_pfm(os.path.join(outdir, "colour.pfm"), 0.1 + 0.8 * rng.random((24, 40, 3)))
+    ny, nx = np.mgrid[0:20, 0:28]
+    nrm = np.stack([0.35 * np.sin(nx / 2.5), 0.35 * np.cos(ny / 2.0), np.ones((20, 28))], -1)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    write_png(os.path.join(outdir, "normals.png"), np.clip((0.5 + 0.5 * nrm) * 255, 0, 255))
+
+
+TEXTURE_SETS = {
+    # what changes on the Cornell box: (Texture directives, the floor / back-wall material, extra geometry)
+    "albedo": ('Texture "alb" "spectrum" "imagemap" "string filename" "albedo.png"\n', 'Material "diffuse" "texture reflectance" "alb"\n'),
+    "trilinear": ('Texture "alb" "spectrum" "imagemap" "string filename" "albedo.png" "string filter" "trilinear" "float uscale" 3 "float vscale" 2 "float udelta" 0.25\n',
+                  'Material "diffuse" "texture reflectance" "alb"\n'),
+    "ewa": ('Texture "alb" "spectrum" "imagemap" "string filename" "colour.pfm" "string filter" "ewa" "float uscale" 4 "float vscale" 4 "string wrap" "clamp" "float scale" 0.9\n',
+            'Material "diffuse" "texture reflectance" "alb"\n'),
+    "point": ('Texture "alb" "spectrum" "imagemap" "string filename" "rgba.png" "string filter" "point" "float uscale" 2 "float vscale" 2 "bool invert" true "string encoding" "linear"\n',
+              'Material "coateddiffuse" "texture reflectance" "alb" "float roughness" 0.2\n'),
+    "grey": ('Texture "alb" "spectrum" "imagemap" "string filename" "grey.png" "string wrap" "black" "float uscale" 1.5 "float vscale" 1.5\n',
+             'Material "diffusetransmission" "texture reflectance" "alb" "texture transmittance" "alb" "float scale" 0.8\n'),
+    "roughness": ('Texture "rough" "float" "imagemap" "string filename" "grey.png" "float scale" 0.4\nTexture "tint" "spectrum" "imagemap" "string filename" "colour.pfm"\n',
+                  'Material "conductor" "texture roughness" "rough" "texture reflectance" "tint"\n'),
+    "bump": ('Texture "h" "float" "imagemap" "string filename" "height.pfm" "float uscale" 2 "float vscale" 2\nTexture "alb" "spectrum" "imagemap" "string filename" "albedo.png"\n',
+             'Material "diffuse" "texture reflectance" "alb" "texture displacement" "h"\n'),
+    "normalmap": ('Texture "alb" "spectrum" "imagemap" "string filename" "albedo.png"\n', 'Material "diffuse" "texture reflectance" "alb" "string normalmap" "normals.png"\n'),
+    "bump_dielectric": ('Texture "h" "float" "imagemap" "string filename" "height.pfm" "float uscale" 3 "float vscale" 3 "string filter" "trilinear"\n',
+                        'Material "dielectric" "float eta" 1.5 "float roughness" 0.15 "texture displacement" "h"\n'),
+}
+
+
+def cornell_textured(outdir, which="albedo", res=(64, 64), spp=16, maxdepth=5, mirror=True):
+    """Cornell box whose floor and back wall carry TEXTURE_SETS[which] (the meshes get uv coordinates and, for the back wall, vertex
+    normals, so that dndu / dndv are not zero), seen directly and -- with mirror -- through a smooth conductor panel and a glass
+    slab, which is where the specular ray differentials of SurfaceInteraction::SpawnRay end up in a texture lookup."""
+    path = cornell(outdir, res=res, spp=spp, maxdepth=maxdepth)
+    texture_images(outdir)
+    s = open(path).read()
+    texdef, mat = TEXTURE_SETS[which]
+    a = s.index("WorldBegin\n") + len("WorldBegin\n")
+    s = s[:a] + texdef + s[a:]
+    floor = 'Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point3 P" [-1 0 -1  -1 0 1  1 0 1  1 0 -1]\n'
+    back = 'Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point3 P" [-1 0 -1  1 0 -1  1 2 -1  -1 2 -1]\n'
+    assert floor in s and back in s
+    s = s.replace(floor, "AttributeBegin\n" + mat + floor[:-1] + ' "point2 uv" [0 0  0 1  1 1  1 0]\nAttributeEnd\n')
+    s = s.replace(back, "AttributeBegin\n" + mat + back[:-1] + ' "point2 uv" [0 0  1 0  1 1  0 1] "normal N" [-0.2 0.1 1  0.2 0.1 1  0.2 -0.1 1  -0.2 -0.1 1]\nAttributeEnd\n')
+    if mirror:
+        s += ('Material "conductor" "float roughness" 0\n'
+              'Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point3 P" [-0.95 0.2 -0.6  -0.95 0.2 0.5  -0.6 1.4 0.5  -0.6 1.4 -0.6]\n'
+              'Material "dielectric" "float eta" 1.45\n'
+              'Shape "trianglemesh" "integer indices" [0 1 2 0 2 3  4 6 5 4 7 6  0 4 5 0 5 1  1 5 6 1 6 2  2 6 7 2 7 3  3 7 4 3 4 0]\n'
+              '  "point3 P" [0.2 0.02 0.1  0.8 0.02 0.1  0.8 0.02 0.7  0.2 0.02 0.7   0.2 0.5 0.1  0.8 0.5 0.1  0.8 0.5 0.7  0.2 0.5 0.7]\n')
+    open(path, "w").write(s)
+    return path
+
+
 def heightfield_mesh(n, seed=1234, amp=0.05, noise=0.01):
     g = np.linspace(-1.0, 1.0, n, dtype=np.float64)
     X, Z = np.meshgrid(g, g, indexing="xy")

@@ -22,7 +22,7 @@ pytestmark = pytest.mark.skipif(not os.path.exists(BINDING), reason="oracle/_ref
 def recorder(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("abi_record") / "libabi_record.so")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-I/usr/local/cuda/include",
-                           os.path.join(ROOT, "tests", "tools", "abi_record.cpp"), os.path.join(ROOT, "pbrt-v4_b200", "csrc", "pbrt_frontend.cpp"), "-o", so])
+                           os.path.join(ROOT, "tests", "tools", "abi_record.cpp"), os.path.join(ROOT, "pbrt-v4_b200", "csrc", "pbrt_frontend.cpp"), "-o", so, "-lz"])
     lib = C.CDLL(so)
     lib.bpt_create.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
     lib.bpt_load_pbrt_ex.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
@@ -69,6 +69,8 @@ def _scenes():
     for k, smp in enumerate(['"paddedsobol" "integer pixelsamples" 8', '"paddedsobol" "integer pixelsamples" 4 "string randomization" "owen"',
                              '"stratified" "integer xsamples" 3 "integer ysamples" 2', '"stratified" "bool jitter" false', '"independent" "integer pixelsamples" 5']):
         cases["sampler_%d" % k] = (lambda d, smp=smp: with_sampler(d, smp))
+    for ts in sorted(scenes.TEXTURE_SETS):    # image textures: PNG / PFM readers, filter / wrap / scale / invert / uv mapping, material parameters
+        cases["textures_" + ts] = (lambda d, ts=ts: scenes.cornell_textured(d, ts, res=(32, 32), spp=1))
     for ls in sorted(scenes.LIGHT_SETS):   # point / spot / distant lights: parameters, defaults, transforms, power / illuminance
         cases["lights_" + ls] = (lambda d, ls=ls: scenes.cornell_lights(d, ls, area=(ls == "all"), res=(32, 32), spp=1))
     for parts in ("t", "s", "r", "ts", "tr", "rs", "trs"):   # every combination of translate / rotate / scale in the instance transform
@@ -97,7 +99,7 @@ def test_front_end_and_reference_parser_binding_issue_identical_abi_calls(record
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["cornell", "mixed_envmap", "instanced_coated", "smoke_grid", "gbuffer_world", "lights_all"])
+@pytest.mark.parametrize("name", ["cornell", "mixed_envmap", "instanced_coated", "smoke_grid", "gbuffer_world", "lights_all", "textures_bump"])
 def test_binding_and_front_end_render_identical_images(tmp_path, name):
     from pbrt_v4_b200 import engine as E, imageio
     path = _scenes()[name](str(tmp_path))

@@ -417,6 +417,46 @@ def test_delta_lights_through_media_match_the_live_reference(E, tmp_path):
     assert (bits(img) == bits(ref)).all(), (int((bits(img) != bits(ref)).any(axis=-1).sum()), float(np.abs(img - ref).max()))
 
 
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/bin/pbrt not on this box")
+@pytest.mark.parametrize("which", ["albedo", "trilinear", "ewa", "point", "grey", "roughness", "bump", "bump_dielectric", "normalmap"])
+def test_image_textures_and_bump_mapping_match_the_live_reference(E, tmp_path, which):
+    """f1: Texture "imagemap" (float and spectrum; PNG 8-bit sRGB / linear, PFM float; point / bilinear / trilinear / EWA; repeat /
+    clamp / black; scale, invert, uv scale and offset) on reflectance, transmittance and roughness parameters, and bump mapping
+    through "displacement" -- with the screen-space differentials they are filtered with: camera ray differentials at the first hit,
+    SpawnRay's specular differentials behind the mirror and the glass slab, Camera::Approximate_dp_dxy after any diffuse bounce
+    (textures.cpp:359-387, util/mipmap.cpp:228-347, interaction.cpp:41-150, materials.h:107-138).  Bit-identical renders."""
+    from pbrt_v4_b200 import scenes, imageio
+    path = scenes.cornell_textured(str(tmp_path), which, res=(48, 48), spp=16)
+    subprocess.check_call([REF_EXE, "--quiet", "--seed", "0", "--outfile", str(tmp_path / "ref.pfm"), path])
+    ref = imageio.read_pfm(str(tmp_path / "ref.pfm"))
+    img = _render(E, path, 16)
+    assert (bits(img) == bits(ref)).all(), (which, int((bits(img) != bits(ref)).any(axis=-1).sum()), float(np.abs(img - ref).max()))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/bin/pbrt not on this box")
+def test_textured_gbuffer_and_media_match_the_live_reference(E, tmp_path):
+    """Textures with the other users of the ray differentials: GBufferFilm (albedo of a textured, bump-mapped surface; Ns after bump
+    mapping) and a camera ray that crosses interface surfaces of a medium before it reaches the textured floor (SkipIntersection)."""
+    from pbrt_v4_b200 import scenes, imageio
+    path = scenes.as_gbuffer(scenes.cornell_textured(str(tmp_path / "g"), "bump", res=(32, 32), spp=4), "world")
+    subprocess.check_call([REF_EXE, "--quiet", "--seed", "0", "--outfile", str(tmp_path / "ref.exr"), path])
+    names, ref = imageio.read_raw_channels(str(tmp_path / "ref.exr"))
+    e = E.Engine(0); e.load_pbrt(path, seed=0); e.render(0, 4); g = e.gbuffer(); e.close()
+    for c, nm in enumerate(names):
+        assert (bits(g[..., c]) == bits(ref[..., c])).all(), nm
+    path = scenes.smoke(str(tmp_path / "s"), grid=8, res=(48, 48), spp=8)
+    scenes.texture_images(str(tmp_path / "s"))
+    txt = open(path).read().replace("WorldBegin\n", 'WorldBegin\nTexture "alb" "spectrum" "imagemap" "string filename" "albedo.png" "string filter" "trilinear" "float uscale" 6 "float vscale" 6\n', 1)
+    old = 'Material "diffuse" "rgb reflectance" [0.6 0.6 0.6]\nShape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point3 P" [-3 0 -3  -3 0 3  3 0 3  3 0 -3]\n'
+    assert old in txt
+    txt = txt.replace(old, 'Material "diffuse" "texture reflectance" "alb"\nShape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point3 P" [-3 0 -3  -3 0 3  3 0 3  3 0 -3] "point2 uv" [0 0  0 1  1 1  1 0]\n')
+    open(path, "w").write(txt)
+    subprocess.check_call([REF_EXE, "--quiet", "--seed", "0", "--outfile", str(tmp_path / "ref.pfm"), path])
+    ref = imageio.read_pfm(str(tmp_path / "ref.pfm"))
+    img = _render(E, path, 8)
+    assert (bits(img) == bits(ref)).all(), (int((bits(img) != bits(ref)).any(axis=-1).sum()), float(np.abs(img - ref).max()))
+
+
 def test_film_write_exr_carries_the_resolved_channels(E, tmp_path):
     """bpt_film_write_exr: the 25 GBuffer channels (and R G B for Film "rgb") in the file == bpt_film_resolve[_gbuffer]."""
     from pbrt_v4_b200 import scenes, imageio

@@ -29,6 +29,7 @@ struct Mesh { bpt_mesh m; std::vector<float> P, N, UV; std::vector<int> idx; };
 struct Light { bpt_light l; std::vector<float> img; Spec L; };
 struct Medium { bpt_medium m; std::vector<float> density, leScale; Spec sa, ss, Le; };
 struct Material { bpt_material m; Spec sp[8]; };
+struct Texture { bpt_texture t; uint64_t hash; };
 struct AreaLight { bpt_area_light a; Spec L; };
 }  // namespace
 
@@ -36,7 +37,8 @@ struct bpt_engine {
     std::string err;
     bpt_camera cam{}; bpt_film film{}; bpt_filter filter{}; bpt_sampler sampler{}; bpt_integrator integ{};
     bool haveCam = false, haveFilm = false, haveFilter = false, haveSampler = false, haveInteg = false;
-    std::vector<Material> materials; std::vector<AreaLight> areaLights; std::vector<Mesh> meshes;
+    std::vector<Material> materials;
+    std::vector<Texture> textures; std::vector<AreaLight> areaLights; std::vector<Mesh> meshes;
     std::vector<bpt_instance> instances; std::vector<Light> lights; std::vector<Medium> media;
     int cameraMedium = -1, space = BPT_SPACE_WORLD;
 };
@@ -68,7 +70,30 @@ static std::string S(const Spec &sp) {
     }
     return "?";
 }
-static std::string Mat(const Material &mt) {
+static std::string Tex(const std::vector<Texture> &tx, const char *what, int id) {
+    if (id == 0) return "";
+    if (id < 0 || id > (int)tx.size()) return std::string(" ") + what + "=BAD";
+    const bpt_texture &t = tx[id - 1].t;
+    char b[320];
+    if (t.kind == BPT_TEXTURE_NORMALMAP) {   // image only; an RGBA file counts as its RGB channels
+        snprintf(b, sizeof(b), " %s=image{%dx%d fmt=%d px=%016" PRIx64 "}", what, t.xres, t.yres, t.format, tx[id - 1].hash);
+        return b;
+    }
+    snprintf(b, sizeof(b), " %s=tex{%dx%dx%d fmt=%d enc=%d px=%016" PRIx64 " filter=%d aniso=%s wrap=%d scale=%s invert=%d uv=%s,%s,%s,%s}", what, t.xres, t.yres, t.n_channels, t.format,
+             t.format == BPT_IMAGE_U8 ? t.encoding : 0, tx[id - 1].hash, t.filter, F(t.max_anisotropy).c_str(), t.wrap, F(t.scale).c_str(), t.invert != 0, F(t.su).c_str(), F(t.sv).c_str(),
+             F(t.du).c_str(), F(t.dv).c_str());
+    return b;
+}
+static std::string MatBody(const Material &mt);
+static std::string Mat(const Material &mt, const std::vector<Texture> &tx) {
+    const bpt_material &m = mt.m;
+    std::string s = MatBody(mt);
+    if (m.type == BPT_MAT_INTERFACE) return s;
+    s.pop_back();   // the closing brace
+    return s + Tex(tx, "refl_tex", m.reflectance_tex) + Tex(tx, "trans_tex", m.transmittance_tex) + Tex(tx, "urough_tex", m.uroughness_tex) + Tex(tx, "vrough_tex", m.vroughness_tex) +
+           Tex(tx, "displacement", m.displacement_tex) + Tex(tx, "normalmap", m.normal_map_tex) + "}";
+}
+static std::string MatBody(const Material &mt) {
     const bpt_material &m = mt.m;
     std::string s = "mat{type=" + std::to_string(m.type);
     if (m.type == BPT_MAT_INTERFACE) return s + "}";
@@ -105,6 +130,21 @@ int bpt_scene_set_materials(bpt_engine *e, const bpt_material *m, int n) {
         Material &o = e->materials[i]; o.m = m[i];
         const bpt_spectrum *sp[8] = {&m[i].reflectance, &m[i].eta, &m[i].k, &m[i].iface_eta, &m[i].conductor_eta, &m[i].conductor_k, &m[i].albedo, &m[i].transmittance};
         for (int k = 0; k < 8; ++k) o.sp[k] = Own(*sp[k]);
+    }
+    return BPT_OK;
+}
+int bpt_scene_set_textures(bpt_engine *e, const bpt_texture *t, int n) {
+    e->textures.resize(n);
+    for (int i = 0; i < n; ++i) {
+        e->textures[i].t = t[i];
+        const size_t es = t[i].format == BPT_IMAGE_U8 ? 1 : 4, bytes = (size_t)t[i].xres * t[i].yres * t[i].n_channels * es;
+        if (t[i].kind == BPT_TEXTURE_NORMALMAP && t[i].n_channels == 4) {
+            uint64_t h = 1469598103934665603ull;
+            for (size_t px = 0; px < (size_t)t[i].xres * t[i].yres; ++px) h = Fnv((const char *)t[i].pixels + px * 4 * es, 3 * es, h);
+            e->textures[i].hash = h;
+        } else
+            e->textures[i].hash = Fnv(t[i].pixels, bytes);
+        e->textures[i].t.pixels = nullptr;
     }
     return BPT_OK;
 }
@@ -189,7 +229,7 @@ int bpt_scene_commit(bpt_engine *e) {
         s += " renderFromObject{" + X(rfo) + "} reverse=" + std::to_string(m.reverse_orientation != 0) + " alpha=" + (m.has_alpha ? F(m.alpha) : std::string("none"));
         Material iface; std::memset(&iface.m, 0, sizeof(iface.m)); iface.m.type = BPT_MAT_INTERFACE;
         const Material &mt = m.material < 0 ? iface : e->materials[m.material];
-        s += " " + Mat(mt);
+        s += " " + Mat(mt, e->textures);
         if (m.area_light >= 0 && mt.m.type != BPT_MAT_INTERFACE) {
             const AreaLight &al = e->areaLights[m.area_light];
             s += " arealight{L=" + S(al.L) + " scale=" + F(al.a.scale) + " two=" + std::to_string(al.a.two_sided != 0) + " power=" + F(al.a.power > 0 ? al.a.power : -1.f) + "}";
