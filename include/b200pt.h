@@ -61,7 +61,7 @@ typedef struct {
 typedef struct { float m[4][4]; } bpt_mat4;
 
 typedef struct {
-    int type;                     /* BPT_CAMERA_* (only PERSPECTIVE is implemented) */
+    int type;                     /* BPT_CAMERA_PERSPECTIVE | BPT_CAMERA_ORTHOGRAPHIC */
     bpt_mat4 camera_from_world;   /* CTM at the Camera directive */
     bpt_mat4 world_from_camera;   /* its tracked inverse (pbrt keeps both); all zeros => computed numerically */
     float fov, lens_radius, focal_distance;

@@ -259,10 +259,10 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
     // camera (cameras.cpp CameraBaseParameters + PerspectiveCamera::Create)
     {
         const CameraSceneEntity &ce = builder.camera;
-        if (ce.name != "perspective") ErrorExit(&ce.loc, "camera \"%s\" is not implemented by the engine", ce.name.ToString());
+        if (ce.name != "perspective" && ce.name != "orthographic") ErrorExit(&ce.loc, "camera \"%s\" is not implemented by the engine", ce.name.ToString());
         const ParameterDictionary &d = ce.parameters;
         bpt_camera c; std::memset(&c, 0, sizeof(c));
-        c.type = BPT_CAMERA_PERSPECTIVE;
+        c.type = ce.name == "perspective" ? BPT_CAMERA_PERSPECTIVE : BPT_CAMERA_ORTHOGRAPHIC;
         c.camera_from_world = ToB(builder.cameraFromWorld.GetMatrix()); c.world_from_camera = ToB(builder.cameraFromWorld.GetInverseMatrix());
         c.fov = d.GetOneFloat("fov", 90.f); c.lens_radius = d.GetOneFloat("lensradius", 0.f); c.focal_distance = d.GetOneFloat("focaldistance", 1e6f);
         c.frame_aspect_ratio = d.GetOneFloat("frameaspectratio", -1.f);

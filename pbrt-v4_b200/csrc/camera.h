@@ -89,6 +89,21 @@ BPT_HD CamSample GetCameraSample(const SamplerParams &sp, const DeviceFilter &fi
 // PerspectiveCamera::GenerateRayDifferential (cameras.cpp:429-447), main ray, taken to render space (CameraTransform::RenderFromCamera)
 BPT_HD void GenerateCameraRay(const DeviceCamera &cam, Vec2 pFilm, Vec2 pLens, Pt3 *oOut, Vec3 *dOut) {
     Pt3 pCamera = XformPoint(cam.cameraFromRaster, Pt3(pFilm.x, pFilm.y, 0));
+    if (cam.type == 1) {   // OrthographicCamera::GenerateRayDifferential (cameras.cpp:308-329): origin on the film plane, direction +z
+        Pt3 o = pCamera;
+        Vec3 dir(0, 0, 1);
+        if (cam.lensRadius > 0) {
+            Vec2 dsk = SampleUniformDiskConcentric(pLens);
+            Vec2 pl(cam.lensRadius * dsk.x, cam.lensRadius * dsk.y);
+            float ft = cam.focalDistance / dir.z;
+            Pt3 pFocus = o + dir * ft;
+            o = Pt3(pl.x, pl.y, 0);
+            dir = Normalize(pFocus - o);
+        }
+        XformRay(cam.renderFromCamera, o, dir);
+        *oOut = o; *dOut = dir;
+        return;
+    }
     Vec3 dir = Normalize(Vec3(pCamera.x, pCamera.y, pCamera.z));
     Pt3 o(0, 0, 0);
     if (cam.lensRadius > 0) {
@@ -110,7 +125,25 @@ struct RayDiffs { Pt3 rxO, ryO; Vec3 rxD, ryD; };
 BPT_HD RayDiffs CameraRayDifferentials(const DeviceCamera &cam, const CamSample &cs, Pt3 o, Vec3 d, bool scaleDifferentials = true) {
     Pt3 pCamera = XformPoint(cam.cameraFromRaster, Pt3(cs.pFilm.x, cs.pFilm.y, 0));
     RayDiffs r;
-    if (cam.lensRadius > 0) {
+    if (cam.type == 1) {   // OrthographicCamera::GenerateRayDifferential (cameras.cpp:330-352), camera space
+        if (cam.lensRadius > 0) {
+            Vec2 dsk = SampleUniformDiskConcentric(cs.pLens);
+            Vec2 pl(cam.lensRadius * dsk.x, cam.lensRadius * dsk.y);
+            // ft from the main ray's (already refocused) direction, as the reference computes it
+            Pt3 pFocus0 = pCamera + Vec3(0, 0, 1) * (cam.focalDistance / 1.f);
+            Vec3 dMain = Normalize(pFocus0 - Pt3(pl.x, pl.y, 0));
+            float ft = cam.focalDistance / dMain.z;
+            Pt3 pFocus = pCamera + cam.dxCamera + (ft * Vec3(0, 0, 1));
+            r.rxO = Pt3(pl.x, pl.y, 0);
+            r.rxD = Normalize(pFocus - r.rxO);
+            pFocus = pCamera + cam.dyCamera + (ft * Vec3(0, 0, 1));
+            r.ryO = Pt3(pl.x, pl.y, 0);
+            r.ryD = Normalize(pFocus - r.ryO);
+        } else {
+            r.rxO = pCamera + cam.dxCamera; r.ryO = pCamera + cam.dyCamera;
+            r.rxD = r.ryD = Vec3(0, 0, 1);
+        }
+    } else if (cam.lensRadius > 0) {
         Vec2 dsk = SampleUniformDiskConcentric(cs.pLens);
         Vec2 pl(cam.lensRadius * dsk.x, cam.lensRadius * dsk.y);
         Vec3 dx = Normalize(Vec3(pCamera.x + cam.dxCamera.x, pCamera.y + cam.dxCamera.y, pCamera.z + cam.dxCamera.z));
@@ -141,6 +174,11 @@ BPT_HD RayDiffs CameraRayDifferentials(const DeviceCamera &cam, const CamSample 
 // CameraBase::FindMinimumDifferentials (cameras.cpp:154-200): the smallest position / direction differentials over 512 camera rays
 // along the film diagonal, in camera space; Camera::Approximate_dp_dxy starts from them.  cameraFromRender = renderFromCamera's inverse.
 inline void FindMinimumDifferentials(DeviceCamera *cam, int fullResX, int fullResY) {
+    if (cam->type == 1) {   // OrthographicCamera's constructor (cameras.h:291-297)
+        cam->minDirDifferentialX = cam->minDirDifferentialY = Vec3(0, 0, 0);
+        cam->minPosDifferentialX = cam->dxCamera; cam->minPosDifferentialY = cam->dyCamera;
+        return;
+    }
     const float inf = BPT_INFINITY;
     cam->minPosDifferentialX = cam->minPosDifferentialY = cam->minDirDifferentialX = cam->minDirDifferentialY = Vec3(inf, inf, inf);
     CamSample cs{};

@@ -466,7 +466,7 @@ extern "C" int bpt_scene_begin(bpt_engine *e) {
 }
 extern "C" int bpt_scene_set_camera(bpt_engine *e, const bpt_camera *c) {
     if (!e || !c) return BPT_ERR_INVALID;
-    if (c->type != BPT_CAMERA_PERSPECTIVE) return e->fail(BPT_ERR_UNSUPPORTED, "only the perspective camera is implemented");
+    if (c->type != BPT_CAMERA_PERSPECTIVE && c->type != BPT_CAMERA_ORTHOGRAPHIC) return e->fail(BPT_ERR_UNSUPPORTED, "camera not implemented (perspective, orthographic)");
     e->cam = *c; e->haveCam = true; return BPT_OK;
 }
 extern "C" int bpt_scene_set_film(bpt_engine *e, const bpt_film *f) {
@@ -719,7 +719,9 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         if (frame > 1.f) { sw[0] = -frame; sw[1] = frame; sw[2] = -1.f; sw[3] = 1.f; }
         else { sw[0] = -1.f; sw[1] = 1.f; sw[2] = -1.f / frame; sw[3] = 1.f / frame; }
         if (e->cam.has_screen_window) for (int i = 0; i < 4; ++i) sw[i] = e->cam.screen_window[i];
-        Xform screenFromCamera = Perspective(e->cam.fov > 0 ? e->cam.fov : 90.f, 1e-2f, 1000.f);
+        // OrthographicCamera: Orthographic(0, 1) = Scale(1, 1, 1 / (zFar - zNear)) * Translate(0, 0, -zNear) (cameras.h:288, util/transform.cpp:115-117)
+        const bool ortho = e->cam.type == BPT_CAMERA_ORTHOGRAPHIC;
+        Xform screenFromCamera = ortho ? Scale(1, 1, 1 / (1.f - 0.f)) * Translate(Vec3(0, 0, -0.f)) : Perspective(e->cam.fov > 0 ? e->cam.fov : 90.f, 1e-2f, 1000.f);
         Xform NDCFromScreen = Scale(1 / (sw[1] - sw[0]), 1 / (sw[3] - sw[2]), 1) * Translate(Vec3(-sw[0], -sw[3], 0));
         Xform rasterFromNDC = Scale((float)fl.xres, -(float)fl.yres, 1);
         Xform rasterFromScreen = rasterFromNDC * NDCFromScreen;
@@ -733,6 +735,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         // dxCamera = cameraFromRaster(Point3f(1,0,0)) - cameraFromRaster(Point3f(0,0,0))  (cameras.h:347-351)
         Pt3 c0 = cameraFromRaster(Pt3(0, 0, 0)), cx = cameraFromRaster(Pt3(1, 0, 0)), cy = cameraFromRaster(Pt3(0, 1, 0));
         dc.dxCamera = cx - c0; dc.dyCamera = cy - c0;
+        if (ortho) { dc.dxCamera = cameraFromRaster(Vec3(1, 0, 0)); dc.dyCamera = cameraFromRaster(Vec3(0, 1, 0)); }   // cameras.h:291-292
         dc.rayDiffScale = std::max(.125f, 1 / std::sqrt((float)std::max(1, e->sampler.spp)));
         if (!e->textures.empty()) {   // Camera::Approximate_dp_dxy needs these; only texture filtering reads them
             dc.cameraFromRender = ToMat4(renderFromCamera.mInv);

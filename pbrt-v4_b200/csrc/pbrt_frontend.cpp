@@ -651,7 +651,7 @@ bool Frontend::parseFile(const std::string &path) {
         }
         if (!directive(t, d, args, pl)) { if (err.find(t.file) == std::string::npos) fail(t, d + ": " + err); return false; }
         std::string un = pl.unused();
-        if (!un.empty() && d != "Film" && d != "Camera") return fail(t, d + ": parameter \"" + un + "\" is not supported by this front end");
+        if (!un.empty()) return fail(t, d + ": parameter \"" + un + "\" is not supported by this front end");
     }
     return true;
 }
@@ -689,9 +689,9 @@ bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::st
     if (d == "ColorSpace") { if (a.empty() || a[0] != "srgb") { err = "only the srgb colour space is supported"; return false; } return true; }
     if (d == "Include") { if (a.empty()) { err = "filename expected"; return false; } std::string fn = a[0]; if (fn[0] != '/') fn = baseDir + "/" + fn; return parseFile(fn); }
     if (d == "Camera") {
-        if (a.empty() || a[0] != "perspective") { err = "only the perspective camera is supported"; return false; }
+        if (a.empty() || (a[0] != "perspective" && a[0] != "orthographic")) { err = "cameras supported: \"perspective\", \"orthographic\""; return false; }
         std::memset(&cam, 0, sizeof(cam));
-        cam.type = BPT_CAMERA_PERSPECTIVE;
+        cam.type = a[0] == "perspective" ? BPT_CAMERA_PERSPECTIVE : BPT_CAMERA_ORTHOGRAPHIC;
         cam.camera_from_world = ToB(gs.ctm.m); cam.world_from_camera = ToB(gs.ctm.mInv);
         cam.fov = pl.f("fov", 90.f); cam.lens_radius = pl.f("lensradius", 0.f); cam.focal_distance = pl.f("focaldistance", 1e6f);
         cam.frame_aspect_ratio = pl.f("frameaspectratio", -1.f);
@@ -757,7 +757,8 @@ bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::st
     }
     if (d == "Integrator") {
         std::string ty = a.empty() ? "volpath" : a[0];
-        if (ty != "volpath" && ty != "path") { err = "integrator \"" + ty + "\" is not supported (volpath)"; return false; }
+        // ("path" is a different estimator in the reference -- no media, no transmittance along shadow rays -- and is not substituted)
+        if (ty != "volpath") { err = "integrator \"" + ty + "\" is not supported (volpath)"; return false; }
         integ.max_depth = pl.i("maxdepth", 5); integ.regularize = pl.b("regularize", false);
         std::string ls = pl.s("lightsampler", "bvh");
         integ.light_sampler = ls == "uniform" ? BPT_LIGHTSAMPLER_UNIFORM : ls == "bvh" ? BPT_LIGHTSAMPLER_BVH : -1;

@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(128) k_medium_scatter(RenderCtx rc, int nextQ)
         ps.rayD[slot] = make_float4(wi.x, wi.y, wi.z, d4.w);
         st4(&ps.beta[slot], beta); st4(&ps.r_l[slot], r_l);
         // specularBounce = false, anyNonSpecularBounces = true
-        ps.misc[slot] = make_uint4(misc.x, misc.y, (unsigned)sampler.dimension, (misc.w & 0xffu) | 0x200u | kPathNoDiffs);   // intr.SpawnRay(wi): a plain Ray, no differentials
+        ps.misc[slot] = make_uint4(misc.x, misc.y, (unsigned)sampler.dimension, (misc.w & 0xcffu) | 0x200u);   // ray.o = p; ray.d = wi (cpu/integrators.cpp:1048-1049): the RayDifferential keeps whatever differentials it had
         int q = WarpAggPush(&rc.counts[nextQ]);
         rc.queues[nextQ][q] = slot;
     }

@@ -69,6 +69,14 @@ def _scenes():
     for k, smp in enumerate(['"paddedsobol" "integer pixelsamples" 8', '"paddedsobol" "integer pixelsamples" 4 "string randomization" "owen"',
                              '"stratified" "integer xsamples" 3 "integer ysamples" 2', '"stratified" "bool jitter" false', '"independent" "integer pixelsamples" 5']):
         cases["sampler_%d" % k] = (lambda d, smp=smp: with_sampler(d, smp))
+    def with_camera(d, cam):
+        p = scenes.cornell(d, res=(32, 32), spp=1)
+        txt = open(p).read()
+        a = txt.index("Camera "); b = txt.index("\n", a)
+        open(p, "w").write(txt[:a] + "Camera " + cam + txt[b:])
+        return p
+    for k, cam in enumerate(['"orthographic" "float screenwindow" [-1.1 1.1 -1.1 1.1]', '"orthographic" "float lensradius" 0.05 "float focaldistance" 3.2 "float frameaspectratio" 1.2']):
+        cases["camera_%d" % k] = (lambda d, cam=cam: with_camera(d, cam))
     for ts in sorted(scenes.TEXTURE_SETS):    # image textures: PNG / PFM readers, filter / wrap / scale / invert / uv mapping, material parameters
         cases["textures_" + ts] = (lambda d, ts=ts: scenes.cornell_textured(d, ts, res=(32, 32), spp=1))
     for ls in sorted(scenes.LIGHT_SETS):   # point / spot / distant lights: parameters, defaults, transforms, power / illuminance

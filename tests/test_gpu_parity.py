@@ -434,6 +434,29 @@ def test_image_textures_and_bump_mapping_match_the_live_reference(E, tmp_path, w
 
 
 @pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/bin/pbrt not on this box")
+@pytest.mark.parametrize("cam", ['"orthographic" "float screenwindow" [-1.1 1.1 -1.1 1.1]',
+                                 '"orthographic" "float lensradius" 0.05 "float focaldistance" 3.2 "float frameaspectratio" 1.2'])
+def test_orthographic_camera_matches_the_live_reference(E, tmp_path, cam):
+    """Camera "orthographic" (cameras.cpp:284-353), with and without a lens: RGB render of the textured, bump-mapped box (the camera's
+    own differentials and its fixed "minimum differentials" feed the texture filter) and the GBuffer geometry channels."""
+    from pbrt_v4_b200 import scenes, imageio
+    path = scenes.cornell_textured(str(tmp_path), "bump", res=(48, 48), spp=8)
+    txt = open(path).read()
+    a = txt.index("Camera "); b = txt.index("\n", a)
+    open(path, "w").write(txt[:a] + "Camera " + cam + txt[b:])
+    subprocess.check_call([REF_EXE, "--quiet", "--seed", "0", "--outfile", str(tmp_path / "ref.pfm"), path])
+    ref = imageio.read_pfm(str(tmp_path / "ref.pfm"))
+    img = _render(E, path, 8)
+    assert ref.max() > 0 and (bits(img) == bits(ref)).all(), (cam, int((bits(img) != bits(ref)).any(axis=-1).sum()), float(np.abs(img - ref).max()))
+    gpath = scenes.as_gbuffer(path, "camera")
+    subprocess.check_call([REF_EXE, "--quiet", "--seed", "0", "--outfile", str(tmp_path / "ref.exr"), gpath])
+    names, gref = imageio.read_raw_channels(str(tmp_path / "ref.exr"))
+    e = E.Engine(0); e.load_pbrt(gpath, seed=0); e.render(0, 8); g = e.gbuffer(); e.close()
+    for c, nm in enumerate(names):
+        assert (bits(g[..., c]) == bits(gref[..., c])).all(), nm
+
+
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/bin/pbrt not on this box")
 def test_textured_gbuffer_and_media_match_the_live_reference(E, tmp_path):
     """Textures with the other users of the ray differentials: GBufferFilm (albedo of a textured, bump-mapped surface; Ns after bump
     mapping) and a camera ray that crosses interface surfaces of a medium before it reaches the textured floor (SkipIntersection)."""
