@@ -127,9 +127,17 @@ typedef struct {
     float scale; int invert;      /* "scale" (1), "invert" */
     float su, sv, du, dv;         /* "uscale" "vscale" "udelta" "vdelta" */
     int kind;                     /* BPT_TEXTURE_IMAGEMAP, or BPT_TEXTURE_NORMALMAP: the RGB image of a material's "normalmap" (read with the
-                                   * linear encoding, looked up bilinearly without a pyramid; only the image fields are used) */
+                                   * linear encoding, looked up bilinearly without a pyramid; only the image fields are used), or one of the
+                                   * image-less classes below */
+    /* Texture "constant" | "scale" | "mix" (textures.h:137-196, 843-890, 199-260): children are texture ids (index + 1) of entries
+     * EARLIER in the array; a constant parameter is its own BPT_TEXTURE_CONSTANT entry, as the reference wraps it in a
+     * Float / SpectrumConstantTexture.  scale: tex1 = "tex", tex2 = "scale" (float).  mix: tex1, tex2, tex3 = "amount" (float). */
+    int is_spectrum;              /* value type of this texture: 0 float, 1 spectrum */
+    int tex1, tex2, tex3;
+    float value_f;                /* BPT_TEXTURE_CONSTANT, float */
+    bpt_spectrum value_s;         /* BPT_TEXTURE_CONSTANT, spectrum ("value") */
 } bpt_texture;
-enum { BPT_TEXTURE_IMAGEMAP = 0, BPT_TEXTURE_NORMALMAP = 1 };
+enum { BPT_TEXTURE_IMAGEMAP = 0, BPT_TEXTURE_NORMALMAP = 1, BPT_TEXTURE_CONSTANT = 2, BPT_TEXTURE_SCALE = 3, BPT_TEXTURE_MIX = 4 };
 
 typedef struct {
     bpt_spectrum L;               /* BPT_SPEC_NONE => colour-space illuminant */

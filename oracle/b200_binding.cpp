@@ -355,8 +355,57 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
     std::vector<bpt_texture> texs;
     std::vector<std::unique_ptr<std::vector<uint8_t>>> texelStore;
     for (const TextureRecord &tr : builder.textures) {
-        if (tr.texname != "imagemap") ErrorExit(&tr.loc, "texture class \"%s\" is not implemented by the engine (imagemap)", tr.texname);
         const ParameterDictionary &d = tr.params;
+        const bool spec = tr.type == "spectrum";
+        // a float / spectrum texture parameter of a texture: a named texture, or a constant in its own constant-texture entry
+        // (TextureParameterDictionary::GetFloatTexture / GetSpectrumTexture, paramdict.cpp)
+        auto floatChild = [&](const std::string &name, float dflt) -> int {
+            const ParsedParameter *p = FindParam(d, name);
+            if (p && p->type == "texture") {
+                p->lookedUp = true;
+                auto it = p->strings.empty() ? tx.floats.end() : tx.floats.find(p->strings[0]);
+                if (it == tx.floats.end()) ErrorExit(&tr.loc, "parameter \"%s\": unknown float texture", name);
+                return it->second;
+            }
+            bpt_texture c; std::memset(&c, 0, sizeof(c));
+            c.kind = BPT_TEXTURE_CONSTANT; c.value_f = d.GetOneFloat(name, dflt);
+            texs.push_back(c); return (int)texs.size();
+        };
+        auto spectrumChild = [&](const std::string &name, float dflt) -> int {
+            const ParsedParameter *p = FindParam(d, name);
+            if (p && p->type == "texture") {
+                p->lookedUp = true;
+                auto it = p->strings.empty() ? tx.spectra.end() : tx.spectra.find(p->strings[0]);
+                if (it == tx.spectra.end()) ErrorExit(&tr.loc, "parameter \"%s\": unknown spectrum texture", name);
+                return it->second;
+            }
+            bpt_texture c; std::memset(&c, 0, sizeof(c));
+            c.kind = BPT_TEXTURE_CONSTANT; c.is_spectrum = 1; c.value_s = GetSpectrum(d, name, st);
+            if (c.value_s.kind == BPT_SPEC_NONE) { c.value_s.kind = BPT_SPEC_CONSTANT; c.value_s.value = dflt; }
+            texs.push_back(c); return (int)texs.size();
+        };
+        if (tr.texname == "constant" || tr.texname == "scale" || tr.texname == "mix") {
+            bpt_texture t; std::memset(&t, 0, sizeof(t));
+            t.is_spectrum = spec;
+            if (tr.texname == "constant") {
+                t.kind = BPT_TEXTURE_CONSTANT;
+                if (spec) { t.value_s = GetSpectrum(d, "value", st); if (t.value_s.kind == BPT_SPEC_NONE) { t.value_s.kind = BPT_SPEC_CONSTANT; t.value_s.value = 1.f; } }
+                else t.value_f = d.GetOneFloat("value", 1.f);
+            } else if (tr.texname == "scale") {
+                t.kind = BPT_TEXTURE_SCALE;
+                t.tex1 = spec ? spectrumChild("tex", 1.f) : floatChild("tex", 1.f);
+                t.tex2 = floatChild("scale", 1.f);
+            } else {
+                t.kind = BPT_TEXTURE_MIX;
+                t.tex1 = spec ? spectrumChild("tex1", 0.f) : floatChild("tex1", 0.f);
+                t.tex2 = spec ? spectrumChild("tex2", 1.f) : floatChild("tex2", 1.f);
+                t.tex3 = floatChild("amount", 0.5f);
+            }
+            texs.push_back(t);
+            (spec ? tx.spectra : tx.floats)[tr.name] = (int)texs.size();
+            continue;
+        }
+        if (tr.texname != "imagemap") ErrorExit(&tr.loc, "texture class \"%s\" is not implemented by the engine (imagemap, constant, scale, mix)", tr.texname);
         if (d.GetOneString("mapping", "uv") != "uv") ErrorExit(&tr.loc, "only the \"uv\" texture mapping is implemented by the engine");
         bpt_texture t; std::memset(&t, 0, sizeof(t));
         t.su = d.GetOneFloat("uscale", 1.f); t.sv = d.GetOneFloat("vscale", 1.f); t.du = d.GetOneFloat("udelta", 0.f); t.dv = d.GetOneFloat("vdelta", 0.f);
@@ -390,6 +439,7 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
             texelStore.emplace_back(new std::vector<uint8_t>((const uint8_t *)image.RawPointer({0, 0}), (const uint8_t *)image.RawPointer({0, 0}) + count * sizeof(float)));
         } else ErrorExit(&tr.loc, "%s: half-precision texture images are not implemented by the engine", filename);
         t.pixels = texelStore.back()->data();
+        t.is_spectrum = spec;
         texs.push_back(t);
         (tr.type == "float" ? tx.floats : tx.spectra)[tr.name] = (int)texs.size();
     }

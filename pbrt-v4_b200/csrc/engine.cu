@@ -16,6 +16,7 @@
 #include "bvh_build.h"
 #include "scene_xforms.h"
 #include "texture_host.h"
+#include "texture.h"
 #include "camera.h"
 #include "exr_writer.h"
 #include "kernels.h"
@@ -53,7 +54,7 @@ struct OwnedLight {
     std::vector<float> image;
 };
 struct OwnedAreaLight { bpt_area_light a; OwnedSpectrum L; };
-struct OwnedTexture { bpt_texture t; HostImage img; };
+struct OwnedTexture { bpt_texture t; HostImage img; OwnedSpectrum value; };
 struct OwnedMedium { bpt_medium m; OwnedSpectrum sigma_a, sigma_s, Le; std::vector<float> density, leScale; };
 
 template <typename T>
@@ -517,6 +518,17 @@ extern "C" int bpt_scene_set_textures(bpt_engine *e, const bpt_texture *t, int n
     e->textures.resize(n);
     for (int i = 0; i < n; ++i) {
         const bpt_texture &b = t[i];
+        if (b.kind == BPT_TEXTURE_CONSTANT || b.kind == BPT_TEXTURE_SCALE || b.kind == BPT_TEXTURE_MIX) {
+            // image-less classes: children are earlier entries
+            const int nch = b.kind == BPT_TEXTURE_CONSTANT ? 0 : b.kind == BPT_TEXTURE_SCALE ? 2 : 3;
+            const int ch[3] = {b.tex1, b.tex2, b.tex3};
+            for (int k = 0; k < nch; ++k) if (ch[k] < 1 || ch[k] > i) return e->fail(BPT_ERR_INVALID, "texture refers to a texture that is not defined before it");
+            OwnedTexture &o = e->textures[i];
+            o.t = b; o.t.pixels = nullptr;
+            o.value.Set(b.value_s);
+            continue;
+        }
+        if (b.kind != BPT_TEXTURE_IMAGEMAP && b.kind != BPT_TEXTURE_NORMALMAP) return e->fail(BPT_ERR_UNSUPPORTED, "texture class not implemented (imagemap, constant, scale, mix)");
         if (!b.pixels || b.xres <= 0 || b.yres <= 0 || (b.n_channels != 1 && b.n_channels != 3 && b.n_channels != 4))
             return e->fail(BPT_ERR_INVALID, "texture image: 1, 3 or 4 channels of 8-bit or float texels expected");
         if (b.format != BPT_IMAGE_U8 && b.format != BPT_IMAGE_F32) return e->fail(BPT_ERR_UNSUPPORTED, "texture image format not implemented (8-bit, float)");
@@ -883,6 +895,10 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         if ((dm.reflectanceTex >= 0 && !reflOK) || (dm.transmittanceTex >= 0 && mt != BPT_MAT_DIFFUSE_TRANSMISSION) ||
             ((dm.uroughnessTex >= 0 || dm.vroughnessTex >= 0) && !roughOK) || (dm.displacementTex >= 0 && mt == BPT_MAT_INTERFACE))
             return e->fail(BPT_ERR_UNSUPPORTED, "texture on a material parameter that does not take one");
+        auto isSpec = [&](int t) { return t >= 0 && e->textures[t].t.is_spectrum != 0; };
+        if ((dm.reflectanceTex >= 0 && !isSpec(dm.reflectanceTex)) || (dm.transmittanceTex >= 0 && !isSpec(dm.transmittanceTex)) || isSpec(dm.uroughnessTex) ||
+            isSpec(dm.vroughnessTex) || isSpec(dm.displacementTex))
+            return e->fail(BPT_ERR_INVALID, "float texture on a spectrum parameter or the other way round");
         auto kindOf = [&](int t) { return t < 0 ? -1 : e->textures[t].t.kind; };
         if (kindOf(dm.normalMapTex) == BPT_TEXTURE_IMAGEMAP || kindOf(dm.reflectanceTex) == BPT_TEXTURE_NORMALMAP || kindOf(dm.transmittanceTex) == BPT_TEXTURE_NORMALMAP ||
             kindOf(dm.uroughnessTex) == BPT_TEXTURE_NORMALMAP || kindOf(dm.vroughnessTex) == BPT_TEXTURE_NORMALMAP || kindOf(dm.displacementTex) == BPT_TEXTURE_NORMALMAP ||
@@ -1418,7 +1434,55 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         std::vector<DeviceTexture> dtex(e->textures.size());
         std::vector<std::vector<HostMIPLevel>> pyramids(e->textures.size());
         size_t nTexels = 0, nLevels = 0;
+        std::vector<int> depth(e->textures.size(), 0);
         for (size_t i = 0; i < e->textures.size(); ++i) {
+            const bpt_texture &tb = e->textures[i].t;
+            if (tb.kind == BPT_TEXTURE_CONSTANT) {
+                DeviceTexture &d = dtex[i];
+                std::memset(&d, 0, sizeof(d));
+                d.kind = TEXKIND_CONSTANT; d.cval = tb.value_f;
+                if (tb.is_spectrum) {
+                    // SpectrumConstantTexture::Create: GetOneSpectrum("value", ConstantSpectrum(1), spectrumType); every spectrum-valued
+                    // parameter textures feed here is a reflectance or transmittance (SpectrumType::Albedo)
+                    if (e->textures[i].value.s.kind == BPT_SPEC_NONE) { d.sval.kind = SPEC_CONSTANT; d.sval.c0 = 1.f; }
+                    else if (!MakeSpectrumRec(e, e->textures[i].value, ST_ALBEDO, spool, &d.sval, &serr)) return e->fail(BPT_ERR_UNSUPPORTED, serr);
+                }
+                continue;
+            }
+            if (tb.kind == BPT_TEXTURE_SCALE || tb.kind == BPT_TEXTURE_MIX) {
+                auto isFloat = [&](int id) { return e->textures[id].t.is_spectrum == 0 && e->textures[id].t.kind != BPT_TEXTURE_NORMALMAP; };
+                auto sameType = [&](int id) { return (e->textures[id].t.is_spectrum != 0) == (tb.is_spectrum != 0) && e->textures[id].t.kind != BPT_TEXTURE_NORMALMAP; };
+                DeviceTexture &d = dtex[i];
+                if (tb.kind == BPT_TEXTURE_MIX) {
+                    int t1 = tb.tex1 - 1, t2 = tb.tex2 - 1, am = tb.tex3 - 1;
+                    if (!sameType(t1) || !sameType(t2) || !isFloat(am)) return e->fail(BPT_ERR_INVALID, "mix texture: value types of tex1 / tex2 / amount do not fit");
+                    std::memset(&d, 0, sizeof(d));
+                    d.kind = TEXKIND_MIX; d.child0 = t1; d.child1 = t2; d.child2 = am;
+                    depth[i] = 1 + std::max(depth[t1], std::max(depth[t2], depth[am]));
+                } else {
+                    // FloatScaledTexture::Create / SpectrumScaledTexture::Create (textures.cpp:892-957): a constant scale of 1 returns "tex"
+                    // itself, a constant scale on an image texture is folded into the image texture's own scale
+                    int tex = tb.tex1 - 1, scale = tb.tex2 - 1;
+                    if (!sameType(tex) || !isFloat(scale)) return e->fail(BPT_ERR_INVALID, "scale texture: value types of tex / scale do not fit");
+                    bool done = false;
+                    for (int pass = 0; pass < (tb.is_spectrum ? 1 : 2) && !done; ++pass) {
+                        if (dtex[scale].kind == TEXKIND_CONSTANT) {
+                            float cs = dtex[scale].cval;
+                            if (cs == 1) { d = dtex[tex]; depth[i] = depth[tex]; done = true; }
+                            else if (dtex[tex].kind == TEXKIND_IMAGEMAP) { d = dtex[tex]; d.scale *= cs; depth[i] = 0; done = true; }
+                        }
+                        if (!done && !tb.is_spectrum) std::swap(tex, scale);
+                    }
+                    if (!done) {
+                        if (!tb.is_spectrum) std::swap(tex, scale);   // the reference's final swap: FloatScaledTexture(scale, tex)
+                        std::memset(&d, 0, sizeof(d));
+                        d.kind = TEXKIND_SCALE; d.child0 = tex; d.child1 = scale;
+                        depth[i] = 1 + std::max(depth[tex], depth[scale]);
+                    }
+                }
+                if (depth[i] > kTexMaxDepth) return e->fail(BPT_ERR_UNSUPPORTED, "texture graph deeper than the engine evaluates (3 levels of scale / mix)");
+                continue;
+            }
             HostImage im = e->textures[i].img;
             if (e->textures[i].t.kind == BPT_TEXTURE_NORMALMAP) {
                 // the image itself, RGB channels (BasicScene::startLoadingNormalMaps, scene.cpp:886-910), decoded as Image::GetChannel does
@@ -1438,7 +1502,8 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             DeviceTexture &d = dtex[i];
             d.firstLevel = (int)nLevels; d.nLevels = (int)pyramids[i].size(); d.nc = im.nc;
             d.wrap = b.wrap; d.filter = b.filter; d.maxAnisotropy = b.max_anisotropy;
-            d.su = b.su; d.sv = b.sv; d.du = b.du; d.dv = b.dv; d.scale = b.scale; d.invert = b.invert; d.pad = 0;
+            d.su = b.su; d.sv = b.sv; d.du = b.du; d.dv = b.dv; d.scale = b.scale; d.invert = b.invert;
+            d.kind = TEXKIND_IMAGEMAP; d.child0 = d.child1 = d.child2 = -1; d.cval = 0; std::memset(&d.sval, 0, sizeof(d.sval));
             for (const HostMIPLevel &lv : pyramids[i]) nTexels += lv.texels.size();
             nLevels += pyramids[i].size();
         }
@@ -1454,6 +1519,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         ECK(e->dMipLevels.upload(dlev));
         ECK(e->dTextures.upload(dtex));
         ECK(e->dEwaLUT.upload(e->tables.F("mip_filter_lut")));
+        ECK(e->specPool.upload(spool.pool));   // constant spectrum textures added their tables
     }
     if ((!dimg.empty() || e->haveTextures) && e->dRgb2spec.n == 0) {
         std::vector<float> t(e->tables.F("rgb2spec_srgb_scale"));

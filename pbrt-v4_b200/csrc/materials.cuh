@@ -16,11 +16,11 @@
 namespace bpt {
 
 template <bool TEX> BPT_HD Spec MatSpectrum(const SpectrumRec &rec, int tex, const SceneView &sv, const Wavelengths &wl, const TexEvalCtx *tc) {
-    if (TEX && tex >= 0) return EvalSpectrumImageTexture(sv, sv.textures[tex], *tc, wl, TEXSPEC_ALBEDO);
+    if (TEX && tex >= 0) return EvalSpectrumTexture<kTexMaxDepth>(sv, tex, *tc, wl, TEXSPEC_ALBEDO);
     return EvalSpectrum(rec, sv.specPool, wl);
 }
 template <bool TEX> BPT_HD float MatFloat(float v, int tex, const SceneView &sv, const TexEvalCtx *tc) {
-    if (TEX && tex >= 0) return EvalFloatImageTexture(sv, sv.textures[tex], *tc);
+    if (TEX && tex >= 0) return EvalFloatTexture<kTexMaxDepth>(sv, tex, *tc);
     return v;
 }
 

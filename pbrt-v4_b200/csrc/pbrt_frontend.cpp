@@ -296,7 +296,52 @@ struct Frontend {
     bool makeTexture(const std::vector<std::string> &a, ParamList &pl) {
         if (a.size() < 3) { err = "Texture \"name\" \"float|spectrum\" \"imagemap\" expected"; return false; }
         if (a[1] != "float" && a[1] != "spectrum") { err = "texture value type must be float or spectrum"; return false; }
-        if (a[2] != "imagemap") { err = "texture class \"" + a[2] + "\" is not supported by this front end (imagemap)"; return false; }
+        const bool spec = a[1] == "spectrum";
+        auto &names = spec ? spectrumTextures : floatTextures;
+        // a parameter of a texture that is itself a float / spectrum texture: "texture <name>", or a constant wrapped in its own
+        // constant-texture entry as TextureParameterDictionary::GetFloatTexture / GetSpectrumTexture do (paramdict.cpp)
+        auto floatChild = [&](const std::string &name, float dflt, int *id) -> bool {
+            Param *q = pl.find(name);
+            if (q && q->type == "texture") {
+                if (q->strs.empty() || !floatTextures.count(q->strs[0])) { err = "parameter \"" + name + "\": unknown float texture"; return false; }
+                *id = floatTextures[q->strs[0]]; return true;
+            }
+            bpt_texture c; std::memset(&c, 0, sizeof(c));
+            c.kind = BPT_TEXTURE_CONSTANT; c.value_f = (q && !q->nums.empty()) ? (float)q->nums[0] : dflt;
+            textures.push_back(c); *id = (int)textures.size(); return true;
+        };
+        auto spectrumChild = [&](const std::string &name, float dflt, int *id) -> bool {
+            Param *q = pl.find(name);
+            if (q && q->type == "texture") {
+                if (q->strs.empty() || !spectrumTextures.count(q->strs[0])) { err = "parameter \"" + name + "\": unknown spectrum texture"; return false; }
+                *id = spectrumTextures[q->strs[0]]; return true;
+            }
+            bpt_texture c; std::memset(&c, 0, sizeof(c));
+            c.kind = BPT_TEXTURE_CONSTANT; c.is_spectrum = 1;
+            if (!getSpectrum(pl, name, &c.value_s)) return false;
+            if (c.value_s.kind == BPT_SPEC_NONE) { c.value_s.kind = BPT_SPEC_CONSTANT; c.value_s.value = dflt; }
+            textures.push_back(c); *id = (int)textures.size(); return true;
+        };
+        if (a[2] == "constant" || a[2] == "scale" || a[2] == "mix") {
+            bpt_texture t; std::memset(&t, 0, sizeof(t));
+            t.is_spectrum = spec;
+            if (a[2] == "constant") {
+                t.kind = BPT_TEXTURE_CONSTANT;
+                if (spec) { if (!getSpectrum(pl, "value", &t.value_s)) return false; if (t.value_s.kind == BPT_SPEC_NONE) { t.value_s.kind = BPT_SPEC_CONSTANT; t.value_s.value = 1.f; } }
+                else t.value_f = pl.f("value", 1.f);
+            } else if (a[2] == "scale") {   // Float / SpectrumScaledTexture::Create (textures.cpp:892-957)
+                t.kind = BPT_TEXTURE_SCALE;
+                if (!(spec ? spectrumChild("tex", 1.f, &t.tex1) : floatChild("tex", 1.f, &t.tex1)) || !floatChild("scale", 1.f, &t.tex2)) return false;
+            } else {                        // Float / SpectrumMixTexture::Create (textures.cpp:533-551)
+                t.kind = BPT_TEXTURE_MIX;
+                if (!(spec ? spectrumChild("tex1", 0.f, &t.tex1) : floatChild("tex1", 0.f, &t.tex1)) ||
+                    !(spec ? spectrumChild("tex2", 1.f, &t.tex2) : floatChild("tex2", 1.f, &t.tex2)) || !floatChild("amount", 0.5f, &t.tex3)) return false;
+            }
+            textures.push_back(t);
+            names[a[0]] = (int)textures.size();
+            return true;
+        }
+        if (a[2] != "imagemap") { err = "texture class \"" + a[2] + "\" is not supported by this front end (imagemap, constant, scale, mix)"; return false; }
         if (pl.s("mapping", "uv") != "uv") { err = "only the \"uv\" texture mapping is supported"; return false; }
         bpt_texture t; std::memset(&t, 0, sizeof(t));
         t.su = pl.f("uscale", 1.f); t.sv = pl.f("vscale", 1.f); t.du = pl.f("udelta", 0.f); t.dv = pl.f("vdelta", 0.f);
@@ -322,8 +367,9 @@ struct Frontend {
         if (png) { if (!readPNG(fn, &t)) return false; }
         else if (hasExt(".pfm")) { if (!readPFMTexture(fn, &t)) return false; }
         else { err = fn + ": texture images are read from .png (8-bit) and .pfm files"; return false; }
+        t.is_spectrum = spec;
         textures.push_back(t);
-        (a[1] == "float" ? floatTextures : spectrumTextures)[a[0]] = (int)textures.size();
+        names[a[0]] = (int)textures.size();
         return true;
     }
 

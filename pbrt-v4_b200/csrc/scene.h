@@ -73,8 +73,13 @@ struct DeviceTexture {
     float su, sv, du, dv;
     float scale;
     int invert;
-    int pad;
+    // Texture classes without an image (textures.h:137-196 constant, 843-890 scale, 199-260 mix): children are texture indices
+    int kind;                  // TEXKIND_*
+    int child0, child1, child2;
+    float cval;                // constant float
+    SpectrumRec sval;          // constant spectrum
 };
+enum { TEXKIND_IMAGEMAP = 0, TEXKIND_CONSTANT = 2, TEXKIND_SCALE = 3, TEXKIND_MIX = 4 };
 
 struct DeviceMaterial {
     int type;                  // MaterialTag

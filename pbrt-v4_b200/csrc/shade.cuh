@@ -199,19 +199,19 @@ __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int
                 isect.dpdus = dpdu; ex.dpdvs = dpdv;
             } else if (mat.displacementTex >= 0) {
                 // BumpMap (materials.h:107-138) + SetShadingGeometry(ns, dpdu, dpdv, shading.dndu, shading.dndv, false)
-                const DeviceTexture &disp = rc.sv.textures[mat.displacementTex];
+                const int disp = mat.displacementTex;
                 TexEvalCtx shifted = tc;
                 float du = .5f * (fabsf(tc.dudx) + fabsf(tc.dudy));
                 if (du == 0) du = .0005f;
                 shifted.p = tc.p + du * isect.dpdus;
                 shifted.uv = Vec2(tc.uv.x + du, tc.uv.y + 0.f);
-                float uDisplace = EvalFloatImageTexture(rc.sv, disp, shifted);
+                float uDisplace = EvalFloatTexture<kTexMaxDepth>(rc.sv, disp, shifted);
                 float dv = .5f * (fabsf(tc.dvdx) + fabsf(tc.dvdy));
                 if (dv == 0) dv = .0005f;
                 shifted.p = tc.p + dv * ex.dpdvs;
                 shifted.uv = Vec2(tc.uv.x + 0.f, tc.uv.y + dv);
-                float vDisplace = EvalFloatImageTexture(rc.sv, disp, shifted);
-                float displace = EvalFloatImageTexture(rc.sv, disp, tc);
+                float vDisplace = EvalFloatTexture<kTexMaxDepth>(rc.sv, disp, shifted);
+                float displace = EvalFloatTexture<kTexMaxDepth>(rc.sv, disp, tc);
                 Vec3 dpdu = isect.dpdus + (uDisplace - displace) / du * V(isect.ns) + displace * V(ex.dndus);
                 Vec3 dpdv = ex.dpdvs + (vDisplace - displace) / dv * V(isect.ns) + displace * V(ex.dndvs);
                 Nrm3 ns(Normalize(Cross(dpdu, dpdv)));

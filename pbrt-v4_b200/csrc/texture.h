@@ -202,4 +202,51 @@ BPT_HD Spec EvalSpectrumImageTexture(const SceneView &sv, const DeviceTexture &t
     return s;
 }
 
+// ---- texture graphs: "constant", "scale", "mix" over image textures (FloatScaledTexture / SpectrumScaledTexture textures.h:843-890,
+// FloatMixTexture / SpectrumMixTexture textures.h:199-260).  The engine bounds the depth at commit (kTexMaxDepth); the recursion is
+// unrolled by the template.
+constexpr int kTexMaxDepth = 3;
+template <int DEPTH> BPT_HD float EvalFloatTexture(const SceneView &sv, int id, const TexEvalCtx &ctx) {
+    const DeviceTexture &t = sv.textures[id];
+    if (t.kind == TEXKIND_IMAGEMAP) return EvalFloatImageTexture(sv, t, ctx);
+    if (t.kind == TEXKIND_CONSTANT) return t.cval;
+    if (DEPTH > 0) {
+        constexpr int D = DEPTH > 0 ? DEPTH - 1 : 0;
+        if (t.kind == TEXKIND_SCALE) {
+            float sc = EvalFloatTexture<D>(sv, t.child1, ctx);
+            if (sc == 0) return 0;
+            return EvalFloatTexture<D>(sv, t.child0, ctx) * sc;
+        }
+        if (t.kind == TEXKIND_MIX) {
+            float amt = EvalFloatTexture<D>(sv, t.child2, ctx);
+            float t1 = 0, t2 = 0;
+            if (amt != 1) t1 = EvalFloatTexture<D>(sv, t.child0, ctx);
+            if (amt != 0) t2 = EvalFloatTexture<D>(sv, t.child1, ctx);
+            return (1 - amt) * t1 + amt * t2;
+        }
+    }
+    return 0;
+}
+template <int DEPTH> BPT_HD Spec EvalSpectrumTexture(const SceneView &sv, int id, const TexEvalCtx &ctx, const Wavelengths &wl, int spectrumType) {
+    const DeviceTexture &t = sv.textures[id];
+    if (t.kind == TEXKIND_IMAGEMAP) return EvalSpectrumImageTexture(sv, t, ctx, wl, spectrumType);
+    if (t.kind == TEXKIND_CONSTANT) return EvalSpectrum(t.sval, sv.specPool, wl);
+    if (DEPTH > 0) {
+        constexpr int D = DEPTH > 0 ? DEPTH - 1 : 0;
+        if (t.kind == TEXKIND_SCALE) {
+            float sc = EvalFloatTexture<D>(sv, t.child1, ctx);
+            if (sc == 0) return Spec(0.f);
+            return EvalSpectrumTexture<D>(sv, t.child0, ctx, wl, spectrumType) * sc;
+        }
+        if (t.kind == TEXKIND_MIX) {
+            float amt = EvalFloatTexture<D>(sv, t.child2, ctx);
+            Spec t1(0.f), t2(0.f);
+            if (amt != 1) t1 = EvalSpectrumTexture<D>(sv, t.child0, ctx, wl, spectrumType);
+            if (amt != 0) t2 = EvalSpectrumTexture<D>(sv, t.child1, ctx, wl, spectrumType);
+            return (1 - amt) * t1 + amt * t2;
+        }
+    }
+    return Spec(0.f);
+}
+
 }  // namespace bpt

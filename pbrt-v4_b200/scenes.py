@@ -160,6 +160,12 @@ TEXTURE_SETS = {
                   'Material "conductor" "texture roughness" "rough" "texture reflectance" "tint"\n'),
     "bump": ('Texture "h" "float" "imagemap" "string filename" "height.pfm" "float uscale" 2 "float vscale" 2\nTexture "alb" "spectrum" "imagemap" "string filename" "albedo.png"\n',
              'Material "diffuse" "texture reflectance" "alb" "texture displacement" "h"\n'),
+    "scale_mix": ('Texture "alb" "spectrum" "imagemap" "string filename" "albedo.png"\nTexture "m" "float" "imagemap" "string filename" "grey.png" "float uscale" 2\n'
+                  'Texture "half" "spectrum" "scale" "texture tex" "alb" "float scale" 0.6\nTexture "tinted" "spectrum" "scale" "texture tex" "alb" "texture scale" "m"\n'
+                  'Texture "both" "spectrum" "mix" "texture tex1" "half" "rgb tex2" [0.1 0.6 0.2] "texture amount" "m"\nTexture "one" "spectrum" "scale" "texture tex" "both" "float scale" 1\n'
+                  'Texture "r" "float" "scale" "texture tex" "m" "float scale" 0.5\nTexture "r2" "float" "mix" "texture tex1" "r" "float tex2" 0.05 "float amount" 0.3\n'
+                  'Texture "c" "spectrum" "constant" "rgb value" [0.7 0.6 0.3]\n',
+                  'Material "coateddiffuse" "texture reflectance" "one" "texture roughness" "r2"\n'),
     "normalmap": ('Texture "alb" "spectrum" "imagemap" "string filename" "albedo.png"\n', 'Material "diffuse" "texture reflectance" "alb" "string normalmap" "normals.png"\n'),
     "bump_dielectric": ('Texture "h" "float" "imagemap" "string filename" "height.pfm" "float uscale" 3 "float vscale" 3 "string filter" "trilinear"\n',
                         'Material "dielectric" "float eta" 1.5 "float roughness" 0.15 "texture displacement" "h"\n'),

@@ -29,7 +29,7 @@ struct Mesh { bpt_mesh m; std::vector<float> P, N, UV; std::vector<int> idx; };
 struct Light { bpt_light l; std::vector<float> img; Spec L; };
 struct Medium { bpt_medium m; std::vector<float> density, leScale; Spec sa, ss, Le; };
 struct Material { bpt_material m; Spec sp[8]; };
-struct Texture { bpt_texture t; uint64_t hash; };
+struct Texture { bpt_texture t; uint64_t hash; Spec value; };
 struct AreaLight { bpt_area_light a; Spec L; };
 }  // namespace
 
@@ -75,11 +75,20 @@ static std::string Tex(const std::vector<Texture> &tx, const char *what, int id)
     if (id < 0 || id > (int)tx.size()) return std::string(" ") + what + "=BAD";
     const bpt_texture &t = tx[id - 1].t;
     char b[320];
+    if (t.kind == BPT_TEXTURE_CONSTANT) return std::string(" ") + what + "=const{" + (t.is_spectrum ? S(tx[id - 1].value) : F(t.value_f)) + "}";
+    if (t.kind == BPT_TEXTURE_SCALE || t.kind == BPT_TEXTURE_MIX) {
+        const bool bad = t.tex1 >= id || t.tex2 >= id || t.tex3 >= id;   // children come first
+        std::string r = std::string(" ") + what + (t.kind == BPT_TEXTURE_SCALE ? "=scale{" : "=mix{") + (t.is_spectrum ? "spectrum" : "float");
+        if (bad) return r + " BAD}";
+        r += Tex(tx, t.kind == BPT_TEXTURE_SCALE ? "tex" : "tex1", t.tex1) + Tex(tx, t.kind == BPT_TEXTURE_SCALE ? "scale" : "tex2", t.tex2);
+        if (t.kind == BPT_TEXTURE_MIX) r += Tex(tx, "amount", t.tex3);
+        return r + "}";
+    }
     if (t.kind == BPT_TEXTURE_NORMALMAP) {   // image only; an RGBA file counts as its RGB channels
         snprintf(b, sizeof(b), " %s=image{%dx%d fmt=%d px=%016" PRIx64 "}", what, t.xres, t.yres, t.format, tx[id - 1].hash);
         return b;
     }
-    snprintf(b, sizeof(b), " %s=tex{%dx%dx%d fmt=%d enc=%d px=%016" PRIx64 " filter=%d aniso=%s wrap=%d scale=%s invert=%d uv=%s,%s,%s,%s}", what, t.xres, t.yres, t.n_channels, t.format,
+    snprintf(b, sizeof(b), " %s=tex{%s %dx%dx%d fmt=%d enc=%d px=%016" PRIx64 " filter=%d aniso=%s wrap=%d scale=%s invert=%d uv=%s,%s,%s,%s}", what, t.is_spectrum ? "spectrum" : "float", t.xres, t.yres, t.n_channels, t.format,
              t.format == BPT_IMAGE_U8 ? t.encoding : 0, tx[id - 1].hash, t.filter, F(t.max_anisotropy).c_str(), t.wrap, F(t.scale).c_str(), t.invert != 0, F(t.su).c_str(), F(t.sv).c_str(),
              F(t.du).c_str(), F(t.dv).c_str());
     return b;
@@ -137,6 +146,7 @@ int bpt_scene_set_textures(bpt_engine *e, const bpt_texture *t, int n) {
     e->textures.resize(n);
     for (int i = 0; i < n; ++i) {
         e->textures[i].t = t[i];
+        if (t[i].kind == BPT_TEXTURE_CONSTANT || t[i].kind == BPT_TEXTURE_SCALE || t[i].kind == BPT_TEXTURE_MIX) { e->textures[i].value = Own(t[i].value_s); e->textures[i].hash = 0; continue; }
         const size_t es = t[i].format == BPT_IMAGE_U8 ? 1 : 4, bytes = (size_t)t[i].xres * t[i].yres * t[i].n_channels * es;
         if (t[i].kind == BPT_TEXTURE_NORMALMAP && t[i].n_channels == 4) {
             uint64_t h = 1469598103934665603ull;
