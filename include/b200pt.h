@@ -137,7 +137,8 @@ typedef struct {
     float value_f;                /* BPT_TEXTURE_CONSTANT, float */
     bpt_spectrum value_s;         /* BPT_TEXTURE_CONSTANT, spectrum ("value") */
 } bpt_texture;
-enum { BPT_TEXTURE_IMAGEMAP = 0, BPT_TEXTURE_NORMALMAP = 1, BPT_TEXTURE_CONSTANT = 2, BPT_TEXTURE_SCALE = 3, BPT_TEXTURE_MIX = 4 };
+enum { BPT_TEXTURE_IMAGEMAP = 0, BPT_TEXTURE_NORMALMAP = 1, BPT_TEXTURE_CONSTANT = 2, BPT_TEXTURE_SCALE = 3, BPT_TEXTURE_MIX = 4,
+       BPT_TEXTURE_CHECKERBOARD = 5 /* two-dimensional (textures.cpp:183-207): tex1, tex2 and the uv mapping su sv du dv */ };
 
 typedef struct {
     bpt_spectrum L;               /* BPT_SPEC_NONE => colour-space illuminant */

@@ -384,9 +384,16 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
             if (c.value_s.kind == BPT_SPEC_NONE) { c.value_s.kind = BPT_SPEC_CONSTANT; c.value_s.value = dflt; }
             texs.push_back(c); return (int)texs.size();
         };
-        if (tr.texname == "constant" || tr.texname == "scale" || tr.texname == "mix") {
+        if (tr.texname == "constant" || tr.texname == "scale" || tr.texname == "mix" || tr.texname == "checkerboard") {
             bpt_texture t; std::memset(&t, 0, sizeof(t));
             t.is_spectrum = spec;
+            if (tr.texname == "checkerboard") {
+                if (d.GetOneInt("dimension", 2) != 2 || d.GetOneString("mapping", "uv") != "uv") ErrorExit(&tr.loc, "only the two-dimensional checkerboard with \"uv\" mapping is implemented by the engine");
+                t.kind = BPT_TEXTURE_CHECKERBOARD;
+                t.tex1 = spec ? spectrumChild("tex1", 1.f) : floatChild("tex1", 1.f);
+                t.tex2 = spec ? spectrumChild("tex2", 0.f) : floatChild("tex2", 0.f);
+                t.su = d.GetOneFloat("uscale", 1.f); t.sv = d.GetOneFloat("vscale", 1.f); t.du = d.GetOneFloat("udelta", 0.f); t.dv = d.GetOneFloat("vdelta", 0.f);
+            } else
             if (tr.texname == "constant") {
                 t.kind = BPT_TEXTURE_CONSTANT;
                 if (spec) { t.value_s = GetSpectrum(d, "value", st); if (t.value_s.kind == BPT_SPEC_NONE) { t.value_s.kind = BPT_SPEC_CONSTANT; t.value_s.value = 1.f; } }
@@ -405,7 +412,7 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
             (spec ? tx.spectra : tx.floats)[tr.name] = (int)texs.size();
             continue;
         }
-        if (tr.texname != "imagemap") ErrorExit(&tr.loc, "texture class \"%s\" is not implemented by the engine (imagemap, constant, scale, mix)", tr.texname);
+        if (tr.texname != "imagemap") ErrorExit(&tr.loc, "texture class \"%s\" is not implemented by the engine (imagemap, constant, scale, mix, checkerboard)", tr.texname);
         if (d.GetOneString("mapping", "uv") != "uv") ErrorExit(&tr.loc, "only the \"uv\" texture mapping is implemented by the engine");
         bpt_texture t; std::memset(&t, 0, sizeof(t));
         t.su = d.GetOneFloat("uscale", 1.f); t.sv = d.GetOneFloat("vscale", 1.f); t.du = d.GetOneFloat("udelta", 0.f); t.dv = d.GetOneFloat("vdelta", 0.f);

@@ -518,9 +518,9 @@ extern "C" int bpt_scene_set_textures(bpt_engine *e, const bpt_texture *t, int n
     e->textures.resize(n);
     for (int i = 0; i < n; ++i) {
         const bpt_texture &b = t[i];
-        if (b.kind == BPT_TEXTURE_CONSTANT || b.kind == BPT_TEXTURE_SCALE || b.kind == BPT_TEXTURE_MIX) {
+        if (b.kind == BPT_TEXTURE_CONSTANT || b.kind == BPT_TEXTURE_SCALE || b.kind == BPT_TEXTURE_MIX || b.kind == BPT_TEXTURE_CHECKERBOARD) {
             // image-less classes: children are earlier entries
-            const int nch = b.kind == BPT_TEXTURE_CONSTANT ? 0 : b.kind == BPT_TEXTURE_SCALE ? 2 : 3;
+            const int nch = b.kind == BPT_TEXTURE_CONSTANT ? 0 : b.kind == BPT_TEXTURE_MIX ? 3 : 2;
             const int ch[3] = {b.tex1, b.tex2, b.tex3};
             for (int k = 0; k < nch; ++k) if (ch[k] < 1 || ch[k] > i) return e->fail(BPT_ERR_INVALID, "texture refers to a texture that is not defined before it");
             OwnedTexture &o = e->textures[i];
@@ -528,7 +528,7 @@ extern "C" int bpt_scene_set_textures(bpt_engine *e, const bpt_texture *t, int n
             o.value.Set(b.value_s);
             continue;
         }
-        if (b.kind != BPT_TEXTURE_IMAGEMAP && b.kind != BPT_TEXTURE_NORMALMAP) return e->fail(BPT_ERR_UNSUPPORTED, "texture class not implemented (imagemap, constant, scale, mix)");
+        if (b.kind != BPT_TEXTURE_IMAGEMAP && b.kind != BPT_TEXTURE_NORMALMAP) return e->fail(BPT_ERR_UNSUPPORTED, "texture class not implemented (imagemap, constant, scale, mix, checkerboard)");
         if (!b.pixels || b.xres <= 0 || b.yres <= 0 || (b.n_channels != 1 && b.n_channels != 3 && b.n_channels != 4))
             return e->fail(BPT_ERR_INVALID, "texture image: 1, 3 or 4 channels of 8-bit or float texels expected");
         if (b.format != BPT_IMAGE_U8 && b.format != BPT_IMAGE_F32) return e->fail(BPT_ERR_UNSUPPORTED, "texture image format not implemented (8-bit, float)");
@@ -1449,11 +1449,18 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
                 }
                 continue;
             }
-            if (tb.kind == BPT_TEXTURE_SCALE || tb.kind == BPT_TEXTURE_MIX) {
+            if (tb.kind == BPT_TEXTURE_SCALE || tb.kind == BPT_TEXTURE_MIX || tb.kind == BPT_TEXTURE_CHECKERBOARD) {
                 auto isFloat = [&](int id) { return e->textures[id].t.is_spectrum == 0 && e->textures[id].t.kind != BPT_TEXTURE_NORMALMAP; };
                 auto sameType = [&](int id) { return (e->textures[id].t.is_spectrum != 0) == (tb.is_spectrum != 0) && e->textures[id].t.kind != BPT_TEXTURE_NORMALMAP; };
                 DeviceTexture &d = dtex[i];
-                if (tb.kind == BPT_TEXTURE_MIX) {
+                if (tb.kind == BPT_TEXTURE_CHECKERBOARD) {   // tex[0] where the weight is 0, tex[1] where it is 1 (textures.h:372-415)
+                    int t1 = tb.tex1 - 1, t2 = tb.tex2 - 1;
+                    if (!sameType(t1) || !sameType(t2)) return e->fail(BPT_ERR_INVALID, "checkerboard texture: value types of tex1 / tex2 do not fit");
+                    std::memset(&d, 0, sizeof(d));
+                    d.kind = TEXKIND_CHECKERBOARD; d.child0 = t1; d.child1 = t2; d.child2 = -1;
+                    d.su = tb.su; d.sv = tb.sv; d.du = tb.du; d.dv = tb.dv;
+                    depth[i] = 1 + std::max(depth[t1], depth[t2]);
+                } else if (tb.kind == BPT_TEXTURE_MIX) {
                     int t1 = tb.tex1 - 1, t2 = tb.tex2 - 1, am = tb.tex3 - 1;
                     if (!sameType(t1) || !sameType(t2) || !isFloat(am)) return e->fail(BPT_ERR_INVALID, "mix texture: value types of tex1 / tex2 / amount do not fit");
                     std::memset(&d, 0, sizeof(d));

@@ -322,9 +322,15 @@ struct Frontend {
             if (c.value_s.kind == BPT_SPEC_NONE) { c.value_s.kind = BPT_SPEC_CONSTANT; c.value_s.value = dflt; }
             textures.push_back(c); *id = (int)textures.size(); return true;
         };
-        if (a[2] == "constant" || a[2] == "scale" || a[2] == "mix") {
+        if (a[2] == "constant" || a[2] == "scale" || a[2] == "mix" || a[2] == "checkerboard") {
             bpt_texture t; std::memset(&t, 0, sizeof(t));
             t.is_spectrum = spec;
+            if (a[2] == "checkerboard") {   // Float / SpectrumCheckerboardTexture::Create (textures.cpp:219-280), two-dimensional
+                if (pl.i("dimension", 2) != 2 || pl.s("mapping", "uv") != "uv") { err = "only the two-dimensional checkerboard with \"uv\" mapping is supported"; return false; }
+                t.kind = BPT_TEXTURE_CHECKERBOARD;
+                if (!(spec ? spectrumChild("tex1", 1.f, &t.tex1) : floatChild("tex1", 1.f, &t.tex1)) || !(spec ? spectrumChild("tex2", 0.f, &t.tex2) : floatChild("tex2", 0.f, &t.tex2))) return false;
+                t.su = pl.f("uscale", 1.f); t.sv = pl.f("vscale", 1.f); t.du = pl.f("udelta", 0.f); t.dv = pl.f("vdelta", 0.f);
+            } else
             if (a[2] == "constant") {
                 t.kind = BPT_TEXTURE_CONSTANT;
                 if (spec) { if (!getSpectrum(pl, "value", &t.value_s)) return false; if (t.value_s.kind == BPT_SPEC_NONE) { t.value_s.kind = BPT_SPEC_CONSTANT; t.value_s.value = 1.f; } }
@@ -341,7 +347,7 @@ struct Frontend {
             names[a[0]] = (int)textures.size();
             return true;
         }
-        if (a[2] != "imagemap") { err = "texture class \"" + a[2] + "\" is not supported by this front end (imagemap, constant, scale, mix)"; return false; }
+        if (a[2] != "imagemap") { err = "texture class \"" + a[2] + "\" is not supported by this front end (imagemap, constant, scale, mix, checkerboard)"; return false; }
         if (pl.s("mapping", "uv") != "uv") { err = "only the \"uv\" texture mapping is supported"; return false; }
         bpt_texture t; std::memset(&t, 0, sizeof(t));
         t.su = pl.f("uscale", 1.f); t.sv = pl.f("vscale", 1.f); t.du = pl.f("udelta", 0.f); t.dv = pl.f("vdelta", 0.f);

@@ -79,7 +79,7 @@ struct DeviceTexture {
     float cval;                // constant float
     SpectrumRec sval;          // constant spectrum
 };
-enum { TEXKIND_IMAGEMAP = 0, TEXKIND_CONSTANT = 2, TEXKIND_SCALE = 3, TEXKIND_MIX = 4 };
+enum { TEXKIND_IMAGEMAP = 0, TEXKIND_CONSTANT = 2, TEXKIND_SCALE = 3, TEXKIND_MIX = 4, TEXKIND_CHECKERBOARD = 5 };
 
 struct DeviceMaterial {
     int type;                  // MaterialTag

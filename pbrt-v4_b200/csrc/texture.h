@@ -206,6 +206,18 @@ BPT_HD Spec EvalSpectrumImageTexture(const SceneView &sv, const DeviceTexture &t
 // FloatMixTexture / SpectrumMixTexture textures.h:199-260).  The engine bounds the depth at commit (kTexMaxDepth); the recursion is
 // unrolled by the template.
 constexpr int kTexMaxDepth = 3;
+// Checkerboard(ctx, map2D, nullptr) (textures.cpp:183-207): the box-filtered weight of the second texture
+BPT_HD float CheckerboardWeight(const DeviceTexture &t, const TexEvalCtx &ctx) {
+    auto d = [](float x) { float y = x / 2 - floorf(x / 2) - 0.5f; return x / 2 + y * (1 - 2 * fabsf(y)); };
+    auto bf = [&](float x, float r) -> float {
+        if (floorf(x - r) == floorf(x + r)) return (float)(1 - 2 * ((int)floorf(x) & 1));
+        return (d(x + r) - 2 * d(x) + d(x - r)) / Sqr(r);
+    };
+    TexCoord2D c = UVMap(t, ctx);
+    float ds = stdmax(fabsf(c.dsdx), fabsf(c.dsdy)), dt = stdmax(fabsf(c.dtdx), fabsf(c.dtdy));
+    ds *= 1.5f; dt *= 1.5f;
+    return 0.5f - bf(c.st.x, ds) * bf(c.st.y, dt) / 2;
+}
 template <int DEPTH> BPT_HD float EvalFloatTexture(const SceneView &sv, int id, const TexEvalCtx &ctx) {
     const DeviceTexture &t = sv.textures[id];
     if (t.kind == TEXKIND_IMAGEMAP) return EvalFloatImageTexture(sv, t, ctx);
@@ -217,8 +229,8 @@ template <int DEPTH> BPT_HD float EvalFloatTexture(const SceneView &sv, int id, 
             if (sc == 0) return 0;
             return EvalFloatTexture<D>(sv, t.child0, ctx) * sc;
         }
-        if (t.kind == TEXKIND_MIX) {
-            float amt = EvalFloatTexture<D>(sv, t.child2, ctx);
+        if (t.kind == TEXKIND_MIX || t.kind == TEXKIND_CHECKERBOARD) {
+            float amt = t.kind == TEXKIND_MIX ? EvalFloatTexture<D>(sv, t.child2, ctx) : CheckerboardWeight(t, ctx);
             float t1 = 0, t2 = 0;
             if (amt != 1) t1 = EvalFloatTexture<D>(sv, t.child0, ctx);
             if (amt != 0) t2 = EvalFloatTexture<D>(sv, t.child1, ctx);
@@ -238,8 +250,8 @@ template <int DEPTH> BPT_HD Spec EvalSpectrumTexture(const SceneView &sv, int id
             if (sc == 0) return Spec(0.f);
             return EvalSpectrumTexture<D>(sv, t.child0, ctx, wl, spectrumType) * sc;
         }
-        if (t.kind == TEXKIND_MIX) {
-            float amt = EvalFloatTexture<D>(sv, t.child2, ctx);
+        if (t.kind == TEXKIND_MIX || t.kind == TEXKIND_CHECKERBOARD) {
+            float amt = t.kind == TEXKIND_MIX ? EvalFloatTexture<D>(sv, t.child2, ctx) : CheckerboardWeight(t, ctx);
             Spec t1(0.f), t2(0.f);
             if (amt != 1) t1 = EvalSpectrumTexture<D>(sv, t.child0, ctx, wl, spectrumType);
             if (amt != 0) t2 = EvalSpectrumTexture<D>(sv, t.child1, ctx, wl, spectrumType);

@@ -166,6 +166,10 @@ TEXTURE_SETS = {
                   'Texture "r" "float" "scale" "texture tex" "m" "float scale" 0.5\nTexture "r2" "float" "mix" "texture tex1" "r" "float tex2" 0.05 "float amount" 0.3\n'
                   'Texture "c" "spectrum" "constant" "rgb value" [0.7 0.6 0.3]\n',
                   'Material "coateddiffuse" "texture reflectance" "one" "texture roughness" "r2"\n'),
+    "checkerboard": ('Texture "alb" "spectrum" "imagemap" "string filename" "albedo.png"\n'
+                     'Texture "chk" "spectrum" "checkerboard" "float uscale" 7 "float vscale" 5.5 "float udelta" 0.1 "texture tex1" "alb" "rgb tex2" [0.08 0.1 0.3]\n'
+                     'Texture "fchk" "float" "checkerboard" "float uscale" 3 "float vscale" 3 "float tex1" 0.02 "float tex2" 0.35\n',
+                     'Material "conductor" "texture reflectance" "chk" "texture roughness" "fchk"\n'),
     "normalmap": ('Texture "alb" "spectrum" "imagemap" "string filename" "albedo.png"\n', 'Material "diffuse" "texture reflectance" "alb" "string normalmap" "normals.png"\n'),
     "bump_dielectric": ('Texture "h" "float" "imagemap" "string filename" "height.pfm" "float uscale" 3 "float vscale" 3 "string filter" "trilinear"\n',
                         'Material "dielectric" "float eta" 1.5 "float roughness" 0.15 "texture displacement" "h"\n'),

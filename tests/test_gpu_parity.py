@@ -418,7 +418,7 @@ def test_delta_lights_through_media_match_the_live_reference(E, tmp_path):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/bin/pbrt not on this box")
-@pytest.mark.parametrize("which", ["albedo", "trilinear", "ewa", "point", "grey", "roughness", "bump", "bump_dielectric", "normalmap", "scale_mix"])
+@pytest.mark.parametrize("which", ["albedo", "trilinear", "ewa", "point", "grey", "roughness", "bump", "bump_dielectric", "normalmap", "scale_mix", "checkerboard"])
 def test_image_textures_and_bump_mapping_match_the_live_reference(E, tmp_path, which):
     """f1: Texture "imagemap" (float and spectrum; PNG 8-bit sRGB / linear, PFM float; point / bilinear / trilinear / EWA; repeat /
     clamp / black; scale, invert, uv scale and offset) on reflectance, transmittance and roughness parameters, and bump mapping

@@ -76,6 +76,11 @@ static std::string Tex(const std::vector<Texture> &tx, const char *what, int id)
     const bpt_texture &t = tx[id - 1].t;
     char b[320];
     if (t.kind == BPT_TEXTURE_CONSTANT) return std::string(" ") + what + "=const{" + (t.is_spectrum ? S(tx[id - 1].value) : F(t.value_f)) + "}";
+    if (t.kind == BPT_TEXTURE_CHECKERBOARD) {
+        if (t.tex1 >= id || t.tex2 >= id) return std::string(" ") + what + "=checkerboard{BAD}";
+        return std::string(" ") + what + "=checkerboard{" + (t.is_spectrum ? "spectrum" : "float") + " uv=" + F(t.su) + "," + F(t.sv) + "," + F(t.du) + "," + F(t.dv) + Tex(tx, "tex1", t.tex1) +
+               Tex(tx, "tex2", t.tex2) + "}";
+    }
     if (t.kind == BPT_TEXTURE_SCALE || t.kind == BPT_TEXTURE_MIX) {
         const bool bad = t.tex1 >= id || t.tex2 >= id || t.tex3 >= id;   // children come first
         std::string r = std::string(" ") + what + (t.kind == BPT_TEXTURE_SCALE ? "=scale{" : "=mix{") + (t.is_spectrum ? "spectrum" : "float");
@@ -146,7 +151,7 @@ int bpt_scene_set_textures(bpt_engine *e, const bpt_texture *t, int n) {
     e->textures.resize(n);
     for (int i = 0; i < n; ++i) {
         e->textures[i].t = t[i];
-        if (t[i].kind == BPT_TEXTURE_CONSTANT || t[i].kind == BPT_TEXTURE_SCALE || t[i].kind == BPT_TEXTURE_MIX) { e->textures[i].value = Own(t[i].value_s); e->textures[i].hash = 0; continue; }
+        if (t[i].kind == BPT_TEXTURE_CONSTANT || t[i].kind == BPT_TEXTURE_SCALE || t[i].kind == BPT_TEXTURE_MIX || t[i].kind == BPT_TEXTURE_CHECKERBOARD) { e->textures[i].value = Own(t[i].value_s); e->textures[i].hash = 0; continue; }
         const size_t es = t[i].format == BPT_IMAGE_U8 ? 1 : 4, bytes = (size_t)t[i].xres * t[i].yres * t[i].n_channels * es;
         if (t[i].kind == BPT_TEXTURE_NORMALMAP && t[i].n_channels == 4) {
             uint64_t h = 1469598103934665603ull;
