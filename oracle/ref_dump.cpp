@@ -126,6 +126,17 @@ static void DumpTables(const char *path) {
     const float *cd = &sRGBToSpectrumTable_Data[0][0][0][0][0];
     b.f32("rgb2spec_srgb_coeffs", std::vector<float>(cd, cd + 3 * 64 * 64 * 64 * 3));
     b.u32("sobol32_2x52", std::vector<uint32_t>(SobolMatrices32, SobolMatrices32 + 2 * SobolMatrixSize));
+    b.u32("sobol32_full", std::vector<uint32_t>(SobolMatrices32, SobolMatrices32 + NSobolDimensions * SobolMatrixSize));
+    {   // SobolIntervalToIndex's matrices, 25 rows of 52 64-bit columns each, as (low, high) 32-bit pairs
+        std::vector<uint32_t> v, vi;
+        for (int r = 0; r < 25; ++r)
+            for (int c = 0; c < SobolMatrixSize; ++c) {
+                v.push_back((uint32_t)VdCSobolMatrices[r][c]); v.push_back((uint32_t)(VdCSobolMatrices[r][c] >> 32));
+                vi.push_back((uint32_t)VdCSobolMatricesInv[r][c]); vi.push_back((uint32_t)(VdCSobolMatricesInv[r][c] >> 32));
+            }
+        b.u32("vdc_sobol", v);
+        b.u32("vdc_sobol_inv", vi);
+    }
     b.f32("mip_filter_lut", std::vector<float>(MIPFilterLUT, MIPFilterLUT + MIPFilterLUTSize));
     b.f32("srgb8_to_linear", std::vector<float>(SRGBToLinearLUT, SRGBToLinearLUT + 256));
     // named spectra (piecewise linear): lambdas then values

@@ -67,7 +67,7 @@ BPT_HD CamSample GetCameraSample(const SamplerParams &sp, const DeviceFilter &fi
     CamSample cs;
     sampler.StartPixelSample(&sp, px, py, sampleIndex, 0);
     cs.lu = sampler.Get1D();
-    Vec2 uf = sampler.Get2D();
+    Vec2 uf = sampler.GetPixel2D();
     Vec2 fp;
     if (filter.sampled == 2) {   // TriangleFilter::Sample (filters.h:224-227): SampleTent per axis, weight 1
         fp = Vec2(SampleTent(uf.x, filter.radiusX), SampleTent(uf.y, filter.radiusY));

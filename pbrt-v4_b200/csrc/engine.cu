@@ -180,6 +180,8 @@ struct bpt_engine {
     DevBuf<int> indexPool;
     DevBuf<float> nPool, uvPool, specPool;
     DevBuf<DeviceMaterial> dMaterials;
+    DevBuf<uint32_t> dSobolFull;
+    DevBuf<uint64_t> dVdc, dVdcInv;
     std::vector<OwnedTexture> textures;
     DevBuf<float> dTexels, dEwaLUT;
     DevBuf<DeviceMIPLevel> dMipLevels;
@@ -484,8 +486,9 @@ extern "C" int bpt_scene_set_filter(bpt_engine *e, const bpt_filter *f) {
 }
 extern "C" int bpt_scene_set_sampler(bpt_engine *e, const bpt_sampler *s) {
     if (!e || !s) return BPT_ERR_INVALID;
-    if (s->type != BPT_SAMPLER_ZSOBOL && s->type != BPT_SAMPLER_INDEPENDENT && s->type != BPT_SAMPLER_STRATIFIED && s->type != BPT_SAMPLER_PADDED_SOBOL)
-        return e->fail(BPT_ERR_UNSUPPORTED, "sampler not implemented (zsobol, independent, stratified, paddedsobol)");
+    if (s->type != BPT_SAMPLER_ZSOBOL && s->type != BPT_SAMPLER_INDEPENDENT && s->type != BPT_SAMPLER_STRATIFIED && s->type != BPT_SAMPLER_PADDED_SOBOL &&
+        s->type != BPT_SAMPLER_SOBOL)
+        return e->fail(BPT_ERR_UNSUPPORTED, "sampler not implemented (zsobol, sobol, paddedsobol, stratified, independent)");
     e->sampler = *s;
     if (s->type == BPT_SAMPLER_STRATIFIED) {
         if (s->x_samples <= 0 || s->y_samples <= 0) return e->fail(BPT_ERR_INVALID, "stratified sampler: xsamples and ysamples must be positive");
@@ -758,7 +761,19 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
 
     // ---- sampler (samplers.h:228-239)
     SamplerParams sp{};
-    sp.type = e->sampler.type == BPT_SAMPLER_ZSOBOL ? 0 : e->sampler.type == BPT_SAMPLER_STRATIFIED ? 2 : e->sampler.type == BPT_SAMPLER_PADDED_SOBOL ? 3 : 1;
+    sp.type = e->sampler.type == BPT_SAMPLER_ZSOBOL ? 0 : e->sampler.type == BPT_SAMPLER_STRATIFIED ? 2 : e->sampler.type == BPT_SAMPLER_PADDED_SOBOL ? 3 :
+              e->sampler.type == BPT_SAMPLER_SOBOL ? 4 : 1;
+    if (sp.type == 4) {   // SobolSampler (samplers.h:482-490): the full generator matrices and SobolIntervalToIndex's matrices
+        if (!e->tables.u32.count("sobol32_full") || !e->tables.u32.count("vdc_sobol") || !e->tables.u32.count("vdc_sobol_inv"))
+            return e->fail(BPT_ERR_IO, "tables blob lacks the Sobol' sampler tables (regenerate it with oracle/_ref/bin/ref_dump tables)");
+        auto pairs = [](const std::vector<uint32_t> &v) { std::vector<uint64_t> o(v.size() / 2); for (size_t i = 0; i < o.size(); ++i) o[i] = (uint64_t)v[2 * i] | ((uint64_t)v[2 * i + 1] << 32); return o; };
+        ECK(e->dSobolFull.upload(e->tables.u32.at("sobol32_full")));
+        ECK(e->dVdc.upload(pairs(e->tables.u32.at("vdc_sobol"))));
+        ECK(e->dVdcInv.upload(pairs(e->tables.u32.at("vdc_sobol_inv"))));
+        sp.sobolFull = e->dSobolFull.p; sp.vdc = e->dVdc.p; sp.vdcInv = e->dVdcInv.p;
+        int scale = 1; while (scale < std::max(fl.xres, fl.yres)) scale <<= 1;
+        sp.scale = scale; sp.log2Scale = 0; while ((1 << sp.log2Scale) < scale) ++sp.log2Scale;
+    }
     sp.xSamples = e->sampler.x_samples; sp.ySamples = e->sampler.y_samples; sp.jitter = e->sampler.jitter;
     sp.randomize = e->sampler.randomize;
     sp.seed = e->sampler.seed;

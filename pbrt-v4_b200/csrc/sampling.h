@@ -189,7 +189,7 @@ BPT_HD uint64_t Hash_pixel_dim_seed(int px, int py, int dimension, int seed) {
 }
 
 struct SamplerParams {
-    int type;                  // 0 = zsobol, 1 = independent, 2 = stratified, 3 = paddedsobol
+    int type;                  // 0 = zsobol, 1 = independent, 2 = stratified, 3 = paddedsobol, 4 = sobol
     int xSamples, ySamples, jitter;   // stratified (samplers.h:568-625)
     int randomize;             // RandomizeStrategy
     int seed;
@@ -201,6 +201,11 @@ struct SamplerParams {
     // for every sample of the pixel, so they are computed once per frame (k_zsobol_prefix) instead of once per Get1D/Get2D call.
     const uint32_t *prefix;
     int prefixDims, prefixW, prefixH, nLowDigits;
+    // SobolSampler (samplers.h:479-565): all 1024 generator matrices and the van der Corput / Sobol' index matrices of
+    // SobolIntervalToIndex (util/sobolmatrices.cpp), in global memory; scale = RoundUpPow2(max(full resolution))
+    const uint32_t *sobolFull;   // [1024][52]
+    const uint64_t *vdc, *vdcInv;   // [25][52]
+    int log2Scale, scale;
 };
 
 // BPT_OUTLINE_SAMPLER (device, the translation unit that owns the Sobol tables): ZSobol Get1D / Get2D as ONE real function
@@ -225,11 +230,24 @@ struct Sampler {
     int pixel;   // index into SamplerParams::prefix, -1: no table / pixel outside the film
     int px, py, sampleIndex;   // stratified / paddedsobol
     RNG rng;   // independent and stratified samplers
+    int64_t sobolIndex;   // SobolSampler
     BPT_HD void StartPixelSample(const SamplerParams *params, int pxIn, int pyIn, int index, int dim) {
         sp = params;
         dimension = dim;
         pixel = -1;
         px = pxIn; py = pyIn; sampleIndex = index;
+        if (sp->type == 4) {   // SobolSampler::StartPixelSample (samplers.h:502-506) + SobolIntervalToIndex (lowdiscrepancy.h:266-287)
+            dimension = dim > 2 ? dim : 2;
+            const uint32_t m = (uint32_t)sp->log2Scale;
+            uint64_t frame = (uint64_t)index;
+            if (m == 0) { sobolIndex = (int64_t)frame; return; }
+            uint64_t idx = frame << (m << 1), delta = 0;
+            for (int c = 0; frame; frame >>= 1, ++c) if (frame & 1) delta ^= sp->vdc[(m - 1) * 52 + c];
+            uint64_t b = ((((uint64_t)(uint32_t)pxIn) << m) | (uint32_t)pyIn) ^ delta;
+            for (int c = 0; b; b >>= 1, ++c) if (b & 1) idx ^= sp->vdcInv[(m - 1) * 52 + c];
+            sobolIndex = (int64_t)idx;
+            return;
+        }
         if (sp->type == 0) {
             mortonIndex = (EncodeMorton2((uint32_t)pxIn, (uint32_t)pyIn) << sp->log2SamplesPerPixel) | (uint64_t)index;
             if (sp->prefix && pxIn >= 0 && pyIn >= 0 && pxIn < sp->prefixW && pyIn < sp->prefixH) pixel = pyIn * sp->prefixW + pxIn;
@@ -305,7 +323,33 @@ struct Sampler {
         dimension += 2;
         return {SobolSampleRand((uint64_t)index, 0, sp->randomize, (uint32_t)hash), SobolSampleRand((uint64_t)index, 1, sp->randomize, (uint32_t)(hash >> 32))};
     }
+    // SobolSampler::SampleDimension (samplers.h:544-557); randomize < 0: NoRandomizer
+    BPT_HD float SobolDimension(int dim, int randomize) const {
+        const uint32_t *C = sp->sobolFull + (size_t)dim * 52;
+        uint32_t v = 0;
+        uint64_t a = (uint64_t)sobolIndex;
+        for (int i = 0; a != 0; a >>= 1, i++) if (a & 1) v ^= C[i];
+        if (randomize > 0) {
+            uint32_t hash = (uint32_t)Hash_i32x2(dim, sp->seed);
+            if (randomize == RANDOMIZE_PERMUTE_DIGITS) v = hash ^ v;
+            else if (randomize == RANDOMIZE_FAST_OWEN) v = FastOwenScramble(v, hash);
+            else v = OwenScramble(v, hash);
+        }
+        return stdmin((float)v * 0x1p-32f, kOneMinusEpsilon);
+    }
+    // Sampler::GetPixel2D: the film-plane sample of GetCameraSample (samplers.h:797-814); only SobolSampler (:525-536) has its own
+    BPT_HD Vec2 GetPixel2D() {
+        if (sp->type != 4) return Get2D();
+        float u[2] = {SobolDimension(0, 0), SobolDimension(1, 0)};
+        const int pix[2] = {px, py};
+        for (int d = 0; d < 2; ++d) u[d] = Clampf(u[d] * sp->scale - pix[d], 0.f, kOneMinusEpsilon);
+        return {u[0], u[1]};
+    }
     BPT_HD float Get1D() {
+        if (sp->type == 4) {
+            if (dimension >= 1024) dimension = 2;
+            return SobolDimension(dimension++, sp->randomize);
+        }
         if (sp->type == 1) { ++dimension; return rng.UniformFloat(); }
         if (sp->type >= 2) return OtherGet1D();
 #if BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
@@ -319,6 +363,12 @@ struct Sampler {
         return SobolSampleRand(sampleIndex, 0, sp->randomize, sampleHash);
     }
     BPT_HD Vec2 Get2D() {
+        if (sp->type == 4) {
+            if (dimension + 1 >= 1024) dimension = 2;
+            Vec2 u(SobolDimension(dimension, sp->randomize), SobolDimension(dimension + 1, sp->randomize));
+            dimension += 2;
+            return u;
+        }
         if (sp->type == 1) { dimension += 2; float a = rng.UniformFloat(); float b = rng.UniformFloat(); return {a, b}; }
         if (sp->type >= 2) return OtherGet2D();
 #if BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)

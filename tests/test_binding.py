@@ -67,7 +67,8 @@ def _scenes():
         open(p, "w").write(txt[:a] + "Sampler " + smp + txt[b:])
         return p
     for k, smp in enumerate(['"paddedsobol" "integer pixelsamples" 8', '"paddedsobol" "integer pixelsamples" 4 "string randomization" "owen"',
-                             '"stratified" "integer xsamples" 3 "integer ysamples" 2', '"stratified" "bool jitter" false', '"independent" "integer pixelsamples" 5']):
+                             '"stratified" "integer xsamples" 3 "integer ysamples" 2', '"stratified" "bool jitter" false', '"independent" "integer pixelsamples" 5',
+                             '"sobol" "integer pixelsamples" 8 "string randomization" "owen"']):
         cases["sampler_%d" % k] = (lambda d, smp=smp: with_sampler(d, smp))
     def with_camera(d, cam):
         p = scenes.cornell(d, res=(32, 32), spp=1)
