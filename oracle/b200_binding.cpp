@@ -324,7 +324,7 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
         s.spp = d.GetOneInt("pixelsamples", 16);
         if (Options->pixelSamples) s.spp = *Options->pixelSamples;
         s.seed = d.GetOneInt("seed", Options->seed);
-        std::string r = d.GetOneString("randomization", "fastowen");
+        std::string r = d.GetOneString("randomization", s.type == BPT_SAMPLER_HALTON ? "permutedigits" : "fastowen");
         s.randomize = r == "none" ? BPT_RANDOMIZE_NONE : r == "permutedigits" ? BPT_RANDOMIZE_PERMUTE_DIGITS : r == "owen" ? BPT_RANDOMIZE_OWEN : BPT_RANDOMIZE_FAST_OWEN;
         if (s.type == BPT_SAMPLER_STRATIFIED) {   // StratifiedSampler::Create (samplers.cpp:297-319)
             s.jitter = d.GetOneBool("jitter", true);

@@ -180,6 +180,10 @@ struct bpt_engine {
     DevBuf<int> indexPool;
     DevBuf<float> nPool, uvPool, specPool;
     DevBuf<DeviceMaterial> dMaterials;
+    DevBuf<int> dPrimes;
+    DevBuf<uint16_t> dHaltonPerms;
+    DevBuf<uint32_t> dHaltonPermOffset;
+    int haltonPermSeed = 0;
     DevBuf<uint32_t> dSobolFull;
     DevBuf<uint64_t> dVdc, dVdcInv;
     std::vector<OwnedTexture> textures;
@@ -487,8 +491,9 @@ extern "C" int bpt_scene_set_filter(bpt_engine *e, const bpt_filter *f) {
 extern "C" int bpt_scene_set_sampler(bpt_engine *e, const bpt_sampler *s) {
     if (!e || !s) return BPT_ERR_INVALID;
     if (s->type != BPT_SAMPLER_ZSOBOL && s->type != BPT_SAMPLER_INDEPENDENT && s->type != BPT_SAMPLER_STRATIFIED && s->type != BPT_SAMPLER_PADDED_SOBOL &&
-        s->type != BPT_SAMPLER_SOBOL)
-        return e->fail(BPT_ERR_UNSUPPORTED, "sampler not implemented (zsobol, sobol, paddedsobol, stratified, independent)");
+        s->type != BPT_SAMPLER_SOBOL && s->type != BPT_SAMPLER_HALTON)
+        return e->fail(BPT_ERR_UNSUPPORTED, "sampler not implemented (zsobol, sobol, paddedsobol, halton, stratified, independent)");
+    if (s->type == BPT_SAMPLER_HALTON && s->randomize == BPT_RANDOMIZE_FAST_OWEN) return e->fail(BPT_ERR_INVALID, "\"fastowen\" randomization not supported by Halton sampler");
     e->sampler = *s;
     if (s->type == BPT_SAMPLER_STRATIFIED) {
         if (s->x_samples <= 0 || s->y_samples <= 0) return e->fail(BPT_ERR_INVALID, "stratified sampler: xsamples and ysamples must be positive");
@@ -762,7 +767,44 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     // ---- sampler (samplers.h:228-239)
     SamplerParams sp{};
     sp.type = e->sampler.type == BPT_SAMPLER_ZSOBOL ? 0 : e->sampler.type == BPT_SAMPLER_STRATIFIED ? 2 : e->sampler.type == BPT_SAMPLER_PADDED_SOBOL ? 3 :
-              e->sampler.type == BPT_SAMPLER_SOBOL ? 4 : 1;
+              e->sampler.type == BPT_SAMPLER_SOBOL ? 4 : e->sampler.type == BPT_SAMPLER_HALTON ? 5 : 1;
+    if (sp.type == 5) {   // HaltonSampler::HaltonSampler (samplers.cpp:32-52), ComputeRadicalInversePermutations (lowdiscrepancy.cpp:47-55)
+        std::vector<int> primes;
+        for (int k = 2; primes.size() < 1000; ++k) { bool pr = true; for (int q : primes) { if (q * q > k) break; if (k % q == 0) { pr = false; break; } } if (pr) primes.push_back(k); }
+        ECK(e->dPrimes.upload(primes));
+        sp.primes = e->dPrimes.p;
+        if (sp.randomize == RANDOMIZE_PERMUTE_DIGITS && (e->haltonPermSeed != sp.seed || e->dHaltonPerms.n == 0)) {
+            std::vector<uint16_t> perms;
+            std::vector<uint32_t> offsets(primes.size());
+            for (size_t i = 0; i < primes.size(); ++i) {
+                const int base = primes[i];
+                int nDigits = 0;
+                float invBase = (float)1 / (float)base, invBaseM = 1;
+                while (1 - (base - 1) * invBaseM < 1) { ++nDigits; invBaseM *= invBase; }
+                offsets[i] = (uint32_t)perms.size();
+                for (int digitIndex = 0; digitIndex < nDigits; ++digitIndex) {
+                    // Hash(base, digitIndex, seed): the three 32-bit arguments packed back to back (util/hash.h:99-107)
+                    uint64_t w[2] = {(uint64_t)(uint32_t)base | ((uint64_t)(uint32_t)digitIndex << 32), (uint64_t)(uint32_t)sp.seed};
+                    uint64_t dseed = MurmurHash64A(w, 12, 0);
+                    for (int digitValue = 0; digitValue < base; ++digitValue) perms.push_back((uint16_t)PermutationElement((uint32_t)digitValue, (uint32_t)base, (uint32_t)dseed));
+                }
+            }
+            ECK(e->dHaltonPerms.upload(perms));
+            ECK(e->dHaltonPermOffset.upload(offsets));
+            e->haltonPermSeed = sp.seed;
+        }
+        sp.haltonPerms = e->dHaltonPerms.p; sp.haltonPermOffset = e->dHaltonPermOffset.p;
+        const int fullRes[2] = {fl.xres, fl.yres};
+        for (int i = 0; i < 2; ++i) {
+            int base = (i == 0) ? 2 : 3, scale = 1, exp = 0;
+            while (scale < std::min(fullRes[i], 128)) { scale *= base; ++exp; }
+            sp.baseScales[i] = scale; sp.baseExponents[i] = exp;
+        }
+        struct G { static void ext(uint64_t a, uint64_t b, int64_t *x, int64_t *y) { if (b == 0) { *x = 1; *y = 0; return; } int64_t d = (int64_t)(a / b), xp, yp; ext(b, a % b, &xp, &yp); *x = yp; *y = xp - (d * yp); } };
+        auto multiplicativeInverse = [](int64_t a, int64_t n) { int64_t x, y; G::ext((uint64_t)a, (uint64_t)n, &x, &y); int64_t r = x - (x / n) * n; return (int)(r < 0 ? r + n : r); };
+        sp.multInverse[0] = multiplicativeInverse(sp.baseScales[1], sp.baseScales[0]);
+        sp.multInverse[1] = multiplicativeInverse(sp.baseScales[0], sp.baseScales[1]);
+    }
     if (sp.type == 4) {   // SobolSampler (samplers.h:482-490): the full generator matrices and SobolIntervalToIndex's matrices
         if (!e->tables.u32.count("sobol32_full") || !e->tables.u32.count("vdc_sobol") || !e->tables.u32.count("vdc_sobol_inv"))
             return e->fail(BPT_ERR_IO, "tables blob lacks the Sobol' sampler tables (regenerate it with oracle/_ref/bin/ref_dump tables)");

@@ -785,15 +785,17 @@ bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::st
         std::string ty = a.empty() ? "zsobol" : a[0];
         if (ty == "zsobol") sampler.type = BPT_SAMPLER_ZSOBOL; else if (ty == "independent") sampler.type = BPT_SAMPLER_INDEPENDENT;
         else if (ty == "paddedsobol") sampler.type = BPT_SAMPLER_PADDED_SOBOL; else if (ty == "stratified") sampler.type = BPT_SAMPLER_STRATIFIED;
-        else if (ty == "sobol") sampler.type = BPT_SAMPLER_SOBOL;
-        else { err = "sampler \"" + ty + "\" is not supported (zsobol, sobol, paddedsobol, stratified, independent)"; return false; }
+        else if (ty == "sobol") sampler.type = BPT_SAMPLER_SOBOL; else if (ty == "halton") sampler.type = BPT_SAMPLER_HALTON;
+        else { err = "sampler \"" + ty + "\" is not supported (zsobol, sobol, paddedsobol, halton, stratified, independent)"; return false; }
         sampler.spp = pl.i("pixelsamples", 16); sampler.seed = pl.i("seed", seedOption);
         if (sampler.type == BPT_SAMPLER_STRATIFIED) {   // StratifiedSampler::Create (samplers.cpp:297-319)
             sampler.jitter = pl.b("jitter", true);
             sampler.x_samples = pl.i("xsamples", 4); sampler.y_samples = pl.i("ysamples", 4);
             sampler.spp = sampler.x_samples * sampler.y_samples;
         }
-        std::string r = pl.s("randomization", "fastowen");
+        // (HaltonSampler::Create, samplers.cpp:77-88: permutedigits by default, no fastowen)
+        std::string r = pl.s("randomization", sampler.type == BPT_SAMPLER_HALTON ? "permutedigits" : "fastowen");
+        if (sampler.type == BPT_SAMPLER_HALTON && r == "fastowen") { err = "\"fastowen\" randomization not supported by Halton sampler"; return false; }
         sampler.randomize = r == "none" ? BPT_RANDOMIZE_NONE : r == "permutedigits" ? BPT_RANDOMIZE_PERMUTE_DIGITS : r == "owen" ? BPT_RANDOMIZE_OWEN : BPT_RANDOMIZE_FAST_OWEN;
         haveSampler = true; return true;
     }

@@ -189,7 +189,7 @@ BPT_HD uint64_t Hash_pixel_dim_seed(int px, int py, int dimension, int seed) {
 }
 
 struct SamplerParams {
-    int type;                  // 0 = zsobol, 1 = independent, 2 = stratified, 3 = paddedsobol, 4 = sobol
+    int type;                  // 0 = zsobol, 1 = independent, 2 = stratified, 3 = paddedsobol, 4 = sobol, 5 = halton
     int xSamples, ySamples, jitter;   // stratified (samplers.h:568-625)
     int randomize;             // RandomizeStrategy
     int seed;
@@ -206,6 +206,13 @@ struct SamplerParams {
     const uint32_t *sobolFull;   // [1024][52]
     const uint64_t *vdc, *vdcInv;   // [25][52]
     int log2Scale, scale;
+    // HaltonSampler (samplers.h:33-141, samplers.cpp:32-52): the first 1000 primes, the digit permutations of
+    // ComputeRadicalInversePermutations(seed) (one block of nDigits x base 16-bit entries per prime, at permOffset[prime index]),
+    // and the constants that take a pixel to its first Halton index
+    const int *primes;
+    const uint16_t *haltonPerms;
+    const uint32_t *haltonPermOffset;
+    int baseScales[2], baseExponents[2], multInverse[2];
 };
 
 // BPT_OUTLINE_SAMPLER (device, the translation unit that owns the Sobol tables): ZSobol Get1D / Get2D as ONE real function
@@ -230,12 +237,32 @@ struct Sampler {
     int pixel;   // index into SamplerParams::prefix, -1: no table / pixel outside the film
     int px, py, sampleIndex;   // stratified / paddedsobol
     RNG rng;   // independent and stratified samplers
-    int64_t sobolIndex;   // SobolSampler
+    int64_t sobolIndex;   // SobolSampler: the Sobol' index; HaltonSampler: haltonIndex
     BPT_HD void StartPixelSample(const SamplerParams *params, int pxIn, int pyIn, int index, int dim) {
         sp = params;
         dimension = dim;
         pixel = -1;
         px = pxIn; py = pyIn; sampleIndex = index;
+        if (sp->type == 5) {   // HaltonSampler::StartPixelSample (samplers.h:53-71)
+            int64_t haltonIndex = 0;
+            int sampleStride = sp->baseScales[0] * sp->baseScales[1];
+            if (sampleStride > 1) {
+                auto mod = [](int a, int b) { int r = a - (a / b) * b; return r < 0 ? r + b : r; };
+                const int pm[2] = {mod(pxIn, 128), mod(pyIn, 128)};
+                for (int i = 0; i < 2; ++i) {
+                    // InverseRadicalInverse(pm[i], base, baseExponents[i]) (lowdiscrepancy.h:104-113)
+                    const int base = i == 0 ? 2 : 3;
+                    uint64_t inverse = (uint64_t)pm[i], dimOffset = 0;
+                    for (int k = 0; k < sp->baseExponents[i]; ++k) { uint64_t digit = inverse % base; inverse /= base; dimOffset = dimOffset * base + digit; }
+                    haltonIndex += dimOffset * (sampleStride / sp->baseScales[i]) * sp->multInverse[i];
+                }
+                haltonIndex %= sampleStride;
+            }
+            haltonIndex += index * sampleStride;
+            sobolIndex = haltonIndex;
+            dimension = dim > 2 ? dim : 2;
+            return;
+        }
         if (sp->type == 4) {   // SobolSampler::StartPixelSample (samplers.h:502-506) + SobolIntervalToIndex (lowdiscrepancy.h:266-287)
             dimension = dim > 2 ? dim : 2;
             const uint32_t m = (uint32_t)sp->log2Scale;
@@ -337,8 +364,58 @@ struct Sampler {
         }
         return stdmin((float)v * 0x1p-32f, kOneMinusEpsilon);
     }
-    // Sampler::GetPixel2D: the film-plane sample of GetCameraSample (samplers.h:797-814); only SobolSampler (:525-536) has its own
+    // RadicalInverse / ScrambledRadicalInverse / OwenScrambledRadicalInverse (lowdiscrepancy.h:86-158) of the sample's Halton index
+    BPT_HD static float RadicalInverse(unsigned base, uint64_t a) {
+        uint64_t limit = ~0ull / base - base;
+        float invBase = (float)1 / (float)base, invBaseM = 1;
+        uint64_t reversedDigits = 0;
+        while (a && reversedDigits < limit) {
+            uint64_t next = a / base;
+            uint64_t digit = a - next * base;
+            reversedDigits = reversedDigits * base + digit;
+            invBaseM *= invBase;
+            a = next;
+        }
+        return stdmin(reversedDigits * invBaseM, kOneMinusEpsilon);
+    }
+    BPT_HD float HaltonDimension(int dim) const {
+        const unsigned base = (unsigned)sp->primes[dim];
+        uint64_t a = (uint64_t)sobolIndex;
+        if (sp->randomize == RANDOMIZE_NONE) return RadicalInverse(base, a);
+        uint64_t limit = ~0ull / base - base;
+        float invBase = (float)1 / (float)base, invBaseM = 1;
+        uint64_t reversedDigits = 0;
+        int digitIndex = 0;
+        if (sp->randomize == RANDOMIZE_PERMUTE_DIGITS) {
+            const uint16_t *perm = sp->haltonPerms + sp->haltonPermOffset[dim];
+            while (1 - (base - 1) * invBaseM < 1 && reversedDigits < limit) {
+                uint64_t next = a / base;
+                int digitValue = (int)(a - next * base);
+                reversedDigits = reversedDigits * base + perm[digitIndex * (int)base + digitValue];
+                invBaseM *= invBase;
+                ++digitIndex;
+                a = next;
+            }
+            return stdmin(invBaseM * reversedDigits, kOneMinusEpsilon);
+        }
+        const uint32_t hash = (uint32_t)MixBits((uint64_t)(1 + (dim << 4)));
+        while (1 - invBaseM < 1 && reversedDigits < limit) {
+            uint64_t next = a / base;
+            int digitValue = (int)(a - next * base);
+            uint32_t digitHash = (uint32_t)MixBits(hash ^ reversedDigits);
+            digitValue = PermutationElement((uint32_t)digitValue, base, digitHash);
+            reversedDigits = reversedDigits * base + digitValue;
+            invBaseM *= invBase;
+            ++digitIndex;
+            a = next;
+        }
+        return stdmin(invBaseM * reversedDigits, kOneMinusEpsilon);
+    }
+    // Sampler::GetPixel2D: the film-plane sample of GetCameraSample (samplers.h:797-814); SobolSampler (:525-536) and HaltonSampler
+    // (:90-93) have their own
     BPT_HD Vec2 GetPixel2D() {
+        if (sp->type == 5)
+            return {RadicalInverse(2, (uint64_t)sobolIndex >> sp->baseExponents[0]), RadicalInverse(3, (uint64_t)(sobolIndex / sp->baseScales[1]))};
         if (sp->type != 4) return Get2D();
         float u[2] = {SobolDimension(0, 0), SobolDimension(1, 0)};
         const int pix[2] = {px, py};
@@ -346,6 +423,10 @@ struct Sampler {
         return {u[0], u[1]};
     }
     BPT_HD float Get1D() {
+        if (sp->type == 5) {
+            if (dimension >= 1000) dimension = 2;
+            return HaltonDimension(dimension++);
+        }
         if (sp->type == 4) {
             if (dimension >= 1024) dimension = 2;
             return SobolDimension(dimension++, sp->randomize);
@@ -363,6 +444,12 @@ struct Sampler {
         return SobolSampleRand(sampleIndex, 0, sp->randomize, sampleHash);
     }
     BPT_HD Vec2 Get2D() {
+        if (sp->type == 5) {
+            if (dimension + 1 >= 1000) dimension = 2;
+            int dim = dimension;
+            dimension += 2;
+            return {HaltonDimension(dim), HaltonDimension(dim + 1)};
+        }
         if (sp->type == 4) {
             if (dimension + 1 >= 1024) dimension = 2;
             Vec2 u(SobolDimension(dimension, sp->randomize), SobolDimension(dimension + 1, sp->randomize));

@@ -212,7 +212,7 @@ int bpt_scene_commit(bpt_engine *e) {
             F(ft.type == BPT_FILTER_GAUSSIAN ? ft.sigma : 0.f).c_str(), F(ft.type == BPT_FILTER_MITCHELL ? ft.b : 0.f).c_str(),
             F(ft.type == BPT_FILTER_MITCHELL ? ft.c : 0.f).c_str(), F(ft.type == BPT_FILTER_SINC ? ft.tau : 0.f).c_str());
     bpt_sampler sm = e->haveSampler ? e->sampler : bpt_sampler{BPT_SAMPLER_ZSOBOL, 16, 0, BPT_RANDOMIZE_FAST_OWEN, 0, 0, 0};
-    const bool strat = sm.type == BPT_SAMPLER_STRATIFIED, sob = sm.type == BPT_SAMPLER_ZSOBOL || sm.type == BPT_SAMPLER_PADDED_SOBOL || sm.type == BPT_SAMPLER_SOBOL;
+    const bool strat = sm.type == BPT_SAMPLER_STRATIFIED, sob = sm.type == BPT_SAMPLER_ZSOBOL || sm.type == BPT_SAMPLER_PADDED_SOBOL || sm.type == BPT_SAMPLER_SOBOL || sm.type == BPT_SAMPLER_HALTON;
     fprintf(f, "sampler type=%d spp=%d seed=%d randomize=%d strata=%dx%d jitter=%d\n", sm.type, strat ? sm.x_samples * sm.y_samples : sm.spp, sm.seed,
             sob ? sm.randomize : 0, strat ? sm.x_samples : 0, strat ? sm.y_samples : 0, strat ? (sm.jitter != 0) : 0);
     bpt_integrator ig = e->haveInteg ? e->integ : bpt_integrator{5, 0, BPT_LIGHTSAMPLER_BVH};
