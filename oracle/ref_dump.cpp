@@ -760,6 +760,36 @@ static void DumpGolden(const char *path) {
         b.f32(StringPrintf("diff%d_in", cfg).c_str(), in);
         b.f32(StringPrintf("diff%d_out", cfg).c_str(), out);
     }
+    // SobolSampler and HaltonSampler: for random (pixel, sample index) the values a path draws first -- Get1D, GetPixel2D, Get1D, Get2D,
+    // then 3 x (Get1D, Get2D) -- and a restart at dimension 997 (both samplers wrap back to dimension 2).  (appended last)
+    {
+        Allocator alloc;
+        const Point2i res(200, 150);
+        struct Cfg { int kind, spp, seed; RandomizeStrategy r; };
+        const Cfg cfgs[7] = {{0, 8, 0, RandomizeStrategy::FastOwen}, {0, 5, 3, RandomizeStrategy::None}, {0, 4, 1, RandomizeStrategy::PermuteDigits}, {0, 16, 2, RandomizeStrategy::Owen},
+                             {1, 8, 0, RandomizeStrategy::PermuteDigits}, {1, 5, 7, RandomizeStrategy::None}, {1, 4, 2, RandomizeStrategy::Owen}};
+        std::vector<float> in, out;
+        for (int c = 0; c < 7; ++c) {
+            SobolSampler sob(cfgs[c].spp, res, cfgs[c].r, cfgs[c].seed);
+            HaltonSampler hal(cfgs[c].spp, res, cfgs[c].r == RandomizeStrategy::FastOwen ? RandomizeStrategy::PermuteDigits : cfgs[c].r, cfgs[c].seed, alloc);
+            Sampler smp = cfgs[c].kind == 0 ? Sampler(&sob) : Sampler(&hal);
+            for (int q = 0; q < 96; ++q) {
+                Point2i p(std::min(res.x - 1, int(rng.Uniform<float>() * res.x)), std::min(res.y - 1, int(rng.Uniform<float>() * res.y)));
+                int si = std::min(cfgs[c].spp - 1, int(rng.Uniform<float>() * cfgs[c].spp));
+                in.insert(in.end(), {(float)c, (float)p.x, (float)p.y, (float)si});
+                smp.StartPixelSample(p, si, 0);
+                out.push_back(smp.Get1D());
+                Point2f px = smp.GetPixel2D(); out.push_back(px.x); out.push_back(px.y);
+                out.push_back(smp.Get1D());
+                Point2f l = smp.Get2D(); out.push_back(l.x); out.push_back(l.y);
+                for (int k = 0; k < 3; ++k) { out.push_back(smp.Get1D()); Point2f u = smp.Get2D(); out.push_back(u.x); out.push_back(u.y); }
+                smp.StartPixelSample(p, si, 997);
+                for (int k = 0; k < 2; ++k) { out.push_back(smp.Get1D()); Point2f u = smp.Get2D(); out.push_back(u.x); out.push_back(u.y); }
+            }
+        }
+        b.f32("smp_in", in);
+        b.f32("smp_out", out);
+    }
 }
 
 int main(int argc, char **argv) {

@@ -768,42 +768,24 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     SamplerParams sp{};
     sp.type = e->sampler.type == BPT_SAMPLER_ZSOBOL ? 0 : e->sampler.type == BPT_SAMPLER_STRATIFIED ? 2 : e->sampler.type == BPT_SAMPLER_PADDED_SOBOL ? 3 :
               e->sampler.type == BPT_SAMPLER_SOBOL ? 4 : e->sampler.type == BPT_SAMPLER_HALTON ? 5 : 1;
+    sp.xSamples = e->sampler.x_samples; sp.ySamples = e->sampler.y_samples; sp.jitter = e->sampler.jitter;
+    sp.randomize = e->sampler.randomize;
+    sp.seed = e->sampler.seed;
+    sp.samplesPerPixel = e->sampler.spp;
     if (sp.type == 5) {   // HaltonSampler::HaltonSampler (samplers.cpp:32-52), ComputeRadicalInversePermutations (lowdiscrepancy.cpp:47-55)
-        std::vector<int> primes;
-        for (int k = 2; primes.size() < 1000; ++k) { bool pr = true; for (int q : primes) { if (q * q > k) break; if (k % q == 0) { pr = false; break; } } if (pr) primes.push_back(k); }
+        std::vector<int> primes = FirstPrimes(1000);
         ECK(e->dPrimes.upload(primes));
         sp.primes = e->dPrimes.p;
         if (sp.randomize == RANDOMIZE_PERMUTE_DIGITS && (e->haltonPermSeed != sp.seed || e->dHaltonPerms.n == 0)) {
             std::vector<uint16_t> perms;
-            std::vector<uint32_t> offsets(primes.size());
-            for (size_t i = 0; i < primes.size(); ++i) {
-                const int base = primes[i];
-                int nDigits = 0;
-                float invBase = (float)1 / (float)base, invBaseM = 1;
-                while (1 - (base - 1) * invBaseM < 1) { ++nDigits; invBaseM *= invBase; }
-                offsets[i] = (uint32_t)perms.size();
-                for (int digitIndex = 0; digitIndex < nDigits; ++digitIndex) {
-                    // Hash(base, digitIndex, seed): the three 32-bit arguments packed back to back (util/hash.h:99-107)
-                    uint64_t w[2] = {(uint64_t)(uint32_t)base | ((uint64_t)(uint32_t)digitIndex << 32), (uint64_t)(uint32_t)sp.seed};
-                    uint64_t dseed = MurmurHash64A(w, 12, 0);
-                    for (int digitValue = 0; digitValue < base; ++digitValue) perms.push_back((uint16_t)PermutationElement((uint32_t)digitValue, (uint32_t)base, (uint32_t)dseed));
-                }
-            }
+            std::vector<uint32_t> offsets;
+            BuildHaltonPermutations(primes, sp.seed, &perms, &offsets);
             ECK(e->dHaltonPerms.upload(perms));
             ECK(e->dHaltonPermOffset.upload(offsets));
             e->haltonPermSeed = sp.seed;
         }
         sp.haltonPerms = e->dHaltonPerms.p; sp.haltonPermOffset = e->dHaltonPermOffset.p;
-        const int fullRes[2] = {fl.xres, fl.yres};
-        for (int i = 0; i < 2; ++i) {
-            int base = (i == 0) ? 2 : 3, scale = 1, exp = 0;
-            while (scale < std::min(fullRes[i], 128)) { scale *= base; ++exp; }
-            sp.baseScales[i] = scale; sp.baseExponents[i] = exp;
-        }
-        struct G { static void ext(uint64_t a, uint64_t b, int64_t *x, int64_t *y) { if (b == 0) { *x = 1; *y = 0; return; } int64_t d = (int64_t)(a / b), xp, yp; ext(b, a % b, &xp, &yp); *x = yp; *y = xp - (d * yp); } };
-        auto multiplicativeInverse = [](int64_t a, int64_t n) { int64_t x, y; G::ext((uint64_t)a, (uint64_t)n, &x, &y); int64_t r = x - (x / n) * n; return (int)(r < 0 ? r + n : r); };
-        sp.multInverse[0] = multiplicativeInverse(sp.baseScales[1], sp.baseScales[0]);
-        sp.multInverse[1] = multiplicativeInverse(sp.baseScales[0], sp.baseScales[1]);
+        HaltonPixelConstants(fl.xres, fl.yres, &sp);
     }
     if (sp.type == 4) {   // SobolSampler (samplers.h:482-490): the full generator matrices and SobolIntervalToIndex's matrices
         if (!e->tables.u32.count("sobol32_full") || !e->tables.u32.count("vdc_sobol") || !e->tables.u32.count("vdc_sobol_inv"))
@@ -816,10 +798,6 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         int scale = 1; while (scale < std::max(fl.xres, fl.yres)) scale <<= 1;
         sp.scale = scale; sp.log2Scale = 0; while ((1 << sp.log2Scale) < scale) ++sp.log2Scale;
     }
-    sp.xSamples = e->sampler.x_samples; sp.ySamples = e->sampler.y_samples; sp.jitter = e->sampler.jitter;
-    sp.randomize = e->sampler.randomize;
-    sp.seed = e->sampler.seed;
-    sp.samplesPerPixel = e->sampler.spp;
     {
         auto log2i = [](unsigned v) { int l = 0; while (v >>= 1) ++l; return l; };
         auto roundUpPow2 = [](int v) { int r = 1; while (r < v) r <<= 1; return r; };

@@ -10,6 +10,7 @@
 //   SampleSphericalTriangle, InvertSphericalTriangleSample   util/sampling.cpp
 //   SampleVisibleWavelengths / PDF             util/sampling.h:163-171
 #pragma once
+#include <vector>
 #include "pmath.h"
 
 namespace bpt {
@@ -682,6 +683,47 @@ BPT_HD float PC2DPDF(const PC2DView &d, Vec2 pr) {
     int iu = Clampi((int)(ox * d.nu), 0, d.nu - 1);
     int iv = Clampi((int)(oy * d.nv), 0, d.nv - 1);
     return d.func[(size_t)iv * d.nu + iu] / d.mfuncInt;
+}
+
+// ---- host: the tables and constants of the Halton sampler (HaltonSampler::HaltonSampler samplers.cpp:32-52,
+// ComputeRadicalInversePermutations lowdiscrepancy.cpp:47-55, DigitPermutation lowdiscrepancy.h:30-49)
+inline std::vector<int> FirstPrimes(int n) {
+    std::vector<int> primes;
+    for (int k = 2; (int)primes.size() < n; ++k) {
+        bool pr = true;
+        for (int q : primes) { if (q * q > k) break; if (k % q == 0) { pr = false; break; } }
+        if (pr) primes.push_back(k);
+    }
+    return primes;
+}
+inline void BuildHaltonPermutations(const std::vector<int> &primes, int seed, std::vector<uint16_t> *perms, std::vector<uint32_t> *offsets) {
+    perms->clear();
+    offsets->assign(primes.size(), 0);
+    for (size_t i = 0; i < primes.size(); ++i) {
+        const int base = primes[i];
+        int nDigits = 0;
+        float invBase = (float)1 / (float)base, invBaseM = 1;
+        while (1 - (base - 1) * invBaseM < 1) { ++nDigits; invBaseM *= invBase; }
+        (*offsets)[i] = (uint32_t)perms->size();
+        for (int digitIndex = 0; digitIndex < nDigits; ++digitIndex) {
+            // Hash(base, digitIndex, seed): the three 32-bit arguments packed back to back (util/hash.h:99-107)
+            uint64_t w[2] = {(uint64_t)(uint32_t)base | ((uint64_t)(uint32_t)digitIndex << 32), (uint64_t)(uint32_t)seed};
+            uint64_t dseed = MurmurHash64A(w, 12, 0);
+            for (int digitValue = 0; digitValue < base; ++digitValue) perms->push_back((uint16_t)PermutationElement((uint32_t)digitValue, (uint32_t)base, (uint32_t)dseed));
+        }
+    }
+}
+inline void HaltonPixelConstants(int xres, int yres, SamplerParams *sp) {
+    const int fullRes[2] = {xres, yres};
+    for (int i = 0; i < 2; ++i) {
+        int base = (i == 0) ? 2 : 3, scale = 1, exp = 0;
+        while (scale < (fullRes[i] < 128 ? fullRes[i] : 128)) { scale *= base; ++exp; }
+        sp->baseScales[i] = scale; sp->baseExponents[i] = exp;
+    }
+    struct G { static void ext(uint64_t a, uint64_t b, int64_t *x, int64_t *y) { if (b == 0) { *x = 1; *y = 0; return; } int64_t d = (int64_t)(a / b), xp, yp; ext(b, a % b, &xp, &yp); *x = yp; *y = xp - (d * yp); } };
+    auto multiplicativeInverse = [](int64_t a, int64_t n) { int64_t x, y; G::ext((uint64_t)a, (uint64_t)n, &x, &y); int64_t r = x - (x / n) * n; return (int)(r < 0 ? r + n : r); };
+    sp->multInverse[0] = multiplicativeInverse(sp->baseScales[1], sp->baseScales[0]);
+    sp->multInverse[1] = multiplicativeInverse(sp->baseScales[0], sp->baseScales[1]);
 }
 
 }  // namespace bpt

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) k_generate_camera_rays(RenderCtx rc, int 
             dir = Normalize(pFocus - o);
         }
         XformRay(rc.camera.renderFromCamera, o, dir);
+        if (rc.camera.type != 0) GenerateCameraRay(rc.camera, pFilm, pLens, &o, &dir);   // orthographic: the helper (uniform branch, rare)
         const PathState &ps = rc.ps;
         ps.rayO[slot] = make_float4(o.x, o.y, o.z, 0.f);
         ps.rayD[slot] = make_float4(dir.x, dir.y, dir.z, time);
