@@ -418,20 +418,23 @@ def main():
         b_ray = 300.0 + n_bar * 80.0 + t_bar * 48.0
         # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/, first-bounce launch of the same
         # workload): dram read + write per ray there, times the rays of an average launch here
-        traffic = None
-        try:
-            txt = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01h_closest_shade_camera.summary.txt")).read()
-            blk = txt[txt.index("k_trace_closest"):]
-            rd = float(re.search(r"dram__bytes_read.sum = ([0-9.]+)\s+\[Gbyte\]", blk).group(1))
-            wr = float(re.search(r"dram__bytes_write.sum = ([0-9.]+)\s+\[Gbyte\]", blk).group(1))
-            ncu_rays = 33554432.0   # rays of the captured launch (32 spp x 1024^2 camera rays)
-            traffic = (rd + wr) * 1e9 / ncu_rays * (rays_c / max(1, sp["launches_trace_closest"]))
-        except Exception:
-            traffic = None
+        traffic, traffic_file = None, None
+        # newest capture first: (summary file, camera rays of its first-bounce launch = spp of the capture x 1024^2)
+        for fn, ncu_rays in (("r02z_hf1m.summary.txt", 8 * 1048576.0), ("r02a_hf1m.summary.txt", 8 * 1048576.0), ("r01h_closest_shade_camera.summary.txt", 32 * 1048576.0)):
+            try:
+                txt = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", fn)).read()
+                blk = txt[txt.index("k_trace_closest"):]
+                rd = float(re.search(r"dram__bytes_read.sum = ([0-9.]+)\s+\[Gbyte\]", blk).group(1))
+                wr = float(re.search(r"dram__bytes_write.sum = ([0-9.]+)\s+\[Gbyte\]", blk).group(1))
+                traffic = (rd + wr) * 1e9 / ncu_rays * (rays_c / max(1, sp["launches_trace_closest"]))
+                traffic_file = fn
+                break
+            except Exception:
+                continue
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic if (dom == "k_trace_closest" and args.workload == "heightfield1m") else None,
-                    "traffic_source": "ncu --set full capture profiles/r01h (dram read+write per ray of the first-bounce launch) x rays of an average launch; "
-                                      "it is ~6 % of the algorithmic bytes because the 60 MB BVH stays in the 126 MB L2",
+                    "traffic_source": "ncu --set full capture profiles/%s (dram read+write per ray of the first-bounce launch) x rays of an average launch; "
+                                      "a few percent of the algorithmic bytes because the 60 MB BVH stays in the 126 MB L2" % traffic_file,
                     "kernel": dom, "peak_source": peak_src, "kernels": kern,
                     "launch_avg_ms": kern[dom]["ms_total"] / max(1, kern[dom]["launches"]),
                     "bytes_per_launch_avg": (bytes_c if dom == "k_trace_closest" else bytes_s) / max(1, kern[dom]["launches"]),

@@ -227,6 +227,10 @@ struct SamplerParams {
 struct SamplerParams;
 #if defined(__CUDACC__) && defined(BPT_SOBOL_DEVICE_TABLE)
 static __device__ __noinline__ float2 ZSobolOutlined(uint64_t mortonIndex, int pixel, int dimension, int nd);
+// The table-driven samplers other than ZSobol (PaddedSobol, Sobol, Halton) as one real function as well, so that kernels rendering
+// with the default sampler do not carry three more inlined samplers at each of their seven call sites.  nd = 1 / 2: Get1D / Get2D
+// at `dimension`; nd = 0: GetPixel2D.
+static __device__ __noinline__ float2 QmcOutlined(int px, int py, int sampleIndex, long long sobolIndex, int dimension, int nd);
 #endif
 constexpr int kDimHashTable = 128;   // Hash(dimension, seed) for dimension < kDimHashTable
 
@@ -415,6 +419,9 @@ struct Sampler {
     // Sampler::GetPixel2D: the film-plane sample of GetCameraSample (samplers.h:797-814); SobolSampler (:525-536) and HaltonSampler
     // (:90-93) have their own
     BPT_HD Vec2 GetPixel2D() {
+#if BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
+        if (sp->type >= 4) { float2 r = QmcOutlined(px, py, sampleIndex, sobolIndex, dimension, 0); return {r.x, r.y}; }
+#endif
         if (sp->type == 5)
             return {RadicalInverse(2, (uint64_t)sobolIndex >> sp->baseExponents[0]), RadicalInverse(3, (uint64_t)(sobolIndex / sp->baseScales[1]))};
         if (sp->type != 4) return Get2D();
@@ -424,6 +431,15 @@ struct Sampler {
         return {u[0], u[1]};
     }
     BPT_HD float Get1D() {
+#if BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
+        if (sp->type >= 3) {
+            if (sp->type == 4 && dimension >= 1024) dimension = 2;
+            if (sp->type == 5 && dimension >= 1000) dimension = 2;
+            float2 r = QmcOutlined(px, py, sampleIndex, sobolIndex, dimension, 1);
+            ++dimension;
+            return r.x;
+        }
+#endif
         if (sp->type == 5) {
             if (dimension >= 1000) dimension = 2;
             return HaltonDimension(dimension++);
@@ -445,6 +461,15 @@ struct Sampler {
         return SobolSampleRand(sampleIndex, 0, sp->randomize, sampleHash);
     }
     BPT_HD Vec2 Get2D() {
+#if BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
+        if (sp->type >= 3) {
+            if (sp->type == 4 && dimension + 1 >= 1024) dimension = 2;
+            if (sp->type == 5 && dimension + 1 >= 1000) dimension = 2;
+            float2 r = QmcOutlined(px, py, sampleIndex, sobolIndex, dimension, 2);
+            dimension += 2;
+            return {r.x, r.y};
+        }
+#endif
         if (sp->type == 5) {
             if (dimension + 1 >= 1000) dimension = 2;
             int dim = dimension;
@@ -475,6 +500,32 @@ struct Sampler {
 #if defined(__CUDACC__) && defined(BPT_SOBOL_DEVICE_TABLE)
 __constant__ SamplerParams c_sampler;
 __constant__ uint64_t c_dimHash[kDimHashTable];
+static __device__ __noinline__ float2 QmcOutlined(int px, int py, int sampleIndex, long long sobolIndex, int dimension, int nd) {
+    Sampler s;
+    s.sp = &c_sampler; s.px = px; s.py = py; s.sampleIndex = sampleIndex; s.sobolIndex = sobolIndex; s.dimension = dimension; s.pixel = -1;
+    float2 r = make_float2(0.f, 0.f);
+    const int type = c_sampler.type;
+    if (nd == 0) {   // GetPixel2D of the Sobol' and Halton samplers (the member functions' own code, not the dispatch above)
+        if (type == 5) { r.x = Sampler::RadicalInverse(2, (uint64_t)sobolIndex >> c_sampler.baseExponents[0]); r.y = Sampler::RadicalInverse(3, (uint64_t)(sobolIndex / c_sampler.baseScales[1])); }
+        else {
+            float u[2] = {s.SobolDimension(0, 0), s.SobolDimension(1, 0)};
+            const int pix[2] = {px, py};
+            for (int d = 0; d < 2; ++d) u[d] = Clampf(u[d] * c_sampler.scale - pix[d], 0.f, kOneMinusEpsilon);
+            r.x = u[0]; r.y = u[1];
+        }
+        return r;
+    }
+    if (type == 3) {
+        if (nd == 1) r.x = s.OtherGet1D(); else { Vec2 u = s.OtherGet2D(); r.x = u.x; r.y = u.y; }
+    } else if (type == 4) {
+        r.x = s.SobolDimension(dimension, c_sampler.randomize);
+        if (nd == 2) r.y = s.SobolDimension(dimension + 1, c_sampler.randomize);
+    } else {
+        r.x = s.HaltonDimension(dimension);
+        if (nd == 2) r.y = s.HaltonDimension(dimension + 1);
+    }
+    return r;
+}
 static __device__ __noinline__ float2 ZSobolOutlined(uint64_t mortonIndex, int pixel, int dimension, int nd) {
     Sampler s;
     s.sp = &c_sampler; s.mortonIndex = mortonIndex; s.pixel = pixel; s.dimension = dimension;
