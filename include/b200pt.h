@@ -186,7 +186,7 @@ typedef struct {
     float cone_angle, cone_delta; /* spot: "coneangle" (30), "conedeltaangle" (5), degrees */
 } bpt_light;
 
-enum { BPT_MEDIUM_UNIFORMGRID = 0, BPT_MEDIUM_HOMOGENEOUS = 1 };
+enum { BPT_MEDIUM_UNIFORMGRID = 0, BPT_MEDIUM_HOMOGENEOUS = 1, BPT_MEDIUM_RGBGRID = 2 };
 /* Medium (media.h:217-352: HomogeneousMedium, GridMedium; created in media.cpp:165-201,249-330), emission through "Le" / "Lescale"
  * (no "temperature" grids). */
 typedef struct {
@@ -199,6 +199,8 @@ typedef struct {
     const float *density; int nx, ny, nz;
     bpt_spectrum Le; float Le_scale;                /* emission: "Le" (BPT_SPEC_NONE: none) and, homogeneous, the float "Lescale" */
     const float *Le_scale_grid;                      /* uniformgrid: the "Lescale" float array (nx*ny*nz values) or NULL */
+    /* "rgbgrid" (RGBGridMedium, media.h:355-427, media.cpp:380-453): nx*ny*nz RGB triples each or NULL; scale = "scale", Le_scale = "Lescale" */
+    const float *sigma_a_rgb, *sigma_s_rgb, *Le_rgb;
 } bpt_medium;
 
 typedef struct {

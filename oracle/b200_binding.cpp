@@ -499,8 +499,28 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
         std::string type = d.GetOneString("type", "");
         if (type == "uniformgrid") m.type = BPT_MEDIUM_UNIFORMGRID;
         else if (type == "homogeneous") m.type = BPT_MEDIUM_HOMOGENEOUS;
+        else if (type == "rgbgrid") m.type = BPT_MEDIUM_RGBGRID;
         else ErrorExit("medium type \"%s\" is not implemented by the engine", type);
         if (!d.GetOneString("preset", "").empty()) ErrorExit("medium presets are not implemented by the engine");
+        if (m.type == BPT_MEDIUM_RGBGRID) {   // RGBGridMedium::Create (media.cpp:380-453)
+            m.nx = d.GetOneInt("nx", 1); m.ny = d.GetOneInt("ny", 1); m.nz = d.GetOneInt("nz", 1);
+            auto grid = [&](const char *name) -> const float * {
+                std::vector<RGB> v = d.GetRGBArray(name);
+                if (v.empty()) return nullptr;
+                if (v.size() != (size_t)m.nx * m.ny * m.nz) ErrorExit("rgbgrid medium: \"%s\" needs nx*ny*nz RGB values", name);
+                std::vector<float> f;
+                for (RGB c : v) { f.push_back(c.r); f.push_back(c.g); f.push_back(c.b); }
+                return st.F(std::move(f));
+            };
+            m.sigma_a_rgb = grid("sigma_a"); m.sigma_s_rgb = grid("sigma_s"); m.Le_rgb = grid("Le");
+            m.scale = d.GetOneFloat("scale", 1.f); m.g = d.GetOneFloat("g", 0.f); m.Le_scale = d.GetOneFloat("Lescale", 1.f);
+            m.world_from_medium = ToB(mr.renderFromMedium.GetMatrix()); m.medium_from_world = ToB(mr.renderFromMedium.GetInverseMatrix());
+            Point3f p0 = d.GetOnePoint3f("p0", Point3f(0, 0, 0)), p1 = d.GetOnePoint3f("p1", Point3f(1, 1, 1));
+            m.bounds[0] = p0.x; m.bounds[1] = p0.y; m.bounds[2] = p0.z; m.bounds[3] = p1.x; m.bounds[4] = p1.y; m.bounds[5] = p1.z;
+            mediumIndex[mr.name] = (int)mediumIndex.size();
+            Check(api, e, api.bpt_scene_add_medium(e, &m), "bpt_scene_add_medium");
+            continue;
+        }
         m.sigma_a = GetSpectrum(d, "sigma_a", st); m.sigma_s = GetSpectrum(d, "sigma_s", st); m.Le = GetSpectrum(d, "Le", st);
         m.scale = d.GetOneFloat("scale", 1.f); m.g = d.GetOneFloat("g", 0.f);
         m.Le_scale = m.type == BPT_MEDIUM_HOMOGENEOUS ? d.GetOneFloat("Lescale", 1.f) : 1.f;

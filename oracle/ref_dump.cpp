@@ -790,6 +790,59 @@ static void DumpGolden(const char *path) {
         b.f32("smp_in", in);
         b.f32("smp_out", out);
     }
+    // RGBGridMedium: the majorant grid and SampleT_maj event traces with sigma_a, sigma_s and Le at the events.  (appended last)
+    {
+        Allocator alloc;
+        const int nx = 7, ny = 9, nz = 5;
+        std::vector<float> rgbA, rgbS, rgbL;
+        std::vector<RGBUnboundedSpectrum> va, vs;
+        std::vector<RGBIlluminantSpectrum> vl;
+        for (int i = 0; i < nx * ny * nz; ++i) {
+            auto c = [&](float sc) { float r = rng.Uniform<float>(); return r < 0.25f ? 0.f : sc * rng.Uniform<float>(); };
+            RGB a(c(1.5f), c(1.5f), c(1.5f)), sg(c(4.f), c(4.f), c(4.f)), le(c(2.f), c(1.f), c(.5f));
+            if (i % 11 == 0) a = RGB(0.4f, 0.4f, 0.4f);   // grey voxels take the constant-coefficient branch of the RGB -> spectrum table
+            rgbA.insert(rgbA.end(), {a.r, a.g, a.b}); rgbS.insert(rgbS.end(), {sg.r, sg.g, sg.b}); rgbL.insert(rgbL.end(), {le.r, le.g, le.b});
+            va.push_back(RGBUnboundedSpectrum(*RGBColorSpace::sRGB, a)); vs.push_back(RGBUnboundedSpectrum(*RGBColorSpace::sRGB, sg));
+            vl.push_back(RGBIlluminantSpectrum(*RGBColorSpace::sRGB, le));
+        }
+        Transform rfm = Translate(Vector3f(-0.2f, 0.1f, 0.3f)) * RotateX(20) * Scale(1.2f, 1.f, 0.8f);
+        Bounds3f bounds(Point3f(-1, 0, -0.5f), Point3f(1, 1.5f, 1));
+        RGBGridMedium med(bounds, rfm, 0.2f, SampledGrid<RGBUnboundedSpectrum>(va, nx, ny, nz, alloc), SampledGrid<RGBUnboundedSpectrum>(vs, nx, ny, nz, alloc), 1.3f,
+                          SampledGrid<RGBIlluminantSpectrum>(vl, nx, ny, nz, alloc), 0.7f, alloc);
+        std::vector<float> params = {(float)nx, (float)ny, (float)nz, bounds.pMin.x, bounds.pMin.y, bounds.pMin.z, bounds.pMax.x, bounds.pMax.y, bounds.pMax.z, 1.3f, 0.7f};
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) params.push_back(rfm.GetInverseMatrix()[i][j]);
+        b.f32("rgbmed_params", params);
+        b.f32("rgbmed_sigma_a", rgbA); b.f32("rgbmed_sigma_s", rgbS); b.f32("rgbmed_Le", rgbL);
+        b.f32("rgbmed_majorant", std::vector<float>(med.majorantGrid.voxels.begin(), med.majorantGrid.voxels.end()));
+        const int kEvents = 5;
+        std::vector<float> in, out;
+        for (int i = 0; i < 512; ++i) {
+            auto r = [&]() { return 2 * rng.Uniform<float>() - 1; };
+            Point3f o(2 * r(), 2 * r(), 2 * r());
+            if (i % 3 == 0) o = rfm(Point3f(bounds.Lerp(Point3f(rng.Uniform<float>(), rng.Uniform<float>(), rng.Uniform<float>()))));
+            Vector3f d = Normalize(Vector3f(r(), r(), r())) * (0.5f + 1.5f * rng.Uniform<float>());
+            Float tMax = (i % 4 == 3) ? Infinity : 4 * rng.Uniform<float>();
+            Float u = rng.Uniform<float>();
+            uint64_t s0 = rng.Uniform<uint32_t>() >> 8, s1 = rng.Uniform<uint32_t>() >> 8;
+            SampledWavelengths lambda = SampledWavelengths::SampleVisible(rng.Uniform<float>());
+            RNG trng(s0, s1);
+            std::vector<float> ev;
+            int nEv = 0;
+            auto cb = [&](Point3f p, MediumProperties mp, SampledSpectrum sigma_maj, SampledSpectrum T_maj) {
+                ev.insert(ev.end(), {p.x, p.y, p.z, mp.sigma_a[0], mp.sigma_a[3], mp.sigma_s[0], mp.sigma_s[2], mp.Le[0], mp.Le[1], sigma_maj[0], T_maj[0], T_maj[3]});
+                return ++nEv < kEvents;
+            };
+            Ray ray(o, d, 0.f, Medium(&med));
+            SampledSpectrum T = SampleT_maj<RGBGridMedium>(ray, tMax, u, trng, lambda, cb);
+            ev.resize(12 * kEvents, 0.f);
+            in.insert(in.end(), {o.x, o.y, o.z, d.x, d.y, d.z, tMax, u, (float)s0, (float)s1, lambda[0], lambda[1], lambda[2], lambda[3]});
+            out.push_back((float)nEv);
+            out.insert(out.end(), ev.begin(), ev.end());
+            out.insert(out.end(), {T[0], T[1], T[2], T[3], trng.Uniform<float>()});
+        }
+        b.f32("rgbmed_in", in);
+        b.f32("rgbmed_out", out);
+    }
 }
 
 int main(int argc, char **argv) {

@@ -55,7 +55,7 @@ struct OwnedLight {
 };
 struct OwnedAreaLight { bpt_area_light a; OwnedSpectrum L; };
 struct OwnedTexture { bpt_texture t; HostImage img; OwnedSpectrum value; };
-struct OwnedMedium { bpt_medium m; OwnedSpectrum sigma_a, sigma_s, Le; std::vector<float> density, leScale; };
+struct OwnedMedium { bpt_medium m; OwnedSpectrum sigma_a, sigma_s, Le; std::vector<float> density, leScale, rgbA, rgbS, rgbLe; };
 
 template <typename T>
 struct DevBuf {
@@ -223,6 +223,7 @@ struct bpt_engine {
     DevBuf<GBufferPixel> gbuf;
     DevBuf<float> gbufOut;
     std::vector<std::unique_ptr<DevBuf<float>>> mediumBufs;
+    std::vector<std::unique_ptr<DevBuf<float4>>> mediumBufs4;
     bool haveInterface = false;
     bool raySort = false;            // BPT_RAY_SORT=1: sort the extension-ray queue by direction/origin key before each trace
     DevBuf<unsigned> sortKeys, sortKeysTmp, sortHist;
@@ -608,14 +609,25 @@ extern "C" int bpt_scene_add_light(bpt_engine *e, const bpt_light *l) {
 }
 extern "C" int bpt_scene_add_medium(bpt_engine *e, const bpt_medium *m) {
     if (!e || !m) return BPT_ERR_INVALID;
-    if (m->type != BPT_MEDIUM_UNIFORMGRID && m->type != BPT_MEDIUM_HOMOGENEOUS) return e->fail(BPT_ERR_UNSUPPORTED, "medium type not implemented (homogeneous, uniformgrid)");
+    if (m->type != BPT_MEDIUM_UNIFORMGRID && m->type != BPT_MEDIUM_HOMOGENEOUS && m->type != BPT_MEDIUM_RGBGRID)
+        return e->fail(BPT_ERR_UNSUPPORTED, "medium type not implemented (homogeneous, uniformgrid, rgbgrid)");
+    if (m->type == BPT_MEDIUM_RGBGRID) {
+        if ((!m->sigma_a_rgb && !m->sigma_s_rgb) || m->nx <= 0 || m->ny <= 0 || m->nz <= 0) return e->fail(BPT_ERR_INVALID, "RGB grid requires \"sigma_a\" and/or \"sigma_s\" parameter values");
+        if (m->Le_rgb && !m->sigma_a_rgb) return e->fail(BPT_ERR_INVALID, "RGB grid requires \"sigma_a\" if \"Le\" value provided");
+    }
     if (m->type == BPT_MEDIUM_UNIFORMGRID && (!m->density || m->nx <= 0 || m->ny <= 0 || m->nz <= 0)) return e->fail(BPT_ERR_INVALID, "uniformgrid medium needs a density grid");
     e->media.emplace_back();
     OwnedMedium &o = e->media.back();
     o.m = *m; o.sigma_a.Set(m->sigma_a); o.sigma_s.Set(m->sigma_s); o.Le.Set(m->Le);
     if (m->type == BPT_MEDIUM_UNIFORMGRID) o.density.assign(m->density, m->density + (size_t)m->nx * m->ny * m->nz);
     if (m->type == BPT_MEDIUM_UNIFORMGRID && m->Le_scale_grid) o.leScale.assign(m->Le_scale_grid, m->Le_scale_grid + (size_t)m->nx * m->ny * m->nz);
-    o.m.density = nullptr; o.m.Le_scale_grid = nullptr;
+    if (m->type == BPT_MEDIUM_RGBGRID) {
+        const size_t n3 = 3 * (size_t)m->nx * m->ny * m->nz;
+        if (m->sigma_a_rgb) o.rgbA.assign(m->sigma_a_rgb, m->sigma_a_rgb + n3);
+        if (m->sigma_s_rgb) o.rgbS.assign(m->sigma_s_rgb, m->sigma_s_rgb + n3);
+        if (m->Le_rgb) o.rgbLe.assign(m->Le_rgb, m->Le_rgb + n3);
+    }
+    o.m.density = nullptr; o.m.Le_scale_grid = nullptr; o.m.sigma_a_rgb = o.m.sigma_s_rgb = o.m.Le_rgb = nullptr;
     return BPT_OK;
 }
 // Engine options that are not part of the scene description (they survive bpt_scene_begin).
@@ -1227,12 +1239,62 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     // ---- media (HomogeneousMedium / GridMedium constructors, media.h:222-232, media.cpp:212-247)
     std::vector<DeviceMedium> dmedia(e->media.size());
     e->mediumBufs.clear();
+    e->mediumBufs4.clear();
     for (size_t i = 0; i < e->media.size(); ++i) {
         const OwnedMedium &om = e->media[i];
         DeviceMedium &dm = dmedia[i];
         std::memset(&dm, 0, sizeof(dm));
-        dm.type = om.m.type == BPT_MEDIUM_HOMOGENEOUS ? MEDIUM_HOMOGENEOUS : MEDIUM_GRID;
+        dm.type = om.m.type == BPT_MEDIUM_HOMOGENEOUS ? MEDIUM_HOMOGENEOUS : om.m.type == BPT_MEDIUM_RGBGRID ? MEDIUM_RGBGRID : MEDIUM_GRID;
         dm.g = om.m.g;
+        if (dm.type == MEDIUM_RGBGRID) {
+            // RGBGridMedium::Create / constructor (media.cpp:339-453): voxels become RGBUnboundedSpectrum / RGBIlluminantSpectrum, the
+            // 16^3 majorant grid holds sigmaScale * (max sigma_a + max sigma_s) over the voxels a cell overlaps
+            Xform renderFromMedium = ResolveRenderFromObject(space, spaces, om.m.world_from_medium, om.m.medium_from_world);
+            dm.mInv = ToMat4(renderFromMedium.mInv);
+            for (int k = 0; k < 3; ++k) { dm.bmin[k] = om.m.bounds[k]; dm.bmax[k] = om.m.bounds[3 + k]; }
+            const int nx = om.m.nx, ny = om.m.ny, nz = om.m.nz;
+            const size_t nv = (size_t)nx * ny * nz;
+            dm.nx = nx; dm.ny = ny; dm.nz = nz;
+            dm.sigmaScale = om.m.scale; dm.rgbLeScale = om.m.Le_scale; dm.Le = -1;
+            dm.illum = spool.addDense(illum);
+            auto voxels = [&](const std::vector<float> &rgb, std::vector<float4> *out, std::vector<float> *maxv) {
+                out->resize(nv); if (maxv) maxv->resize(nv);
+                for (size_t v = 0; v < nv; ++v) {
+                    const float *c = &rgb[3 * v];
+                    float m = stdmax(stdmax(c[0], c[1]), c[2]), scale = 2 * m, q[3] = {0, 0, 0}, co[3];
+                    if (scale) { q[0] = c[0] / scale; q[1] = c[1] / scale; q[2] = c[2] / scale; }
+                    RGBToCoeffs(e->tables, q, co);
+                    (*out)[v] = make_float4(scale, co[0], co[1], co[2]);
+                    if (maxv) {   // RGBUnboundedSpectrum::MaxValue = scale * RGBSigmoidPolynomial::MaxValue (util/color.h:346-352)
+                        float result = stdmax(SigmoidPoly(co[0], co[1], co[2], 360.f), SigmoidPoly(co[0], co[1], co[2], 830.f));
+                        float lambda = -co[1] / (2 * co[0]);
+                        if (lambda >= 360 && lambda <= 830) result = stdmax(result, SigmoidPoly(co[0], co[1], co[2], lambda));
+                        (*maxv)[v] = scale * result;
+                    }
+                }
+            };
+            std::vector<float4> va, vs, vl;
+            std::vector<float> ma, ms;
+            auto up4 = [&](const std::vector<float4> &v, const float4 **dst) -> cudaError_t {
+                e->mediumBufs4.emplace_back(new DevBuf<float4>());
+                cudaError_t rcu = e->mediumBufs4.back()->upload(v);
+                *dst = e->mediumBufs4.back()->p;
+                return rcu;
+            };
+            if (!om.rgbA.empty()) { voxels(om.rgbA, &va, &ma); ECK(up4(va, &dm.rgbA)); }
+            if (!om.rgbS.empty()) { voxels(om.rgbS, &vs, &ms); ECK(up4(vs, &dm.rgbS)); }
+            if (!om.rgbLe.empty()) { voxels(om.rgbLe, &vl, nullptr); ECK(up4(vl, &dm.rgbLe)); }
+            const int R = 16;
+            dm.mres[0] = dm.mres[1] = dm.mres[2] = R;
+            std::vector<float> maj((size_t)R * R * R), majA((size_t)R * R * R, 1.f), majS((size_t)R * R * R, 1.f);
+            if (!ma.empty()) ComputeMajorantGrid(ma.data(), nx, ny, nz, R, majA.data());
+            if (!ms.empty()) ComputeMajorantGrid(ms.data(), nx, ny, nz, R, majS.data());
+            for (size_t c = 0; c < maj.size(); ++c) { float maxSigma_t = majA[c] + majS[c]; maj[c] = om.m.scale * maxSigma_t; }
+            e->mediumBufs.emplace_back(new DevBuf<float>());
+            ECK(e->mediumBufs.back()->upload(maj));
+            dm.majorant = e->mediumBufs.back()->p;
+            continue;
+        }
         for (int k = 0; k < 2; ++k) {
             // DenselySampledSpectrum(spec) at integer wavelengths, then Scale(sigmaScale)
             const OwnedSpectrum &os = k == 0 ? om.sigma_a : om.sigma_s;

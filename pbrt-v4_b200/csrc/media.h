@@ -15,7 +15,7 @@
 
 namespace bpt {
 
-enum { MEDIUM_HOMOGENEOUS = 0, MEDIUM_GRID = 1 };
+enum { MEDIUM_HOMOGENEOUS = 0, MEDIUM_GRID = 1, MEDIUM_RGBGRID = 2 };
 
 struct DeviceMedium {
     int type;
@@ -31,6 +31,11 @@ struct DeviceMedium {
     int Le;                      // offset of the 471-entry Le_spec table, -1: the medium does not emit
     const float *leScale;        // GridMedium::LeScale (SampledGrid<Float>), lnx*lny*lnz
     int lnx, lny, lnz;
+    // RGBGridMedium (media.h:355-427): per voxel an RGBUnboundedSpectrum / RGBIlluminantSpectrum as (scale, c0, c1, c2); a null grid is
+    // the constant 1 for the coefficients and "no emission" for Le; `majorant` already holds sigmaScale * (max sigma_a + max sigma_s)
+    const float4 *rgbA, *rgbS, *rgbLe;
+    float sigmaScale, rgbLeScale;
+    int illum;                   // 471-entry table of the colour space's illuminant (RGBIlluminantSpectrum::Sample)
 };
 
 // ------------------------------------------------------------------ phase function
@@ -189,7 +194,7 @@ BPT_HD MajorantIter MediumSampleRay(const DeviceMedium &m, const float *specPool
     float tMin, tMax;
     if (!BoundsIntersectP(m.bmin, m.bmax, r.o, r.d, raytMax, &tMin, &tMax)) return it;
     it.kind = 2;
-    it.sigma = sigma_a + sigma_s;
+    it.sigma = m.type == MEDIUM_RGBGRID ? Spec(1.f) : sigma_a + sigma_s;   // RGBGridMedium::SampleRay: sigma_t = 1 (media.h:413)
     it.tMin = tMin; it.tMax = tMax;
     it.grid = m.majorant;
     // DDAMajorantIterator constructor
@@ -243,8 +248,43 @@ BPT_HD float ScalarGridLookup(const float *g, int nx, int ny, int nz, Vec3 p) {
     float d11 = Lerp(dx, fetch(ix, iy + 1, iz + 1), fetch(ix + 1, iy + 1, iz + 1));
     return Lerp(dz, Lerp(dy, d00, d10), Lerp(dy, d01, d11));
 }
+// SampledGrid<RGBUnboundedSpectrum / RGBIlluminantSpectrum>::Lookup(p, convert) (util/containers.h:803-835): trilinear over the
+// spectra sampled at the wavelengths; a voxel outside the grid converts a default-constructed spectrum, i.e. zero
+BPT_HD Spec RGBGridLookup(const float4 *g, int nx, int ny, int nz, Vec3 p, const Wavelengths &wl, const float *illum) {
+    auto fetch = [&](int x, int y, int z) -> Spec {
+        if (x < 0 || y < 0 || z < 0 || x >= nx || y >= ny || z >= nz) return Spec(0.f);
+        size_t i = ((size_t)z * ny + y) * nx + x;
+#if defined(__CUDA_ARCH__)
+        float4 v = __ldg(g + i);
+#else
+        float4 v = g[i];
+#endif
+        Spec s;
+        for (int k = 0; k < 4; ++k) s[k] = v.x * SigmoidPoly(v.y, v.z, v.w, wl.lambda[k]);
+        if (illum) s = s * DenseSample(illum, wl);
+        return s;
+    };
+    auto lerp = [](float t, const Spec &a, const Spec &b) { return (1 - t) * a + t * b; };
+    float sx = p.x * nx - .5f, sy = p.y * ny - .5f, sz = p.z * nz - .5f;
+    int ix = (int)floorf(sx), iy = (int)floorf(sy), iz = (int)floorf(sz);
+    float dx = sx - (float)ix, dy = sy - (float)iy, dz = sz - (float)iz;
+    Spec d00 = lerp(dx, fetch(ix, iy, iz), fetch(ix + 1, iy, iz));
+    Spec d10 = lerp(dx, fetch(ix, iy + 1, iz), fetch(ix + 1, iy + 1, iz));
+    Spec d01 = lerp(dx, fetch(ix, iy, iz + 1), fetch(ix + 1, iy, iz + 1));
+    Spec d11 = lerp(dx, fetch(ix, iy + 1, iz + 1), fetch(ix + 1, iy + 1, iz + 1));
+    return lerp(dz, lerp(dy, d00, d10), lerp(dy, d01, d11));
+}
 BPT_HD MediumProps MediumSamplePoint(const DeviceMedium &m, const float *specPool, Pt3 p, const Wavelengths &wl) {
     MediumProps mp;
+    if (m.type == MEDIUM_RGBGRID) {   // RGBGridMedium::SamplePoint (media.h:377-401)
+        Pt3 pm = ApplyInversePoint(m.mInv, p);
+        Vec3 po = BoundsOffset(m.bmin, m.bmax, pm);
+        mp.sigma_a = m.sigmaScale * (m.rgbA ? RGBGridLookup(m.rgbA, m.nx, m.ny, m.nz, po, wl, nullptr) : Spec(1.f));
+        mp.sigma_s = m.sigmaScale * (m.rgbS ? RGBGridLookup(m.rgbS, m.nx, m.ny, m.nz, po, wl, nullptr) : Spec(1.f));
+        mp.Le = Spec(0.f);
+        if (m.rgbLe && m.rgbLeScale > 0) mp.Le = m.rgbLeScale * RGBGridLookup(m.rgbLe, m.nx, m.ny, m.nz, po, wl, specPool + m.illum);
+        return mp;
+    }
     mp.sigma_a = DenseSample(specPool + m.sigmaA, wl);
     mp.sigma_s = DenseSample(specPool + m.sigmaS, wl);
     mp.Le = Spec(0.f);

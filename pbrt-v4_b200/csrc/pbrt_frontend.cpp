@@ -845,8 +845,31 @@ bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::st
         std::string type = pl.s("type", "");
         if (type == "uniformgrid") m.type = BPT_MEDIUM_UNIFORMGRID;
         else if (type == "homogeneous") m.type = BPT_MEDIUM_HOMOGENEOUS;
-        else { err = "medium type \"" + type + "\" is not supported (homogeneous, uniformgrid)"; return false; }
+        else if (type == "rgbgrid") m.type = BPT_MEDIUM_RGBGRID;
+        else { err = "medium type \"" + type + "\" is not supported (homogeneous, uniformgrid, rgbgrid)"; return false; }
         if (pl.find("preset")) { err = "medium presets are not supported"; return false; }
+        if (m.type == BPT_MEDIUM_RGBGRID) {   // RGBGridMedium::Create (media.cpp:380-453): RGB arrays, one triple per voxel
+            m.nx = pl.i("nx", 1); m.ny = pl.i("ny", 1); m.nz = pl.i("nz", 1);
+            const size_t want = 3 * (size_t)m.nx * m.ny * m.nz;
+            auto grid = [&](const char *name, const float **out) -> bool {
+                *out = nullptr;
+                Param *q = pl.find(name);
+                if (!q) return true;
+                if (q->type != "rgb" || q->nums.size() != want) { err = std::string("rgbgrid medium: \"") + name + "\" needs nx*ny*nz RGB values"; return false; }
+                densityStore.emplace_back(new std::vector<float>(q->nums.begin(), q->nums.end()));
+                *out = densityStore.back()->data();
+                return true;
+            };
+            if (!grid("sigma_a", &m.sigma_a_rgb) || !grid("sigma_s", &m.sigma_s_rgb) || !grid("Le", &m.Le_rgb)) return false;
+            if (!m.sigma_a_rgb && !m.sigma_s_rgb) { err = "RGB grid requires \"sigma_a\" and/or \"sigma_s\" parameter values"; return false; }
+            if (m.Le_rgb && !m.sigma_a_rgb) { err = "RGB grid requires \"sigma_a\" if \"Le\" value provided"; return false; }
+            m.scale = pl.f("scale", 1.f); m.g = pl.f("g", 0.f); m.Le_scale = pl.f("Lescale", 1.f);
+            m.world_from_medium = ToB(gs.ctm.m); m.medium_from_world = ToB(gs.ctm.mInv);
+            m.bounds[0] = m.bounds[1] = m.bounds[2] = 0; m.bounds[3] = m.bounds[4] = m.bounds[5] = 1;
+            if (Param *q = pl.find("p0")) { if (q->nums.size() != 3) { err = "p0 needs three values"; return false; } for (int k = 0; k < 3; ++k) m.bounds[k] = (float)q->nums[k]; }
+            if (Param *q = pl.find("p1")) { if (q->nums.size() != 3) { err = "p1 needs three values"; return false; } for (int k = 0; k < 3; ++k) m.bounds[3 + k] = (float)q->nums[k]; }
+            media.push_back(m); namedMedia[a[0]] = (int)media.size() - 1; return true;
+        }
         if (!getSpectrum(pl, "sigma_a", &m.sigma_a) || !getSpectrum(pl, "sigma_s", &m.sigma_s) || !getSpectrum(pl, "Le", &m.Le)) return false;
         m.scale = pl.f("scale", 1.f); m.g = pl.f("g", 0.f);
         m.Le_scale = m.type == BPT_MEDIUM_HOMOGENEOUS ? pl.f("Lescale", 1.f) : 1.f;

@@ -405,6 +405,27 @@ def smoke(outdir, grid=256, res=(1024, 1024), spp=2048, maxdepth=5, seed=7, homo
     return path
 
 
+def smoke_rgb(outdir, grid=12, res=(64, 64), spp=16, maxdepth=5, seed=7, emission=True):
+    """The smoke scene with an "rgbgrid" medium (RGBGridMedium, media.h:355-427): coloured absorption and scattering per voxel and,
+    with emission, an "Le" grid -- the same box, floor and light as smoke()."""
+    path = smoke(outdir, grid=grid, res=res, spp=spp, maxdepth=maxdepth, seed=seed)
+    s = open(path).read()
+    a = s.index("  MakeNamedMedium"); b = s.index("AttributeEnd\n", a)
+    d = smoke_density(grid, seed).reshape(-1)
+    rng = np.random.Generator(np.random.PCG64(seed + 1))
+    tint = 0.5 + 0.5 * rng.random((d.size, 3))
+    def arr(v):
+        flat = np.asarray(v, dtype=np.float64).reshape(-1)
+        return "\n".join(" ".join(repr(float(x)) for x in flat[i:i + 12]) for i in range(0, flat.size, 12))
+    med = (f"  MakeNamedMedium \"smoke\" \"string type\" \"rgbgrid\" \"float g\" 0.3 \"float scale\" 1.5 \"integer nx\" {grid} \"integer ny\" {grid} \"integer nz\" {grid}\n"
+           f"    \"point3 p0\" [0 0 0] \"point3 p1\" [1 1 1]\n    \"rgb sigma_a\" [\n{arr(2 * d[:, None] * tint)}\n    ]\n    \"rgb sigma_s\" [\n{arr(8 * d[:, None] * tint[:, ::-1])}\n    ]\n")
+    if emission:
+        med += f"    \"rgb Le\" [\n{arr(d[:, None] ** 2 * np.array([2.0, 0.9, 0.3]))}\n    ] \"float Lescale\" 1.5\n"
+    s = s[:a] + med + s[b:]
+    open(path, "w").write(s)
+    return path
+
+
 def as_gbuffer(path, coordinate_system="camera"):
     """Rewrites a generated scene to use Film "gbuffer" (output name *.exr); returns the new path."""
     s = open(path).read().replace('Film "rgb"', f'Film "gbuffer" "string coordinatesystem" "{coordinate_system}"').replace('"out.pfm"', '"out.exr"')

@@ -43,6 +43,7 @@ def _scenes():
         "gbuffer_world": lambda d: scenes.as_gbuffer(scenes.cornell(d, res=(64, 64), spp=4), "world"),
         "smoke_emissive_homogeneous": lambda d: scenes.smoke(d, res=(32, 32), spp=1, homogeneous=True, emission="le"),
         "smoke_emissive_grid": lambda d: scenes.smoke(d, grid=8, res=(32, 32), spp=1, emission="grid"),
+        "smoke_rgbgrid": lambda d: scenes.smoke_rgb(d, grid=6, res=(32, 32), spp=1),
     }
     def filtered(d, flt):
         p = scenes.cornell(d, res=(32, 32), spp=1)

@@ -461,6 +461,19 @@ def test_orthographic_camera_matches_the_live_reference(E, tmp_path, cam):
 
 
 @pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/bin/pbrt not on this box")
+@pytest.mark.parametrize("emission", [False, True])
+def test_rgb_grid_medium_matches_the_live_reference(E, tmp_path, emission):
+    """Medium "rgbgrid" (RGBGridMedium, media.h:355-427): per-voxel RGB absorption / scattering coefficients (and emission) looked up
+    trilinearly as spectra, majorants from the per-voxel spectral maxima; whole render bit-identical."""
+    from pbrt_v4_b200 import scenes, imageio
+    path = scenes.smoke_rgb(str(tmp_path), grid=12, res=(48, 48), spp=16, emission=emission)
+    subprocess.check_call([REF_EXE, "--quiet", "--seed", "0", "--outfile", str(tmp_path / "ref.pfm"), path])
+    ref = imageio.read_pfm(str(tmp_path / "ref.pfm"))
+    img = _render(E, path, 16)
+    assert (bits(img) == bits(ref)).all(), (emission, int((bits(img) != bits(ref)).any(axis=-1).sum()), float(np.abs(img - ref).max()))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/bin/pbrt not on this box")
 def test_textured_gbuffer_and_media_match_the_live_reference(E, tmp_path):
     """Textures with the other users of the ray differentials: GBufferFilm (albedo of a textured, bump-mapped surface; Ns after bump
     mapping) and a camera ray that crosses interface surfaces of a medium before it reaches the textured floor (SkipIntersection)."""

@@ -27,7 +27,7 @@ namespace {
 struct Spec { bpt_spectrum s; std::vector<float> samples; };
 struct Mesh { bpt_mesh m; std::vector<float> P, N, UV; std::vector<int> idx; };
 struct Light { bpt_light l; std::vector<float> img; Spec L; };
-struct Medium { bpt_medium m; std::vector<float> density, leScale; Spec sa, ss, Le; };
+struct Medium { bpt_medium m; std::vector<float> density, leScale; Spec sa, ss, Le; uint64_t rgbHash[3]; };
 struct Material { bpt_material m; Spec sp[8]; };
 struct Texture { bpt_texture t; uint64_t hash; Spec value; };
 struct AreaLight { bpt_area_light a; Spec L; };
@@ -186,6 +186,8 @@ int bpt_scene_add_medium(bpt_engine *e, const bpt_medium *m) {
     e->media.emplace_back(); Medium &o = e->media.back(); o.m = *m; o.sa = Own(m->sigma_a); o.ss = Own(m->sigma_s); o.Le = Own(m->Le);
     if (m->density) o.density.assign(m->density, m->density + (size_t)m->nx * m->ny * m->nz);
     if (m->Le_scale_grid) o.leScale.assign(m->Le_scale_grid, m->Le_scale_grid + (size_t)m->nx * m->ny * m->nz);
+    const float *g3[3] = {m->sigma_a_rgb, m->sigma_s_rgb, m->Le_rgb};
+    for (int k = 0; k < 3; ++k) o.rgbHash[k] = (m->type == BPT_MEDIUM_RGBGRID && g3[k]) ? Fnv(g3[k], 12 * (size_t)m->nx * m->ny * m->nz) : 0;
     return BPT_OK;
 }
 int bpt_scene_set_camera_medium(bpt_engine *e, int m) { e->cameraMedium = m; return BPT_OK; }
@@ -226,6 +228,12 @@ int bpt_scene_commit(bpt_engine *e) {
         char b[96]; snprintf(b, sizeof(b), " grid=%dx%dx%d:%016" PRIx64, md.m.nx, md.m.ny, md.m.nz, Fnv(md.density.data(), md.density.size() * 4));
         std::string s = "medium{type=" + std::to_string(md.m.type) + " sa=" + S(md.sa) + " ss=" + S(md.ss) + " Le=" + S(md.Le) + " scale=" + F(md.m.scale) + " g=" + F(md.m.g) +
                         " Lescale=" + F(md.Le.s.kind == BPT_SPEC_NONE ? 1.f : md.m.Le_scale) + ":" + std::to_string(md.leScale.empty() ? 0ull : (unsigned long long)Fnv(md.leScale.data(), md.leScale.size() * 4));
+        if (md.m.type == BPT_MEDIUM_RGBGRID) {
+            char rb[200]; snprintf(rb, sizeof(rb), " rgbgrid=%dx%dx%d:%016" PRIx64 ",%016" PRIx64 ",%016" PRIx64, md.m.nx, md.m.ny, md.m.nz, md.rgbHash[0], md.rgbHash[1], md.rgbHash[2]);
+            std::string r = "medium{type=2 scale=" + F(md.m.scale) + " g=" + F(md.m.g) + " Lescale=" + F(md.m.Le_scale) + rb + " bounds=";
+            for (int k = 0; k < 6; ++k) r += F(md.m.bounds[k]) + (k < 5 ? "," : "");
+            return r + " " + X(rfm) + "}";
+        }
         if (md.m.type == BPT_MEDIUM_UNIFORMGRID) {
             s += b; s += " bounds=";
             for (int k = 0; k < 6; ++k) s += F(md.m.bounds[k]) + (k < 5 ? "," : "");
