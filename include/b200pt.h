@@ -83,7 +83,7 @@ typedef struct {
 
 typedef struct { int type; float xradius, yradius; float sigma, b, c, tau; } bpt_filter;
 typedef struct {
-    int type;                     /* BPT_SAMPLER_*: ZSOBOL, SOBOL, PADDED_SOBOL, HALTON, STRATIFIED, INDEPENDENT are implemented */
+    int type;                     /* BPT_SAMPLER_*: all but the MLT samplers are implemented */
     int spp; int seed; int randomize;
     int x_samples, y_samples, jitter;   /* STRATIFIED (samplers.cpp:297-319); spp is x_samples * y_samples then */
 } bpt_sampler;

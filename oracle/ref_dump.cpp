@@ -69,6 +69,8 @@
 #include <pbrt/util/rng.h>
 #include <pbrt/util/sampling.h>
 #include <pbrt/util/sobolmatrices.h>
+#include <pbrt/util/pmj02tables.h>
+#include <pbrt/util/bluenoise.h>
 #include <pbrt/util/spectrum.h>
 #undef private
 #undef protected
@@ -136,6 +138,15 @@ static void DumpTables(const char *path) {
             }
         b.u32("vdc_sobol", v);
         b.u32("vdc_sobol_inv", vi);
+    }
+    {   // PMJ02BNSampler: the five pmj02bn sets (fixed point) and the blue-noise textures (two 16-bit values per word, [texture][x][y] order)
+        const uint32_t *pm = &pmj02bnSamples[0][0][0];
+        b.u32("pmj02bn_samples", std::vector<uint32_t>(pm, pm + (size_t)nPMJ02bnSets * nPMJ02bnSamples * 2));
+        const uint16_t *bn = &BlueNoiseTextures[0][0][0];
+        const size_t nb = (size_t)NumBlueNoiseTextures * BlueNoiseResolution * BlueNoiseResolution;
+        std::vector<uint32_t> packed(nb / 2);
+        for (size_t i = 0; i < nb / 2; ++i) packed[i] = (uint32_t)bn[2 * i] | ((uint32_t)bn[2 * i + 1] << 16);
+        b.u32("blue_noise_u16x2", packed);
     }
     b.f32("mip_filter_lut", std::vector<float>(MIPFilterLUT, MIPFilterLUT + MIPFilterLUTSize));
     b.f32("srgb8_to_linear", std::vector<float>(SRGBToLinearLUT, SRGBToLinearLUT + 256));
@@ -842,6 +853,30 @@ static void DumpGolden(const char *path) {
         }
         b.f32("rgbmed_in", in);
         b.f32("rgbmed_out", out);
+    }
+    // PMJ02BNSampler: the same draw sequence as the Sobol' / Halton vectors above, three sample counts (one not a power of four).  (appended last)
+    {
+        Allocator alloc;
+        const int spps[3] = {16, 4, 6};
+        const int seeds[3] = {0, 5, 1};
+        std::vector<float> in, out;
+        for (int c = 0; c < 3; ++c) {
+            PMJ02BNSampler pmj(spps[c], seeds[c], alloc);
+            Sampler smp(&pmj);
+            for (int q = 0; q < 96; ++q) {
+                Point2i p(int(rng.Uniform<float>() * 300), int(rng.Uniform<float>() * 200));
+                int si = std::min(spps[c] - 1, int(rng.Uniform<float>() * spps[c]));
+                in.insert(in.end(), {(float)c, (float)p.x, (float)p.y, (float)si});
+                smp.StartPixelSample(p, si, 0);
+                out.push_back(smp.Get1D());
+                Point2f px = smp.GetPixel2D(); out.push_back(px.x); out.push_back(px.y);
+                out.push_back(smp.Get1D());
+                Point2f l = smp.Get2D(); out.push_back(l.x); out.push_back(l.y);
+                for (int k = 0; k < 5; ++k) { out.push_back(smp.Get1D()); Point2f u = smp.Get2D(); out.push_back(u.x); out.push_back(u.y); }
+            }
+        }
+        b.f32("pmj_in", in);
+        b.f32("pmj_out", out);
     }
 }
 

@@ -180,6 +180,9 @@ struct bpt_engine {
     DevBuf<int> indexPool;
     DevBuf<float> nPool, uvPool, specPool;
     DevBuf<DeviceMaterial> dMaterials;
+    DevBuf<uint32_t> dPmjSamples;
+    DevBuf<uint16_t> dBlueNoise;
+    DevBuf<float> dPmjPixel;
     DevBuf<int> dPrimes;
     DevBuf<uint16_t> dHaltonPerms;
     DevBuf<uint32_t> dHaltonPermOffset;
@@ -492,8 +495,8 @@ extern "C" int bpt_scene_set_filter(bpt_engine *e, const bpt_filter *f) {
 extern "C" int bpt_scene_set_sampler(bpt_engine *e, const bpt_sampler *s) {
     if (!e || !s) return BPT_ERR_INVALID;
     if (s->type != BPT_SAMPLER_ZSOBOL && s->type != BPT_SAMPLER_INDEPENDENT && s->type != BPT_SAMPLER_STRATIFIED && s->type != BPT_SAMPLER_PADDED_SOBOL &&
-        s->type != BPT_SAMPLER_SOBOL && s->type != BPT_SAMPLER_HALTON)
-        return e->fail(BPT_ERR_UNSUPPORTED, "sampler not implemented (zsobol, sobol, paddedsobol, halton, stratified, independent)");
+        s->type != BPT_SAMPLER_SOBOL && s->type != BPT_SAMPLER_HALTON && s->type != BPT_SAMPLER_PMJ02BN)
+        return e->fail(BPT_ERR_UNSUPPORTED, "sampler not implemented (zsobol, sobol, paddedsobol, halton, pmj02bn, stratified, independent)");
     if (s->type == BPT_SAMPLER_HALTON && s->randomize == BPT_RANDOMIZE_FAST_OWEN) return e->fail(BPT_ERR_INVALID, "\"fastowen\" randomization not supported by Halton sampler");
     e->sampler = *s;
     if (s->type == BPT_SAMPLER_STRATIFIED) {
@@ -779,11 +782,22 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     // ---- sampler (samplers.h:228-239)
     SamplerParams sp{};
     sp.type = e->sampler.type == BPT_SAMPLER_ZSOBOL ? 0 : e->sampler.type == BPT_SAMPLER_STRATIFIED ? 2 : e->sampler.type == BPT_SAMPLER_PADDED_SOBOL ? 3 :
-              e->sampler.type == BPT_SAMPLER_SOBOL ? 4 : e->sampler.type == BPT_SAMPLER_HALTON ? 5 : 1;
+              e->sampler.type == BPT_SAMPLER_SOBOL ? 4 : e->sampler.type == BPT_SAMPLER_HALTON ? 5 : e->sampler.type == BPT_SAMPLER_PMJ02BN ? 6 : 1;
     sp.xSamples = e->sampler.x_samples; sp.ySamples = e->sampler.y_samples; sp.jitter = e->sampler.jitter;
     sp.randomize = e->sampler.randomize;
     sp.seed = e->sampler.seed;
     sp.samplesPerPixel = e->sampler.spp;
+    if (sp.type == 6) {   // PMJ02BNSampler::PMJ02BNSampler (samplers.cpp:173-207)
+        if (!e->tables.u32.count("pmj02bn_samples") || !e->tables.u32.count("blue_noise_u16x2"))
+            return e->fail(BPT_ERR_IO, "tables blob lacks the pmj02bn sampler tables (regenerate it with oracle/_ref/bin/ref_dump tables)");
+        const std::vector<uint32_t> &pm = e->tables.u32.at("pmj02bn_samples"), &bn = e->tables.u32.at("blue_noise_u16x2");
+        std::vector<float> pix;
+        if (!BuildPmjPixelSamples(pm.data(), sp.samplesPerPixel, &sp.pixelTileSize, &pix)) return e->fail(BPT_ERR_INVALID, "PMJ02BNSampler only supports up to 65536 samples per pixel");
+        std::vector<uint16_t> bn16(2 * bn.size());
+        for (size_t i = 0; i < bn.size(); ++i) { bn16[2 * i] = (uint16_t)(bn[i] & 0xffffu); bn16[2 * i + 1] = (uint16_t)(bn[i] >> 16); }
+        ECK(e->dPmjSamples.upload(pm)); ECK(e->dBlueNoise.upload(bn16)); ECK(e->dPmjPixel.upload(pix));
+        sp.pmjSamples = e->dPmjSamples.p; sp.blueNoise = e->dBlueNoise.p; sp.pmjPixelSamples = e->dPmjPixel.p;
+    }
     if (sp.type == 5) {   // HaltonSampler::HaltonSampler (samplers.cpp:32-52), ComputeRadicalInversePermutations (lowdiscrepancy.cpp:47-55)
         std::vector<int> primes = FirstPrimes(1000);
         ECK(e->dPrimes.upload(primes));

@@ -786,7 +786,8 @@ bool Frontend::directive(Tokenizer &t, const std::string &d, std::vector<std::st
         if (ty == "zsobol") sampler.type = BPT_SAMPLER_ZSOBOL; else if (ty == "independent") sampler.type = BPT_SAMPLER_INDEPENDENT;
         else if (ty == "paddedsobol") sampler.type = BPT_SAMPLER_PADDED_SOBOL; else if (ty == "stratified") sampler.type = BPT_SAMPLER_STRATIFIED;
         else if (ty == "sobol") sampler.type = BPT_SAMPLER_SOBOL; else if (ty == "halton") sampler.type = BPT_SAMPLER_HALTON;
-        else { err = "sampler \"" + ty + "\" is not supported (zsobol, sobol, paddedsobol, halton, stratified, independent)"; return false; }
+        else if (ty == "pmj02bn") sampler.type = BPT_SAMPLER_PMJ02BN;
+        else { err = "sampler \"" + ty + "\" is not supported (zsobol, sobol, paddedsobol, halton, pmj02bn, stratified, independent)"; return false; }
         sampler.spp = pl.i("pixelsamples", 16); sampler.seed = pl.i("seed", seedOption);
         if (sampler.type == BPT_SAMPLER_STRATIFIED) {   // StratifiedSampler::Create (samplers.cpp:297-319)
             sampler.jitter = pl.b("jitter", true);

@@ -190,7 +190,7 @@ BPT_HD uint64_t Hash_pixel_dim_seed(int px, int py, int dimension, int seed) {
 }
 
 struct SamplerParams {
-    int type;                  // 0 = zsobol, 1 = independent, 2 = stratified, 3 = paddedsobol, 4 = sobol, 5 = halton
+    int type;                  // 0 = zsobol, 1 = independent, 2 = stratified, 3 = paddedsobol, 4 = sobol, 5 = halton, 6 = pmj02bn
     int xSamples, ySamples, jitter;   // stratified (samplers.h:568-625)
     int randomize;             // RandomizeStrategy
     int seed;
@@ -214,6 +214,12 @@ struct SamplerParams {
     const uint16_t *haltonPerms;
     const uint32_t *haltonPermOffset;
     int baseScales[2], baseExponents[2], multInverse[2];
+    // PMJ02BNSampler (samplers.h:367-439, samplers.cpp:173-207): the five 65536-point pmj02bn sets (fixed point), the 48 blue-noise
+    // textures [texture][x][y], and the pixel samples of the first set sorted into pixelTileSize^2 pixels
+    const uint32_t *pmjSamples;     // [5][65536][2]
+    const uint16_t *blueNoise;      // [48][128][128]
+    const float *pmjPixelSamples;   // [pixelTileSize^2 * samplesPerPixel][2]
+    int pixelTileSize;
 };
 
 // BPT_OUTLINE_SAMPLER (device, the translation unit that owns the Sobol tables): ZSobol Get1D / Get2D as ONE real function
@@ -248,6 +254,7 @@ struct Sampler {
         dimension = dim;
         pixel = -1;
         px = pxIn; py = pyIn; sampleIndex = index;
+        if (sp->type == 6) { dimension = dim > 2 ? dim : 2; return; }   // PMJ02BNSampler::StartPixelSample (samplers.h:381-385)
         if (sp->type == 5) {   // HaltonSampler::StartPixelSample (samplers.h:53-71)
             int64_t haltonIndex = 0;
             int sampleStride = sp->baseScales[0] * sp->baseScales[1];
@@ -416,12 +423,48 @@ struct Sampler {
         }
         return stdmin(invBaseM * reversedDigits, kOneMinusEpsilon);
     }
-    // Sampler::GetPixel2D: the film-plane sample of GetCameraSample (samplers.h:797-814); SobolSampler (:525-536) and HaltonSampler
-    // (:90-93) have their own
+    // PMJ02BNSampler::Get1D / Get2D / GetPixel2D (samplers.h:388-427), BlueNoise (util/bluenoise.h:25-30), GetPMJ02BNSample
+    // (util/pmj02tables.h:26-41)
+    BPT_HD float BlueNoise(int textureIndex) const {
+        textureIndex %= 48;
+        int x = px % 128, y = py % 128;
+        return sp->blueNoise[((size_t)textureIndex * 128 + x) * 128 + y] / 65535.f;
+    }
+    BPT_HD float Pmj1D() {
+        uint64_t hash = Hash_pixel_dim_seed(px, py, dimension, sp->seed);
+        int index = PermutationElement((uint32_t)sampleIndex, (uint32_t)sp->samplesPerPixel, (uint32_t)hash);
+        float delta = BlueNoise(dimension);
+        ++dimension;
+        return stdmin((index + delta) / sp->samplesPerPixel, kOneMinusEpsilon);
+    }
+    BPT_HD Vec2 Pmj2D() {
+        int index = sampleIndex;
+        int pmjInstance = dimension / 2;
+        if (pmjInstance >= 5) {
+            uint64_t hash = Hash_pixel_dim_seed(px, py, dimension, sp->seed);
+            index = PermutationElement((uint32_t)sampleIndex, (uint32_t)sp->samplesPerPixel, (uint32_t)hash);
+        }
+        const uint32_t *smp = sp->pmjSamples + ((size_t)(pmjInstance % 5) * 65536 + (size_t)(index % 65536)) * 2;
+        Vec2 u((float)smp[0] * 0x1p-32f, (float)smp[1] * 0x1p-32f);
+        u.x += BlueNoise(dimension); u.y += BlueNoise(dimension + 1);
+        if (u.x >= 1) u.x -= 1;
+        if (u.y >= 1) u.y -= 1;
+        dimension += 2;
+        return {stdmin(u.x, kOneMinusEpsilon), stdmin(u.y, kOneMinusEpsilon)};
+    }
+    // Sampler::GetPixel2D: the film-plane sample of GetCameraSample (samplers.h:797-814); SobolSampler (:525-536), HaltonSampler
+    // (:90-93) and PMJ02BNSampler (:399-403) have their own
+    BPT_HD Vec2 PmjPixel2D() const {
+        int tx = px % sp->pixelTileSize, ty = py % sp->pixelTileSize;
+        int offset = (tx + ty * sp->pixelTileSize) * sp->samplesPerPixel;
+        const float *q = sp->pmjPixelSamples + 2 * (size_t)(offset + sampleIndex);
+        return {q[0], q[1]};
+    }
     BPT_HD Vec2 GetPixel2D() {
 #if BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
         if (sp->type >= 4) { float2 r = QmcOutlined(px, py, sampleIndex, sobolIndex, dimension, 0); return {r.x, r.y}; }
 #endif
+        if (sp->type == 6) return PmjPixel2D();
         if (sp->type == 5)
             return {RadicalInverse(2, (uint64_t)sobolIndex >> sp->baseExponents[0]), RadicalInverse(3, (uint64_t)(sobolIndex / sp->baseScales[1]))};
         if (sp->type != 4) return Get2D();
@@ -440,6 +483,7 @@ struct Sampler {
             return r.x;
         }
 #endif
+        if (sp->type == 6) return Pmj1D();
         if (sp->type == 5) {
             if (dimension >= 1000) dimension = 2;
             return HaltonDimension(dimension++);
@@ -470,6 +514,7 @@ struct Sampler {
             return {r.x, r.y};
         }
 #endif
+        if (sp->type == 6) return Pmj2D();
         if (sp->type == 5) {
             if (dimension + 1 >= 1000) dimension = 2;
             int dim = dimension;
@@ -505,8 +550,9 @@ static __device__ __noinline__ float2 QmcOutlined(int px, int py, int sampleInde
     s.sp = &c_sampler; s.px = px; s.py = py; s.sampleIndex = sampleIndex; s.sobolIndex = sobolIndex; s.dimension = dimension; s.pixel = -1;
     float2 r = make_float2(0.f, 0.f);
     const int type = c_sampler.type;
-    if (nd == 0) {   // GetPixel2D of the Sobol' and Halton samplers (the member functions' own code, not the dispatch above)
-        if (type == 5) { r.x = Sampler::RadicalInverse(2, (uint64_t)sobolIndex >> c_sampler.baseExponents[0]); r.y = Sampler::RadicalInverse(3, (uint64_t)(sobolIndex / c_sampler.baseScales[1])); }
+    if (nd == 0) {   // GetPixel2D of the Sobol', Halton and pmj02bn samplers (the member functions' own code, not the dispatch above)
+        if (type == 6) { Vec2 u = s.PmjPixel2D(); r.x = u.x; r.y = u.y; }
+        else if (type == 5) { r.x = Sampler::RadicalInverse(2, (uint64_t)sobolIndex >> c_sampler.baseExponents[0]); r.y = Sampler::RadicalInverse(3, (uint64_t)(sobolIndex / c_sampler.baseScales[1])); }
         else {
             float u[2] = {s.SobolDimension(0, 0), s.SobolDimension(1, 0)};
             const int pix[2] = {px, py};
@@ -517,6 +563,8 @@ static __device__ __noinline__ float2 QmcOutlined(int px, int py, int sampleInde
     }
     if (type == 3) {
         if (nd == 1) r.x = s.OtherGet1D(); else { Vec2 u = s.OtherGet2D(); r.x = u.x; r.y = u.y; }
+    } else if (type == 6) {
+        if (nd == 1) r.x = s.Pmj1D(); else { Vec2 u = s.Pmj2D(); r.x = u.x; r.y = u.y; }
     } else if (type == 4) {
         r.x = s.SobolDimension(dimension, c_sampler.randomize);
         if (nd == 2) r.y = s.SobolDimension(dimension + 1, c_sampler.randomize);
@@ -763,6 +811,29 @@ inline void BuildHaltonPermutations(const std::vector<int> &primes, int seed, st
             for (int digitValue = 0; digitValue < base; ++digitValue) perms->push_back((uint16_t)PermutationElement((uint32_t)digitValue, (uint32_t)base, (uint32_t)dseed));
         }
     }
+}
+// PMJ02BNSampler::PMJ02BNSampler (samplers.cpp:173-207): the points of the first pmj02bn set sorted into the pixels of a
+// pixelTileSize x pixelTileSize tile, samplesPerPixel each (GetPMJ02BNSample's CPU branch converts the fixed-point values in double)
+inline bool BuildPmjPixelSamples(const uint32_t *pmjSamples, int samplesPerPixel, int *pixelTileSize, std::vector<float> *pixelSamples) {
+    auto log4 = [](int v) { int l = 0; while (v >>= 2) ++l; return l; };
+    auto roundUpPow4 = [](int v) { int r = 1; while (r < v) r <<= 2; return r; };
+    if (samplesPerPixel > 65536 || samplesPerPixel < 1) return false;
+    *pixelTileSize = 1 << (log4(65536) - log4(roundUpPow4(samplesPerPixel)));
+    const int T = *pixelTileSize;
+    pixelSamples->assign((size_t)2 * T * T * samplesPerPixel, 0.f);
+    std::vector<int> nStored((size_t)T * T, 0);
+    for (int i = 0; i < 65536; ++i) {
+        float px = (float)(pmjSamples[2 * i] * 0x1p-32), py = (float)(pmjSamples[2 * i + 1] * 0x1p-32);
+        px *= T; py *= T;
+        int pixelOffset = int(px) + int(py) * T;
+        if (nStored[pixelOffset] == samplesPerPixel) continue;
+        int sampleOffset = pixelOffset * samplesPerPixel + nStored[pixelOffset];
+        (*pixelSamples)[2 * (size_t)sampleOffset] = px - std::floor(px);
+        (*pixelSamples)[2 * (size_t)sampleOffset + 1] = py - std::floor(py);
+        ++nStored[pixelOffset];
+    }
+    for (int c : nStored) if (c != samplesPerPixel) return false;
+    return true;
 }
 inline void HaltonPixelConstants(int xres, int yres, SamplerParams *sp) {
     const int fullRes[2] = {xres, yres};

@@ -69,7 +69,7 @@ def _scenes():
         return p
     for k, smp in enumerate(['"paddedsobol" "integer pixelsamples" 8', '"paddedsobol" "integer pixelsamples" 4 "string randomization" "owen"',
                              '"stratified" "integer xsamples" 3 "integer ysamples" 2', '"stratified" "bool jitter" false', '"independent" "integer pixelsamples" 5',
-                             '"sobol" "integer pixelsamples" 8 "string randomization" "owen"', '"halton" "integer pixelsamples" 8', '"halton" "string randomization" "owen" "integer seed" 2']):
+                             '"sobol" "integer pixelsamples" 8 "string randomization" "owen"', '"halton" "integer pixelsamples" 8', '"halton" "string randomization" "owen" "integer seed" 2', '"pmj02bn" "integer pixelsamples" 4']):
         cases["sampler_%d" % k] = (lambda d, smp=smp: with_sampler(d, smp))
     def with_camera(d, cam):
         p = scenes.cornell(d, res=(32, 32), spp=1)

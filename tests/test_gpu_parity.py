@@ -343,9 +343,10 @@ def test_gbuffer_film_with_media_and_interface_surfaces_matches_the_live_referen
                                  '"sobol" "integer pixelsamples" 8', '"sobol" "integer pixelsamples" 6 "string randomization" "none"',
                                  '"sobol" "integer pixelsamples" 4 "string randomization" "permutedigits" "integer seed" 3',
                                  '"halton" "integer pixelsamples" 8', '"halton" "integer pixelsamples" 5 "string randomization" "none"',
-                                 '"halton" "integer pixelsamples" 4 "string randomization" "owen"'])
+                                 '"halton" "integer pixelsamples" 4 "string randomization" "owen"',
+                                 '"pmj02bn" "integer pixelsamples" 16', '"pmj02bn" "integer pixelsamples" 6 "integer seed" 2'])
 def test_samplers_of_the_dispatch_surface_match_the_live_reference(E, tmp_path, smp):
-    """Sampler {Independent, Stratified, Halton, PaddedSobol, Sobol, ZSobol} (base/sampler.h:40-42; samplers.h:367-625): every sampler is a
+    """Sampler {PMJ02BN, Independent, Stratified, Halton, PaddedSobol, Sobol, ZSobol} (base/sampler.h:40-42; samplers.h:367-625): every sampler is a
     stateless function of (pixel, sample index, dimension), so a whole Cornell render must be bit-identical to the reference's.
     Un-jittered stratified samples sit on an exact lattice, and in the axis-aligned box 0.8 % of those camera rays run exactly through
     edges shared by two walls (same hit point bit for bit, either primitive is a valid closest hit: profiles/r02o_stratified_diag.log);

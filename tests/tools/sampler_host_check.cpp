@@ -69,6 +69,37 @@ int main() {
         }
     }
     int total = 0;
+    // ---- pmj02bn
+    if (!g.count("pmj_in") || !tb.count("pmj02bn_samples") || !tb.count("blue_noise_u16x2")) { printf("missing pmj golden / tables\n"); return 3; }
+    {
+        std::vector<float> pin = F(g["pmj_in"]), pout = F(g["pmj_out"]);
+        const std::vector<uint32_t> &pm = tb["pmj02bn_samples"], &bn = tb["blue_noise_u16x2"];
+        std::vector<uint16_t> bn16(2 * bn.size());
+        for (size_t i = 0; i < bn.size(); ++i) { bn16[2 * i] = (uint16_t)(bn[i] & 0xffffu); bn16[2 * i + 1] = (uint16_t)(bn[i] >> 16); }
+        const int spps[3] = {16, 4, 6}, seeds[3] = {0, 5, 1}, PO = 21;
+        int pbad = 0, pn = (int)pin.size() / 4;
+        std::vector<float> pix; int curCfg = -1, tile = 0;
+        for (int q = 0; q < pn; ++q) {
+            const float *a = &pin[4 * q], *o = &pout[(size_t)PO * q];
+            int c = (int)a[0];
+            SamplerParams sp; memset(&sp, 0, sizeof(sp));
+            sp.type = 6; sp.seed = seeds[c]; sp.samplesPerPixel = spps[c];
+            if (c != curCfg) { if (!BuildPmjPixelSamples(pm.data(), spps[c], &tile, &pix)) { printf("pixel sample table failed\n"); return 2; } curCfg = c; }
+            sp.pmjSamples = pm.data(); sp.blueNoise = bn16.data(); sp.pmjPixelSamples = pix.data(); sp.pixelTileSize = tile;
+            Sampler s; std::vector<float> m;
+            s.StartPixelSample(&sp, (int)a[1], (int)a[2], (int)a[3], 0);
+            m.push_back(s.Get1D());
+            Vec2 px = s.GetPixel2D(); m.push_back(px.x); m.push_back(px.y);
+            m.push_back(s.Get1D());
+            Vec2 l = s.Get2D(); m.push_back(l.x); m.push_back(l.y);
+            for (int k = 0; k < 5; ++k) { m.push_back(s.Get1D()); Vec2 u = s.Get2D(); m.push_back(u.x); m.push_back(u.y); }
+            bool ok = true;
+            for (int k = 0; k < PO; ++k) ok = ok && eq(m[k], o[k]);
+            if (!ok && pbad++ < 3) { printf("pmj02bn config %d pixel %d %d sample %d:", c, (int)a[1], (int)a[2], (int)a[3]); for (int k = 0; k < PO; ++k) if (!eq(m[k], o[k])) printf(" [%d] %.9g vs %.9g", k, m[k], o[k]); printf("\n"); }
+        }
+        printf("pmj02bn (spp 16 / 4 / 6): %d mismatches of %d\n", pbad, pn);
+        total += pbad;
+    }
     for (int c = 0; c < 7; ++c) { printf("%s spp %d seed %d randomize %d: %d mismatches of %d\n", cfgs[c].kind ? "halton" : "sobol", cfgs[c].spp, cfgs[c].seed, cfgs[c].r, bad[c], cnt[c]); total += bad[c]; }
     return total ? 2 : 0;
 }
