@@ -164,6 +164,27 @@ typedef struct {
     float alpha;                  /* constant alpha (texture-valued alpha: not implemented) */
 } bpt_mesh;
 
+/* Shape "sphere" / "disk" / "cylinder" (shapes.cpp:72-83, 107-117, 135-146: Sphere / Disk / Cylinder::Create).  Parameters as the
+ * .pbrt file gives them (phimax in degrees; the constructors' clamping is the engine's business).  Intersected as custom primitives of
+ * the BVH like the reference's GPU path does (gpu/optix/aggregate.cpp:848-1025, optix.cu:301-377).  Stochastic alpha on a quadric
+ * is not implemented (the reference re-intersects the same shape behind a rejected hit, cpu/primitive.cpp:66-73). */
+#define BPT_SHAPE_SPHERE 0
+#define BPT_SHAPE_DISK 1
+#define BPT_SHAPE_CYLINDER 2
+typedef struct {
+    int type;
+    float radius;                 /* all three */
+    float zmin, zmax;             /* sphere, cylinder */
+    float phimax;                 /* degrees */
+    float height, innerradius;    /* disk */
+    bpt_mat4 world_from_object;   /* as bpt_mesh */
+    bpt_mat4 object_from_world;
+    int reverse_orientation;
+    int material, area_light;
+    int medium_inside, medium_outside;
+    int object_id;
+} bpt_quadric;
+
 typedef struct {
     int object_id;
     bpt_mat4 world_from_instance;  /* CTM at the ObjectInstance directive */
@@ -248,6 +269,7 @@ int bpt_scene_set_materials(bpt_engine *e, const bpt_material *m, int n);
 int bpt_scene_set_textures(bpt_engine *e, const bpt_texture *t, int n);
 int bpt_scene_set_area_lights(bpt_engine *e, const bpt_area_light *a, int n);
 int bpt_scene_add_mesh(bpt_engine *e, const bpt_mesh *m);
+int bpt_scene_add_quadric(bpt_engine *e, const bpt_quadric *q);   /* takes its place among the meshes in scene order (area-light order, scene.cpp CreateLights) */
 int bpt_scene_add_instance(bpt_engine *e, const bpt_instance *i);
 int bpt_scene_add_light(bpt_engine *e, const bpt_light *l);
 int bpt_scene_add_medium(bpt_engine *e, const bpt_medium *m);

@@ -59,7 +59,7 @@ struct Api {
 #define BPT_FN(name) decltype(&::name) name = nullptr;
     BPT_FN(bpt_create) BPT_FN(bpt_destroy) BPT_FN(bpt_last_error) BPT_FN(bpt_scene_begin) BPT_FN(bpt_scene_set_transform_space)
     BPT_FN(bpt_scene_set_camera) BPT_FN(bpt_scene_set_film) BPT_FN(bpt_scene_set_filter) BPT_FN(bpt_scene_set_sampler)
-    BPT_FN(bpt_scene_set_integrator) BPT_FN(bpt_scene_set_materials) BPT_FN(bpt_scene_set_textures) BPT_FN(bpt_scene_set_area_lights) BPT_FN(bpt_scene_add_mesh)
+    BPT_FN(bpt_scene_set_integrator) BPT_FN(bpt_scene_set_materials) BPT_FN(bpt_scene_set_textures) BPT_FN(bpt_scene_set_area_lights) BPT_FN(bpt_scene_add_mesh) BPT_FN(bpt_scene_add_quadric)
     BPT_FN(bpt_scene_add_instance) BPT_FN(bpt_scene_add_light) BPT_FN(bpt_scene_add_medium) BPT_FN(bpt_scene_set_camera_medium)
     BPT_FN(bpt_scene_commit) BPT_FN(bpt_render) BPT_FN(bpt_film_resolve) BPT_FN(bpt_film_resolve_gbuffer)
 #undef BPT_FN
@@ -69,7 +69,7 @@ struct Api {
 #define BPT_FN(name) name = (decltype(name))dlsym(h, #name); if (!name) ErrorExit("%s: symbol %s missing", path, #name);
         BPT_FN(bpt_create) BPT_FN(bpt_destroy) BPT_FN(bpt_last_error) BPT_FN(bpt_scene_begin) BPT_FN(bpt_scene_set_transform_space)
         BPT_FN(bpt_scene_set_camera) BPT_FN(bpt_scene_set_film) BPT_FN(bpt_scene_set_filter) BPT_FN(bpt_scene_set_sampler)
-        BPT_FN(bpt_scene_set_integrator) BPT_FN(bpt_scene_set_materials) BPT_FN(bpt_scene_set_textures) BPT_FN(bpt_scene_set_area_lights) BPT_FN(bpt_scene_add_mesh)
+        BPT_FN(bpt_scene_set_integrator) BPT_FN(bpt_scene_set_materials) BPT_FN(bpt_scene_set_textures) BPT_FN(bpt_scene_set_area_lights) BPT_FN(bpt_scene_add_mesh) BPT_FN(bpt_scene_add_quadric)
         BPT_FN(bpt_scene_add_instance) BPT_FN(bpt_scene_add_light) BPT_FN(bpt_scene_add_medium) BPT_FN(bpt_scene_set_camera_medium)
         BPT_FN(bpt_scene_commit) BPT_FN(bpt_render) BPT_FN(bpt_film_resolve) BPT_FN(bpt_film_resolve_gbuffer)
 #undef BPT_FN
@@ -550,6 +550,24 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
     auto addShape = [&](const ShapeSceneEntity &sh, int objectId) {
         const ParameterDictionary &d = sh.parameters;
         std::vector<float> P, N, UV; std::vector<int> idx;
+        if (sh.name == "sphere" || sh.name == "disk" || sh.name == "cylinder") {
+            // Sphere / Disk / Cylinder::Create (shapes.cpp:72-83, 107-117, 135-146)
+            bpt_quadric q; std::memset(&q, 0, sizeof(q));
+            q.radius = d.GetOneFloat("radius", 1.f); q.phimax = d.GetOneFloat("phimax", 360.f);
+            if (sh.name == "sphere") { q.type = BPT_SHAPE_SPHERE; q.zmin = d.GetOneFloat("zmin", -q.radius); q.zmax = d.GetOneFloat("zmax", q.radius); }
+            else if (sh.name == "cylinder") { q.type = BPT_SHAPE_CYLINDER; q.zmin = d.GetOneFloat("zmin", -1.f); q.zmax = d.GetOneFloat("zmax", 1.f); }
+            else { q.type = BPT_SHAPE_DISK; q.height = d.GetOneFloat("height", 0.f); q.innerradius = d.GetOneFloat("innerradius", 0.f); }
+            if (!d.GetTexture("alpha").empty() || d.GetOneFloat("alpha", 1.f) < 1.f) ErrorExit(&sh.loc, "alpha on a %s is not implemented by the engine", sh.name.ToString());
+            q.world_from_object = ToB(sh.renderFromObject->GetMatrix()); q.object_from_world = ToB(sh.renderFromObject->GetInverseMatrix());
+            q.reverse_orientation = sh.reverseOrientation;
+            int qmi = sh.materialName.empty() ? sh.materialIndex : namedIndex.at(sh.materialName);
+            q.material = mats[qmi].type == BPT_MAT_INTERFACE ? -1 : qmi;
+            q.area_light = sh.lightIndex;
+            q.medium_inside = mediumOf(sh.insideMedium); q.medium_outside = mediumOf(sh.outsideMedium);
+            q.object_id = objectId;
+            Check(api, e, api.bpt_scene_add_quadric(e, &q), "bpt_scene_add_quadric");
+            return;
+        }
         if (sh.name == "trianglemesh") {
             for (Point3f p : d.GetPoint3fArray("P")) { P.push_back(p.x); P.push_back(p.y); P.push_back(p.z); }
             idx = d.GetIntArray("indices");
@@ -564,7 +582,7 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
             for (Normal3f n : mesh.n) { N.push_back(n.x); N.push_back(n.y); N.push_back(n.z); }
             for (Point2f u : mesh.uv) { UV.push_back(u.x); UV.push_back(u.y); }
             idx.assign(mesh.triIndices.begin(), mesh.triIndices.end());
-        } else ErrorExit(&sh.loc, "shape \"%s\" is not implemented by the engine (triangle meshes)", sh.name.ToString());
+        } else ErrorExit(&sh.loc, "shape \"%s\" is not implemented by the engine (triangle meshes, sphere, disk, cylinder)", sh.name.ToString());
         if (!d.GetTexture("alpha").empty()) ErrorExit(&sh.loc, "texture-valued alpha is not implemented by the engine");
         bpt_mesh m; std::memset(&m, 0, sizeof(m));
         if (Float alpha = d.GetOneFloat("alpha", 1.f); alpha < 1.f) { m.has_alpha = 1; m.alpha = alpha; }   // getAlphaTexture (scene.cpp)

@@ -878,6 +878,91 @@ static void DumpGolden(const char *path) {
         b.f32("pmj_in", in);
         b.f32("pmj_out", out);
     }
+    // quadrics (Sphere / Disk / Cylinder): constructor-derived members, bounds, BasicIntersect + InteractionFromIntersection,
+    // Sample(ctx, u) and PDF(ctx, wi) -- for csrc/quadrics.h (tests/tools/quadric_host_check.cpp)
+    {
+        RNG qr(977);
+        auto U = [&]() { return qr.Uniform<float>(); };
+        std::vector<float> shapes, rays, hits, samp, sampOut;
+        const int nShapes = 18, nRays = 400, nSamp = 96;
+        for (int k = 0; k < nShapes; ++k) {
+            int type = k % 3;   // 0 sphere, 1 disk, 2 cylinder
+            Transform rfo = Translate(Vector3f(2 * U() - 1, 2 * U() - 1, 2 * U() - 1)) * Rotate(360 * U(), Normalize(Vector3f(U() - .5f, U() - .5f, U() - .3f)));
+            if (k >= 6) rfo = rfo * Scale(.5f + U(), .5f + U(), (k % 2 ? -1.f : 1.f) * (.5f + U()));
+            if (k < 3) rfo = Transform();
+            // the scene's way of deriving the inverse (scene.h:475-477): rebuilt from the product matrix
+            rfo = Transform(rfo.GetMatrix());
+            Transform ofr = Inverse(rfo);
+            bool reverse = (k / 3) % 2 == 1;
+            float radius = .4f + U(), zmin = -radius * (k < 9 ? 2.f : U()), zmax = radius * (k < 9 ? 2.f : U()), phimax = k < 9 ? 360.f : 90.f + 250.f * U();
+            if (type == 2) { zmin = -.3f - U(); zmax = .3f + U(); }
+            float height = U() - .5f, inner = k < 9 ? 0.f : .3f * radius * U();
+            Sphere sph(&rfo, &ofr, reverse, radius, zmin, zmax, phimax);
+            Disk dsk(&rfo, &ofr, reverse, height, radius, inner, phimax);
+            Cylinder cyl(&rfo, &ofr, reverse, radius, zmin, zmax, phimax);
+            Shape shape = type == 0 ? Shape(&sph) : (type == 1 ? Shape(&dsk) : Shape(&cyl));
+            shapes.insert(shapes.end(), {(float)type, radius, zmin, zmax, phimax, height, inner, reverse ? 1.f : 0.f});
+            for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) shapes.push_back(rfo.GetMatrix()[i][j]);
+            for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) shapes.push_back(ofr.GetMatrix()[i][j]);
+            Bounds3f bb = shape.Bounds();
+            DirectionCone nb = shape.NormalBounds();
+            shapes.insert(shapes.end(), {bb.pMin.x, bb.pMin.y, bb.pMin.z, bb.pMax.x, bb.pMax.y, bb.pMax.z, shape.Area(), nb.w.x, nb.w.y, nb.w.z, nb.cosTheta,
+                                         rfo.SwapsHandedness() ? 1.f : 0.f});
+            Point3f c = rfo(Point3f(0, 0, type == 1 ? height : 0));
+            for (int r = 0; r < nRays; ++r) {
+                Point3f o = c + (r % 5 == 0 ? .3f : 3.f) * Vector3f(2 * U() - 1, 2 * U() - 1, 2 * U() - 1);
+                Point3f tgt = c + radius * Vector3f(2 * U() - 1, 2 * U() - 1, 2 * U() - 1);
+                Vector3f d = tgt - o;
+                if (r % 3 == 0) d = Normalize(d);
+                float tMax = r % 7 == 0 ? 2 * U() : Infinity;
+                rays.insert(rays.end(), {o.x, o.y, o.z, d.x, d.y, d.z, tMax});
+                Ray ray(o, d);
+                pstd::optional<ShapeIntersection> si = shape.Intersect(ray, tMax);
+                float out[40] = {0};
+                out[0] = si ? 1.f : 0.f;
+                out[39] = shape.IntersectP(ray, tMax) ? 1.f : 0.f;
+                if (si) {
+                    const SurfaceInteraction &in = si->intr;
+                    float v[] = {si->tHit, in.pi.x.LowerBound(), in.pi.x.UpperBound(), in.pi.y.LowerBound(), in.pi.y.UpperBound(), in.pi.z.LowerBound(), in.pi.z.UpperBound(),
+                                 in.n.x, in.n.y, in.n.z, in.shading.n.x, in.shading.n.y, in.shading.n.z, in.uv[0], in.uv[1], in.dpdu.x, in.dpdu.y, in.dpdu.z,
+                                 in.dpdv.x, in.dpdv.y, in.dpdv.z, in.dndu.x, in.dndu.y, in.dndu.z, in.dndv.x, in.dndv.y, in.dndv.z, in.wo.x, in.wo.y, in.wo.z,
+                                 in.shading.dpdu.x, in.shading.dpdu.y, in.shading.dpdu.z};
+                    for (size_t q = 0; q < sizeof(v) / sizeof(v[0]); ++q) out[1 + q] = v[q];
+                }
+                hits.insert(hits.end(), out, out + 40);
+            }
+            for (int r = 0; r < nSamp; ++r) {
+                // reference points outside, near and (spheres) inside the shape
+                float dist = r % 4 == 0 ? .5f * radius : (r % 4 == 1 ? 1.05f * radius : 4.f + 40.f * U());
+                Point3f p = c + dist * Normalize(Vector3f(2 * U() - 1, 2 * U() - 1, 2 * U() - 1));
+                Vector3f err = r % 2 ? Vector3f(1e-5f * U(), 1e-5f * U(), 1e-5f * U()) : Vector3f(0, 0, 0);
+                Normal3f n = r % 3 == 0 ? Normal3f(0, 0, 0) : Normal3f(Normalize(Vector3f(2 * U() - 1, 2 * U() - 1, 2 * U() - 1)));
+                Point2f u(U(), U());
+                ShapeSampleContext ctx(Point3fi(p, err), n, n, 0.f);
+                samp.insert(samp.end(), {ctx.pi.x.LowerBound(), ctx.pi.x.UpperBound(), ctx.pi.y.LowerBound(), ctx.pi.y.UpperBound(), ctx.pi.z.LowerBound(), ctx.pi.z.UpperBound(),
+                                         n.x, n.y, n.z, u[0], u[1]});
+                pstd::optional<ShapeSample> ss = shape.Sample(ctx, u);
+                float out[20] = {0};
+                out[0] = ss ? 1.f : 0.f;
+                Vector3f wi = Normalize(Vector3f(2 * U() - 1, 2 * U() - 1, 2 * U() - 1));
+                if (ss) {
+                    const Interaction &in = ss->intr;
+                    float v[] = {in.pi.x.LowerBound(), in.pi.x.UpperBound(), in.pi.y.LowerBound(), in.pi.y.UpperBound(), in.pi.z.LowerBound(), in.pi.z.UpperBound(),
+                                 in.n.x, in.n.y, in.n.z, in.uv[0], in.uv[1], ss->pdf};
+                    for (size_t q = 0; q < sizeof(v) / sizeof(v[0]); ++q) out[1 + q] = v[q];
+                    if (r % 2 == 0 && LengthSquared(in.p() - ctx.p()) > 0) wi = Normalize(in.p() - ctx.p());
+                }
+                out[13] = wi.x; out[14] = wi.y; out[15] = wi.z;
+                out[16] = shape.PDF(ctx, wi);
+                sampOut.insert(sampOut.end(), out, out + 20);
+            }
+        }
+        b.f32("quad_shapes", shapes);
+        b.f32("quad_rays", rays);
+        b.f32("quad_hits", hits);
+        b.f32("quad_samp_in", samp);
+        b.f32("quad_samp_out", sampOut);
+    }
 }
 
 int main(int argc, char **argv) {

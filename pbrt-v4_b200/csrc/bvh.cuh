@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include "pmath.h"
 #include "shapes.h"
+#include "quadrics.h"
 #ifndef BPT_FOLD_I2F
 #define BPT_FOLD_I2F 0   // measured neutral (XU relief, but +2 % node visits): profiles/r01d_fold_prefetch_sweep.log
 #endif
@@ -28,6 +29,8 @@ struct BVHView {
     const float4 *tris;       // 3 float4 per triangle in leaf order (p0.w = original triangle id; top level: instance id)
     const DeviceInstance *instances;   // non-null: two-level scene
     const float *meshAlpha;            // per mesh id: constant alpha of alpha-tested meshes (class bit 30 of the leaf record)
+    const DeviceShape *shapes;         // quadrics (class bit 29 of the leaf record: the record holds the shape's bounds, not vertices)
+    const int *meshShape;              // per mesh id: index into shapes, -1 for triangle meshes
 };
 
 #define BPT_STACK_SIZE 40
@@ -144,6 +147,29 @@ static __device__ __noinline__ bool AlphaHashRejects(const float *meshAlpha, int
 BPT_D bool AlphaRejects(const BVHView &bvh, const RayPre &r, unsigned cls, float meshIdBits) {
     if (!(cls & kClsAlpha)) return false;
     return AlphaHashRejects(bvh.meshAlpha, __float_as_int(meshIdBits), r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
+}
+// Quadric leaves (Sphere / Disk / Cylinder as custom primitives, gpu/optix/optix.cu:301-377): the leaf record carries the shape's
+// bounding box where a triangle has its vertices, is flagged degenerate (so the triangle test never runs on it) and has class bit 29
+// set.  The test is Shape::IntersectP / BasicIntersect with the current tMax; a hit is reported as (pObj, tHit), from which the
+// shading kernels rebuild the QuadricIntersection.  Outlined: scenes without quadrics only pay the class-bit test on degenerate records.
+constexpr unsigned kClsShape = 0x20000000u;
+static __device__ __noinline__ float4 IntersectQuadricLeaf(const DeviceShape *shapes, const int *meshShape, int mesh, float ox, float oy, float oz,
+                                                           float dx, float dy, float dz, float tMax) {
+    QuadricHit qh;
+    if (!QuadricBasicIntersect(shapes[__ldg(meshShape + mesh)], Pt3(ox, oy, oz), Vec3(dx, dy, dz), tMax, &qh)) return make_float4(0.f, 0.f, 0.f, -1.f);
+    return make_float4(qh.pObj.x, qh.pObj.y, qh.pObj.z, qh.t);
+}
+// One leaf record against the ray: the reference's Primitive::Intersect(ray, tMax) for whatever the record holds
+BPT_D bool LeafIntersect(const BVHView &bvh, const RayPre &rp, float tMax, float4 a, float4 b, float4 c, TriHit *th) {
+    const unsigned cls = __float_as_uint(b.w);
+    if (cls & 0x80000000u) {
+        if (!(cls & kClsShape)) return false;   // degenerate triangle (shapes.cpp:172)
+        float4 q = IntersectQuadricLeaf(bvh.shapes, bvh.meshShape, __float_as_int(c.w), rp.o.x, rp.o.y, rp.o.z, rp.d.x, rp.d.y, rp.d.z, tMax);
+        if (q.w < 0) return false;
+        th->b0 = q.x; th->b1 = q.y; th->b2 = q.z; th->t = q.w;
+        return true;
+    }
+    return IntersectTrianglePre(rp, tMax, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), th) && !AlphaRejects(bvh, rp, cls, c.w);
 }
 BPT_D unsigned ExtractByte(unsigned x, unsigned i) { return (x >> (i * 8)) & 0xff; }
 BPT_D unsigned SignExtendS8x4(unsigned x) {
@@ -272,9 +298,7 @@ BPT_D void TraceRay(const BVHView &bvh, Pt3 o, Vec3 d, float tMax, HitRec *rec, 
             float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
             if (COUNT) ++*nTris;
             TriHit th;
-            if (!(__float_as_uint(b.w) & 0x80000000u) &&
-                IntersectTrianglePre(rp, rec->t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th) &&
-                !AlphaRejects(bvh, rp, __float_as_uint(b.w), c.w)) {
+            if (LeafIntersect(bvh, rp, rec->t, a, b, c, &th)) {
                 rec->tri = (int)tri; rec->b0 = th.b0; rec->b1 = th.b1; rec->b2 = th.b2; rec->t = th.t;
                 if (ANYHIT) return;
                 tBox = th.t * (1 + 2 * gamma_n(3));
@@ -479,9 +503,7 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
                     }
 #else
                     TriHit th;
-                    if (!(__float_as_uint(b.w) & 0x80000000u) &&
-                        IntersectTrianglePre(rp, rec.t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th) &&
-                        !AlphaRejects(bvh, rp, __float_as_uint(b.w), c.w)) {
+                    if (LeafIntersect(bvh, rp, rec.t, a, b, c, &th)) {
                         rec.tri = (int)tri; rec.b0 = th.b0; rec.b1 = th.b1; rec.b2 = th.b2; rec.t = th.t;
                         if (ANYHIT) { finished = true; head = tail; }
                         else tBox = th.t * (1 + 2 * gamma_n(3));
@@ -656,9 +678,7 @@ BPT_D void TraversePersistentInst(const BVHView &bvh, const DeviceInstance *inst
                     float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                     if (COUNT) ++*nTris;
                     TriHit th;
-                    if (!(__float_as_uint(b.w) & 0x80000000u) &&
-                        IntersectTrianglePre(rp, rec.t, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), &th) &&
-                        !AlphaRejects(bvh, rp, __float_as_uint(b.w), c.w)) {
+                    if (LeafIntersect(bvh, rp, rec.t, a, b, c, &th)) {
                         rec.tri = (int)tri; rec.b0 = th.b0; rec.b1 = th.b1; rec.b2 = th.b2; rec.t = th.t; rec.inst = inst;
                         hitHere = true;
                         if (ANYHIT) { finished = true; head = tail; }

@@ -47,6 +47,8 @@ struct OwnedMesh {
     bpt_mesh m;
     std::vector<float> P, N, UV;
     std::vector<int> idx;
+    bool isQuadric = false;      // one Sphere / Disk / Cylinder: m carries the common members (n_triangles = 1: its bounds record)
+    bpt_quadric q{};
 };
 struct OwnedLight {
     bpt_light l;
@@ -177,6 +179,8 @@ struct bpt_engine {
     DevBuf<int> rawIdx;
     DevBuf<DeviceMesh> dMeshes;
     DevBuf<float> dMeshAlpha;        // per mesh: constant alpha of the stochastic alpha test (1 = none)
+    DevBuf<DeviceShape> dShapes;     // quadrics
+    DevBuf<int> dMeshShape;          // per mesh: index into dShapes, -1 for triangle meshes
     DevBuf<int> indexPool;
     DevBuf<float> nPool, uvPool, specPool;
     DevBuf<DeviceMaterial> dMaterials;
@@ -576,6 +580,21 @@ extern "C" int bpt_scene_add_mesh(bpt_engine *e, const bpt_mesh *m) {
     o.m.P = o.m.N = o.m.UV = nullptr; o.m.indices = nullptr;
     return BPT_OK;
 }
+extern "C" int bpt_scene_add_quadric(bpt_engine *e, const bpt_quadric *q) {
+    if (!e || !q) return e ? e->fail(BPT_ERR_INVALID, "bad quadric") : BPT_ERR_INVALID;
+    if (q->type != BPT_SHAPE_SPHERE && q->type != BPT_SHAPE_DISK && q->type != BPT_SHAPE_CYLINDER) return e->fail(BPT_ERR_UNSUPPORTED, "shape type not implemented (trianglemesh, sphere, disk, cylinder)");
+    if (!(q->radius > 0)) return e->fail(BPT_ERR_INVALID, "quadric radius must be positive");
+    e->meshes.emplace_back();
+    OwnedMesh &o = e->meshes.back();
+    o.isQuadric = true; o.q = *q;
+    o.m = bpt_mesh{};
+    o.m.n_vertices = 0; o.m.n_triangles = 1;
+    o.m.world_from_object = q->world_from_object; o.m.object_from_world = q->object_from_world;
+    o.m.reverse_orientation = q->reverse_orientation; o.m.material = q->material; o.m.area_light = q->area_light;
+    o.m.medium_inside = q->medium_inside; o.m.medium_outside = q->medium_outside; o.m.object_id = q->object_id;
+    o.m.has_alpha = 0; o.m.alpha = 1.f;
+    return BPT_OK;
+}
 // In-library fast path of the .pbrt front end (csrc/pbrt_frontend.cpp lives in the same shared object): the arrays it has just read
 // from a PLY file are moved into the engine instead of copied through the public ABI (2 x 19 MB of memcpy per re-commit of the 1 M-
 // triangle bench scene).  Same validation as bpt_scene_add_mesh.
@@ -970,6 +989,9 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
 
     // ---- meshes: transform to render space (TriangleMesh ctor util/mesh.cpp:25-70), build pools and lights
     std::vector<float> meshAlpha(e->meshes.size(), 1.f);
+    std::vector<int> meshShape(e->meshes.size(), -1);
+    std::vector<DeviceShape> dshapes;
+    bool instancedQuadrics = false;   // an object definition holds a quadric: its instances keep the reference's (loose) bounds
     bool anyAlpha = false;
     std::unique_ptr<float4[]> tri;   // host-assembled ranges only (untouched pages of the rest are never committed)
     std::vector<DeviceMesh> dmesh(e->meshes.size());
@@ -1015,7 +1037,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         if (om.m.object_id >= 0 && om.m.area_light >= 0) return e->fail(BPT_ERR_UNSUPPORTED, "area lights are not supported with object instancing");
         if (om.m.material >= (int)e->materials.size()) return e->fail(BPT_ERR_INVALID, "mesh material index out of range");
         Xform renderFromObject = ResolveRenderFromObject(space, spaces, om.m.world_from_object, om.m.object_from_world);   // scene.h:475-477
-        const bool deviceAssemble = om.m.area_light < 0 && om.m.n_triangles >= kDeviceAssembleMin;
+        const bool deviceAssemble = !om.isQuadric && om.m.area_light < 0 && om.m.n_triangles >= kDeviceAssembleMin;
         std::vector<Pt3> P(deviceAssemble ? 0 : om.m.n_vertices);
         if (!deviceAssemble)
             for (int v = 0; v < om.m.n_vertices; ++v) P[v] = renderFromObject(Pt3(om.P[3 * v], om.P[3 * v + 1], om.P[3 * v + 2]));
@@ -1029,6 +1051,23 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         dm.nOffset = (int)(nPool.size() / 3);
         dm.uvOffset = (int)(uvPool.size() / 2);
         dm.mediumInside = om.m.medium_inside; dm.mediumOutside = om.m.medium_outside;
+        dm.shape = -1;
+        DeviceShape dshape{};
+        Bounds3 shapeBounds;
+        if (om.isQuadric) {
+            // Sphere / Disk / Cylinder constructors (shapes.h:118-128, 407-417, 801-812) and ::Bounds (shapes.cpp:33-36, 85-88, 121-124)
+            const bpt_quadric &q = om.q;
+            Pt3 bmin, bmax;
+            dshape = MakeQuadric(q.type == BPT_SHAPE_SPHERE ? SHAPE_SPHERE : (q.type == BPT_SHAPE_DISK ? SHAPE_DISK : SHAPE_CYLINDER), q.radius, q.zmin, q.zmax, q.phimax,
+                                 q.height, q.innerradius, q.reverse_orientation != 0, renderFromObject.SwapsHandedness(), ToMat4(renderFromObject.m),
+                                 ToMat4(renderFromObject.mInv), &bmin, &bmax);
+            for (int c = 0; c < 8; ++c)   // Transform::operator()(const Bounds3f &) (util/transform.cpp:134-139)
+                shapeBounds = Union(shapeBounds, renderFromObject(Pt3((c & 1) ? bmax.x : bmin.x, (c & 2) ? bmax.y : bmin.y, (c & 4) ? bmax.z : bmin.z)));
+            dm.shape = (int)dshapes.size();
+            dm.flags = 0;
+            if (om.m.object_id >= 0) instancedQuadrics = true;
+        }
+        meshShape[mi] = dm.shape;
         if (!om.N.empty() || !om.UV.empty()) indexPool.insert(indexPool.end(), om.idx.begin(), om.idx.end());
         if (!om.N.empty())
             for (int v = 0; v < om.m.n_vertices; ++v) {
@@ -1069,6 +1108,41 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         if (deviceAssemble) {
             devVerts = std::max(devVerts, (size_t)om.m.n_vertices); devIdx = std::max(devIdx, (size_t)om.m.n_triangles);
             triCursor += om.m.n_triangles;
+            continue;
+        }
+        if (om.isQuadric) {
+            // one pool record: the bounds where a triangle has its vertices (p2 = p0: the builder flags it degenerate, so only the
+            // quadric test of the traversal ever looks at it), class bit kClsShape
+            int gtri = (int)triCursor;
+            float4 *tp = &tri[3 * triCursor++];
+            tp[0] = make_float4(shapeBounds.pMin.x, shapeBounds.pMin.y, shapeBounds.pMin.z, b2f((uint32_t)mi));
+            tp[1] = make_float4(shapeBounds.pMax.x, shapeBounds.pMax.y, shapeBounds.pMax.z, b2f(0u));
+            tp[2] = make_float4(shapeBounds.pMin.x, shapeBounds.pMin.y, shapeBounds.pMin.z, b2f(cls | kClsShape));
+            if (emissive) {
+                DeviceLight dl{};
+                dl.type = LIGHT_DIFFUSE_AREA; dl.tri = gtri; dl.twoSided = al->a.two_sided; dl.LemitTable = Lrec.table;
+                float area = QuadricArea(dshape);
+                float scale = lightScale;
+                if (al->a.power > 0) {
+                    float k_e = 1;
+                    k_e *= (al->a.two_sided ? 2 : 1) * area * kPi;
+                    scale *= al->a.power / k_e;
+                }
+                dl.scale = scale;
+                dlights.push_back(dl);
+                // DiffuseAreaLight::Bounds (lights.cpp:788-807) with Shape::NormalBounds: the whole sphere of directions for Sphere /
+                // Cylinder (shapes.h:134, 594), the transformed +z normal for a Disk (shapes.cpp:90-95)
+                float phi = LemitMax;
+                phi *= scale * area * kPi;
+                Vec3 w(0, 0, 1); float cosTheta = -1;
+                if (dshape.type == SHAPE_DISK) {
+                    Nrm3 n = renderFromObject(Nrm3(0, 0, 1));
+                    if (om.q.reverse_orientation) n = -n;
+                    w = Normalize(V(n)); cosTheta = 1;
+                }
+                lbounds.push_back(LightBoundsH(shapeBounds, w, phi, cosTheta, std::cos(kPi / 2), al->a.two_sided != 0));
+            }
+            dshapes.push_back(dshape);
             continue;
         }
         for (int t = 0; t < om.m.n_triangles; ++t) {
@@ -1394,6 +1468,8 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     ECK(cudaStreamSynchronize(e->stream));
     ECK(e->dMeshes.upload(dmesh));
     ECK(e->dMeshAlpha.upload(meshAlpha));
+    ECK(e->dMeshShape.upload(meshShape));
+    if (!dshapes.empty()) ECK(e->dShapes.upload(dshapes));
     (void)anyAlpha;
     ECK(e->indexPool.upload(indexPool));
     ECK(e->nPool.upload(nPool));
@@ -1486,7 +1562,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             looseScene = Union(looseScene, Pt3(tlasPrims[3 * k].x, tlasPrims[3 * k].y, tlasPrims[3 * k].z));
             looseScene = Union(looseScene, Pt3(tlasPrims[3 * k + 1].x, tlasPrims[3 * k + 1].y, tlasPrims[3 * k + 1].z));
         }
-        if (!std::getenv("BPT_LOOSE_INSTANCE_BOUNDS")) {
+        if (!std::getenv("BPT_LOOSE_INSTANCE_BOUNDS") && !instancedQuadrics) {
             std::vector<int> first(dinst.size()), count(dinst.size());
             for (size_t k = 0; k < dinst.size(); ++k) { first[k] = groupStart[instGroup[k]]; count[k] = groupStart[instGroup[k] + 1] - groupStart[instGroup[k]]; }
             ECK(e->dInstFirstTri.upload(first)); ECK(e->dInstTriCount.upload(count));
@@ -1714,6 +1790,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     rc.bvh.nodes = e->bvh.nodes; rc.bvh.tris = e->bvh.tris;
     rc.bvh.instances = instanced ? e->dInstances.p : nullptr;
     rc.bvh.meshAlpha = e->dMeshAlpha.p;
+    rc.bvh.shapes = e->dShapes.p; rc.bvh.meshShape = e->dMeshShape.p;
     ECK(e->hitInst.alloc(instanced ? maxPaths : 1));
     rc.ps.hitInst = e->hitInst.p;
     SceneView &sv = rc.sv;
@@ -1727,6 +1804,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     sv.cieX = e->dTables.p; sv.cieY = e->dTables.p + kNLambda; sv.cieZ = e->dTables.p + 2 * kNLambda; sv.illumD65 = e->dTables.p + 3 * kNLambda;
     sv.textures = e->haveTextures ? e->dTextures.p : nullptr; sv.mipLevels = e->haveTextures ? e->dMipLevels.p : nullptr;
     sv.ewaLUT = e->haveTextures ? e->dEwaLUT.p : nullptr;
+    sv.shapes = e->dShapes.p;
     sv.rgb2specScale = e->dRgb2spec.n ? e->dRgb2spec.p : nullptr; sv.rgb2specCoeffs = e->dRgb2spec.n ? e->dRgb2spec.p + 64 : nullptr;
     sv.nLights = (int)dlights.size();
     // ZSobol digit-prefix table: [dimension][pixel] uint32 (only when the permuted index fits in 32 bits)

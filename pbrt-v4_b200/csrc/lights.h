@@ -8,6 +8,7 @@
 #pragma once
 #include "scene.h"
 #include "shapes.h"
+#include "quadrics.h"
 
 namespace bpt {
 
@@ -39,6 +40,7 @@ struct SceneView {
     const DeviceTexture *textures;    // image textures (null: none)
     const DeviceMIPLevel *mipLevels;
     const float *ewaLUT;              // MIPFilterLUT, 128 entries (util/mipmap.cpp:59)
+    const DeviceShape *shapes;        // quadrics (null: none)
 };
 
 #if defined(__CUDACC__)
@@ -141,6 +143,20 @@ BPT_HD TriData LoadTriangle(const SceneView &sv, int tri) {
     return td;
 }
 
+// SurfaceInteraction of a recorded hit: triangles record barycentrics, quadrics the object-space hit point (quadrics.h)
+BPT_HD SurfaceIntr HitInteraction(const SceneView &sv, const TriData &td, float b0, float b1, float b2, SurfaceExtras *ex = nullptr) {
+    const int shape = sv.meshes[td.mesh].shape;
+    if (shape >= 0) return QuadricInteraction(sv.shapes[shape], Pt3(b0, b1, b2), ex);
+    TriHit th{b0, b1, b2, 0.f};
+    return TriangleInteraction(td.p0, td.p1, td.p2, td.a, th, ex);
+}
+// wo of that interaction in the space of the enclosing BVH, for a ray of direction d in that space
+BPT_HD Vec3 HitWo(const SceneView &sv, const TriData &td, Vec3 d) {
+    const int shape = sv.meshes[td.mesh].shape;
+    if (shape >= 0) return QuadricWo(sv.shapes[shape], d);
+    return Normalize(-d);
+}
+
 // ---------------------------------------------------------------- DiffuseAreaLight
 BPT_HD Spec AreaLightL(const SceneView &sv, const DeviceLight &light, Nrm3 n, Vec3 w, const Wavelengths &wl) {
     if (!light.twoSided && Dot(n, w) < 0) return Spec(0.f);
@@ -154,7 +170,9 @@ BPT_HD LightLiSample AreaLightSampleLi(const SceneView &sv, const DeviceLight &l
     LightLiSample ls;
     ls.valid = false;
     TriData td = LoadTriangle(sv, light.tri);
-    ShapeSample ss = TriangleSampleSolidAngle(td.p0, td.p1, td.p2, td.a, ctx.p(), ctx.ns, u);
+    const int shape = sv.meshes[td.mesh].shape;
+    ShapeSample ss = shape >= 0 ? QuadricSampleSolidAngle(sv.shapes[shape], ctx.pi, ctx.n, u)
+                                : TriangleSampleSolidAngle(td.p0, td.p1, td.p2, td.a, ctx.p(), ctx.ns, u);
     if (!ss.valid || ss.pdf == 0 || LengthSquared(ss.pi.p() - ctx.p()) == 0) return ls;
     Vec3 wi = Normalize(ss.pi.p() - ctx.p());
     Spec Le = AreaLightL(sv, light, ss.n, -wi, wl);
@@ -164,6 +182,8 @@ BPT_HD LightLiSample AreaLightSampleLi(const SceneView &sv, const DeviceLight &l
 }
 BPT_HD float AreaLightPDF_Li(const SceneView &sv, const DeviceLight &light, const LightSampleContext &ctx, Vec3 wi) {
     TriData td = LoadTriangle(sv, light.tri);
+    const int shape = sv.meshes[td.mesh].shape;
+    if (shape >= 0) return QuadricPDFSolidAngle(sv.shapes[shape], ctx.pi, ctx.n, wi);
     return TrianglePDFSolidAngle(td.p0, td.p1, td.p2, td.a, ctx.pi, ctx.n, ctx.ns, wi);
 }
 

@@ -98,6 +98,8 @@ struct GState {
 struct MeshRec {
     std::vector<float> P, N, UV; std::vector<int> idx;
     bpt_mesh m;
+    bool isQuadric = false;   // Shape "sphere" / "disk" / "cylinder": q carries the parameters, m the members common to all shapes
+    bpt_quadric q;
 };
 
 struct Frontend {
@@ -628,7 +630,18 @@ struct Frontend {
             if (fn.empty()) { err = "plymesh: missing filename"; return false; }
             if (fn[0] != '/') fn = baseDir + "/" + fn;
             if (!readPLY(fn, mr.get())) return false;
-        } else { err = "shape \"" + type + "\" is not supported (triangle meshes only)"; return false; }
+        } else if (type == "sphere" || type == "disk" || type == "cylinder") {
+            // Sphere / Disk / Cylinder::Create (shapes.cpp:72-83, 107-117, 135-146): the defaults are theirs
+            mr->isQuadric = true;
+            std::memset(&mr->q, 0, sizeof(mr->q));
+            bpt_quadric &q = mr->q;
+            q.radius = pl.f("radius", 1.f);
+            q.phimax = pl.f("phimax", 360.f);
+            if (type == "sphere") { q.type = BPT_SHAPE_SPHERE; q.zmin = pl.f("zmin", -q.radius); q.zmax = pl.f("zmax", q.radius); }
+            else if (type == "cylinder") { q.type = BPT_SHAPE_CYLINDER; q.zmin = pl.f("zmin", -1.f); q.zmax = pl.f("zmax", 1.f); }
+            else { q.type = BPT_SHAPE_DISK; q.height = pl.f("height", 0.f); q.innerradius = pl.f("innerradius", 0.f); }
+            if (pl.find("alpha")) { err = "alpha on a " + type + " is not supported (triangle meshes only)"; return false; }
+        } else { err = "shape \"" + type + "\" is not supported (trianglemesh, plymesh, sphere, disk, cylinder)"; return false; }
         std::memset(&mr->m, 0, sizeof(mr->m));
         if (Param *al = pl.find("alpha")) {   // getAlphaTexture (scene.cpp): "float alpha" < 1 -> FloatConstantTexture; texture-valued alpha: not implemented
             if (al->type != "float" || al->nums.size() != 1) { err = "texture-valued alpha is not supported (constant \"float alpha\" only)"; return false; }
@@ -994,6 +1007,14 @@ bool Frontend::finish() {
     }
     for (auto &m : meshes) {
         bpt_mesh bm = m->m;
+        if (m->isQuadric) {
+            bpt_quadric q = m->q;
+            q.world_from_object = bm.world_from_object; q.object_from_world = bm.object_from_world; q.reverse_orientation = bm.reverse_orientation;
+            q.material = bm.material; q.area_light = bm.area_light; q.medium_inside = bm.medium_inside; q.medium_outside = bm.medium_outside;
+            q.object_id = bm.object_id;
+            if (!ck(bpt_scene_add_quadric(e, &q))) return false;
+            continue;
+        }
 #ifdef BPT_FRONTEND_IN_LIBRARY
         if (!ck(bpt_internal_add_mesh_move(e, &bm, std::move(m->P), std::move(m->N), std::move(m->UV), std::move(m->idx)))) return false;
 #else

@@ -108,6 +108,7 @@ struct DeviceMesh {
     int nOffset;               // offset (in float3) into the normal pool
     int uvOffset;              // offset (in float2) into the uv pool
     int mediumInside, mediumOutside;   // -1 = none
+    int shape;                 // >= 0: this "mesh" is one quadric (index into SceneView::shapes, quadrics.h); its single pool record holds the bounds
 };
 
 struct DeviceLight {

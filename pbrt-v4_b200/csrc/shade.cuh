@@ -110,18 +110,19 @@ __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int
         float4 h = ps.hit[slot];
         int tri = __float_as_int(h.x);
         TriData td = LoadTriangle(rc.sv, tri);
-        TriHit th{h.y, h.z, h.w, 0.f};
         SurfaceExtras ex;
-        SurfaceIntr isect = TriangleInteraction(td.p0, td.p1, td.p2, td.a, th, TEX ? &ex : nullptr);
+        SurfaceIntr isect = HitInteraction(rc.sv, td, h.y, h.z, h.w, TEX ? &ex : nullptr);
         const DeviceMesh &mesh = rc.sv.meshes[td.mesh];
         float4 d4 = ps.rayD[slot];
         // isect.wo: the Interaction constructor normalises it (interaction.h:32-33, wo(Normalize(wo))) -- not a no-op in float: a third
-        // of all unit vectors change in the last bit when normalised again, which the microfacet BxDFs see (r02c bisection)
-        Vec3 wo = Normalize(-Vec3(d4.x, d4.y, d4.z));
+        // of all unit vectors change in the last bit when normalised again, which the microfacet BxDFs see (r02c bisection).
+        // A quadric takes -ray.d to object space first and normalises there and on the way back (HitWo).
+        Vec3 wo = HitWo(rc.sv, td, Vec3(d4.x, d4.y, d4.z));
         if (rc.sv.instances) {
             const DeviceInstance &I = rc.sv.instances[ps.hitInst[slot]];
             if (!I.identity) {
-                isect = XformInteraction(I, isect); wo = InstancedWo(I, Vec3(d4.x, d4.y, d4.z));
+                // ret.wo = Normalize(t(si.wo)), si.wo the interaction's wo in instance space (cpu/primitive.cpp:114-123)
+                isect = XformInteraction(I, isect); wo = Normalize(XformVec(I.m, HitWo(rc.sv, td, XformVec(I.mInv, Vec3(d4.x, d4.y, d4.z)))));
                 if (TEX) ex = XformExtras(I, ex);
             }
         }

@@ -237,8 +237,7 @@ __global__ void __launch_bounds__(128) k_handle_emissive(RenderCtx rc) {
         float4 h = ps.hit[slot];
         int tri = __float_as_int(h.x);
         TriData td = LoadTriangle(rc.sv, tri);
-        TriHit th{h.y, h.z, h.w, 0.f};
-        SurfaceIntr isect = TriangleInteraction(td.p0, td.p1, td.p2, td.a, th);
+        SurfaceIntr isect = HitInteraction(rc.sv, td, h.y, h.z, h.w);
         const DeviceMesh &mesh = rc.sv.meshes[td.mesh];
         int lightIndex = mesh.areaLightBase + td.triIndex;
         const DeviceLight &light = rc.sv.lights[lightIndex];
@@ -545,8 +544,7 @@ __global__ void __launch_bounds__(128, BPT_MEDIUM_CTAS) k_trace_shadow_tr(Render
             if (rec.tri < 0) break;
             // lightRay = si->intr.SpawnRayTo(ls->pLight)
             TriData td = LoadTriangle(rc.sv, tri);
-            TriHit th{rec.b0, rec.b1, rec.b2, rec.t};
-            SurfaceIntr isect = TriangleInteraction(td.p0, td.p1, td.p2, td.a, th);
+            SurfaceIntr isect = HitInteraction(rc.sv, td, rec.b0, rec.b1, rec.b2);
             Pt3 pf = OffsetRayOrigin(isect.pi, isect.n, pLight.p() - isect.pi.p());
             Pt3 pt = OffsetRayOrigin(pLight, nLight, pf - pLight.p());
             o = pf; d = pt - pf;

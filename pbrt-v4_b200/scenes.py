@@ -98,6 +98,68 @@ def cornell_lights(outdir, lights="all", area=True, res=(64, 64), spp=16, maxdep
     return path
 
 
+QUADRIC_SETS = {
+    # Sphere / Disk / Cylinder (shapes.h:107-790) in the Cornell box.  Each entry: (text inserted after WorldBegin, text appended, keep the quad light)
+    "spheres": ("", (
+        'AttributeBegin\n  Translate -0.45 0.35 -0.2\n  Material "diffuse" "rgb reflectance" [0.2 0.4 0.8]\n  Shape "sphere" "float radius" 0.35\nAttributeEnd\n'
+        'AttributeBegin\n  Translate 0.45 0.4 0.3\n  Material "dielectric" "float eta" 1.5\n  Shape "sphere" "float radius" 0.3\nAttributeEnd\n'
+        'AttributeBegin\n  Translate 0.1 1.2 -0.4\n  Rotate 40 1 0.3 0.2\n  Scale 1 0.7 1.2\n  Material "conductor" "float roughness" 0.15\n'
+        '  Shape "sphere" "float radius" 0.3 "float zmin" -0.2 "float zmax" 0.25 "float phimax" 300\nAttributeEnd\n'), True),
+    "disk_cylinder": ("", (
+        'AttributeBegin\n  Translate -0.4 0 0.1\n  Rotate -90 1 0 0\n  Material "coateddiffuse" "rgb reflectance" [0.7 0.3 0.2] "float roughness" 0.05\n'
+        '  Shape "cylinder" "float radius" 0.25 "float zmin" 0 "float zmax" 0.8\n  Shape "disk" "float radius" 0.25 "float height" 0.8\nAttributeEnd\n'
+        'AttributeBegin\n  Translate 0.45 0.5 -0.1\n  Rotate 30 0 1 0\n  Rotate 70 1 0 0\n  Scale 1 1.3 -1\n  Material "conductor" "float roughness" 0.05\n'
+        '  Shape "cylinder" "float radius" 0.2 "float zmin" -0.3 "float zmax" 0.4 "float phimax" 250\n'
+        '  ReverseOrientation\n  Shape "disk" "float radius" 0.3 "float innerradius" 0.12 "float height" -0.3 "float phimax" 250\nAttributeEnd\n'), True),
+    "lights": ("", (
+        'AttributeBegin\n  Translate -0.5 1.5 0\n  AreaLightSource "diffuse" "rgb L" [9 7 4]\n  Shape "sphere" "float radius" 0.12\nAttributeEnd\n'
+        'AttributeBegin\n  Translate 0.4 1.9 0.2\n  Rotate 100 1 0 0.2\n  AreaLightSource "diffuse" "rgb L" [6 8 10] "bool twosided" true\n  Shape "disk" "float radius" 0.25 "float innerradius" 0.05\nAttributeEnd\n'
+        'AttributeBegin\n  Translate 0.5 0.3 0.3\n  Rotate 90 0 1 0\n  AreaLightSource "diffuse" "blackbody L" 3000 "float power" 30\n  Shape "cylinder" "float radius" 0.05 "float zmin" -0.4 "float zmax" 0.4\nAttributeEnd\n'
+        'AttributeBegin\n  Translate -0.2 0.4 -0.3\n  Material "diffuse" "rgb reflectance" [0.6 0.6 0.6]\n  Shape "sphere" "float radius" 0.4\nAttributeEnd\n'
+        # a large emissive sphere that contains part of the scene: reference points inside it take the area-sampling branch
+        'AttributeBegin\n  Translate 0.6 0.2 -0.7\n  AreaLightSource "diffuse" "rgb L" [0.3 0.3 0.5] "bool twosided" true\n  ReverseOrientation\n  Shape "sphere" "float radius" 0.5 "float zmax" 0.3\nAttributeEnd\n'), False),
+    "instanced": ("", (
+        'AttributeBegin\n  Material "coatedconductor"\n  ObjectBegin "thing"\n    Shape "sphere" "float radius" 0.12\n'
+        '    AttributeBegin\n      Translate 0 0 0.12\n      Shape "cylinder" "float radius" 0.05 "float zmin" 0 "float zmax" 0.25\n      Shape "disk" "float radius" 0.05 "float height" 0.25\n    AttributeEnd\n'
+        '    Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point3 P" [-0.2 -0.2 -0.12  0.2 -0.2 -0.12  0.2 0.2 -0.12  -0.2 0.2 -0.12]\n'
+        '  ObjectEnd\nAttributeEnd\n'
+        'AttributeBegin\n  Translate -0.45 0.5 0\n  Rotate 25 1 0 0.3\n  ObjectInstance "thing"\nAttributeEnd\n'
+        'AttributeBegin\n  Translate 0.4 0.9 -0.2\n  Rotate -70 0.2 1 0\n  Scale 1.5 1.2 2\n  ObjectInstance "thing"\nAttributeEnd\n'
+        'AttributeBegin\n  Translate 0.1 0.3 0.4\n  Scale -1 1 1\n  Rotate 200 0 0 1\n  ObjectInstance "thing"\nAttributeEnd\n'
+        'AttributeBegin\n  Translate 0.5 0.25 0.5\n  Material "diffuse" "rgb reflectance" [0.3 0.6 0.3]\n  Shape "sphere" "float radius" 0.2\nAttributeEnd\n'), True),
+    "media": ('MakeNamedMedium "fog" "string type" "homogeneous" "rgb sigma_a" [1 1.5 2] "rgb sigma_s" [6 6 5] "float g" 0.4 "float scale" 1.5\n', (
+        'AttributeBegin\n  MediumInterface "fog" ""\n  Material "interface"\n  Translate -0.3 0.6 0\n  Shape "sphere" "float radius" 0.45\nAttributeEnd\n'
+        'AttributeBegin\n  MediumInterface "fog" ""\n  Material "dielectric" "float eta" 1.33\n  Translate 0.5 0.35 0.2\n  Rotate -90 1 0 0\n'
+        '  Shape "cylinder" "float radius" 0.25 "float zmin" -0.3 "float zmax" 0.3\n  Shape "disk" "float radius" 0.25 "float height" 0.3\n'
+        '  ReverseOrientation\n  Shape "disk" "float radius" 0.25 "float height" -0.3\nAttributeEnd\n'), True),
+    "textured": ('Texture "alb" "spectrum" "imagemap" "string filename" "albedo.png" "float uscale" 4 "float vscale" 2\n'
+                 'Texture "hm" "float" "imagemap" "string filename" "height.pfm" "float scale" 0.03 "float uscale" 3 "float vscale" 3\n', (
+        'AttributeBegin\n  Translate -0.4 0.45 -0.1\n  Rotate 30 0.3 1 0\n  Material "diffuse" "texture reflectance" "alb" "texture displacement" "hm"\n  Shape "sphere" "float radius" 0.42\nAttributeEnd\n'
+        'AttributeBegin\n  Translate 0.5 0 0.2\n  Rotate -90 1 0 0\n  Material "coateddiffuse" "texture reflectance" "alb" "float roughness" 0.1\n'
+        '  Shape "cylinder" "float radius" 0.22 "float zmin" 0 "float zmax" 0.9\n  Shape "disk" "float radius" 0.22 "float height" 0.9\nAttributeEnd\n'
+        'Material "conductor" "float roughness" 0\n'
+        'Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point3 P" [0.95 0.2 -0.6  0.95 0.2 0.5  0.6 1.4 0.5  0.6 1.4 -0.6]\n'), True),
+}
+
+
+def cornell_quadrics(outdir, which="spheres", res=(64, 64), spp=16, maxdepth=5):
+    """Cornell box with QUADRIC_SETS[which]: spheres / disks / cylinders as surfaces (diffuse, glass, conductors, clipped by zmin /
+    zmax / phimax, under rotations, non-uniform and mirroring scales), as area lights, inside object instances, as the boundary of
+    a participating medium, and carrying image textures and bump maps (their dndu / dndv are not zero)."""
+    path = cornell(outdir, res=res, spp=spp, maxdepth=maxdepth)
+    head, tail, keep_quad = QUADRIC_SETS[which]
+    s = open(path).read()
+    if which == "textured":
+        texture_images(outdir)
+    if not keep_quad:
+        a = s.index("AttributeBegin\n  AreaLightSource"); b = s.index("AttributeEnd\n", a) + len("AttributeEnd\n")
+        s = s[:a] + s[b:]
+    a = s.index("WorldBegin\n") + len("WorldBegin\n")
+    s = s[:a] + head + s[a:] + tail
+    open(path, "w").write(s)
+    return path
+
+
 def write_png(path, img):
     """8-bit PNG (grey HxW, grey+alpha HxWx2, RGB HxWx3 or RGBA HxWx4), filter type 0 rows, zlib level 6."""
     import struct, zlib

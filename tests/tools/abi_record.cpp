@@ -25,7 +25,7 @@ using namespace bpt;
 
 namespace {
 struct Spec { bpt_spectrum s; std::vector<float> samples; };
-struct Mesh { bpt_mesh m; std::vector<float> P, N, UV; std::vector<int> idx; };
+struct Mesh { bpt_mesh m; std::vector<float> P, N, UV; std::vector<int> idx; bool isQuadric = false; bpt_quadric q; };
 struct Light { bpt_light l; std::vector<float> img; Spec L; };
 struct Medium { bpt_medium m; std::vector<float> density, leScale; Spec sa, ss, Le; uint64_t rgbHash[3]; };
 struct Material { bpt_material m; Spec sp[8]; };
@@ -176,6 +176,13 @@ int bpt_scene_add_mesh(bpt_engine *e, const bpt_mesh *m) {
     o.idx.assign(m->indices, m->indices + 3 * (size_t)m->n_triangles);
     return BPT_OK;
 }
+int bpt_scene_add_quadric(bpt_engine *e, const bpt_quadric *q) {
+    e->meshes.emplace_back(); Mesh &o = e->meshes.back(); std::memset(&o.m, 0, sizeof(o.m)); o.isQuadric = true; o.q = *q;
+    o.m.world_from_object = q->world_from_object; o.m.object_from_world = q->object_from_world; o.m.reverse_orientation = q->reverse_orientation;
+    o.m.material = q->material; o.m.area_light = q->area_light; o.m.medium_inside = q->medium_inside; o.m.medium_outside = q->medium_outside;
+    o.m.object_id = q->object_id;
+    return BPT_OK;
+}
 int bpt_scene_add_instance(bpt_engine *e, const bpt_instance *i) { e->instances.push_back(*i); return BPT_OK; }
 int bpt_scene_add_light(bpt_engine *e, const bpt_light *l) {
     e->lights.emplace_back(); Light &o = e->lights.back(); o.l = *l; o.L = Own(l->L);
@@ -246,9 +253,14 @@ int bpt_scene_commit(bpt_engine *e) {
         Xform rfo = ResolveRenderFromObject(e->space, cs, m.world_from_object, m.object_from_world);
         std::string s = "mesh nv=" + std::to_string(m.n_vertices) + " nt=" + std::to_string(m.n_triangles);
         char b[200];
+        if (ms.isQuadric)
+            s = "quadric type=" + std::to_string(ms.q.type) + " radius=" + F(ms.q.radius) + " zmin=" + F(ms.q.zmin) + " zmax=" + F(ms.q.zmax) + " phimax=" + F(ms.q.phimax) +
+                " height=" + F(ms.q.height) + " innerradius=" + F(ms.q.innerradius);
+        else {
         snprintf(b, sizeof(b), " P=%016" PRIx64 " N=%016" PRIx64 " UV=%016" PRIx64 " idx=%016" PRIx64, Fnv(ms.P.data(), ms.P.size() * 4),
                  ms.N.empty() ? 0 : Fnv(ms.N.data(), ms.N.size() * 4), ms.UV.empty() ? 0 : Fnv(ms.UV.data(), ms.UV.size() * 4), Fnv(ms.idx.data(), ms.idx.size() * 4));
         s += b;
+        }
         s += " renderFromObject{" + X(rfo) + "} reverse=" + std::to_string(m.reverse_orientation != 0) + " alpha=" + (m.has_alpha ? F(m.alpha) : std::string("none"));
         Material iface; std::memset(&iface.m, 0, sizeof(iface.m)); iface.m.type = BPT_MAT_INTERFACE;
         const Material &mt = m.material < 0 ? iface : e->materials[m.material];
