@@ -269,6 +269,11 @@ int bpt_scene_set_materials(bpt_engine *e, const bpt_material *m, int n);
 int bpt_scene_set_textures(bpt_engine *e, const bpt_texture *t, int n);
 int bpt_scene_set_area_lights(bpt_engine *e, const bpt_area_light *a, int n);
 int bpt_scene_add_mesh(bpt_engine *e, const bpt_mesh *m);
+/* Shape "bilinearmesh" (BilinearPatch::CreateMesh, shapes.cpp:910-999) and the quad faces of a PLY file (shapes.cpp:1435-1461): a bpt_mesh
+ * whose `indices` hold FOUR vertex indices per patch (p00, p10, p01, p11) and whose n_triangles is the number of patches.  Intersected
+ * as custom primitives like the quadrics (gpu/optix/optix.cu:379-469); area lights sample them as the reference does (spherical
+ * rectangles for rectangular patches).  "emissionfilename" and alpha are not implemented. */
+int bpt_scene_add_bilinear_mesh(bpt_engine *e, const bpt_mesh *m);
 int bpt_scene_add_quadric(bpt_engine *e, const bpt_quadric *q);   /* takes its place among the meshes in scene order (area-light order, scene.cpp CreateLights) */
 int bpt_scene_add_instance(bpt_engine *e, const bpt_instance *i);
 int bpt_scene_add_light(bpt_engine *e, const bpt_light *l);

@@ -59,7 +59,7 @@ struct Api {
 #define BPT_FN(name) decltype(&::name) name = nullptr;
     BPT_FN(bpt_create) BPT_FN(bpt_destroy) BPT_FN(bpt_last_error) BPT_FN(bpt_scene_begin) BPT_FN(bpt_scene_set_transform_space)
     BPT_FN(bpt_scene_set_camera) BPT_FN(bpt_scene_set_film) BPT_FN(bpt_scene_set_filter) BPT_FN(bpt_scene_set_sampler)
-    BPT_FN(bpt_scene_set_integrator) BPT_FN(bpt_scene_set_materials) BPT_FN(bpt_scene_set_textures) BPT_FN(bpt_scene_set_area_lights) BPT_FN(bpt_scene_add_mesh) BPT_FN(bpt_scene_add_quadric)
+    BPT_FN(bpt_scene_set_integrator) BPT_FN(bpt_scene_set_materials) BPT_FN(bpt_scene_set_textures) BPT_FN(bpt_scene_set_area_lights) BPT_FN(bpt_scene_add_mesh) BPT_FN(bpt_scene_add_quadric) BPT_FN(bpt_scene_add_bilinear_mesh)
     BPT_FN(bpt_scene_add_instance) BPT_FN(bpt_scene_add_light) BPT_FN(bpt_scene_add_medium) BPT_FN(bpt_scene_set_camera_medium)
     BPT_FN(bpt_scene_commit) BPT_FN(bpt_render) BPT_FN(bpt_film_resolve) BPT_FN(bpt_film_resolve_gbuffer)
 #undef BPT_FN
@@ -69,7 +69,7 @@ struct Api {
 #define BPT_FN(name) name = (decltype(name))dlsym(h, #name); if (!name) ErrorExit("%s: symbol %s missing", path, #name);
         BPT_FN(bpt_create) BPT_FN(bpt_destroy) BPT_FN(bpt_last_error) BPT_FN(bpt_scene_begin) BPT_FN(bpt_scene_set_transform_space)
         BPT_FN(bpt_scene_set_camera) BPT_FN(bpt_scene_set_film) BPT_FN(bpt_scene_set_filter) BPT_FN(bpt_scene_set_sampler)
-        BPT_FN(bpt_scene_set_integrator) BPT_FN(bpt_scene_set_materials) BPT_FN(bpt_scene_set_textures) BPT_FN(bpt_scene_set_area_lights) BPT_FN(bpt_scene_add_mesh) BPT_FN(bpt_scene_add_quadric)
+        BPT_FN(bpt_scene_set_integrator) BPT_FN(bpt_scene_set_materials) BPT_FN(bpt_scene_set_textures) BPT_FN(bpt_scene_set_area_lights) BPT_FN(bpt_scene_add_mesh) BPT_FN(bpt_scene_add_quadric) BPT_FN(bpt_scene_add_bilinear_mesh)
         BPT_FN(bpt_scene_add_instance) BPT_FN(bpt_scene_add_light) BPT_FN(bpt_scene_add_medium) BPT_FN(bpt_scene_set_camera_medium)
         BPT_FN(bpt_scene_commit) BPT_FN(bpt_render) BPT_FN(bpt_film_resolve) BPT_FN(bpt_film_resolve_gbuffer)
 #undef BPT_FN
@@ -568,7 +568,16 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
             Check(api, e, api.bpt_scene_add_quadric(e, &q), "bpt_scene_add_quadric");
             return;
         }
-        if (sh.name == "trianglemesh") {
+        std::vector<int> quadIdx;   // bilinear patches: "bilinearmesh", or the quad faces of a PLY file (a second mesh over the same vertices)
+        if (sh.name == "bilinearmesh") {   // BilinearPatch::CreateMesh (shapes.cpp:910-999)
+            for (Point3f p : d.GetPoint3fArray("P")) { P.push_back(p.x); P.push_back(p.y); P.push_back(p.z); }
+            quadIdx = d.GetIntArray("indices");
+            if (quadIdx.empty() && P.size() == 12) quadIdx = {0, 1, 2, 3};
+            while (quadIdx.size() % 4) quadIdx.pop_back();
+            for (Normal3f n : d.GetNormal3fArray("N")) { N.push_back(n.x); N.push_back(n.y); N.push_back(n.z); }
+            for (Point2f u : d.GetPoint2fArray("uv")) { UV.push_back(u.x); UV.push_back(u.y); }
+            if (!d.GetOneString("emissionfilename", "").empty()) ErrorExit(&sh.loc, "\"emissionfilename\" is not implemented by the engine");
+        } else if (sh.name == "trianglemesh") {
             for (Point3f p : d.GetPoint3fArray("P")) { P.push_back(p.x); P.push_back(p.y); P.push_back(p.z); }
             idx = d.GetIntArray("indices");
             if (idx.empty() && P.size() == 9) idx = {0, 1, 2};
@@ -577,16 +586,17 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
         } else if (sh.name == "plymesh") {
             std::string fn = ResolveFilename(d.GetOneString("filename", ""));
             TriQuadMesh mesh = TriQuadMesh::ReadPLY(fn);
-            if (!mesh.quadIndices.empty()) ErrorExit(&sh.loc, "%s: quad faces (bilinear patches) are not implemented by the engine", fn);
+            quadIdx.assign(mesh.quadIndices.begin(), mesh.quadIndices.end());
             for (Point3f p : mesh.p) { P.push_back(p.x); P.push_back(p.y); P.push_back(p.z); }
             for (Normal3f n : mesh.n) { N.push_back(n.x); N.push_back(n.y); N.push_back(n.z); }
             for (Point2f u : mesh.uv) { UV.push_back(u.x); UV.push_back(u.y); }
             idx.assign(mesh.triIndices.begin(), mesh.triIndices.end());
-        } else ErrorExit(&sh.loc, "shape \"%s\" is not implemented by the engine (triangle meshes, sphere, disk, cylinder)", sh.name.ToString());
+        } else ErrorExit(&sh.loc, "shape \"%s\" is not implemented by the engine (triangle meshes, bilinear patches, sphere, disk, cylinder)", sh.name.ToString());
         if (!d.GetTexture("alpha").empty()) ErrorExit(&sh.loc, "texture-valued alpha is not implemented by the engine");
         bpt_mesh m; std::memset(&m, 0, sizeof(m));
         if (Float alpha = d.GetOneFloat("alpha", 1.f); alpha < 1.f) { m.has_alpha = 1; m.alpha = alpha; }   // getAlphaTexture (scene.cpp)
         m.n_vertices = (int)P.size() / 3; m.n_triangles = (int)idx.size() / 3;
+        const bool haveTris = !idx.empty();
         m.P = st.F(std::move(P)); m.N = N.empty() ? nullptr : st.F(std::move(N)); m.UV = UV.empty() ? nullptr : st.F(std::move(UV)); m.indices = st.I(std::move(idx));
         m.world_from_object = ToB(sh.renderFromObject->GetMatrix()); m.object_from_world = ToB(sh.renderFromObject->GetInverseMatrix());
         m.reverse_orientation = sh.reverseOrientation;
@@ -595,7 +605,12 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
         m.area_light = sh.lightIndex;
         m.medium_inside = mediumOf(sh.insideMedium); m.medium_outside = mediumOf(sh.outsideMedium);
         m.object_id = objectId;
-        Check(api, e, api.bpt_scene_add_mesh(e, &m), "bpt_scene_add_mesh");
+        if (haveTris || quadIdx.empty()) Check(api, e, api.bpt_scene_add_mesh(e, &m), "bpt_scene_add_mesh");
+        if (!quadIdx.empty()) {   // Shape::Create: the triangles of a PLY file first, then its quads (shapes.cpp:1435-1461)
+            if (m.has_alpha) ErrorExit(&sh.loc, "alpha on bilinear patches is not implemented by the engine");
+            m.n_triangles = (int)quadIdx.size() / 4; m.indices = st.I(std::move(quadIdx));
+            Check(api, e, api.bpt_scene_add_bilinear_mesh(e, &m), "bpt_scene_add_bilinear_mesh");
+        }
     };
     if (!scene.animatedShapes.empty()) ErrorExit("animated shapes are not implemented by the engine");
     for (const ShapeSceneEntity &sh : scene.shapes) addShape(sh, -1);

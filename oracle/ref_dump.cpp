@@ -963,6 +963,97 @@ static void DumpGolden(const char *path) {
         b.f32("quad_samp_in", samp);
         b.f32("quad_samp_out", sampOut);
     }
+    // bilinear patches: meshes of one patch each (flat rectangle, flat non-rectangle, twisted, degenerate-to-triangle; with and without
+    // uv / N; mirrored transform) -- render-space vertices, area, IsRectangle, bounds, NormalBounds, Intersect + interaction,
+    // Sample(ctx, u), PDF(ctx, wi) -- for csrc/bilinear.h (tests/tools/bilinear_host_check.cpp)
+    {
+        RNG qr(4242);
+        auto U = [&]() { return qr.Uniform<float>(); };
+        Allocator alloc;
+        std::vector<float> patches, rays, hits, samp, sampOut;
+        const int nPatches = 16, nRays = 300, nSamp = 96;
+        for (int k = 0; k < nPatches; ++k) {
+            int kind = k % 4;   // 0 rectangle, 1 planar quad, 2 twisted, 3 triangle (two coincident vertices)
+            bool withUV = (k / 4) % 2 == 1, withN = k >= 8, reverse = k % 5 == 2;
+            Transform rfo = Translate(Vector3f(2 * U() - 1, 2 * U() - 1, 2 * U() - 1)) * Rotate(360 * U(), Normalize(Vector3f(U() - .5f, U() - .5f, U() - .3f)));
+            if (k >= 12) rfo = rfo * Scale(-1.f - U(), .5f + U(), .5f + U());
+            rfo = Transform(rfo.GetMatrix());
+            float w = .5f + 1.5f * U(), h = .5f + 1.5f * U();
+            std::vector<Point3f> P = {Point3f(0, 0, 0), Point3f(w, 0, 0), Point3f(0, h, 0), Point3f(w, h, 0)};
+            if (kind == 1) { P[3] = Point3f(w * (1.2f + U()), h * (.6f + U()), 0); P[1].y = .2f * U(); }
+            if (kind == 2) { P[3].z = .3f + U(); P[0].z = -.4f * U(); }
+            if (kind == 3) P[3] = P[1];
+            std::vector<Point2f> UV;
+            if (withUV) UV = {Point2f(.1f * U(), .1f * U()), Point2f(1 + U(), .2f * U()), Point2f(.2f * U(), 1 + U()), Point2f(1.5f + U(), 1.3f + U())};
+            std::vector<Normal3f> N;
+            if (withN) for (int i = 0; i < 4; ++i) N.push_back(Normal3f(.4f * (U() - .5f), .4f * (U() - .5f), (k % 2 ? -1.f : 1.f)));
+            BilinearPatchMesh *mesh = alloc.new_object<BilinearPatchMesh>(rfo, reverse, std::vector<int>{0, 1, 2, 3}, P, N, UV, std::vector<int>(), nullptr, alloc);
+            pstd::vector<Shape> shapes = BilinearPatch::CreatePatches(mesh, alloc);
+            Shape shape = shapes[0];
+            const BilinearPatch *blp = shape.Cast<BilinearPatch>();
+            patches.insert(patches.end(), {withUV ? 1.f : 0.f, withN ? 1.f : 0.f, (reverse ^ mesh->transformSwapsHandedness) ? 1.f : 0.f, blp->IsRectangle(mesh) ? 1.f : 0.f, shape.Area()});
+            for (int i = 0; i < 4; ++i) {
+                patches.insert(patches.end(), {mesh->p[i].x, mesh->p[i].y, mesh->p[i].z});
+                patches.insert(patches.end(), {withUV ? mesh->uv[i].x : 0.f, withUV ? mesh->uv[i].y : 0.f});
+                patches.insert(patches.end(), {withN ? mesh->n[i].x : 0.f, withN ? mesh->n[i].y : 0.f, withN ? mesh->n[i].z : 0.f});
+            }
+            Bounds3f bb = shape.Bounds();
+            DirectionCone nb = shape.NormalBounds();
+            patches.insert(patches.end(), {bb.pMin.x, bb.pMin.y, bb.pMin.z, bb.pMax.x, bb.pMax.y, bb.pMax.z, nb.w.x, nb.w.y, nb.w.z, nb.cosTheta});
+            Point3f c = Lerp(.5f, Lerp(.5f, mesh->p[0], mesh->p[2]), Lerp(.5f, mesh->p[1], mesh->p[3]));
+            for (int r = 0; r < nRays; ++r) {
+                Point3f o = c + (r % 5 == 0 ? .4f : 3.f) * Vector3f(2 * U() - 1, 2 * U() - 1, 2 * U() - 1);
+                Point3f tgt = Lerp(1.2f * U() - .1f, Lerp(1.2f * U() - .1f, mesh->p[0], mesh->p[2]), Lerp(U(), mesh->p[1], mesh->p[3]));
+                Vector3f d = tgt - o;
+                if (r % 3 == 0) d = Normalize(d);
+                float tMax = r % 7 == 0 ? 2 * U() : Infinity;
+                rays.insert(rays.end(), {o.x, o.y, o.z, d.x, d.y, d.z, tMax});
+                Ray ray(o, d);
+                pstd::optional<ShapeIntersection> si = shape.Intersect(ray, tMax);
+                float out[40] = {0};
+                out[0] = si ? 1.f : 0.f;
+                out[39] = shape.IntersectP(ray, tMax) ? 1.f : 0.f;
+                if (si) {
+                    const SurfaceInteraction &in = si->intr;
+                    float v[] = {si->tHit, in.pi.x.LowerBound(), in.pi.x.UpperBound(), in.pi.y.LowerBound(), in.pi.y.UpperBound(), in.pi.z.LowerBound(), in.pi.z.UpperBound(),
+                                 in.n.x, in.n.y, in.n.z, in.shading.n.x, in.shading.n.y, in.shading.n.z, in.uv[0], in.uv[1], in.dpdu.x, in.dpdu.y, in.dpdu.z,
+                                 in.dpdv.x, in.dpdv.y, in.dpdv.z, in.shading.dndu.x, in.shading.dndu.y, in.shading.dndu.z, in.shading.dndv.x, in.shading.dndv.y, in.shading.dndv.z,
+                                 in.shading.dpdu.x, in.shading.dpdu.y, in.shading.dpdu.z, in.shading.dpdv.x, in.shading.dpdv.y, in.shading.dpdv.z};
+                    for (size_t q = 0; q < sizeof(v) / sizeof(v[0]); ++q) out[1 + q] = v[q];
+                }
+                hits.insert(hits.end(), out, out + 40);
+            }
+            for (int r = 0; r < nSamp; ++r) {
+                float dist = r % 4 == 0 ? .3f : (r % 4 == 1 ? 1.5f : 6.f + 60.f * U());
+                Point3f p = c + dist * Normalize(Vector3f(2 * U() - 1, 2 * U() - 1, 2 * U() - 1));
+                Vector3f err = r % 2 ? Vector3f(1e-5f * U(), 1e-5f * U(), 1e-5f * U()) : Vector3f(0, 0, 0);
+                Normal3f n = r % 3 == 0 ? Normal3f(0, 0, 0) : Normal3f(Normalize(Vector3f(2 * U() - 1, 2 * U() - 1, 2 * U() - 1)));
+                Point2f u(U(), U());
+                ShapeSampleContext ctx(Point3fi(p, err), n, n, 0.f);
+                samp.insert(samp.end(), {ctx.pi.x.LowerBound(), ctx.pi.x.UpperBound(), ctx.pi.y.LowerBound(), ctx.pi.y.UpperBound(), ctx.pi.z.LowerBound(), ctx.pi.z.UpperBound(),
+                                         n.x, n.y, n.z, u[0], u[1]});
+                pstd::optional<ShapeSample> ss = shape.Sample(ctx, u);
+                float out[20] = {0};
+                out[0] = ss ? 1.f : 0.f;
+                Vector3f wi = Normalize(Vector3f(2 * U() - 1, 2 * U() - 1, 2 * U() - 1));
+                if (ss) {
+                    const Interaction &in = ss->intr;
+                    float v[] = {in.pi.x.LowerBound(), in.pi.x.UpperBound(), in.pi.y.LowerBound(), in.pi.y.UpperBound(), in.pi.z.LowerBound(), in.pi.z.UpperBound(),
+                                 in.n.x, in.n.y, in.n.z, in.uv[0], in.uv[1], ss->pdf};
+                    for (size_t q = 0; q < sizeof(v) / sizeof(v[0]); ++q) out[1 + q] = v[q];
+                    if (r % 8 != 7 && LengthSquared(in.p() - ctx.p()) > 0) wi = Normalize(in.p() - ctx.p());
+                }
+                out[13] = wi.x; out[14] = wi.y; out[15] = wi.z;
+                out[16] = shape.PDF(ctx, wi);
+                sampOut.insert(sampOut.end(), out, out + 20);
+            }
+        }
+        b.f32("blp_patches", patches);
+        b.f32("blp_rays", rays);
+        b.f32("blp_hits", hits);
+        b.f32("blp_samp_in", samp);
+        b.f32("blp_samp_out", sampOut);
+    }
 }
 
 int main(int argc, char **argv) {

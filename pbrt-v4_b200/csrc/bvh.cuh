@@ -17,6 +17,7 @@
 #include "pmath.h"
 #include "shapes.h"
 #include "quadrics.h"
+#include "bilinear.h"
 #ifndef BPT_FOLD_I2F
 #define BPT_FOLD_I2F 0   // measured neutral (XU relief, but +2 % node visits): profiles/r01d_fold_prefetch_sweep.log
 #endif
@@ -30,7 +31,9 @@ struct BVHView {
     const DeviceInstance *instances;   // non-null: two-level scene
     const float *meshAlpha;            // per mesh id: constant alpha of alpha-tested meshes (class bit 30 of the leaf record)
     const DeviceShape *shapes;         // quadrics (class bit 29 of the leaf record: the record holds the shape's bounds, not vertices)
-    const int *meshShape;              // per mesh id: index into shapes, -1 for triangle meshes
+    const float4 *patches;             // bilinear patches, 4 float4 each (same class bit)
+    const int4 *meshShape;             // per mesh id: { quadric index or -1, first patch or -1, pool index of the mesh's first record relative to
+                                       //   its BVH's first record (leaf records carry that relative index in p0.w), - }
 };
 
 #define BPT_STACK_SIZE 40
@@ -148,23 +151,36 @@ BPT_D bool AlphaRejects(const BVHView &bvh, const RayPre &r, unsigned cls, float
     if (!(cls & kClsAlpha)) return false;
     return AlphaHashRejects(bvh.meshAlpha, __float_as_int(meshIdBits), r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
 }
-// Quadric leaves (Sphere / Disk / Cylinder as custom primitives, gpu/optix/optix.cu:301-377): the leaf record carries the shape's
+// Shape leaves (Sphere / Disk / Cylinder / BilinearPatch as custom primitives, gpu/optix/optix.cu:301-469): the leaf record carries the shape's
 // bounding box where a triangle has its vertices, is flagged degenerate (so the triangle test never runs on it) and has class bit 29
 // set.  The test is Shape::IntersectP / BasicIntersect with the current tMax; a hit is reported as (pObj, tHit), from which the
 // shading kernels rebuild the QuadricIntersection.  Outlined: scenes without quadrics only pay the class-bit test on degenerate records.
 constexpr unsigned kClsShape = 0x20000000u;
-static __device__ __noinline__ float4 IntersectQuadricLeaf(const DeviceShape *shapes, const int *meshShape, int mesh, float ox, float oy, float oz,
-                                                           float dx, float dy, float dz, float tMax) {
-    QuadricHit qh;
-    if (!QuadricBasicIntersect(shapes[__ldg(meshShape + mesh)], Pt3(ox, oy, oz), Vec3(dx, dy, dz), tMax, &qh)) return make_float4(0.f, 0.f, 0.f, -1.f);
-    return make_float4(qh.pObj.x, qh.pObj.y, qh.pObj.z, qh.t);
+static __device__ __noinline__ float4 IntersectShapeLeaf(const DeviceShape *shapes, const float4 *patches, const int4 *meshShape, int mesh, int orig, float ox, float oy,
+                                                         float oz, float dx, float dy, float dz, float tMax) {
+    const int4 ms = __ldg(meshShape + mesh);
+    if (ms.x >= 0) {
+        QuadricHit qh;
+        if (!QuadricBasicIntersect(shapes[ms.x], Pt3(ox, oy, oz), Vec3(dx, dy, dz), tMax, &qh)) return make_float4(0.f, 0.f, 0.f, -1.f);
+        return make_float4(qh.pObj.x, qh.pObj.y, qh.pObj.z, qh.t);
+    }
+    // bilinear patch (gpu/optix/optix.cu:379-469): hit = (u, v)
+    const float4 *q = patches + 4 * (size_t)(ms.y + (orig - ms.z));
+    float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+    float u, v, t;
+    if (!IntersectBilinearPatch(Pt3(ox, oy, oz), Vec3(dx, dy, dz), tMax, Pt3(a.x, a.y, a.z), Pt3(b.x, b.y, b.z), Pt3(c.x, c.y, c.z), Pt3(d.x, d.y, d.z), &u, &v, &t))
+        return make_float4(0.f, 0.f, 0.f, -1.f);
+    return make_float4(u, v, 0.f, t);
 }
 // One leaf record against the ray: the reference's Primitive::Intersect(ray, tMax) for whatever the record holds
+// SHAPES = false compiles the triangle-only test (scenes without quadrics run kernels that do not contain the call at all: the
+// outlined call costs the closest-hit kernel registers around the call site, wavefront_shapes.cu)
+template <bool SHAPES>
 BPT_D bool LeafIntersect(const BVHView &bvh, const RayPre &rp, float tMax, float4 a, float4 b, float4 c, TriHit *th) {
     const unsigned cls = __float_as_uint(b.w);
     if (cls & 0x80000000u) {
-        if (!(cls & kClsShape)) return false;   // degenerate triangle (shapes.cpp:172)
-        float4 q = IntersectQuadricLeaf(bvh.shapes, bvh.meshShape, __float_as_int(c.w), rp.o.x, rp.o.y, rp.o.z, rp.d.x, rp.d.y, rp.d.z, tMax);
+        if (!SHAPES || !(cls & kClsShape)) return false;   // degenerate triangle (shapes.cpp:172)
+        float4 q = IntersectShapeLeaf(bvh.shapes, bvh.patches, bvh.meshShape, __float_as_int(c.w), __float_as_int(a.w), rp.o.x, rp.o.y, rp.o.z, rp.d.x, rp.d.y, rp.d.z, tMax);
         if (q.w < 0) return false;
         th->b0 = q.x; th->b1 = q.y; th->b2 = q.z; th->t = q.w;
         return true;
@@ -251,7 +267,7 @@ BPT_D unsigned NodeIntersect(Vec3 o, Vec3 idir, unsigned octinv4, float tMax, fl
 // Traversal statistics (counting build only)
 struct TraceCounters { unsigned long long nodes, tris, rays; };
 
-template <bool ANYHIT, bool COUNT>
+template <bool ANYHIT, bool COUNT, bool SHAPES>
 BPT_D void TraceRay(const BVHView &bvh, Pt3 o, Vec3 d, float tMax, HitRec *rec, unsigned *nNodes, unsigned *nTris) {
     RayPre rp = MakeRayPre(o, d);
     Vec3 idir(SafeInvDir(d.x), SafeInvDir(d.y), SafeInvDir(d.z));
@@ -298,7 +314,7 @@ BPT_D void TraceRay(const BVHView &bvh, Pt3 o, Vec3 d, float tMax, HitRec *rec, 
             float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
             if (COUNT) ++*nTris;
             TriHit th;
-            if (LeafIntersect(bvh, rp, rec->t, a, b, c, &th)) {
+            if (LeafIntersect<SHAPES>(bvh, rp, rec->t, a, b, c, &th)) {
                 rec->tri = (int)tri; rec->b0 = th.b0; rec->b1 = th.b1; rec->b2 = th.b2; rec->t = th.t;
                 if (ANYHIT) return;
                 tBox = th.t * (1 + 2 * gamma_n(3));
@@ -357,7 +373,7 @@ constexpr int kFlushLanes = BPT_FLUSH_LANES;   // start triangle rounds when thi
 constexpr int kRoundLanes = BPT_ROUND_LANES;   // keep going while this many lanes still have candidates
 constexpr bool kDeferCommit = BPT_DEFER_COMMIT != 0;   // finished lanes wait and commit together with the next refill
 
-template <bool ANYHIT, bool COUNT, typename LoadF, typename CommitF>
+template <bool ANYHIT, bool COUNT, bool SHAPES, typename LoadF, typename CommitF>
 BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF Load, CommitF Commit, unsigned *nNodes,
                               unsigned *nTris, unsigned *nRaysDone) {
     const unsigned FULL = 0xffffffffu;
@@ -503,7 +519,7 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
                     }
 #else
                     TriHit th;
-                    if (LeafIntersect(bvh, rp, rec.t, a, b, c, &th)) {
+                    if (LeafIntersect<SHAPES>(bvh, rp, rec.t, a, b, c, &th)) {
                         rec.tri = (int)tri; rec.b0 = th.b0; rec.b1 = th.b1; rec.b2 = th.b2; rec.t = th.t;
                         if (ANYHIT) { finished = true; head = tail; }
                         else tBox = th.t * (1 + 2 * gamma_n(3));
@@ -536,7 +552,7 @@ BPT_D void TraversePersistent(const BVHView &bvh, int nRays, int *cursor, LoadF 
 // traversed with the shifted tMax, and -- like the reference -- the reported tHit stays in the instance-space
 // parameterisation.  Stack protocol: [saved top-level node group][sentinel] are pushed on entry; the sentinel is popped
 // only after the lane's deferred triangle groups (which belong to the instance) are drained.
-template <bool ANYHIT, bool COUNT, typename LoadF, typename CommitF>
+template <bool ANYHIT, bool COUNT, bool SHAPES, typename LoadF, typename CommitF>
 BPT_D void TraversePersistentInst(const BVHView &bvh, const DeviceInstance *instances, int nRays, int *cursor, LoadF Load,
                                   CommitF Commit, unsigned *nNodes, unsigned *nTris, unsigned *nRaysDone) {
     const unsigned FULL = 0xffffffffu;
@@ -678,7 +694,7 @@ BPT_D void TraversePersistentInst(const BVHView &bvh, const DeviceInstance *inst
                     float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                     if (COUNT) ++*nTris;
                     TriHit th;
-                    if (LeafIntersect(bvh, rp, rec.t, a, b, c, &th)) {
+                    if (LeafIntersect<SHAPES>(bvh, rp, rec.t, a, b, c, &th)) {
                         rec.tri = (int)tri; rec.b0 = th.b0; rec.b1 = th.b1; rec.b2 = th.b2; rec.t = th.t; rec.inst = inst;
                         hitHere = true;
                         if (ANYHIT) { finished = true; head = tail; }

@@ -49,6 +49,7 @@ struct OwnedMesh {
     std::vector<int> idx;
     bool isQuadric = false;      // one Sphere / Disk / Cylinder: m carries the common members (n_triangles = 1: its bounds record)
     bpt_quadric q{};
+    bool isBilinear = false;     // bilinear patch mesh: idx holds four vertex indices per patch, m.n_triangles = number of patches
 };
 struct OwnedLight {
     bpt_light l;
@@ -180,7 +181,9 @@ struct bpt_engine {
     DevBuf<DeviceMesh> dMeshes;
     DevBuf<float> dMeshAlpha;        // per mesh: constant alpha of the stochastic alpha test (1 = none)
     DevBuf<DeviceShape> dShapes;     // quadrics
-    DevBuf<int> dMeshShape;          // per mesh: index into dShapes, -1 for triangle meshes
+    bool haveShapes = false;         // the scene has quadrics: the kernel set of wavefront_shapes.cu runs it
+    DevBuf<int4> dMeshShape;         // per mesh: { quadric index | -1, first patch | -1, first pool record relative to its BVH, 0 }
+    DevBuf<float4> dPatches;         // bilinear patches, 4 float4 each
     DevBuf<int> indexPool;
     DevBuf<float> nPool, uvPool, specPool;
     DevBuf<DeviceMaterial> dMaterials;
@@ -448,7 +451,9 @@ extern "C" int bpt_create(int cuda_device, const char *tables_path, bpt_engine *
     }
     UploadSobolTable(e->tables.u32.at("sobol32_2x52").data());
     UploadSobolTableTex(e->tables.u32.at("sobol32_2x52").data());
+    tu_shapes::UploadSobolTable(e->tables.u32.at("sobol32_2x52").data());
     ConfigureKernels();
+    tu_shapes::ConfigureKernels();
     // defaults (scene.cpp / film.cpp / samplers.cpp defaults)
     e->filter = bpt_filter{BPT_FILTER_GAUSSIAN, 1.5f, 1.5f, 0.5f, 1.f / 3.f, 1.f / 3.f, 3.f};
     e->sampler = bpt_sampler{BPT_SAMPLER_ZSOBOL, 16, 0, BPT_RANDOMIZE_FAST_OWEN};
@@ -577,6 +582,21 @@ extern "C" int bpt_scene_add_mesh(bpt_engine *e, const bpt_mesh *m) {
     if (m->N) o.N.assign(m->N, m->N + 3 * (size_t)m->n_vertices);
     if (m->UV) o.UV.assign(m->UV, m->UV + 2 * (size_t)m->n_vertices);
     o.idx.assign(m->indices, m->indices + 3 * (size_t)m->n_triangles);
+    o.m.P = o.m.N = o.m.UV = nullptr; o.m.indices = nullptr;
+    return BPT_OK;
+}
+extern "C" int bpt_scene_add_bilinear_mesh(bpt_engine *e, const bpt_mesh *m) {
+    if (!e || !m || !m->P || !m->indices || m->n_vertices <= 0 || m->n_triangles < 0) return e ? e->fail(BPT_ERR_INVALID, "bad bilinear mesh") : BPT_ERR_INVALID;
+    for (int i = 0; i < 4 * m->n_triangles; ++i)
+        if (m->indices[i] < 0 || m->indices[i] >= m->n_vertices) return e->fail(BPT_ERR_INVALID, "bilinear mesh index out of range");
+    if (m->has_alpha && m->alpha < 1) return e->fail(BPT_ERR_UNSUPPORTED, "alpha on bilinear patches is not implemented");
+    e->meshes.emplace_back();
+    OwnedMesh &o = e->meshes.back();
+    o.m = *m; o.isBilinear = true;
+    o.P.assign(m->P, m->P + 3 * (size_t)m->n_vertices);
+    if (m->N) o.N.assign(m->N, m->N + 3 * (size_t)m->n_vertices);
+    if (m->UV) o.UV.assign(m->UV, m->UV + 2 * (size_t)m->n_vertices);
+    o.idx.assign(m->indices, m->indices + 4 * (size_t)m->n_triangles);
     o.m.P = o.m.N = o.m.UV = nullptr; o.m.indices = nullptr;
     return BPT_OK;
 }
@@ -989,7 +1009,8 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
 
     // ---- meshes: transform to render space (TriangleMesh ctor util/mesh.cpp:25-70), build pools and lights
     std::vector<float> meshAlpha(e->meshes.size(), 1.f);
-    std::vector<int> meshShape(e->meshes.size(), -1);
+    std::vector<int4> meshShape(e->meshes.size(), make_int4(-1, -1, 0, 0));
+    std::vector<float4> patchPool;
     std::vector<DeviceShape> dshapes;
     bool instancedQuadrics = false;   // an object definition holds a quadric: its instances keep the reference's (loose) bounds
     bool anyAlpha = false;
@@ -1037,7 +1058,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         if (om.m.object_id >= 0 && om.m.area_light >= 0) return e->fail(BPT_ERR_UNSUPPORTED, "area lights are not supported with object instancing");
         if (om.m.material >= (int)e->materials.size()) return e->fail(BPT_ERR_INVALID, "mesh material index out of range");
         Xform renderFromObject = ResolveRenderFromObject(space, spaces, om.m.world_from_object, om.m.object_from_world);   // scene.h:475-477
-        const bool deviceAssemble = !om.isQuadric && om.m.area_light < 0 && om.m.n_triangles >= kDeviceAssembleMin;
+        const bool deviceAssemble = !om.isQuadric && !om.isBilinear && om.m.area_light < 0 && om.m.n_triangles >= kDeviceAssembleMin;
         std::vector<Pt3> P(deviceAssemble ? 0 : om.m.n_vertices);
         if (!deviceAssemble)
             for (int v = 0; v < om.m.n_vertices; ++v) P[v] = renderFromObject(Pt3(om.P[3 * v], om.P[3 * v + 1], om.P[3 * v + 2]));
@@ -1051,7 +1072,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
         dm.nOffset = (int)(nPool.size() / 3);
         dm.uvOffset = (int)(uvPool.size() / 2);
         dm.mediumInside = om.m.medium_inside; dm.mediumOutside = om.m.medium_outside;
-        dm.shape = -1;
+        dm.shape = -1; dm.patchBase = -1;
         DeviceShape dshape{};
         Bounds3 shapeBounds;
         if (om.isQuadric) {
@@ -1067,7 +1088,11 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             dm.flags = 0;
             if (om.m.object_id >= 0) instancedQuadrics = true;
         }
-        meshShape[mi] = dm.shape;
+        if (om.isBilinear) {
+            dm.patchBase = (int)(patchPool.size() / 4);
+            if (om.m.object_id >= 0) instancedQuadrics = true;
+        }
+        meshShape[mi] = make_int4(dm.shape, dm.patchBase, (int)triCursor - groupStart[om.m.object_id + 1], 0);
         if (!om.N.empty() || !om.UV.empty()) indexPool.insert(indexPool.end(), om.idx.begin(), om.idx.end());
         if (!om.N.empty())
             for (int v = 0; v < om.m.n_vertices; ++v) {
@@ -1143,6 +1168,49 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
                 lbounds.push_back(LightBoundsH(shapeBounds, w, phi, cosTheta, std::cos(kPi / 2), al->a.two_sided != 0));
             }
             dshapes.push_back(dshape);
+            continue;
+        }
+        if (om.isBilinear) {
+            // one pool record per patch: its bounds (BilinearPatch::Bounds, shapes.cpp:1071-1079), class bit kClsShape; vertices in the patch pool
+            for (int t = 0; t < om.m.n_triangles; ++t) {
+                PatchData pd;
+                pd.p00 = P[om.idx[4 * t]]; pd.p10 = P[om.idx[4 * t + 1]]; pd.p01 = P[om.idx[4 * t + 2]]; pd.p11 = P[om.idx[4 * t + 3]];
+                pd.flipNormal = flip; pd.hasN = !om.N.empty(); pd.hasUV = !om.UV.empty();
+                if (pd.hasN) {
+                    size_t nb = 3 * (size_t)dm.nOffset;
+                    auto NN = [&](int v) { return Nrm3(nPool[nb + 3 * v], nPool[nb + 3 * v + 1], nPool[nb + 3 * v + 2]); };
+                    pd.n00 = NN(om.idx[4 * t]); pd.n10 = NN(om.idx[4 * t + 1]); pd.n01 = NN(om.idx[4 * t + 2]); pd.n11 = NN(om.idx[4 * t + 3]);
+                }
+                pd.isRectangle = PatchIsRectangle(pd.p00, pd.p10, pd.p01, pd.p11);
+                pd.area = PatchArea(pd.p00, pd.p10, pd.p01, pd.p11);
+                patchPool.push_back(make_float4(pd.p00.x, pd.p00.y, pd.p00.z, pd.area));
+                patchPool.push_back(make_float4(pd.p10.x, pd.p10.y, pd.p10.z, b2f(pd.isRectangle ? 1u : 0u)));
+                patchPool.push_back(make_float4(pd.p01.x, pd.p01.y, pd.p01.z, 0.f));
+                patchPool.push_back(make_float4(pd.p11.x, pd.p11.y, pd.p11.z, 0.f));
+                Bounds3 pb = Union(Bounds3(pd.p00, pd.p01), Bounds3(pd.p10, pd.p11));
+                int gtri = (int)triCursor;
+                float4 *tp = &tri[3 * triCursor++];
+                tp[0] = make_float4(pb.pMin.x, pb.pMin.y, pb.pMin.z, b2f((uint32_t)mi));
+                tp[1] = make_float4(pb.pMax.x, pb.pMax.y, pb.pMax.z, b2f((uint32_t)t));
+                tp[2] = make_float4(pb.pMin.x, pb.pMin.y, pb.pMin.z, b2f(cls | kClsShape));
+                if (emissive) {
+                    DeviceLight dl{};
+                    dl.type = LIGHT_DIFFUSE_AREA; dl.tri = gtri; dl.twoSided = al->a.two_sided; dl.LemitTable = Lrec.table;
+                    float scale = lightScale;
+                    if (al->a.power > 0) {
+                        float k_e = 1;
+                        k_e *= (al->a.two_sided ? 2 : 1) * pd.area * kPi;
+                        scale *= al->a.power / k_e;
+                    }
+                    dl.scale = scale;
+                    dlights.push_back(dl);
+                    float phi = LemitMax;
+                    phi *= scale * pd.area * kPi;
+                    Vec3 w; float cosTheta;
+                    PatchNormalBounds(pd, &w, &cosTheta);   // BilinearPatch::NormalBounds (shapes.cpp:1081-1130)
+                    lbounds.push_back(LightBoundsH(pb, w, phi, cosTheta, std::cos(kPi / 2), al->a.two_sided != 0));
+                }
+            }
             continue;
         }
         for (int t = 0; t < om.m.n_triangles; ++t) {
@@ -1470,6 +1538,8 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     ECK(e->dMeshAlpha.upload(meshAlpha));
     ECK(e->dMeshShape.upload(meshShape));
     if (!dshapes.empty()) ECK(e->dShapes.upload(dshapes));
+    if (!patchPool.empty()) ECK(e->dPatches.upload(patchPool));
+    e->haveShapes = !dshapes.empty() || !patchPool.empty();
     (void)anyAlpha;
     ECK(e->indexPool.upload(indexPool));
     ECK(e->nPool.upload(nPool));
@@ -1790,7 +1860,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     rc.bvh.nodes = e->bvh.nodes; rc.bvh.tris = e->bvh.tris;
     rc.bvh.instances = instanced ? e->dInstances.p : nullptr;
     rc.bvh.meshAlpha = e->dMeshAlpha.p;
-    rc.bvh.shapes = e->dShapes.p; rc.bvh.meshShape = e->dMeshShape.p;
+    rc.bvh.shapes = e->dShapes.p; rc.bvh.patches = e->dPatches.p; rc.bvh.meshShape = e->dMeshShape.p;
     ECK(e->hitInst.alloc(instanced ? maxPaths : 1));
     rc.ps.hitInst = e->hitInst.p;
     SceneView &sv = rc.sv;
@@ -1804,7 +1874,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
     sv.cieX = e->dTables.p; sv.cieY = e->dTables.p + kNLambda; sv.cieZ = e->dTables.p + 2 * kNLambda; sv.illumD65 = e->dTables.p + 3 * kNLambda;
     sv.textures = e->haveTextures ? e->dTextures.p : nullptr; sv.mipLevels = e->haveTextures ? e->dMipLevels.p : nullptr;
     sv.ewaLUT = e->haveTextures ? e->dEwaLUT.p : nullptr;
-    sv.shapes = e->dShapes.p;
+    sv.shapes = e->dShapes.p; sv.patches = e->dPatches.p;
     sv.rgb2specScale = e->dRgb2spec.n ? e->dRgb2spec.p : nullptr; sv.rgb2specCoeffs = e->dRgb2spec.n ? e->dRgb2spec.p + 64 : nullptr;
     sv.nLights = (int)dlights.size();
     // ZSobol digit-prefix table: [dimension][pixel] uint32 (only when the permuted index fits in 32 bits)
@@ -1900,7 +1970,10 @@ static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int 
     auto profEnd = [&]() { if (profile) cudaEventRecord(prof.back().second.second, st); };
     const int sms = e->smCount;
     int launches = 0;
-    UploadSamplerConstants(rc.sampler, st);
+    // kernel set: wavefront.cu (triangles only) or wavefront_shapes.cu (quadric leaves, interactions, area lights compiled in)
+    const bool useShapes = e->haveShapes;
+#define KSEL(f) (useShapes ? &tu_shapes::f : &f)
+    KSEL(UploadSamplerConstants)(rc.sampler, st);
     if (e->haveTextures) UploadSamplerConstantsTex(rc.sampler, st);
     ECK(cudaEventRecord(e->ev0, st));
     // scanline bands so that a band of S samples fits in the path-state arrays
@@ -1913,28 +1986,28 @@ static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int 
         int S = std::max(1, std::min(n_samples, rc.maxPaths / nPix));
         for (int s0 = 0; s0 < n_samples; s0 += S) {
             int ns = std::min(S, n_samples - s0);
-            LaunchResetAll(rc, st); ++launches;
-            LaunchGenerateCameraRays(rc, x0, x1, by0, by1, first_sample + s0, ns, sms, st); ++launches;
+            KSEL(LaunchResetAll)(rc, st); ++launches;
+            KSEL(LaunchGenerateCameraRays)(rc, x0, x1, by0, by1, first_sample + s0, ns, sms, st); ++launches;
             int cur = Q_RAY0, next = Q_RAY1;
             int maxDepth = rc.integ.maxDepth;
             // Scenes with media or interface surfaces need one wavefront iteration per path *segment* (null collisions and
             // interface crossings do not advance depth): iterate until the ray queue is empty.  Otherwise depth == iteration.
             const bool dynamic = rc.useTr != 0;
             for (int depth = 0; dynamic ? depth < 100000 : depth <= maxDepth; ++depth) {
-                LaunchResetDepth(rc, next, st); ++launches;
-                profBegin(0); LaunchTraceClosest(rc, cur, count, sms, st); ++launches; profEnd();
-                if (rc.nMedia > 0) { profBegin(4); LaunchSampleMedium(rc, next, sms, st); launches += 2; profEnd(); }
-                if (rc.nInfinite > 0) { LaunchHandleEscaped(rc, sms, st); ++launches; }
-                if (e->haveAreaLights) { LaunchHandleEmissive(rc, sms, st); ++launches; }
+                KSEL(LaunchResetDepth)(rc, next, st); ++launches;
+                profBegin(0); KSEL(LaunchTraceClosest)(rc, cur, count, sms, st); ++launches; profEnd();
+                if (rc.nMedia > 0) { profBegin(4); KSEL(LaunchSampleMedium)(rc, next, sms, st); launches += 2; profEnd(); }
+                if (rc.nInfinite > 0) { KSEL(LaunchHandleEscaped)(rc, sms, st); ++launches; }
+                if (e->haveAreaLights) { KSEL(LaunchHandleEmissive)(rc, sms, st); ++launches; }
                 // (GBufferFilm with maxdepth 0: the visible surface is still initialised at the first hit, cpu/integrators.cpp:1118-1145,
                 // before Li() returns at the depth test -- the shading kernels do both, so they run once more)
                 if (!dynamic && depth == maxDepth && !(rc.film.isGBuffer && depth == 0)) break;
                 profBegin(2);
                 for (int m = 0; m < MAT_NTAGS; ++m)
-                    if (e->materialPresent[m]) { if (e->haveTextures) LaunchShadeTex(rc, m, next, sms, st); else LaunchShade(rc, m, next, sms, st); ++launches; }
+                    if (e->materialPresent[m]) { if (e->haveTextures) LaunchShadeTex(rc, m, next, sms, st); else KSEL(LaunchShade)(rc, m, next, sms, st); ++launches; }
                 profEnd();
                 profBegin(1);
-                if (rc.useTr) LaunchTraceShadowTr(rc, sms, st); else LaunchTraceShadow(rc, count, sms, st);
+                if (rc.useTr) KSEL(LaunchTraceShadowTr)(rc, sms, st); else KSEL(LaunchTraceShadow)(rc, count, sms, st);
                 ++launches; profEnd();
                 std::swap(cur, next);
                 if (dynamic || e->raySort) {
@@ -1944,7 +2017,7 @@ static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int 
                     if (live == 0) break;
                     if (e->raySort && !(!dynamic && depth + 1 > maxDepth)) {
                         profBegin(3);
-                        bool flipped = LaunchRaySort(rc, cur, live, e->bvh.bmin, e->bvh.bmax, e->sortKeys.p, e->sortKeysTmp.p, e->sortQueueTmp.p,
+                        bool flipped = KSEL(LaunchRaySort)(rc, cur, live, e->bvh.bmin, e->bvh.bmax, e->sortKeys.p, e->sortKeysTmp.p, e->sortQueueTmp.p,
                                                      e->sortHist.p, st);
                         launches += 4;
                         if (flipped) ECK(cudaMemcpyAsync(rc.queues[cur], e->sortQueueTmp.p, sizeof(int) * (size_t)live, cudaMemcpyDeviceToDevice, st));
@@ -1952,7 +2025,8 @@ static int RenderImpl(bpt_engine *e, int first_sample, int n_samples, const int 
                     }
                 }
             }
-            LaunchUpdateFilm(rc, x0, x1, by0, by1, ns, sms, st); ++launches;
+            KSEL(LaunchUpdateFilm)(rc, x0, x1, by0, by1, ns, sms, st); ++launches;
+#undef KSEL
         }
     }
     ECK(cudaEventRecord(e->ev1, st));
@@ -2117,7 +2191,7 @@ extern "C" int bpt_get_stats(bpt_engine *e, bpt_stats *out) {
 extern "C" int bpt_trace_closest_device(bpt_engine *e, const void *rays_dev, int n, void *hits_dev, int flags) {
     if (!e || !e->committed || !rays_dev || !hits_dev || n < 0) return BPT_ERR_INVALID;
     ECK(cudaSetDevice(e->device));
-    LaunchTraceRaw(e->rc.bvh, (const float4 *)rays_dev, n, (float4 *)hits_dev, nullptr, e->rawCursor.p, e->stats.p, (flags & 2) != 0, (flags & 1) != 0,
+    (e->haveShapes ? &tu_shapes::LaunchTraceRaw : &LaunchTraceRaw)(e->rc.bvh, (const float4 *)rays_dev, n, (float4 *)hits_dev, nullptr, e->rawCursor.p, e->stats.p, (flags & 2) != 0, (flags & 1) != 0,
                    e->smCount, e->stream);
     ECK(cudaStreamSynchronize(e->stream));
     return BPT_OK;
@@ -2128,7 +2202,7 @@ static int TraceHost(bpt_engine *e, const float *rays, int n, float *hits, float
     DevBuf<float4> dr, dh; DevBuf<float> dt;
     ECK(dr.alloc(2 * (size_t)n)); ECK(dh.alloc(n)); ECK(dt.alloc(n));
     ECK(cudaMemcpy(dr.p, rays, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice));
-    LaunchTraceRaw(e->rc.bvh, dr.p, n, dh.p, dt.p, e->rawCursor.p, e->stats.p, any, false, e->smCount, e->stream);
+    (e->haveShapes ? &tu_shapes::LaunchTraceRaw : &LaunchTraceRaw)(e->rc.bvh, dr.p, n, dh.p, dt.p, e->rawCursor.p, e->stats.p, any, false, e->smCount, e->stream);
     ECK(cudaStreamSynchronize(e->stream));
     ECK(cudaGetLastError());
     std::vector<float> hh(4 * (size_t)n);

@@ -9,6 +9,7 @@
 #include "scene.h"
 #include "shapes.h"
 #include "quadrics.h"
+#include "bilinear.h"
 
 namespace bpt {
 
@@ -41,6 +42,7 @@ struct SceneView {
     const DeviceMIPLevel *mipLevels;
     const float *ewaLUT;              // MIPFilterLUT, 128 entries (util/mipmap.cpp:59)
     const DeviceShape *shapes;        // quadrics (null: none)
+    const float4 *patches;            // bilinear patches: p00 | area, p10 | isRectangle, p01, p11 (rendering space)
 };
 
 #if defined(__CUDACC__)
@@ -143,17 +145,47 @@ BPT_HD TriData LoadTriangle(const SceneView &sv, int tri) {
     return td;
 }
 
-// SurfaceInteraction of a recorded hit: triangles record barycentrics, quadrics the object-space hit point (quadrics.h)
+// Patch i of a bilinear patch mesh with the per-vertex attributes of its mesh
+BPT_HD PatchData LoadPatch(const SceneView &sv, const DeviceMesh &m, int i) {
+    PatchData pd;
+    const float4 *q = sv.patches + 4 * (size_t)(m.patchBase + i);
+    float4 a = q[0], b = q[1], c = q[2], d = q[3];
+    pd.p00 = Pt3(a.x, a.y, a.z); pd.p10 = Pt3(b.x, b.y, b.z); pd.p01 = Pt3(c.x, c.y, c.z); pd.p11 = Pt3(d.x, d.y, d.z);
+    pd.area = a.w; pd.isRectangle = f2b(b.w) != 0;
+    pd.flipNormal = m.flags & 1; pd.hasN = (m.flags & 2) != 0; pd.hasUV = (m.flags & 4) != 0;
+    if (pd.hasN || pd.hasUV) {
+        const int *v = sv.indexPool + m.indexOffset + 4 * i;
+        int v0 = v[0], v1 = v[1], v2 = v[2], v3 = v[3];
+        if (pd.hasN) {
+            const float *n = sv.nPool + 3 * (size_t)m.nOffset;
+            pd.n00 = Nrm3(n[3 * v0], n[3 * v0 + 1], n[3 * v0 + 2]); pd.n10 = Nrm3(n[3 * v1], n[3 * v1 + 1], n[3 * v1 + 2]);
+            pd.n01 = Nrm3(n[3 * v2], n[3 * v2 + 1], n[3 * v2 + 2]); pd.n11 = Nrm3(n[3 * v3], n[3 * v3 + 1], n[3 * v3 + 2]);
+        }
+        if (pd.hasUV) {
+            const float *uv = sv.uvPool + 2 * (size_t)m.uvOffset;
+            pd.uv00 = Vec2(uv[2 * v0], uv[2 * v0 + 1]); pd.uv10 = Vec2(uv[2 * v1], uv[2 * v1 + 1]);
+            pd.uv01 = Vec2(uv[2 * v2], uv[2 * v2 + 1]); pd.uv11 = Vec2(uv[2 * v3], uv[2 * v3 + 1]);
+        }
+    }
+    return pd;
+}
+
+// SurfaceInteraction of a recorded hit: triangles record barycentrics, quadrics the object-space hit point (quadrics.h), bilinear
+// patches (u, v)
+// (SHAPES = false: the kernels of scenes without quadrics, compiled without the dispatch)
+template <bool SHAPES>
 BPT_HD SurfaceIntr HitInteraction(const SceneView &sv, const TriData &td, float b0, float b1, float b2, SurfaceExtras *ex = nullptr) {
-    const int shape = sv.meshes[td.mesh].shape;
-    if (shape >= 0) return QuadricInteraction(sv.shapes[shape], Pt3(b0, b1, b2), ex);
+    const int shape = SHAPES ? sv.meshes[td.mesh].shape : -1;
+    if (SHAPES && shape >= 0) return QuadricInteraction(sv.shapes[shape], Pt3(b0, b1, b2), ex);
+    if (SHAPES && sv.meshes[td.mesh].patchBase >= 0) return BilinearInteraction(LoadPatch(sv, sv.meshes[td.mesh], td.triIndex), b0, b1, ex);
     TriHit th{b0, b1, b2, 0.f};
     return TriangleInteraction(td.p0, td.p1, td.p2, td.a, th, ex);
 }
 // wo of that interaction in the space of the enclosing BVH, for a ray of direction d in that space
+template <bool SHAPES>
 BPT_HD Vec3 HitWo(const SceneView &sv, const TriData &td, Vec3 d) {
-    const int shape = sv.meshes[td.mesh].shape;
-    if (shape >= 0) return QuadricWo(sv.shapes[shape], d);
+    const int shape = SHAPES ? sv.meshes[td.mesh].shape : -1;
+    if (SHAPES && shape >= 0) return QuadricWo(sv.shapes[shape], d);
     return Normalize(-d);
 }
 
@@ -165,14 +197,17 @@ BPT_HD Spec AreaLightL(const SceneView &sv, const DeviceLight &light, Nrm3 n, Ve
 
 struct LightLiSample { Spec L; Vec3 wi; float pdf; Pt3i pLight; Nrm3 nLight; bool valid; };
 
+template <bool SHAPES>
 BPT_HD LightLiSample AreaLightSampleLi(const SceneView &sv, const DeviceLight &light, const LightSampleContext &ctx, Vec2 u,
                                        const Wavelengths &wl) {
     LightLiSample ls;
     ls.valid = false;
     TriData td = LoadTriangle(sv, light.tri);
-    const int shape = sv.meshes[td.mesh].shape;
-    ShapeSample ss = shape >= 0 ? QuadricSampleSolidAngle(sv.shapes[shape], ctx.pi, ctx.n, u)
-                                : TriangleSampleSolidAngle(td.p0, td.p1, td.p2, td.a, ctx.p(), ctx.ns, u);
+    const int shape = SHAPES ? sv.meshes[td.mesh].shape : -1;
+    ShapeSample ss;
+    if (SHAPES && shape >= 0) ss = QuadricSampleSolidAngle(sv.shapes[shape], ctx.pi, ctx.n, u);
+    else if (SHAPES && sv.meshes[td.mesh].patchBase >= 0) ss = PatchSampleSolidAngle(LoadPatch(sv, sv.meshes[td.mesh], td.triIndex), ctx.p(), ctx.ns, u);
+    else ss = TriangleSampleSolidAngle(td.p0, td.p1, td.p2, td.a, ctx.p(), ctx.ns, u);
     if (!ss.valid || ss.pdf == 0 || LengthSquared(ss.pi.p() - ctx.p()) == 0) return ls;
     Vec3 wi = Normalize(ss.pi.p() - ctx.p());
     Spec Le = AreaLightL(sv, light, ss.n, -wi, wl);
@@ -180,10 +215,12 @@ BPT_HD LightLiSample AreaLightSampleLi(const SceneView &sv, const DeviceLight &l
     ls.L = Le; ls.wi = wi; ls.pdf = ss.pdf; ls.pLight = ss.pi; ls.nLight = ss.n; ls.valid = true;
     return ls;
 }
+template <bool SHAPES>
 BPT_HD float AreaLightPDF_Li(const SceneView &sv, const DeviceLight &light, const LightSampleContext &ctx, Vec3 wi) {
     TriData td = LoadTriangle(sv, light.tri);
-    const int shape = sv.meshes[td.mesh].shape;
-    if (shape >= 0) return QuadricPDFSolidAngle(sv.shapes[shape], ctx.pi, ctx.n, wi);
+    const int shape = SHAPES ? sv.meshes[td.mesh].shape : -1;
+    if (SHAPES && shape >= 0) return QuadricPDFSolidAngle(sv.shapes[shape], ctx.pi, ctx.n, wi);
+    if (SHAPES && sv.meshes[td.mesh].patchBase >= 0) return PatchPDFSolidAngle(LoadPatch(sv, sv.meshes[td.mesh], td.triIndex), ctx.pi, ctx.n, ctx.ns, wi);
     return TrianglePDFSolidAngle(td.p0, td.p1, td.p2, td.a, ctx.pi, ctx.n, ctx.ns, wi);
 }
 

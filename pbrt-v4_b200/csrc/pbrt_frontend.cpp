@@ -97,6 +97,7 @@ struct GState {
 
 struct MeshRec {
     std::vector<float> P, N, UV; std::vector<int> idx;
+    std::vector<int> quadIdx;   // bilinear patches (Shape "bilinearmesh", or the quad faces of a PLY file): p00, p10, p01, p11 per patch
     bpt_mesh m;
     bool isQuadric = false;   // Shape "sphere" / "disk" / "cylinder": q carries the parameters, m the members common to all shapes
     bpt_quadric q;
@@ -570,8 +571,10 @@ struct Frontend {
                     decode(0);
                     for (auto &th : pool) th.join();
                 }
-                for (int b : bad) if (b) { err = path + ": only triangle faces are supported (quads become bilinear patches in pbrt)"; return false; }
-                return true;
+                bool allTriangles = true;
+                for (int b : bad) if (b) allTriangles = false;
+                if (allTriangles) return true;
+                mr->idx.clear();   // a face that is not a triangle: the generic walk below sorts triangles and quads
             }
             mr->idx.reserve(3 * (size_t)nFaces);
             for (int f = 0; f < nFaces; ++f)
@@ -581,9 +584,11 @@ struct Frontend {
                     int cnt = (int)load(q, a.cntType); q += tsz[a.cntType];
                     if (q + (size_t)cnt * tsz[a.type] > end) { err = path + ": truncated face data"; return false; }
                     if (a.isIdx) {
-                        if (cnt != 3) { err = path + ": only triangle faces are supported (quads become bilinear patches in pbrt)"; return false; }
-                        if (a.type == 2 || a.type == 3) { int32_t v3[3]; memcpy(v3, q, 12); mr->idx.push_back(v3[0]); mr->idx.push_back(v3[1]); mr->idx.push_back(v3[2]); }
-                        else for (int k = 0; k < 3; ++k) mr->idx.push_back((int)load(q + (size_t)k * tsz[a.type], a.type));
+                        if (cnt != 3 && cnt != 4) { err = path + ": only triangle and quad faces are supported"; return false; }
+                        int v4[4];
+                        for (int k = 0; k < cnt; ++k) v4[k] = (int)load(q + (size_t)k * tsz[a.type], a.type);
+                        if (cnt == 3) { mr->idx.push_back(v4[0]); mr->idx.push_back(v4[1]); mr->idx.push_back(v4[2]); }
+                        else { mr->quadIdx.push_back(v4[0]); mr->quadIdx.push_back(v4[1]); mr->quadIdx.push_back(v4[3]); mr->quadIdx.push_back(v4[2]); }   // util/mesh.cpp:302-305
                     }
                     q += (size_t)cnt * tsz[a.type];
                 }
@@ -605,7 +610,8 @@ struct Frontend {
                 for (int k = 0; k < (int)cnt; ++k) { double d; if (!readNum(p.listItem, &d)) { err = path + ": truncated face data"; return false; } v[k] = (int)d; }
                 if (p.name == "vertex_indices" || p.name == "vertex_index") {
                     if (cnt == 3) mr->idx.insert(mr->idx.end(), v.begin(), v.end());
-                    else { err = path + ": only triangle faces are supported (quads become bilinear patches in pbrt)"; return false; }
+                    else if (cnt == 4) { mr->quadIdx.push_back(v[0]); mr->quadIdx.push_back(v[1]); mr->quadIdx.push_back(v[3]); mr->quadIdx.push_back(v[2]); }
+                    else { err = path + ": only triangle and quad faces are supported"; return false; }
                 }
             }
         return true;
@@ -630,6 +636,20 @@ struct Frontend {
             if (fn.empty()) { err = "plymesh: missing filename"; return false; }
             if (fn[0] != '/') fn = baseDir + "/" + fn;
             if (!readPLY(fn, mr.get())) return false;
+        } else if (type == "bilinearmesh") {   // BilinearPatch::CreateMesh (shapes.cpp:910-999)
+            Param *P = pl.find("P");
+            if (!P || P->nums.size() % 3) { err = "bilinearmesh: missing or bad \"P\""; return false; }
+            mr->P.assign(P->nums.begin(), P->nums.end());
+            Param *I = pl.find("indices");
+            if (I) mr->quadIdx.assign(I->nums.begin(), I->nums.end());
+            else if (mr->P.size() == 12) mr->quadIdx = {0, 1, 2, 3};
+            else { err = "bilinearmesh: \"indices\" required"; return false; }
+            while (mr->quadIdx.size() % 4) mr->quadIdx.pop_back();
+            if (Param *N = pl.find("N")) mr->N.assign(N->nums.begin(), N->nums.end());
+            if (Param *U = pl.find("uv")) mr->UV.assign(U->nums.begin(), U->nums.end());
+            if (!mr->N.empty() && mr->N.size() != mr->P.size()) { err = "bilinearmesh: N size mismatch"; return false; }
+            if (!mr->UV.empty() && mr->UV.size() / 2 != mr->P.size() / 3) { err = "bilinearmesh: uv size mismatch"; return false; }
+            if (pl.find("emissionfilename")) { err = "bilinearmesh: \"emissionfilename\" is not supported"; return false; }
         } else if (type == "sphere" || type == "disk" || type == "cylinder") {
             // Sphere / Disk / Cylinder::Create (shapes.cpp:72-83, 107-117, 135-146): the defaults are theirs
             mr->isQuadric = true;
@@ -641,11 +661,12 @@ struct Frontend {
             else if (type == "cylinder") { q.type = BPT_SHAPE_CYLINDER; q.zmin = pl.f("zmin", -1.f); q.zmax = pl.f("zmax", 1.f); }
             else { q.type = BPT_SHAPE_DISK; q.height = pl.f("height", 0.f); q.innerradius = pl.f("innerradius", 0.f); }
             if (pl.find("alpha")) { err = "alpha on a " + type + " is not supported (triangle meshes only)"; return false; }
-        } else { err = "shape \"" + type + "\" is not supported (trianglemesh, plymesh, sphere, disk, cylinder)"; return false; }
+        } else { err = "shape \"" + type + "\" is not supported (trianglemesh, plymesh, bilinearmesh, sphere, disk, cylinder)"; return false; }
         std::memset(&mr->m, 0, sizeof(mr->m));
         if (Param *al = pl.find("alpha")) {   // getAlphaTexture (scene.cpp): "float alpha" < 1 -> FloatConstantTexture; texture-valued alpha: not implemented
             if (al->type != "float" || al->nums.size() != 1) { err = "texture-valued alpha is not supported (constant \"float alpha\" only)"; return false; }
             if ((float)al->nums[0] < 1.f) { mr->m.has_alpha = 1; mr->m.alpha = (float)al->nums[0]; }
+            if (mr->m.has_alpha && !mr->quadIdx.empty()) { err = "alpha on bilinear patches is not supported"; return false; }
         }
         mr->m.n_vertices = (int)mr->P.size() / 3; mr->m.n_triangles = (int)mr->idx.size() / 3;
         mr->m.world_from_object = ToB(gs.ctm.m); mr->m.object_from_world = ToB(gs.ctm.mInv);
@@ -1013,6 +1034,14 @@ bool Frontend::finish() {
             q.material = bm.material; q.area_light = bm.area_light; q.medium_inside = bm.medium_inside; q.medium_outside = bm.medium_outside;
             q.object_id = bm.object_id;
             if (!ck(bpt_scene_add_quadric(e, &q))) return false;
+            continue;
+        }
+        if (!m->quadIdx.empty()) {
+            // Shape::Create: the triangles of a PLY file first, then its quads as a bilinear patch mesh over the same vertices (shapes.cpp:1435-1461)
+            bm.P = m->P.data(); bm.N = m->N.empty() ? nullptr : m->N.data(); bm.UV = m->UV.empty() ? nullptr : m->UV.data();
+            if (!m->idx.empty()) { bm.indices = m->idx.data(); if (!ck(bpt_scene_add_mesh(e, &bm))) return false; }
+            bm.n_triangles = (int)m->quadIdx.size() / 4; bm.indices = m->quadIdx.data();
+            if (!ck(bpt_scene_add_bilinear_mesh(e, &bm))) return false;
             continue;
         }
 #ifdef BPT_FRONTEND_IN_LIBRARY

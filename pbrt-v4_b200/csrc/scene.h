@@ -109,6 +109,8 @@ struct DeviceMesh {
     int uvOffset;              // offset (in float2) into the uv pool
     int mediumInside, mediumOutside;   // -1 = none
     int shape;                 // >= 0: this "mesh" is one quadric (index into SceneView::shapes, quadrics.h); its single pool record holds the bounds
+    int patchBase;             // >= 0: a bilinear patch mesh; patch i of the mesh is SceneView::patches[4 * (patchBase + i)] (bilinear.h), its pool
+                               // record holds the patch's bounds, indexPool has four vertex indices per patch (for N / uv)
 };
 
 struct DeviceLight {

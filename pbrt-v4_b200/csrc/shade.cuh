@@ -100,7 +100,7 @@ __device__ __forceinline__ void StoreRayDiffs(const RenderCtx &rc, int slot, con
     rc.ps.rdiff[3 * M + slot] = make_float4(r.ryD.x, r.ryD.y, r.ryD.z, 0.f);
 }
 
-template <typename Material, bool TEX>
+template <typename Material, bool TEX, bool SHAPES>
 __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int nextQ) {
     const int n = rc.counts[Q_MAT0 + Material::kTag];
     const int *queue = rc.queues[Q_MAT0 + Material::kTag];
@@ -111,18 +111,18 @@ __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int
         int tri = __float_as_int(h.x);
         TriData td = LoadTriangle(rc.sv, tri);
         SurfaceExtras ex;
-        SurfaceIntr isect = HitInteraction(rc.sv, td, h.y, h.z, h.w, TEX ? &ex : nullptr);
+        SurfaceIntr isect = HitInteraction<SHAPES>(rc.sv, td, h.y, h.z, h.w, TEX ? &ex : nullptr);
         const DeviceMesh &mesh = rc.sv.meshes[td.mesh];
         float4 d4 = ps.rayD[slot];
         // isect.wo: the Interaction constructor normalises it (interaction.h:32-33, wo(Normalize(wo))) -- not a no-op in float: a third
         // of all unit vectors change in the last bit when normalised again, which the microfacet BxDFs see (r02c bisection).
         // A quadric takes -ray.d to object space first and normalises there and on the way back (HitWo).
-        Vec3 wo = HitWo(rc.sv, td, Vec3(d4.x, d4.y, d4.z));
+        Vec3 wo = HitWo<SHAPES>(rc.sv, td, Vec3(d4.x, d4.y, d4.z));
         if (rc.sv.instances) {
             const DeviceInstance &I = rc.sv.instances[ps.hitInst[slot]];
             if (!I.identity) {
                 // ret.wo = Normalize(t(si.wo)), si.wo the interaction's wo in instance space (cpu/primitive.cpp:114-123)
-                isect = XformInteraction(I, isect); wo = Normalize(XformVec(I.m, HitWo(rc.sv, td, XformVec(I.mInv, Vec3(d4.x, d4.y, d4.z)))));
+                isect = XformInteraction(I, isect); wo = Normalize(XformVec(I.m, HitWo<SHAPES>(rc.sv, td, XformVec(I.mInv, Vec3(d4.x, d4.y, d4.z)))));
                 if (TEX) ex = XformExtras(I, ex);
             }
         }
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(128, BPT_SHADE_CTAS) k_shade(RenderCtx rc, int
             if (lightIndex >= 0) {
                 const DeviceLight &light = rc.sv.lights[lightIndex];
                 LightLiSample ls;
-                if (light.type == LIGHT_DIFFUSE_AREA) ls = AreaLightSampleLi(rc.sv, light, ctx, uLight, wl);
+                if (light.type == LIGHT_DIFFUSE_AREA) ls = AreaLightSampleLi<SHAPES>(rc.sv, light, ctx, uLight, wl);
                 else if (IsDeltaLight(light.type)) ls = DeltaLightSampleLi(rc.sv.specPool, light, ctx.p(), wl);
                 else ls = InfiniteLightSampleLi(rc.sv, light, ctx, uLight, wl);
                 if (ls.valid && ls.L.IsNonZero() && ls.pdf != 0) {

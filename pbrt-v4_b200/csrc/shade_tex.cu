@@ -3,13 +3,23 @@
 // textures.h:1215-1240).  A separate translation unit so that scenes without textures keep the constant-parameter kernels'
 // registers and instruction footprint (and so that the two sets compile in parallel); it carries its own copies of the sampler's
 // constant-memory tables.
+// Compiled twice (the build's long pole is ptxas on these kernels): as it is for the single-layer materials, and through
+// shade_tex_layered.cu (BPT_TEX_LAYERED) for the two LayeredBxDF materials; each object file has its own constant tables.
+#ifndef BPT_TEX_LAYERED
+#define BPT_TEX_LAYERED 0
+#endif
 #define BPT_SOBOL_DEVICE_TABLE
 #include "shade.cuh"
 #include "kernels.h"
 
 namespace bpt {
+#if BPT_TEX_LAYERED
+#define TEXFN(name) name##Layered
+#else
+#define TEXFN(name) name
+#endif
 
-void UploadSobolTableTex(const uint32_t *t) {
+void TEXFN(UploadSobolTableTex)(const uint32_t *t) {
     cudaMemcpyToSymbol(c_sobol32, t, sizeof(uint32_t) * 104);
     static uint32_t lut[2 * 4 * 256];
     for (int d = 0; d < 2; ++d)
@@ -20,26 +30,36 @@ void UploadSobolTableTex(const uint32_t *t) {
                 lut[(d * 4 + b) * 256 + x] = v;
             }
     cudaMemcpyToSymbol(g_sobolByteLUT, lut, sizeof(lut));
+#if !BPT_TEX_LAYERED
+    UploadSobolTableTexLayered(t);
+#endif
 }
 
-void UploadSamplerConstantsTex(const SamplerParams &sp, cudaStream_t st) {
+void TEXFN(UploadSamplerConstantsTex)(const SamplerParams &sp, cudaStream_t st) {
     static thread_local uint64_t hashes[kDimHashTable];
     for (int d = 0; d < kDimHashTable; ++d) hashes[d] = Hash_i32x2(d, sp.seed);
     cudaMemcpyToSymbolAsync(c_sampler, &sp, sizeof(SamplerParams), 0, cudaMemcpyHostToDevice, st);
     cudaMemcpyToSymbolAsync(c_dimHash, hashes, sizeof(hashes), 0, cudaMemcpyHostToDevice, st);
+#if !BPT_TEX_LAYERED
+    UploadSamplerConstantsTexLayered(sp, st);
+#endif
 }
 
-void LaunchShadeTex(const RenderCtx &rc, int materialTag, int nextQ, int sms, cudaStream_t st) {
+void TEXFN(LaunchShadeTex)(const RenderCtx &rc, int materialTag, int nextQ, int sms, cudaStream_t st) {
     const int grid = sms * 2 * BPT_SHADE_CTAS;
     switch (materialTag) {
-    case MAT_DIFFUSE: k_shade<DiffuseMaterialEval, true><<<grid, 128, 0, st>>>(rc, nextQ); break;
-    case MAT_CONDUCTOR: k_shade<ConductorMaterialEval, true><<<grid, 128, 0, st>>>(rc, nextQ); break;
-    case MAT_DIELECTRIC: k_shade<DielectricMaterialEval, true><<<grid, 128, 0, st>>>(rc, nextQ); break;
-    case MAT_COATED_CONDUCTOR: k_shade<CoatedConductorMaterialEval, true><<<grid, 128, 0, st>>>(rc, nextQ); break;
-    case MAT_COATED_DIFFUSE: k_shade<CoatedDiffuseMaterialEval, true><<<grid, 128, 0, st>>>(rc, nextQ); break;
-    case MAT_DIFFUSE_TRANSMISSION: k_shade<DiffuseTransmissionMaterialEval, true><<<grid, 128, 0, st>>>(rc, nextQ); break;
-    case MAT_THIN_DIELECTRIC: k_shade<ThinDielectricMaterialEval, true><<<grid, 128, 0, st>>>(rc, nextQ); break;
-    case MAT_INTERFACE: k_shade<InterfaceMaterialEval, true><<<sms * 4, 128, 0, st>>>(rc, nextQ); break;
+#if BPT_TEX_LAYERED
+    case MAT_COATED_CONDUCTOR: k_shade<CoatedConductorMaterialEval, true, true><<<grid, 128, 0, st>>>(rc, nextQ); break;
+    case MAT_COATED_DIFFUSE: k_shade<CoatedDiffuseMaterialEval, true, true><<<grid, 128, 0, st>>>(rc, nextQ); break;
+#else
+    case MAT_DIFFUSE: k_shade<DiffuseMaterialEval, true, true><<<grid, 128, 0, st>>>(rc, nextQ); break;
+    case MAT_CONDUCTOR: k_shade<ConductorMaterialEval, true, true><<<grid, 128, 0, st>>>(rc, nextQ); break;
+    case MAT_DIELECTRIC: k_shade<DielectricMaterialEval, true, true><<<grid, 128, 0, st>>>(rc, nextQ); break;
+    case MAT_COATED_CONDUCTOR: case MAT_COATED_DIFFUSE: LaunchShadeTexLayered(rc, materialTag, nextQ, sms, st); break;
+    case MAT_DIFFUSE_TRANSMISSION: k_shade<DiffuseTransmissionMaterialEval, true, true><<<grid, 128, 0, st>>>(rc, nextQ); break;
+    case MAT_THIN_DIELECTRIC: k_shade<ThinDielectricMaterialEval, true, true><<<grid, 128, 0, st>>>(rc, nextQ); break;
+    case MAT_INTERFACE: k_shade<InterfaceMaterialEval, true, true><<<sms * 4, 128, 0, st>>>(rc, nextQ); break;
+#endif
     default: break;
     }
 }

@@ -11,6 +11,14 @@
 //   k_update_film             EvaluatePixelSample tail + RGBFilm::AddSample film.h:239-255 (wavefront/film.cpp:13-39)
 // Sampler dimensions are consumed sequentially exactly as VolPathIntegrator::Li does: the path
 // carries its own dimension counter.
+// This file is compiled twice: as it is (BPT_WITH_SHAPES = 0: triangle-only scenes, the benchmark configurations) and through
+// wavefront_shapes.cu (BPT_WITH_SHAPES = 1: the same kernels with the quadric leaf test and the quadric interactions / area lights
+// compiled in, every name inside namespace bpt::tu_shapes).  The engine picks the set per scene, so the quadric code costs scenes
+// without quadrics nothing (with it in, the closest-hit kernel gained local-memory traffic around the outlined call and the diffuse
+// shading kernel went from 96 to 109 registers).
+#ifndef BPT_WITH_SHAPES
+#define BPT_WITH_SHAPES 0
+#endif
 #define BPT_SOBOL_DEVICE_TABLE
 #include "wavefront.cuh"
 #include "radix_sort.cuh"
@@ -21,6 +29,10 @@
 #include "shade.cuh"
 
 namespace bpt {
+#if BPT_WITH_SHAPES
+namespace tu_shapes {
+#endif
+constexpr bool kShapes = BPT_WITH_SHAPES != 0;
 
 uint32_t h_sobol32[2 * 52];
 
@@ -188,9 +200,9 @@ __global__ void __launch_bounds__(128, BPT_TRACE_CTAS) k_trace_closest(RenderCtx
         }
     };
     if (INST)
-        TraversePersistentInst<false, COUNT>(rc.bvh, rc.bvh.instances, nRays, &rc.counts[Q_CURSOR_CLOSEST], load, commitInst, &locNodes, &locTris, &locRays);
+        TraversePersistentInst<false, COUNT, kShapes>(rc.bvh, rc.bvh.instances, nRays, &rc.counts[Q_CURSOR_CLOSEST], load, commitInst, &locNodes, &locTris, &locRays);
     else
-        TraversePersistent<false, COUNT>(rc.bvh, nRays, &rc.counts[Q_CURSOR_CLOSEST], load, commit, &locNodes, &locTris, &locRays);
+        TraversePersistent<false, COUNT, kShapes>(rc.bvh, nRays, &rc.counts[Q_CURSOR_CLOSEST], load, commit, &locNodes, &locTris, &locRays);
     if (COUNT) {
         atomicAdd(&rc.stats[3], (unsigned long long)locNodes);
         atomicAdd(&rc.stats[4], (unsigned long long)locTris);
@@ -218,9 +230,9 @@ __global__ void __launch_bounds__(128, BPT_TRACE_CTAS) k_trace_shadow(RenderCtx 
         }
     };
     if (INST)
-        TraversePersistentInst<true, COUNT>(rc.bvh, rc.bvh.instances, nRays, &rc.counts[Q_CURSOR_SHADOW], load, commit, &locNodes, &locTris, &locRays);
+        TraversePersistentInst<true, COUNT, kShapes>(rc.bvh, rc.bvh.instances, nRays, &rc.counts[Q_CURSOR_SHADOW], load, commit, &locNodes, &locTris, &locRays);
     else
-        TraversePersistent<true, COUNT>(rc.bvh, nRays, &rc.counts[Q_CURSOR_SHADOW], load, commit, &locNodes, &locTris, &locRays);
+        TraversePersistent<true, COUNT, kShapes>(rc.bvh, nRays, &rc.counts[Q_CURSOR_SHADOW], load, commit, &locNodes, &locTris, &locRays);
     if (COUNT) {
         atomicAdd(&rc.stats[6], (unsigned long long)locNodes);
         atomicAdd(&rc.stats[7], (unsigned long long)locTris);
@@ -237,7 +249,7 @@ __global__ void __launch_bounds__(128) k_handle_emissive(RenderCtx rc) {
         float4 h = ps.hit[slot];
         int tri = __float_as_int(h.x);
         TriData td = LoadTriangle(rc.sv, tri);
-        SurfaceIntr isect = HitInteraction(rc.sv, td, h.y, h.z, h.w);
+        SurfaceIntr isect = HitInteraction<kShapes>(rc.sv, td, h.y, h.z, h.w);
         const DeviceMesh &mesh = rc.sv.meshes[td.mesh];
         int lightIndex = mesh.areaLightBase + td.triIndex;
         const DeviceLight &light = rc.sv.lights[lightIndex];
@@ -256,7 +268,7 @@ __global__ void __launch_bounds__(128) k_handle_emissive(RenderCtx rc) {
             L += beta * Le / r_u.Average();
         else {
             LightSampleContext prev = LoadCtx(ps, slot);
-            float p_l = LightSamplerPMF(rc.sv, prev, lightIndex) * AreaLightPDF_Li(rc.sv, light, prev, rd);
+            float p_l = LightSamplerPMF(rc.sv, prev, lightIndex) * AreaLightPDF_Li<kShapes>(rc.sv, light, prev, rd);
             Spec r_l = ld4(&ps.r_l[slot]);
             r_l *= p_l;
             L += beta * Le / (r_u + r_l).Average();
@@ -453,7 +465,7 @@ __global__ void __launch_bounds__(128) k_medium_scatter(RenderCtx rc, int nextQ)
         if (lightIndex >= 0) {
             const DeviceLight &light = rc.sv.lights[lightIndex];
             LightLiSample ls;
-            if (light.type == LIGHT_DIFFUSE_AREA) ls = AreaLightSampleLi(rc.sv, light, ctx, uLight, wl);
+            if (light.type == LIGHT_DIFFUSE_AREA) ls = AreaLightSampleLi<kShapes>(rc.sv, light, ctx, uLight, wl);
             else if (IsDeltaLight(light.type)) ls = DeltaLightSampleLi(rc.sv.specPool, light, ctx.p(), wl);
             else ls = InfiniteLightSampleLi(rc.sv, light, ctx, uLight, wl);
             if (ls.valid && ls.L.IsNonZero() && ls.pdf != 0) {
@@ -510,7 +522,7 @@ __global__ void __launch_bounds__(128, BPT_MEDIUM_CTAS) k_trace_shadow_tr(Render
         while (d != Vec3(0, 0, 0)) {
             HitRec rec;
             unsigned nn = 0, nt = 0;
-            TraceRay<false, false>(rc.bvh, o, d, 1 - kShadowEpsilon, &rec, &nn, &nt);
+            TraceRay<false, false, kShapes>(rc.bvh, o, d, 1 - kShadowEpsilon, &rec, &nn, &nt);
             int tri = -1; unsigned cls = 0;
             if (rec.tri >= 0) {
                 const float4 *tp = rc.bvh.tris + (size_t)rec.tri * 3;
@@ -544,7 +556,7 @@ __global__ void __launch_bounds__(128, BPT_MEDIUM_CTAS) k_trace_shadow_tr(Render
             if (rec.tri < 0) break;
             // lightRay = si->intr.SpawnRayTo(ls->pLight)
             TriData td = LoadTriangle(rc.sv, tri);
-            SurfaceIntr isect = HitInteraction(rc.sv, td, rec.b0, rec.b1, rec.b2);
+            SurfaceIntr isect = HitInteraction<kShapes>(rc.sv, td, rec.b0, rec.b1, rec.b2);
             Pt3 pf = OffsetRayOrigin(isect.pi, isect.n, pLight.p() - isect.pi.p());
             Pt3 pt = OffsetRayOrigin(pLight, nLight, pf - pLight.p());
             o = pf; d = pt - pf;
@@ -731,8 +743,8 @@ __global__ void __launch_bounds__(128) k_trace_raw(BVHView bvh, const float4 *ra
         hits[i] = make_float4(__int_as_float(orig), rec.b0, rec.b1, rec.b2);
         if (tOut) tOut[i] = rec.tri >= 0 ? rec.t : BPT_INFINITY;
     };
-    if (bvh.instances) TraversePersistentInst<ANY, COUNT>(bvh, bvh.instances, n, cursor, load, commitInst, &locNodes, &locTris, &locRays);
-    else TraversePersistent<ANY, COUNT>(bvh, n, cursor, load, commit, &locNodes, &locTris, &locRays);
+    if (bvh.instances) TraversePersistentInst<ANY, COUNT, kShapes>(bvh, bvh.instances, n, cursor, load, commitInst, &locNodes, &locTris, &locRays);
+    else TraversePersistent<ANY, COUNT, kShapes>(bvh, n, cursor, load, commit, &locNodes, &locTris, &locRays);
     if (COUNT && stats) { atomicAdd(&stats[3], (unsigned long long)locNodes); atomicAdd(&stats[4], (unsigned long long)locTris); }
 }
 
@@ -859,14 +871,14 @@ void LaunchHandleEmissive(const RenderCtx &rc, int sms, cudaStream_t st) { k_han
 void LaunchHandleEscaped(const RenderCtx &rc, int sms, cudaStream_t st) { k_handle_escaped<<<GridFor(sms, 4), 128, 0, st>>>(rc); }
 void LaunchShade(const RenderCtx &rc, int materialTag, int nextQ, int sms, cudaStream_t st) {
     switch (materialTag) {
-    case MAT_DIFFUSE: k_shade<DiffuseMaterialEval, false><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
-    case MAT_CONDUCTOR: k_shade<ConductorMaterialEval, false><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
-    case MAT_DIELECTRIC: k_shade<DielectricMaterialEval, false><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
-    case MAT_COATED_CONDUCTOR: k_shade<CoatedConductorMaterialEval, false><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
-    case MAT_COATED_DIFFUSE: k_shade<CoatedDiffuseMaterialEval, false><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
-    case MAT_DIFFUSE_TRANSMISSION: k_shade<DiffuseTransmissionMaterialEval, false><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
-    case MAT_THIN_DIELECTRIC: k_shade<ThinDielectricMaterialEval, false><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
-    case MAT_INTERFACE: k_shade<InterfaceMaterialEval, false><<<GridFor(sms, 4), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_DIFFUSE: k_shade<DiffuseMaterialEval, false, kShapes><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_CONDUCTOR: k_shade<ConductorMaterialEval, false, kShapes><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_DIELECTRIC: k_shade<DielectricMaterialEval, false, kShapes><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_COATED_CONDUCTOR: k_shade<CoatedConductorMaterialEval, false, kShapes><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_COATED_DIFFUSE: k_shade<CoatedDiffuseMaterialEval, false, kShapes><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_DIFFUSE_TRANSMISSION: k_shade<DiffuseTransmissionMaterialEval, false, kShapes><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_THIN_DIELECTRIC: k_shade<ThinDielectricMaterialEval, false, kShapes><<<GridFor(sms, 2 * BPT_SHADE_CTAS), 128, 0, st>>>(rc, nextQ); break;
+    case MAT_INTERFACE: k_shade<InterfaceMaterialEval, false, kShapes><<<GridFor(sms, 4), 128, 0, st>>>(rc, nextQ); break;
     default: break;
     }
 }
@@ -896,4 +908,7 @@ void LaunchProbeTri(const float *rays, const float *tris, int n, float *out, cud
     k_probe_tri<<<(n + 127) / 128, 128, 0, st>>>(rays, tris, n, out);
 }
 
+#if BPT_WITH_SHAPES
+}  // namespace tu_shapes
+#endif
 }  // namespace bpt

@@ -28,7 +28,7 @@ class BptStats(C.Structure):
 
 EXPORTS = """bpt_create bpt_destroy bpt_last_error bpt_scene_begin bpt_scene_set_camera bpt_scene_set_film
 bpt_scene_set_filter bpt_scene_set_sampler bpt_scene_set_integrator bpt_scene_set_materials bpt_scene_set_area_lights
-bpt_scene_add_mesh bpt_scene_add_quadric bpt_scene_add_instance bpt_scene_add_light bpt_scene_add_medium bpt_scene_set_camera_medium
+bpt_scene_add_mesh bpt_scene_add_quadric bpt_scene_add_bilinear_mesh bpt_scene_add_instance bpt_scene_add_light bpt_scene_add_medium bpt_scene_set_camera_medium
 bpt_scene_commit bpt_load_pbrt bpt_load_pbrt_ex bpt_frontend_error bpt_render bpt_render_bands bpt_film_resolve_gbuffer bpt_film_clear bpt_stats_reset bpt_film_read bpt_film_write
 bpt_film_copy_to_device bpt_film_copy_from_device bpt_film_resolve bpt_film_dims bpt_get_stats bpt_trace_closest
 bpt_trace_any bpt_trace_closest_device bpt_probe_sampler bpt_probe_intersect_triangle bpt_render_stream bpt_render_bands_stream

@@ -160,6 +160,77 @@ def cornell_quadrics(outdir, which="spheres", res=(64, 64), spp=16, maxdepth=5):
     return path
 
 
+def write_ply_faces(path, P, faces, N=None, UV=None):
+    """binary_little_endian PLY whose faces are triangles and quads mixed (lists of 3 or 4 vertex indices); optional normals and uv."""
+    P = np.asarray(P, dtype="<f4").reshape(-1, 3)
+    cols = [P]
+    hdr = "ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n" % len(P)
+    if N is not None:
+        hdr += "property float nx\nproperty float ny\nproperty float nz\n"; cols.append(np.asarray(N, dtype="<f4").reshape(-1, 3))
+    if UV is not None:
+        hdr += "property float u\nproperty float v\n"; cols.append(np.asarray(UV, dtype="<f4").reshape(-1, 2))
+    hdr += "element face %d\nproperty list uchar int vertex_indices\nend_header\n" % len(faces)
+    with open(path, "wb") as f:
+        f.write(hdr.encode())
+        f.write(np.hstack(cols).astype("<f4").tobytes())
+        for face in faces:
+            f.write(bytes([len(face)]) + np.asarray(face, dtype="<i4").tobytes())
+
+
+BILINEAR_SETS = {
+    # BilinearPatch (shapes.h:1350-1545) in the Cornell box: (text appended, keep the triangle quad light)
+    "patches": ((
+        # the ceiling light as a rectangular patch: spherical-rectangle sampling (shapes.cpp:1262-1300)
+        'AttributeBegin\n  AreaLightSource "diffuse" "rgb L" [17 12 4]\n  Material "diffuse" "rgb reflectance" [0 0 0]\n'
+        '  Shape "bilinearmesh" "point3 P" [-0.25 1.98 -0.25  -0.25 1.98 0.25  0.25 1.98 -0.25  0.25 1.98 0.25]\nAttributeEnd\n'
+        # a twisted emissive patch (area sampling with the bilinear warp), two-sided
+        'AttributeBegin\n  AreaLightSource "diffuse" "rgb L" [2 3 5] "bool twosided" true\n'
+        '  Shape "bilinearmesh" "point3 P" [-0.9 0.1 -0.8  -0.5 0.15 -0.9  -0.95 0.7 -0.7  -0.55 0.6 -0.4]\nAttributeEnd\n'
+        # a saddle with uv coordinates and vertex normals, under a mirroring transform
+        'AttributeBegin\n  Translate 0.35 0.3 0.1\n  Rotate 25 0 1 0\n  Scale -1 1 1\n  Material "coateddiffuse" "rgb reflectance" [0.6 0.3 0.2] "float roughness" 0.1\n'
+        '  Shape "bilinearmesh" "integer indices" [0 1 3 4  1 2 4 5] "point3 P" [-0.4 0 -0.3  0 0.25 -0.3  0.4 0 -0.3  -0.4 0.3 0.3  0 0 0.3  0.4 0.35 0.3]\n'
+        '    "point2 uv" [0 0  0.5 0  1 0.1  0 1  0.5 0.9  1 1] "normal N" [0.2 1 0.1  0 1 0.3  -0.2 1 0.1  0.1 1 -0.2  0 1 -0.1  -0.3 1 0]\nAttributeEnd\n'
+        # a patch collapsed to a triangle and a glass sheet
+        'AttributeBegin\n  Material "dielectric" "float eta" 1.5\n  ReverseOrientation\n'
+        '  Shape "bilinearmesh" "point3 P" [-0.6 0.05 0.5  -0.1 0.05 0.6  -0.6 0.9 0.4  -0.1 0.9 0.6]\nAttributeEnd\n'
+        'AttributeBegin\n  Material "conductor" "float roughness" 0.2\n  Shape "bilinearmesh" "point3 P" [0.5 1.2 -0.6  0.9 1.2 -0.6  0.7 1.7 -0.7  0.9 1.2 -0.6]\nAttributeEnd\n'), False),
+    "ply": ((
+        'AttributeBegin\n  Translate -0.35 0.45 -0.1\n  Rotate 30 1 1 0\n  Material "diffuse" "rgb reflectance" [0.3 0.5 0.7]\n  Shape "plymesh" "string filename" "quads.ply"\nAttributeEnd\n'
+        'AttributeBegin\n  Material "conductor" "float roughness" 0.1\n  ObjectBegin "q"\n    Shape "plymesh" "string filename" "quads.ply"\n  ObjectEnd\nAttributeEnd\n'
+        'AttributeBegin\n  Translate 0.45 0.4 0.2\n  Rotate -50 0 1 0.2\n  Scale 0.8 1.1 0.8\n  ObjectInstance "q"\nAttributeEnd\n'), True),
+}
+
+
+def cornell_bilinear(outdir, which="patches", res=(64, 64), spp=16, maxdepth=5):
+    """Cornell box with BILINEAR_SETS[which]: bilinear patches as surfaces and as area lights (rectangles sampled as spherical
+    rectangles, other patches by area), with uv / N, collapsed to triangles, and the quad faces of a PLY file (a box whose sides are
+    quads and whose caps are triangle fans: triangle mesh + bilinear patch mesh over the same vertices), top-level and instanced."""
+    path = cornell(outdir, res=res, spp=spp, maxdepth=maxdepth)
+    tail, keep_quad = BILINEAR_SETS[which]
+    s = open(path).read()
+    if which == "ply":
+        # an open prism: 8 ring vertices bottom / top + 2 cap centres; sides = quads, caps = triangles; smooth-ish normals, uv
+        k = 8
+        ang = np.arange(k) * 2 * np.pi / k
+        ring = np.stack([0.25 * np.cos(ang), 0.25 * np.sin(ang)], 1)
+        P = [[x, -0.3, z] for x, z in ring] + [[1.3 * x, 0.3, 1.3 * z] for x, z in ring] + [[0, -0.3, 0], [0, 0.3, 0]]
+        N = [[x, -0.1, z] for x, z in ring] + [[x, 0.2, z] for x, z in ring] + [[0, -1, 0], [0, 1, 0]]
+        UV = [[i / k, 0] for i in range(k)] + [[i / k, 1] for i in range(k)] + [[0.5, 0], [0.5, 1]]
+        faces = []
+        for i in range(k):
+            j = (i + 1) % k
+            faces.append([i, j, k + j, k + i])
+            faces.append([2 * k, j, i])
+            faces.append([2 * k + 1, k + i, k + j])
+        write_ply_faces(os.path.join(outdir, "quads.ply"), P, faces, N=N, UV=UV)
+    if not keep_quad:
+        a = s.index("AttributeBegin\n  AreaLightSource"); b = s.index("AttributeEnd\n", a) + len("AttributeEnd\n")
+        s = s[:a] + s[b:]
+    s += tail
+    open(path, "w").write(s)
+    return path
+
+
 def write_png(path, img):
     """8-bit PNG (grey HxW, grey+alpha HxWx2, RGB HxWx3 or RGBA HxWx4), filter type 0 rows, zlib level 6."""
     import struct, zlib

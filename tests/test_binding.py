@@ -85,6 +85,8 @@ def _scenes():
         cases["lights_" + ls] = (lambda d, ls=ls: scenes.cornell_lights(d, ls, area=(ls == "all"), res=(32, 32), spp=1))
     for qs in sorted(scenes.QUADRIC_SETS):   # Shape "sphere" / "disk" / "cylinder": parameters, defaults, transforms, area lights, instances, media
         cases["quadrics_" + qs] = (lambda d, qs=qs: scenes.cornell_quadrics(d, qs, res=(32, 32), spp=1))
+    for bs in sorted(scenes.BILINEAR_SETS):   # Shape "bilinearmesh" and the quad faces of PLY files
+        cases["bilinear_" + bs] = (lambda d, bs=bs: scenes.cornell_bilinear(d, bs, res=(32, 32), spp=1))
     for parts in ("t", "s", "r", "ts", "tr", "rs", "trs"):   # every combination of translate / rotate / scale in the instance transform
         cases["instances_" + parts] = (lambda d, parts=parts: scenes.instanced(d, n_inst=40, subdiv=1, res=(32, 32), spp=1, material="diffuse", parts=parts))
     return cases
@@ -111,7 +113,7 @@ def test_front_end_and_reference_parser_binding_issue_identical_abi_calls(record
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["cornell", "mixed_envmap", "instanced_coated", "smoke_grid", "gbuffer_world", "lights_all", "textures_bump", "quadrics_instanced", "quadrics_lights"])
+@pytest.mark.parametrize("name", ["cornell", "mixed_envmap", "instanced_coated", "smoke_grid", "gbuffer_world", "lights_all", "textures_bump", "quadrics_instanced", "quadrics_lights", "bilinear_ply"])
 def test_binding_and_front_end_render_identical_images(tmp_path, name):
     from pbrt_v4_b200 import engine as E, imageio
     path = _scenes()[name](str(tmp_path))

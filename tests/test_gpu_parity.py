@@ -517,6 +517,24 @@ def test_spheres_disks_and_cylinders_match_the_live_reference(E, tmp_path, which
     assert nd == 0, (which, nd, rmse.tolist(), float(np.abs(img - ref).max()))
 
 
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/bin/pbrt not on this box")
+@pytest.mark.parametrize("which", ["patches", "ply"])
+def test_bilinear_patches_match_the_live_reference(E, tmp_path, which):
+    """f3: BilinearPatch (shapes.h:1279-1545, shapes.cpp:1038-1357) as custom-primitive leaves: IntersectBilinearPatch, the interaction
+    with (s,t) re-parameterisation and interpolated shading normals (RotateFromTo), rectangular patches as area lights sampled as
+    spherical rectangles, twisted patches sampled by area with the bilinear warp, their NormalBounds in the light BVH, patches
+    collapsed to triangles, mirroring transforms / ReverseOrientation; the quad faces of a PLY file (triangle mesh + patch mesh over
+    the same vertices, util/mesh.cpp:296-306), top-level and inside an object instance.  Whole renders, bit-identical."""
+    from pbrt_v4_b200 import scenes, imageio
+    path = scenes.cornell_bilinear(str(tmp_path), which, res=(64, 64), spp=16)
+    subprocess.check_call([REF_EXE, "--quiet", "--seed", "0", "--outfile", str(tmp_path / "ref.pfm"), path])
+    ref = imageio.read_pfm(str(tmp_path / "ref.pfm"))
+    img = _render(E, path, 16)
+    assert ref.max() > 0
+    nd, rmse = _compare(img, ref)
+    assert nd == 0, (which, nd, rmse.tolist(), float(np.abs(img - ref).max()))
+
+
 def test_raw_rays_against_quadrics_match_the_host_restatement(E, tmp_path):
     """The traversal's quadric leaves against a brute-force loop over the same shapes on the host is covered by the renders above;
     here: closest-hit t of raw rays is finite exactly where any-hit reports occlusion, on a scene with all three quadrics."""

@@ -11,7 +11,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("tool", ["bxdf_host_check", "envmap_host_check", "media_host_check", "nee_host_check", "camera_host_check", "triintr_host_check", "material_host_check", "texture_host_check", "sampler_host_check", "rgbmedium_host_check", "quadric_host_check"])
+@pytest.mark.parametrize("tool", ["bxdf_host_check", "envmap_host_check", "media_host_check", "nee_host_check", "camera_host_check", "triintr_host_check", "material_host_check", "texture_host_check", "sampler_host_check", "rgbmedium_host_check", "quadric_host_check", "bilinear_host_check"])
 def test_host_restatement_matches_reference_golden(tool, tmp_path):
     exe = str(tmp_path / tool)
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-mfma", "-std=c++17", "-I/usr/local/cuda/include",

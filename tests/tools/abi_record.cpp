@@ -25,7 +25,7 @@ using namespace bpt;
 
 namespace {
 struct Spec { bpt_spectrum s; std::vector<float> samples; };
-struct Mesh { bpt_mesh m; std::vector<float> P, N, UV; std::vector<int> idx; bool isQuadric = false; bpt_quadric q; };
+struct Mesh { bpt_mesh m; std::vector<float> P, N, UV; std::vector<int> idx; bool isQuadric = false; bpt_quadric q; bool isBilinear = false; };
 struct Light { bpt_light l; std::vector<float> img; Spec L; };
 struct Medium { bpt_medium m; std::vector<float> density, leScale; Spec sa, ss, Le; uint64_t rgbHash[3]; };
 struct Material { bpt_material m; Spec sp[8]; };
@@ -176,6 +176,14 @@ int bpt_scene_add_mesh(bpt_engine *e, const bpt_mesh *m) {
     o.idx.assign(m->indices, m->indices + 3 * (size_t)m->n_triangles);
     return BPT_OK;
 }
+int bpt_scene_add_bilinear_mesh(bpt_engine *e, const bpt_mesh *m) {
+    e->meshes.emplace_back(); Mesh &o = e->meshes.back(); o.m = *m; o.isBilinear = true;
+    o.P.assign(m->P, m->P + 3 * (size_t)m->n_vertices);
+    if (m->N) o.N.assign(m->N, m->N + 3 * (size_t)m->n_vertices);
+    if (m->UV) o.UV.assign(m->UV, m->UV + 2 * (size_t)m->n_vertices);
+    o.idx.assign(m->indices, m->indices + 4 * (size_t)m->n_triangles);
+    return BPT_OK;
+}
 int bpt_scene_add_quadric(bpt_engine *e, const bpt_quadric *q) {
     e->meshes.emplace_back(); Mesh &o = e->meshes.back(); std::memset(&o.m, 0, sizeof(o.m)); o.isQuadric = true; o.q = *q;
     o.m.world_from_object = q->world_from_object; o.m.object_from_world = q->object_from_world; o.m.reverse_orientation = q->reverse_orientation;
@@ -251,7 +259,7 @@ int bpt_scene_commit(bpt_engine *e) {
     auto meshStr = [&](const Mesh &ms) {
         const bpt_mesh &m = ms.m;
         Xform rfo = ResolveRenderFromObject(e->space, cs, m.world_from_object, m.object_from_world);
-        std::string s = "mesh nv=" + std::to_string(m.n_vertices) + " nt=" + std::to_string(m.n_triangles);
+        std::string s = std::string(ms.isBilinear ? "bilinearmesh" : "mesh") + " nv=" + std::to_string(m.n_vertices) + " nt=" + std::to_string(m.n_triangles);
         char b[200];
         if (ms.isQuadric)
             s = "quadric type=" + std::to_string(ms.q.type) + " radius=" + F(ms.q.radius) + " zmin=" + F(ms.q.zmin) + " zmax=" + F(ms.q.zmax) + " phimax=" + F(ms.q.phimax) +

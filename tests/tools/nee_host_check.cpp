@@ -75,7 +75,7 @@ int main() {
         if (li < 0) continue;
         if (!eq(pmf, o[1]) || !eq(LightSamplerPMF(sv, ctx, li), o[2])) { if (badPmf++ < 3) printf("query %d: pmf %g / %g vs %g / %g\n", q, pmf, LightSamplerPMF(sv, ctx, li), o[1], o[2]); }
         if (!eq(LightSamplerPMF(sv, ctx, (int)a[13]), o[3])) ++badOther;
-        LightLiSample ls = AreaLightSampleLi(sv, lights[li], ctx, Vec2(a[7], a[8]), wl);
+        LightLiSample ls = AreaLightSampleLi<false>(sv, lights[li], ctx, Vec2(a[7], a[8]), wl);
         bool refValid = o[4] == 1;
         if (ls.valid != refValid) { if (badLi++ < 3) printf("query %d: SampleLi valid %d vs %d\n", q, (int)ls.valid, (int)refValid); continue; }
         if (!refValid) continue;
@@ -84,7 +84,7 @@ int main() {
         bool ok = eq(ls.L[0], o[5]) && eq(ls.L[1], o[6]) && eq(ls.L[3], o[7]) && eq(ls.wi.x, o[8]) && eq(ls.wi.y, o[9]) && eq(ls.wi.z, o[10]) && eq(ls.pdf, o[11]) &&
                   eq(pl.x, o[12]) && eq(pl.y, o[13]) && eq(pl.z, o[14]) && eq(ls.nLight.x, o[15]) && eq(ls.nLight.y, o[16]) && eq(ls.nLight.z, o[17]);
         if (!ok) { if (badLi++ < 3) printf("query %d: SampleLi L %g wi %g %g %g pdf %g p %g %g %g  vs  L %g wi %g %g %g pdf %g p %g %g %g\n", q, ls.L[0], ls.wi.x, ls.wi.y, ls.wi.z, ls.pdf, pl.x, pl.y, pl.z, o[5], o[8], o[9], o[10], o[11], o[12], o[13], o[14]); }
-        float pdfLi = AreaLightPDF_Li(sv, lights[li], ctx, ls.wi);
+        float pdfLi = AreaLightPDF_Li<false>(sv, lights[li], ctx, ls.wi);
         if (!eq(pdfLi, o[18])) { if (badPdf++ < 3) printf("query %d: PDF_Li %g vs %g\n", q, pdfLi, o[18]); }
     }
     printf("light BVH: %zu nodes for %d lights\n", lb.nodes.size(), nL);
