@@ -136,7 +136,13 @@ typedef struct {
     int tex1, tex2, tex3;
     float value_f;                /* BPT_TEXTURE_CONSTANT, float */
     bpt_spectrum value_s;         /* BPT_TEXTURE_CONSTANT, spectrum ("value") */
+    /* "mapping" of imagemap / checkerboard textures (TextureMapping2D::Create, textures.cpp:49-73): uv (su sv du dv above), or spherical /
+     * cylindrical / planar (textures.h:108-215), which look the shading point up through the inverse of the CTM at the Texture directive */
+    int mapping;                  /* BPT_TEXMAP_* */
+    bpt_mat4 world_from_texture, texture_from_world;   /* read like a mesh's matrices (bpt_scene_set_transform_space) */
+    float v1[3], v2[3];           /* planar: "v1" (1 0 0), "v2" (0 1 0); its "udelta" / "vdelta" are du / dv */
 } bpt_texture;
+enum { BPT_TEXMAP_UV = 0, BPT_TEXMAP_SPHERICAL = 1, BPT_TEXMAP_CYLINDRICAL = 2, BPT_TEXMAP_PLANAR = 3 };
 enum { BPT_TEXTURE_IMAGEMAP = 0, BPT_TEXTURE_NORMALMAP = 1, BPT_TEXTURE_CONSTANT = 2, BPT_TEXTURE_SCALE = 3, BPT_TEXTURE_MIX = 4,
        BPT_TEXTURE_CHECKERBOARD = 5 /* two-dimensional (textures.cpp:183-207): tex1, tex2 and the uv mapping su sv du dv */ };
 

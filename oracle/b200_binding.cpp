@@ -81,7 +81,7 @@ static bpt_mat4 ToB(const SquareMatrix<4> &m) { bpt_mat4 r; for (int i = 0; i < 
 // ---- the builder: BasicSceneBuilder plus a record of what BasicScene does not keep
 struct LightRecord { std::string type; ParameterDictionary params; Transform renderFromLight; };
 struct MediumRecord { std::string name; ParameterDictionary params; Transform renderFromMedium; };
-struct TextureRecord { std::string name, type, texname; ParameterDictionary params; FileLoc loc; };
+struct TextureRecord { std::string name, type, texname; ParameterDictionary params; FileLoc loc; pbrt::Transform renderFromTexture; };
 
 class B200SceneBuilder : public BasicSceneBuilder {
   public:
@@ -104,7 +104,7 @@ class B200SceneBuilder : public BasicSceneBuilder {
     void Texture(const std::string &name, const std::string &type, const std::string &texname, ParsedParameterVector params, FileLoc loc) override {
         // BasicScene hands image textures to loading jobs and keeps no entity for them (scene.cpp:912-1010): record the directive
         ParsedParameterVector copy = params;
-        textures.push_back(TextureRecord{NormalizeUTF8(name), type, texname, ParameterDictionary(std::move(copy), graphicsState.textureAttributes, graphicsState.colorSpace), loc});
+        textures.push_back(TextureRecord{NormalizeUTF8(name), type, texname, ParameterDictionary(std::move(copy), graphicsState.textureAttributes, graphicsState.colorSpace), loc, RenderFromObject(0)});
         BasicSceneBuilder::Texture(name, type, texname, std::move(params), loc);
     }
     class Transform cameraFromWorld;
@@ -354,6 +354,22 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
     TexIds tx;
     std::vector<bpt_texture> texs;
     std::vector<std::unique_ptr<std::vector<uint8_t>>> texelStore;
+    // TextureMapping2D::Create (textures.cpp:49-73)
+    auto SetMapping = [&](const TextureRecord &tr, bpt_texture *t) {
+        const ParameterDictionary &d = tr.params;
+        std::string type = d.GetOneString("mapping", "uv");
+        t->su = d.GetOneFloat("uscale", 1.f); t->sv = d.GetOneFloat("vscale", 1.f); t->du = d.GetOneFloat("udelta", 0.f); t->dv = d.GetOneFloat("vdelta", 0.f);
+        t->v1[0] = 1; t->v2[1] = 1;
+        if (type == "uv") { t->mapping = BPT_TEXMAP_UV; return; }
+        if (type == "spherical") t->mapping = BPT_TEXMAP_SPHERICAL;
+        else if (type == "cylindrical") t->mapping = BPT_TEXMAP_CYLINDRICAL;
+        else if (type == "planar") {
+            t->mapping = BPT_TEXMAP_PLANAR;
+            Vector3f v1 = d.GetOneVector3f("v1", Vector3f(1, 0, 0)), v2 = d.GetOneVector3f("v2", Vector3f(0, 1, 0));
+            for (int k = 0; k < 3; ++k) { t->v1[k] = v1[k]; t->v2[k] = v2[k]; }
+        } else ErrorExit(&tr.loc, "2D texture mapping \"%s\" unknown", type);
+        t->world_from_texture = ToB(tr.renderFromTexture.GetMatrix()); t->texture_from_world = ToB(tr.renderFromTexture.GetInverseMatrix());
+    };
     for (const TextureRecord &tr : builder.textures) {
         const ParameterDictionary &d = tr.params;
         const bool spec = tr.type == "spectrum";
@@ -388,11 +404,11 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
             bpt_texture t; std::memset(&t, 0, sizeof(t));
             t.is_spectrum = spec;
             if (tr.texname == "checkerboard") {
-                if (d.GetOneInt("dimension", 2) != 2 || d.GetOneString("mapping", "uv") != "uv") ErrorExit(&tr.loc, "only the two-dimensional checkerboard with \"uv\" mapping is implemented by the engine");
+                if (d.GetOneInt("dimension", 2) != 2) ErrorExit(&tr.loc, "only the two-dimensional checkerboard is implemented by the engine");
                 t.kind = BPT_TEXTURE_CHECKERBOARD;
+                SetMapping(tr, &t);
                 t.tex1 = spec ? spectrumChild("tex1", 1.f) : floatChild("tex1", 1.f);
                 t.tex2 = spec ? spectrumChild("tex2", 0.f) : floatChild("tex2", 0.f);
-                t.su = d.GetOneFloat("uscale", 1.f); t.sv = d.GetOneFloat("vscale", 1.f); t.du = d.GetOneFloat("udelta", 0.f); t.dv = d.GetOneFloat("vdelta", 0.f);
             } else
             if (tr.texname == "constant") {
                 t.kind = BPT_TEXTURE_CONSTANT;
@@ -413,9 +429,8 @@ void RenderB200(BasicScene &scene, B200SceneBuilder &builder, Api &api) {
             continue;
         }
         if (tr.texname != "imagemap") ErrorExit(&tr.loc, "texture class \"%s\" is not implemented by the engine (imagemap, constant, scale, mix, checkerboard)", tr.texname);
-        if (d.GetOneString("mapping", "uv") != "uv") ErrorExit(&tr.loc, "only the \"uv\" texture mapping is implemented by the engine");
         bpt_texture t; std::memset(&t, 0, sizeof(t));
-        t.su = d.GetOneFloat("uscale", 1.f); t.sv = d.GetOneFloat("vscale", 1.f); t.du = d.GetOneFloat("udelta", 0.f); t.dv = d.GetOneFloat("vdelta", 0.f);
+        SetMapping(tr, &t);
         t.max_anisotropy = d.GetOneFloat("maxanisotropy", 8.f);
         pstd::optional<FilterFunction> ff = ParseFilter(d.GetOneString("filter", "bilinear"));
         if (!ff) ErrorExit(&tr.loc, "filter function unknown");

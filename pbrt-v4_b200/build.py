@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200pt.so")
-SOURCES = ["engine.cu", "wavefront.cu", "wavefront_shapes.cu", "shade_tex.cu", "shade_tex_layered.cu", "bvh_build.cu", "pbrt_frontend.cpp"]
+SOURCES = ["engine.cu", "wavefront.cu", "wavefront_shapes.cu", "shade_tex.cu", "shade_tex_part1.cu", "shade_tex_part2.cu", "shade_tex_part3.cu", "bvh_build.cu", "pbrt_frontend.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17", "-DBPT_FRONTEND_IN_LIBRARY=1",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=default", "-diag-suppress", "20096"]

@@ -690,6 +690,14 @@ extern "C" int bpt_scene_set_camera_medium(bpt_engine *e, int medium) { if (!e) 
 // ------------------------------------------------------------------------------------------- commit
 static Mat4 ToMat4(const M4 &a) { Mat4 r; std::memcpy(r.m, a.m, sizeof(r.m)); return r; }
 
+// TextureMapping2D::Create (textures.cpp:49-73) for the mappings that look at the shading point: textureFromRender = Inverse(renderFromTexture)
+static void SetTextureMapping(DeviceTexture *d, const bpt_texture &b, int space, const CameraSpaces &spaces) {
+    d->mapping = b.mapping;
+    if (b.mapping == BPT_TEXMAP_UV) return;
+    Xform renderFromTexture = ResolveRenderFromObject(space, spaces, b.world_from_texture, b.texture_from_world);
+    d->textureFromRender = ToMat4(renderFromTexture.mInv);
+    d->vs = Vec3(b.v1[0], b.v1[1], b.v1[2]); d->vt = Vec3(b.v2[0], b.v2[1], b.v2[2]);
+}
 extern "C" int bpt_scene_commit(bpt_engine *e) {
     const bool timing = std::getenv("BPT_TIMING") != nullptr;
     auto tc0 = std::chrono::steady_clock::now();
@@ -1716,6 +1724,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
                     std::memset(&d, 0, sizeof(d));
                     d.kind = TEXKIND_CHECKERBOARD; d.child0 = t1; d.child1 = t2; d.child2 = -1;
                     d.su = tb.su; d.sv = tb.sv; d.du = tb.du; d.dv = tb.dv;
+                    SetTextureMapping(&d, tb, space, spaces);
                     depth[i] = 1 + std::max(depth[t1], depth[t2]);
                 } else if (tb.kind == BPT_TEXTURE_MIX) {
                     int t1 = tb.tex1 - 1, t2 = tb.tex2 - 1, am = tb.tex3 - 1;
@@ -1767,6 +1776,7 @@ extern "C" int bpt_scene_commit(bpt_engine *e) {
             d.firstLevel = (int)nLevels; d.nLevels = (int)pyramids[i].size(); d.nc = im.nc;
             d.wrap = b.wrap; d.filter = b.filter; d.maxAnisotropy = b.max_anisotropy;
             d.su = b.su; d.sv = b.sv; d.du = b.du; d.dv = b.dv; d.scale = b.scale; d.invert = b.invert;
+            SetTextureMapping(&d, b, space, spaces);
             d.kind = TEXKIND_IMAGEMAP; d.child0 = d.child1 = d.child2 = -1; d.cval = 0; std::memset(&d.sval, 0, sizeof(d.sval));
             for (const HostMIPLevel &lv : pyramids[i]) nTexels += lv.texels.size();
             nLevels += pyramids[i].size();

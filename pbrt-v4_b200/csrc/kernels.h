@@ -33,10 +33,16 @@ BPT_WAVEFRONT_LAUNCHERS
 void UploadSobolTableTex(const uint32_t *t);
 void UploadSamplerConstantsTex(const SamplerParams &sp, cudaStream_t st);
 void LaunchShadeTex(const RenderCtx &rc, int materialTag, int nextQ, int sms, cudaStream_t st);
-// shade_tex_layered.cu (reached through the three functions above)
-void UploadSobolTableTexLayered(const uint32_t *t);
-void UploadSamplerConstantsTexLayered(const SamplerParams &sp, cudaStream_t st);
-void LaunchShadeTexLayered(const RenderCtx &rc, int materialTag, int nextQ, int sms, cudaStream_t st);
+// shade_tex_part1 / 2 / 3.cu (reached through the three functions above)
+void UploadSobolTableTexPart1(const uint32_t *t);
+void UploadSamplerConstantsTexPart1(const SamplerParams &sp, cudaStream_t st);
+void LaunchShadeTexPart1(const RenderCtx &rc, int materialTag, int nextQ, int sms, cudaStream_t st);
+void UploadSobolTableTexPart2(const uint32_t *t);
+void UploadSamplerConstantsTexPart2(const SamplerParams &sp, cudaStream_t st);
+void LaunchShadeTexPart2(const RenderCtx &rc, int materialTag, int nextQ, int sms, cudaStream_t st);
+void UploadSobolTableTexPart3(const uint32_t *t);
+void UploadSamplerConstantsTexPart3(const SamplerParams &sp, cudaStream_t st);
+void LaunchShadeTexPart3(const RenderCtx &rc, int materialTag, int nextQ, int sms, cudaStream_t st);
 // wavefront_shapes.cu: the same launchers over the kernels compiled with quadric support
 namespace tu_shapes {
 BPT_WAVEFRONT_LAUNCHERS

@@ -329,10 +329,10 @@ struct Frontend {
             bpt_texture t; std::memset(&t, 0, sizeof(t));
             t.is_spectrum = spec;
             if (a[2] == "checkerboard") {   // Float / SpectrumCheckerboardTexture::Create (textures.cpp:219-280), two-dimensional
-                if (pl.i("dimension", 2) != 2 || pl.s("mapping", "uv") != "uv") { err = "only the two-dimensional checkerboard with \"uv\" mapping is supported"; return false; }
+                if (pl.i("dimension", 2) != 2) { err = "only the two-dimensional checkerboard is supported"; return false; }
                 t.kind = BPT_TEXTURE_CHECKERBOARD;
+                if (!textureMapping(pl, &t)) return false;
                 if (!(spec ? spectrumChild("tex1", 1.f, &t.tex1) : floatChild("tex1", 1.f, &t.tex1)) || !(spec ? spectrumChild("tex2", 0.f, &t.tex2) : floatChild("tex2", 0.f, &t.tex2))) return false;
-                t.su = pl.f("uscale", 1.f); t.sv = pl.f("vscale", 1.f); t.du = pl.f("udelta", 0.f); t.dv = pl.f("vdelta", 0.f);
             } else
             if (a[2] == "constant") {
                 t.kind = BPT_TEXTURE_CONSTANT;
@@ -351,9 +351,8 @@ struct Frontend {
             return true;
         }
         if (a[2] != "imagemap") { err = "texture class \"" + a[2] + "\" is not supported by this front end (imagemap, constant, scale, mix, checkerboard)"; return false; }
-        if (pl.s("mapping", "uv") != "uv") { err = "only the \"uv\" texture mapping is supported"; return false; }
         bpt_texture t; std::memset(&t, 0, sizeof(t));
-        t.su = pl.f("uscale", 1.f); t.sv = pl.f("vscale", 1.f); t.du = pl.f("udelta", 0.f); t.dv = pl.f("vdelta", 0.f);
+        if (!textureMapping(pl, &t)) return false;
         t.max_anisotropy = pl.f("maxanisotropy", 8.f);
         std::string filter = pl.s("filter", "bilinear");
         if (filter == "ewa" || filter == "EWA") t.filter = BPT_TEXFILTER_EWA;
@@ -614,6 +613,23 @@ struct Frontend {
                     else { err = path + ": only triangle and quad faces are supported"; return false; }
                 }
             }
+        return true;
+    }
+
+    // TextureMapping2D::Create (textures.cpp:49-73)
+    bool textureMapping(ParamList &pl, bpt_texture *t) {
+        std::string type = pl.s("mapping", "uv");
+        t->su = pl.f("uscale", 1.f); t->sv = pl.f("vscale", 1.f); t->du = pl.f("udelta", 0.f); t->dv = pl.f("vdelta", 0.f);
+        t->v1[0] = 1; t->v2[1] = 1;
+        if (type == "uv") { t->mapping = BPT_TEXMAP_UV; return true; }
+        if (type == "spherical") t->mapping = BPT_TEXMAP_SPHERICAL;
+        else if (type == "cylindrical") t->mapping = BPT_TEXMAP_CYLINDRICAL;
+        else if (type == "planar") {
+            t->mapping = BPT_TEXMAP_PLANAR;
+            if (Param *v = pl.find("v1")) { if (v->nums.size() != 3) { err = "planar mapping: bad \"v1\""; return false; } for (int k = 0; k < 3; ++k) t->v1[k] = (float)v->nums[k]; }
+            if (Param *v = pl.find("v2")) { if (v->nums.size() != 3) { err = "planar mapping: bad \"v2\""; return false; } for (int k = 0; k < 3; ++k) t->v2[k] = (float)v->nums[k]; }
+        } else { err = "2D texture mapping \"" + type + "\" unknown"; return false; }
+        t->world_from_texture = ToB(gs.ctm.m); t->texture_from_world = ToB(gs.ctm.mInv);
         return true;
     }
 

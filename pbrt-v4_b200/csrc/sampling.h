@@ -236,7 +236,14 @@ static __device__ __noinline__ float2 ZSobolOutlined(uint64_t mortonIndex, int p
 // The table-driven samplers other than ZSobol (PaddedSobol, Sobol, Halton) as one real function as well, so that kernels rendering
 // with the default sampler do not carry three more inlined samplers at each of their seven call sites.  nd = 1 / 2: Get1D / Get2D
 // at `dimension`; nd = 0: GetPixel2D.
-static __device__ __noinline__ float2 QmcOutlined(int px, int py, int sampleIndex, long long sobolIndex, int dimension, int nd);
+static __device__ __noinline__ float2 QmcOutlined(int px, int py, int sampleIndex, int dimension, int nd);
+// The per-pixel-sample set-up of the Sobol' / Halton samplers (SobolIntervalToIndex, the Halton index with its 64-bit divisions) runs
+// INSIDE that function, per call: inlined into StartPixelSample it grew k_shade<Diffuse> from 22.9 k to 32.5 k instructions and the
+// camera kernel from 7.1 k to 13.4 k (r02u: -11 % on the ZSobol benchmark, whose kernels stall on instruction fetch), and carrying the
+// 64-bit index through the kernels cost them registers.  Those samplers pay for it; the default one does not.
+#define BPT_QMC_OUTLINED 1
+#else
+#define BPT_QMC_OUTLINED 0
 #endif
 constexpr int kDimHashTable = 128;   // Hash(dimension, seed) for dimension < kDimHashTable
 
@@ -254,6 +261,32 @@ struct Sampler {
         dimension = dim;
         pixel = -1;
         px = pxIn; py = pyIn; sampleIndex = index;
+#if BPT_QMC_OUTLINED && BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__)
+        // device: every sampler is evaluated as a stateless function of (pixel, sample index, dimension) by one of two real functions
+        // (ZSobolOutlined / QmcOutlined); the RNG of the independent / stratified samplers is re-seeded and advanced to
+        // index * 65536 + dimension there (its position is that at every call, samplers.h:457-460, 586-592), the global index of
+        // Sobol' / Halton recomputed.  Only the default sampler keeps per-path state (Morton index, prefix-table slot).
+        if (sp->type >= 4) dimension = dim > 2 ? dim : 2;
+        if (sp->type == 0) {
+            mortonIndex = (EncodeMorton2((uint32_t)pxIn, (uint32_t)pyIn) << sp->log2SamplesPerPixel) | (uint64_t)index;
+            if (sp->prefix && pxIn >= 0 && pyIn >= 0 && pxIn < sp->prefixW && pyIn < sp->prefixH) pixel = pyIn * sp->prefixW + pxIn;
+        }
+        return;
+#endif
+        if (sp->type >= 4) { StartQmc(pxIn, pyIn, index, dim); return; }
+        if (sp->type == 0) {
+            mortonIndex = (EncodeMorton2((uint32_t)pxIn, (uint32_t)pyIn) << sp->log2SamplesPerPixel) | (uint64_t)index;
+            if (sp->prefix && pxIn >= 0 && pyIn >= 0 && pxIn < sp->prefixW && pyIn < sp->prefixH) pixel = pyIn * sp->prefixW + pxIn;
+        } else if (sp->type != 3) {   // (PaddedSobolSampler::StartPixelSample, samplers.h:389-393, keeps no other state)
+            // IndependentSampler / StratifiedSampler::StartPixelSample (samplers.h:457-460, 586-592): Hash(Point2i p, int seed)
+            uint64_t w[2] = {(uint64_t)(uint32_t)pxIn | ((uint64_t)(uint32_t)pyIn << 32), (uint64_t)(uint32_t)sp->seed};
+            uint64_t h = MurmurHash64A(w, 12, 0);
+            rng.SetSequence(h, MixBits(h));
+            rng.Advance((int64_t)((uint64_t)index * 65536ull + (uint64_t)dim));
+        }
+    }
+    // the samplers with a global sample index (types 4, 5) and pmj02bn (6)
+    BPT_HD void StartQmc(int pxIn, int pyIn, int index, int dim) {
         if (sp->type == 6) { dimension = dim > 2 ? dim : 2; return; }   // PMJ02BNSampler::StartPixelSample (samplers.h:381-385)
         if (sp->type == 5) {   // HaltonSampler::StartPixelSample (samplers.h:53-71)
             int64_t haltonIndex = 0;
@@ -286,16 +319,6 @@ struct Sampler {
             for (int c = 0; b; b >>= 1, ++c) if (b & 1) idx ^= sp->vdcInv[(m - 1) * 52 + c];
             sobolIndex = (int64_t)idx;
             return;
-        }
-        if (sp->type == 0) {
-            mortonIndex = (EncodeMorton2((uint32_t)pxIn, (uint32_t)pyIn) << sp->log2SamplesPerPixel) | (uint64_t)index;
-            if (sp->prefix && pxIn >= 0 && pyIn >= 0 && pxIn < sp->prefixW && pyIn < sp->prefixH) pixel = pyIn * sp->prefixW + pxIn;
-        } else if (sp->type != 3) {   // (PaddedSobolSampler::StartPixelSample, samplers.h:389-393, keeps no other state)
-            // IndependentSampler / StratifiedSampler::StartPixelSample (samplers.h:457-460, 586-592): Hash(Point2i p, int seed)
-            uint64_t w[2] = {(uint64_t)(uint32_t)pxIn | ((uint64_t)(uint32_t)pyIn << 32), (uint64_t)(uint32_t)sp->seed};
-            uint64_t h = MurmurHash64A(w, 12, 0);
-            rng.SetSequence(h, MixBits(h));
-            rng.Advance((int64_t)((uint64_t)index * 65536ull + (uint64_t)dim));
         }
     }
     BPT_HD uint64_t GetSampleIndex() const {
@@ -461,9 +484,10 @@ struct Sampler {
         return {q[0], q[1]};
     }
     BPT_HD Vec2 GetPixel2D() {
-#if BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
-        if (sp->type >= 4) { float2 r = QmcOutlined(px, py, sampleIndex, sobolIndex, dimension, 0); return {r.x, r.y}; }
-#endif
+#if BPT_QMC_OUTLINED && BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__)
+        if (sp->type >= 4) { float2 r = QmcOutlined(px, py, sampleIndex, dimension, 0); return {r.x, r.y}; }
+        return Get2D();
+#else
         if (sp->type == 6) return PmjPixel2D();
         if (sp->type == 5)
             return {RadicalInverse(2, (uint64_t)sobolIndex >> sp->baseExponents[0]), RadicalInverse(3, (uint64_t)(sobolIndex / sp->baseScales[1]))};
@@ -472,17 +496,16 @@ struct Sampler {
         const int pix[2] = {px, py};
         for (int d = 0; d < 2; ++d) u[d] = Clampf(u[d] * sp->scale - pix[d], 0.f, kOneMinusEpsilon);
         return {u[0], u[1]};
+#endif
     }
     BPT_HD float Get1D() {
-#if BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
-        if (sp->type >= 3) {
-            if (sp->type == 4 && dimension >= 1024) dimension = 2;
-            if (sp->type == 5 && dimension >= 1000) dimension = 2;
-            float2 r = QmcOutlined(px, py, sampleIndex, sobolIndex, dimension, 1);
-            ++dimension;
-            return r.x;
-        }
-#endif
+#if BPT_QMC_OUTLINED && BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__)
+        if (sp->type == 4 && dimension >= 1024) dimension = 2;
+        if (sp->type == 5 && dimension >= 1000) dimension = 2;
+        float2 r = sp->type == 0 ? ZSobolOutlined(mortonIndex, pixel, dimension, 1) : QmcOutlined(px, py, sampleIndex, dimension, 1);
+        ++dimension;
+        return r.x;
+#else
         if (sp->type == 6) return Pmj1D();
         if (sp->type == 5) {
             if (dimension >= 1000) dimension = 2;
@@ -494,26 +517,20 @@ struct Sampler {
         }
         if (sp->type == 1) { ++dimension; return rng.UniformFloat(); }
         if (sp->type >= 2) return OtherGet1D();
-#if BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
-        float2 r = ZSobolOutlined(mortonIndex, pixel, dimension, 1);
-        ++dimension;
-        return r.x;
-#endif
         uint64_t sampleIndex = GetSampleIndex();
         ++dimension;
         uint32_t sampleHash = (uint32_t)Hash_i32x2(dimension, sp->seed);
         return SobolSampleRand(sampleIndex, 0, sp->randomize, sampleHash);
+#endif
     }
     BPT_HD Vec2 Get2D() {
-#if BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
-        if (sp->type >= 3) {
-            if (sp->type == 4 && dimension + 1 >= 1024) dimension = 2;
-            if (sp->type == 5 && dimension + 1 >= 1000) dimension = 2;
-            float2 r = QmcOutlined(px, py, sampleIndex, sobolIndex, dimension, 2);
-            dimension += 2;
-            return {r.x, r.y};
-        }
-#endif
+#if BPT_QMC_OUTLINED && BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__)
+        if (sp->type == 4 && dimension + 1 >= 1024) dimension = 2;
+        if (sp->type == 5 && dimension + 1 >= 1000) dimension = 2;
+        float2 r = sp->type == 0 ? ZSobolOutlined(mortonIndex, pixel, dimension, 2) : QmcOutlined(px, py, sampleIndex, dimension, 2);
+        dimension += 2;
+        return {r.x, r.y};
+#else
         if (sp->type == 6) return Pmj2D();
         if (sp->type == 5) {
             if (dimension + 1 >= 1000) dimension = 2;
@@ -529,25 +546,24 @@ struct Sampler {
         }
         if (sp->type == 1) { dimension += 2; float a = rng.UniformFloat(); float b = rng.UniformFloat(); return {a, b}; }
         if (sp->type >= 2) return OtherGet2D();
-#if BPT_OUTLINE_SAMPLER && defined(__CUDA_ARCH__) && defined(BPT_SOBOL_DEVICE_TABLE)
-        float2 r = ZSobolOutlined(mortonIndex, pixel, dimension, 2);
-        dimension += 2;
-        return {r.x, r.y};
-#endif
         uint64_t sampleIndex = GetSampleIndex();
         dimension += 2;
         uint64_t bits = Hash_i32x2(dimension, sp->seed);
         return {SobolSampleRand(sampleIndex, 0, sp->randomize, (uint32_t)bits),
                 SobolSampleRand(sampleIndex, 1, sp->randomize, (uint32_t)(bits >> 32))};
+#endif
     }
 };
 
 #if defined(__CUDACC__) && defined(BPT_SOBOL_DEVICE_TABLE)
 __constant__ SamplerParams c_sampler;
 __constant__ uint64_t c_dimHash[kDimHashTable];
-static __device__ __noinline__ float2 QmcOutlined(int px, int py, int sampleIndex, long long sobolIndex, int dimension, int nd) {
+static __device__ __noinline__ float2 QmcOutlined(int px, int py, int sampleIndex, int dimension, int nd) {
     Sampler s;
-    s.sp = &c_sampler; s.px = px; s.py = py; s.sampleIndex = sampleIndex; s.sobolIndex = sobolIndex; s.dimension = dimension; s.pixel = -1;
+    s.sp = &c_sampler; s.px = px; s.py = py; s.sampleIndex = sampleIndex; s.sobolIndex = 0; s.pixel = -1;
+    if (c_sampler.type >= 4) s.StartQmc(px, py, sampleIndex, 0);   // Sobol' / Halton global index
+    const long long sobolIndex = s.sobolIndex;
+    s.dimension = dimension;
     float2 r = make_float2(0.f, 0.f);
     const int type = c_sampler.type;
     if (nd == 0) {   // GetPixel2D of the Sobol', Halton and pmj02bn samplers (the member functions' own code, not the dispatch above)
@@ -561,8 +577,15 @@ static __device__ __noinline__ float2 QmcOutlined(int px, int py, int sampleInde
         }
         return r;
     }
-    if (type == 3) {
-        if (nd == 1) r.x = s.OtherGet1D(); else { Vec2 u = s.OtherGet2D(); r.x = u.x; r.y = u.y; }
+    if (type <= 3) {
+        if (type != 3) {   // IndependentSampler / StratifiedSampler: the RNG as StartPixelSample + the Get calls so far have left it
+            uint64_t w[2] = {(uint64_t)(uint32_t)px | ((uint64_t)(uint32_t)py << 32), (uint64_t)(uint32_t)c_sampler.seed};
+            uint64_t h = MurmurHash64A(w, 12, 0);
+            s.rng.SetSequence(h, MixBits(h));
+            s.rng.Advance((int64_t)((uint64_t)sampleIndex * 65536ull + (uint64_t)dimension));
+        }
+        if (type == 1) { r.x = s.rng.UniformFloat(); if (nd == 2) r.y = s.rng.UniformFloat(); }
+        else if (nd == 1) r.x = s.OtherGet1D(); else { Vec2 u = s.OtherGet2D(); r.x = u.x; r.y = u.y; }
     } else if (type == 6) {
         if (nd == 1) r.x = s.Pmj1D(); else { Vec2 u = s.Pmj2D(); r.x = u.x; r.y = u.y; }
     } else if (type == 4) {

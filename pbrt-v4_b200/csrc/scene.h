@@ -78,6 +78,9 @@ struct DeviceTexture {
     int child0, child1, child2;
     float cval;                // constant float
     SpectrumRec sval;          // constant spectrum
+    int mapping;               // TextureMapping2D: 0 uv, 1 spherical, 2 cylindrical, 3 planar (textures.h:86-215)
+    Mat4 textureFromRender;    // Inverse(renderFromTexture) for the three point mappings
+    Vec3 vs, vt;               // planar (its ds / dt are du / dv)
 };
 enum { TEXKIND_IMAGEMAP = 0, TEXKIND_CONSTANT = 2, TEXKIND_SCALE = 3, TEXKIND_MIX = 4, TEXKIND_CHECKERBOARD = 5 };
 

@@ -158,6 +158,39 @@ BPT_TEX_FN TexVal<IS_RGB> MipFilter(const DeviceTexture &tex, const DeviceMIPLev
 struct TexCoord2D { Vec2 st; float dsdx, dsdy, dtdx, dtdy; };
 BPT_HD TexCoord2D UVMap(const DeviceTexture &t, const TexEvalCtx &ctx) {
     TexCoord2D c;
+    if (t.mapping != 0) {
+        // SphericalMapping / CylindricalMapping / PlanarMapping::Map (textures.h:117-140, 151-165, 177-189)
+        const float (*m)[4] = t.textureFromRender.m;
+        auto xp = [&](Pt3 p) {   // Transform::operator()(Point3f)
+            float x = m[0][0] * p.x + m[0][1] * p.y + m[0][2] * p.z + m[0][3], y = m[1][0] * p.x + m[1][1] * p.y + m[1][2] * p.z + m[1][3];
+            float z = m[2][0] * p.x + m[2][1] * p.y + m[2][2] * p.z + m[2][3], w = m[3][0] * p.x + m[3][1] * p.y + m[3][2] * p.z + m[3][3];
+            return w == 1 ? Pt3(x, y, z) : Pt3(x, y, z) / w;
+        };
+        auto xv = [&](Vec3 v) { return Vec3(m[0][0] * v.x + m[0][1] * v.y + m[0][2] * v.z, m[1][0] * v.x + m[1][1] * v.y + m[1][2] * v.z, m[2][0] * v.x + m[2][1] * v.y + m[2][2] * v.z); };
+        Pt3 pt = xp(ctx.p);
+        Vec3 dpdx = xv(ctx.dpdx), dpdy = xv(ctx.dpdy);
+        if (t.mapping == 3) {
+            Vec3 vec(pt.x, pt.y, pt.z);
+            c.dsdx = Dot(t.vs, dpdx); c.dsdy = Dot(t.vs, dpdy); c.dtdx = Dot(t.vt, dpdx); c.dtdy = Dot(t.vt, dpdy);
+            c.st = Vec2(t.du + Dot(vec, t.vs), t.dv + Dot(vec, t.vt));
+            return c;
+        }
+        float x2y2 = Sqr(pt.x) + Sqr(pt.y);
+        Vec3 dsdp = Vec3(-pt.y, pt.x, 0) / (2 * kPi * x2y2);
+        Vec3 dtdp(0, 0, 1);
+        if (t.mapping == 1) {
+            float sqrtx2y2 = sqrtf(x2y2);
+            dtdp = 1 / (kPi * (x2y2 + Sqr(pt.z))) * Vec3(pt.x * pt.z / sqrtx2y2, pt.y * pt.z / sqrtx2y2, -sqrtx2y2);
+        }
+        c.dsdx = Dot(dsdp, dpdx); c.dsdy = Dot(dsdp, dpdy); c.dtdx = Dot(dtdp, dpdx); c.dtdy = Dot(dtdp, dpdy);
+        if (t.mapping == 1) {
+            Vec3 vec = Normalize(pt - Pt3(0, 0, 0));
+            float phi = ATan2F(vec.y, vec.x);                       // SphericalPhi
+            c.st = Vec2(SafeACos(vec.z) * kInvPi, ((phi < 0) ? (phi + 2 * kPi) : phi) * kInv2Pi);
+        } else
+            c.st = Vec2((kPi + ATan2F(pt.y, pt.x)) * kInv2Pi, pt.z);
+        return c;
+    }
     c.dsdx = t.su * ctx.dudx; c.dsdy = t.su * ctx.dudy;
     c.dtdx = t.sv * ctx.dvdx; c.dtdy = t.sv * ctx.dvdy;
     c.st = Vec2(t.su * ctx.uv.x + t.du, t.sv * ctx.uv.y + t.dv);

@@ -132,6 +132,16 @@ QUADRIC_SETS = {
         'AttributeBegin\n  MediumInterface "fog" ""\n  Material "dielectric" "float eta" 1.33\n  Translate 0.5 0.35 0.2\n  Rotate -90 1 0 0\n'
         '  Shape "cylinder" "float radius" 0.25 "float zmin" -0.3 "float zmax" 0.3\n  Shape "disk" "float radius" 0.25 "float height" 0.3\n'
         '  ReverseOrientation\n  Shape "disk" "float radius" 0.25 "float height" -0.3\nAttributeEnd\n'), True),
+    "mappings": ('AttributeBegin\n  Translate -0.4 0.45 -0.1\n  Rotate 30 0.3 1 0\n  Texture "sph" "spectrum" "imagemap" "string filename" "albedo.png" "string mapping" "spherical" "string filter" "trilinear"\nAttributeEnd\n'
+                 'AttributeBegin\n  Translate 0.5 0 0.2\n  Rotate -90 1 0 0\n  Scale 1 1 0.5\n  Texture "cyl" "spectrum" "imagemap" "string filename" "colour.pfm" "string mapping" "cylindrical" "string filter" "ewa"\nAttributeEnd\n'
+                 'AttributeBegin\n  Rotate 20 0 1 0\n  Texture "pla" "spectrum" "checkerboard" "string mapping" "planar" "vector3 v1" [3 0 0.5] "vector3 v2" [0 2 1] "float udelta" 0.25 "rgb tex1" [0.7 0.7 0.2] "rgb tex2" [0.1 0.2 0.6]\nAttributeEnd\n', (
+        'AttributeBegin\n  Translate -0.4 0.45 -0.1\n  Rotate 30 0.3 1 0\n  Material "diffuse" "texture reflectance" "sph"\n  Shape "sphere" "float radius" 0.42\nAttributeEnd\n'
+        'AttributeBegin\n  Translate 0.5 0 0.2\n  Rotate -90 1 0 0\n  Material "coateddiffuse" "texture reflectance" "cyl" "float roughness" 0.1\n'
+        '  Shape "cylinder" "float radius" 0.22 "float zmin" 0 "float zmax" 0.9\n  Shape "disk" "float radius" 0.22 "float height" 0.9\nAttributeEnd\n'
+        'Material "diffuse" "texture reflectance" "pla"\n'
+        'Shape "bilinearmesh" "point3 P" [-0.2 0.02 0.3  0.45 0.02 0.5  -0.3 0.02 0.9  0.4 0.3 0.95]\n'
+        'Material "conductor" "float roughness" 0\n'
+        'Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point3 P" [0.95 0.2 -0.6  0.95 0.2 0.5  0.6 1.4 0.5  0.6 1.4 -0.6]\n'), True),
     "textured": ('Texture "alb" "spectrum" "imagemap" "string filename" "albedo.png" "float uscale" 4 "float vscale" 2\n'
                  'Texture "hm" "float" "imagemap" "string filename" "height.pfm" "float scale" 0.03 "float uscale" 3 "float vscale" 3\n', (
         'AttributeBegin\n  Translate -0.4 0.45 -0.1\n  Rotate 30 0.3 1 0\n  Material "diffuse" "texture reflectance" "alb" "texture displacement" "hm"\n  Shape "sphere" "float radius" 0.42\nAttributeEnd\n'
@@ -149,7 +159,7 @@ def cornell_quadrics(outdir, which="spheres", res=(64, 64), spp=16, maxdepth=5):
     path = cornell(outdir, res=res, spp=spp, maxdepth=maxdepth)
     head, tail, keep_quad = QUADRIC_SETS[which]
     s = open(path).read()
-    if which == "textured":
+    if which in ("textured", "mappings"):
         texture_images(outdir)
     if not keep_quad:
         a = s.index("AttributeBegin\n  AreaLightSource"); b = s.index("AttributeEnd\n", a) + len("AttributeEnd\n")

@@ -29,7 +29,7 @@ struct Mesh { bpt_mesh m; std::vector<float> P, N, UV; std::vector<int> idx; boo
 struct Light { bpt_light l; std::vector<float> img; Spec L; };
 struct Medium { bpt_medium m; std::vector<float> density, leScale; Spec sa, ss, Le; uint64_t rgbHash[3]; };
 struct Material { bpt_material m; Spec sp[8]; };
-struct Texture { bpt_texture t; uint64_t hash; Spec value; };
+struct Texture { bpt_texture t; uint64_t hash; Spec value; std::string mapStr; };
 struct AreaLight { bpt_area_light a; Spec L; };
 }  // namespace
 
@@ -78,7 +78,7 @@ static std::string Tex(const std::vector<Texture> &tx, const char *what, int id)
     if (t.kind == BPT_TEXTURE_CONSTANT) return std::string(" ") + what + "=const{" + (t.is_spectrum ? S(tx[id - 1].value) : F(t.value_f)) + "}";
     if (t.kind == BPT_TEXTURE_CHECKERBOARD) {
         if (t.tex1 >= id || t.tex2 >= id) return std::string(" ") + what + "=checkerboard{BAD}";
-        return std::string(" ") + what + "=checkerboard{" + (t.is_spectrum ? "spectrum" : "float") + " uv=" + F(t.su) + "," + F(t.sv) + "," + F(t.du) + "," + F(t.dv) + Tex(tx, "tex1", t.tex1) +
+        return std::string(" ") + what + "=checkerboard{" + (t.is_spectrum ? "spectrum" : "float") + " uv=" + F(t.su) + "," + F(t.sv) + "," + F(t.du) + "," + F(t.dv) + tx[id - 1].mapStr + Tex(tx, "tex1", t.tex1) +
                Tex(tx, "tex2", t.tex2) + "}";
     }
     if (t.kind == BPT_TEXTURE_SCALE || t.kind == BPT_TEXTURE_MIX) {
@@ -96,7 +96,7 @@ static std::string Tex(const std::vector<Texture> &tx, const char *what, int id)
     snprintf(b, sizeof(b), " %s=tex{%s %dx%dx%d fmt=%d enc=%d px=%016" PRIx64 " filter=%d aniso=%s wrap=%d scale=%s invert=%d uv=%s,%s,%s,%s}", what, t.is_spectrum ? "spectrum" : "float", t.xres, t.yres, t.n_channels, t.format,
              t.format == BPT_IMAGE_U8 ? t.encoding : 0, tx[id - 1].hash, t.filter, F(t.max_anisotropy).c_str(), t.wrap, F(t.scale).c_str(), t.invert != 0, F(t.su).c_str(), F(t.sv).c_str(),
              F(t.du).c_str(), F(t.dv).c_str());
-    return b;
+    return std::string(b) + tx[id - 1].mapStr;
 }
 static std::string MatBody(const Material &mt);
 static std::string Mat(const Material &mt, const std::vector<Texture> &tx) {
@@ -213,6 +213,13 @@ int bpt_scene_commit(bpt_engine *e) {
     if (!f) { e->err = "cannot open BPT_RECORD_OUT"; return BPT_ERR_IO; }
     CameraSpaces cs;
     if (!e->haveCam || !ResolveCameraSpaces(e->cam, &cs)) { e->err = "no / singular camera"; return BPT_ERR_INVALID; }
+    for (Texture &t : e->textures) {   // texture mappings that look at the shading point: resolved to rendering space like every other transform
+        t.mapStr.clear();
+        if (t.t.mapping == BPT_TEXMAP_UV || (t.t.kind != BPT_TEXTURE_IMAGEMAP && t.t.kind != BPT_TEXTURE_CHECKERBOARD)) continue;
+        Xform rft = ResolveRenderFromObject(e->space, cs, t.t.world_from_texture, t.t.texture_from_world);
+        t.mapStr = " mapping=" + std::to_string(t.t.mapping) + "{" + X(rft) + " v1=" + F(t.t.v1[0]) + "," + F(t.t.v1[1]) + "," + F(t.t.v1[2]) + " v2=" + F(t.t.v2[0]) + "," + F(t.t.v2[1]) + "," +
+                   F(t.t.v2[2]) + "}";
+    }
     const bpt_camera &c = e->cam;
     fprintf(f, "camera type=%d renderFromCamera{%s} worldFromRender{%s} fov=%s lens=%s focal=%s aspect=%s sw=%d:%s,%s,%s,%s shutter=%s,%s medium=%s\n", c.type,
             X(cs.renderFromCamera).c_str(), X(cs.worldFromRender).c_str(), F(c.fov).c_str(), F(c.lens_radius).c_str(), F(c.focal_distance).c_str(),
