@@ -420,7 +420,7 @@ def main():
         # workload): dram read + write per ray there, times the rays of an average launch here
         traffic, traffic_file = None, None
         # newest capture first: (summary file, camera rays of its first-bounce launch = spp of the capture x 1024^2)
-        for fn, ncu_rays in (("r02z_hf1m.summary.txt", 8 * 1048576.0), ("r02a_hf1m.summary.txt", 8 * 1048576.0), ("r01h_closest_shade_camera.summary.txt", 32 * 1048576.0)):
+        for fn, ncu_rays in (("r02v_hf1m.summary.txt", 8 * 1048576.0), ("r02u_hf1m.summary.txt", 8 * 1048576.0), ("r02a_hf1m.summary.txt", 8 * 1048576.0), ("r01h_closest_shade_camera.summary.txt", 32 * 1048576.0)):
             try:
                 txt = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", fn)).read()
                 blk = txt[txt.index("k_trace_closest"):]

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200pt.so")
-SOURCES = ["engine.cu", "wavefront.cu", "wavefront_shapes.cu", "shade_tex.cu", "shade_tex_part1.cu", "shade_tex_part2.cu", "shade_tex_part3.cu", "bvh_build.cu", "pbrt_frontend.cpp"]
+SOURCES = ["shade_tex_part1.cu", "shade_tex_part2.cu", "shade_tex_part3.cu", "shade_tex.cu", "wavefront_shapes.cu", "wavefront.cu", "engine.cu", "bvh_build.cu", "pbrt_frontend.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17", "-DBPT_FRONTEND_IN_LIBRARY=1",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=default", "-diag-suppress", "20096"]
@@ -43,12 +43,22 @@ def build(force=False, verbose=False):
             cmd = [NVCC] + FLAGS + ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             print(" ".join(cmd))
-        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
-    for s, p in procs:
+        procs.append((s, cmd))
+    # at most BPT_BUILD_JOBS compilers at a time (ptxas on the shading kernels takes several GB each; nine at once were OOM-killed)
+    jobs = int(os.environ.get("BPT_BUILD_JOBS", "5"))
+    running, failed = [], None
+    pending = list(procs)
+    while pending or running:
+        while pending and len(running) < jobs:
+            s, cmd = pending.pop(0)
+            running.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        s, p = running.pop(0)
         out, _ = p.communicate()
-        if p.returncode != 0:
+        if p.returncode != 0 and failed is None:
             sys.stderr.write(out.decode())
-            raise RuntimeError(f"nvcc failed on {s}")
+            failed = s
+    if failed:
+        raise RuntimeError(f"nvcc failed on {failed}")
     cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-ldl", "-lz"]
     subprocess.check_call(cmd)
     return OUT

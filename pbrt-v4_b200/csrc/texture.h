@@ -156,10 +156,10 @@ BPT_TEX_FN TexVal<IS_RGB> MipFilter(const DeviceTexture &tex, const DeviceMIPLev
 }
 
 struct TexCoord2D { Vec2 st; float dsdx, dsdy, dtdx, dtdy; };
-BPT_HD TexCoord2D UVMap(const DeviceTexture &t, const TexEvalCtx &ctx) {
+// SphericalMapping / CylindricalMapping / PlanarMapping::Map (textures.h:117-140, 151-165, 177-189).  A real function: inlined at
+// every texture evaluation of the unrolled texture graphs it multiplied the size (and the ptxas time) of the TEX shading kernels.
+static BPT_TEX_FN TexCoord2D PointMap(const DeviceTexture &t, Pt3 p, Vec3 dpdxR, Vec3 dpdyR) {
     TexCoord2D c;
-    if (t.mapping != 0) {
-        // SphericalMapping / CylindricalMapping / PlanarMapping::Map (textures.h:117-140, 151-165, 177-189)
         const float (*m)[4] = t.textureFromRender.m;
         auto xp = [&](Pt3 p) {   // Transform::operator()(Point3f)
             float x = m[0][0] * p.x + m[0][1] * p.y + m[0][2] * p.z + m[0][3], y = m[1][0] * p.x + m[1][1] * p.y + m[1][2] * p.z + m[1][3];
@@ -167,8 +167,8 @@ BPT_HD TexCoord2D UVMap(const DeviceTexture &t, const TexEvalCtx &ctx) {
             return w == 1 ? Pt3(x, y, z) : Pt3(x, y, z) / w;
         };
         auto xv = [&](Vec3 v) { return Vec3(m[0][0] * v.x + m[0][1] * v.y + m[0][2] * v.z, m[1][0] * v.x + m[1][1] * v.y + m[1][2] * v.z, m[2][0] * v.x + m[2][1] * v.y + m[2][2] * v.z); };
-        Pt3 pt = xp(ctx.p);
-        Vec3 dpdx = xv(ctx.dpdx), dpdy = xv(ctx.dpdy);
+        Pt3 pt = xp(p);
+        Vec3 dpdx = xv(dpdxR), dpdy = xv(dpdyR);
         if (t.mapping == 3) {
             Vec3 vec(pt.x, pt.y, pt.z);
             c.dsdx = Dot(t.vs, dpdx); c.dsdy = Dot(t.vs, dpdy); c.dtdx = Dot(t.vt, dpdx); c.dtdy = Dot(t.vt, dpdy);
@@ -190,7 +190,10 @@ BPT_HD TexCoord2D UVMap(const DeviceTexture &t, const TexEvalCtx &ctx) {
         } else
             c.st = Vec2((kPi + ATan2F(pt.y, pt.x)) * kInv2Pi, pt.z);
         return c;
-    }
+}
+BPT_HD TexCoord2D UVMap(const DeviceTexture &t, const TexEvalCtx &ctx) {
+    if (t.mapping != 0) return PointMap(t, ctx.p, ctx.dpdx, ctx.dpdy);
+    TexCoord2D c;
     c.dsdx = t.su * ctx.dudx; c.dsdy = t.su * ctx.dudy;
     c.dtdx = t.sv * ctx.dvdx; c.dtdy = t.sv * ctx.dvdy;
     c.st = Vec2(t.su * ctx.uv.x + t.du, t.sv * ctx.uv.y + t.dv);
